@@ -1,0 +1,41 @@
+"""Runs the restated oracle against the UNMODIFIED reference modules.  Only possible in the
+build container (needs /root/reference); skipped elsewhere — the committed golden fixtures
+(test_oracle_golden.py) carry the same pin to the GPU box."""
+import pytest
+import torch
+
+from oracle import ref_harness as rh
+from oracle import hstu_oracle as orc
+from b200rec import synth
+
+pytestmark = pytest.mark.skipif(not rh.available(), reason="reference tree not mounted")
+
+SMALL = dict(n_layers=2, n_heads=2, item_embedding_size=32, hstu_embedding_size=32,
+             MAX_ITEM_LIST_LENGTH=10, train_batch_size=5, num_negatives=20, item_num=200)
+
+
+@pytest.mark.parametrize("preset,over", [
+    ("A", dict(train_batch_size=16, num_negatives=64, item_num=500)),
+    ("B", SMALL), ("D", SMALL), ("C", SMALL),
+    ("D", dict(SMALL, num_segment_head=2, pred_len=4, eval_pred_len=4)),
+])
+def test_train_step_matches_reference(preset, over):
+    cfg = synth.make_config(preset, **over)
+    dl = synth.make_dataload(cfg)
+    ref = rh.build_reference_model(dict(cfg), cfg["item_num"], dl.category_counts, dl.category_to_int)
+    ref.eval()
+    batch = synth.make_train_batch(cfg, seed=11, zipf=False)
+    out = ref(batch)
+    out["loss"].backward()
+    sd = orc.state_dict_from_module(ref, requires_grad=True)
+    o2 = orc.OracleHSTU(cfg, sd, dl.category_counts, dl.category_to_int).forward(batch)
+    o2["loss"].backward()
+    assert abs(float(out["loss"].detach()) - float(o2["loss"].detach())) < 2e-6 * max(1, abs(float(out["loss"].detach())))
+    for k, p in ref.named_parameters():
+        if p.grad is None:
+            assert sd[k].grad is None, k
+        else:
+            assert torch.allclose(p.grad, sd[k].grad, rtol=1e-4, atol=1e-7), k
+    for k in out:
+        if k != "loss":
+            assert abs(float(out[k]) - float(o2[k])) < 1e-5, k
