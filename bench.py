@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""HSTU multi-head train (+ eval) throughput on synthetic data of BASELINE.json's shapes.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config B] [--impl reference]
+
+Own arm: one process per GPU (torchrun for N > 1).  A step = forward + backward + fused AdamW over
+one synthetic batch of the named config (default B = HSTU-Pixel8M-prior, BASELINE.json configs[1]).
+`value` = samples/s with the batch resident in HBM; `e2e` = the same step driven from pinned HOST
+buffers (H2D of the batch and D2H of the loss inside the timed region).  `roofline` is for the
+dominant kernel (the tcgen05 GEMM): algorithmic FLOPs of every GEMM launch in the timed region /
+their CUDA-event durations.  `cpu_baseline` / `--impl reference`: the reference algorithm on the
+host cores (the unmodified reference when /root/reference is mounted, else the oracle port).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+WORKLOADS = {"A": "HSTU-Pixel8M-base-small (A)", "A2": "HSTU-Pixel8M-base-small 2 attn heads (A2)",
+             "B": "HSTU-Pixel8M-prior (B)", "C": "HSTU-MerRec-prior (C)", "D": "HSTU-EBNerd-prior-mult (D)"}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="B")
+    ap.add_argument("--impl", default="b200rec", choices=["b200rec", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=0, help="override per-GPU batch (0 = config value)")
+    ap.add_argument("--layers", type=int, default=0, help="override n_layers (debug only; marks the line invalid)")
+    ap.add_argument("--cpu-batch", type=int, default=4, help="samples per CPU-baseline step")
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--eval-users", type=int, default=256)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(float(r[0])) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def train_flops_per_sample(cfg, valid_frac=1.0):
+    """SURVEY §8(d) forward FLOPs per sample x3 (dedup counts, all rows valid upper bound)."""
+    D, Lc, P = cfg["hstu_embedding_size"], cfg["MAX_ITEM_LIST_LENGTH"], cfg["pred_len"]
+    NL, S, C = cfg["n_layers"], cfg["num_segment_head"], cfg["num_prior_head"]
+    H = S + C if cfg["head_interaction"] == "additive" else S * C
+    nneg = cfg["num_negatives"]
+    body = NL * (10 * D * D * Lc + 4 * Lc * Lc * D)
+    heads = H * 2 * D * D * Lc * (1 if cfg["medusa_num_layers"] else 0)
+    by_cat = bool(cfg["neg_sample_by_cat"]) and cfg["loss"] == "prior"
+    sets = (C if by_cat else 0) + (1 if (not by_cat or cfg["head_interaction"] == "additive") else 0)
+    q_rows = H * Lc if cfg["loss"] == "prior" else (P // (P // S if cfg["medusa_num_layers"] else P)) * Lc
+    nce_q = 2 * D * nneg * q_rows
+    fix = 2 * D * nneg * (Lc + P) * sets
+    return 3 * (body + heads + nce_q) + fix
+
+
+def make_cfg(args):
+    from b200rec import synth
+    over = {}
+    if args.batch:
+        over["train_batch_size"] = args.batch
+        # keep n negatives per sample as in the named config
+        base = synth.PRESETS[args.config]
+        over["num_negatives"] = base["num_negatives"] // base["train_batch_size"] * args.batch
+    if args.layers:
+        over["n_layers"] = args.layers
+    return synth.make_config(args.config, **over)
+
+
+# ------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_run(cfg, batch_size, steps, warmup=1):
+    """Times the reference algorithm on the host cores (fwd + bwd + dense torch AdamW)."""
+    from b200rec import synth
+    from oracle import ref_harness as rh
+    from oracle import hstu_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_per = cfg["num_negatives"] // cfg["train_batch_size"]
+    c = synth.Config(cfg)
+    c["train_batch_size"] = batch_size
+    c["num_negatives"] = n_per * batch_size
+    dl = synth.make_dataload(c)
+    batch = synth.make_train_batch(c, seed=1)
+    if rh.available():
+        kind = "reference"
+        model = rh.build_reference_model(dict(c), c["item_num"], dl.category_counts, dl.category_to_int)
+        model.eval()  # dropout off, as in the parity runs
+        params = [p for p in model.parameters() if p.requires_grad]
+        step_fn = lambda: model(batch)["loss"]
+    else:
+        kind = "port"
+        from b200rec.hstu import HSTU
+        torch.manual_seed(2020)
+        host = HSTU(c, dl, compute_dtype=torch.float32)          # parameter container only (CPU, no kernels)
+        sd = {k: v.detach().clone().requires_grad_(v.is_floating_point() and "_rel_attn_bias" not in k)
+              for k, v in host.state_dict().items()}
+        oracle = orc.OracleHSTU(c, sd, dl.category_counts, dl.category_to_int)
+        params = [v for v in sd.values() if v.requires_grad]
+        step_fn = lambda: oracle.forward(batch)["loss"]
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.0)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss = step_fn()
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return {"value": batch_size / sec, "unit": "samples/s", "cores": cores, "kind": kind,
+            "sample": f"{steps} steps of batch {batch_size} (config {cfg['name']} at reduced batch, "
+                      f"{n_per} negatives/sample/set, fp32, dense AdamW)", "ms_per_step": sec * 1e3}
+
+
+# ------------------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = make_cfg(args)
+    base = {"metric": "train_samples_per_sec", "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "data": "synthetic", "config": {
+                "workload": f"{WORKLOADS.get(cfg['name'], cfg['name'])}: {cfg['n_layers']} blocks D={cfg['hstu_embedding_size']} "
+                            f"L={cfg['MAX_ITEM_LIST_LENGTH']} P={cfg['pred_len']} heads={cfg['num_segment_head']}+"
+                            f"{cfg['num_prior_head']} {cfg['head_interaction']} negatives={cfg['num_negatives']}/set "
+                            f"items={cfg['item_num']}",
+                "per_gpu_batch": cfg["train_batch_size"], "global_batch": cfg["train_batch_size"] * world,
+                "parallelism": f"dp{world}", "l2": "working set >> 126 MB L2 (activations + 1.8 GB table); no flush"}}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_run(cfg, args.cpu_batch, max(1, args.steps), warmup=max(1, min(args.warmup, 1)))
+        line = dict(base)
+        line.update({"impl": "reference", "value": r["value"], "ms_per_step": r["ms_per_step"], "dtype": "f32",
+                     "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                     "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "gpu_launches": 0})
+        print(json.dumps(line))
+        return
+
+    from b200rec import synth, _lib as L
+    from b200rec.hstu import HSTU
+    from b200rec.optim import FusedAdamW
+    from b200rec import parallel
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    cfg["sparse_embedding_grad"] = True
+    dl = synth.make_dataload(cfg)
+    torch.manual_seed(2020)
+    model = HSTU(cfg, dl, compute_dtype=dtype).to(dev).eval()   # eval(): dropout off
+    opt = FusedAdamW(model, lr=1e-4, weight_decay=0.0)
+    dp = parallel.DataParallel(model, opt) if world > 1 else None
+    item_tags = synth.make_item_tags(cfg, torch.Generator().manual_seed(4242))
+    n_batches = 4
+    host_batches = [tuple(t.pin_memory() for t in synth.make_train_batch(cfg, seed=10 + i, rank=rank, world_size=1,
+                                                                         item_tags=item_tags))
+                    for i in range(n_batches)]
+    dev_batches = [tuple(t.to(dev) for t in b) for b in host_batches]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_batches[0])
+
+    def step(batch):
+        opt.zero_grad()
+        out = model(batch)
+        out["loss"].backward()
+        if dp is not None:
+            dp.sync_gradients()
+        opt.step()
+        return out["loss"]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(dev_batches[i % n_batches])
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    # ---- timed region 1: batch resident in HBM
+    L.gemm_timing = []
+    launches0 = L.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        loss = step(dev_batches[i % n_batches])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = L.launches - launches0
+    gemm_events = L.gemm_timing
+    L.gemm_timing = None
+    # ---- timed region 2: end to end from pinned host buffers
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    f0.record()
+    last = None
+    for i in range(args.steps):
+        b = tuple(t.to(dev, non_blocking=True) for t in host_batches[i % n_batches])
+        last = float(step(b).item())           # D2H read of the step's loss
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    B = cfg["train_batch_size"]
+    value = B * world * args.steps / (ms / 1e3)
+    e2e = B * world * args.steps / (ms_e2e / 1e3)
+    pk, pk_src = peaks()
+    gflops = sum(f for (_, _, f) in gemm_events)
+    gms = sum(s.elapsed_time(e) for (s, e, _) in gemm_events)
+    ach = gflops / (gms / 1e3) / 1e12 if gms > 0 else 0.0
+    peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+    line = dict(base)
+    line.update({
+        "value": value, "ms_per_step": ms / args.steps, "dtype": args.dtype,
+        "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all GEMM launches of the step)",
+                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
+                     "traffic": None, "peak_source": pk_src + ", sustained bf16",
+                     "gemm_ms_per_step": gms / args.steps, "gemm_share_of_step": gms / ms if ms else None,
+                     "gemm_launches_per_step": len(gemm_events) / args.steps},
+        "model_flops_utilisation": train_flops_per_sample(cfg) * value / 1e12 / peak if peak else None,
+        "clocks": sampler.summary() if sampler else None,
+        "loss_last": last,
+    })
+    if args.layers:
+        line["invalid"] = "n_layers overridden (debug run)"
+    if not args.no_eval:
+        try:
+            line["eval"] = eval_bench(cfg, model, item_tags, dev, args.eval_users)
+        except Exception as ex:  # eval is a secondary number; never lose the train line
+            line["eval"] = {"error": repr(ex)[:200]}
+    if not args.no_cpu:
+        r = cpu_reference_run(cfg, args.cpu_batch, args.cpu_steps)
+        line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def eval_bench(cfg, model, item_tags, dev, users):
+    """Secondary metric: eval users/s = predict + masks + cross-head merge + top-200 + hit matrix."""
+    from b200rec import synth
+    from b200rec.evaluator import Collector
+    ev = synth.make_eval_batch(cfg, seed=3, batch_size=users, item_tags=item_tags)
+    C = cfg["eval_num_cats"]
+    tags = item_tags.t().contiguous().to(dev) if cfg["category_by"] == "item" else \
+        torch.ones(C, cfg["item_num"], dtype=torch.bool, device=dev)
+    feat = model.compute_item_all()
+    seq, tt = ev["item_seq"].to(dev), ev["target_tags"].to(dev)
+    hist = (ev["history_index"][0].to(dev), ev["history_index"][1].to(dev))
+    tgt = ev["item_target"].to(dev)
+    coll = Collector(cfg)
+
+    def one():
+        top = model.predict_topk(seq, feat, tags, tt, history_index=hist, K=max(cfg["topk"]))
+        coll.eval_batch_collect(None, ev["positive_u"], tgt, None, topk=top)
+
+    for _ in range(2):
+        one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n = 3
+    for _ in range(n):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    return {"metric": "eval_users_per_sec", "value": users / (ms / 1e3), "unit": "users/s", "users_per_batch": users,
+            "items": cfg["item_num"], "heads": model.medusa_num_heads, "K": max(cfg["topk"]), "ms_per_batch": ms}
+
+
+if __name__ == "__main__":
+    main()

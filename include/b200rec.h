@@ -1,0 +1,237 @@
+/* b200rec.h — C ABI of libb200rec.so: hand-written sm_100a kernels for the HSTU multi-head
+ * train / eval hot path.
+ *
+ * The reference (zhykoties/Multi-Head-Recommendation-with-Human-Priors) has NO native/FFI
+ * interface: its hot path is eager PyTorch inside code/REC/model/IDNet/hstu.py and
+ * code/REC/evaluator/collector.py.  Each entry point below therefore cites the reference
+ * Python op sequence (file:line under code/REC/) it replaces.  The Python host
+ * (b200rec.hstu.HSTU, same constructor / forward / predict / compute_item_all as the
+ * reference class) binds these symbols with ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; b200rec_last_error() gives
+ *     the message of the last failure on the calling thread.
+ *   - all pointers are DEVICE pointers unless the name ends in _host; no function allocates
+ *     or synchronises; work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - dtype codes: B200REC_F32 = 0, B200REC_BF16 = 1.  "act" tensors use the compute dtype of
+ *     the mode (bf16 production / fp32 verification); residual stream, LN statistics, logits,
+ *     losses and parameter gradients are always fp32.
+ *   - jagged layout: only valid tokens are stored, T = number of tokens; tok_b[t] is the
+ *     sequence of token t, tok_pos[t] its absolute position in the padded frame [0, L),
+ *     seq_off[b]..seq_off[b+1] the token range of sequence b (tokens of one sequence are
+ *     contiguous and ordered by position).
+ */
+#ifndef B200REC_H
+#define B200REC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200REC_F32 0
+#define B200REC_BF16 1
+
+const char* b200rec_last_error(void);
+int b200rec_version(void);
+/* 1 when the current device is sm_100 (tcgen05/TMA kernels usable). */
+int b200rec_device_is_sm100(void);
+
+/* ------------------------------------------------------------------ embedding (SURVEY §8 a1,a2)
+ * hstu.py:637,670,752 `self.item_embedding(ids)`; :640-643 position embedding add. */
+/* out[r,:] = table[ids[r],:]          (out dtype f32 or bf16) */
+int b200rec_gather_rows(const float* table, int D, const int64_t* ids, int64_t n_ids,
+                        void* out, int out_dtype, void* stream);
+/* x[t,:] = table[items[tok_b[t]*LP + tok_pos[t]],:] + pos_table[tok_pos[t],:] */
+int b200rec_embed_tokens(const float* table, const float* pos_table, const int64_t* items,
+                         const int32_t* tok_b, const int32_t* tok_pos, int T, int LP, int D,
+                         float* x, void* stream);
+/* hstu.py:670-672 / :605-606: gather + L2 normalise.  out_hat[r] = row/||row|| (act dtype),
+ * inv_norm[r] = 1/||row||.  table==NULL -> rows are read from `rows_in` (fp32 [n,D]) instead. */
+int b200rec_gather_l2norm(const float* table, const float* rows_in, int D, const int64_t* ids,
+                          int64_t n, void* out_hat, int out_dtype, float* inv_norm, void* stream);
+/* backward of x_hat = x/||x||:  dx = (dxh - xh * <xh, dxh>) * inv_norm.   dxh fp32. */
+int b200rec_l2norm_bwd(const void* x_hat, int act_dtype, const float* inv_norm, const float* d_xhat,
+                       int64_t n, int D, float* dx, int accumulate, void* stream);
+
+/* d_pos[pos,:] = sum over sequences (ascending b) of dx0[tok_index[b*LP+pos],:]; pos in [0, L). */
+int b200rec_pos_emb_grad(const float* dx0, const int32_t* tok_index, int B, int LP, int L, int D,
+                         float* d_pos, void* stream);
+/* Decode-head ResBlock backward (llm_heads.py:26-40) on the [T, H, D] head block:
+ * dz = d_hd * silu'(z) (act dtype; skipped when z == NULL), dy[t,:] = sum_h d_hd[t,h,:]. */
+int b200rec_resblock_bwd(const float* d_hd, const void* z, int act_dtype, int64_t T, int H, int D,
+                         void* dz, float* dy, void* stream);
+
+/* Deterministic embedding gradient (replaces autograd's atomic embedding_dense_backward).
+ * ids[n] (i64) name the table row of each of the n gradient rows grad_rows[n,D] (fp32).  Rows are
+ * radix-sorted by id (stable), and each unique id's rows are summed in ascending input position by
+ * one warp-group: bit-reproducible.  id 0 (padding_idx, hstu.py:413) and ids < 0 get no gradient.
+ * Outputs: uniq_ids[<=n], uniq_rows[<=n, D], n_uniq (device int32), row_slot[N] is NOT touched.
+ * workspace: b200rec_scatter_add_workspace_bytes(n). */
+size_t b200rec_scatter_add_workspace_bytes(int64_t n_ids);
+int b200rec_scatter_add_sorted(const int64_t* ids, int64_t n_ids, const float* grad_rows, int D,
+                               int64_t* uniq_ids, float* uniq_rows, int32_t* n_uniq,
+                               void* workspace, size_t workspace_bytes, void* stream);
+/* dense[uniq_ids[i],:] (+)= uniq_rows[i,:] for i < *n_uniq (rows are unique -> deterministic). */
+int b200rec_rows_to_dense(const int64_t* uniq_ids, const float* uniq_rows, const int32_t* n_uniq,
+                          int64_t max_rows, int D, float* dense, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------ norms (a4)
+ * hstu.py:213-219 F.layer_norm(x,[D],eps) without affine. */
+int b200rec_layernorm_fwd(const float* x, int T, int D, float eps, void* y, int y_dtype,
+                          float* mean, float* rstd, void* stream);
+/* dx = LN'(x; dy) (+ residual_grad if not NULL).  dy in act dtype, leading dimension ldy. */
+int b200rec_layernorm_bwd(const void* dy, int dy_dtype, int ldy, const float* x, const float* mean,
+                          const float* rstd, int T, int D, const float* residual_grad, float* dx,
+                          void* stream);
+/* hstu.py:277 o_input = u * LN(attn): oin = u * LN(a).  u has leading dimension ldu (it is a column
+ * slice of the uvqk activation). */
+int b200rec_gate_ln_fwd(const void* u, int ldu, const float* a, int T, int D, float eps, void* oin,
+                        int act_dtype, float* mean, float* rstd, void* stream);
+/* backward: du = d_oin*LN(a) ; da = LN'(a; d_oin*u).  Writes d_pre_u = du * silu'(pre_u) directly
+ * (pre_u = pre-activation slice, ld ldu) into d_pre_u (ld ldu). */
+int b200rec_gate_ln_bwd(const void* d_oin, const void* u, const void* pre_u, int ldu, const float* a,
+                        const float* mean, const float* rstd, int T, int D, void* d_pre_u, float* da,
+                        int act_dtype, void* stream);
+/* y = cast(x) elementwise, n elements (fp32 -> act dtype). */
+int b200rec_cast(const float* x, int64_t n, void* y, int y_dtype, void* stream);
+/* col_sum[j] = sum_i x[i, j]  (deterministic two-stage), x act dtype or fp32, ld = ldx */
+int b200rec_colsum(const void* x, int x_dtype, int ldx, int rows, int cols, float* out,
+                   int accumulate, void* stream);
+
+/* ------------------------------------------------------------------ GEMM (a4,a7,a10,a15)
+ * C[M,N] = epilogue( A[M,K] * B[N,K]^T ).  Replaces torch.matmul / nn.Linear / einsum at
+ * hstu.py:243 (uvqk), :280 (_o), llm_heads.py:40 (ResBlock), hstu.py:611-613 (NCE logits / fix),
+ * :979 (eval scoring) and their autograd backward.
+ * in_dtype BF16 -> tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), TMA-fed, persistent;
+ * in_dtype F32  -> SIMT fp32 verification kernel (same epilogues).
+ * a_major/b_major: 0 = K-major (A[m*lda+k], B[n*ldb+k]); 1 = MN-major (A[k*lda+m], B[k*ldb+n]). */
+enum {
+  B200REC_EPI_STORE = 0,      /* C = alpha*acc                                              */
+  B200REC_EPI_ACCUM = 1,      /* C += alpha*acc (C fp32)                                    */
+  B200REC_EPI_SILU_DUAL = 2,  /* C2 = acc (pre-activation), C = silu(acc)                   */
+  B200REC_EPI_BIAS_RESID = 3, /* C = acc + bias[n] + resid[m, n]                            */
+  B200REC_EPI_RESBLOCK = 4,   /* z = acc + bias[n]; C2 = z; C = resid[m, n % n_split] + silu(z) */
+  B200REC_EPI_GT_BITS = 5     /* C is uint32 [M, N/32]: bit (n%32) of word n/32 = acc > alpha */
+};
+typedef struct {
+  int M, N, K;
+  const void* A; int64_t lda; int a_major;
+  const void* B; int64_t ldb; int b_major;
+  int in_dtype;
+  void* C; int64_t ldc; int c_dtype;
+  void* C2; int64_t ldc2; int c2_dtype;
+  int epilogue;
+  float alpha;
+  const float* alpha_dev; /* optional device scalar: STORE/ACCUM use alpha * (*alpha_dev) */
+  const float* bias;
+  const float* resid; int64_t ldr;
+  /* n_split > 0: RESBLOCK reads resid[m, n % n_split] (one residual row shared by the H head blocks
+   * of a [T, H*D] output).  If additionally c_split_stride > 0, column n is stored at
+   * C + (n / n_split) * c_split_stride + m*ldc + n % n_split (per-head [H, T, D] blocks). */
+  int n_split; int64_t c_split_stride; int64_t c2_split_stride;
+} b200rec_gemm_args;
+int b200rec_gemm(const b200rec_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------ HSTU attention (a3,a5)
+ * hstu.py:137-160: per head, A = silu(q k^T) / n_pad * [key valid & j <= i], out = A v.
+ * q,k,v are column slices of the [T, 4D] activation (leading dimension ld, act dtype), heads are
+ * contiguous dh-wide column groups.  Jagged over seq_off[B+1]; key_valid[t] (u8) masks keys
+ * (hstu.py:1025).  out fp32 [T, D]. */
+int b200rec_hstu_attn_fwd(const void* q, const void* k, const void* v, int ld, int act_dtype,
+                          const int32_t* seq_off, const uint8_t* key_valid, int B, int T,
+                          int n_heads, int dh, float inv_n, int max_len, float* out, void* stream);
+/* backward: recomputes S.  d_out fp32 [T,D].  Writes d_pre_{q,k,v} =
+ * d{q,k,v} * silu'(pre_{q,k,v}) into the [T,4D] pre-activation-gradient buffer (ld, act dtype). */
+int b200rec_hstu_attn_bwd(const void* q, const void* k, const void* v, const void* pre_q,
+                          const void* pre_k, const void* pre_v, int ld, int act_dtype,
+                          const int32_t* seq_off, const uint8_t* key_valid, int B, int T,
+                          int n_heads, int dh, float inv_n, int max_len, const float* d_out,
+                          void* d_pre_q, void* d_pre_k, void* d_pre_v, void* stream);
+
+/* ------------------------------------------------------------------ NCE / sampled softmax (a9-a12)
+ * hstu.py:600-619 nce_loss + :697 cross_entropy + :704-713 per-offset means, restructured:
+ * one query row per (head, token) shared by all offsets p (SURVEY A.4 dedup identity).
+ *
+ * For one (negative set, head): logits[T, n_neg] (fp32) = q_hat @ neg_hat^T already computed by
+ * b200rec_gemm; same_bits[B*LP, n_neg/32] = bits of (t_hat @ neg_hat^T > nce_thres).
+ * Token (t,p) is valid iff tok_ok[(tok_b[t]*LP + tok_pos[t]+1+p)*tok_ok_ld + tok_ok_col] != 0
+ * (caller folds attn-mask & category tag into tok_ok; p_mask selects offsets served by this head).
+ * Outputs per (t,p): loss[t*P+p] (0 if invalid), g0[t*P+p] = coef*(softmax_0 - 1),
+ * dscale[t*P+p] = coef * sum_k softmax-grad_k * z_k, rank0[t*P+p] = #negatives with logit > pos
+ * (or -1), nvalid[t*P+p] = #unmasked logits incl. pos.  If G != NULL also writes
+ * G[t, j] = tau * sum_p coef_p * softmax_p[j] (act dtype), the gradient w.r.t. the cosine logits.
+ * coef[p] (device fp32[P]) = lambda_p * w_c / max(cnt_p, 1)  (hstu.py:708-712, 850-852). */
+int b200rec_nce_loss_fwd(const float* logits, int64_t ld_logits, int n_neg,
+                         const uint32_t* same_bits, const void* q_hat, int64_t ldq,
+                         const void* t_hat, int act_dtype, int D, const int32_t* tok_b,
+                         const int32_t* tok_pos, int T, int LP, int P, uint32_t p_mask,
+                         const uint8_t* tok_ok, int tok_ok_ld, int tok_ok_col, const float* coef,
+                         const float* logit_scale, float* loss, float* g0, float* dscale,
+                         int32_t* rank0, int32_t* nvalid, void* G, int64_t ldg, void* stream);
+/* gscale (nullable device scalar) multiplies the upstream gradient in the two pos_bwd calls. */
+/* coef[p] = lam[p] * w / max(cnt[p], 1)   (hstu.py:708-712, 850-852) */
+int b200rec_nce_coef(const int32_t* cnt, const float* lam, float w, int P, float* coef, void* stream);
+/* cnt[p] = #valid tokens at offset p for this (head / category):  (hstu.py:705-707) */
+int b200rec_nce_count(const int32_t* tok_b, const int32_t* tok_pos, int T, int LP, int P,
+                      const uint8_t* tok_ok, int tok_ok_ld, int tok_ok_col, int32_t* cnt,
+                      void* stream);
+/* positive-logit backward, deterministic:
+ *   d_qhat[t,:]  += tau * sum_p g0[t,p] * t_hat[b, pos+1+p,:]            (query side)
+ *   d_that[r,:]  += tau * sum_p g0[t(b, pos_r-1-p), p] * q_hat[t(...),:] (target side, gather form)
+ * tok_index[b*LP + pos] = t or -1. */
+int b200rec_nce_pos_bwd_q(const float* g0, const void* t_hat, int act_dtype, int D,
+                          const int32_t* tok_b, const int32_t* tok_pos, int T, int LP, int P,
+                          const float* logit_scale, const float* gscale, float* d_qhat, int64_t ldd,
+                          void* stream);
+int b200rec_nce_pos_bwd_t(const float* g0, const void* q_hat, int64_t ldq, int act_dtype, int D,
+                          const int32_t* tok_index, int B, int LP, int P, const float* logit_scale,
+                          const float* gscale, float* d_that, void* stream);
+/* out[0] (+)= scale * sum_i x[i]   deterministic fixed-order tree. */
+int b200rec_reduce_sum(const float* x, int64_t n, float scale, float* out, int accumulate,
+                       void* stream);
+
+/* ------------------------------------------------------------------ eval (a15-a17)
+ * hstu.py:979-999 scores + prior masks, trainer.py:724-726 id-0 / history masks and
+ * collector.py:241-275 cross-head merge, fused via the identity merge == topk(max over heads).
+ * scores[B*H, N] fp32 (row = b*H + h) from b200rec_gemm.  head_cat[h] = category whose item-tag
+ * bit masks head h (-1: none); item_tag_bits[N] u32 (bit c = item has tag c); head_on[B*H] u8
+ * (prior_given_at_test / switch masks); hist_off[B+1], hist_items: per-user history ids.
+ * Tie rule: value desc, item id asc, head asc.
+ * Outputs topk_idx[B,K] i64, topk_val[B,K] f32, topk_head[B,K] i32.
+ * workspace: b200rec_topk_workspace_bytes(B, N). */
+size_t b200rec_topk_workspace_bytes(int B, int64_t N);
+int b200rec_score_mask_topk(const float* scores, int64_t ld_scores, int B, int H, int64_t N, int K,
+                            const int32_t* head_cat, const uint32_t* item_tag_bits,
+                            const uint8_t* head_on, const int32_t* hist_off,
+                            const int64_t* hist_items, int split_mode, int64_t* topk_idx,
+                            float* topk_val, int32_t* topk_head, void* workspace,
+                            size_t workspace_bytes, void* stream);
+/* In-place masks for the reference-compatible predict() that returns [B,H,N] scores
+ * (hstu.py:983-999): rows of switched-off heads and items outside the head's category -> -inf. */
+int b200rec_apply_score_masks(float* scores, int64_t ld_scores, int B, int H, int64_t N,
+                              const int32_t* head_cat, const uint32_t* item_tag_bits,
+                              const uint8_t* head_on, void* stream);
+/* collector.py:300-316: hit[b, k] |= topk_idx[b,k] in positive_i[b, 0:p+1]; pos_len quirk.
+ * out[n_p, B, K+1] int32 for the n_p entries of pred_list (host array). */
+int b200rec_hit_matrix(const int64_t* topk_idx, const int64_t* positive_i, int B, int K, int Pe,
+                       const int32_t* pred_list_host, int n_p, int32_t* out, void* stream);
+
+/* ------------------------------------------------------------------ optimizer (§8 f N1)
+ * torch.optim.AdamW semantics (trainer.py:296-299), fused single pass, fp32 state. */
+int b200rec_adamw(float* p, float* m, float* v, const float* g, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, float grad_scale,
+                  void* stream);
+/* dense-equivalent AdamW over an embedding table whose gradient is given in compact form
+ * (uniq_ids, uniq_rows, n_uniq): rows without gradient use g = 0 (momentum still moves them). */
+int b200rec_adamw_rows(float* p, float* m, float* v, int64_t n_rows, int D, const int64_t* uniq_ids,
+                       const float* uniq_rows, const int32_t* n_uniq, int32_t* row_slot_ws, float lr,
+                       float beta1, float beta2, float eps, float weight_decay, int step,
+                       float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200REC_H */

@@ -1,0 +1,157 @@
+"""ctypes binding of libb200rec.so (the C ABI declared in include/b200rec.h).
+
+There is no CPU fallback: a missing library or a failing kernel raises.  torch is used only to
+own device memory and to name the current CUDA stream.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200rec.so")
+
+F32, BF16 = 0, 1
+EPI_STORE, EPI_ACCUM, EPI_SILU_DUAL, EPI_BIAS_RESID, EPI_RESBLOCK, EPI_GT_BITS = range(6)
+
+_lib = None
+launches = 0  # number of C-ABI kernel entry points invoked (bench.py's gpu_launches claim)
+gemm_timing = None  # bench.py sets this to a list: (start_event, end_event, flops) per GEMM launch
+
+
+class B200RecError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+        ("A", C.c_void_p), ("lda", C.c_int64), ("a_major", C.c_int),
+        ("B", C.c_void_p), ("ldb", C.c_int64), ("b_major", C.c_int),
+        ("in_dtype", C.c_int),
+        ("C", C.c_void_p), ("ldc", C.c_int64), ("c_dtype", C.c_int),
+        ("C2", C.c_void_p), ("ldc2", C.c_int64), ("c2_dtype", C.c_int),
+        ("epilogue", C.c_int),
+        ("alpha", C.c_float),
+        ("alpha_dev", C.c_void_p),
+        ("bias", C.c_void_p),
+        ("resid", C.c_void_p), ("ldr", C.c_int64),
+        ("n_split", C.c_int), ("c_split_stride", C.c_int64), ("c2_split_stride", C.c_int64),
+    ]
+
+
+_P, _I, _L, _F, _Z = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+_SIGS = {
+    "b200rec_version": (C.c_int, []),
+    "b200rec_device_is_sm100": (C.c_int, []),
+    "b200rec_gather_rows": (C.c_int, [_P, _I, _P, _L, _P, _I, _P]),
+    "b200rec_embed_tokens": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "b200rec_gather_l2norm": (C.c_int, [_P, _P, _I, _P, _L, _P, _I, _P, _P]),
+    "b200rec_l2norm_bwd": (C.c_int, [_P, _I, _P, _P, _L, _I, _P, _I, _P]),
+    "b200rec_pos_emb_grad": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    "b200rec_resblock_bwd": (C.c_int, [_P, _P, _I, _L, _I, _I, _P, _P, _P]),
+    "b200rec_scatter_add_workspace_bytes": (_Z, [_L]),
+    "b200rec_scatter_add_sorted": (C.c_int, [_P, _L, _P, _I, _P, _P, _P, _P, _Z, _P]),
+    "b200rec_rows_to_dense": (C.c_int, [_P, _P, _P, _L, _I, _P, _I, _P]),
+    "b200rec_layernorm_fwd": (C.c_int, [_P, _I, _I, _F, _P, _I, _P, _P, _P]),
+    "b200rec_layernorm_bwd": (C.c_int, [_P, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P]),
+    "b200rec_gate_ln_fwd": (C.c_int, [_P, _I, _P, _I, _I, _F, _P, _I, _P, _P, _P]),
+    "b200rec_gate_ln_bwd": (C.c_int, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _I, _P]),
+    "b200rec_cast": (C.c_int, [_P, _L, _P, _I, _P]),
+    "b200rec_colsum": (C.c_int, [_P, _I, _I, _I, _I, _P, _I, _P]),
+    "b200rec_reduce_sum": (C.c_int, [_P, _L, _F, _P, _I, _P]),
+    "b200rec_gemm": (C.c_int, [C.POINTER(GemmArgs), _P]),
+    "b200rec_gemm_force_bn": (None, [_I]),
+    "b200rec_hstu_attn_fwd": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P]),
+    "b200rec_hstu_attn_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P,
+                                        _P, _P, _P, _P]),
+    "b200rec_nce_loss_fwd": (C.c_int, [_P, _L, _I, _P, _P, _L, _P, _I, _I, _P, _P, _I, _I, _I, C.c_uint32,
+                                       _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
+    "b200rec_nce_count": (C.c_int, [_P, _P, _I, _I, _I, _P, _I, _I, _P, _P]),
+    "b200rec_nce_coef": (C.c_int, [_P, _P, _F, _I, _P, _P]),
+    "b200rec_nce_pos_bwd_q": (C.c_int, [_P, _P, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P, _L, _P]),
+    "b200rec_nce_pos_bwd_t": (C.c_int, [_P, _P, _L, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "b200rec_topk_workspace_bytes": (_Z, [_I, _L]),
+    "b200rec_score_mask_topk": (C.c_int, [_P, _L, _I, _I, _L, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
+    "b200rec_apply_score_masks": (C.c_int, [_P, _L, _I, _I, _L, _P, _P, _P, _P]),
+    "b200rec_hit_matrix": (C.c_int, [_P, _P, _I, _I, _I, _P, _I, _P, _P]),
+    "b200rec_adamw": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
+    "b200rec_adamw_rows": (C.c_int, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _F, _F, _F, _F, _F, _I, _F, _P]),
+}
+EXPORTS = ["b200rec_last_error"] + sorted(_SIGS)
+
+
+def lib():
+    """Loads the shared library once; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise B200RecError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(make -C multi-head-recommendation-with-human-priors_b200/csrc). There is no CPU fallback.")
+        l = C.CDLL(LIB_PATH)
+        l.b200rec_last_error.restype = C.c_char_p
+        l.b200rec_last_error.argtypes = []
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def _check(rc, name):
+    if rc != 0:
+        raise B200RecError(f"{name} failed ({rc}): {lib().b200rec_last_error().decode()}")
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dt(t_or_dtype):
+    d = t_or_dtype.dtype if isinstance(t_or_dtype, torch.Tensor) else t_or_dtype
+    if d == torch.float32:
+        return F32
+    if d == torch.bfloat16:
+        return BF16
+    raise B200RecError(f"unsupported dtype {d}")
+
+
+def call(name, *args):
+    global launches
+    launches += 1
+    _check(getattr(lib(), name)(*args), name)
+
+
+def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epilogue=EPI_STORE, alpha=1.0,
+         alpha_dev=None, bias=None, resid=None, ldr=0, C2=None, ldc2=0, n_split=0, c_dtype=None):
+    """C[M,N] = epi(A[M,K] @ B[N,K]^T).  A/B are tensors (or views) whose data_ptr is element (0,0)."""
+    global launches
+    a = GemmArgs()
+    a.M, a.N, a.K = M, N, K
+    a.A, a.lda, a.a_major = A.data_ptr(), lda, a_major
+    a.B, a.ldb, a.b_major = B.data_ptr(), ldb, b_major
+    a.in_dtype = dt(A)
+    if dt(B) != a.in_dtype:
+        raise B200RecError("gemm: A and B dtypes differ")
+    a.C, a.ldc = C_out.data_ptr(), ldc
+    a.c_dtype = F32 if epilogue == EPI_GT_BITS else (dt(C_out) if c_dtype is None else c_dtype)
+    a.C2, a.ldc2, a.c2_dtype = ptr(C2), ldc2, (dt(C2) if C2 is not None else F32)
+    a.epilogue, a.alpha = epilogue, alpha
+    a.alpha_dev = ptr(alpha_dev)
+    a.bias, a.resid, a.ldr = ptr(bias), ptr(resid), ldr
+    a.n_split, a.c_split_stride, a.c2_split_stride = n_split, 0, 0
+    launches += 1
+    if gemm_timing is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _check(lib().b200rec_gemm(C.byref(a), stream()), "b200rec_gemm")
+        e1.record()
+        gemm_timing.append((e0, e1, 2.0 * M * N * K))
+        return
+    _check(lib().b200rec_gemm(C.byref(a), stream()), "b200rec_gemm")

@@ -1,0 +1,48 @@
+// C-ABI plumbing: error strings, device probe, GEMM dispatcher.
+#include <stdarg.h>
+#include <string.h>
+
+#include "gemm_epilogue.cuh"
+
+static thread_local char g_err[512] = "";
+
+void b200rec_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+const char* b200rec_last_error(void) { return g_err; }
+int b200rec_version(void) { return 100; }
+
+int b200rec_device_is_sm100(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10;
+}
+
+int gemm_simt_launch(const b200rec_gemm_args* a, const EpiParams& ep, cudaStream_t st);
+int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep, cudaStream_t st);
+
+int b200rec_gemm(const b200rec_gemm_args* a, void* stream) {
+  B200_CHECK_ARG(a != nullptr, "gemm: null args");
+  B200_CHECK_ARG(a->M >= 0 && a->N >= 0 && a->K > 0, "gemm: bad shape %d %d %d", a->M, a->N, a->K);
+  if (a->M == 0 || a->N == 0) return 0;
+  EpiParams ep;
+  ep.C = a->C; ep.ldc = a->ldc; ep.c_dtype = a->c_dtype;
+  ep.C2 = a->C2; ep.ldc2 = a->ldc2; ep.c2_dtype = a->c2_dtype;
+  ep.mode = a->epilogue; ep.alpha = a->alpha; ep.alpha_dev = a->alpha_dev;
+  ep.bias = a->bias; ep.resid = a->resid; ep.ldr = a->ldr;
+  ep.n_split = a->n_split; ep.c_split_stride = a->c_split_stride; ep.c2_split_stride = a->c2_split_stride;
+  ep.M = a->M; ep.N = a->N;
+  B200_CHECK_ARG(a->C != nullptr, "gemm: null C");
+  if (a->epilogue == B200REC_EPI_SILU_DUAL) B200_CHECK_ARG(a->C2 != nullptr, "gemm: SILU_DUAL needs C2");
+  if (a->epilogue == B200REC_EPI_RESBLOCK) B200_CHECK_ARG(a->resid != nullptr, "gemm: RESBLOCK needs resid");
+  if (a->epilogue == B200REC_EPI_ACCUM) B200_CHECK_ARG(a->c_dtype == B200REC_F32, "gemm: ACCUM needs fp32 C");
+  if (a->in_dtype == B200REC_F32) return gemm_simt_launch(a, ep, (cudaStream_t)stream);
+  if (a->in_dtype == B200REC_BF16) return gemm_tc_launch(a, ep, (cudaStream_t)stream);
+  b200rec_set_error("gemm: bad in_dtype %d", a->in_dtype);
+  return 1;
+}

@@ -1,0 +1,125 @@
+// Shared helpers for libb200rec kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/b200rec.h"
+
+typedef __nv_bfloat16 bf16;
+
+void b200rec_set_error(const char* fmt, ...);
+
+#define B200_CHECK_ARG(cond, ...)         \
+  do {                                    \
+    if (!(cond)) {                        \
+      b200rec_set_error(__VA_ARGS__);     \
+      return 1;                           \
+    }                                     \
+  } while (0)
+
+#define B200_CUDA_OK(expr)                                                             \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      b200rec_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return 2;                                                                        \
+    }                                                                                  \
+  } while (0)
+
+#define B200_LAUNCH_OK() B200_CUDA_OK(cudaGetLastError())
+
+static inline int ceil_div_i(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- dtype helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
+__device__ __forceinline__ float silu_grad_f(float z) {
+  float s = 1.f / (1.f + __expf(-z));
+  return s * (1.f + z * (1.f - s));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum, result broadcast to every thread.  `red` is >= 33 floats of shared memory.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float t = lane < nw ? red[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float t = lane < nw ? red[lane] : -INFINITY;
+    t = warp_max(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+// 16-byte vector access helpers for rows of floats / bf16 (callers guarantee alignment).
+struct alignas(16) f32x4 { float x, y, z, w; };
+struct alignas(8) bf16x4 { bf16 x, y, z, w; };
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+  typedef f32x4 type;
+};
+template <> struct Vec4<bf16> {
+  typedef bf16x4 type;
+};
+
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, float (&o)[4]) {
+  typename Vec4<T>::type v = *reinterpret_cast<const typename Vec4<T>::type*>(p);
+  o[0] = to_f32(v.x); o[1] = to_f32(v.y); o[2] = to_f32(v.z); o[3] = to_f32(v.w);
+}
+template <typename T>
+__device__ __forceinline__ void store4(T* p, const float (&o)[4]) {
+  typename Vec4<T>::type v;
+  v.x = from_f32<T>(o[0]); v.y = from_f32<T>(o[1]); v.z = from_f32<T>(o[2]); v.w = from_f32<T>(o[3]);
+  *reinterpret_cast<typename Vec4<T>::type*>(p) = v;
+}
+
+#define DISPATCH_ACT(dtype, T, ...)                       \
+  do {                                                    \
+    if ((dtype) == B200REC_F32) {                         \
+      typedef float T;                                    \
+      __VA_ARGS__                                         \
+    } else if ((dtype) == B200REC_BF16) {                 \
+      typedef bf16 T;                                     \
+      __VA_ARGS__                                         \
+    } else {                                              \
+      b200rec_set_error("bad dtype %d", (int)(dtype));    \
+      return 1;                                           \
+    }                                                     \
+  } while (0)

@@ -1,0 +1,174 @@
+// Epilogues shared by the tcgen05 GEMM and the fp32 SIMT verification GEMM.
+#pragma once
+#include "common.cuh"
+
+struct EpiParams {
+  void* C; int64_t ldc; int c_dtype;
+  void* C2; int64_t ldc2; int c2_dtype;
+  int mode; float alpha;
+  const float* alpha_dev;  // optional device scalar multiplied into alpha (upstream grad scale)
+  const float* bias;
+  const float* resid; int64_t ldr;
+  int n_split; int64_t c_split_stride, c2_split_stride;
+  int M, N;
+};
+
+__device__ __forceinline__ void epi_store_scalar(void* base, int dtype, int64_t off, float v) {
+  if (dtype == B200REC_F32) ((float*)base)[off] = v;
+  else ((bf16*)base)[off] = __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ int64_t epi_offset(const EpiParams& p, int m, int n, int64_t ld, int64_t split_stride) {
+  if (p.n_split > 0 && split_stride > 0) {
+    int h = n / p.n_split;
+    return (int64_t)h * split_stride + (int64_t)m * ld + (n - h * p.n_split);
+  }
+  return (int64_t)m * ld + n;
+}
+
+// one element (SIMT path).  GT_BITS uses atomicOr: the caller zero-fills C first.
+__device__ __forceinline__ void epi_apply_scalar(const EpiParams& p, int m, int n, float acc) {
+  if (m >= p.M || n >= p.N) return;
+  switch (p.mode) {
+    case B200REC_EPI_STORE:
+      epi_store_scalar(p.C, p.c_dtype, epi_offset(p, m, n, p.ldc, p.c_split_stride), p.alpha * acc);
+      break;
+    case B200REC_EPI_ACCUM: {
+      float* c = (float*)p.C + epi_offset(p, m, n, p.ldc, p.c_split_stride);
+      *c += p.alpha * acc;
+      break;
+    }
+    case B200REC_EPI_SILU_DUAL:
+      epi_store_scalar(p.C2, p.c2_dtype, epi_offset(p, m, n, p.ldc2, p.c2_split_stride), acc);
+      epi_store_scalar(p.C, p.c_dtype, epi_offset(p, m, n, p.ldc, p.c_split_stride), silu_f(acc));
+      break;
+    case B200REC_EPI_BIAS_RESID: {
+      float v = acc + (p.bias ? p.bias[n] : 0.f) + (p.resid ? p.resid[(int64_t)m * p.ldr + n] : 0.f);
+      epi_store_scalar(p.C, p.c_dtype, epi_offset(p, m, n, p.ldc, p.c_split_stride), v);
+      break;
+    }
+    case B200REC_EPI_RESBLOCK: {
+      float z = acc + (p.bias ? p.bias[n] : 0.f);
+      int nr = p.n_split > 0 ? n % p.n_split : n;
+      if (p.C2) epi_store_scalar(p.C2, p.c2_dtype, epi_offset(p, m, n, p.ldc2, p.c2_split_stride), z);
+      epi_store_scalar(p.C, p.c_dtype, epi_offset(p, m, n, p.ldc, p.c_split_stride),
+                       p.resid[(int64_t)m * p.ldr + nr] + silu_f(z));
+      break;
+    }
+    case B200REC_EPI_GT_BITS:
+      if (acc > p.alpha) atomicOr((unsigned int*)p.C + (int64_t)m * p.ldc + (n >> 5), 1u << (n & 31));
+      break;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void store_chunk(T* dst, const float* v, int n_valid);
+template <>
+__device__ __forceinline__ void store_chunk<float>(float* dst, const float* v, int n_valid) {
+  if (n_valid == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      f32x4 q = {v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]};
+      reinterpret_cast<f32x4*>(dst)[i] = q;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < n_valid) dst[i] = v[i];
+  }
+}
+template <>
+__device__ __forceinline__ void store_chunk<bf16>(bf16* dst, const float* v, int n_valid) {
+  if (n_valid == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 q;
+      __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]);
+      __nv_bfloat162 b = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+      __nv_bfloat162 c = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
+      __nv_bfloat162 d = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+      q.x = *reinterpret_cast<uint32_t*>(&a);
+      q.y = *reinterpret_cast<uint32_t*>(&b);
+      q.z = *reinterpret_cast<uint32_t*>(&c);
+      q.w = *reinterpret_cast<uint32_t*>(&d);
+      reinterpret_cast<uint4*>(dst)[i] = q;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < n_valid) dst[i] = __float2bfloat16_rn(v[i]);
+  }
+}
+
+__device__ __forceinline__ void store_chunk_dt(void* base, int dtype, int64_t off, const float* v, int n_valid) {
+  if (dtype == B200REC_F32) store_chunk<float>((float*)base + off, v, n_valid);
+  else store_chunk<bf16>((bf16*)base + off, v, n_valid);
+}
+
+// 32 consecutive columns [n0, n0+32) of row m held by one thread (tcgen05.ld 32x32b layout).
+// n0 is a multiple of 32 and (when n_split > 0) n_split is a multiple of 32, so a chunk never
+// straddles a split boundary.
+__device__ __forceinline__ void epi_apply_chunk32(const EpiParams& p, int m, int n0, float (&acc)[32]) {
+  if (m >= p.M || n0 >= p.N) return;
+  int n_valid = min(32, p.N - n0);
+  switch (p.mode) {
+    case B200REC_EPI_STORE: {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] *= p.alpha;
+      store_chunk_dt(p.C, p.c_dtype, epi_offset(p, m, n0, p.ldc, p.c_split_stride), acc, n_valid);
+      break;
+    }
+    case B200REC_EPI_ACCUM: {
+      float* c = (float*)p.C + epi_offset(p, m, n0, p.ldc, p.c_split_stride);
+      if (n_valid == 32 && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          f32x4 q = reinterpret_cast<f32x4*>(c)[i];
+          q.x += p.alpha * acc[4 * i]; q.y += p.alpha * acc[4 * i + 1];
+          q.z += p.alpha * acc[4 * i + 2]; q.w += p.alpha * acc[4 * i + 3];
+          reinterpret_cast<f32x4*>(c)[i] = q;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < n_valid) c[i] += p.alpha * acc[i];
+      }
+      break;
+    }
+    case B200REC_EPI_SILU_DUAL: {
+      store_chunk_dt(p.C2, p.c2_dtype, epi_offset(p, m, n0, p.ldc2, p.c2_split_stride), acc, n_valid);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = silu_f(acc[i]);
+      store_chunk_dt(p.C, p.c_dtype, epi_offset(p, m, n0, p.ldc, p.c_split_stride), acc, n_valid);
+      break;
+    }
+    case B200REC_EPI_BIAS_RESID: {
+      const float* r = p.resid ? p.resid + (int64_t)m * p.ldr + n0 : nullptr;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < n_valid) acc[i] += (p.bias ? __ldg(p.bias + n0 + i) : 0.f) + (r ? r[i] : 0.f);
+      store_chunk_dt(p.C, p.c_dtype, epi_offset(p, m, n0, p.ldc, p.c_split_stride), acc, n_valid);
+      break;
+    }
+    case B200REC_EPI_RESBLOCK: {
+      int nr0 = p.n_split > 0 ? n0 % p.n_split : n0;
+      const float* r = p.resid + (int64_t)m * p.ldr + nr0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < n_valid) acc[i] += (p.bias ? __ldg(p.bias + n0 + i) : 0.f);
+      if (p.C2) store_chunk_dt(p.C2, p.c2_dtype, epi_offset(p, m, n0, p.ldc2, p.c2_split_stride), acc, n_valid);
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < n_valid) acc[i] = r[i] + silu_f(acc[i]);
+      store_chunk_dt(p.C, p.c_dtype, epi_offset(p, m, n0, p.ldc, p.c_split_stride), acc, n_valid);
+      break;
+    }
+    case B200REC_EPI_GT_BITS: {
+      uint32_t w = 0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) w |= (i < n_valid && acc[i] > p.alpha) ? (1u << i) : 0u;
+      ((uint32_t*)p.C)[(int64_t)m * p.ldc + (n0 >> 5)] = w;
+      break;
+    }
+  }
+}

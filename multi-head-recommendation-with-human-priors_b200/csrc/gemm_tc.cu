@@ -1,0 +1,244 @@
+// Persistent warp-specialised bf16 GEMM on the 5th-gen tensor cores (sm_100a):
+//   TMA (cp.async.bulk.tensor, 128B swizzle) -> smem ring -> tcgen05.mma kind::f16 (1 thread)
+//   -> fp32 accumulators in TMEM (2 stages) -> tcgen05.ld -> fused epilogue -> global.
+// C[M,N] = epi(A[M,K] * B[N,K]^T); each operand may be K-major or MN-major in global memory
+// (MN-major avoids every explicit transpose in the backward pass: dW = X^T dY, dX = dY W).
+// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue (TMEM lane quarters).
+#include <mutex>
+#include <unordered_map>
+
+#include "gemm_epilogue.cuh"
+#include "tc_ptx.cuh"
+
+#define TC_BM 128
+#define TC_BK 64
+#define TC_THREADS 192
+#define TC_TMEM_COLS 512
+#define TC_SMEM_LIMIT (227 * 1024)
+
+struct TcParams {
+  int M, N, K;
+  int BN;          // 128 or 256
+  int stages;
+  int a_mn, b_mn;  // 1 = MN-major operand
+  int num_m, num_n;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const TcParams p, const EpiParams ep_in) {
+  EpiParams ep = ep_in;
+  if (ep.alpha_dev && (ep.mode == B200REC_EPI_STORE || ep.mode == B200REC_EPI_ACCUM)) ep.alpha *= *ep.alpha_dev;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024B alignment
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = TC_BM * 128u;
+  const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
+  // barrier layout: full[stages], empty[stages], tmem_full[2], tmem_empty[2], tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TC_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int num_tiles = p.num_m * p.num_n;
+  const int num_k = (p.K + TC_BK - 1) / TC_BK;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % p.num_m) * TC_BM;
+        const int n0 = (tile / p.num_m) * p.BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+          const uint32_t sb = sa + a_bytes;
+          mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+          const int k0 = kb * TC_BK;
+          if (!p.a_mn) {
+            tma_load_2d(sa, &map_a, full_bar(s), k0, m0);  // box {64 k, 128 m}
+          } else {
+            for (int j = 0; j < TC_BM / 64; ++j)          // boxes {64 m, 64 k}
+              tma_load_2d(sa + j * 8192u, &map_a, full_bar(s), m0 + 64 * j, k0);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sb, &map_b, full_bar(s), k0, n0);  // box {64 k, BN n}
+          } else {
+            for (int j = 0; j < p.BN / 64; ++j)
+              tma_load_2d(sb + j * 8192u, &map_b, full_bar(s), n0 + 64 * j, k0);
+          }
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(TC_BM, p.BN, p.a_mn, p.b_mn);
+      int s = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * (uint32_t)p.BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
+          const uint32_t sb = sa + a_bytes;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // K-major: 16 k-elements = 32 bytes inside the 128B swizzle span; 8-row groups 1024B apart.
+            // MN-major: 16 k-rows = 2 x 1024B atoms; next 64-wide mn block 8192B (64 k-rows x 128B) away.
+            const uint64_t da = p.a_mn ? umma_smem_desc(sa + k * 2048u, 8192u, 1024u)
+                                       : umma_smem_desc(sa + k * 32u, 16u, 1024u);
+            const uint64_t db = p.b_mn ? umma_smem_desc(sb + k * 2048u, 8192u, 1024u)
+                                       : umma_smem_desc(sb + k * 32u, 16u, 1024u);
+            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32)
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % p.num_m) * TC_BM;
+      const int n0 = (tile / p.num_m) * p.BN;
+      mbar_wait(tfull_bar(acc), acc_ph);
+      tc_fence_after();
+      const int m = m0 + quarter * 32 + lane;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * (uint32_t)p.BN;
+      for (int c = 0; c < p.BN / 32; ++c) {
+        float v[32];
+        tmem_ld_32x32(t_row + (uint32_t)c * 32u, v);
+        epi_apply_chunk32(ep, m, n0 + c * 32, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+  });
+  return fn;
+}
+
+// 2D bf16 tensor map: inner (contiguous) extent d0, outer extent d1, row pitch ld elements.
+static int make_map(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t box0,
+                    uint32_t box1) {
+  EncodeTiledFn fn = get_encode_fn();
+  B200_CHECK_ARG(fn != nullptr, "cuTensorMapEncodeTiled not available");
+  cuuint64_t dims[2] = {d0, d1};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): ptr=%p d0=%llu d1=%llu ld=%llu box=%u,%u",
+                 (int)r, ptr, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)ld, box0, box1);
+  return 0;
+}
+
+static int g_num_sms = 0;
+static int g_force_bn = 0;  // test hook
+
+extern "C" void b200rec_gemm_force_bn(int bn) { g_force_bn = bn; }
+
+int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep, cudaStream_t st) {
+  B200_CHECK_ARG(((uintptr_t)a->A & 15) == 0 && ((uintptr_t)a->B & 15) == 0, "gemm: A/B must be 16-byte aligned");
+  B200_CHECK_ARG(a->lda % 8 == 0 && a->ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 (16-byte pitch)");
+  if (g_num_sms == 0) {
+    int dev = 0;
+    B200_CUDA_OK(cudaGetDevice(&dev));
+    B200_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+  }
+  TcParams p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.a_mn = a->a_major; p.b_mn = a->b_major;
+  p.BN = (a->N > 128) ? 256 : 128;
+  // prefer more tiles than SMs: fall back to BN=128 when the 256-wide grid under-fills the GPU
+  if (p.BN == 256 && (int64_t)ceil_div_i(a->M, TC_BM) * ceil_div_i(a->N, 256) < g_num_sms) p.BN = 128;
+  if (g_force_bn == 128 || g_force_bn == 256) p.BN = g_force_bn;
+  if (a->n_split > 0)
+    B200_CHECK_ARG(a->n_split % 32 == 0, "gemm: n_split must be a multiple of 32");
+  const uint32_t stage_bytes = TC_BM * 128u + (uint32_t)p.BN * 128u;
+  p.stages = (TC_SMEM_LIMIT - 1024 - 256) / stage_bytes;
+  if (p.stages > 8) p.stages = 8;
+  p.num_m = ceil_div_i(a->M, TC_BM);
+  p.num_n = ceil_div_i(a->N, p.BN);
+  CUtensorMap ma, mb;
+  if (!p.a_mn) {
+    if (make_map(&ma, a->A, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, 64, TC_BM)) return 1;
+  } else {
+    if (make_map(&ma, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, 64)) return 1;
+  }
+  if (!p.b_mn) {
+    if (make_map(&mb, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, 64, (uint32_t)p.BN)) return 1;
+  } else {
+    if (make_map(&mb, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, 64)) return 1;
+  }
+  int tiles = p.num_m * p.num_n;
+  int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
+  gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep);
+  B200_LAUNCH_OK();
+  return 0;
+}

@@ -1,0 +1,356 @@
+// Sampled-softmax (NCE) loss over deduplicated query rows.
+// One block owns one query row (head, token): its cosine logits against the negative set are read
+// once into shared memory and shared by every prediction offset p that uses this head; the
+// false-negative filter (hstu.py:613-614) comes from a bit matrix built by the GEMM epilogue.
+#include "common.cuh"
+
+#define NCE_THREADS 256
+#define NCE_MAXP 16
+
+struct Stats {
+  float m, s, w;  // max, sum exp(z-m), sum exp(z-m)*z
+  int gt;         // #logits greater than the reference positive logit
+  int cnt;        // #logits counted
+};
+
+__device__ __forceinline__ void stats_merge(Stats& a, const Stats& b) {
+  float m = fmaxf(a.m, b.m);
+  float fa = a.m == -INFINITY ? 0.f : __expf(a.m - m);
+  float fb = b.m == -INFINITY ? 0.f : __expf(b.m - m);
+  a.s = a.s * fa + b.s * fb;
+  a.w = a.w * fa + b.w * fb;
+  a.m = m;
+  a.gt += b.gt;
+  a.cnt += b.cnt;
+}
+
+// deterministic block reduction of Stats (fixed tree), result broadcast
+__device__ Stats block_stats(Stats v, Stats* red) {
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Stats t;
+    t.m = __shfl_xor_sync(0xffffffffu, v.m, o);
+    t.s = __shfl_xor_sync(0xffffffffu, v.s, o);
+    t.w = __shfl_xor_sync(0xffffffffu, v.w, o);
+    t.gt = __shfl_xor_sync(0xffffffffu, v.gt, o);
+    t.cnt = __shfl_xor_sync(0xffffffffu, v.cnt, o);
+    // order the merge by lane so both partners compute the identical value
+    if (lane & o) { Stats u = t; stats_merge(u, v); v = u; } else { stats_merge(v, t); }
+  }
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  Stats r = red[0];
+  for (int i = 1; i < nw; ++i) stats_merge(r, red[i]);
+  return r;
+}
+
+template <typename TA>
+__global__ void __launch_bounds__(NCE_THREADS)
+nce_loss_fwd_kernel(const float* __restrict__ logits, int64_t ld_logits, int n_neg,
+                    const uint32_t* __restrict__ same_bits, const TA* __restrict__ q_hat, int64_t ldq,
+                    const TA* __restrict__ t_hat, int D, const int32_t* __restrict__ tok_b,
+                    const int32_t* __restrict__ tok_pos, int LP, int P, uint32_t p_mask,
+                    const uint8_t* __restrict__ tok_ok, int tok_ok_ld, int tok_ok_col,
+                    const float* __restrict__ coef, const float* __restrict__ logit_scale, float* __restrict__ loss,
+                    float* __restrict__ g0, float* __restrict__ dscale, int32_t* __restrict__ rank0,
+                    int32_t* __restrict__ nvalid, TA* __restrict__ G, int64_t ldg) {
+  extern __shared__ __align__(16) float sm[];
+  float* z = sm;               // [n_neg]  scaled logits tau * cos
+  float* qrow = sm + n_neg;    // [D]
+  __shared__ Stats red_stats[NCE_THREADS / 32];
+  __shared__ float red[40];
+  __shared__ float s_pos[NCE_MAXP], s_lse[NCE_MAXP], s_coef[NCE_MAXP];
+  __shared__ int s_valid[NCE_MAXP], s_masked[NCE_MAXP];
+  __shared__ int s_any;
+
+  const int t = blockIdx.x;
+  const int b = tok_b[t], pos = tok_pos[t];
+  const float tau = __expf(fminf(fmaxf(*logit_scale, 0.f), 4.605170185988092f));  // clamp(0, ln 100)
+  const int n_words = (n_neg + 31) >> 5;
+
+  if (threadIdx.x < NCE_MAXP) {
+    int p = threadIdx.x;
+    int ok = 0;
+    if (p < P && ((p_mask >> p) & 1u)) {
+      int64_t r = (int64_t)b * LP + pos + 1 + p;
+      ok = tok_ok[r * tok_ok_ld + tok_ok_col] != 0;
+    }
+    s_valid[p] = ok;
+    s_masked[p] = 0;
+    s_coef[p] = (p < P) ? coef[p] : 0.f;
+  }
+  if (threadIdx.x == 0) s_any = 0;
+  __syncthreads();
+  if (threadIdx.x < P && s_valid[threadIdx.x]) s_any = 1;
+  __syncthreads();
+  if (!s_any) {  // no prediction offset uses this row
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+      loss[(int64_t)t * P + p] = 0.f;
+      g0[(int64_t)t * P + p] = 0.f;
+      dscale[(int64_t)t * P + p] = 0.f;
+      rank0[(int64_t)t * P + p] = -1;
+      nvalid[(int64_t)t * P + p] = 0;
+    }
+    if (G)
+      for (int j = threadIdx.x; j < n_neg; j += blockDim.x) G[(int64_t)t * ldg + j] = from_f32<TA>(0.f);
+    return;
+  }
+
+  // stage the query row and the scaled logits row
+  for (int d = threadIdx.x; d < D; d += blockDim.x) qrow[d] = to_f32(q_hat[(int64_t)t * ldq + d]);
+  for (int j = threadIdx.x; j < n_neg; j += blockDim.x) z[j] = tau * logits[(int64_t)t * ld_logits + j];
+  __syncthreads();
+
+  // positive logits and "row has filtered negatives" flags
+  for (int p = 0; p < P; ++p) {
+    if (!s_valid[p]) continue;
+    int64_t r = (int64_t)b * LP + pos + 1 + p;
+    float acc = 0.f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) acc += qrow[d] * to_f32(t_hat[r * D + d]);
+    acc = block_sum(acc, red);
+    uint32_t any = 0;
+    for (int w = threadIdx.x; w < n_words; w += blockDim.x) any |= same_bits[r * n_words + w];
+    if (any) atomicOr(&s_masked[p], 1);
+    if (threadIdx.x == 0) s_pos[p] = tau * acc;
+    __syncthreads();
+  }
+
+  // unfiltered row statistics (shared by every offset without filtered negatives)
+  const float pos0 = s_valid[0] ? s_pos[0] : INFINITY;
+  Stats all;
+  all.m = -INFINITY; all.s = 0.f; all.w = 0.f; all.gt = 0; all.cnt = 0;
+  {
+    float m = -INFINITY;
+    for (int j = threadIdx.x; j < n_neg; j += blockDim.x) m = fmaxf(m, z[j]);
+    Stats loc;
+    loc.m = m; loc.s = 0.f; loc.w = 0.f; loc.gt = 0; loc.cnt = 0;
+    for (int j = threadIdx.x; j < n_neg; j += blockDim.x) {
+      float e = __expf(z[j] - m);
+      loc.s += e;
+      loc.w += e * z[j];
+      loc.gt += z[j] > pos0;
+      loc.cnt += 1;
+    }
+    all = block_stats(loc, red_stats);
+  }
+
+  float a_common = 0.f;  // sum over unfiltered offsets of coef_p * exp(m_all - lse_p)
+  for (int p = 0; p < P; ++p) {
+    if (!s_valid[p]) {
+      if (threadIdx.x == 0) {
+        loss[(int64_t)t * P + p] = 0.f;
+        g0[(int64_t)t * P + p] = 0.f;
+        dscale[(int64_t)t * P + p] = 0.f;
+        rank0[(int64_t)t * P + p] = -1;
+        nvalid[(int64_t)t * P + p] = 0;
+      }
+      continue;
+    }
+    Stats st = all;
+    if (s_masked[p]) {  // exact pass over the un-filtered negatives of this target
+      const uint32_t* bits = same_bits + ((int64_t)b * LP + pos + 1 + p) * n_words;
+      float m = -INFINITY;
+      for (int j = threadIdx.x; j < n_neg; j += blockDim.x)
+        if (!((bits[j >> 5] >> (j & 31)) & 1u)) m = fmaxf(m, z[j]);
+      Stats loc;
+      loc.m = m; loc.s = 0.f; loc.w = 0.f; loc.gt = 0; loc.cnt = 0;
+      for (int j = threadIdx.x; j < n_neg; j += blockDim.x)
+        if (!((bits[j >> 5] >> (j & 31)) & 1u)) {
+          float e = __expf(z[j] - m);
+          loc.s += e;
+          loc.w += e * z[j];
+          loc.gt += z[j] > s_pos[p];
+          loc.cnt += 1;
+        }
+      st = block_stats(loc, red_stats);
+    }
+    const float zp = s_pos[p];
+    const float M = fmaxf(st.m, zp);
+    const float en = st.m == -INFINITY ? 0.f : __expf(st.m - M);
+    const float ep = __expf(zp - M);
+    const float denom = st.s * en + ep;
+    const float lse = M + __logf(denom);
+    const float sm0 = ep / denom;
+    const float c = s_coef[p];
+    if (threadIdx.x == 0) {
+      s_lse[p] = lse;
+      loss[(int64_t)t * P + p] = c * (lse - zp);
+      g0[(int64_t)t * P + p] = c * (sm0 - 1.f);
+      // d loss / d logit_scale = sum_k softmax_k z_k - z_0
+      dscale[(int64_t)t * P + p] = c * ((st.w * en + ep * zp) / denom - zp);
+      rank0[(int64_t)t * P + p] = (p == 0 || s_masked[p]) ? st.gt : -1;
+      nvalid[(int64_t)t * P + p] = st.cnt + 1;
+    }
+    if (!s_masked[p]) a_common += c * __expf(all.m - lse);
+  }
+  if (G == nullptr) return;
+  __syncthreads();
+  // gradient w.r.t. the cosine logits:  G[j] = tau * sum_p coef_p * softmax_p[j]
+  for (int j = threadIdx.x; j < n_neg; j += blockDim.x) {
+    float g = a_common * __expf(z[j] - all.m);
+    for (int p = 0; p < P; ++p) {
+      if (s_valid[p] && s_masked[p]) {
+        const uint32_t* bits = same_bits + ((int64_t)b * LP + pos + 1 + p) * n_words;
+        if (!((bits[j >> 5] >> (j & 31)) & 1u)) g += s_coef[p] * __expf(z[j] - s_lse[p]);
+      }
+    }
+    G[(int64_t)t * ldg + j] = from_f32<TA>(tau * g);
+  }
+}
+
+int b200rec_nce_loss_fwd(const float* logits, int64_t ld_logits, int n_neg, const uint32_t* same_bits,
+                         const void* q_hat, int64_t ldq, const void* t_hat, int act_dtype, int D,
+                         const int32_t* tok_b, const int32_t* tok_pos, int T, int LP, int P, uint32_t p_mask,
+                         const uint8_t* tok_ok, int tok_ok_ld, int tok_ok_col, const float* coef,
+                         const float* logit_scale, float* loss, float* g0, float* dscale, int32_t* rank0,
+                         int32_t* nvalid, void* G, int64_t ldg, void* stream) {
+  B200_CHECK_ARG(P >= 1 && P <= NCE_MAXP, "nce_loss_fwd: pred_len %d not in [1,%d]", P, NCE_MAXP);
+  if (T == 0) return 0;
+  size_t smem = (size_t)(n_neg + D) * sizeof(float);
+  B200_CHECK_ARG(smem <= 200 * 1024, "nce_loss_fwd: n_neg=%d too large for the shared-memory row cache", n_neg);
+  DISPATCH_ACT(act_dtype, TA, {
+    B200_CUDA_OK(cudaFuncSetAttribute(nce_loss_fwd_kernel<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    nce_loss_fwd_kernel<TA><<<T, NCE_THREADS, smem, (cudaStream_t)stream>>>(
+        logits, ld_logits, n_neg, same_bits, (const TA*)q_hat, ldq, (const TA*)t_hat, D, tok_b, tok_pos, LP, P,
+        p_mask, tok_ok, tok_ok_ld, tok_ok_col, coef, logit_scale, loss, g0, dscale, rank0, nvalid, (TA*)G, ldg);
+  });
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ counts / coefs
+__global__ void nce_count_kernel(const int32_t* __restrict__ tok_b, const int32_t* __restrict__ tok_pos, int T,
+                                 int LP, int P, const uint8_t* __restrict__ tok_ok, int tok_ok_ld, int tok_ok_col,
+                                 int32_t* __restrict__ cnt) {
+  __shared__ int loc[NCE_MAXP];
+  if (threadIdx.x < NCE_MAXP) loc[threadIdx.x] = 0;
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < T * P) {
+    int t = i / P, p = i - t * P;
+    int64_t r = (int64_t)tok_b[t] * LP + tok_pos[t] + 1 + p;
+    if (tok_ok[r * tok_ok_ld + tok_ok_col]) atomicAdd(&loc[p], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < P && loc[threadIdx.x]) atomicAdd(&cnt[threadIdx.x], loc[threadIdx.x]);
+}
+
+int b200rec_nce_count(const int32_t* tok_b, const int32_t* tok_pos, int T, int LP, int P, const uint8_t* tok_ok,
+                      int tok_ok_ld, int tok_ok_col, int32_t* cnt, void* stream) {
+  B200_CHECK_ARG(P >= 1 && P <= NCE_MAXP, "nce_count: pred_len %d not in [1,%d]", P, NCE_MAXP);
+  B200_CUDA_OK(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * P, (cudaStream_t)stream));
+  if (T == 0) return 0;
+  nce_count_kernel<<<ceil_div_i((int64_t)T * P, 256), 256, 0, (cudaStream_t)stream>>>(tok_b, tok_pos, T, LP, P,
+                                                                                    tok_ok, tok_ok_ld, tok_ok_col,
+                                                                                    cnt);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+__global__ void nce_coef_kernel(const int32_t* __restrict__ cnt, const float* __restrict__ lam, float w, int P,
+                                float* __restrict__ coef) {
+  int p = threadIdx.x;
+  if (p < P) coef[p] = lam[p] * w / fmaxf((float)cnt[p], 1.f);
+}
+
+extern "C" int b200rec_nce_coef(const int32_t* cnt, const float* lam, float w, int P, float* coef, void* stream) {
+  nce_coef_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(cnt, lam, w, P, coef);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ positive-logit backward
+template <typename TA>
+__global__ void __launch_bounds__(256) nce_pos_bwd_q_kernel(const float* __restrict__ g0, const TA* __restrict__ t_hat,
+                                                            int D4, const int32_t* __restrict__ tok_b,
+                                                            const int32_t* __restrict__ tok_pos, int LP, int P,
+                                                            const float* __restrict__ logit_scale,
+                                                            const float* __restrict__ gscale,
+                                                            float* __restrict__ d_qhat, int64_t ldd) {
+  const int t = blockIdx.x;
+  const float tau = __expf(fminf(fmaxf(*logit_scale, 0.f), 4.605170185988092f)) * (gscale ? *gscale : 1.f);
+  const int64_t r0 = (int64_t)tok_b[t] * LP + tok_pos[t] + 1;
+  for (int c = threadIdx.x; c < D4; c += blockDim.x) {
+    float acc[4];
+    load4<float>(d_qhat + (int64_t)t * ldd + c * 4, acc);
+    for (int p = 0; p < P; ++p) {
+      float g = g0[(int64_t)t * P + p];
+      if (g != 0.f) {
+        float v[4];
+        load4<TA>(t_hat + ((r0 + p) * D4 + c) * 4, v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] += tau * g * v[k];
+      }
+    }
+    store4<float>(d_qhat + (int64_t)t * ldd + c * 4, acc);
+  }
+}
+
+int b200rec_nce_pos_bwd_q(const float* g0, const void* t_hat, int act_dtype, int D, const int32_t* tok_b,
+                          const int32_t* tok_pos, int T, int LP, int P, const float* logit_scale,
+                          const float* gscale, float* d_qhat, int64_t ldd, void* stream) {
+  if (T == 0) return 0;
+  B200_CHECK_ARG(D % 4 == 0 && ldd % 4 == 0, "nce_pos_bwd_q: bad D/ldd");
+  DISPATCH_ACT(act_dtype, TA, {
+    nce_pos_bwd_q_kernel<TA><<<T, 256, 0, (cudaStream_t)stream>>>(g0, (const TA*)t_hat, D / 4, tok_b, tok_pos, LP, P,
+                                                                  logit_scale, gscale, d_qhat, ldd);
+  });
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+// gather form: target row r = (b, pos_r) collects from queries at l = pos_r - 1 - p
+template <typename TA>
+__global__ void __launch_bounds__(256) nce_pos_bwd_t_kernel(const float* __restrict__ g0, const TA* __restrict__ q_hat,
+                                                            int64_t ldq, int D4, const int32_t* __restrict__ tok_index,
+                                                            int LP, int P, const float* __restrict__ logit_scale,
+                                                            const float* __restrict__ gscale,
+                                                            float* __restrict__ d_that) {
+  const int64_t r = blockIdx.x;
+  const int b = (int)(r / LP), pos_r = (int)(r - (int64_t)b * LP);
+  const float tau = __expf(fminf(fmaxf(*logit_scale, 0.f), 4.605170185988092f)) * (gscale ? *gscale : 1.f);
+  __shared__ int s_t[NCE_MAXP];
+  __shared__ float s_g[NCE_MAXP];
+  if (threadIdx.x < P) {
+    int p = threadIdx.x;
+    int l = pos_r - 1 - p;
+    int t = l >= 0 ? tok_index[(int64_t)b * LP + l] : -1;
+    float g = t >= 0 ? g0[(int64_t)t * P + p] : 0.f;
+    s_t[p] = g != 0.f ? t : -1;
+    s_g[p] = g;
+  }
+  __syncthreads();
+  bool any = false;
+  for (int p = 0; p < P; ++p) any |= s_t[p] >= 0;
+  if (!any) return;
+  for (int c = threadIdx.x; c < D4; c += blockDim.x) {
+    float acc[4];
+    load4<float>(d_that + (r * D4 + c) * 4, acc);
+    for (int p = 0; p < P; ++p) {
+      if (s_t[p] >= 0) {
+        float v[4];
+        load4<TA>(q_hat + (int64_t)s_t[p] * ldq + c * 4, v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] += tau * s_g[p] * v[k];
+      }
+    }
+    store4<float>(d_that + (r * D4 + c) * 4, acc);
+  }
+}
+
+int b200rec_nce_pos_bwd_t(const float* g0, const void* q_hat, int64_t ldq, int act_dtype, int D,
+                          const int32_t* tok_index, int B, int LP, int P, const float* logit_scale,
+                          const float* gscale, float* d_that, void* stream) {
+  if (B == 0) return 0;
+  B200_CHECK_ARG(D % 4 == 0 && ldq % 4 == 0, "nce_pos_bwd_t: bad D/ldq");
+  B200_CHECK_ARG(P <= NCE_MAXP, "nce_pos_bwd_t: pred_len too large");
+  DISPATCH_ACT(act_dtype, TA, {
+    nce_pos_bwd_t_kernel<TA><<<B * LP, 256, 0, (cudaStream_t)stream>>>(g0, (const TA*)q_hat, ldq, D / 4, tok_index, LP,
+                                                                       P, logit_scale, gscale, d_that);
+  });
+  B200_LAUNCH_OK();
+  return 0;
+}

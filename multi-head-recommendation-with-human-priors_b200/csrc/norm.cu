@@ -1,0 +1,342 @@
+// Row-wise normalisation kernels of the HSTU block: one warp per token row, the row
+// is held in registers between the statistics pass and the write (single HBM read of each input).
+#include "common.cuh"
+
+#define ROWS_PER_BLOCK 8  // 256 threads
+
+template <typename TY, int MAXV>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, int T, int D4, float eps,
+                                                            TY* __restrict__ y, float* __restrict__ mean,
+                                                            float* __restrict__ rstd) {
+  int lane = threadIdx.x & 31;
+  int r = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  if (r >= T) return;
+  float v[MAXV][4];
+  float s = 0.f;
+#pragma unroll
+  for (int u = 0; u < MAXV; ++u) {
+    int c = lane + u * 32;
+    if (c < D4) {
+      load4<float>(x + ((int64_t)r * D4 + c) * 4, v[u]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s += v[u][k];
+    }
+  }
+  float D = (float)(D4 * 4);
+  float mu = warp_sum(s) / D;
+  float ss = 0.f;
+#pragma unroll
+  for (int u = 0; u < MAXV; ++u) {
+    int c = lane + u * 32;
+    if (c < D4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float d = v[u][k] - mu;
+        ss += d * d;
+      }
+    }
+  }
+  float rs = rsqrtf(warp_sum(ss) / D + eps);
+  if (lane == 0) {
+    mean[r] = mu;
+    rstd[r] = rs;
+  }
+#pragma unroll
+  for (int u = 0; u < MAXV; ++u) {
+    int c = lane + u * 32;
+    if (c < D4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[u][k] = (v[u][k] - mu) * rs;
+      store4<TY>(y + ((int64_t)r * D4 + c) * 4, v[u]);
+    }
+  }
+}
+
+int b200rec_layernorm_fwd(const float* x, int T, int D, float eps, void* y, int y_dtype, float* mean, float* rstd,
+                          void* stream) {
+  B200_CHECK_ARG(D % 4 == 0 && D <= 2048, "layernorm_fwd: D=%d must be a multiple of 4 and <= 2048", D);
+  if (T == 0) return 0;
+  int blocks = ceil_div_i(T, ROWS_PER_BLOCK);
+  DISPATCH_ACT(y_dtype, TY, {
+    if (D <= 512)
+      layernorm_fwd_kernel<TY, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, T, D / 4, eps, (TY*)y, mean, rstd);
+    else
+      layernorm_fwd_kernel<TY, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, T, D / 4, eps, (TY*)y, mean, rstd);
+  });
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+template <typename TG, int MAXV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TG* __restrict__ dy, int64_t ldy,
+                                                            const float* __restrict__ x,
+                                                            const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, int T, int D4,
+                                                            const float* __restrict__ resid, float* __restrict__ dx) {
+  int lane = threadIdx.x & 31;
+  int r = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  if (r >= T) return;
+  float mu = mean[r], rs = rstd[r];
+  float xh[MAXV][4], g[MAXV][4];
+  float sg = 0.f, sgx = 0.f;
+#pragma unroll
+  for (int u = 0; u < MAXV; ++u) {
+    int c = lane + u * 32;
+    if (c < D4) {
+      load4<float>(x + ((int64_t)r * D4 + c) * 4, xh[u]);
+      load4<TG>(dy + (int64_t)r * ldy + c * 4, g[u]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        xh[u][k] = (xh[u][k] - mu) * rs;
+        sg += g[u][k];
+        sgx += g[u][k] * xh[u][k];
+      }
+    }
+  }
+  float D = (float)(D4 * 4);
+  sg = warp_sum(sg) / D;
+  sgx = warp_sum(sgx) / D;
+#pragma unroll
+  for (int u = 0; u < MAXV; ++u) {
+    int c = lane + u * 32;
+    if (c < D4) {
+      float o[4];
+      if (resid) load4<float>(resid + ((int64_t)r * D4 + c) * 4, o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float d = rs * (g[u][k] - sg - xh[u][k] * sgx);
+        o[k] = resid ? o[k] + d : d;
+      }
+      store4<float>(dx + ((int64_t)r * D4 + c) * 4, o);
+    }
+  }
+}
+
+int b200rec_layernorm_bwd(const void* dy, int dy_dtype, int ldy, const float* x, const float* mean, const float* rstd,
+                          int T, int D, const float* residual_grad, float* dx, void* stream) {
+  B200_CHECK_ARG(D % 4 == 0 && D <= 2048 && ldy % 4 == 0, "layernorm_bwd: bad D=%d ldy=%d", D, ldy);
+  if (T == 0) return 0;
+  int blocks = ceil_div_i(T, ROWS_PER_BLOCK);
+  DISPATCH_ACT(dy_dtype, TG, {
+    if (D <= 512)
+      layernorm_bwd_kernel<TG, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TG*)dy, ldy, x, mean, rstd, T,
+                                                                            D / 4, residual_grad, dx);
+    else
+      layernorm_bwd_kernel<TG, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TG*)dy, ldy, x, mean, rstd, T,
+                                                                             D / 4, residual_grad, dx);
+  });
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- gate: oin = u * LN(a)
+template <typename TA, int MAXV>
+__global__ void __launch_bounds__(256) gate_ln_fwd_kernel(const TA* __restrict__ u, int64_t ldu,
+                                                          const float* __restrict__ a, int T, int D4, float eps,
+                                                          TA* __restrict__ oin, float* __restrict__ mean,
+                                                          float* __restrict__ rstd) {
+  int lane = threadIdx.x & 31;
+  int r = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  if (r >= T) return;
+  float v[MAXV][4];
+  float s = 0.f;
+#pragma unroll
+  for (int k4 = 0; k4 < MAXV; ++k4) {
+    int c = lane + k4 * 32;
+    if (c < D4) {
+      load4<float>(a + ((int64_t)r * D4 + c) * 4, v[k4]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s += v[k4][k];
+    }
+  }
+  float D = (float)(D4 * 4);
+  float mu = warp_sum(s) / D;
+  float ss = 0.f;
+#pragma unroll
+  for (int k4 = 0; k4 < MAXV; ++k4) {
+    int c = lane + k4 * 32;
+    if (c < D4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float d = v[k4][k] - mu;
+        ss += d * d;
+      }
+    }
+  }
+  float rs = rsqrtf(warp_sum(ss) / D + eps);
+  if (lane == 0) {
+    mean[r] = mu;
+    rstd[r] = rs;
+  }
+#pragma unroll
+  for (int k4 = 0; k4 < MAXV; ++k4) {
+    int c = lane + k4 * 32;
+    if (c < D4) {
+      float uu[4];
+      load4<TA>(u + (int64_t)r * ldu + c * 4, uu);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k4][k] = (v[k4][k] - mu) * rs * uu[k];
+      store4<TA>(oin + ((int64_t)r * D4 + c) * 4, v[k4]);
+    }
+  }
+}
+
+int b200rec_gate_ln_fwd(const void* u, int ldu, const float* a, int T, int D, float eps, void* oin, int act_dtype,
+                        float* mean, float* rstd, void* stream) {
+  B200_CHECK_ARG(D % 4 == 0 && D <= 2048 && ldu % 4 == 0, "gate_ln_fwd: bad D=%d ldu=%d", D, ldu);
+  if (T == 0) return 0;
+  int blocks = ceil_div_i(T, ROWS_PER_BLOCK);
+  DISPATCH_ACT(act_dtype, TA, {
+    if (D <= 512)
+      gate_ln_fwd_kernel<TA, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TA*)u, ldu, a, T, D / 4, eps,
+                                                                          (TA*)oin, mean, rstd);
+    else
+      gate_ln_fwd_kernel<TA, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TA*)u, ldu, a, T, D / 4, eps,
+                                                                           (TA*)oin, mean, rstd);
+  });
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+template <typename TA, int MAXV>
+__global__ void __launch_bounds__(256) gate_ln_bwd_kernel(const TA* __restrict__ d_oin, const TA* __restrict__ u,
+                                                          const TA* __restrict__ pre_u, int64_t ldu,
+                                                          const float* __restrict__ a, const float* __restrict__ mean,
+                                                          const float* __restrict__ rstd, int T, int D4,
+                                                          TA* __restrict__ d_pre_u, float* __restrict__ da) {
+  int lane = threadIdx.x & 31;
+  int r = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  if (r >= T) return;
+  float mu = mean[r], rs = rstd[r];
+  float lna[MAXV][4], g[MAXV][4];  // g becomes d_lna
+  float sg = 0.f, sgx = 0.f;
+#pragma unroll
+  for (int k4 = 0; k4 < MAXV; ++k4) {
+    int c = lane + k4 * 32;
+    if (c < D4) {
+      float go[4], uu[4], pu[4], dpu[4];
+      load4<float>(a + ((int64_t)r * D4 + c) * 4, lna[k4]);
+      load4<TA>(d_oin + ((int64_t)r * D4 + c) * 4, go);
+      load4<TA>(u + (int64_t)r * ldu + c * 4, uu);
+      load4<TA>(pre_u + (int64_t)r * ldu + c * 4, pu);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        lna[k4][k] = (lna[k4][k] - mu) * rs;
+        dpu[k] = go[k] * lna[k4][k] * silu_grad_f(pu[k]);
+        g[k4][k] = go[k] * uu[k];
+        sg += g[k4][k];
+        sgx += g[k4][k] * lna[k4][k];
+      }
+      store4<TA>(d_pre_u + (int64_t)r * ldu + c * 4, dpu);
+    }
+  }
+  float D = (float)(D4 * 4);
+  sg = warp_sum(sg) / D;
+  sgx = warp_sum(sgx) / D;
+#pragma unroll
+  for (int k4 = 0; k4 < MAXV; ++k4) {
+    int c = lane + k4 * 32;
+    if (c < D4) {
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = rs * (g[k4][k] - sg - lna[k4][k] * sgx);
+      store4<float>(da + ((int64_t)r * D4 + c) * 4, o);
+    }
+  }
+}
+
+int b200rec_gate_ln_bwd(const void* d_oin, const void* u, const void* pre_u, int ldu, const float* a,
+                        const float* mean, const float* rstd, int T, int D, void* d_pre_u, float* da, int act_dtype,
+                        void* stream) {
+  B200_CHECK_ARG(D % 4 == 0 && D <= 2048 && ldu % 4 == 0, "gate_ln_bwd: bad D=%d ldu=%d", D, ldu);
+  if (T == 0) return 0;
+  int blocks = ceil_div_i(T, ROWS_PER_BLOCK);
+  DISPATCH_ACT(act_dtype, TA, {
+    if (D <= 512)
+      gate_ln_bwd_kernel<TA, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+          (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, da);
+    else
+      gate_ln_bwd_kernel<TA, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+          (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, da);
+  });
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- cast / column sums / reductions
+template <typename TY>
+__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ x, int64_t n4, TY* __restrict__ y) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float v[4];
+    load4<float>(x + i * 4, v);
+    store4<TY>(y + i * 4, v);
+  }
+}
+template <typename TY>
+__global__ void cast_tail_kernel(const float* __restrict__ x, int64_t beg, int64_t n, TY* __restrict__ y) {
+  int64_t i = beg + threadIdx.x;
+  if (i < n) y[i] = from_f32<TY>(x[i]);
+}
+
+int b200rec_cast(const float* x, int64_t n, void* y, int y_dtype, void* stream) {
+  if (n == 0) return 0;
+  int64_t n4 = n / 4;
+  DISPATCH_ACT(y_dtype, TY, {
+    if (n4 > 0) {
+      int blocks = (int)std::min<int64_t>((n4 + 255) / 256, 148 * 16);
+      cast_kernel<TY><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n4, (TY*)y);
+    }
+    if (n4 * 4 < n) cast_tail_kernel<TY><<<1, 4, 0, (cudaStream_t)stream>>>(x, n4 * 4, n, (TY*)y);
+  });
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+// block = 32 columns x 8 row lanes; each thread walks rows r = lane_r, lane_r+8, ...; partials are
+// combined in fixed order -> deterministic.
+template <typename TX>
+__global__ void __launch_bounds__(256) colsum_kernel(const TX* __restrict__ x, int64_t ldx, int rows, int cols,
+                                                     float* __restrict__ out, int accumulate) {
+  __shared__ float part[8][33];
+  int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  int c = blockIdx.x * 32 + cx;
+  float s = 0.f;
+  if (c < cols)
+    for (int r = ry; r < rows; r += 8) s += to_f32(x[(int64_t)r * ldx + c]);
+  part[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][cx];
+    out[c] = accumulate ? out[c] + t : t;
+  }
+}
+
+int b200rec_colsum(const void* x, int x_dtype, int ldx, int rows, int cols, float* out, int accumulate,
+                   void* stream) {
+  if (cols == 0) return 0;
+  int blocks = ceil_div_i(cols, 32);
+  DISPATCH_ACT(x_dtype, TX, {
+    colsum_kernel<TX><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TX*)x, ldx, rows, cols, out, accumulate);
+  });
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+// single block, fixed-order tree: deterministic scalar reduction (loss sums, dscale)
+__global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restrict__ x, int64_t n, float scale,
+                                                          float* __restrict__ out, int accumulate) {
+  __shared__ float red[40];
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[0] = accumulate ? out[0] + scale * s : scale * s;
+}
+
+int b200rec_reduce_sum(const float* x, int64_t n, float scale, float* out, int accumulate, void* stream) {
+  reduce_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, scale, out, accumulate);
+  B200_LAUNCH_OK();
+  return 0;
+}

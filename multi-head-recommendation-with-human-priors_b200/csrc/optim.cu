@@ -1,0 +1,106 @@
+// Fused AdamW (torch.optim.AdamW maths, trainer.py:296-299), one pass over p/m/v.  The embedding
+// variant consumes the compact (unique id, row) gradient of the sorted-segment scatter-add and is
+// dense-equivalent: rows without a gradient still decay and move with their momentum.
+#include "common.cuh"
+
+struct AdamCoef {
+  float lr, b1, b2, eps, wd, bc1, bc2_sqrt, gs;
+};
+
+__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, const AdamCoef& c) {
+  g *= c.gs;
+  p *= (1.f - c.lr * c.wd);
+  m = c.b1 * m + (1.f - c.b1) * g;
+  v = c.b2 * v + (1.f - c.b2) * g * g;
+  float denom = sqrtf(v) / c.bc2_sqrt + c.eps;
+  p -= (c.lr / c.bc1) * (m / denom);
+}
+
+static AdamCoef make_coef(float lr, float b1, float b2, float eps, float wd, int step, float gs) {
+  AdamCoef c;
+  c.lr = lr; c.b1 = b1; c.b2 = b2; c.eps = eps; c.wd = wd; c.gs = gs;
+  c.bc1 = 1.f - powf(b1, (float)step);
+  c.bc2_sqrt = sqrtf(1.f - powf(b2, (float)step));
+  return c;
+}
+
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ m,
+                                                    float* __restrict__ v, const float* __restrict__ g, int64_t n,
+                                                    AdamCoef c) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = n / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float pp[4], mm[4], vv[4], gg[4];
+    load4<float>(p + i * 4, pp);
+    load4<float>(m + i * 4, mm);
+    load4<float>(v + i * 4, vv);
+    load4<float>(g + i * 4, gg);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) adam_update(pp[k], mm[k], vv[k], gg[k], c);
+    store4<float>(p + i * 4, pp);
+    store4<float>(m + i * 4, mm);
+    store4<float>(v + i * 4, vv);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    int64_t i = n4 * 4 + threadIdx.x;
+    adam_update(p[i], m[i], v[i], g[i], c);
+  }
+}
+
+int b200rec_adamw(float* p, float* m, float* v, const float* g, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, float grad_scale, void* stream) {
+  if (n == 0) return 0;
+  B200_CHECK_ARG(((uintptr_t)p & 15) == 0 && ((uintptr_t)m & 15) == 0 && ((uintptr_t)v & 15) == 0 &&
+                     ((uintptr_t)g & 15) == 0,
+                 "adamw: pointers must be 16-byte aligned");
+  AdamCoef c = make_coef(lr, beta1, beta2, eps, weight_decay, step, grad_scale);
+  int blocks = (int)std::min<int64_t>((n / 4 + 255) / 256 + 1, 148 * 16);
+  adamw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, m, v, g, n, c);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+__global__ void row_slot_kernel(const int64_t* __restrict__ uniq_ids, const int32_t* __restrict__ n_uniq,
+                                int32_t* __restrict__ row_slot) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < *n_uniq) row_slot[uniq_ids[i]] = i;
+}
+
+__global__ void __launch_bounds__(256) adamw_rows_kernel(float* __restrict__ p, float* __restrict__ m,
+                                                         float* __restrict__ v, int64_t n_vec, int D4,
+                                                         const int32_t* __restrict__ row_slot,
+                                                         const float* __restrict__ uniq_rows, AdamCoef c) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+    int64_t r = i / D4;
+    int col = (int)(i - r * D4);
+    int slot = __ldg(row_slot + r);
+    float pp[4], mm[4], vv[4], gg[4] = {0.f, 0.f, 0.f, 0.f};
+    load4<float>(p + i * 4, pp);
+    load4<float>(m + i * 4, mm);
+    load4<float>(v + i * 4, vv);
+    if (slot >= 0) load4<float>(uniq_rows + ((int64_t)slot * D4 + col) * 4, gg);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) adam_update(pp[k], mm[k], vv[k], gg[k], c);
+    store4<float>(p + i * 4, pp);
+    store4<float>(m + i * 4, mm);
+    store4<float>(v + i * 4, vv);
+  }
+}
+
+int b200rec_adamw_rows(float* p, float* m, float* v, int64_t n_rows, int D, const int64_t* uniq_ids,
+                       const float* uniq_rows, const int32_t* n_uniq, int32_t* row_slot_ws, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CHECK_ARG(D % 4 == 0, "adamw_rows: D=%d must be a multiple of 4", D);
+  if (n_rows == 0) return 0;
+  AdamCoef c = make_coef(lr, beta1, beta2, eps, weight_decay, step, grad_scale);
+  B200_CUDA_OK(cudaMemsetAsync(row_slot_ws, 0xff, (size_t)n_rows * 4, st));
+  // n_uniq lives on the device: launch for the worst case (every row touched)
+  row_slot_kernel<<<ceil_div_i(n_rows, 256), 256, 0, st>>>(uniq_ids, n_uniq, row_slot_ws);
+  int64_t n_vec = n_rows * (D / 4);
+  int blocks = (int)std::min<int64_t>((n_vec + 255) / 256, 148 * 16);
+  adamw_rows_kernel<<<blocks, 256, 0, st>>>(p, m, v, n_vec, D / 4, row_slot_ws, uniq_rows, c);
+  B200_LAUNCH_OK();
+  return 0;
+}

@@ -1,0 +1,783 @@
+"""B200-native HSTU with multi-head prior-guided decoding: drop-in for the reference model class.
+
+Mirrors `REC.model.IDNet.hstu.HSTU` (reference code/REC/model/IDNet/hstu.py:331-1030): same
+constructor `HSTU(config, dataload)`, same `forward(interaction) -> dict` with `'loss'` and the
+logging keys, same `predict(...)`, `compute_item_all()`, parameter / buffer names and init
+order (so a reference checkpoint loads with `load_state_dict`, and the same seed gives the same
+initial weights).  All arithmetic runs in hand-written sm_100a kernels behind the C ABI in
+include/b200rec.h; torch only owns memory and streams.  No CPU path: tensors must be CUDA.
+
+Restructurings relative to the reference (each proven equal on valid rows):
+  * jagged body: only valid tokens are computed (hstu.py:645 mask -> seq_off / tok_pos);
+  * one query row per (head, token) shared by all prediction offsets, one fix-mask row per
+    target position (hstu.py:600-619 recomputes both per (b, p, l));
+  * deterministic sorted-segment embedding gradient instead of atomic index_add;
+  * eval: top-K of the max over heads == the collector's per-head top-K + sort + dedupe.
+Not implemented (raise): head_interaction='hierarchical', prior_switch, medusa_num_layers > 1,
+item_embedding_size != hstu_embedding_size, dropout > 0 in training mode.
+"""
+import math
+from collections import defaultdict
+from logging import getLogger
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+LN_EPS = 1e-6  # hstu.py:177
+
+
+def truncated_normal_(x, mean, std):
+    """hstu.py:23-31 (resample-4 truncated normal); same RNG consumption as the reference."""
+    with torch.no_grad():
+        tmp = x.new_empty(x.shape + (4,)).normal_()
+        valid = (tmp < 2) & (tmp > -2)
+        ind = valid.max(-1, keepdim=True)[1]
+        x.data.copy_(tmp.gather(-1, ind).squeeze(-1))
+        x.data.mul_(std).add_(mean)
+    return x
+
+
+class _RelBias(nn.Module):
+    """Parameters of RelativeBucketedTimeAndPositionBasedBias (hstu.py:74-97).  The reference builds
+    them but never applies them in the block; kept for state-dict parity, no gradient."""
+
+    def __init__(self, max_seq_len, num_buckets):
+        super().__init__()
+        self._ts_w = nn.Parameter(torch.empty(num_buckets + 1).normal_(mean=0, std=0.02))
+        self._pos_w = nn.Parameter(torch.empty(2 * max_seq_len - 1).normal_(mean=0, std=0.02))
+
+
+class _STU(nn.Module):
+    """Parameter holder for one SequentialTransductionUnitJagged (hstu.py:163-211)."""
+
+    def __init__(self, D, rel_bias):
+        super().__init__()
+        self._rel_attn_bias = rel_bias
+        self._uvqk = nn.Parameter(torch.empty((D, 4 * D)).normal_(mean=0, std=0.02))
+        self._o = nn.Linear(D, D)
+        nn.init.xavier_uniform_(self._o.weight)
+
+
+class _Body(nn.Module):
+    def __init__(self, blocks):
+        super().__init__()
+        self._attention_layers = nn.ModuleList(blocks)
+
+
+class _ResBlock(nn.Module):
+    """Parameter holder for llm_heads.ResBlock (llm_heads.py:16-24): linear [D, D] + bias."""
+
+    def __init__(self, D):
+        super().__init__()
+        self.linear = nn.Linear(D, D)
+        nn.init.zeros_(self.linear.weight)
+
+
+class _Job:
+    """One NCE contraction: query head `head` against negative set `nset`, serving the prediction
+    offsets in `p_mask` with token-validity column `col` and loss weight `w`."""
+    __slots__ = ("part", "cat", "head", "nset", "p_mask", "col", "w", "seg")
+
+    def __init__(self, part, cat, head, nset, p_mask, col, w, seg):
+        self.part, self.cat, self.head, self.nset = part, cat, head, nset
+        self.p_mask, self.col, self.w, self.seg = p_mask, col, w, seg
+
+
+class HSTU(nn.Module):
+    def __init__(self, config, dataload, compute_dtype=torch.bfloat16):
+        super().__init__()
+        self.logger = getLogger()
+        self.compute_dtype = compute_dtype
+        self.item_num = dataload.item_num
+        D_item = config["item_embedding_size"]
+        D = config["hstu_embedding_size"]
+        if D_item != D:
+            raise NotImplementedError("item_embedding_size != hstu_embedding_size (item_id_proj_tower) is not built")
+        self._hstu_embedding_dim = D
+        self.max_seq_length = config["MAX_ITEM_LIST_LENGTH"]
+        self.pred_len = config["pred_len"]
+        self.medusa_lambda = config["medusa_lambda"]
+        self.num_segment_head = config["num_segment_head"]
+        self.num_prior_head = config["num_prior_head"]
+        self.head_interaction = config["head_interaction"]
+        if self.head_interaction == "multiplicative":
+            self.medusa_num_heads = self.num_segment_head * self.num_prior_head
+        elif self.head_interaction == "additive":
+            self.medusa_num_heads = self.num_segment_head + self.num_prior_head
+        elif self.head_interaction == "hierarchical":
+            raise NotImplementedError("head_interaction='hierarchical' is not built in this round")
+        else:
+            raise ValueError(f'Unknown head_interaction: {config["head_interaction"]}')
+        self.medusa_num_layers = config["medusa_num_layers"]
+        if self.medusa_num_layers > 1:
+            raise NotImplementedError("medusa_num_layers > 1 is not built in this round")
+        self.category_by = config["category_by"]
+        self._num_blocks = config["n_layers"]
+        self._num_heads = config["n_heads"]
+        self._dqk = D // self._num_heads
+        if (config["hidden_act"] or "silu") != "silu":
+            raise NotImplementedError("only hidden_act='silu' is built")
+        self._linear_dropout_rate = config["hidden_dropout_prob"] or 0.0
+        self._enable_relative_attention_bias = bool(config["enable_relative_attention_bias"])
+        # ---- parameters, created in the reference's order (hstu.py:380-425, 486-493) ----
+        self.position_embedding = nn.Embedding(self.max_seq_length + 1, D)
+        blocks = []
+        for _ in range(self._num_blocks):
+            rb = _RelBias(2 * self.max_seq_length, 128) if self._enable_relative_attention_bias else None
+            blocks.append(_STU(D, rb))
+        self._hstu = _Body(blocks)
+        self.item_embedding = nn.Embedding(self.item_num, D_item, padding_idx=0)
+        self.item_id_proj_tower = nn.Identity()
+        self.loss = config["loss"]
+        self.neg_sample_by_cat = bool(config["neg_sample_by_cat"]) and self.loss == "prior"
+        if (config["pos_sample_mix_ratio"] or 0) > 0:
+            raise NotImplementedError("pos_sample_mix_ratio > 0 draws torch RNG inside forward; not built")
+        if self.loss not in ("nce", "prior"):
+            raise NotImplementedError(f"loss={self.loss} is not supported")
+        if config["fix_temp"]:
+            self.register_buffer("logit_scale", torch.tensor(np.log(1 / 0.05)))
+        else:
+            self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1 / 0.05))
+        self.nce_thres = config["nce_thres"] if config["nce_thres"] else 0.99
+        self.seg_len = self.pred_len
+        if self.medusa_num_layers > 0:
+            assert self.pred_len % self.num_segment_head == 0, "pred_len must be divisible by the number of segments"
+            self.seg_len = self.pred_len // self.num_segment_head
+        hd = torch.tensor([self.medusa_lambda ** i for i in range(self.pred_len)])
+        self.register_buffer("horizon_discount", hd / sum(hd))
+        if self.medusa_num_layers == 0:
+            self.medusa_head = nn.ModuleList([nn.Identity() for _ in range(self.medusa_num_heads)])
+            self.prior_loss_weight = [1 / self.num_prior_head] * self.num_prior_head
+        else:
+            self.medusa_head = nn.ModuleList(
+                [nn.Sequential(*([_ResBlock(D)] * self.medusa_num_layers)) for _ in range(self.medusa_num_heads)])
+            self.weighted_prior_loss = config["weighted_prior_loss"]
+            if self.loss != "prior":
+                assert self.num_prior_head == 1, "Only prior loss is allowed for num_prior_head > 1"
+            if self.loss == "prior" and self.weighted_prior_loss:
+                tot = sum(dataload.category_counts.values())
+                self.prior_loss_weight = [0 for _ in range(self.num_prior_head)]
+                for name, cnt in dataload.category_counts.items():
+                    self.prior_loss_weight[dataload.category_to_int[name]] = cnt / tot
+            else:
+                self.prior_loss_weight = [1 / self.num_prior_head] * self.num_prior_head
+            if self.loss == "prior" and config["prior_switch"] is not None:
+                raise NotImplementedError("prior_switch aux heads are not built (off in every shipped script)")
+        self.prior_switch = None
+        self.eval_pred_len = config["eval_pred_len"]
+        self.prior_given_at_test = config.get("prior_given_at_test", False)
+        self.given_prior_len = config.get("given_prior_len", self.eval_pred_len) if self.prior_given_at_test \
+            else self.eval_pred_len
+        self.int_to_category = config["int_to_category"]
+        self.register_buffer("_attn_mask", torch.triu(
+            torch.ones((self.max_seq_length, self.max_seq_length), dtype=torch.bool), diagonal=1))
+        self.sparse_embedding_grad = bool(config.get("sparse_embedding_grad", False))
+        self.emb_grad = None       # (uniq_ids, uniq_rows, n_uniq) of the last backward
+        self._table_cache = None   # normalised compute-dtype item table for predict
+        self._verbose = False
+        self.reset_params()
+        self._jobs = self._build_jobs()
+
+    # ------------------------------------------------------------------ init (hstu.py:574-588)
+    def reset_params(self):
+        for name, p in self.named_parameters():
+            if ("_hstu" in name) or ("_embedding_module" in name) or ("logit_scale" in name):
+                continue
+            truncated_normal_(p.data, mean=0.0, std=0.02)
+
+    def _build_jobs(self):
+        P, S, C = self.pred_len, self.num_segment_head, self.num_prior_head
+        n_sets_global = C if self.neg_sample_by_cat else 0   # index of the global set in neg_items[:, -1]
+        jobs = []
+
+        def pmask(seg, seg_len):
+            return sum(1 << p for p in range(P) if p // seg_len == seg)
+
+        if self.loss == "nce" or (self.loss == "prior" and self.head_interaction == "additive"):
+            n_seg = P // self.seg_len
+            for s in range(n_seg):
+                jobs.append(_Job("nce", -1, s, n_sets_global, pmask(s, self.seg_len), 0, 1.0, s))
+        if self.loss == "prior":
+            seg_len = P if self.head_interaction == "additive" else self.seg_len
+            for c in range(C):
+                nset = c if self.neg_sample_by_cat else n_sets_global
+                for s in range(P // seg_len):
+                    head = S + c if self.head_interaction == "additive" else s * C + c
+                    jobs.append(_Job("prior", c, head, nset, pmask(s, seg_len), 1 + c, float(self.prior_loss_weight[c]), s))
+        return jobs
+
+    # ------------------------------------------------------------------ helpers
+    def _act(self):
+        return self.compute_dtype
+
+    def _phys_heads(self):
+        return self.medusa_num_heads if self.medusa_num_layers > 0 else 1
+
+    def _cast_weights(self):
+        """Compute-dtype copies of the dense weights for this step (fp32 masters stay in the Parameters)."""
+        act = self._act()
+        D = self._hstu_embedding_dim
+        w = {}
+        for i, blk in enumerate(self._hstu._attention_layers):
+            if act == torch.float32:
+                w[f"uvqk{i}"], w[f"o{i}"] = blk._uvqk.data, blk._o.weight.data
+            else:
+                u = torch.empty((D, 4 * D), dtype=act, device=blk._uvqk.device)
+                o = torch.empty((D, D), dtype=act, device=blk._uvqk.device)
+                L.call("b200rec_cast", blk._uvqk.data_ptr(), u.numel(), u.data_ptr(), L.dt(u), L.stream())
+                L.call("b200rec_cast", blk._o.weight.data_ptr(), o.numel(), o.data_ptr(), L.dt(o), L.stream())
+                w[f"uvqk{i}"], w[f"o{i}"] = u, o
+        if self.medusa_num_layers > 0:
+            H = self.medusa_num_heads
+            dev = self.item_embedding.weight.device
+            wc = torch.empty((H * D, D), dtype=act, device=dev)
+            bc = torch.empty((H * D,), dtype=torch.float32, device=dev)
+            for h in range(H):
+                lin = self.medusa_head[h][0].linear
+                if act == torch.float32:
+                    wc[h * D:(h + 1) * D].copy_(lin.weight.data)
+                else:
+                    L.call("b200rec_cast", lin.weight.data_ptr(), D * D, wc[h * D:].data_ptr(), L.dt(wc), L.stream())
+                bc[h * D:(h + 1) * D].copy_(lin.bias.data)
+            w["heads_w"], w["heads_b"] = wc, bc
+        return w
+
+    @staticmethod
+    def _tokens(valid, force_last=False):
+        """Jagged index of a [B, L] validity mask.  force_last adds position L-1 of every sequence as a
+        (key-masked) query token so predict() can read it like the reference reads output[:, -1]."""
+        B, Lx = valid.shape
+        tok_mask = valid.clone()
+        if force_last:
+            tok_mask[:, -1] = True
+        idx = tok_mask.nonzero(as_tuple=False)            # sorted by (b, pos); host sync for T
+        tok_b = idx[:, 0].to(torch.int32).contiguous()
+        tok_pos = idx[:, 1].to(torch.int32).contiguous()
+        seq_off = torch.zeros(B + 1, dtype=torch.int32, device=valid.device)
+        seq_off[1:] = tok_mask.sum(1).cumsum(0).to(torch.int32)
+        key_valid = valid[idx[:, 0], idx[:, 1]].to(torch.uint8).contiguous()
+        return tok_b, tok_pos, seq_off, key_valid, int(idx.shape[0])
+
+    # ------------------------------------------------------------------ body (hstu.py:221-328)
+    def _body_forward(self, x, w, seq_off, key_valid, B, T, n_pad, max_len, save):
+        D, nh, dh = self._hstu_embedding_dim, self._num_heads, self._dqk
+        act, dev = self._act(), x.device
+        a_dt = L.dt(act)
+        saved = []
+        st = L.stream()
+        for i in range(self._num_blocks):
+            blk = self._hstu._attention_layers[i]
+            n = torch.empty((T, D), dtype=act, device=dev)
+            mean1 = torch.empty(T, dtype=torch.float32, device=dev)
+            rstd1 = torch.empty(T, dtype=torch.float32, device=dev)
+            L.call("b200rec_layernorm_fwd", x.data_ptr(), T, D, LN_EPS, n.data_ptr(), a_dt, mean1.data_ptr(),
+                   rstd1.data_ptr(), st)
+            actv = torch.empty((T, 4 * D), dtype=act, device=dev)
+            pre = torch.empty((T, 4 * D), dtype=act, device=dev)
+            # uvqk = silu(n @ W): W is [D, 4D] = [K, N] -> MN-major B operand
+            L.gemm(n, w[f"uvqk{i}"], actv, T, 4 * D, D, lda=D, ldb=4 * D, b_major=1, ldc=4 * D,
+                   epilogue=L.EPI_SILU_DUAL, C2=pre, ldc2=4 * D)
+            a = torch.empty((T, D), dtype=torch.float32, device=dev)
+            u, v, q, k = actv[:, 0:D], actv[:, D:2 * D], actv[:, 2 * D:3 * D], actv[:, 3 * D:4 * D]
+            L.call("b200rec_hstu_attn_fwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), 4 * D, a_dt,
+                   seq_off.data_ptr(), key_valid.data_ptr(), B, T, nh, dh, 1.0 / n_pad, max_len, a.data_ptr(), st)
+            oin = torch.empty((T, D), dtype=act, device=dev)
+            mean2 = torch.empty(T, dtype=torch.float32, device=dev)
+            rstd2 = torch.empty(T, dtype=torch.float32, device=dev)
+            L.call("b200rec_gate_ln_fwd", u.data_ptr(), 4 * D, a.data_ptr(), T, D, LN_EPS, oin.data_ptr(), a_dt,
+                   mean2.data_ptr(), rstd2.data_ptr(), st)
+            x_next = torch.empty((T, D), dtype=torch.float32, device=dev)
+            L.gemm(oin, w[f"o{i}"], x_next, T, D, D, lda=D, ldb=D, ldc=D, epilogue=L.EPI_BIAS_RESID,
+                   bias=blk._o.bias.data, resid=x, ldr=D)
+            if save:
+                saved.append((x, mean1, rstd1, n, actv, pre, a, mean2, rstd2, oin))
+            x = x_next
+        return x, saved
+
+    def _body_backward(self, dx, saved, w, seq_off, key_valid, B, T, n_pad, max_len, grads):
+        D, nh, dh = self._hstu_embedding_dim, self._num_heads, self._dqk
+        act, dev = self._act(), dx.device
+        a_dt = L.dt(act)
+        st = L.stream()
+        for i in reversed(range(self._num_blocks)):
+            blk = self._hstu._attention_layers[i]
+            x, mean1, rstd1, n, actv, pre, a, mean2, rstd2, oin = saved[i]
+            if act == torch.float32:
+                dxb = dx
+            else:
+                dxb = torch.empty((T, D), dtype=act, device=dev)
+                L.call("b200rec_cast", dx.data_ptr(), dx.numel(), dxb.data_ptr(), a_dt, st)
+            # d_oin = dx @ W_o   (W_o [Dout, Din] = [K, N] -> MN-major B)
+            d_oin = torch.empty((T, D), dtype=act, device=dev)
+            L.gemm(dxb, w[f"o{i}"], d_oin, T, D, D, lda=D, ldb=D, b_major=1, ldc=D)
+            # dW_o[Dout, Din] = dx^T @ oin  (both operands MN-major, K = T)
+            dWo = torch.empty((D, D), dtype=torch.float32, device=dev)
+            L.gemm(dxb, oin, dWo, D, D, T, lda=D, a_major=1, ldb=D, b_major=1, ldc=D)
+            dbo = torch.empty(D, dtype=torch.float32, device=dev)
+            L.call("b200rec_colsum", dx.data_ptr(), L.F32, D, T, D, dbo.data_ptr(), 0, st)
+            d_pre = torch.empty((T, 4 * D), dtype=act, device=dev)
+            da = torch.empty((T, D), dtype=torch.float32, device=dev)
+            L.call("b200rec_gate_ln_bwd", d_oin.data_ptr(), actv.data_ptr(), pre.data_ptr(), 4 * D, a.data_ptr(),
+                   mean2.data_ptr(), rstd2.data_ptr(), T, D, d_pre.data_ptr(), da.data_ptr(), a_dt, st)
+            sl = lambda t, j: t[:, j * D:(j + 1) * D]
+            L.call("b200rec_hstu_attn_bwd", sl(actv, 2).data_ptr(), sl(actv, 3).data_ptr(), sl(actv, 1).data_ptr(),
+                   sl(pre, 2).data_ptr(), sl(pre, 3).data_ptr(), sl(pre, 1).data_ptr(), 4 * D, a_dt,
+                   seq_off.data_ptr(), key_valid.data_ptr(), B, T, nh, dh, 1.0 / n_pad, max_len, da.data_ptr(),
+                   sl(d_pre, 2).data_ptr(), sl(d_pre, 3).data_ptr(), sl(d_pre, 1).data_ptr(), st)
+            # dW_uvqk[D, 4D] = n^T @ d_pre  (both MN-major, K = T)
+            dWu = torch.empty((D, 4 * D), dtype=torch.float32, device=dev)
+            L.gemm(n, d_pre, dWu, D, 4 * D, T, lda=D, a_major=1, ldb=4 * D, b_major=1, ldc=4 * D)
+            # dn = d_pre @ W_uvqk^T  (W [D, 4D] = [N, K] -> K-major B)
+            dn = torch.empty((T, D), dtype=act, device=dev)
+            L.gemm(d_pre, w[f"uvqk{i}"], dn, T, D, 4 * D, lda=4 * D, ldb=4 * D, ldc=D)
+            dx_prev = torch.empty((T, D), dtype=torch.float32, device=dev)
+            L.call("b200rec_layernorm_bwd", dn.data_ptr(), a_dt, D, x.data_ptr(), mean1.data_ptr(), rstd1.data_ptr(),
+                   T, D, dx.data_ptr(), dx_prev.data_ptr(), st)
+            grads[blk._uvqk] = dWu
+            grads[blk._o.weight] = dWo
+            grads[blk._o.bias] = dbo
+            dx = dx_prev
+            saved[i] = None
+        return dx
+
+    # ------------------------------------------------------------------ heads (hstu.py:652-667)
+    def _heads_forward(self, y, w, rows):
+        """y fp32 [rows, D] -> hd fp32 [rows, Hx, D], z (pre-activation, act) or None, yb (act copy)."""
+        D, Hx = self._hstu_embedding_dim, self._phys_heads()
+        act, dev = self._act(), y.device
+        if self.medusa_num_layers == 0:
+            return y.view(rows, 1, D), None, None
+        if act == torch.float32:
+            yb = y
+        else:
+            yb = torch.empty((rows, D), dtype=act, device=dev)
+            L.call("b200rec_cast", y.data_ptr(), y.numel(), yb.data_ptr(), L.dt(act), L.stream())
+        hd = torch.empty((rows, Hx, D), dtype=torch.float32, device=dev)
+        z = torch.empty((rows, Hx, D), dtype=act, device=dev)
+        L.gemm(yb, w["heads_w"], hd, rows, Hx * D, D, lda=D, ldb=D, ldc=Hx * D, epilogue=L.EPI_RESBLOCK,
+               bias=w["heads_b"], resid=y, ldr=D, C2=z, ldc2=Hx * D, n_split=D)
+        return hd, z, yb
+
+    # ------------------------------------------------------------------ training (hstu.py:631-872)
+    def forward(self, interaction):
+        items, neg_items, mask, tags = interaction
+        if not items.is_cuda:
+            raise L.B200RecError("b200rec.HSTU.forward needs CUDA tensors (there is no CPU path)")
+        if self.training and self._linear_dropout_rate > 0:
+            raise NotImplementedError("hidden_dropout_prob > 0 in training mode is not built; use model.eval() "
+                                      "or hidden_dropout_prob=0 (parity runs do the same, SURVEY App. C)")
+        params = [p for p in self.parameters()]
+        loss = _TrainStep.apply(self, items, neg_items, mask, tags, *params)
+        out = defaultdict(float)
+        out.update(self._last_logs)
+        out["loss"] = loss
+        return out
+
+    def _train_forward(self, items, neg_items, mask, tags, need_grad):
+        dev = items.device
+        D, P, Lc = self._hstu_embedding_dim, self.pred_len, self.max_seq_length
+        B, LP = items.shape
+        assert LP == Lc + P, f"items must be [B, L+P] = [B, {Lc + P}], got {tuple(items.shape)}"
+        act, a_dt, st = self._act(), L.dt(self._act()), L.stream()
+        items = items.contiguous()
+        m = mask.bool()
+        W = self.item_embedding.weight.data
+        ctx = {}
+        # ---- jagged token index (valid context positions only)
+        tok_b, tok_pos, seq_off, key_valid, T = self._tokens(m[:, :Lc])
+        tok_index = torch.full((B * LP,), -1, dtype=torch.int32, device=dev)
+        tok_index[tok_b.long() * LP + tok_pos.long()] = torch.arange(T, dtype=torch.int32, device=dev)
+        C = self.num_prior_head
+        n_col = 1 + (C if self.loss == "prior" else 0)
+        tok_ok = torch.zeros((B * LP, n_col), dtype=torch.uint8, device=dev)
+        tok_ok[:, 0] = m.reshape(-1)
+        if self.loss == "prior":
+            tok_ok[:, 1:] = (m.unsqueeze(-1) & tags[:, :, :C].bool()).reshape(B * LP, C)
+        w = self._cast_weights()
+        # ---- embedding + body
+        x = torch.empty((T, D), dtype=torch.float32, device=dev)
+        L.call("b200rec_embed_tokens", W.data_ptr(), self.position_embedding.weight.data_ptr(), items.data_ptr(),
+               tok_b.data_ptr(), tok_pos.data_ptr(), T, LP, D, x.data_ptr(), st)
+        y, saved = self._body_forward(x, w, seq_off, key_valid, B, T, Lc, Lc, need_grad)
+        hd, z, yb = self._heads_forward(y, w, T)
+        Hx = hd.shape[1]
+        qhat = torch.empty((T * Hx, D), dtype=act, device=dev)
+        qinv = torch.empty(T * Hx, dtype=torch.float32, device=dev)
+        L.call("b200rec_gather_l2norm", None, hd.data_ptr(), D, None, T * Hx, qhat.data_ptr(), a_dt, qinv.data_ptr(), st)
+        # ---- targets and negatives: gather + L2 normalise (hstu.py:605-606, 670-672)
+        flat_items = items.reshape(-1)
+        that = torch.empty((B * LP, D), dtype=act, device=dev)
+        tinv = torch.empty(B * LP, dtype=torch.float32, device=dev)
+        L.call("b200rec_gather_l2norm", W.data_ptr(), None, D, flat_items.data_ptr(), B * LP, that.data_ptr(), a_dt,
+               tinv.data_ptr(), st)
+        n_sets = neg_items.shape[1]
+        n_neg = B * neg_items.shape[2]
+        n_words = (n_neg + 31) // 32
+        ld_neg = n_words * 32
+        neg_ids = neg_items.permute(1, 0, 2).contiguous().view(n_sets, n_neg)   # set-major id lists
+        used_sets = sorted({j.nset for j in self._jobs})
+        nhat, ninv, bits = {}, {}, {}
+        for s in used_sets:
+            nh_ = torch.empty((n_neg, D), dtype=act, device=dev)
+            ni_ = torch.empty(n_neg, dtype=torch.float32, device=dev)
+            L.call("b200rec_gather_l2norm", W.data_ptr(), None, D, neg_ids[s].data_ptr(), n_neg, nh_.data_ptr(), a_dt,
+                   ni_.data_ptr(), st)
+            bt = torch.empty((B * LP, n_words), dtype=torch.int32, device=dev)
+            # false-negative filter bits: that @ nhat^T > nce_thres   (hstu.py:613-614)
+            L.gemm(that, nh_, bt, B * LP, n_neg, D, lda=D, ldb=D, ldc=n_words, epilogue=L.EPI_GT_BITS,
+                   alpha=float(self.nce_thres))
+            nhat[s], ninv[s], bits[s] = nh_, ni_, bt
+        # ---- per-offset token counts -> loss coefficients (hstu.py:704-712, 846-852)
+        lam = self.horizon_discount.to(torch.float32)
+        coefs, cnts = {}, {}
+        for j in self._jobs:
+            key = (j.col, j.w)
+            if key not in coefs:
+                cnt = torch.empty(P, dtype=torch.int32, device=dev)
+                L.call("b200rec_nce_count", tok_b.data_ptr(), tok_pos.data_ptr(), T, LP, P, tok_ok.data_ptr(), n_col,
+                       j.col, cnt.data_ptr(), st)
+                cf = torch.empty(P, dtype=torch.float32, device=dev)
+                L.call("b200rec_nce_coef", cnt.data_ptr(), lam.data_ptr(), float(j.w), P, cf.data_ptr(), st)
+                coefs[key], cnts[key] = cf, cnt
+        # ---- NCE jobs
+        scale = self.logit_scale.data.to(torch.float32)
+        job_out = []
+        for j in self._jobs:
+            hq = j.head if self.medusa_num_layers > 0 else 0
+            q_h = qhat.view(T, Hx * D)[:, hq * D:(hq + 1) * D]
+            logits = torch.empty((T, ld_neg), dtype=torch.float32, device=dev)
+            L.gemm(q_h, nhat[j.nset], logits, T, n_neg, D, lda=Hx * D, ldb=D, ldc=ld_neg)
+            lossv = torch.empty((T, P), dtype=torch.float32, device=dev)
+            g0 = torch.empty((T, P), dtype=torch.float32, device=dev)
+            dsc = torch.empty((T, P), dtype=torch.float32, device=dev)
+            rank0 = torch.empty((T, P), dtype=torch.int32, device=dev)
+            nval = torch.empty((T, P), dtype=torch.int32, device=dev)
+            G = torch.empty((T, ld_neg), dtype=act, device=dev) if need_grad else None
+            L.call("b200rec_nce_loss_fwd", logits.data_ptr(), ld_neg, n_neg, bits[j.nset].data_ptr(), q_h.data_ptr(),
+                   Hx * D, that.data_ptr(), a_dt, D, tok_b.data_ptr(), tok_pos.data_ptr(), T, LP, P, j.p_mask,
+                   tok_ok.data_ptr(), n_col, j.col, coefs[(j.col, j.w)].data_ptr(), scale.data_ptr(),
+                   lossv.data_ptr(), g0.data_ptr(), dsc.data_ptr(), rank0.data_ptr(), nval.data_ptr(), L.ptr(G),
+                   ld_neg, st)
+            per_p = torch.empty(P, dtype=torch.float32, device=dev)
+            L.call("b200rec_colsum", lossv.data_ptr(), L.F32, P, T, P, per_p.data_ptr(), 0, st)
+            job_out.append(dict(job=j, per_p=per_p, g0=g0, dsc=dsc, rank0=rank0, nval=nval, G=G, hq=hq))
+            del logits
+        # ---- total loss + logging scalars (tiny [P] vectors)
+        half = 0.5 if (self.loss == "prior" and self.head_interaction == "additive") else 1.0   # hstu.py:870
+        total = torch.zeros((), dtype=torch.float32, device=dev)
+        logs = {}
+        S = self.num_segment_head
+        seg_acc = {}
+        for o in job_out:
+            j, per_p = o["job"], o["per_p"]
+            total = total + per_p.sum()
+            if j.part == "nce":
+                logs[f"seg_{j.seg}_loss"] = per_p.sum().detach()
+            else:
+                name = f"head_nce_{self.int_to_category[j.cat]}_loss"
+                logs[name] = logs.get(name, 0) + per_p.sum().detach()
+                if self.head_interaction != "additive":
+                    seg_acc[j.seg] = seg_acc.get(j.seg, 0) + per_p.sum().detach()
+        if self.loss == "prior" and self.head_interaction != "additive":
+            for s in range(S):
+                logs[f"seg_{s}_loss"] = logs.get(f"seg_{s}_loss", 0) + seg_acc.get(s, 0)
+        # top-k logging from the rank of the positive (hstu.py:621-629, 720-723, 860-863): the nce part
+        # logs first; the first prior head overwrites it when it has offset-0 tokens (device-side select).
+        cur = None
+        for o in job_out:
+            j = o["job"]
+            if not (j.p_mask & 1) or (j.part == "prior" and j.cat != 0):
+                continue
+            r0, nv = o["rank0"][:, 0], o["nval"][:, 0]
+            sel = nv > 0
+            cntv = sel.sum()
+            den = cntv.clamp_min(1).float()
+            upd = {"nce_samples": (nv.float() * sel).sum() / den}
+            for k in (1, 5, 10, 50, 100):
+                if k > n_neg + 1:
+                    break
+                upd[f"nce_top{k}_acc"] = ((r0 < k) & sel).sum().float() / den
+            if cur is None:
+                cur = upd
+            else:
+                cur = {k: torch.where(cntv > 0, v, cur[k]) for k, v in upd.items()}
+        if cur is not None:
+            logs.update(cur)
+        loss = total * half
+        if need_grad:
+            ctx = dict(B=B, LP=LP, T=T, tok_b=tok_b, tok_pos=tok_pos, seq_off=seq_off, key_valid=key_valid,
+                       tok_index=tok_index, w=w, saved=saved, hd=hd, z=z, yb=yb, qhat=qhat, qinv=qinv, that=that,
+                       tinv=tinv, nhat=nhat, ninv=ninv, neg_ids=neg_ids, job_out=job_out, scale=scale, half=half,
+                       items=items, mask=m, n_neg=n_neg, ld_neg=ld_neg, Hx=Hx, used_sets=used_sets)
+        return loss, logs, ctx
+
+    def _train_backward(self, ctx, gscale):
+        """gscale: device fp32 scalar = upstream grad * (0.5 for additive).  Returns {param: grad}."""
+        D, P, Lc = self._hstu_embedding_dim, self.pred_len, self.max_seq_length
+        B, LP, T, Hx = ctx["B"], ctx["LP"], ctx["T"], ctx["Hx"]
+        dev = ctx["that"].device
+        act, a_dt, st = self._act(), L.dt(self._act()), L.stream()
+        w = ctx["w"]
+        n_neg, ld_neg = ctx["n_neg"], ctx["ld_neg"]
+        grads = {}
+        qhat2 = ctx["qhat"].view(T, Hx * D)
+        dqhat = torch.zeros((T, Hx * D), dtype=torch.float32, device=dev)
+        dthat = torch.zeros((B * LP, D), dtype=torch.float32, device=dev)
+        dnhat = {}
+        written = set()
+        dscale_sum = torch.zeros((), dtype=torch.float32, device=dev)
+        for o in ctx["job_out"]:
+            j, G, g0, hq = o["job"], o["G"], o["g0"], o["hq"]
+            q_h = qhat2[:, hq * D:(hq + 1) * D]
+            dq_h = dqhat[:, hq * D:(hq + 1) * D]
+            nh_ = ctx["nhat"][j.nset]
+            # dq_hat = G @ nhat   (nhat [n_neg, D] = [K, N] -> MN-major B)
+            L.gemm(G, nh_, dq_h, T, D, n_neg, lda=ld_neg, ldb=D, b_major=1, ldc=Hx * D,
+                   epilogue=L.EPI_ACCUM if hq in written else L.EPI_STORE, alpha_dev=gscale)
+            written.add(hq)
+            L.call("b200rec_nce_pos_bwd_q", g0.data_ptr(), ctx["that"].data_ptr(), a_dt, D, ctx["tok_b"].data_ptr(),
+                   ctx["tok_pos"].data_ptr(), T, LP, P, ctx["scale"].data_ptr(), gscale.data_ptr(), dq_h.data_ptr(),
+                   Hx * D, st)
+            # dn_hat += G^T @ q_hat   (both MN-major, K = T)
+            first = j.nset not in dnhat
+            if first:
+                dnhat[j.nset] = torch.empty((n_neg, D), dtype=torch.float32, device=dev)
+            L.gemm(G, q_h, dnhat[j.nset], n_neg, D, T, lda=ld_neg, a_major=1, ldb=Hx * D, b_major=1, ldc=D,
+                   epilogue=L.EPI_STORE if first else L.EPI_ACCUM, alpha_dev=gscale)
+            L.call("b200rec_nce_pos_bwd_t", g0.data_ptr(), q_h.data_ptr(), Hx * D, a_dt, D,
+                   ctx["tok_index"].data_ptr(), B, LP, P, ctx["scale"].data_ptr(), gscale.data_ptr(),
+                   dthat.data_ptr(), st)
+            L.call("b200rec_reduce_sum", o["dsc"].data_ptr(), T * P, 1.0, dscale_sum.data_ptr(), 1, st)
+            o["G"] = None
+        if isinstance(self.logit_scale, nn.Parameter):
+            grads[self.logit_scale] = (dscale_sum * gscale).reshape(self.logit_scale.shape)
+        # ---- through the L2 normalisation of the heads, the ResBlocks, into dy
+        d_hd = torch.empty((T * Hx, D), dtype=torch.float32, device=dev)
+        L.call("b200rec_l2norm_bwd", ctx["qhat"].data_ptr(), a_dt, ctx["qinv"].data_ptr(), dqhat.data_ptr(), T * Hx, D,
+               d_hd.data_ptr(), 0, st)
+        dy = torch.empty((T, D), dtype=torch.float32, device=dev)
+        if self.medusa_num_layers > 0:
+            dz = torch.empty((T, Hx * D), dtype=act, device=dev)
+            L.call("b200rec_resblock_bwd", d_hd.data_ptr(), ctx["z"].data_ptr(), a_dt, T, Hx, D, dz.data_ptr(),
+                   dy.data_ptr(), st)
+            # dy += dz @ Wcat   (Wcat [H*D, D] = [K, N] -> MN-major B)
+            L.gemm(dz, w["heads_w"], dy, T, D, Hx * D, lda=Hx * D, ldb=D, b_major=1, ldc=D, epilogue=L.EPI_ACCUM)
+            # dWcat[H*D, D] = dz^T @ yb  (both MN-major, K = T)
+            dWc = torch.empty((Hx * D, D), dtype=torch.float32, device=dev)
+            L.gemm(dz, ctx["yb"], dWc, Hx * D, D, T, lda=Hx * D, a_major=1, ldb=D, b_major=1, ldc=D)
+            dbc = torch.empty(Hx * D, dtype=torch.float32, device=dev)
+            L.call("b200rec_colsum", dz.data_ptr(), a_dt, Hx * D, T, Hx * D, dbc.data_ptr(), 0, st)
+            for h in range(Hx):
+                lin = self.medusa_head[h][0].linear
+                grads[lin.weight] = dWc[h * D:(h + 1) * D]
+                grads[lin.bias] = dbc[h * D:(h + 1) * D]
+        else:
+            L.call("b200rec_resblock_bwd", d_hd.data_ptr(), None, a_dt, T, Hx, D, None, dy.data_ptr(), st)
+        # ---- body
+        dx0 = self._body_backward(dy, ctx["saved"], w, ctx["seq_off"], ctx["key_valid"], B, T, Lc, Lc, grads)
+        # ---- position embedding (rows 0..L-1 used; row L never, hstu.py:380,640-643)
+        dpos = torch.zeros_like(self.position_embedding.weight.data)
+        L.call("b200rec_pos_emb_grad", dx0.data_ptr(), ctx["tok_index"].data_ptr(), B, LP, Lc, D, dpos.data_ptr(), st)
+        grads[self.position_embedding.weight] = dpos
+        # ---- item embedding: concatenate gradient rows + ids, one sorted-segment reduction
+        items, m = ctx["items"], ctx["mask"]
+        sets = ctx["used_sets"]
+        n_rows = T + B * LP + len(sets) * n_neg
+        rows = torch.empty((n_rows, D), dtype=torch.float32, device=dev)
+        ids = torch.empty(n_rows, dtype=torch.int64, device=dev)
+        rows[:T].copy_(dx0)
+        ids[:T] = items.reshape(-1)[ctx["tok_b"].long() * LP + ctx["tok_pos"].long()]
+        L.call("b200rec_l2norm_bwd", ctx["that"].data_ptr(), a_dt, ctx["tinv"].data_ptr(), dthat.data_ptr(), B * LP, D,
+               rows[T:].data_ptr(), 0, st)
+        tgt_ids = torch.where(m, items, torch.full_like(items, -1))
+        tgt_ids[:, 0] = -1                       # position 0 is never a target
+        ids[T:T + B * LP] = tgt_ids.reshape(-1)
+        off = T + B * LP
+        for s in sets:
+            L.call("b200rec_l2norm_bwd", ctx["nhat"][s].data_ptr(), a_dt, ctx["ninv"][s].data_ptr(),
+                   dnhat[s].data_ptr(), n_neg, D, rows[off:].data_ptr(), 0, st)
+            ids[off:off + n_neg] = ctx["neg_ids"][s]
+            off += n_neg
+        ws_bytes = L.lib().b200rec_scatter_add_workspace_bytes(n_rows)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        uniq_ids = torch.empty(n_rows, dtype=torch.int64, device=dev)
+        uniq_rows = torch.empty((n_rows, D), dtype=torch.float32, device=dev)
+        n_uniq = torch.zeros(1, dtype=torch.int32, device=dev)
+        L.call("b200rec_scatter_add_sorted", ids.data_ptr(), n_rows, rows.data_ptr(), D, uniq_ids.data_ptr(),
+               uniq_rows.data_ptr(), n_uniq.data_ptr(), ws.data_ptr(), ws_bytes, st)
+        self.emb_grad = (uniq_ids, uniq_rows, n_uniq)
+        if not self.sparse_embedding_grad:
+            dense = torch.zeros_like(self.item_embedding.weight.data)
+            L.call("b200rec_rows_to_dense", uniq_ids.data_ptr(), uniq_rows.data_ptr(), n_uniq.data_ptr(), n_rows, D,
+                   dense.data_ptr(), 0, st)
+            grads[self.item_embedding.weight] = dense
+        return grads
+
+    # ------------------------------------------------------------------ eval (hstu.py:874-1021)
+    @torch.no_grad()
+    def compute_item_all(self):
+        W = self.item_embedding.weight.data
+        N, D = W.shape
+        out = torch.empty((N, D), dtype=torch.float32, device=W.device)
+        inv = torch.empty(N, dtype=torch.float32, device=W.device)
+        L.call("b200rec_gather_l2norm", None, W.data_ptr(), D, None, N, out.data_ptr(), L.F32, inv.data_ptr(), L.stream())
+        return out
+
+    @torch.no_grad()
+    def user_heads(self, item_seq):
+        """L2-normalised decode-head embeddings of the last position: act dtype [B, H, D]."""
+        if not item_seq.is_cuda:
+            raise L.B200RecError("b200rec.HSTU.predict needs CUDA tensors (there is no CPU path)")
+        dev = item_seq.device
+        D = self._hstu_embedding_dim
+        B, Ls = item_seq.shape
+        item_seq = item_seq.contiguous()
+        act, a_dt, st = self._act(), L.dt(self._act()), L.stream()
+        tok_b, tok_pos, seq_off, key_valid, T = self._tokens(item_seq != 0, force_last=True)
+        w = self._cast_weights()
+        x = torch.empty((T, D), dtype=torch.float32, device=dev)
+        L.call("b200rec_embed_tokens", self.item_embedding.weight.data_ptr(), self.position_embedding.weight.data_ptr(),
+               item_seq.data_ptr(), tok_b.data_ptr(), tok_pos.data_ptr(), T, Ls, D, x.data_ptr(), st)
+        y, _ = self._body_forward(x, w, seq_off, key_valid, B, T, Ls, Ls, False)
+        last = (seq_off[1:] - 1).long()
+        y_last = torch.empty((B, D), dtype=torch.float32, device=dev)
+        L.call("b200rec_gather_rows", y.data_ptr(), D, last.data_ptr(), B, y_last.data_ptr(), L.F32, st)
+        hd, _, _ = self._heads_forward(y_last, w, B)
+        H = self.medusa_num_heads
+        if hd.shape[1] != H:                       # identity heads: every head is the body output
+            hd = hd.expand(B, H, D).contiguous()
+        U = torch.empty((B * H, D), dtype=act, device=dev)
+        uinv = torch.empty(B * H, dtype=torch.float32, device=dev)
+        L.call("b200rec_gather_l2norm", None, hd.data_ptr(), D, None, B * H, U.data_ptr(), a_dt, uinv.data_ptr(), st)
+        return U.view(B, H, D)
+
+    def _table_hat(self, all_item_feature):
+        """predict() re-normalises the table (hstu.py:974-975); cache the compute-dtype copy."""
+        key = (all_item_feature.data_ptr(), all_item_feature._version, tuple(all_item_feature.shape), self._act())
+        if self._table_cache is None or self._table_cache[0] != key:
+            N, D = all_item_feature.shape
+            feat = all_item_feature.float().contiguous()
+            th = torch.empty((N, D), dtype=self._act(), device=feat.device)
+            inv = torch.empty(N, dtype=torch.float32, device=feat.device)
+            L.call("b200rec_gather_l2norm", None, feat.data_ptr(), D, None, N, th.data_ptr(), L.dt(self._act()),
+                   inv.data_ptr(), L.stream())
+            self._table_cache = (key, th)
+        return self._table_cache[1]
+
+    def eval_masks(self, all_item_tags, target_tags, B, device):
+        """head_cat[H] (category whose item tags gate head h, -1 none), item_tag_bits[N] (bit c = tag c),
+        head_on[B, H] (prior_given_at_test), per hstu.py:982-999."""
+        H, S, C = self.medusa_num_heads, self.num_segment_head, self.num_prior_head
+        if self.loss != "prior":
+            return None, None, None
+        if self.head_interaction == "additive":
+            cats = [-1] * S + list(range(C))
+        else:
+            cats = [h % C for h in range(H)]
+        head_cat = torch.tensor(cats, dtype=torch.int32, device=device)
+        tagsb = all_item_tags.bool()                                   # [C, N]
+        weights = (1 << torch.arange(tagsb.shape[0], device=device, dtype=torch.int64)).unsqueeze(1)
+        item_tag_bits = (tagsb.to(torch.int64) * weights).sum(0).to(torch.int32).contiguous()
+        head_on = None
+        if self.prior_given_at_test:
+            on_c = target_tags[:, :self.given_prior_len].bool().any(dim=1)[:, :C]          # [B, C]
+            if self.head_interaction == "additive":
+                head_on = torch.cat([torch.ones(B, S, dtype=torch.bool, device=device), on_c], dim=1)
+            else:
+                head_on = on_c.repeat(1, S)
+            head_on = head_on.to(torch.uint8).contiguous()
+        return head_cat, item_tag_bits, head_on
+
+    @torch.no_grad()
+    def predict(self, item_seq, time_seq, all_item_feature, all_item_tags, target_tags, save_for_eval=False):
+        """Reference-compatible: returns (scores fp32 [B, H, N] with prior masks, logs, user_embs, head_embs)."""
+        U = self.user_heads(item_seq)
+        B, H, D = U.shape
+        table = self._table_hat(all_item_feature)
+        N = table.shape[0]
+        scores = torch.empty((B * H, N), dtype=torch.float32, device=U.device)
+        L.gemm(U.view(B * H, D), table, scores, B * H, N, D, lda=D, ldb=D, ldc=N)
+        head_cat, bits, head_on = self.eval_masks(all_item_tags, target_tags, B, U.device)
+        if head_cat is not None:
+            L.call("b200rec_apply_score_masks", scores.data_ptr(), N, B, H, N, head_cat.data_ptr(), bits.data_ptr(),
+                   L.ptr(head_on), L.stream())
+        logs = {"num_samples": self.eval_pred_len * B}
+        head_embs = U.float().cpu().numpy() if save_for_eval else None
+        return scores.view(B, H, N), logs, None, head_embs
+
+    @torch.no_grad()
+    def predict_topk(self, item_seq, all_item_feature, all_item_tags, target_tags, history_index=None, K=200,
+                     split_mode="combine", user_chunk=None):
+        """Fused eval entry: masks (prior / id 0 / history) + cross-head merge + top-K without returning
+        the [B, H, N] tensor.  Returns (topk_idx i64 [B,K], topk_val f32 [B,K], topk_head i32 [B,K])."""
+        U = self.user_heads(item_seq)
+        B, H, D = U.shape
+        dev = U.device
+        table = self._table_hat(all_item_feature)
+        N = table.shape[0]
+        head_cat, bits, head_on = self.eval_masks(all_item_tags, target_tags, B, dev)
+        hist_off = hist_items = None
+        if history_index is not None:
+            hu, hi = history_index
+            order = torch.argsort(hu, stable=True)
+            hist_items = hi[order].to(torch.int64).contiguous()
+            counts = torch.bincount(hu, minlength=B)
+            hist_off = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+            hist_off[1:] = counts.cumsum(0).to(torch.int32)
+        idx = torch.empty((B, K), dtype=torch.int64, device=dev)
+        val = torch.empty((B, K), dtype=torch.float32, device=dev)
+        hsrc = torch.empty((B, K), dtype=torch.int32, device=dev)
+        if user_chunk is None:
+            user_chunk = max(1, min(B, int((8 << 30) // max(1, H * N * 4))))
+        mode = 1 if (split_mode == "average" and H > 1) else 0
+        for b0 in range(0, B, user_chunk):
+            b1 = min(B, b0 + user_chunk)
+            nb = b1 - b0
+            scores = torch.empty((nb * H, N), dtype=torch.float32, device=dev)
+            L.gemm(U[b0:b1].reshape(nb * H, D), table, scores, nb * H, N, D, lda=D, ldb=D, ldc=N)
+            ws_bytes = L.lib().b200rec_topk_workspace_bytes(nb, N)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            ho = hist_off[b0:b1 + 1].contiguous() if hist_off is not None else None
+            L.call("b200rec_score_mask_topk", scores.data_ptr(), N, nb, H, N, K, L.ptr(head_cat), L.ptr(bits),
+                   L.ptr(head_on[b0:b1].contiguous() if head_on is not None else None), L.ptr(ho), L.ptr(hist_items),
+                   mode, idx[b0:b1].data_ptr(), val[b0:b1].data_ptr(), hsrc[b0:b1].data_ptr(), ws.data_ptr(),
+                   ws_bytes, L.stream())
+        return idx, val, hsrc
+
+    def get_attention_mask(self, item_seq, bidirectional=False):
+        """hstu.py:1023-1030 (API parity; the kernels take seq_off / key_valid instead)."""
+        keep = (item_seq != 0).unsqueeze(1).unsqueeze(2)
+        if not bidirectional:
+            keep = torch.tril(keep.expand((-1, -1, item_seq.size(-1), -1)))
+        return keep
+
+
+class _TrainStep(torch.autograd.Function):
+    """Whole-model autograd node: forward runs the CUDA forward and keeps activations, backward runs
+    the hand-written backward and hands one gradient per parameter to autograd."""
+
+    @staticmethod
+    def forward(ctx, model, items, neg_items, mask, tags, *params):
+        need_grad = any(p.requires_grad for p in params) and torch.is_grad_enabled()
+        loss, logs, saved = model._train_forward(items, neg_items, mask, tags, need_grad)
+        ctx.model, ctx.saved, ctx.params = model, saved, params
+        ctx.set_materialize_grads(False)
+        model._last_logs = logs
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        model, saved = ctx.model, ctx.saved
+        if g_loss is None or not saved:
+            return (None,) * (5 + len(ctx.params))
+        gscale = (g_loss.reshape(()).to(torch.float32) * saved["half"]).contiguous()
+        grads = model._train_backward(saved, gscale)
+        ctx.saved = None
+        out = []
+        for p in ctx.params:
+            g = grads.get(p)
+            out.append(g if (g is not None and p.requires_grad) else None)
+        return (None, None, None, None, None) + tuple(out)

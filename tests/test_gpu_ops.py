@@ -1,0 +1,437 @@
+"""Per-kernel parity tests through the C ABI (libb200rec.so) against plain PyTorch fp32 references.
+Run on the B200 box:  python -m pytest tests -m gpu -q"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from b200rec import _lib as L  # noqa: E402
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rnd(*shape, dtype=torch.float32, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(dev())
+
+
+# ------------------------------------------------------------------------------------ embedding
+@pytest.mark.parametrize("D,n", [(64, 1000), (1024, 4097), (256, 1)])
+@pytest.mark.parametrize("odt", [torch.float32, torch.bfloat16])
+def test_gather_rows_bit_exact(D, n, odt):
+    table = rnd(5000, D, seed=1)
+    ids = torch.randint(0, 5000, (n,), generator=torch.Generator().manual_seed(2)).to(dev())
+    out = torch.empty(n, D, dtype=odt, device=dev())
+    L.call("b200rec_gather_rows", table.data_ptr(), D, ids.data_ptr(), n, out.data_ptr(), L.dt(out), L.stream())
+    assert torch.equal(out, table[ids].to(odt))
+
+
+def test_gather_rows_empty():
+    table = rnd(10, 64)
+    ids = torch.empty(0, dtype=torch.int64, device=dev())
+    out = torch.empty(0, 64, device=dev())
+    L.call("b200rec_gather_rows", table.data_ptr(), 64, ids.data_ptr(), 0, out.data_ptr(), L.F32, L.stream())
+
+
+def test_embed_tokens():
+    B, LP, D, N = 7, 13, 64, 300
+    table, pos = rnd(N, D, seed=1), rnd(LP, D, seed=2)
+    items = torch.randint(1, N, (B, LP), generator=torch.Generator().manual_seed(3)).to(dev())
+    valid = (torch.rand(B, LP, generator=torch.Generator().manual_seed(4)) < 0.7).to(dev())
+    idx = valid.nonzero()
+    tb, tp = idx[:, 0].int().contiguous(), idx[:, 1].int().contiguous()
+    T = idx.shape[0]
+    x = torch.empty(T, D, device=dev())
+    L.call("b200rec_embed_tokens", table.data_ptr(), pos.data_ptr(), items.data_ptr(), tb.data_ptr(), tp.data_ptr(),
+           T, LP, D, x.data_ptr(), L.stream())
+    ref = table[items[idx[:, 0], idx[:, 1]]] + pos[idx[:, 1]]
+    assert torch.equal(x, ref)
+
+
+@pytest.mark.parametrize("D", [32, 64, 1024])
+def test_gather_l2norm_and_bwd(D):
+    n = 777
+    table = rnd(2000, D, seed=5)
+    ids = torch.randint(0, 2000, (n,), generator=torch.Generator().manual_seed(6)).to(dev())
+    for odt, tol in [(torch.float32, 1e-6), (torch.bfloat16, 1e-2)]:
+        out = torch.empty(n, D, dtype=odt, device=dev())
+        inv = torch.empty(n, device=dev())
+        L.call("b200rec_gather_l2norm", table.data_ptr(), None, D, ids.data_ptr(), n, out.data_ptr(), L.dt(out),
+               inv.data_ptr(), L.stream())
+        rows = table[ids].clone().requires_grad_(True)
+        ref = rows / rows.norm(dim=-1, keepdim=True)
+        assert torch.allclose(out.float(), ref.detach(), atol=tol, rtol=tol)
+        assert torch.allclose(inv, 1 / rows.detach().norm(dim=-1), rtol=1e-5)
+        if odt == torch.float32:
+            g = rnd(n, D, seed=7)
+            ref.backward(g)
+            dx = torch.empty(n, D, device=dev())
+            L.call("b200rec_l2norm_bwd", out.data_ptr(), L.F32, inv.data_ptr(), g.data_ptr(), n, D, dx.data_ptr(), 0,
+                   L.stream())
+            assert torch.allclose(dx, rows.grad, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("n,N,D", [(5000, 300, 64), (20000, 100000, 128), (1, 10, 32), (4096, 50, 1024)])
+def test_scatter_add_sorted_rows_and_determinism(n, N, D):
+    g = torch.Generator().manual_seed(8)
+    ids = torch.randint(-1, N, (n,), generator=g).to(dev())          # includes -1 and 0 (no gradient)
+    rows = rnd(n, D, seed=9)
+    ws_bytes = L.lib().b200rec_scatter_add_workspace_bytes(n)
+    outs = []
+    for _ in range(2):
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev())
+        uid = torch.full((n,), -7, dtype=torch.int64, device=dev())
+        urows = torch.empty(n, D, device=dev())
+        nu = torch.zeros(1, dtype=torch.int32, device=dev())
+        L.call("b200rec_scatter_add_sorted", ids.data_ptr(), n, rows.data_ptr(), D, uid.data_ptr(), urows.data_ptr(),
+               nu.data_ptr(), ws.data_ptr(), ws_bytes, L.stream())
+        k = int(nu.item())
+        outs.append((uid[:k].clone(), urows[:k].clone()))
+    valid = ids > 0
+    ref_ids = torch.unique(ids[valid])                                # sorted ascending
+    assert torch.equal(outs[0][0], ref_ids)                            # bit-exact gradient row set
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])   # bit-reproducible
+    dense = torch.zeros(N, D, device=dev(), dtype=torch.float64)
+    dense.index_add_(0, ids[valid], rows[valid].double())
+    assert torch.allclose(outs[0][1].double(), dense[ref_ids], rtol=1e-5, atol=1e-5)
+    # sequential in-order fp32 sum is the stated summation order: check one multi-row id exactly
+    cnt = torch.bincount(ids[valid], minlength=N)
+    j = int(torch.argmax(cnt))
+    acc = torch.zeros(D, device=dev())
+    for r in rows[ids == j]:
+        acc = acc + r
+    assert torch.equal(outs[0][1][(ref_ids == j).nonzero()[0, 0]], acc)
+    d2 = torch.zeros(N, D, device=dev())
+    nu = torch.tensor([ref_ids.numel()], dtype=torch.int32, device=dev())
+    L.call("b200rec_rows_to_dense", outs[0][0].data_ptr(), outs[0][1].data_ptr(), nu.data_ptr(), n, D, d2.data_ptr(),
+           0, L.stream())
+    assert torch.equal(d2[ref_ids], outs[0][1]) and float(d2.abs().sum()) == float(outs[0][1].abs().sum())
+
+
+# ------------------------------------------------------------------------------------ norms
+@pytest.mark.parametrize("T,D", [(100, 64), (257, 1024), (3, 32), (50, 256)])
+def test_layernorm_fwd_bwd(T, D):
+    x = rnd(T, D, seed=10, scale=2.0)
+    y = torch.empty(T, D, device=dev())
+    mean, rstd = torch.empty(T, device=dev()), torch.empty(T, device=dev())
+    L.call("b200rec_layernorm_fwd", x.data_ptr(), T, D, 1e-6, y.data_ptr(), L.F32, mean.data_ptr(), rstd.data_ptr(),
+           L.stream())
+    xr = x.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, [D], eps=1e-6)
+    assert torch.allclose(y, ref.detach(), rtol=1e-5, atol=1e-5)
+    dy, res = rnd(T, D, seed=11), rnd(T, D, seed=12)
+    ref.backward(dy)
+    dx = torch.empty(T, D, device=dev())
+    L.call("b200rec_layernorm_bwd", dy.data_ptr(), L.F32, D, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), T, D,
+           res.data_ptr(), dx.data_ptr(), L.stream())
+    assert torch.allclose(dx, xr.grad + res, rtol=1e-4, atol=1e-5)
+    yb = torch.empty(T, D, dtype=torch.bfloat16, device=dev())
+    L.call("b200rec_layernorm_fwd", x.data_ptr(), T, D, 1e-6, yb.data_ptr(), L.BF16, mean.data_ptr(), rstd.data_ptr(),
+           L.stream())
+    assert torch.allclose(yb.float(), ref.detach(), rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("T,D", [(90, 64), (130, 1024)])
+def test_gate_ln_fwd_bwd(T, D):
+    act = rnd(T, 4 * D, seed=13)
+    pre = rnd(T, 4 * D, seed=14)
+    a = rnd(T, D, seed=15)
+    oin = torch.empty(T, D, device=dev())
+    mean, rstd = torch.empty(T, device=dev()), torch.empty(T, device=dev())
+    L.call("b200rec_gate_ln_fwd", act.data_ptr(), 4 * D, a.data_ptr(), T, D, 1e-6, oin.data_ptr(), L.F32,
+           mean.data_ptr(), rstd.data_ptr(), L.stream())
+    pr = pre[:, :D].clone().requires_grad_(True)
+    ar = a.clone().requires_grad_(True)
+    # reference: u = silu(pre_u) would tie u and pre; the kernel takes u and pre_u separately, so build
+    # the reference the same way: oin = u * LN(a), and d_pre_u = d_u * silu'(pre_u)
+    u = act[:, :D].clone().requires_grad_(True)
+    ref = u * torch.nn.functional.layer_norm(ar, [D], eps=1e-6)
+    assert torch.allclose(oin, ref.detach(), rtol=1e-5, atol=1e-5)
+    g = rnd(T, D, seed=16)
+    ref.backward(g)
+    d_pre = torch.zeros(T, 4 * D, device=dev())
+    da = torch.empty(T, D, device=dev())
+    L.call("b200rec_gate_ln_bwd", g.data_ptr(), act.data_ptr(), pre.data_ptr(), 4 * D, a.data_ptr(), mean.data_ptr(),
+           rstd.data_ptr(), T, D, d_pre.data_ptr(), da.data_ptr(), L.F32, L.stream())
+    sg = torch.sigmoid(pre[:, :D])
+    silu_grad = sg * (1 + pre[:, :D] * (1 - sg))
+    assert torch.allclose(da, ar.grad, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(d_pre[:, :D], u.grad * silu_grad, rtol=1e-4, atol=1e-5)
+    assert float(d_pre[:, D:].abs().sum()) == 0.0
+
+
+def test_cast_colsum_reduce():
+    x = rnd(1234, 96, seed=17)
+    y = torch.empty(1234, 96, dtype=torch.bfloat16, device=dev())
+    L.call("b200rec_cast", x.data_ptr(), x.numel(), y.data_ptr(), L.BF16, L.stream())
+    assert torch.equal(y, x.to(torch.bfloat16))
+    out = torch.empty(96, device=dev())
+    L.call("b200rec_colsum", x.data_ptr(), L.F32, 96, 1234, 96, out.data_ptr(), 0, L.stream())
+    assert torch.allclose(out, x.sum(0), rtol=1e-4, atol=1e-4)
+    s = torch.zeros((), device=dev())
+    L.call("b200rec_reduce_sum", x.data_ptr(), x.numel(), 0.5, s.data_ptr(), 0, L.stream())
+    assert abs(float(s) - 0.5 * float(x.double().sum())) < 1e-2
+
+
+# ------------------------------------------------------------------------------------ GEMM
+def _gemm_ref(A, B, a_major, b_major):
+    Am = A.float() if a_major == 0 else A.float().t()
+    Bm = B.float() if b_major == 0 else B.float().t()
+    return Am @ Bm.t()
+
+
+def _mk_operands(M, N, K, a_major, b_major, dtype, seed):
+    A = rnd(M, K, seed=seed, dtype=dtype) if a_major == 0 else rnd(K, M, seed=seed, dtype=dtype)
+    B = rnd(N, K, seed=seed + 1, dtype=dtype) if b_major == 0 else rnd(K, N, seed=seed + 1, dtype=dtype)
+    return A, B
+
+
+SHAPES = [(128, 256, 64), (256, 512, 1024), (100, 72, 40), (6400, 1024, 1024), (333, 200, 136), (64, 4096, 512),
+          (1000, 1024, 2000)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("a_major,b_major", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_store_all_majors(M, N, K, a_major, b_major, dtype):
+    if dtype == torch.bfloat16:   # TMA needs 16-byte pitches
+        M, N, K = (M + 7) // 8 * 8, (N + 7) // 8 * 8, (K + 7) // 8 * 8
+    A, B = _mk_operands(M, N, K, a_major, b_major, dtype, seed=20)
+    Cm = torch.full((M, N), float("nan"), device=dev())
+    L.gemm(A, B, Cm, M, N, K, lda=A.shape[1], ldb=B.shape[1], ldc=N, a_major=a_major, b_major=b_major)
+    ref = _gemm_ref(A, B, a_major, b_major)
+    tol = 1e-4 if dtype == torch.float32 else 2e-3
+    err = (Cm - ref).abs().max().item() / max(1.0, ref.abs().max().item())
+    assert err < tol, f"rel err {err}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("bn", [128, 256])
+def test_gemm_epilogues(dtype, bn):
+    L.lib().b200rec_gemm_force_bn(bn)
+    try:
+        M, N, K = 520, 768, 256
+        A, B = _mk_operands(M, N, K, 0, 0, dtype, seed=30)
+        ref = _gemm_ref(A, B, 0, 0)
+        tol = dict(rtol=1e-4, atol=1e-4) if dtype == torch.float32 else dict(rtol=2e-2, atol=5e-2)
+        # SILU_DUAL
+        C1 = torch.empty(M, N, dtype=dtype, device=dev())
+        C2 = torch.empty(M, N, dtype=dtype, device=dev())
+        L.gemm(A, B, C1, M, N, K, lda=K, ldb=K, ldc=N, epilogue=L.EPI_SILU_DUAL, C2=C2, ldc2=N)
+        assert torch.allclose(C2.float(), ref, **tol)
+        assert torch.allclose(C1.float(), torch.nn.functional.silu(ref), **tol)
+        # BIAS_RESID
+        bias, resid = rnd(N, seed=31), rnd(M, N, seed=32)
+        C3 = torch.empty(M, N, device=dev())
+        L.gemm(A, B, C3, M, N, K, lda=K, ldb=K, ldc=N, epilogue=L.EPI_BIAS_RESID, bias=bias, resid=resid, ldr=N)
+        assert torch.allclose(C3, ref + bias + resid, **tol)
+        # RESBLOCK with residual shared by 3 column blocks of width 256
+        r2 = rnd(M, 256, seed=33)
+        C4 = torch.empty(M, N, device=dev())
+        Z = torch.empty(M, N, dtype=dtype, device=dev())
+        L.gemm(A, B, C4, M, N, K, lda=K, ldb=K, ldc=N, epilogue=L.EPI_RESBLOCK, bias=bias, resid=r2, ldr=256, C2=Z,
+               ldc2=N, n_split=256)
+        z = ref + bias
+        assert torch.allclose(Z.float(), z, **tol)
+        assert torch.allclose(C4, r2.repeat(1, 3) + torch.nn.functional.silu(z), **tol)
+        # ACCUM with device alpha
+        C5 = rnd(M, N, seed=34)
+        base = C5.clone()
+        adev = torch.tensor(0.25, device=dev())
+        L.gemm(A, B, C5, M, N, K, lda=K, ldb=K, ldc=N, epilogue=L.EPI_ACCUM, alpha=2.0, alpha_dev=adev)
+        assert torch.allclose(C5, base + 0.5 * ref, **tol)
+        # GT_BITS
+        n_words = (N + 31) // 32
+        bits = torch.empty(M, n_words, dtype=torch.int32, device=dev())
+        thr = 3.0
+        L.gemm(A, B, bits, M, N, K, lda=K, ldb=K, ldc=n_words, epilogue=L.EPI_GT_BITS, alpha=thr)
+        got = ((bits.unsqueeze(-1) >> torch.arange(32, device=dev())) & 1).reshape(M, n_words * 32)[:, :N].bool()
+        want = ref > thr
+        near = (ref - thr).abs() < (1e-3 if dtype == torch.float32 else 0.1)
+        assert bool(((got == want) | near).all())
+    finally:
+        L.lib().b200rec_gemm_force_bn(0)
+
+
+def test_gemm_strided_views_bf16():
+    """A and C as column slices of wider buffers (q_hat head slices, d_qhat slices)."""
+    T, H, D, Nn = 300, 3, 64, 96
+    q = rnd(T, H * D, seed=40, dtype=torch.bfloat16)
+    neg = rnd(Nn, D, seed=41, dtype=torch.bfloat16)
+    out = torch.zeros(T, H * Nn, device=dev())
+    for h in range(H):
+        L.gemm(q[:, h * D:], neg, out[:, h * Nn:], T, Nn, D, lda=H * D, ldb=D, ldc=H * Nn)
+    ref = torch.cat([q[:, h * D:(h + 1) * D].float() @ neg.float().t() for h in range(H)], dim=1)
+    assert torch.allclose(out, ref, rtol=2e-2, atol=2e-2)
+
+
+# ------------------------------------------------------------------------------------ attention
+def _attn_ref(act, seq_off, key_valid, nh, dh, n_pad):
+    D = nh * dh
+    out = torch.zeros(act.shape[0], D, device=act.device, dtype=act.dtype)
+    for b in range(seq_off.numel() - 1):
+        s, e = int(seq_off[b]), int(seq_off[b + 1])
+        if e == s:
+            continue
+        l = e - s
+        v, q, k = act[s:e, D:2 * D], act[s:e, 2 * D:3 * D], act[s:e, 3 * D:]
+        qh, kh, vh = [t.reshape(l, nh, dh).permute(1, 0, 2) for t in (q, k, v)]
+        A = torch.nn.functional.silu(qh @ kh.transpose(-1, -2)) / n_pad
+        keep = torch.tril(torch.ones(l, l, device=act.device, dtype=torch.bool)) & key_valid[s:e].bool()[None, :]
+        A = A * keep
+        out[s:e] = (A @ vh).permute(1, 0, 2).reshape(l, D)
+    return out
+
+
+@pytest.mark.parametrize("nh,dh,lens", [(2, 16, [5, 0, 12, 1]), (1, 32, [20, 7]), (4, 64, [50, 33, 50, 2, 64, 65]),
+                                        (2, 64, [150, 130])])
+def test_hstu_attention_fwd_bwd(nh, dh, lens):
+    D = nh * dh
+    T = sum(lens)
+    B = len(lens)
+    n_pad = max(max(lens), 1)
+    seq_off = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev())
+    key_valid = (torch.rand(T, generator=torch.Generator().manual_seed(50)) < 0.9).to(torch.uint8).to(dev())
+    pre = rnd(T, 4 * D, seed=51, scale=0.7)
+    pre_r = pre.clone().requires_grad_(True)
+    act_r = torch.nn.functional.silu(pre_r)
+    act = act_r.detach().contiguous()
+    out = torch.empty(T, D, device=dev())
+    sl = lambda t, j: t[:, j * D:(j + 1) * D]
+    L.call("b200rec_hstu_attn_fwd", sl(act, 2).data_ptr(), sl(act, 3).data_ptr(), sl(act, 1).data_ptr(), 4 * D, L.F32,
+           seq_off.data_ptr(), key_valid.data_ptr(), B, T, nh, dh, 1.0 / n_pad, max(lens), out.data_ptr(), L.stream())
+    ref = _attn_ref(act_r, seq_off, key_valid, nh, dh, n_pad)
+    assert torch.allclose(out, ref.detach(), rtol=1e-4, atol=1e-5)
+    g = rnd(T, D, seed=52)
+    ref.backward(g)
+    d_pre = torch.zeros(T, 4 * D, device=dev())
+    L.call("b200rec_hstu_attn_bwd", sl(act, 2).data_ptr(), sl(act, 3).data_ptr(), sl(act, 1).data_ptr(),
+           sl(pre, 2).data_ptr(), sl(pre, 3).data_ptr(), sl(pre, 1).data_ptr(), 4 * D, L.F32, seq_off.data_ptr(),
+           key_valid.data_ptr(), B, T, nh, dh, 1.0 / n_pad, max(lens), g.data_ptr(), sl(d_pre, 2).data_ptr(),
+           sl(d_pre, 3).data_ptr(), sl(d_pre, 1).data_ptr(), L.stream())
+    assert torch.allclose(d_pre[:, D:], pre_r.grad[:, D:], rtol=1e-3, atol=1e-5)
+    assert float(d_pre[:, :D].abs().sum()) == 0.0
+    # bf16 activations, fp32 accumulation
+    actb, preb = act.to(torch.bfloat16), pre.to(torch.bfloat16)
+    outb = torch.empty(T, D, device=dev())
+    L.call("b200rec_hstu_attn_fwd", sl(actb, 2).data_ptr(), sl(actb, 3).data_ptr(), sl(actb, 1).data_ptr(), 4 * D,
+           L.BF16, seq_off.data_ptr(), key_valid.data_ptr(), B, T, nh, dh, 1.0 / n_pad, max(lens), outb.data_ptr(),
+           L.stream())
+    assert torch.allclose(outb, ref.detach(), rtol=5e-2, atol=5e-3)
+
+
+# ------------------------------------------------------------------------------------ top-K / hit matrix
+@pytest.mark.parametrize("B,H,N,K", [(3, 1, 1000, 20), (4, 5, 5000, 200), (2, 12, 70000, 200)])
+def test_score_mask_topk_matches_torch(B, H, N, K):
+    scores = rnd(B * H, N, seed=60)
+    C = 4
+    tags = (torch.rand(N, C, generator=torch.Generator().manual_seed(61)) < 0.5)
+    bits = (tags.long() * (1 << torch.arange(C))).sum(1).to(torch.int32).to(dev())
+    head_cat = torch.tensor([(-1 if h % 3 == 0 else h % C) for h in range(H)], dtype=torch.int32, device=dev())
+    head_on = (torch.rand(B, H, generator=torch.Generator().manual_seed(62)) < 0.8).to(torch.uint8).to(dev())
+    head_on[:, 0] = 1
+    hu = torch.randint(0, B, (50,), generator=torch.Generator().manual_seed(63))
+    hi = torch.randint(1, N, (50,), generator=torch.Generator().manual_seed(64))
+    order = torch.argsort(hu, stable=True)
+    hist_items = hi[order].to(dev())
+    hist_off = torch.zeros(B + 1, dtype=torch.int32)
+    hist_off[1:] = torch.bincount(hu, minlength=B).cumsum(0)
+    hist_off = hist_off.to(dev())
+    idx = torch.empty(B, K, dtype=torch.int64, device=dev())
+    val = torch.empty(B, K, device=dev())
+    hs = torch.empty(B, K, dtype=torch.int32, device=dev())
+    wsb = L.lib().b200rec_topk_workspace_bytes(B, N)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev())
+    L.call("b200rec_score_mask_topk", scores.data_ptr(), N, B, H, N, K, head_cat.data_ptr(), bits.data_ptr(),
+           head_on.data_ptr(), hist_off.data_ptr(), hist_items.data_ptr(), 0, idx.data_ptr(), val.data_ptr(),
+           hs.data_ptr(), ws.data_ptr(), wsb, L.stream())
+    s = scores.view(B, H, N).clone()
+    tg = tags.to(dev())
+    for h in range(H):
+        c = int(head_cat[h])
+        if c >= 0:
+            s[:, h, ~tg[:, c]] = float("-inf")
+    s.masked_fill_(~head_on.bool().unsqueeze(-1), float("-inf"))
+    s[:, :, 0] = float("-inf")
+    s[hu.to(dev()), :, hi.to(dev())] = float("-inf")
+    mx, am = s.max(dim=1)
+    v2, i2 = torch.topk(mx, K, dim=-1)
+    assert torch.equal(idx, i2)                       # tie-free random scores: ids exact, order exact
+    assert torch.equal(val, v2)
+    assert torch.equal(hs.long(), torch.gather(am, 1, i2))
+
+
+def test_topk_ties_and_neg_inf_rule():
+    """Tie rule: value desc, then item id asc; -inf fillers enter by ascending id when < K finite."""
+    B, H, N, K = 2, 1, 500, 16
+    scores = torch.full((B, N), float("-inf"), device=dev())
+    scores[0, [7, 9, 300]] = torch.tensor([1.0, 1.0, 2.0], device=dev())
+    scores[1, 10:40] = 0.5
+    idx = torch.empty(B, K, dtype=torch.int64, device=dev())
+    val = torch.empty(B, K, device=dev())
+    hs = torch.empty(B, K, dtype=torch.int32, device=dev())
+    wsb = L.lib().b200rec_topk_workspace_bytes(B, N)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev())
+    L.call("b200rec_score_mask_topk", scores.data_ptr(), N, B, H, N, K, None, None, None, None, None, 0,
+           idx.data_ptr(), val.data_ptr(), hs.data_ptr(), ws.data_ptr(), wsb, L.stream())
+    assert idx[0].tolist() == [300, 7, 9] + [i for i in range(N) if i not in (7, 9, 300)][:K - 3]
+    assert idx[1].tolist() == list(range(10, 10 + K))
+
+
+def test_hit_matrix_quirks():
+    from oracle import hstu_oracle as orc
+    B, K, Pe = 6, 20, 8
+    g = torch.Generator().manual_seed(70)
+    topk = torch.stack([torch.randperm(60, generator=g)[:K] for _ in range(B)]).to(dev())
+    pos = torch.randint(0, 60, (B, Pe), generator=g)
+    pos[0, 3] = pos[0, 1]                      # duplicate targets exercise the pos_len quirk
+    plist = [0, 3, 7]
+    import numpy as np
+    pl = np.asarray(plist, dtype=np.int32)
+    out = torch.empty(len(plist), B, K + 1, dtype=torch.int32, device=dev())
+    posd = pos.to(dev())
+    L.call("b200rec_hit_matrix", topk.data_ptr(), posd.data_ptr(), B, K, Pe, pl.ctypes.data, len(plist),
+           out.data_ptr(), L.stream())
+    ref = orc.hit_matrices(topk.cpu().numpy(), pos.numpy(), plist)
+    for q, p in enumerate(plist):
+        assert (out[q].cpu().numpy() == ref[p]).all()
+
+
+# ------------------------------------------------------------------------------------ optimizer
+def test_adamw_matches_torch():
+    p0, g = rnd(1001, seed=80), rnd(1001, seed=81)
+    p_ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([p_ref], lr=1e-2, weight_decay=0.1)
+    p, m, v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    for step in range(1, 4):
+        p_ref.grad = g * step
+        opt.step()
+        gs = (g * step).contiguous()
+        L.call("b200rec_adamw", p.data_ptr(), m.data_ptr(), v.data_ptr(), gs.data_ptr(), p.numel(), 1e-2, 0.9, 0.999,
+               1e-8, 0.1, step, 1.0, L.stream())
+    assert torch.allclose(p, p_ref.data, rtol=1e-5, atol=1e-6)
+
+
+def test_adamw_rows_dense_equivalent():
+    N, D = 300, 64
+    p0 = rnd(N, D, seed=82)
+    ids = torch.tensor([5, 17, 299], device=dev())
+    rows = rnd(3, D, seed=83)
+    p_ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([p_ref], lr=1e-2, weight_decay=0.01)
+    p, m, v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    slot = torch.empty(N, dtype=torch.int32, device=dev())
+    nu = torch.tensor([3], dtype=torch.int32, device=dev())
+    for step in range(1, 4):
+        dense = torch.zeros(N, D, device=dev())
+        dense[ids] = rows * step
+        p_ref.grad = dense
+        opt.step()
+        r = (rows * step).contiguous()
+        L.call("b200rec_adamw_rows", p.data_ptr(), m.data_ptr(), v.data_ptr(), N, D, ids.data_ptr(), r.data_ptr(),
+               nu.data_ptr(), slot.data_ptr(), 1e-2, 0.9, 0.999, 1e-8, 0.01, step, 1.0, L.stream())
+    assert torch.allclose(p, p_ref.data, rtol=1e-5, atol=1e-6)
