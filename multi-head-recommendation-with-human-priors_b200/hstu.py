@@ -370,7 +370,8 @@ class HSTU(nn.Module):
             raise NotImplementedError("hidden_dropout_prob > 0 in training mode is not built; use model.eval() "
                                       "or hidden_dropout_prob=0 (parity runs do the same, SURVEY App. C)")
         params = [p for p in self.parameters()]
-        loss = _TrainStep.apply(self, items, neg_items, mask, tags, *params)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        loss = _TrainStep.apply(self, need_grad, items, neg_items, mask, tags, *params)
         out = defaultdict(float)
         out.update(self._last_logs)
         out["loss"] = loss
@@ -760,8 +761,7 @@ class _TrainStep(torch.autograd.Function):
     the hand-written backward and hands one gradient per parameter to autograd."""
 
     @staticmethod
-    def forward(ctx, model, items, neg_items, mask, tags, *params):
-        need_grad = any(p.requires_grad for p in params) and torch.is_grad_enabled()
+    def forward(ctx, model, need_grad, items, neg_items, mask, tags, *params):
         loss, logs, saved = model._train_forward(items, neg_items, mask, tags, need_grad)
         ctx.model, ctx.saved, ctx.params = model, saved, params
         ctx.set_materialize_grads(False)
@@ -772,7 +772,7 @@ class _TrainStep(torch.autograd.Function):
     def backward(ctx, g_loss):
         model, saved = ctx.model, ctx.saved
         if g_loss is None or not saved:
-            return (None,) * (5 + len(ctx.params))
+            return (None,) * (6 + len(ctx.params))
         gscale = (g_loss.reshape(()).to(torch.float32) * saved["half"]).contiguous()
         grads = model._train_backward(saved, gscale)
         ctx.saved = None
@@ -780,4 +780,4 @@ class _TrainStep(torch.autograd.Function):
         for p in ctx.params:
             g = grads.get(p)
             out.append(g if (g is not None and p.requires_grad) else None)
-        return (None, None, None, None, None) + tuple(out)
+        return (None, None, None, None, None, None) + tuple(out)

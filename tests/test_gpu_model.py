@@ -123,7 +123,7 @@ def _eval_inputs(fx, cfg):
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
 def test_eval_matches_reference(name, dtype):
     fx = load_golden(name)
     cfg, model = build(fx, dtype)
