@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--eval-users", type=int, default=256)
+    ap.add_argument("--profile", action="store_true", help="print a per-kernel time table of one step (torch.profiler)")
     return ap.parse_args()
 
 
@@ -228,6 +229,13 @@ def main():
     for i in range(args.warmup):
         step(dev_batches[i % n_batches])
     barrier()
+    if args.profile and rank == 0:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step(dev_batches[0])
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=60),
+              file=sys.stderr)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()

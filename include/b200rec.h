@@ -97,9 +97,11 @@ int b200rec_gate_ln_bwd(const void* d_oin, const void* u, const void* pre_u, int
                         int act_dtype, void* stream);
 /* y = cast(x) elementwise, n elements (fp32 -> act dtype). */
 int b200rec_cast(const float* x, int64_t n, void* y, int y_dtype, void* stream);
-/* col_sum[j] = sum_i x[i, j]  (deterministic two-stage), x act dtype or fp32, ld = ldx */
+/* col_sum[j] = sum_i x[i, j]  (deterministic two-stage: 256-row slabs, then slabs in ascending
+ * order), x act dtype or fp32, ld = ldx.  workspace: b200rec_colsum_workspace_bytes(rows, cols). */
+size_t b200rec_colsum_workspace_bytes(int rows, int cols);
 int b200rec_colsum(const void* x, int x_dtype, int ldx, int rows, int cols, float* out,
-                   int accumulate, void* stream);
+                   int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ GEMM (a4,a7,a10,a15)
  * C[M,N] = epilogue( A[M,K] * B[N,K]^T ).  Replaces torch.matmul / nn.Linear / einsum at
@@ -114,7 +116,8 @@ enum {
   B200REC_EPI_SILU_DUAL = 2,  /* C2 = acc (pre-activation), C = silu(acc)                   */
   B200REC_EPI_BIAS_RESID = 3, /* C = acc + bias[n] + resid[m, n]                            */
   B200REC_EPI_RESBLOCK = 4,   /* z = acc + bias[n]; C2 = z; C = resid[m, n % n_split] + silu(z) */
-  B200REC_EPI_GT_BITS = 5     /* C is uint32 [M, N/32]: bit (n%32) of word n/32 = acc > alpha */
+  B200REC_EPI_GT_BITS = 5     /* C is uint32 [M, N/32]: bit (n%32) of word n/32 = acc > alpha;
+                                 optional C2 = u8[M], set to 1 for rows with any bit (zero it first) */
 };
 typedef struct {
   int M, N, K;
@@ -163,9 +166,13 @@ int b200rec_hstu_attn_bwd(const void* q, const void* k, const void* v, const voi
  * dscale[t*P+p] = coef * sum_k softmax-grad_k * z_k, rank0[t*P+p] = #negatives with logit > pos
  * (or -1), nvalid[t*P+p] = #unmasked logits incl. pos.  If G != NULL also writes
  * G[t, j] = tau * sum_p coef_p * softmax_p[j] (act dtype), the gradient w.r.t. the cosine logits.
- * coef[p] (device fp32[P]) = lambda_p * w_c / max(cnt_p, 1)  (hstu.py:708-712, 850-852). */
+ * coef[p] (device fp32[P]) = lambda_p * w_c / max(cnt_p, 1)  (hstu.py:708-712, 850-852).
+ * row_any[B*LP] (u8, from the GT_BITS epilogue's C2: row has any filtered negative) and pos_ws
+ * (fp32 [T*P] scratch) enable the register-resident fast path (n_neg <= 8192, n_neg % 4 == 0);
+ * pass NULL for either to use the generic shared-memory kernel. */
 int b200rec_nce_loss_fwd(const float* logits, int64_t ld_logits, int n_neg,
-                         const uint32_t* same_bits, const void* q_hat, int64_t ldq,
+                         const uint32_t* same_bits, const uint8_t* row_any, float* pos_ws,
+                         const void* q_hat, int64_t ldq,
                          const void* t_hat, int act_dtype, int D, const int32_t* tok_b,
                          const int32_t* tok_pos, int T, int LP, int P, uint32_t p_mask,
                          const uint8_t* tok_ok, int tok_ok_ld, int tok_ok_col, const float* coef,

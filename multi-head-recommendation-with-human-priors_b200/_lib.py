@@ -58,14 +58,15 @@ _SIGS = {
     "b200rec_gate_ln_fwd": (C.c_int, [_P, _I, _P, _I, _I, _F, _P, _I, _P, _P, _P]),
     "b200rec_gate_ln_bwd": (C.c_int, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _I, _P]),
     "b200rec_cast": (C.c_int, [_P, _L, _P, _I, _P]),
-    "b200rec_colsum": (C.c_int, [_P, _I, _I, _I, _I, _P, _I, _P]),
+    "b200rec_colsum_workspace_bytes": (_Z, [_I, _I]),
+    "b200rec_colsum": (C.c_int, [_P, _I, _I, _I, _I, _P, _I, _P, _Z, _P]),
     "b200rec_reduce_sum": (C.c_int, [_P, _L, _F, _P, _I, _P]),
     "b200rec_gemm": (C.c_int, [C.POINTER(GemmArgs), _P]),
     "b200rec_gemm_force_bn": (None, [_I]),
     "b200rec_hstu_attn_fwd": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P]),
     "b200rec_hstu_attn_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P,
                                         _P, _P, _P, _P]),
-    "b200rec_nce_loss_fwd": (C.c_int, [_P, _L, _I, _P, _P, _L, _P, _I, _I, _P, _P, _I, _I, _I, C.c_uint32,
+    "b200rec_nce_loss_fwd": (C.c_int, [_P, _L, _I, _P, _P, _P, _P, _L, _P, _I, _I, _P, _P, _I, _I, _I, C.c_uint32,
                                        _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
     "b200rec_nce_count": (C.c_int, [_P, _P, _I, _I, _I, _P, _I, _I, _P, _P]),
     "b200rec_nce_coef": (C.c_int, [_P, _P, _F, _I, _P, _P]),
@@ -141,7 +142,8 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epilogue=
         raise B200RecError("gemm: A and B dtypes differ")
     a.C, a.ldc = C_out.data_ptr(), ldc
     a.c_dtype = F32 if epilogue == EPI_GT_BITS else (dt(C_out) if c_dtype is None else c_dtype)
-    a.C2, a.ldc2, a.c2_dtype = ptr(C2), ldc2, (dt(C2) if C2 is not None else F32)
+    a.C2, a.ldc2 = ptr(C2), ldc2
+    a.c2_dtype = dt(C2) if (C2 is not None and epilogue != EPI_GT_BITS) else F32
     a.epilogue, a.alpha = epilogue, alpha
     a.alpha_dev = ptr(alpha_dev)
     a.bias, a.resid, a.ldr = ptr(bias), ptr(resid), ldr
@@ -155,3 +157,11 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epilogue=
         gemm_timing.append((e0, e1, 2.0 * M * N * K))
         return
     _check(lib().b200rec_gemm(C.byref(a), stream()), "b200rec_gemm")
+
+
+def colsum(x, rows, cols, ldx, out, accumulate=False):
+    """out[j] (+)= sum_i x[i, j]; deterministic."""
+    nbytes = lib().b200rec_colsum_workspace_bytes(rows, cols)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    call("b200rec_colsum", x.data_ptr(), dt(x), ldx, rows, cols, out.data_ptr(), 1 if accumulate else 0,
+         ws.data_ptr(), nbytes, stream())

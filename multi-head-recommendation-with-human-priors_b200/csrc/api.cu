@@ -37,6 +37,18 @@ int b200rec_gemm(const b200rec_gemm_args* a, void* stream) {
   ep.bias = a->bias; ep.resid = a->resid; ep.ldr = a->ldr;
   ep.n_split = a->n_split; ep.c_split_stride = a->c_split_stride; ep.c2_split_stride = a->c2_split_stride;
   ep.M = a->M; ep.N = a->N;
+  {
+    // vector (4-element) epilogue access is legal when every touched pointer is 16-byte aligned for
+    // fp32 / 8-byte for bf16 and every leading dimension is a multiple of 4 elements
+    auto ok = [](const void* ptr, int64_t ld, int dtype) {
+      if (!ptr) return true;
+      uintptr_t al = dtype == B200REC_F32 ? 16 : 8;
+      return ((uintptr_t)ptr % al) == 0 && (ld % 4) == 0;
+    };
+    ep.vec_ok = ok(a->C, a->ldc, a->c_dtype) && ok(a->C2, a->ldc2, a->c2_dtype) && ok(a->bias, 0, B200REC_F32) &&
+                ok(a->resid, a->ldr, B200REC_F32) && (a->n_split % 4 == 0) && a->c_split_stride % 4 == 0 &&
+                a->c2_split_stride % 4 == 0 && a->epilogue != B200REC_EPI_GT_BITS;
+  }
   B200_CHECK_ARG(a->C != nullptr, "gemm: null C");
   if (a->epilogue == B200REC_EPI_SILU_DUAL) B200_CHECK_ARG(a->C2 != nullptr, "gemm: SILU_DUAL needs C2");
   if (a->epilogue == B200REC_EPI_RESBLOCK) B200_CHECK_ARG(a->resid != nullptr, "gemm: RESBLOCK needs resid");

@@ -11,6 +11,7 @@ struct EpiParams {
   const float* resid; int64_t ldr;
   int n_split; int64_t c_split_stride, c2_split_stride;
   int M, N;
+  int vec_ok;  // host-checked: every pointer / leading dimension allows 4-element vector access
 };
 
 __device__ __forceinline__ void epi_store_scalar(void* base, int dtype, int64_t off, float v) {
@@ -56,7 +57,10 @@ __device__ __forceinline__ void epi_apply_scalar(const EpiParams& p, int m, int 
       break;
     }
     case B200REC_EPI_GT_BITS:
-      if (acc > p.alpha) atomicOr((unsigned int*)p.C + (int64_t)m * p.ldc + (n >> 5), 1u << (n & 31));
+      if (acc > p.alpha) {
+        atomicOr((unsigned int*)p.C + (int64_t)m * p.ldc + (n >> 5), 1u << (n & 31));
+        if (p.C2) ((uint8_t*)p.C2)[m] = 1;  // "row has a set bit" flag (caller zero-fills)
+      }
       break;
   }
 }
@@ -168,7 +172,124 @@ __device__ __forceinline__ void epi_apply_chunk32(const EpiParams& p, int m, int
 #pragma unroll
       for (int i = 0; i < 32; ++i) w |= (i < n_valid && acc[i] > p.alpha) ? (1u << i) : 0u;
       ((uint32_t*)p.C)[(int64_t)m * p.ldc + (n0 >> 5)] = w;
+      if (w != 0u && p.C2) ((uint8_t*)p.C2)[m] = 1;  // "row has a set bit" flag (caller zero-fills)
       break;
     }
+  }
+}
+
+// 4 consecutive columns [n, n+4) of row m held by one lane (coalesced phase of the tcgen05 epilogue:
+// 8 lanes cover 128 contiguous bytes of a row, so every global access is a full-line transaction).
+template <typename T>
+__device__ __forceinline__ void st4_dt(T* p, const float (&v)[4]) { store4<T>(p, v); }
+
+__device__ __forceinline__ void store4_dt(void* base, int dtype, int64_t off, const float (&v)[4]) {
+  if (dtype == B200REC_F32) store4<float>((float*)base + off, v);
+  else store4<bf16>((bf16*)base + off, v);
+}
+
+// out-of-line tail / unaligned path keeps the hot epilogue small (instruction-cache resident)
+static __device__ __noinline__ void epi_apply_tail4(const EpiParams& p, int m, int n, float v0, float v1, float v2, float v3) {
+  epi_apply_scalar(p, m, n, v0);
+  epi_apply_scalar(p, m, n + 1, v1);
+  epi_apply_scalar(p, m, n + 2, v2);
+  epi_apply_scalar(p, m, n + 3, v3);
+}
+
+template <int MODE>
+__device__ __forceinline__ void epi_apply_vec4(const EpiParams& p, int m, int n, float (&v)[4]) {
+  if (m >= p.M || n >= p.N) return;
+  if (!p.vec_ok || n + 4 > p.N) {
+    epi_apply_tail4(p, m, n, v[0], v[1], v[2], v[3]);
+    return;
+  }
+  if (MODE == B200REC_EPI_STORE) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] *= p.alpha;
+    store4_dt(p.C, p.c_dtype, epi_offset(p, m, n, p.ldc, p.c_split_stride), v);
+  } else if (MODE == B200REC_EPI_ACCUM) {
+    float* c = (float*)p.C + epi_offset(p, m, n, p.ldc, p.c_split_stride);
+    float o[4];
+    load4<float>(c, o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] += p.alpha * v[i];
+    store4<float>(c, o);
+  } else if (MODE == B200REC_EPI_SILU_DUAL) {
+    store4_dt(p.C2, p.c2_dtype, epi_offset(p, m, n, p.ldc2, p.c2_split_stride), v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = silu_f(v[i]);
+    store4_dt(p.C, p.c_dtype, epi_offset(p, m, n, p.ldc, p.c_split_stride), v);
+  } else if (MODE == B200REC_EPI_BIAS_RESID) {
+    if (p.bias) {
+      float b[4];
+      load4<float>(p.bias + n, b);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] += b[i];
+    }
+    if (p.resid) {
+      float r[4];
+      load4<float>(p.resid + (int64_t)m * p.ldr + n, r);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] += r[i];
+    }
+    store4_dt(p.C, p.c_dtype, epi_offset(p, m, n, p.ldc, p.c_split_stride), v);
+  } else if (MODE == B200REC_EPI_RESBLOCK) {
+    if (p.bias) {
+      float b[4];
+      load4<float>(p.bias + n, b);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] += b[i];
+    }
+    if (p.C2) store4_dt(p.C2, p.c2_dtype, epi_offset(p, m, n, p.ldc2, p.c2_split_stride), v);
+    int nr = p.n_split > 0 ? n % p.n_split : n;
+    float r[4];
+    load4<float>(p.resid + (int64_t)m * p.ldr + nr, r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = r[i] + silu_f(v[i]);
+    store4_dt(p.C, p.c_dtype, epi_offset(p, m, n, p.ldc, p.c_split_stride), v);
+  }
+}
+
+// Variant with the row-dependent addend (residual row, or C itself for ACCUM) already in registers:
+// the caller issues all such loads of a chunk first so they overlap instead of serialising.
+template <int MODE>
+__device__ __forceinline__ bool epi_needs_prefetch() {
+  return MODE == B200REC_EPI_ACCUM || MODE == B200REC_EPI_BIAS_RESID || MODE == B200REC_EPI_RESBLOCK;
+}
+
+template <int MODE>
+__device__ __forceinline__ bool epi_prefetch_vec4(const EpiParams& p, int m, int n, float (&r)[4]) {
+  if (m >= p.M || !p.vec_ok || n + 4 > p.N) return false;
+  if (MODE == B200REC_EPI_ACCUM) {
+    load4<float>((const float*)p.C + epi_offset(p, m, n, p.ldc, p.c_split_stride), r);
+  } else if (MODE == B200REC_EPI_BIAS_RESID) {
+    if (p.resid) load4<float>(p.resid + (int64_t)m * p.ldr + n, r);
+    else r[0] = r[1] = r[2] = r[3] = 0.f;
+  } else if (MODE == B200REC_EPI_RESBLOCK) {
+    int nr = p.n_split > 0 ? n % p.n_split : n;
+    load4<float>(p.resid + (int64_t)m * p.ldr + nr, r);
+  }
+  return true;
+}
+
+template <int MODE>
+__device__ __forceinline__ void epi_finish_vec4(const EpiParams& p, int m, int n, float (&v)[4], const float (&r)[4],
+                                                const float (&b)[4]) {
+  if (MODE == B200REC_EPI_ACCUM) {
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = r[i] + p.alpha * v[i];
+    store4<float>((float*)p.C + epi_offset(p, m, n, p.ldc, p.c_split_stride), o);
+  } else if (MODE == B200REC_EPI_BIAS_RESID) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] += b[i] + r[i];
+    store4_dt(p.C, p.c_dtype, epi_offset(p, m, n, p.ldc, p.c_split_stride), v);
+  } else if (MODE == B200REC_EPI_RESBLOCK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] += b[i];
+    if (p.C2) store4_dt(p.C2, p.c2_dtype, epi_offset(p, m, n, p.ldc2, p.c2_split_stride), v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = r[i] + silu_f(v[i]);
+    store4_dt(p.C, p.c_dtype, epi_offset(p, m, n, p.ldc, p.c_split_stride), v);
   }
 }

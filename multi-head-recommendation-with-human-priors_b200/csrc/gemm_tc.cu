@@ -3,7 +3,9 @@
 //   -> fp32 accumulators in TMEM (2 stages) -> tcgen05.ld -> fused epilogue -> global.
 // C[M,N] = epi(A[M,K] * B[N,K]^T); each operand may be K-major or MN-major in global memory
 // (MN-major avoids every explicit transpose in the backward pass: dW = X^T dY, dX = dY W).
-// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue (TMEM lane quarters).
+// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..9 = epilogue (two warps per TMEM lane
+// quarter).  Epilogue = TMEM -> registers (lane = row) -> swizzled smem transpose -> lanes along the row
+// -> fused math + fully coalesced 16-byte global accesses (8 lanes cover 128 contiguous bytes).
 #include <mutex>
 #include <unordered_map>
 
@@ -12,7 +14,9 @@
 
 #define TC_BM 128
 #define TC_BK 64
-#define TC_THREADS 192
+#define TC_THREADS 320
+#define TC_EPI_WARPS 8
+#define TC_STAGE_BYTES (TC_EPI_WARPS * 4096)
 #define TC_TMEM_COLS 512
 #define TC_SMEM_LIMIT (227 * 1024)
 
@@ -24,6 +28,7 @@ struct TcParams {
   int num_m, num_n;
 };
 
+template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcParams p, const EpiParams ep_in) {
@@ -42,6 +47,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
+  const uint32_t epi_stage_base = bar_base + 256u;  // TC_EPI_WARPS x 4 KB transpose buffers
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -52,7 +58,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), TC_EPI_WARPS);
     }
     mbar_fence_init();
   }
@@ -132,7 +138,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else {
     // ===================== epilogue warps =====================
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32)
+    const int quarter = warp & 3;        // TMEM lanes [32*quarter, 32*quarter+32) are visible to this warp
+    const int e = warp - 2;              // 0..7
+    const int half = e >> 2;             // the two warps of a quarter take alternate 32-column chunks
+    const uint32_t stg = epi_stage_base + (uint32_t)e * 4096u;
+    const int cg = lane & 7, sub = lane >> 3;
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -140,12 +150,69 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int n0 = (tile / p.num_m) * p.BN;
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
-      const int m = m0 + quarter * 32 + lane;
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * (uint32_t)p.BN;
-      for (int c = 0; c < p.BN / 32; ++c) {
+      for (int c = half; c < p.BN / 32; c += 2) {
         float v[32];
         tmem_ld_32x32(t_row + (uint32_t)c * 32u, v);
-        epi_apply_chunk32(ep, m, n0 + c * 32, v);
+        if (MODE == B200REC_EPI_GT_BITS) {
+          uint32_t wbits = 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) wbits |= (v[i] > ep.alpha) ? (1u << i) : 0u;
+          const int m = m0 + quarter * 32 + lane, nn = n0 + c * 32;
+          if (m < ep.M && nn < ep.N) {
+            if (nn + 32 > ep.N) wbits &= (1u << (ep.N - nn)) - 1u;
+            ((uint32_t*)ep.C)[(int64_t)m * ep.ldc + (nn >> 5)] = wbits;
+            if (wbits != 0u && ep.C2) ((uint8_t*)ep.C2)[m] = 1;
+          }
+          continue;
+        }
+        // phase 1: lane owns row `lane`; 16-byte chunk q goes to physical chunk q ^ (lane & 7)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t addr = stg + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[4 * q]), "f"(v[4 * q + 1]),
+                       "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
+                       : "memory");
+        }
+        __syncwarp();
+        // phase 2: 8 lanes cover one 128-byte row segment, 4 rows per pass
+        const int ncol = n0 + c * 32 + cg * 4;
+        if (epi_needs_prefetch<MODE>()) {
+          // issue every row-dependent global load of the chunk before consuming any (latency overlap)
+          float pre[8][4];
+          bool okv[8];
+          float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+          if (MODE != B200REC_EPI_ACCUM && ep.bias && ep.vec_ok && ncol + 4 <= ep.N) load4<float>(ep.bias + ncol, bias4);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            okv[j] = epi_prefetch_vec4<MODE>(ep, m0 + quarter * 32 + 4 * j + sub, ncol, pre[j]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int row = 4 * j + sub;
+            const uint32_t addr = stg + (uint32_t)row * 128u + (uint32_t)((cg ^ (row & 7)) << 4);
+            float x[4];
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3])
+                         : "r"(addr)
+                         : "memory");
+            const int m = m0 + quarter * 32 + row;
+            if (okv[j]) epi_finish_vec4<MODE>(ep, m, ncol, x, pre[j], bias4);
+            else if (m < ep.M && ncol < ep.N) epi_apply_tail4(ep, m, ncol, x[0], x[1], x[2], x[3]);
+          }
+        } else {
+#pragma unroll 2
+          for (int j = 0; j < 8; ++j) {
+            const int row = 4 * j + sub;
+            const uint32_t addr = stg + (uint32_t)row * 128u + (uint32_t)((cg ^ (row & 7)) << 4);
+            float x[4];
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3])
+                         : "r"(addr)
+                         : "memory");
+            epi_apply_vec4<MODE>(ep, m0 + quarter * 32 + row, ncol, x);
+          }
+        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -208,19 +275,29 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep, cudaStream_t
     int dev = 0;
     B200_CUDA_OK(cudaGetDevice(&dev));
     B200_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
   }
   TcParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.a_mn = a->a_major; p.b_mn = a->b_major;
-  p.BN = (a->N > 128) ? 256 : 128;
-  // prefer more tiles than SMs: fall back to BN=128 when the 256-wide grid under-fills the GPU
-  if (p.BN == 256 && (int64_t)ceil_div_i(a->M, TC_BM) * ceil_div_i(a->N, 256) < g_num_sms) p.BN = 128;
+  {
+    // wave quantisation: cost ~ waves x tile width; take the cheaper of the two tile widths
+    const int64_t nm = ceil_div_i(a->M, TC_BM);
+    const int64_t w256 = (nm * ceil_div_i(a->N, 256) + g_num_sms - 1) / g_num_sms * 2;
+    const int64_t w128 = (nm * ceil_div_i(a->N, 128) + g_num_sms - 1) / g_num_sms;
+    // the 128-wide tile reads 128 B/clk of shared memory per MMA (the port limit) -> 15% handicap
+    p.BN = (a->N > 128 && w256 * 100 <= w128 * 160) ? 256 : 128;
+  }
   if (g_force_bn == 128 || g_force_bn == 256) p.BN = g_force_bn;
   if (a->n_split > 0)
     B200_CHECK_ARG(a->n_split % 32 == 0, "gemm: n_split must be a multiple of 32");
   const uint32_t stage_bytes = TC_BM * 128u + (uint32_t)p.BN * 128u;
-  p.stages = (TC_SMEM_LIMIT - 1024 - 256) / stage_bytes;
+  p.stages = (TC_SMEM_LIMIT - 1024 - 256 - TC_STAGE_BYTES) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   p.num_m = ceil_div_i(a->M, TC_BM);
   p.num_n = ceil_div_i(a->N, p.BN);
@@ -237,8 +314,16 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep, cudaStream_t
   }
   int tiles = p.num_m * p.num_n;
   int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
-  gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep);
+  size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256 + TC_STAGE_BYTES;
+  switch (ep.mode) {
+    case B200REC_EPI_STORE: gemm_tc_kernel<0><<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep); break;
+    case B200REC_EPI_ACCUM: gemm_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep); break;
+    case B200REC_EPI_SILU_DUAL: gemm_tc_kernel<2><<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep); break;
+    case B200REC_EPI_BIAS_RESID: gemm_tc_kernel<3><<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep); break;
+    case B200REC_EPI_RESBLOCK: gemm_tc_kernel<4><<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep); break;
+    case B200REC_EPI_GT_BITS: gemm_tc_kernel<5><<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep); break;
+    default: b200rec_set_error("gemm: bad epilogue %d", ep.mode); return 1;
+  }
   B200_LAUNCH_OK();
   return 0;
 }

@@ -200,14 +200,236 @@ nce_loss_fwd_kernel(const float* __restrict__ logits, int64_t ld_logits, int n_n
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fast path (n_neg <= 8192, n_neg % 4 == 0): positive cosines come from a warp-per-(t,p) pre-kernel,
+// "target row has filtered negatives" flags from the bit-GEMM epilogue, and the logits row lives in
+// registers (32 per thread) between the statistics pass and the gradient pass: one global read of
+// the row, one block reduction, no shared-memory staging.
+template <typename TA>
+__global__ void __launch_bounds__(256) nce_pos_kernel(const TA* __restrict__ q_hat, int64_t ldq,
+                                                      const TA* __restrict__ t_hat, int D4,
+                                                      const int32_t* __restrict__ tok_b,
+                                                      const int32_t* __restrict__ tok_pos, int T, int LP, int P,
+                                                      uint32_t p_mask, const uint8_t* __restrict__ tok_ok,
+                                                      int tok_ok_ld, int tok_ok_col, float* __restrict__ pos_cos) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= (int64_t)T * P) return;
+  const int t = (int)(w / P), p = (int)(w - (int64_t)t * P);
+  float acc = 0.f;
+  bool ok = false;
+  if ((p_mask >> p) & 1u) {
+    const int64_t r = (int64_t)tok_b[t] * LP + tok_pos[t] + 1 + p;
+    ok = tok_ok[r * tok_ok_ld + tok_ok_col] != 0;
+    if (ok) {
+      for (int c = lane; c < D4; c += 32) {
+        float a[4], b[4];
+        load4<TA>(q_hat + (int64_t)t * ldq + c * 4, a);
+        load4<TA>(t_hat + (r * D4 + c) * 4, b);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc += a[k] * b[k];
+      }
+      acc = warp_sum(acc);
+    }
+  }
+  if (lane == 0) pos_cos[w] = ok ? acc : __int_as_float(0x7fc00000);  // NaN marks "offset not served"
+}
+
+#define NCE_RV 8  // float4 vectors per thread -> up to 8192 negatives per row
+
+template <typename TA>
+__global__ void __launch_bounds__(256)
+nce_loss_fwd_reg_kernel(const float* __restrict__ logits, int64_t ld_logits, int n_neg,
+                        const uint32_t* __restrict__ same_bits, const uint8_t* __restrict__ row_any,
+                        const float* __restrict__ pos_cos, const int32_t* __restrict__ tok_b,
+                        const int32_t* __restrict__ tok_pos, int LP, int P, const float* __restrict__ coef,
+                        const float* __restrict__ logit_scale, float* __restrict__ loss, float* __restrict__ g0,
+                        float* __restrict__ dscale, int32_t* __restrict__ rank0, int32_t* __restrict__ nvalid,
+                        TA* __restrict__ G, int64_t ldg) {
+  __shared__ Stats red_stats[8];
+  __shared__ float s_pos[NCE_MAXP], s_lse[NCE_MAXP], s_coef[NCE_MAXP];
+  __shared__ int s_valid[NCE_MAXP], s_masked[NCE_MAXP];
+  __shared__ int s_any;
+  const int t = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int64_t r0 = (int64_t)tok_b[t] * LP + tok_pos[t] + 1;
+  const float tau = __expf(fminf(fmaxf(*logit_scale, 0.f), 4.605170185988092f));
+  const int n_words = (n_neg + 31) >> 5;
+  const int n_vec = n_neg >> 2;
+  if (tid == 0) s_any = 0;
+  __syncthreads();
+  if (tid < NCE_MAXP) {
+    int p = tid;
+    float pc = p < P ? pos_cos[(int64_t)t * P + p] : __int_as_float(0x7fc00000);
+    int ok = pc == pc;
+    s_valid[p] = ok;
+    s_pos[p] = ok ? tau * pc : 0.f;
+    s_masked[p] = (ok && row_any[r0 + p]) ? 1 : 0;
+    s_coef[p] = p < P ? coef[p] : 0.f;
+    if (ok) s_any = 1;
+  }
+  __syncthreads();
+  if (!s_any) {
+    for (int p = tid; p < P; p += blockDim.x) {
+      loss[(int64_t)t * P + p] = 0.f;
+      g0[(int64_t)t * P + p] = 0.f;
+      dscale[(int64_t)t * P + p] = 0.f;
+      rank0[(int64_t)t * P + p] = -1;
+      nvalid[(int64_t)t * P + p] = 0;
+    }
+    if (G) {
+      float zero[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int v = tid; v < n_vec; v += 256) store4<TA>(G + (int64_t)t * ldg + v * 4, zero);
+    }
+    return;
+  }
+  // the row: thread owns vectors tid, tid+256, ...
+  float z[NCE_RV][4];
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < NCE_RV; ++k) {
+    int v = tid + k * 256;
+    if (v < n_vec) {
+      load4<float>(logits + (int64_t)t * ld_logits + v * 4, z[k]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        z[k][e] *= tau;
+        m = fmaxf(m, z[k][e]);
+      }
+    }
+  }
+  const float pos0 = s_valid[0] ? s_pos[0] : INFINITY;
+  Stats loc;
+  loc.m = m; loc.s = 0.f; loc.w = 0.f; loc.gt = 0; loc.cnt = 0;
+#pragma unroll
+  for (int k = 0; k < NCE_RV; ++k) {
+    int v = tid + k * 256;
+    if (v < n_vec) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float ex = __expf(z[k][e] - m);
+        loc.s += ex;
+        loc.w += ex * z[k][e];
+        loc.gt += z[k][e] > pos0;
+        loc.cnt += 1;
+      }
+    }
+  }
+  const Stats all = block_stats(loc, red_stats);
+  float a_common = 0.f;
+  for (int p = 0; p < P; ++p) {
+    if (!s_valid[p]) {
+      if (tid == 0) {
+        loss[(int64_t)t * P + p] = 0.f;
+        g0[(int64_t)t * P + p] = 0.f;
+        dscale[(int64_t)t * P + p] = 0.f;
+        rank0[(int64_t)t * P + p] = -1;
+        nvalid[(int64_t)t * P + p] = 0;
+      }
+      continue;
+    }
+    Stats st = all;
+    if (s_masked[p]) {  // exact pass over the negatives this target does not filter
+      const uint32_t* bits = same_bits + (r0 + p) * n_words;
+      float mm = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < NCE_RV; ++k) {
+        int v = tid + k * 256;
+        if (v < n_vec) {
+          uint32_t wbits = bits[(v * 4) >> 5] >> ((v * 4) & 31);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (!((wbits >> e) & 1u)) mm = fmaxf(mm, z[k][e]);
+        }
+      }
+      Stats l2;
+      l2.m = mm; l2.s = 0.f; l2.w = 0.f; l2.gt = 0; l2.cnt = 0;
+#pragma unroll
+      for (int k = 0; k < NCE_RV; ++k) {
+        int v = tid + k * 256;
+        if (v < n_vec) {
+          uint32_t wbits = bits[(v * 4) >> 5] >> ((v * 4) & 31);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (!((wbits >> e) & 1u)) {
+              float ex = __expf(z[k][e] - mm);
+              l2.s += ex;
+              l2.w += ex * z[k][e];
+              l2.gt += z[k][e] > s_pos[p];
+              l2.cnt += 1;
+            }
+        }
+      }
+      st = block_stats(l2, red_stats);
+    }
+    const float zp = s_pos[p];
+    const float M = fmaxf(st.m, zp);
+    const float en = st.m == -INFINITY ? 0.f : __expf(st.m - M);
+    const float ep = __expf(zp - M);
+    const float denom = st.s * en + ep;
+    const float lse = M + __logf(denom);
+    const float c = s_coef[p];
+    if (tid == 0) {
+      s_lse[p] = lse;
+      loss[(int64_t)t * P + p] = c * (lse - zp);
+      g0[(int64_t)t * P + p] = c * (ep / denom - 1.f);
+      dscale[(int64_t)t * P + p] = c * ((st.w * en + ep * zp) / denom - zp);
+      rank0[(int64_t)t * P + p] = (p == 0 || s_masked[p]) ? st.gt : -1;
+      nvalid[(int64_t)t * P + p] = st.cnt + 1;
+    }
+    if (!s_masked[p]) a_common += c * __expf(all.m - lse);
+  }
+  if (G == nullptr) return;
+  __syncthreads();
+  int any_masked = 0;
+  for (int p = 0; p < P; ++p) any_masked |= (s_valid[p] && s_masked[p]);
+#pragma unroll
+  for (int k = 0; k < NCE_RV; ++k) {
+    int v = tid + k * 256;
+    if (v < n_vec) {
+      float g[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) g[e] = a_common * __expf(z[k][e] - all.m);
+      if (any_masked) {
+        for (int p = 0; p < P; ++p) {
+          if (s_valid[p] && s_masked[p]) {
+            const uint32_t* bits = same_bits + (r0 + p) * n_words;
+            uint32_t wbits = bits[(v * 4) >> 5] >> ((v * 4) & 31);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (!((wbits >> e) & 1u)) g[e] += s_coef[p] * __expf(z[k][e] - s_lse[p]);
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) g[e] *= tau;
+      store4<TA>(G + (int64_t)t * ldg + v * 4, g);
+    }
+  }
+}
+
 int b200rec_nce_loss_fwd(const float* logits, int64_t ld_logits, int n_neg, const uint32_t* same_bits,
-                         const void* q_hat, int64_t ldq, const void* t_hat, int act_dtype, int D,
+                         const uint8_t* row_any, float* pos_ws, const void* q_hat, int64_t ldq, const void* t_hat, int act_dtype, int D,
                          const int32_t* tok_b, const int32_t* tok_pos, int T, int LP, int P, uint32_t p_mask,
                          const uint8_t* tok_ok, int tok_ok_ld, int tok_ok_col, const float* coef,
                          const float* logit_scale, float* loss, float* g0, float* dscale, int32_t* rank0,
                          int32_t* nvalid, void* G, int64_t ldg, void* stream) {
   B200_CHECK_ARG(P >= 1 && P <= NCE_MAXP, "nce_loss_fwd: pred_len %d not in [1,%d]", P, NCE_MAXP);
   if (T == 0) return 0;
+  if (row_any != nullptr && pos_ws != nullptr && n_neg % 4 == 0 && n_neg <= NCE_RV * 256 * 4 &&
+      ld_logits % 4 == 0 && ldg % 4 == 0 && D % 4 == 0 && ldq % 4 == 0) {
+    DISPATCH_ACT(act_dtype, TA, {
+      nce_pos_kernel<TA><<<ceil_div_i((int64_t)T * P, 8), 256, 0, (cudaStream_t)stream>>>(
+          (const TA*)q_hat, ldq, (const TA*)t_hat, D / 4, tok_b, tok_pos, T, LP, P, p_mask, tok_ok, tok_ok_ld,
+          tok_ok_col, pos_ws);
+      nce_loss_fwd_reg_kernel<TA><<<T, 256, 0, (cudaStream_t)stream>>>(
+          logits, ld_logits, n_neg, same_bits, row_any, pos_ws, tok_b, tok_pos, LP, P, coef, logit_scale, loss, g0,
+          dscale, rank0, nvalid, (TA*)G, ldg);
+    });
+    B200_LAUNCH_OK();
+    return 0;
+  }
   size_t smem = (size_t)(n_neg + D) * sizeof(float);
   B200_CHECK_ARG(smem <= 200 * 1024, "nce_loss_fwd: n_neg=%d too large for the shared-memory row cache", n_neg);
   DISPATCH_ACT(act_dtype, TA, {

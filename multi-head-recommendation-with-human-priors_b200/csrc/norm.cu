@@ -293,34 +293,54 @@ int b200rec_cast(const float* x, int64_t n, void* y, int y_dtype, void* stream) 
   return 0;
 }
 
-// block = 32 columns x 8 row lanes; each thread walks rows r = lane_r, lane_r+8, ...; partials are
-// combined in fixed order -> deterministic.
+// Column sums in two deterministic stages: (1) each block sums a 256-row slab of 32 columns into
+// ws[slab][col]; (2) one thread per column adds the slabs in ascending order.
+#define CS_SLAB 256
 template <typename TX>
-__global__ void __launch_bounds__(256) colsum_kernel(const TX* __restrict__ x, int64_t ldx, int rows, int cols,
-                                                     float* __restrict__ out, int accumulate) {
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const TX* __restrict__ x, int64_t ldx, int rows, int cols,
+                                                             float* __restrict__ ws) {
   __shared__ float part[8][33];
   int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   int c = blockIdx.x * 32 + cx;
+  int r0 = blockIdx.y * CS_SLAB, r1 = min(rows, r0 + CS_SLAB);
   float s = 0.f;
   if (c < cols)
-    for (int r = ry; r < rows; r += 8) s += to_f32(x[(int64_t)r * ldx + c]);
+    for (int r = r0 + ry; r < r1; r += 8) s += to_f32(x[(int64_t)r * ldx + c]);
   part[ry][cx] = s;
   __syncthreads();
   if (ry == 0 && c < cols) {
     float t = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) t += part[k][cx];
-    out[c] = accumulate ? out[c] + t : t;
+    ws[(int64_t)blockIdx.y * cols + c] = t;
   }
 }
 
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ ws, int slabs, int cols,
+                                                           float* __restrict__ out, int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float t = 0.f;
+  for (int s = 0; s < slabs; ++s) t += ws[(int64_t)s * cols + c];
+  out[c] = accumulate ? out[c] + t : t;
+}
+
+size_t b200rec_colsum_workspace_bytes(int rows, int cols) {
+  return (size_t)std::max(1, ceil_div_i(rows, CS_SLAB)) * (size_t)std::max(cols, 1) * sizeof(float);
+}
+
 int b200rec_colsum(const void* x, int x_dtype, int ldx, int rows, int cols, float* out, int accumulate,
-                   void* stream) {
+                   void* workspace, size_t workspace_bytes, void* stream) {
   if (cols == 0) return 0;
-  int blocks = ceil_div_i(cols, 32);
+  B200_CHECK_ARG(workspace_bytes >= b200rec_colsum_workspace_bytes(rows, cols), "colsum: workspace too small");
+  int slabs = std::max(1, ceil_div_i(rows, CS_SLAB));
+  dim3 grid(ceil_div_i(cols, 32), slabs);
   DISPATCH_ACT(x_dtype, TX, {
-    colsum_kernel<TX><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TX*)x, ldx, rows, cols, out, accumulate);
+    colsum_partial_kernel<TX><<<grid, 256, 0, (cudaStream_t)stream>>>((const TX*)x, ldx, rows, cols,
+                                                                     (float*)workspace);
   });
+  colsum_final_kernel<<<ceil_div_i(cols, 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, slabs, cols,
+                                                                              out, accumulate);
   B200_LAUNCH_OK();
   return 0;
 }

@@ -317,7 +317,7 @@ class HSTU(nn.Module):
             dWo = torch.empty((D, D), dtype=torch.float32, device=dev)
             L.gemm(dxb, oin, dWo, D, D, T, lda=D, a_major=1, ldb=D, b_major=1, ldc=D)
             dbo = torch.empty(D, dtype=torch.float32, device=dev)
-            L.call("b200rec_colsum", dx.data_ptr(), L.F32, D, T, D, dbo.data_ptr(), 0, st)
+            L.colsum(dx, T, D, D, dbo)
             d_pre = torch.empty((T, 4 * D), dtype=act, device=dev)
             da = torch.empty((T, D), dtype=torch.float32, device=dev)
             L.call("b200rec_gate_ln_bwd", d_oin.data_ptr(), actv.data_ptr(), pre.data_ptr(), 4 * D, a.data_ptr(),
@@ -420,7 +420,7 @@ class HSTU(nn.Module):
         ld_neg = n_words * 32
         neg_ids = neg_items.permute(1, 0, 2).contiguous().view(n_sets, n_neg)   # set-major id lists
         used_sets = sorted({j.nset for j in self._jobs})
-        nhat, ninv, bits = {}, {}, {}
+        nhat, ninv, bits, row_any = {}, {}, {}, {}
         for s in used_sets:
             nh_ = torch.empty((n_neg, D), dtype=act, device=dev)
             ni_ = torch.empty(n_neg, dtype=torch.float32, device=dev)
@@ -428,9 +428,10 @@ class HSTU(nn.Module):
                    ni_.data_ptr(), st)
             bt = torch.empty((B * LP, n_words), dtype=torch.int32, device=dev)
             # false-negative filter bits: that @ nhat^T > nce_thres   (hstu.py:613-614)
+            ra = torch.zeros(B * LP + P + 1, dtype=torch.uint8, device=dev)
             L.gemm(that, nh_, bt, B * LP, n_neg, D, lda=D, ldb=D, ldc=n_words, epilogue=L.EPI_GT_BITS,
-                   alpha=float(self.nce_thres))
-            nhat[s], ninv[s], bits[s] = nh_, ni_, bt
+                   alpha=float(self.nce_thres), C2=ra)
+            nhat[s], ninv[s], bits[s], row_any[s] = nh_, ni_, bt, ra
         # ---- per-offset token counts -> loss coefficients (hstu.py:704-712, 846-852)
         lam = self.horizon_discount.to(torch.float32)
         coefs, cnts = {}, {}
@@ -446,6 +447,7 @@ class HSTU(nn.Module):
         # ---- NCE jobs
         scale = self.logit_scale.data.to(torch.float32)
         job_out = []
+        pos_ws = torch.empty(T * P, dtype=torch.float32, device=dev)
         for j in self._jobs:
             hq = j.head if self.medusa_num_layers > 0 else 0
             q_h = qhat.view(T, Hx * D)[:, hq * D:(hq + 1) * D]
@@ -457,13 +459,14 @@ class HSTU(nn.Module):
             rank0 = torch.empty((T, P), dtype=torch.int32, device=dev)
             nval = torch.empty((T, P), dtype=torch.int32, device=dev)
             G = torch.empty((T, ld_neg), dtype=act, device=dev) if need_grad else None
-            L.call("b200rec_nce_loss_fwd", logits.data_ptr(), ld_neg, n_neg, bits[j.nset].data_ptr(), q_h.data_ptr(),
+            L.call("b200rec_nce_loss_fwd", logits.data_ptr(), ld_neg, n_neg, bits[j.nset].data_ptr(),
+                   row_any[j.nset].data_ptr(), pos_ws.data_ptr(), q_h.data_ptr(),
                    Hx * D, that.data_ptr(), a_dt, D, tok_b.data_ptr(), tok_pos.data_ptr(), T, LP, P, j.p_mask,
                    tok_ok.data_ptr(), n_col, j.col, coefs[(j.col, j.w)].data_ptr(), scale.data_ptr(),
                    lossv.data_ptr(), g0.data_ptr(), dsc.data_ptr(), rank0.data_ptr(), nval.data_ptr(), L.ptr(G),
                    ld_neg, st)
             per_p = torch.empty(P, dtype=torch.float32, device=dev)
-            L.call("b200rec_colsum", lossv.data_ptr(), L.F32, P, T, P, per_p.data_ptr(), 0, st)
+            L.colsum(lossv, T, P, P, per_p)
             job_out.append(dict(job=j, per_p=per_p, g0=g0, dsc=dsc, rank0=rank0, nval=nval, G=G, hq=hq))
             del logits
         # ---- total loss + logging scalars (tiny [P] vectors)
@@ -570,7 +573,7 @@ class HSTU(nn.Module):
             dWc = torch.empty((Hx * D, D), dtype=torch.float32, device=dev)
             L.gemm(dz, ctx["yb"], dWc, Hx * D, D, T, lda=Hx * D, a_major=1, ldb=D, b_major=1, ldc=D)
             dbc = torch.empty(Hx * D, dtype=torch.float32, device=dev)
-            L.call("b200rec_colsum", dz.data_ptr(), a_dt, Hx * D, T, Hx * D, dbc.data_ptr(), 0, st)
+            L.colsum(dz, T, Hx * D, Hx * D, dbc)
             for h in range(Hx):
                 lin = self.medusa_head[h][0].linear
                 grads[lin.weight] = dWc[h * D:(h + 1) * D]

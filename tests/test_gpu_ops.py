@@ -171,7 +171,7 @@ def test_cast_colsum_reduce():
     L.call("b200rec_cast", x.data_ptr(), x.numel(), y.data_ptr(), L.BF16, L.stream())
     assert torch.equal(y, x.to(torch.bfloat16))
     out = torch.empty(96, device=dev())
-    L.call("b200rec_colsum", x.data_ptr(), L.F32, 96, 1234, 96, out.data_ptr(), 0, L.stream())
+    L.colsum(x, 1234, 96, 96, out)
     assert torch.allclose(out, x.sum(0), rtol=1e-4, atol=1e-4)
     s = torch.zeros((), device=dev())
     L.call("b200rec_reduce_sum", x.data_ptr(), x.numel(), 0.5, s.data_ptr(), 0, L.stream())
