@@ -90,10 +90,10 @@ int b200rec_layernorm_bwd(const void* dy, int dy_dtype, int ldy, const float* x,
  * slice of the uvqk activation). */
 int b200rec_gate_ln_fwd(const void* u, int ldu, const float* a, int T, int D, float eps, void* oin,
                         int act_dtype, float* mean, float* rstd, void* stream);
-/* backward: du = d_oin*LN(a) ; da = LN'(a; d_oin*u).  Writes d_pre_u = du * silu'(pre_u) directly
+/* backward: du = d_oin*LN(a) ; da = LN'(a; d_oin*u) (act dtype).  Writes d_pre_u = du * silu'(pre_u) directly
  * (pre_u = pre-activation slice, ld ldu) into d_pre_u (ld ldu). */
 int b200rec_gate_ln_bwd(const void* d_oin, const void* u, const void* pre_u, int ldu, const float* a,
-                        const float* mean, const float* rstd, int T, int D, void* d_pre_u, float* da,
+                        const float* mean, const float* rstd, int T, int D, void* d_pre_u, void* da,
                         int act_dtype, void* stream);
 /* y = cast(x) elementwise, n elements (fp32 -> act dtype). */
 int b200rec_cast(const float* x, int64_t n, void* y, int y_dtype, void* stream);
@@ -146,13 +146,22 @@ int b200rec_gemm(const b200rec_gemm_args* args, void* stream);
 int b200rec_hstu_attn_fwd(const void* q, const void* k, const void* v, int ld, int act_dtype,
                           const int32_t* seq_off, const uint8_t* key_valid, int B, int T,
                           int n_heads, int dh, float inv_n, int max_len, float* out, void* stream);
-/* backward: recomputes S.  d_out fp32 [T,D].  Writes d_pre_{q,k,v} =
+/* backward: recomputes S.  d_out act dtype [T,D].  Writes d_pre_{q,k,v} =
  * d{q,k,v} * silu'(pre_{q,k,v}) into the [T,4D] pre-activation-gradient buffer (ld, act dtype). */
 int b200rec_hstu_attn_bwd(const void* q, const void* k, const void* v, const void* pre_q,
                           const void* pre_k, const void* pre_v, int ld, int act_dtype,
                           const int32_t* seq_off, const uint8_t* key_valid, int B, int T,
-                          int n_heads, int dh, float inv_n, int max_len, const float* d_out,
+                          int n_heads, int dh, float inv_n, int max_len, const void* d_out,
                           void* d_pre_q, void* d_pre_k, void* d_pre_v, void* stream);
+
+/* Tensor-core variants (bf16 only, dh in {32, 64}): tcgen05.mma for QK^T / AV / the backward
+ * contractions, TMA-fed, scores kept in TMEM / shared memory.  act, pre and d_pre point at column 0 of
+ * the [T, 4D] u|v|q|k buffers (ld = 4D); d_out is bf16 [T, D]; out is fp32 [T, D]. */
+int b200rec_hstu_attn_tc_fwd(const void* act, int ld, const int32_t* seq_off, const uint8_t* key_valid,
+                             int B, int T, int n_heads, int dh, float inv_n, float* out, void* stream);
+int b200rec_hstu_attn_tc_bwd(const void* act, const void* pre, int ld, const int32_t* seq_off,
+                             const uint8_t* key_valid, int B, int T, int n_heads, int dh, float inv_n,
+                             const void* d_out, void* d_pre, void* stream);
 
 /* ------------------------------------------------------------------ NCE / sampled softmax (a9-a12)
  * hstu.py:600-619 nce_loss + :697 cross_entropy + :704-713 per-offset means, restructured:

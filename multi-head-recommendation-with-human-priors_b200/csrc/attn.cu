@@ -148,7 +148,7 @@ template <typename TA, int DH>
 __global__ void __launch_bounds__(256)
 hstu_attn_bwd_dq_kernel(const TA* __restrict__ q, const TA* __restrict__ k, const TA* __restrict__ v,
                         const TA* __restrict__ pre_q, int64_t ld, const int32_t* __restrict__ seq_off,
-                        const uint8_t* __restrict__ key_valid, float inv_n, const float* __restrict__ d_out, int D,
+                        const uint8_t* __restrict__ key_valid, float inv_n, const TA* __restrict__ d_out, int D,
                         TA* __restrict__ d_pre_q) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   AttnSmem<DH>& sm = *reinterpret_cast<AttnSmem<DH>*>(smem_raw);
@@ -159,7 +159,7 @@ hstu_attn_bwd_dq_kernel(const TA* __restrict__ q, const TA* __restrict__ k, cons
   const int nq = min(AT, len - q0);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   load_tile<TA, DH>(sm.q, q + h * DH, ld, t0 + q0, nq);
-  load_tile<float, DH>(sm.dout, d_out + h * DH, D, t0 + q0, nq);
+  load_tile<TA, DH>(sm.dout, d_out + h * DH, D, t0 + q0, nq);
   float dq[4][DH / 16];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256)
 hstu_attn_bwd_dkv_kernel(const TA* __restrict__ q, const TA* __restrict__ k, const TA* __restrict__ v,
                          const TA* __restrict__ pre_k, const TA* __restrict__ pre_v, int64_t ld,
                          const int32_t* __restrict__ seq_off, const uint8_t* __restrict__ key_valid, float inv_n,
-                         const float* __restrict__ d_out, int D, TA* __restrict__ d_pre_k, TA* __restrict__ d_pre_v) {
+                         const TA* __restrict__ d_out, int D, TA* __restrict__ d_pre_k, TA* __restrict__ d_pre_v) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   AttnSmem<DH>& sm = *reinterpret_cast<AttnSmem<DH>*>(smem_raw);
   const int b = blockIdx.z, h = blockIdx.y, kt = blockIdx.x;
@@ -229,7 +229,7 @@ hstu_attn_bwd_dkv_kernel(const TA* __restrict__ q, const TA* __restrict__ k, con
     const int nq = min(AT, len - q0);
     __syncthreads();
     load_tile<TA, DH>(sm.q, q + h * DH, ld, t0 + q0, nq);
-    load_tile<float, DH>(sm.dout, d_out + h * DH, D, t0 + q0, nq);
+    load_tile<TA, DH>(sm.dout, d_out + h * DH, D, t0 + q0, nq);
     __syncthreads();
     float s[4][4], da[4][4];
     tile_xyT<DH>(sm.q, sm.k, s);
@@ -278,7 +278,7 @@ static int attn_fwd_launch(const void* q, const void* k, const void* v, int ld, 
 template <typename TA, int DH>
 static int attn_bwd_launch(const void* q, const void* k, const void* v, const void* pre_q, const void* pre_k,
                            const void* pre_v, int ld, const int32_t* seq_off, const uint8_t* key_valid, int B,
-                           int n_heads, float inv_n, int max_len, const float* d_out, void* d_pre_q, void* d_pre_k,
+                           int n_heads, float inv_n, int max_len, const void* d_out, void* d_pre_q, void* d_pre_k,
                            void* d_pre_v, cudaStream_t st) {
   size_t smem = sizeof(AttnSmem<DH>);
   B200_CUDA_OK(cudaFuncSetAttribute(hstu_attn_bwd_dq_kernel<TA, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -287,12 +287,12 @@ static int attn_bwd_launch(const void* q, const void* k, const void* v, const vo
                                     (int)smem));
   dim3 grid(ceil_div_i(max_len, AT), n_heads, B);
   hstu_attn_bwd_dq_kernel<TA, DH><<<grid, 256, smem, st>>>((const TA*)q, (const TA*)k, (const TA*)v,
-                                                           (const TA*)pre_q, ld, seq_off, key_valid, inv_n, d_out,
-                                                           n_heads * DH, (TA*)d_pre_q);
+                                                           (const TA*)pre_q, ld, seq_off, key_valid, inv_n,
+                                                           (const TA*)d_out, n_heads * DH, (TA*)d_pre_q);
   hstu_attn_bwd_dkv_kernel<TA, DH><<<grid, 256, smem, st>>>((const TA*)q, (const TA*)k, (const TA*)v,
                                                             (const TA*)pre_k, (const TA*)pre_v, ld, seq_off,
-                                                            key_valid, inv_n, d_out, n_heads * DH, (TA*)d_pre_k,
-                                                            (TA*)d_pre_v);
+                                                            key_valid, inv_n, (const TA*)d_out, n_heads * DH,
+                                                            (TA*)d_pre_k, (TA*)d_pre_v);
   B200_LAUNCH_OK();
   return 0;
 }
@@ -323,7 +323,7 @@ int b200rec_hstu_attn_fwd(const void* q, const void* k, const void* v, int ld, i
 int b200rec_hstu_attn_bwd(const void* q, const void* k, const void* v, const void* pre_q, const void* pre_k,
                           const void* pre_v, int ld, int act_dtype, const int32_t* seq_off,
                           const uint8_t* key_valid, int B, int T, int n_heads, int dh, float inv_n, int max_len,
-                          const float* d_out, void* d_pre_q, void* d_pre_k, void* d_pre_v, void* stream) {
+                          const void* d_out, void* d_pre_q, void* d_pre_k, void* d_pre_v, void* stream) {
   if (T == 0 || B == 0) return 0;
   B200_CHECK_ARG(ld % 4 == 0, "attention: ld=%d must be a multiple of 4", ld);
   DISPATCH_ACT(act_dtype, TA, {

@@ -1,0 +1,497 @@
+// HSTU attention on the 5th-gen tensor cores (sm_100a): bf16 operands fed by TMA, QK^T / AV and the
+// backward contractions issued as tcgen05.mma with fp32 accumulators in TMEM; the pointwise SiLU, the
+// 1/n_pad scale and the jagged causal mask run on the TMEM->register path and the probabilities go
+// back to shared memory (128B-swizzled K-major) as the A operand of the second MMA.  Scores never
+// touch HBM.
+//
+// Tiling is over the GLOBAL jagged token axis: a query tile is 128 consecutive
+// tokens (it may span several short sequences), its key tiles run from the tile holding the first
+// token's sequence start up to the diagonal tile, and the mask is
+//   keep(i, j) = seq_start(i) <= j <= i  and  key_valid[j]
+// so sequences of any length (L = 50 ... 400+) use the same kernel with no padding rows.
+// Backward = two deterministic passes (dQ per query tile; dK/dV per key tile, computed in the
+// transposed orientation so that keys sit on the TMEM lanes), each recomputing S (App. D.1).
+#include <limits.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+int b200_make_map_bf16(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t box0,
+                       uint32_t box1, int swizzle_bytes);
+
+// sequence index of token t: largest b with seq_off[b] <= t
+__device__ __forceinline__ int find_seq(const int32_t* __restrict__ seq_off, int B, int t) {
+  int lo = 0, hi = B - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (seq_off[mid] <= t) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// 32 consecutive columns [col0, col0+32) of row `row` -> bf16 into a K-major SWIZZLE_128B tile made of
+// 64-column blocks of [R rows x 128 bytes] (the canonical UMMA A-operand layout TMA would produce).
+__device__ __forceinline__ void put_row32_sw128(uint32_t tile, int R, int row, int col0, const float (&v)[32]) {
+  const uint32_t base = tile + (uint32_t)(col0 >> 6) * (uint32_t)(R * 128) + (uint32_t)row * 128u;
+  const int cin = (col0 & 63) >> 3;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * q + 2 * e], v[8 * q + 2 * e + 1]);
+      w[e] = *reinterpret_cast<uint32_t*>(&h2);
+    }
+    const uint32_t addr = base + (uint32_t)(((cin + q) ^ (row & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                 : "memory");
+  }
+}
+
+template <int DH>
+struct AtCfg {
+  static constexpr int SWZ = DH * 2;                       // bytes per tile row = TMA swizzle span
+  static constexpr uint32_t LAY = SWZ == 128 ? 2u : 4u;    // UMMA layout code
+  static constexpr uint32_t ATOM = 8 * SWZ;                // 8-row swizzle atom
+  // K-major operand (rows = M/N index, DH along K), k-step ks of 16 elements
+  static __device__ __forceinline__ uint64_t desc_k(uint32_t tile, int ks) {
+    return umma_smem_desc_l(tile + ks * 32, 16, ATOM, LAY);
+  }
+  // MN-major B operand ([K rows][N = DH] as stored), k-step ks of 16 rows
+  static __device__ __forceinline__ uint64_t desc_mn(uint32_t tile, int ks) {
+    return umma_smem_desc_l(tile + ks * 16 * SWZ, ATOM, ATOM, LAY);
+  }
+};
+// K-major A operand written by put_row32_sw128 (128 rows, K = keys/queries), k-step ks of 16 columns
+__device__ __forceinline__ uint64_t desc_p(uint32_t tile, int ks) {
+  return umma_smem_desc_l(tile + (ks >> 2) * (128 * 128) + (ks & 3) * 32, 16, 1024, 2u);
+}
+
+// --------------------------------------------------------------------------------------- forward
+template <int DH>
+__global__ void __launch_bounds__(128)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const int32_t* __restrict__ seq_off, int B,
+                   const uint8_t* __restrict__ key_valid, int T, int D, float inv_n, float* __restrict__ out) {
+  using C = AtCfg<DH>;
+  constexpr uint32_t TILE = 128 * C::SWZ;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base, sK = sQ + TILE, sV = sK + TILE, sP = sV + TILE;  // sP: 2 x 16 KB
+  const uint32_t bars = sP + 32768;
+  const uint32_t bar_q = bars, bar_kv = bars + 8, bar_s = bars + 16, bar_o = bars + 24, tslot = bars + 32;
+  __shared__ uint8_t s_kvalid[128];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y;
+  const int ti = q0 + tid;
+  if (tid == 0) {
+    tma_prefetch_desc(&map128);
+    mbar_init(bar_q, 1); mbar_init(bar_kv, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tslot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot));
+  const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tS = 0, tO = 128;  // TMEM columns
+
+  const int my_start = ti < T ? seq_off[find_seq(seq_off, B, ti)] : INT_MAX;
+  const int kt_first = seq_off[find_seq(seq_off, B, q0)] >> 7;
+  const int kt_last = blockIdx.x;
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_q, TILE);
+    tma_load_2d(sQ, &map128, bar_q, 2 * D + h * DH, q0);
+  }
+  const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+  const uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);
+  uint32_t ph = 0;
+  for (int kt = kt_first; kt <= kt_last; ++kt, ph ^= 1u) {
+    const int k0 = kt * 128;
+    if (tid == 0) {
+      if (kt > kt_first) mbar_wait(bar_o, ph ^ 1u);  // previous P*V retired: K, V and P buffers are free
+      mbar_arrive_expect_tx(bar_kv, 2 * TILE);
+      tma_load_2d(sK, &map128, bar_kv, 3 * D + h * DH, k0);
+      tma_load_2d(sV, &map128, bar_kv, 1 * D + h * DH, k0);
+    }
+    s_kvalid[tid] = (k0 + tid < T) ? key_valid[k0 + tid] : 0;
+    if (tid == 0) {
+      if (kt == kt_first) mbar_wait(bar_q, 0);
+      mbar_wait(bar_kv, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < DH / 16; ++ks)
+        umma_bf16(tmem + tS, C::desc_k(sQ, ks), C::desc_k(sK, ks), idesc_s, ks > 0);
+      umma_commit(bar_s);
+    }
+    __syncthreads();
+    mbar_wait(bar_s, ph);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      float v[32];
+      tmem_ld_32x32(t_lane + tS + c * 32, v);
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int tj = k0 + c * 32 + e;
+        const bool keep = (tj <= ti) && (tj >= my_start) && s_kvalid[c * 32 + e];
+        v[e] = keep ? silu_f(v[e]) * inv_n : 0.f;
+      }
+      put_row32_sw128(sP, 128, tid, c * 32, v);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+        umma_bf16(tmem + tO, desc_p(sP, ks), C::desc_mn(sV, ks), idesc_o, (kt > kt_first || ks > 0));
+      umma_commit(bar_o);
+    }
+  }
+  mbar_wait(bar_o, ph ^ 1u);
+  tc_fence_after();
+#pragma unroll 1
+  for (int c = 0; c < DH / 32; ++c) {
+    float v[32];
+    tmem_ld_32x32(t_lane + tO + c * 32, v);
+    if (ti < T) {
+      float* dst = out + (int64_t)ti * D + h * DH + c * 32;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float o4[4] = {v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]};
+        store4<float>(dst + 4 * e, o4);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// --------------------------------------------------------------------------------------- backward: dQ
+template <int DH>
+__global__ void __launch_bounds__(128)
+attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map64,
+                      const __grid_constant__ CUtensorMap mapdo128, const int32_t* __restrict__ seq_off, int B,
+                      const uint8_t* __restrict__ key_valid, int T, int D, float inv_n,
+                      const bf16* __restrict__ pre_q, int64_t ld, bf16* __restrict__ d_pre_q) {
+  using C = AtCfg<DH>;
+  constexpr uint32_t TILE = 128 * C::SWZ;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base, sdO = sQ + TILE, sK = sdO + TILE, sV = sK + TILE / 2, sdS = sV + TILE / 2;  // sdS 16 KB
+  const uint32_t bars = sdS + 16384;
+  const uint32_t bar_q = bars, bar_kv = bars + 8, bar_s = bars + 16, bar_o = bars + 24, tslot = bars + 32;
+  __shared__ uint8_t s_kvalid[64];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y;
+  const int ti = q0 + tid;
+  if (tid == 0) {
+    tma_prefetch_desc(&map128); tma_prefetch_desc(&map64); tma_prefetch_desc(&mapdo128);
+    mbar_init(bar_q, 1); mbar_init(bar_kv, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tslot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot));
+  const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tS = 0, tdA = 64, tdQ = 128;
+
+  const int my_start = ti < T ? seq_off[find_seq(seq_off, B, ti)] : INT_MAX;
+  const int kt_first = seq_off[find_seq(seq_off, B, q0)] >> 6;
+  const int kt_last = min(q0 + 127, T - 1) >> 6;
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_q, 2 * TILE);
+    tma_load_2d(sQ, &map128, bar_q, 2 * D + h * DH, q0);
+    tma_load_2d(sdO, &mapdo128, bar_q, h * DH, q0);
+  }
+  const uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+  const uint32_t idesc_q = umma_idesc_bf16(128, DH, 0, 1);
+  uint32_t ph = 0;
+  for (int kt = kt_first; kt <= kt_last; ++kt, ph ^= 1u) {
+    const int k0 = kt * 64;
+    if (tid == 0) {
+      if (kt > kt_first) mbar_wait(bar_o, ph ^ 1u);
+      mbar_arrive_expect_tx(bar_kv, TILE);
+      tma_load_2d(sK, &map64, bar_kv, 3 * D + h * DH, k0);
+      tma_load_2d(sV, &map64, bar_kv, 1 * D + h * DH, k0);
+    }
+    if (tid < 64) s_kvalid[tid] = (k0 + tid < T) ? key_valid[k0 + tid] : 0;
+    if (tid == 0) {
+      if (kt == kt_first) mbar_wait(bar_q, 0);
+      mbar_wait(bar_kv, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < DH / 16; ++ks)
+        umma_bf16(tmem + tS, C::desc_k(sQ, ks), C::desc_k(sK, ks), idesc_s, ks > 0);      // S  = Q K^T
+#pragma unroll
+      for (int ks = 0; ks < DH / 16; ++ks)
+        umma_bf16(tmem + tdA, C::desc_k(sdO, ks), C::desc_k(sV, ks), idesc_s, ks > 0);    // dA = dO V^T
+      umma_commit(bar_s);
+    }
+    __syncthreads();
+    mbar_wait(bar_s, ph);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      float s[32], da[32];
+      tmem_ld_32x32(t_lane + tS + c * 32, s);
+      tmem_ld_32x32(t_lane + tdA + c * 32, da);
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int tj = k0 + c * 32 + e;
+        const bool keep = (tj <= ti) && (tj >= my_start) && s_kvalid[c * 32 + e];
+        s[e] = keep ? da[e] * inv_n * silu_grad_f(s[e]) : 0.f;
+      }
+      put_row32_sw128(sdS, 128, tid, c * 32, s);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        umma_bf16(tmem + tdQ, desc_p(sdS, ks), C::desc_mn(sK, ks), idesc_q, (kt > kt_first || ks > 0));  // dQ += dS K
+      umma_commit(bar_o);
+    }
+  }
+  mbar_wait(bar_o, ph ^ 1u);
+  tc_fence_after();
+#pragma unroll 1
+  for (int c = 0; c < DH / 32; ++c) {
+    float v[32];
+    tmem_ld_32x32(t_lane + tdQ + c * 32, v);
+    if (ti < T) {
+      const int64_t off = (int64_t)ti * ld + h * DH + c * 32;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float p4[4], o4[4];
+        load4<bf16>(pre_q + off + 4 * e, p4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o4[k] = v[4 * e + k] * silu_grad_f(p4[k]);
+        store4<bf16>(d_pre_q + off + 4 * e, o4);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// --------------------------------------------------------------------------------------- backward: dK, dV
+template <int DH>
+__global__ void __launch_bounds__(128)
+attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map64,
+                       const __grid_constant__ CUtensorMap mapdo64, const int32_t* __restrict__ seq_off, int B,
+                       const uint8_t* __restrict__ key_valid, int T, int D, float inv_n,
+                       const bf16* __restrict__ pre_k, const bf16* __restrict__ pre_v, int64_t ld,
+                       bf16* __restrict__ d_pre_k, bf16* __restrict__ d_pre_v) {
+  using C = AtCfg<DH>;
+  constexpr uint32_t TILE = 128 * C::SWZ;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sK = base, sV = sK + TILE, sQ = sV + TILE, sdO = sQ + TILE / 2, sPT = sdO + TILE / 2,
+                 sdST = sPT + 16384;
+  const uint32_t bars = sdST + 16384;
+  const uint32_t bar_kv = bars, bar_q = bars + 8, bar_s = bars + 16, bar_o = bars + 24, tslot = bars + 32;
+  __shared__ int s_qstart[64];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int k0 = blockIdx.x * 128, h = blockIdx.y;
+  const int tj = k0 + tid;
+  if (tid == 0) {
+    tma_prefetch_desc(&map128); tma_prefetch_desc(&map64); tma_prefetch_desc(&mapdo64);
+    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tslot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot));
+  const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tS = 0, tdA = 64, tdK = 128, tdV = 192;
+
+  const bool kv_ok = tj < T && key_valid[tj] != 0;
+  const int k_last = min(k0 + 127, T - 1);
+  const int q_hi = seq_off[find_seq(seq_off, B, k_last) + 1] - 1;   // last token of the last key's sequence
+  const int qt_first = k0 >> 6, qt_last = q_hi >> 6;
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_kv, 2 * TILE);
+    tma_load_2d(sK, &map128, bar_kv, 3 * D + h * DH, k0);
+    tma_load_2d(sV, &map128, bar_kv, 1 * D + h * DH, k0);
+  }
+  const uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+  const uint32_t idesc_g = umma_idesc_bf16(128, DH, 0, 1);
+  uint32_t ph = 0;
+  for (int qt = qt_first; qt <= qt_last; ++qt, ph ^= 1u) {
+    const int i0 = qt * 64;
+    if (tid == 0) {
+      if (qt > qt_first) mbar_wait(bar_o, ph ^ 1u);
+      mbar_arrive_expect_tx(bar_q, TILE);
+      tma_load_2d(sQ, &map64, bar_q, 2 * D + h * DH, i0);
+      tma_load_2d(sdO, &mapdo64, bar_q, h * DH, i0);
+    }
+    if (tid < 64) s_qstart[tid] = (i0 + tid < T) ? seq_off[find_seq(seq_off, B, i0 + tid)] : INT_MAX;
+    if (tid == 0) {
+      if (qt == qt_first) mbar_wait(bar_kv, 0);
+      mbar_wait(bar_q, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < DH / 16; ++ks)
+        umma_bf16(tmem + tS, C::desc_k(sK, ks), C::desc_k(sQ, ks), idesc_s, ks > 0);      // S^T  = K Q^T
+#pragma unroll
+      for (int ks = 0; ks < DH / 16; ++ks)
+        umma_bf16(tmem + tdA, C::desc_k(sV, ks), C::desc_k(sdO, ks), idesc_s, ks > 0);    // dA^T = V dO^T
+      umma_commit(bar_s);
+    }
+    __syncthreads();
+    mbar_wait(bar_s, ph);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      float s[32], da[32];
+      tmem_ld_32x32(t_lane + tS + c * 32, s);
+      tmem_ld_32x32(t_lane + tdA + c * 32, da);
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int tq = i0 + c * 32 + e;
+        const bool keep = kv_ok && (tj <= tq) && (tj >= s_qstart[c * 32 + e]);
+        const float sv = s[e];
+        s[e] = keep ? silu_f(sv) * inv_n : 0.f;                       // P^T
+        da[e] = keep ? da[e] * inv_n * silu_grad_f(sv) : 0.f;         // dS^T
+      }
+      put_row32_sw128(sPT, 128, tid, c * 32, s);
+      put_row32_sw128(sdST, 128, tid, c * 32, da);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        umma_bf16(tmem + tdV, desc_p(sPT, ks), C::desc_mn(sdO, ks), idesc_g, (qt > qt_first || ks > 0));  // dV += P^T dO
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        umma_bf16(tmem + tdK, desc_p(sdST, ks), C::desc_mn(sQ, ks), idesc_g, (qt > qt_first || ks > 0));  // dK += dS^T Q
+      umma_commit(bar_o);
+    }
+  }
+  mbar_wait(bar_o, ph ^ 1u);
+  tc_fence_after();
+#pragma unroll 1
+  for (int c = 0; c < DH / 32; ++c) {
+    float gk[32], gv[32];
+    tmem_ld_32x32(t_lane + tdK + c * 32, gk);
+    tmem_ld_32x32(t_lane + tdV + c * 32, gv);
+    if (tj < T) {
+      const int64_t off = (int64_t)tj * ld + h * DH + c * 32;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float p4[4], o4[4];
+        load4<bf16>(pre_k + off + 4 * e, p4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o4[k] = gk[4 * e + k] * silu_grad_f(p4[k]);
+        store4<bf16>(d_pre_k + off + 4 * e, o4);
+        load4<bf16>(pre_v + off + 4 * e, p4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o4[k] = gv[4 * e + k] * silu_grad_f(p4[k]);
+        store4<bf16>(d_pre_v + off + 4 * e, o4);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// --------------------------------------------------------------------------------------- host
+template <int DH>
+static int attn_tc_fwd_launch(const bf16* act_base, int64_t ld, const int32_t* seq_off, int B, const uint8_t* key_valid,
+                              int T, int n_heads, float inv_n, float* out, cudaStream_t st) {
+  const int D = n_heads * DH;
+  CUtensorMap m128;
+  if (b200_make_map_bf16(&m128, act_base, (uint64_t)ld, (uint64_t)T, (uint64_t)ld, DH, 128, DH * 2)) return 1;
+  size_t smem = 3 * 128 * DH * 2 + 32768 + 256 + 1024;
+  B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ceil_div_i(T, 128), n_heads);
+  attn_tc_fwd_kernel<DH><<<grid, 128, smem, st>>>(m128, seq_off, B, key_valid, T, D, inv_n, out);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+template <int DH>
+static int attn_tc_bwd_launch(const bf16* act_base, const bf16* pre_base, int64_t ld, const int32_t* seq_off, int B,
+                              const uint8_t* key_valid, int T, int n_heads, float inv_n, const bf16* d_out,
+                              bf16* d_pre_base, cudaStream_t st) {
+  const int D = n_heads * DH;
+  CUtensorMap m128, m64, do128, do64;
+  if (b200_make_map_bf16(&m128, act_base, (uint64_t)ld, (uint64_t)T, (uint64_t)ld, DH, 128, DH * 2)) return 1;
+  if (b200_make_map_bf16(&m64, act_base, (uint64_t)ld, (uint64_t)T, (uint64_t)ld, DH, 64, DH * 2)) return 1;
+  if (b200_make_map_bf16(&do128, d_out, (uint64_t)D, (uint64_t)T, (uint64_t)D, DH, 128, DH * 2)) return 1;
+  if (b200_make_map_bf16(&do64, d_out, (uint64_t)D, (uint64_t)T, (uint64_t)D, DH, 64, DH * 2)) return 1;
+  size_t smem_q = 3 * 128 * DH * 2 + 16384 + 256 + 1024;
+  size_t smem_kv = 3 * 128 * DH * 2 + 32768 + 256 + 1024;
+  B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_bwd_dq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem_q));
+  B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_bwd_dkv_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem_kv));
+  dim3 grid(ceil_div_i(T, 128), n_heads);
+  // column slices of the [T, 4D] buffers: u | v | q | k
+  attn_tc_bwd_dq_kernel<DH><<<grid, 128, smem_q, st>>>(m128, m64, do128, seq_off, B, key_valid, T, D, inv_n,
+                                                       pre_base + 2 * D, ld, d_pre_base + 2 * D);
+  attn_tc_bwd_dkv_kernel<DH><<<grid, 128, smem_kv, st>>>(m128, m64, do64, seq_off, B, key_valid, T, D, inv_n,
+                                                         pre_base + 3 * D, pre_base + 1 * D, ld, d_pre_base + 3 * D,
+                                                         d_pre_base + 1 * D);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+// act / pre / d_pre point at column 0 of the [T, 4D] uvqk buffers (bf16, leading dimension ld = 4D).
+extern "C" int b200rec_hstu_attn_tc_fwd(const void* act, int ld, const int32_t* seq_off, const uint8_t* key_valid,
+                                        int B, int T, int n_heads, int dh, float inv_n, float* out, void* stream) {
+  if (T == 0 || B == 0) return 0;
+  B200_CHECK_ARG(ld == 4 * n_heads * dh, "attn_tc: ld must be 4*D");
+  B200_CHECK_ARG(((uintptr_t)act & 15) == 0, "attn_tc: act must be 16-byte aligned");
+  if (dh == 64)
+    return attn_tc_fwd_launch<64>((const bf16*)act, ld, seq_off, B, key_valid, T, n_heads, inv_n, out,
+                                  (cudaStream_t)stream);
+  if (dh == 32)
+    return attn_tc_fwd_launch<32>((const bf16*)act, ld, seq_off, B, key_valid, T, n_heads, inv_n, out,
+                                  (cudaStream_t)stream);
+  b200rec_set_error("attn_tc: head dim %d not supported (32 or 64)", dh);
+  return 1;
+}
+
+extern "C" int b200rec_hstu_attn_tc_bwd(const void* act, const void* pre, int ld, const int32_t* seq_off,
+                                        const uint8_t* key_valid, int B, int T, int n_heads, int dh, float inv_n,
+                                        const void* d_out, void* d_pre, void* stream) {
+  if (T == 0 || B == 0) return 0;
+  B200_CHECK_ARG(ld == 4 * n_heads * dh, "attn_tc: ld must be 4*D");
+  B200_CHECK_ARG(((uintptr_t)act & 15) == 0 && ((uintptr_t)d_out & 15) == 0, "attn_tc: 16-byte alignment");
+  if (dh == 64)
+    return attn_tc_bwd_launch<64>((const bf16*)act, (const bf16*)pre, ld, seq_off, B, key_valid, T, n_heads, inv_n,
+                                  (const bf16*)d_out, (bf16*)d_pre, (cudaStream_t)stream);
+  if (dh == 32)
+    return attn_tc_bwd_launch<32>((const bf16*)act, (const bf16*)pre, ld, seq_off, B, key_valid, T, n_heads, inv_n,
+                                  (const bf16*)d_out, (bf16*)d_pre, (cudaStream_t)stream);
+  b200rec_set_error("attn_tc: head dim %d not supported (32 or 64)", dh);
+  return 1;
+}

@@ -246,9 +246,10 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2D bf16 tensor map: inner (contiguous) extent d0, outer extent d1, row pitch ld elements.
-static int make_map(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t box0,
-                    uint32_t box1) {
+// 2D bf16 tensor map: inner (contiguous) extent d0, outer extent d1, row pitch ld elements;
+// swizzle_bytes in {32, 64, 128} must equal the inner box width in bytes.
+int b200_make_map_bf16(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t box0,
+                       uint32_t box1, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   B200_CHECK_ARG(fn != nullptr, "cuTensorMapEncodeTiled not available");
   cuuint64_t dims[2] = {d0, d1};
@@ -256,11 +257,19 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, u
   cuuint32_t box[2] = {box0, box1};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                       : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B200_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): ptr=%p d0=%llu d1=%llu ld=%llu box=%u,%u",
                  (int)r, ptr, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)ld, box0, box1);
   return 0;
+}
+
+static int make_map(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t box0,
+                    uint32_t box1) {
+  return b200_make_map_bf16(m, ptr, d0, d1, ld, box0, box1, 128);
 }
 
 static int g_num_sms = 0;

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(256) gate_ln_bwd_kernel(const TA* __restrict__
                                                           const TA* __restrict__ pre_u, int64_t ldu,
                                                           const float* __restrict__ a, const float* __restrict__ mean,
                                                           const float* __restrict__ rstd, int T, int D4,
-                                                          TA* __restrict__ d_pre_u, float* __restrict__ da) {
+                                                          TA* __restrict__ d_pre_u, TA* __restrict__ da) {
   int lane = threadIdx.x & 31;
   int r = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= T) return;
@@ -240,13 +240,13 @@ __global__ void __launch_bounds__(256) gate_ln_bwd_kernel(const TA* __restrict__
       float o[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) o[k] = rs * (g[k4][k] - sg - lna[k4][k] * sgx);
-      store4<float>(da + ((int64_t)r * D4 + c) * 4, o);
+      store4<TA>(da + ((int64_t)r * D4 + c) * 4, o);
     }
   }
 }
 
 int b200rec_gate_ln_bwd(const void* d_oin, const void* u, const void* pre_u, int ldu, const float* a,
-                        const float* mean, const float* rstd, int T, int D, void* d_pre_u, float* da, int act_dtype,
+                        const float* mean, const float* rstd, int T, int D, void* d_pre_u, void* da, int act_dtype,
                         void* stream) {
   B200_CHECK_ARG(D % 4 == 0 && D <= 2048 && ldu % 4 == 0, "gate_ln_bwd: bad D=%d ldu=%d", D, ldu);
   if (T == 0) return 0;
@@ -254,10 +254,10 @@ int b200rec_gate_ln_bwd(const void* d_oin, const void* u, const void* pre_u, int
   DISPATCH_ACT(act_dtype, TA, {
     if (D <= 512)
       gate_ln_bwd_kernel<TA, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>(
-          (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, da);
+          (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, (TA*)da);
     else
       gate_ln_bwd_kernel<TA, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>(
-          (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, da);
+          (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, (TA*)da);
   });
   B200_LAUNCH_OK();
   return 0;

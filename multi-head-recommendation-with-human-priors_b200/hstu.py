@@ -175,6 +175,7 @@ class HSTU(nn.Module):
         self.register_buffer("_attn_mask", torch.triu(
             torch.ones((self.max_seq_length, self.max_seq_length), dtype=torch.bool), diagonal=1))
         self.sparse_embedding_grad = bool(config.get("sparse_embedding_grad", False))
+        self.use_tc_attention = bool(config.get("tc_attention", True))
         self.emb_grad = None       # (uniq_ids, uniq_rows, n_uniq) of the last backward
         self._table_cache = None   # normalised compute-dtype item table for predict
         self._verbose = False
@@ -212,6 +213,10 @@ class HSTU(nn.Module):
     # ------------------------------------------------------------------ helpers
     def _act(self):
         return self.compute_dtype
+
+    def _tc_attention(self):
+        """tcgen05 attention: bf16 compute dtype and a head dim the tensor-core kernel tiles (32 / 64)."""
+        return self.compute_dtype == torch.bfloat16 and self._dqk in (32, 64) and self.use_tc_attention
 
     def _phys_heads(self):
         return self.medusa_num_heads if self.medusa_num_layers > 0 else 1
@@ -282,8 +287,12 @@ class HSTU(nn.Module):
                    epilogue=L.EPI_SILU_DUAL, C2=pre, ldc2=4 * D)
             a = torch.empty((T, D), dtype=torch.float32, device=dev)
             u, v, q, k = actv[:, 0:D], actv[:, D:2 * D], actv[:, 2 * D:3 * D], actv[:, 3 * D:4 * D]
-            L.call("b200rec_hstu_attn_fwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), 4 * D, a_dt,
-                   seq_off.data_ptr(), key_valid.data_ptr(), B, T, nh, dh, 1.0 / n_pad, max_len, a.data_ptr(), st)
+            if self._tc_attention():
+                L.call("b200rec_hstu_attn_tc_fwd", actv.data_ptr(), 4 * D, seq_off.data_ptr(), key_valid.data_ptr(), B,
+                       T, nh, dh, 1.0 / n_pad, a.data_ptr(), st)
+            else:
+                L.call("b200rec_hstu_attn_fwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), 4 * D, a_dt,
+                       seq_off.data_ptr(), key_valid.data_ptr(), B, T, nh, dh, 1.0 / n_pad, max_len, a.data_ptr(), st)
             oin = torch.empty((T, D), dtype=act, device=dev)
             mean2 = torch.empty(T, dtype=torch.float32, device=dev)
             rstd2 = torch.empty(T, dtype=torch.float32, device=dev)
@@ -319,11 +328,15 @@ class HSTU(nn.Module):
             dbo = torch.empty(D, dtype=torch.float32, device=dev)
             L.colsum(dx, T, D, D, dbo)
             d_pre = torch.empty((T, 4 * D), dtype=act, device=dev)
-            da = torch.empty((T, D), dtype=torch.float32, device=dev)
+            da = torch.empty((T, D), dtype=act, device=dev)
             L.call("b200rec_gate_ln_bwd", d_oin.data_ptr(), actv.data_ptr(), pre.data_ptr(), 4 * D, a.data_ptr(),
                    mean2.data_ptr(), rstd2.data_ptr(), T, D, d_pre.data_ptr(), da.data_ptr(), a_dt, st)
             sl = lambda t, j: t[:, j * D:(j + 1) * D]
-            L.call("b200rec_hstu_attn_bwd", sl(actv, 2).data_ptr(), sl(actv, 3).data_ptr(), sl(actv, 1).data_ptr(),
+            if self._tc_attention():
+                L.call("b200rec_hstu_attn_tc_bwd", actv.data_ptr(), pre.data_ptr(), 4 * D, seq_off.data_ptr(),
+                       key_valid.data_ptr(), B, T, nh, dh, 1.0 / n_pad, da.data_ptr(), d_pre.data_ptr(), st)
+            else:
+              L.call("b200rec_hstu_attn_bwd", sl(actv, 2).data_ptr(), sl(actv, 3).data_ptr(), sl(actv, 1).data_ptr(),
                    sl(pre, 2).data_ptr(), sl(pre, 3).data_ptr(), sl(pre, 1).data_ptr(), 4 * D, a_dt,
                    seq_off.data_ptr(), key_valid.data_ptr(), B, T, nh, dh, 1.0 / n_pad, max_len, da.data_ptr(),
                    sl(d_pre, 2).data_ptr(), sl(d_pre, 3).data_ptr(), sl(d_pre, 1).data_ptr(), st)

@@ -436,3 +436,41 @@ def test_adamw_rows_dense_equivalent():
         L.call("b200rec_adamw_rows", p.data_ptr(), m.data_ptr(), v.data_ptr(), N, D, ids.data_ptr(), r.data_ptr(),
                nu.data_ptr(), slot.data_ptr(), 1e-2, 0.9, 0.999, 1e-8, 0.01, step, 1.0, L.stream())
     assert torch.allclose(p, p_ref.data, rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------ tcgen05 attention
+@pytest.mark.parametrize("nh,dh,lens", [(2, 64, [50, 33, 50, 2, 64, 65, 1, 0, 128, 7]), (4, 32, [50] * 9 + [17, 3]),
+                                        (1, 64, [400, 150, 390]), (3, 64, [5])], ids=["bf16-a", "bf16-b", "bf16-c", "bf16-d"])
+def test_hstu_attention_tensor_core_fwd_bwd(nh, dh, lens):
+    D = nh * dh
+    T = sum(lens)
+    B = len(lens)
+    n_pad = max(lens)
+    seq_off = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev())
+    key_valid = (torch.rand(T, generator=torch.Generator().manual_seed(90)) < 0.9).to(torch.uint8).to(dev())
+    pre = rnd(T, 4 * D, seed=91, scale=0.7).to(torch.bfloat16)
+    pre_r = pre.float().clone().requires_grad_(True)
+    act_r = torch.nn.functional.silu(pre_r)
+    act = act_r.detach().to(torch.bfloat16).contiguous()
+    # reference on the bf16-rounded activations (fp32 math)
+    act_q = act.float().clone().requires_grad_(True)
+    ref = _attn_ref(act_q, seq_off, key_valid, nh, dh, n_pad)
+    out = torch.full((T, D), float("nan"), device=dev())
+    L.call("b200rec_hstu_attn_tc_fwd", act.data_ptr(), 4 * D, seq_off.data_ptr(), key_valid.data_ptr(), B, T, nh, dh,
+           1.0 / n_pad, out.data_ptr(), L.stream())
+    scale = ref.detach().abs().max().item()
+    assert (out - ref.detach()).abs().max().item() < 2e-2 * scale + 1e-4
+    g = rnd(T, D, seed=92).to(torch.bfloat16)
+    ref.backward(g.float())
+    sg = torch.sigmoid(pre.float())
+    silu_grad = sg * (1 + pre.float() * (1 - sg))
+    want = act_q.grad * silu_grad                      # d_pre = d_act * silu'(pre)
+    d_pre = torch.zeros(T, 4 * D, dtype=torch.bfloat16, device=dev())
+    L.call("b200rec_hstu_attn_tc_bwd", act.data_ptr(), pre.data_ptr(), 4 * D, seq_off.data_ptr(), key_valid.data_ptr(),
+           B, T, nh, dh, 1.0 / n_pad, g.data_ptr(), d_pre.data_ptr(), L.stream())
+    assert float(d_pre[:, :D].float().abs().sum()) == 0.0
+    for j, name in [(1, "dv"), (2, "dq"), (3, "dk")]:
+        a, b = d_pre[:, j * D:(j + 1) * D].float(), want[:, j * D:(j + 1) * D]
+        err = (a - b).abs().max().item() / max(b.abs().max().item(), 1e-6)
+        cos = float((a.flatten() @ b.flatten()) / (a.norm() * b.norm() + 1e-30))
+        assert err < 5e-2 and cos > 0.999, (name, err, cos)
