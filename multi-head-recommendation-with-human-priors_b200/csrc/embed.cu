@@ -123,9 +123,12 @@ int b200rec_gather_l2norm(const float* table, const float* rows_in, int D, const
     if (D <= 512)
       gather_l2norm_kernel<TO, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>(table, rows_in, D / 4, ids, n,
                                                                             (TO*)out_hat, inv_norm);
+    else if (D <= 1024)
+      gather_l2norm_kernel<TO, 8><<<blocks, 256, 0, (cudaStream_t)stream>>>(table, rows_in, D / 4, ids, n,
+                                                                            (TO*)out_hat, inv_norm);
     else
       gather_l2norm_kernel<TO, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>(table, rows_in, D / 4, ids, n,
-                                                                             (TO*)out_hat, inv_norm);
+                                                                            (TO*)out_hat, inv_norm);
   });
   B200_LAUNCH_OK();
   return 0;
@@ -177,9 +180,12 @@ int b200rec_l2norm_bwd(const void* x_hat, int act_dtype, const float* inv_norm, 
     if (D <= 512)
       l2norm_bwd_kernel<TA, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TA*)x_hat, inv_norm, d_xhat, n,
                                                                          D / 4, dx, accumulate);
+    else if (D <= 1024)
+      l2norm_bwd_kernel<TA, 8><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TA*)x_hat, inv_norm, d_xhat, n,
+                                                                         D / 4, dx, accumulate);
     else
       l2norm_bwd_kernel<TA, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TA*)x_hat, inv_norm, d_xhat, n,
-                                                                          D / 4, dx, accumulate);
+                                                                         D / 4, dx, accumulate);
   });
   B200_LAUNCH_OK();
   return 0;

@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(256) nce_pos_kernel(const TA* __restrict__ q_h
 #define NCE_RV 8  // float4 vectors per thread -> up to 8192 negatives per row
 
 template <typename TA>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 nce_loss_fwd_reg_kernel(const float* __restrict__ logits, int64_t ld_logits, int n_neg,
                         const uint32_t* __restrict__ same_bits, const uint8_t* __restrict__ row_any,
                         const float* __restrict__ pos_cos, const int32_t* __restrict__ tok_b,

@@ -60,6 +60,8 @@ int b200rec_layernorm_fwd(const float* x, int T, int D, float eps, void* y, int 
   DISPATCH_ACT(y_dtype, TY, {
     if (D <= 512)
       layernorm_fwd_kernel<TY, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, T, D / 4, eps, (TY*)y, mean, rstd);
+    else if (D <= 1024)
+      layernorm_fwd_kernel<TY, 8><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, T, D / 4, eps, (TY*)y, mean, rstd);
     else
       layernorm_fwd_kernel<TY, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, T, D / 4, eps, (TY*)y, mean, rstd);
   });
@@ -121,9 +123,12 @@ int b200rec_layernorm_bwd(const void* dy, int dy_dtype, int ldy, const float* x,
     if (D <= 512)
       layernorm_bwd_kernel<TG, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TG*)dy, ldy, x, mean, rstd, T,
                                                                             D / 4, residual_grad, dx);
+    else if (D <= 1024)
+      layernorm_bwd_kernel<TG, 8><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TG*)dy, ldy, x, mean, rstd, T,
+                                                                            D / 4, residual_grad, dx);
     else
       layernorm_bwd_kernel<TG, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TG*)dy, ldy, x, mean, rstd, T,
-                                                                             D / 4, residual_grad, dx);
+                                                                            D / 4, residual_grad, dx);
   });
   B200_LAUNCH_OK();
   return 0;
@@ -190,9 +195,12 @@ int b200rec_gate_ln_fwd(const void* u, int ldu, const float* a, int T, int D, fl
     if (D <= 512)
       gate_ln_fwd_kernel<TA, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TA*)u, ldu, a, T, D / 4, eps,
                                                                           (TA*)oin, mean, rstd);
+    else if (D <= 1024)
+      gate_ln_fwd_kernel<TA, 8><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TA*)u, ldu, a, T, D / 4, eps,
+                                                                          (TA*)oin, mean, rstd);
     else
       gate_ln_fwd_kernel<TA, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TA*)u, ldu, a, T, D / 4, eps,
-                                                                           (TA*)oin, mean, rstd);
+                                                                          (TA*)oin, mean, rstd);
   });
   B200_LAUNCH_OK();
   return 0;
@@ -254,6 +262,9 @@ int b200rec_gate_ln_bwd(const void* d_oin, const void* u, const void* pre_u, int
   DISPATCH_ACT(act_dtype, TA, {
     if (D <= 512)
       gate_ln_bwd_kernel<TA, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+          (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, (TA*)da);
+    else if (D <= 1024)
+      gate_ln_bwd_kernel<TA, 8><<<blocks, 256, 0, (cudaStream_t)stream>>>(
           (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, (TA*)da);
     else
       gate_ln_bwd_kernel<TA, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>(
