@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--eval-users", type=int, default=256)
+    ap.add_argument("--replicate-table", action="store_true", help="N>1: keep the item table replicated")
     ap.add_argument("--profile", action="store_true", help="print a per-kernel time table of one step (torch.profiler)")
     return ap.parse_args()
 
@@ -174,7 +175,7 @@ def main():
                             f"{cfg['num_prior_head']} {cfg['head_interaction']} negatives={cfg['num_negatives']}/set "
                             f"items={cfg['item_num']}",
                 "per_gpu_batch": cfg["train_batch_size"], "global_batch": cfg["train_batch_size"] * world,
-                "parallelism": f"dp{world}", "l2": "working set >> 126 MB L2 (activations + 1.8 GB table); no flush"}}
+                "parallelism": f"dp{world}" + ("+row-sharded-table(a2a)" if world > 1 and not args.replicate_table else ""), "l2": "working set >> 126 MB L2 (activations + 1.8 GB table); no flush"}}
     if args.impl == "reference":
         if rank != 0:
             return
@@ -203,10 +204,12 @@ def main():
     torch.manual_seed(2020)
     model = HSTU(cfg, dl, compute_dtype=dtype).to(dev).eval()   # eval(): dropout off
     opt = FusedAdamW(model, lr=1e-4, weight_decay=0.0)
+    if world > 1 and not args.replicate_table:
+        model.shard_item_table()          # rows id % W == rank; lookups / gradient rows by all-to-all
     dp = parallel.DataParallel(model, opt) if world > 1 else None
     item_tags = synth.make_item_tags(cfg, torch.Generator().manual_seed(4242))
     n_batches = 4
-    host_batches = [tuple(t.pin_memory() for t in synth.make_train_batch(cfg, seed=10 + i, rank=rank, world_size=1,
+    host_batches = [tuple(t.pin_memory() for t in synth.make_train_batch(cfg, seed=10 + i, rank=rank, world_size=world,
                                                                          item_tags=item_tags))
                     for i in range(n_batches)]
     dev_batches = [tuple(t.to(dev) for t in b) for b in host_batches]
@@ -334,6 +337,12 @@ def eval_bench(cfg, model, item_tags, dev, users):
     for _ in range(2):
         one()
     torch.cuda.synchronize()
+    if os.environ.get("B200REC_PROFILE_EVAL"):
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            one()
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=15, max_name_column_width=60), file=sys.stderr)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     n = 3

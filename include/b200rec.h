@@ -216,15 +216,17 @@ int b200rec_reduce_sum(const float* x, int64_t n, float scale, float* out, int a
  * bit masks head h (-1: none); item_tag_bits[N] u32 (bit c = item has tag c); head_on[B*H] u8
  * (prior_given_at_test / switch masks); hist_off[B+1], hist_items: per-user history ids.
  * Tie rule: value desc, item id asc, head asc.
+ * Row i of `scores` is global item id i*id_stride + id_offset (1, 0 for an unsharded table; W, rank for
+ * a table sharded by id % W): id 0 / history masks and the returned ids are in global ids.
  * Outputs topk_idx[B,K] i64, topk_val[B,K] f32, topk_head[B,K] i32.
  * workspace: b200rec_topk_workspace_bytes(B, N). */
 size_t b200rec_topk_workspace_bytes(int B, int64_t N);
 int b200rec_score_mask_topk(const float* scores, int64_t ld_scores, int B, int H, int64_t N, int K,
                             const int32_t* head_cat, const uint32_t* item_tag_bits,
                             const uint8_t* head_on, const int32_t* hist_off,
-                            const int64_t* hist_items, int split_mode, int64_t* topk_idx,
-                            float* topk_val, int32_t* topk_head, void* workspace,
-                            size_t workspace_bytes, void* stream);
+                            const int64_t* hist_items, int split_mode, int64_t id_offset,
+                            int64_t id_stride, int64_t* topk_idx, float* topk_val, int32_t* topk_head,
+                            void* workspace, size_t workspace_bytes, void* stream);
 /* In-place masks for the reference-compatible predict() that returns [B,H,N] scores
  * (hstu.py:983-999): rows of switched-off heads and items outside the head's category -> -inf. */
 int b200rec_apply_score_masks(float* scores, int64_t ld_scores, int B, int H, int64_t N,

@@ -75,7 +75,8 @@ _SIGS = {
     "b200rec_nce_pos_bwd_q": (C.c_int, [_P, _P, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P, _L, _P]),
     "b200rec_nce_pos_bwd_t": (C.c_int, [_P, _P, _L, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P]),
     "b200rec_topk_workspace_bytes": (_Z, [_I, _L]),
-    "b200rec_score_mask_topk": (C.c_int, [_P, _L, _I, _I, _L, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _Z, _P]),
+    "b200rec_score_mask_topk": (C.c_int, [_P, _L, _I, _I, _L, _I, _P, _P, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _Z,
+                                          _P]),
     "b200rec_apply_score_masks": (C.c_int, [_P, _L, _I, _I, _L, _P, _P, _P, _P]),
     "b200rec_hit_matrix": (C.c_int, [_P, _P, _I, _I, _I, _P, _I, _P, _P]),
     "b200rec_adamw": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P]),

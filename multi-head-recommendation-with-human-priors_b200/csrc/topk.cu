@@ -14,8 +14,8 @@ __device__ __forceinline__ uint32_t order_key(float v) {  // ascending-order-pre
 __global__ void __launch_bounds__(256)
 fold_heads_kernel(const float* __restrict__ scores, int64_t ld, int H, int64_t N,
                   const int32_t* __restrict__ head_cat, const uint32_t* __restrict__ item_tag_bits,
-                  const uint8_t* __restrict__ head_on, int split_mode, float* __restrict__ fval,
-                  uint8_t* __restrict__ fhead) {
+                  const uint8_t* __restrict__ head_on, int split_mode, int64_t id_offset, int64_t id_stride,
+                  float* __restrict__ fval, uint8_t* __restrict__ fhead) {
   const int b = blockIdx.y;
   __shared__ int s_cat[64];
   __shared__ uint8_t s_on[64];
@@ -29,7 +29,7 @@ fold_heads_kernel(const float* __restrict__ scores, int64_t ld, int H, int64_t N
     int bh = 0;
     float sum = 0.f;
     int nfin = 0;
-    if (i != 0) {  // trainer.py:724  scores[:, :, 0] = -inf
+    if (i * id_stride + id_offset != 0) {  // trainer.py:724  scores[:, :, 0] = -inf (global item id 0)
       uint32_t tags = item_tag_bits ? item_tag_bits[i] : 0xffffffffu;
       for (int h = 0; h < H; ++h) {
         float v = scores[((int64_t)b * H + h) * ld + i];
@@ -50,11 +50,14 @@ fold_heads_kernel(const float* __restrict__ scores, int64_t ld, int H, int64_t N
 
 // history suppression (trainer.py:725-726): fval[b, item] = -inf
 __global__ void suppress_history_kernel(const int32_t* __restrict__ hist_off, const int64_t* __restrict__ hist_items,
-                                        int B, int64_t N, float* __restrict__ fval, int split_mode) {
+                                        int B, int64_t N, float* __restrict__ fval, int split_mode,
+                                        int64_t id_offset, int64_t id_stride) {
   int b = blockIdx.x;
   for (int i = hist_off[b] + threadIdx.x; i < hist_off[b + 1]; i += blockDim.x) {
-    int64_t it = hist_items[i];
-    if (it >= 0 && it < N) fval[(int64_t)b * N + it] = split_mode == 1 ? 0.f : -INFINITY;
+    int64_t g = hist_items[i] - id_offset;  // global id -> row of this shard (if it lives here)
+    if (g < 0 || g % id_stride != 0) continue;
+    int64_t it = g / id_stride;
+    if (it < N) fval[(int64_t)b * N + it] = split_mode == 1 ? 0.f : -INFINITY;
   }
 }
 
@@ -64,7 +67,7 @@ __global__ void suppress_history_kernel(const int32_t* __restrict__ hist_off, co
 
 __global__ void __launch_bounds__(SEL_THREADS)
 select_topk_kernel(const float* __restrict__ fval, const uint8_t* __restrict__ fhead, int64_t N, int K,
-                   int64_t* __restrict__ topk_idx, float* __restrict__ topk_val, int32_t* __restrict__ topk_head) {
+                   int64_t id_offset, int64_t id_stride, int64_t* __restrict__ topk_idx, float* __restrict__ topk_val, int32_t* __restrict__ topk_head) {
   __shared__ unsigned int hist[256];
   __shared__ unsigned long long cand[SEL_MAXK];
   __shared__ unsigned int s_prefix, s_remaining, s_count, s_scan[SEL_THREADS / 32 + 1];
@@ -160,7 +163,7 @@ select_topk_kernel(const float* __restrict__ fval, const uint8_t* __restrict__ f
   for (int i = tid; i < K; i += SEL_THREADS) {
     unsigned long long c = cand[i];
     uint32_t id = (uint32_t)(c & 0xffffffffull);
-    topk_idx[(int64_t)b * K + i] = (int64_t)id;
+    topk_idx[(int64_t)b * K + i] = (int64_t)id * id_stride + id_offset;
     topk_val[(int64_t)b * K + i] = row[id];
     topk_head[(int64_t)b * K + i] = fhead[(int64_t)b * N + id];
   }
@@ -174,22 +177,23 @@ size_t b200rec_topk_workspace_bytes(int B, int64_t N) {
 
 int b200rec_score_mask_topk(const float* scores, int64_t ld_scores, int B, int H, int64_t N, int K,
                             const int32_t* head_cat, const uint32_t* item_tag_bits, const uint8_t* head_on,
-                            const int32_t* hist_off, const int64_t* hist_items, int split_mode, int64_t* topk_idx,
-                            float* topk_val, int32_t* topk_head, void* workspace, size_t workspace_bytes,
-                            void* stream) {
+                            const int32_t* hist_off, const int64_t* hist_items, int split_mode, int64_t id_offset,
+                            int64_t id_stride, int64_t* topk_idx, float* topk_val, int32_t* topk_head,
+                            void* workspace, size_t workspace_bytes, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   B200_CHECK_ARG(H >= 1 && H <= 64, "score_mask_topk: H=%d not in [1,64]", H);
   B200_CHECK_ARG(K >= 1 && K <= SEL_MAXK && K <= N, "score_mask_topk: K=%d not in [1,%d] or > N", K, SEL_MAXK);
   B200_CHECK_ARG(N < (1ll << 32), "score_mask_topk: N too large");
+  B200_CHECK_ARG(id_stride >= 1 && id_offset >= 0, "score_mask_topk: bad id mapping");
   B200_CHECK_ARG(workspace_bytes >= b200rec_topk_workspace_bytes(B, N), "score_mask_topk: workspace too small");
   if (B == 0) return 0;
   float* fval = (float*)workspace;
   uint8_t* fhead = (uint8_t*)workspace + (((size_t)B * N * 4 + 255) & ~(size_t)255);
   dim3 grid((unsigned)std::min<int64_t>((N + 255) / 256, 148 * 8), B);
   fold_heads_kernel<<<grid, 256, 0, st>>>(scores, ld_scores, H, N, head_cat, item_tag_bits, head_on, split_mode,
-                                          fval, fhead);
-  if (hist_off && hist_items) suppress_history_kernel<<<B, 128, 0, st>>>(hist_off, hist_items, B, N, fval, split_mode);
-  select_topk_kernel<<<B, SEL_THREADS, 0, st>>>(fval, fhead, N, K, topk_idx, topk_val, topk_head);
+                                          id_offset, id_stride, fval, fhead);
+  if (hist_off && hist_items) suppress_history_kernel<<<B, 128, 0, st>>>(hist_off, hist_items, B, N, fval, split_mode, id_offset, id_stride);
+  select_topk_kernel<<<B, SEL_THREADS, 0, st>>>(fval, fhead, N, K, id_offset, id_stride, topk_idx, topk_val, topk_head);
   B200_LAUNCH_OK();
   return 0;
 }

@@ -96,7 +96,7 @@ class Collector(object):
         if self.split_mode not in ("combine", "average"):
             raise ValueError(f"Unknown split_mode: {self.split_mode}")
         # masks were applied by predict() / the caller; id 0 is re-masked inside (idempotent)
-        L.call("b200rec_score_mask_topk", s.data_ptr(), N, B, H, N, K, None, None, None, None, None, mode,
+        L.call("b200rec_score_mask_topk", s.data_ptr(), N, B, H, N, K, None, None, None, None, None, mode, 0, 1,
                idx.data_ptr(), val.data_ptr(), hsrc.data_ptr(), ws.data_ptr(), ws_bytes, L.stream())
         return idx, val, hsrc
 

@@ -25,6 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
+from . import parallel
 
 LN_EPS = 1e-6  # hstu.py:177
 
@@ -176,6 +177,8 @@ class HSTU(nn.Module):
             torch.ones((self.max_seq_length, self.max_seq_length), dtype=torch.bool), diagonal=1))
         self.sparse_embedding_grad = bool(config.get("sparse_embedding_grad", False))
         self.use_tc_attention = bool(config.get("tc_attention", True))
+        self.share_negatives = bool(config.get("share_negatives", True))   # all-gather negatives across ranks
+        self.sharded_table = None  # parallel.ShardedTable once shard_item_table() was called
         self.emb_grad = None       # (uniq_ids, uniq_rows, n_uniq) of the last backward
         self._table_cache = None   # normalised compute-dtype item table for predict
         self._verbose = False
@@ -249,6 +252,29 @@ class HSTU(nn.Module):
                 bc[h * D:(h + 1) * D].copy_(lin.bias.data)
             w["heads_w"], w["heads_b"] = wc, bc
         return w
+
+    def shard_item_table(self, group=None):
+        """Keep only the rows `id % world == rank` of the item table on this rank.  Call after
+        .to(device).  Lookups / gradient rows then travel by all-to-all (parallel.ShardedTable)."""
+        W = parallel.world(group)
+        rank = torch.distributed.get_rank(group) if W > 1 else 0
+        full = self.item_embedding.weight.data
+        self.item_embedding.weight.data = parallel.ShardedTable.shard_of(full, W, rank)
+        self.sharded_table = parallel.ShardedTable(self.item_embedding.weight.data, self.item_num, group)
+        self._table_cache = None
+        return self
+
+    def _table_rows(self, items, neg_ids):
+        """Returns (table, item_index [B, LP], neg_index [sets, n_neg], uniq_ids or None): the tensor the
+        gather kernels read and the row indices into it.  Replicated table: the table itself and the ids.
+        Sharded table: the unique requested rows fetched by all-to-all and positions in that cache."""
+        if self.sharded_table is None:
+            return self.item_embedding.weight.data, items, neg_ids, None
+        B, LP = items.shape
+        all_ids = torch.cat([items.reshape(-1), neg_ids.reshape(-1)])
+        uniq, inv = torch.unique(all_ids, return_inverse=True)
+        cache = self.sharded_table.fetch(uniq)
+        return cache, inv[:B * LP].view(B, LP).contiguous(), inv[B * LP:].view(neg_ids.shape).contiguous(), uniq
 
     @staticmethod
     def _tokens(valid, force_last=False):
@@ -398,7 +424,13 @@ class HSTU(nn.Module):
         act, a_dt, st = self._act(), L.dt(self._act()), L.stream()
         items = items.contiguous()
         m = mask.bool()
-        W = self.item_embedding.weight.data
+        if self.share_negatives:
+            neg_items = parallel.gather_negative_ids(neg_items)      # [W*B, sets, n], hstu.py:673,755
+        n_sets = neg_items.shape[1]
+        n_neg = neg_items.shape[0] * neg_items.shape[2]
+        neg_ids = neg_items.permute(1, 0, 2).contiguous().view(n_sets, n_neg)   # set-major id lists
+        gl_items, gl_neg_ids = items, neg_ids                                   # global item ids
+        W, items, neg_ids, uniq_rows_ids = self._table_rows(items, neg_ids)
         ctx = {}
         # ---- jagged token index (valid context positions only)
         tok_b, tok_pos, seq_off, key_valid, T = self._tokens(m[:, :Lc])
@@ -427,11 +459,8 @@ class HSTU(nn.Module):
         tinv = torch.empty(B * LP, dtype=torch.float32, device=dev)
         L.call("b200rec_gather_l2norm", W.data_ptr(), None, D, flat_items.data_ptr(), B * LP, that.data_ptr(), a_dt,
                tinv.data_ptr(), st)
-        n_sets = neg_items.shape[1]
-        n_neg = B * neg_items.shape[2]
         n_words = (n_neg + 31) // 32
         ld_neg = n_words * 32
-        neg_ids = neg_items.permute(1, 0, 2).contiguous().view(n_sets, n_neg)   # set-major id lists
         used_sets = sorted({j.nset for j in self._jobs})
         nhat, ninv, bits, row_any = {}, {}, {}, {}
         for s in used_sets:
@@ -528,7 +557,8 @@ class HSTU(nn.Module):
             ctx = dict(B=B, LP=LP, T=T, tok_b=tok_b, tok_pos=tok_pos, seq_off=seq_off, key_valid=key_valid,
                        tok_index=tok_index, w=w, saved=saved, hd=hd, z=z, yb=yb, qhat=qhat, qinv=qinv, that=that,
                        tinv=tinv, nhat=nhat, ninv=ninv, neg_ids=neg_ids, job_out=job_out, scale=scale, half=half,
-                       items=items, mask=m, n_neg=n_neg, ld_neg=ld_neg, Hx=Hx, used_sets=used_sets)
+                       items=items, mask=m, n_neg=n_neg, ld_neg=ld_neg, Hx=Hx, used_sets=used_sets,
+                       gl_items=gl_items, gl_neg_ids=gl_neg_ids, uniq_rows_ids=uniq_rows_ids)
         return loss, logs, ctx
 
     def _train_backward(self, ctx, gscale):
@@ -600,31 +630,42 @@ class HSTU(nn.Module):
         L.call("b200rec_pos_emb_grad", dx0.data_ptr(), ctx["tok_index"].data_ptr(), B, LP, Lc, D, dpos.data_ptr(), st)
         grads[self.position_embedding.weight] = dpos
         # ---- item embedding: concatenate gradient rows + ids, one sorted-segment reduction
+        # `items` / `neg_ids` index the table the kernels read (global ids, or positions in the fetched-row
+        # cache of a sharded table); keys <= 0 carry no gradient (padding_idx 0, masked positions).
         items, m = ctx["items"], ctx["mask"]
+        sharded = ctx["uniq_rows_ids"] is not None
+        shift = 1 if sharded else 0          # cache position 0 is a real row: shift keys by one
         sets = ctx["used_sets"]
         n_rows = T + B * LP + len(sets) * n_neg
         rows = torch.empty((n_rows, D), dtype=torch.float32, device=dev)
         ids = torch.empty(n_rows, dtype=torch.int64, device=dev)
         rows[:T].copy_(dx0)
-        ids[:T] = items.reshape(-1)[ctx["tok_b"].long() * LP + ctx["tok_pos"].long()]
+        tok_flat = ctx["tok_b"].long() * LP + ctx["tok_pos"].long()
+        ids[:T] = items.reshape(-1)[tok_flat] + shift
         L.call("b200rec_l2norm_bwd", ctx["that"].data_ptr(), a_dt, ctx["tinv"].data_ptr(), dthat.data_ptr(), B * LP, D,
                rows[T:].data_ptr(), 0, st)
-        tgt_ids = torch.where(m, items, torch.full_like(items, -1))
-        tgt_ids[:, 0] = -1                       # position 0 is never a target
+        tgt_ids = torch.where(m, items + shift, torch.zeros_like(items))
+        tgt_ids[:, 0] = 0                        # position 0 is never a target
         ids[T:T + B * LP] = tgt_ids.reshape(-1)
         off = T + B * LP
         for s in sets:
             L.call("b200rec_l2norm_bwd", ctx["nhat"][s].data_ptr(), a_dt, ctx["ninv"][s].data_ptr(),
                    dnhat[s].data_ptr(), n_neg, D, rows[off:].data_ptr(), 0, st)
-            ids[off:off + n_neg] = ctx["neg_ids"][s]
+            ids[off:off + n_neg] = ctx["neg_ids"][s] + shift
             off += n_neg
-        ws_bytes = L.lib().b200rec_scatter_add_workspace_bytes(n_rows)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        uniq_ids = torch.empty(n_rows, dtype=torch.int64, device=dev)
-        uniq_rows = torch.empty((n_rows, D), dtype=torch.float32, device=dev)
-        n_uniq = torch.zeros(1, dtype=torch.int32, device=dev)
-        L.call("b200rec_scatter_add_sorted", ids.data_ptr(), n_rows, rows.data_ptr(), D, uniq_ids.data_ptr(),
-               uniq_rows.data_ptr(), n_uniq.data_ptr(), ws.data_ptr(), ws_bytes, st)
+        if sharded:                              # padding id 0 never gets a gradient
+            gl = torch.cat([ctx["gl_items"].reshape(-1)[tok_flat], ctx["gl_items"].reshape(-1)] +
+                           [ctx["gl_neg_ids"][s] for s in sets])
+            ids = torch.where(gl == 0, torch.zeros_like(ids), ids)
+        uniq_ids, uniq_rows, n_uniq = parallel.cuda_segment_reduce(ids, rows)
+        if sharded:
+            # one gradient row per fetched id, sent to the owners; the owner reduces over ranks (mean)
+            U = ctx["uniq_rows_ids"].numel()
+            g = torch.zeros((U, D), dtype=torch.float32, device=dev)
+            L.call("b200rec_rows_to_dense", (uniq_ids - 1).contiguous().data_ptr(), uniq_rows.data_ptr(),
+                   n_uniq.data_ptr(), n_rows, D, g.data_ptr(), 0, st)
+            self.emb_grad = self.sharded_table.push_grads(g, scale=1.0 / self.sharded_table.W)
+            return grads
         self.emb_grad = (uniq_ids, uniq_rows, n_uniq)
         if not self.sparse_embedding_grad:
             dense = torch.zeros_like(self.item_embedding.weight.data)
@@ -656,8 +697,12 @@ class HSTU(nn.Module):
         tok_b, tok_pos, seq_off, key_valid, T = self._tokens(item_seq != 0, force_last=True)
         w = self._cast_weights()
         x = torch.empty((T, D), dtype=torch.float32, device=dev)
-        L.call("b200rec_embed_tokens", self.item_embedding.weight.data_ptr(), self.position_embedding.weight.data_ptr(),
-               item_seq.data_ptr(), tok_b.data_ptr(), tok_pos.data_ptr(), T, Ls, D, x.data_ptr(), st)
+        table, seq_idx = self.item_embedding.weight.data, item_seq
+        if self.sharded_table is not None:
+            uniq, inv = torch.unique(item_seq.reshape(-1), return_inverse=True)
+            table, seq_idx = self.sharded_table.fetch(uniq), inv.view(B, Ls).contiguous()
+        L.call("b200rec_embed_tokens", table.data_ptr(), self.position_embedding.weight.data_ptr(),
+               seq_idx.data_ptr(), tok_b.data_ptr(), tok_pos.data_ptr(), T, Ls, D, x.data_ptr(), st)
         y, _ = self._body_forward(x, w, seq_off, key_valid, B, T, Ls, Ls, False)
         last = (seq_off[1:] - 1).long()
         y_last = torch.empty((B, D), dtype=torch.float32, device=dev)
@@ -729,29 +774,59 @@ class HSTU(nn.Module):
     def predict_topk(self, item_seq, all_item_feature, all_item_tags, target_tags, history_index=None, K=200,
                      split_mode="combine", user_chunk=None):
         """Fused eval entry: masks (prior / id 0 / history) + cross-head merge + top-K without returning
-        the [B, H, N] tensor.  Returns (topk_idx i64 [B,K], topk_val f32 [B,K], topk_head i32 [B,K])."""
+        the [B, H, N] tensor.  Returns (topk_idx i64 [B,K], topk_val f32 [B,K], topk_head i32 [B,K]).
+        With a row-sharded table (`shard_item_table`) `all_item_feature` / `all_item_tags` are this rank's
+        rows (`id % W == rank`); every rank scores all ranks' users against its rows and the per-shard
+        lists are exchanged and merged (value desc, id asc)."""
         U = self.user_heads(item_seq)
         B, H, D = U.shape
         dev = U.device
+        head_cat, bits, head_on = self.eval_masks(all_item_tags, target_tags, B, dev)
+        hu = hi = None
+        if history_index is not None:
+            hu, hi = history_index[0].to(torch.int64), history_index[1].to(torch.int64)
+        st_ = self.sharded_table
+        Wd, rank = (st_.W, st_.rank) if st_ is not None else (1, 0)
+        if Wd > 1:
+            import torch.distributed as dist
+            g = st_.group
+
+            def gather_cat(t):
+                out = [torch.empty_like(t) for _ in range(Wd)]
+                dist.all_gather(out, t.contiguous(), group=g)
+                return torch.cat(out, dim=0)
+
+            U = gather_cat(U)
+            if head_on is not None:
+                head_on = gather_cat(head_on)
+            if hu is not None:   # ragged (user, item) pairs: pad to the max count, shift users by rank*B
+                cnt = torch.tensor([hu.numel()], device=dev)
+                cnts = [torch.zeros_like(cnt) for _ in range(Wd)]
+                dist.all_gather(cnts, cnt, group=g)
+                mx = max(int(c.item()) for c in cnts)
+                pu = torch.full((mx,), -1, dtype=torch.int64, device=dev)
+                pi = torch.zeros((mx,), dtype=torch.int64, device=dev)
+                pu[:hu.numel()] = hu + rank * B
+                pi[:hi.numel()] = hi
+                pu, pi = gather_cat(pu), gather_cat(pi)
+                hu, hi = pu[pu >= 0], pi[pu >= 0]
+        Ball = U.shape[0]
         table = self._table_hat(all_item_feature)
         N = table.shape[0]
-        head_cat, bits, head_on = self.eval_masks(all_item_tags, target_tags, B, dev)
         hist_off = hist_items = None
-        if history_index is not None:
-            hu, hi = history_index
+        if hu is not None:
             order = torch.argsort(hu, stable=True)
-            hist_items = hi[order].to(torch.int64).contiguous()
-            counts = torch.bincount(hu, minlength=B)
-            hist_off = torch.zeros(B + 1, dtype=torch.int32, device=dev)
-            hist_off[1:] = counts.cumsum(0).to(torch.int32)
-        idx = torch.empty((B, K), dtype=torch.int64, device=dev)
-        val = torch.empty((B, K), dtype=torch.float32, device=dev)
-        hsrc = torch.empty((B, K), dtype=torch.int32, device=dev)
+            hist_items = hi[order].contiguous()
+            hist_off = torch.zeros(Ball + 1, dtype=torch.int32, device=dev)
+            hist_off[1:] = torch.bincount(hu, minlength=Ball).cumsum(0).to(torch.int32)
+        idx = torch.empty((Ball, K), dtype=torch.int64, device=dev)
+        val = torch.empty((Ball, K), dtype=torch.float32, device=dev)
+        hsrc = torch.empty((Ball, K), dtype=torch.int32, device=dev)
         if user_chunk is None:
-            user_chunk = max(1, min(B, int((8 << 30) // max(1, H * N * 4))))
+            user_chunk = max(1, min(Ball, int((8 << 30) // max(1, H * N * 4))))
         mode = 1 if (split_mode == "average" and H > 1) else 0
-        for b0 in range(0, B, user_chunk):
-            b1 = min(B, b0 + user_chunk)
+        for b0 in range(0, Ball, user_chunk):
+            b1 = min(Ball, b0 + user_chunk)
             nb = b1 - b0
             scores = torch.empty((nb * H, N), dtype=torch.float32, device=dev)
             L.gemm(U[b0:b1].reshape(nb * H, D), table, scores, nb * H, N, D, lda=D, ldb=D, ldc=N)
@@ -760,9 +835,19 @@ class HSTU(nn.Module):
             ho = hist_off[b0:b1 + 1].contiguous() if hist_off is not None else None
             L.call("b200rec_score_mask_topk", scores.data_ptr(), N, nb, H, N, K, L.ptr(head_cat), L.ptr(bits),
                    L.ptr(head_on[b0:b1].contiguous() if head_on is not None else None), L.ptr(ho), L.ptr(hist_items),
-                   mode, idx[b0:b1].data_ptr(), val[b0:b1].data_ptr(), hsrc[b0:b1].data_ptr(), ws.data_ptr(),
-                   ws_bytes, L.stream())
-        return idx, val, hsrc
+                   mode, rank, Wd, idx[b0:b1].data_ptr(), val[b0:b1].data_ptr(), hsrc[b0:b1].data_ptr(),
+                   ws.data_ptr(), ws_bytes, L.stream())
+        if Wd == 1:
+            return idx, val, hsrc
+        # exchange: block w of my lists (users of rank w) goes to rank w; I receive every shard's list of my users
+        import torch.distributed as dist
+        outs = []
+        for t in (val, idx, hsrc):
+            r = torch.empty_like(t)
+            dist.all_to_all_single(r, t.contiguous(), group=st_.group)
+            outs.append(r.view(Wd, B, K))
+        v, i, h = outs
+        return parallel.merge_topk(list(v), list(i), list(h), K)
 
     def get_attention_mask(self, item_seq, bidirectional=False):
         """hstu.py:1023-1030 (API parity; the kernels take seq_off / key_valid instead)."""

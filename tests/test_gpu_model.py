@@ -215,3 +215,32 @@ def test_medium_shapes_against_oracle():
                 continue
             cos = float((g @ r) / (g.norm() * r.norm() + 1e-30))
             assert cos > ctol, (dtype, k, cos)
+
+
+@pytest.mark.parametrize("name", ["prior_additive", "nce_pred4"])
+def test_sharded_table_world1_equals_replicated(name):
+    """shard_item_table() on one rank routes every lookup / gradient through the fetch-cache path."""
+    fx = load_golden(name)
+    cfg, model = build(fx, torch.float32, sparse_embedding_grad=True)
+    model.shard_item_table()
+    out = model(to_dev(fx["train_batch"]))
+    assert abs(float(out["loss"]) - fx["loss"]) <= 2e-5 * max(1.0, abs(fx["loss"]))
+    out["loss"].backward()
+    lid, lrows, nu = model.emb_grad
+    k = int(nu.item())
+    dense = torch.zeros_like(fx["grads"]["item_embedding.weight"])
+    dense[lid[:k].cpu()] = lrows[:k].cpu()
+    ref = fx["grads"]["item_embedding.weight"]
+    assert (dense - ref).abs().max().item() < 2e-4 * ref.abs().max().item()
+    g = model._hstu._attention_layers[0]._uvqk.grad.cpu()
+    r = fx["grads"]["_hstu._attention_layers.0._uvqk"]
+    assert (g - r).abs().max().item() < 2e-4 * r.abs().max().item()
+    # eval through the sharded entry
+    ev, all_item_tags, _ = _eval_inputs(fx, cfg)
+    feat = model.compute_item_all()
+    hu, hi = ev["history_index"]
+    idx, val, hs = model.predict_topk(ev["item_seq"].to(dev()), feat, all_item_tags, ev["target_tags"].to(dev()),
+                                      history_index=(hu.to(dev()), hi.to(dev())), K=max(cfg["topk"]))
+    from oracle import hstu_oracle as orc
+    ref_idx, _, _ = orc.collect_topk(fx["scores"], max(cfg["topk"]), cfg["split_mode"])
+    assert np.array_equal(idx.cpu().numpy(), ref_idx)

@@ -348,7 +348,7 @@ def test_score_mask_topk_matches_torch(B, H, N, K):
     wsb = L.lib().b200rec_topk_workspace_bytes(B, N)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev())
     L.call("b200rec_score_mask_topk", scores.data_ptr(), N, B, H, N, K, head_cat.data_ptr(), bits.data_ptr(),
-           head_on.data_ptr(), hist_off.data_ptr(), hist_items.data_ptr(), 0, idx.data_ptr(), val.data_ptr(),
+           head_on.data_ptr(), hist_off.data_ptr(), hist_items.data_ptr(), 0, 0, 1, idx.data_ptr(), val.data_ptr(),
            hs.data_ptr(), ws.data_ptr(), wsb, L.stream())
     s = scores.view(B, H, N).clone()
     tg = tags.to(dev())
@@ -377,7 +377,7 @@ def test_topk_ties_and_neg_inf_rule():
     hs = torch.empty(B, K, dtype=torch.int32, device=dev())
     wsb = L.lib().b200rec_topk_workspace_bytes(B, N)
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev())
-    L.call("b200rec_score_mask_topk", scores.data_ptr(), N, B, H, N, K, None, None, None, None, None, 0,
+    L.call("b200rec_score_mask_topk", scores.data_ptr(), N, B, H, N, K, None, None, None, None, None, 0, 0, 1,
            idx.data_ptr(), val.data_ptr(), hs.data_ptr(), ws.data_ptr(), wsb, L.stream())
     assert idx[0].tolist() == [300, 7, 9] + [i for i in range(N) if i not in (7, 9, 300)][:K - 3]
     assert idx[1].tolist() == list(range(10, 10 + K))

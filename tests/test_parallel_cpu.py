@@ -80,3 +80,77 @@ def test_dp_gradient_exchange_world2():
     dense /= 2
     assert torch.allclose(m0, dense[u0], atol=1e-6)
     assert set(u0.tolist()) == set(ids0.tolist()) | set(ids1.tolist())
+
+
+# ---------------------------------------------------------------------------- sharded table routing
+def _torch_row_gather(table, idx):
+    return table[idx].clone()
+
+
+def _torch_segment_reduce(ids, rows):
+    keep = ids > 0
+    uniq, inv = torch.unique(ids[keep], return_inverse=True)
+    out = torch.zeros(uniq.numel(), rows.shape[1]).index_add_(0, inv, rows[keep])
+    return uniq, out, torch.tensor([uniq.numel()], dtype=torch.int32)
+
+
+def _shard_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from b200rec import parallel
+    N, D = 23, 4
+    full = torch.arange(N * D, dtype=torch.float32).view(N, D)
+    st = parallel.ShardedTable(parallel.ShardedTable.shard_of(full, world, rank), N, None,
+                               row_gather=_torch_row_gather, segment_reduce=_torch_segment_reduce)
+    g = torch.Generator().manual_seed(7 + rank)
+    ids = torch.unique(torch.randint(0, N, (11,), generator=g))
+    rows = st.fetch(ids)
+    ok_fetch = torch.equal(rows, full[ids])
+    grads = torch.randn(ids.numel(), D, generator=g)
+    lid, lrows, nu = st.push_grads(grads, scale=0.5)
+    negs = parallel.gather_negative_ids(torch.full((2, 3, 2), rank, dtype=torch.int64))
+    q.put((rank, ok_fetch, ids, grads, lid[: int(nu)], lrows[: int(nu)], negs))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_table_fetch_and_push_world2():
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    N, D, W = 23, 4, 2
+    dense = torch.zeros(N, D)
+    for rank, ok, ids, grads, *_ in res:
+        assert ok
+        dense.index_add_(0, ids, grads)
+    dense *= 0.5
+    dense[0] = 0                                     # padding id 0 never gets a gradient
+    for rank, ok, ids, grads, lid, lrows, negs in res:
+        got = torch.zeros(N, D)
+        got[lid * W + rank] = lrows                  # local row r of rank k is global id r*W + k
+        want = torch.zeros(N, D)
+        want[rank::W] = dense[rank::W]
+        assert torch.allclose(got, want, atol=1e-6)
+        assert negs.shape == (4, 3, 2) and torch.equal(negs[:2], torch.zeros(2, 3, 2, dtype=torch.int64)) \
+            and torch.equal(negs[2:], torch.ones(2, 3, 2, dtype=torch.int64))
+
+
+def test_merge_topk_tie_rule():
+    from b200rec import parallel
+    v0 = torch.tensor([[5.0, 3.0, float("-inf")]])
+    i0 = torch.tensor([[4, 2, 0]])
+    v1 = torch.tensor([[5.0, 4.0, 3.0]])
+    i1 = torch.tensor([[1, 7, 9]])
+    h = torch.zeros(1, 3, dtype=torch.int32)
+    idx, val, _ = parallel.merge_topk([v0, v1], [i0, i1], [h, h], 4)
+    assert idx.tolist() == [[1, 4, 7, 2]] and val.tolist() == [[5.0, 5.0, 4.0, 3.0]]
