@@ -47,13 +47,24 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
   }
 }
 
+__global__ void __launch_bounds__(256) adamw_scalar_kernel(float* __restrict__ p, float* __restrict__ m,
+                                                           float* __restrict__ v, const float* __restrict__ g,
+                                                           int64_t n, AdamCoef c) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    adam_update(p[i], m[i], v[i], g[i], c);
+}
+
 int b200rec_adamw(float* p, float* m, float* v, const float* g, int64_t n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int step, float grad_scale, void* stream) {
   if (n == 0) return 0;
-  B200_CHECK_ARG(((uintptr_t)p & 15) == 0 && ((uintptr_t)m & 15) == 0 && ((uintptr_t)v & 15) == 0 &&
-                     ((uintptr_t)g & 15) == 0,
-                 "adamw: pointers must be 16-byte aligned");
   AdamCoef c = make_coef(lr, beta1, beta2, eps, weight_decay, step, grad_scale);
+  if ((((uintptr_t)p | (uintptr_t)m | (uintptr_t)v | (uintptr_t)g) & 15) != 0) {  // unaligned view: scalar path
+    adamw_scalar_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(p, m, v, g,
+                                                                                                           n, c);
+    B200_LAUNCH_OK();
+    return 0;
+  }
   int blocks = (int)std::min<int64_t>((n / 4 + 255) / 256 + 1, 148 * 16);
   adamw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, m, v, g, n, c);
   B200_LAUNCH_OK();

@@ -73,14 +73,15 @@ def flatten_dense_grads(params):
     with_grad = [p for p in params if p.grad is not None]
     if not with_grad:
         return None, []
-    total = sum(p.grad.numel() for p in with_grad)
-    flat = torch.empty(total, dtype=torch.float32, device=with_grad[0].grad.device)
+    # every view starts on a 16-byte boundary (vector loads in the fused optimizer)
+    total = sum((p.grad.numel() + 3) // 4 * 4 for p in with_grad)
+    flat = torch.zeros(total, dtype=torch.float32, device=with_grad[0].grad.device)
     off = 0
     for p in with_grad:
         n = p.grad.numel()
         flat[off:off + n].copy_(p.grad.reshape(-1))
         p.grad = flat[off:off + n].view_as(p.grad)
-        off += n
+        off += (n + 3) // 4 * 4
     return flat, with_grad
 
 
