@@ -118,6 +118,15 @@ enum {
   B200REC_EPI_RESBLOCK = 4,   /* z = acc + bias[n]; C2 = z; C = resid[m, n % n_split] + silu(z) */
   B200REC_EPI_GT_BITS = 5     /* C is uint32 [M, N/32]: bit (n%32) of word n/32 = acc > alpha;
                                  optional C2 = u8[M], set to 1 for rows with any bit (zero it first) */
+  ,
+  B200REC_EPI_FOLD_HEADS = 6  /* eval scoring (hstu.py:979-999 + collector.py:241-275 fused): rows are
+                                 (user, head) with `fold_hp` (power of two <= 32) rows per user; per item
+                                 column the masked max over the user's heads goes to C = fval fp32
+                                 [M/fold_hp, N] and the arg-max head to C2 = fhead u8 [M/fold_hp, N].
+                                 Masks: fold_head_on[m] (u8, 0 = head off / padding row),
+                                 fold_head_cat[h] (category gating head h, -1 none) against
+                                 fold_item_tags[n] (bit c = item n has tag c), global item id 0
+                                 (n*fold_id_stride + fold_id_offset == 0).  bf16 (tcgen05) path only. */
 };
 typedef struct {
   int M, N, K;
@@ -135,6 +144,10 @@ typedef struct {
    * of a [T, H*D] output).  If additionally c_split_stride > 0, column n is stored at
    * C + (n / n_split) * c_split_stride + m*ldc + n % n_split (per-head [H, T, D] blocks). */
   int n_split; int64_t c_split_stride; int64_t c2_split_stride;
+  /* B200REC_EPI_FOLD_HEADS only */
+  int fold_hp;
+  const uint8_t* fold_head_on; const int32_t* fold_head_cat; const uint32_t* fold_item_tags;
+  int64_t fold_id_offset; int64_t fold_id_stride;
 } b200rec_gemm_args;
 int b200rec_gemm(const b200rec_gemm_args* args, void* stream);
 
@@ -227,6 +240,12 @@ int b200rec_score_mask_topk(const float* scores, int64_t ld_scores, int B, int H
                             const int64_t* hist_items, int split_mode, int64_t id_offset,
                             int64_t id_stride, int64_t* topk_idx, float* topk_val, int32_t* topk_head,
                             void* workspace, size_t workspace_bytes, void* stream);
+/* Second half of b200rec_score_mask_topk for scores already folded over heads (B200REC_EPI_FOLD_HEADS):
+ * history suppression on fval, then per-user radix select + sort.  Same tie rule and id mapping. */
+int b200rec_topk_select(float* fval, const uint8_t* fhead, int B, int64_t N, int K,
+                        const int32_t* hist_off, const int64_t* hist_items, int64_t id_offset,
+                        int64_t id_stride, int64_t* topk_idx, float* topk_val, int32_t* topk_head,
+                        void* stream);
 /* In-place masks for the reference-compatible predict() that returns [B,H,N] scores
  * (hstu.py:983-999): rows of switched-off heads and items outside the head's category -> -inf. */
 int b200rec_apply_score_masks(float* scores, int64_t ld_scores, int B, int H, int64_t N,

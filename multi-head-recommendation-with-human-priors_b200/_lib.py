@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200rec.so")
 
 F32, BF16 = 0, 1
-EPI_STORE, EPI_ACCUM, EPI_SILU_DUAL, EPI_BIAS_RESID, EPI_RESBLOCK, EPI_GT_BITS = range(6)
+EPI_STORE, EPI_ACCUM, EPI_SILU_DUAL, EPI_BIAS_RESID, EPI_RESBLOCK, EPI_GT_BITS, EPI_FOLD_HEADS = range(7)
 
 _lib = None
 launches = 0  # number of C-ABI kernel entry points invoked (bench.py's gpu_launches claim)
@@ -37,6 +37,9 @@ class GemmArgs(C.Structure):
         ("bias", C.c_void_p),
         ("resid", C.c_void_p), ("ldr", C.c_int64),
         ("n_split", C.c_int), ("c_split_stride", C.c_int64), ("c2_split_stride", C.c_int64),
+        ("fold_hp", C.c_int),
+        ("fold_head_on", C.c_void_p), ("fold_head_cat", C.c_void_p), ("fold_item_tags", C.c_void_p),
+        ("fold_id_offset", C.c_int64), ("fold_id_stride", C.c_int64),
     ]
 
 
@@ -77,6 +80,7 @@ _SIGS = {
     "b200rec_topk_workspace_bytes": (_Z, [_I, _L]),
     "b200rec_score_mask_topk": (C.c_int, [_P, _L, _I, _I, _L, _I, _P, _P, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _Z,
                                           _P]),
+    "b200rec_topk_select": (C.c_int, [_P, _P, _I, _L, _I, _P, _P, _L, _L, _P, _P, _P, _P]),
     "b200rec_apply_score_masks": (C.c_int, [_P, _L, _I, _I, _L, _P, _P, _P, _P]),
     "b200rec_hit_matrix": (C.c_int, [_P, _P, _I, _I, _I, _P, _I, _P, _P]),
     "b200rec_adamw": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
@@ -133,7 +137,7 @@ def call(name, *args):
 
 
 def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epilogue=EPI_STORE, alpha=1.0,
-         alpha_dev=None, bias=None, resid=None, ldr=0, C2=None, ldc2=0, n_split=0, c_dtype=None):
+         alpha_dev=None, bias=None, resid=None, ldr=0, C2=None, ldc2=0, n_split=0, c_dtype=None, fold=None):
     """C[M,N] = epi(A[M,K] @ B[N,K]^T).  A/B are tensors (or views) whose data_ptr is element (0,0)."""
     global launches
     a = GemmArgs()
@@ -144,9 +148,13 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epilogue=
     if dt(B) != a.in_dtype:
         raise B200RecError("gemm: A and B dtypes differ")
     a.C, a.ldc = C_out.data_ptr(), ldc
-    a.c_dtype = F32 if epilogue == EPI_GT_BITS else (dt(C_out) if c_dtype is None else c_dtype)
+    raw_out = epilogue in (EPI_GT_BITS, EPI_FOLD_HEADS)
+    a.c_dtype = F32 if raw_out else (dt(C_out) if c_dtype is None else c_dtype)
     a.C2, a.ldc2 = ptr(C2), ldc2
-    a.c2_dtype = dt(C2) if (C2 is not None and epilogue != EPI_GT_BITS) else F32
+    a.c2_dtype = dt(C2) if (C2 is not None and not raw_out) else F32
+    if fold is not None:   # (hp, head_on u8[M], head_cat i32[hp] or None, item_tags u32[N] or None, id_offset, id_stride)
+        a.fold_hp, a.fold_head_on, a.fold_head_cat, a.fold_item_tags = fold[0], ptr(fold[1]), ptr(fold[2]), ptr(fold[3])
+        a.fold_id_offset, a.fold_id_stride = fold[4], fold[5]
     a.epilogue, a.alpha = epilogue, alpha
     a.alpha_dev = ptr(alpha_dev)
     a.bias, a.resid, a.ldr = ptr(bias), ptr(resid), ldr

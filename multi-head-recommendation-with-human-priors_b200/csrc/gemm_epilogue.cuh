@@ -12,6 +12,10 @@ struct EpiParams {
   int n_split; int64_t c_split_stride, c2_split_stride;
   int M, N;
   int vec_ok;  // host-checked: every pointer / leading dimension allows 4-element vector access
+  // B200REC_EPI_FOLD_HEADS
+  int fold_hp;
+  const uint8_t* fold_head_on; const int32_t* fold_head_cat; const uint32_t* fold_item_tags;
+  int64_t fold_id_offset, fold_id_stride;
 };
 
 __device__ __forceinline__ void epi_store_scalar(void* base, int dtype, int64_t off, float v) {

@@ -177,6 +177,72 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         __syncwarp();
         // phase 2: 8 lanes cover one 128-byte row segment, 4 rows per pass
         const int ncol = n0 + c * 32 + cg * 4;
+        if (MODE == B200REC_EPI_FOLD_HEADS) {
+          // rows of this warp = 32/hp users x hp heads.  Lane (cg, sub) folds rows [8*sub, 8*sub+8) of its
+          // 4 columns; partial results of one user are combined across sub-lanes with shuffles.
+          const int hp = ep.fold_hp;
+          const int mrow0 = m0 + quarter * 32;
+          uint32_t tg[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+          bool colok[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int n = ncol + i;
+            colok[i] = n < ep.N && ((int64_t)n * ep.fold_id_stride + ep.fold_id_offset != 0);
+            if (ep.fold_item_tags && n < ep.N) tg[i] = __ldg(ep.fold_item_tags + n);
+          }
+          const int grp = hp >= 8 ? 8 : hp;            // rows folded sequentially by one lane
+#pragma unroll 1
+          for (int g = 0; g < 8 / grp; ++g) {
+            float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            int bh[4] = {0, 0, 0, 0};
+            for (int r = 0; r < grp; ++r) {
+              const int row = sub * 8 + g * grp + r;
+              const int m = mrow0 + row;
+              const int h = row & (hp - 1);
+              const uint32_t addr = stg + (uint32_t)row * 128u + (uint32_t)((cg ^ (row & 7)) << 4);
+              float x[4];
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3])
+                           : "r"(addr)
+                           : "memory");
+              const bool on = m < ep.M && __ldg(ep.fold_head_on + m) != 0;
+              const int cat = ep.fold_head_cat ? __ldg(ep.fold_head_cat + h) : -1;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const bool keep = on && colok[i] && (cat < 0 || ((tg[i] >> cat) & 1u));
+                const float v = keep ? x[i] : -INFINITY;
+                if (v > best[i]) { best[i] = v; bh[i] = h; }   // strict >: lowest head wins ties
+              }
+            }
+            // hp > 8: the user's heads are spread over hp/8 sub-lanes (lane stride 8)
+            for (int o = 8; o < hp; o <<= 1) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float ov = __shfl_xor_sync(0xffffffffu, best[i], o);
+                const int oh = __shfl_xor_sync(0xffffffffu, bh[i], o);
+                if (ov > best[i] || (ov == best[i] && oh < bh[i])) { best[i] = ov; bh[i] = oh; }
+              }
+            }
+            const int subs_per_user = hp >= 8 ? hp / 8 : 1;
+            if ((sub % subs_per_user) == 0) {
+              const int row_first = sub * 8 + g * grp;
+              const int64_t user = (int64_t)(mrow0 + row_first) / hp;
+              if (mrow0 + row_first < ep.M && ncol < ep.N) {
+                float* fv = (float*)ep.C + user * ep.ldc + ncol;
+                uint8_t* fh = (uint8_t*)ep.C2 + user * ep.ldc2 + ncol;
+                if (ncol + 4 <= ep.N) {
+                  store4<float>(fv, best);
+                  *reinterpret_cast<uint32_t*>(fh) = (uint32_t)bh[0] | ((uint32_t)bh[1] << 8) | ((uint32_t)bh[2] << 16) |
+                                                     ((uint32_t)bh[3] << 24);
+                } else {
+                  for (int i = 0; i < 4 && ncol + i < ep.N; ++i) { fv[i] = best[i]; fh[i] = (uint8_t)bh[i]; }
+                }
+              }
+            }
+          }
+          __syncwarp();
+          continue;
+        }
         if (epi_needs_prefetch<MODE>()) {
           // issue every row-dependent global load of the chunk before consuming any (latency overlap)
           float pre[8][4];
@@ -290,6 +356,7 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep, cudaStream_t
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
   }
   TcParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
@@ -331,6 +398,7 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep, cudaStream_t
     case B200REC_EPI_BIAS_RESID: gemm_tc_kernel<3><<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep); break;
     case B200REC_EPI_RESBLOCK: gemm_tc_kernel<4><<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep); break;
     case B200REC_EPI_GT_BITS: gemm_tc_kernel<5><<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep); break;
+    case B200REC_EPI_FOLD_HEADS: gemm_tc_kernel<6><<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep); break;
     default: b200rec_set_error("gemm: bad epilogue %d", ep.mode); return 1;
   }
   B200_LAUNCH_OK();

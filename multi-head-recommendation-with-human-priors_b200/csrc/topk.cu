@@ -198,6 +198,19 @@ int b200rec_score_mask_topk(const float* scores, int64_t ld_scores, int B, int H
   return 0;
 }
 
+int b200rec_topk_select(float* fval, const uint8_t* fhead, int B, int64_t N, int K, const int32_t* hist_off,
+                        const int64_t* hist_items, int64_t id_offset, int64_t id_stride, int64_t* topk_idx,
+                        float* topk_val, int32_t* topk_head, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CHECK_ARG(K >= 1 && K <= SEL_MAXK && K <= N, "topk_select: K=%d not in [1,%d] or > N", K, SEL_MAXK);
+  B200_CHECK_ARG(N < (1ll << 32) && id_stride >= 1 && id_offset >= 0, "topk_select: bad N / id mapping");
+  if (B == 0) return 0;
+  if (hist_off && hist_items) suppress_history_kernel<<<B, 128, 0, st>>>(hist_off, hist_items, B, N, fval, 0, id_offset, id_stride);
+  select_topk_kernel<<<B, SEL_THREADS, 0, st>>>(fval, fhead, N, K, id_offset, id_stride, topk_idx, topk_val, topk_head);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
 // ---- hit matrix (collector.py:300-316) -----------------------------------------------------------
 __global__ void hit_matrix_kernel(const int64_t* __restrict__ topk_idx, const int64_t* __restrict__ positive_i, int B,
                                   int K, int Pe, int p, int32_t* __restrict__ out) {

@@ -177,6 +177,7 @@ class HSTU(nn.Module):
             torch.ones((self.max_seq_length, self.max_seq_length), dtype=torch.bool), diagonal=1))
         self.sparse_embedding_grad = bool(config.get("sparse_embedding_grad", False))
         self.use_tc_attention = bool(config.get("tc_attention", True))
+        self.use_fused_eval = bool(config.get("fused_eval", True))
         self.share_negatives = bool(config.get("share_negatives", True))   # all-gather negatives across ranks
         self.sharded_table = None  # parallel.ShardedTable once shard_item_table() was called
         self.emb_grad = None       # (uniq_ids, uniq_rows, n_uniq) of the last backward
@@ -822,21 +823,50 @@ class HSTU(nn.Module):
         idx = torch.empty((Ball, K), dtype=torch.int64, device=dev)
         val = torch.empty((Ball, K), dtype=torch.float32, device=dev)
         hsrc = torch.empty((Ball, K), dtype=torch.int32, device=dev)
-        if user_chunk is None:
-            user_chunk = max(1, min(Ball, int((8 << 30) // max(1, H * N * 4))))
         mode = 1 if (split_mode == "average" and H > 1) else 0
-        for b0 in range(0, Ball, user_chunk):
-            b1 = min(Ball, b0 + user_chunk)
-            nb = b1 - b0
-            scores = torch.empty((nb * H, N), dtype=torch.float32, device=dev)
-            L.gemm(U[b0:b1].reshape(nb * H, D), table, scores, nb * H, N, D, lda=D, ldb=D, ldc=N)
-            ws_bytes = L.lib().b200rec_topk_workspace_bytes(nb, N)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            ho = hist_off[b0:b1 + 1].contiguous() if hist_off is not None else None
-            L.call("b200rec_score_mask_topk", scores.data_ptr(), N, nb, H, N, K, L.ptr(head_cat), L.ptr(bits),
-                   L.ptr(head_on[b0:b1].contiguous() if head_on is not None else None), L.ptr(ho), L.ptr(hist_items),
-                   mode, rank, Wd, idx[b0:b1].data_ptr(), val[b0:b1].data_ptr(), hsrc[b0:b1].data_ptr(),
-                   ws.data_ptr(), ws_bytes, L.stream())
+        fused = self._act() == torch.bfloat16 and mode == 0 and H <= 32 and N % 4 == 0 and self.use_fused_eval
+        if fused:
+            # scoring GEMM with the fold-heads epilogue: [Ball*hp, D] x [N, D]^T -> (max, argmax head) per item;
+            # the [B, H, N] score tensor is never written.
+            hp = 1
+            while hp < H:
+                hp *= 2
+            Up = torch.zeros((Ball, hp, D), dtype=U.dtype, device=dev)
+            Up[:, :H] = U
+            on = torch.zeros((Ball, hp), dtype=torch.uint8, device=dev)
+            on[:, :H] = head_on if head_on is not None else 1
+            cat = None
+            if head_cat is not None:
+                cat = torch.full((hp,), -1, dtype=torch.int32, device=dev)
+                cat[:H] = head_cat
+            if user_chunk is None:
+                user_chunk = max(1, min(Ball, int((8 << 30) // max(1, N * 5))))
+            for b0 in range(0, Ball, user_chunk):
+                b1 = min(Ball, b0 + user_chunk)
+                nb = b1 - b0
+                fval = torch.empty((nb, N), dtype=torch.float32, device=dev)
+                fhead = torch.empty((nb, N), dtype=torch.uint8, device=dev)
+                L.gemm(Up[b0:b1].reshape(nb * hp, D), table, fval, nb * hp, N, D, lda=D, ldb=D, ldc=N,
+                       epilogue=L.EPI_FOLD_HEADS, C2=fhead, ldc2=N,
+                       fold=(hp, on[b0:b1].reshape(-1).contiguous(), cat, bits, rank, Wd))
+                ho = hist_off[b0:b1 + 1].contiguous() if hist_off is not None else None
+                L.call("b200rec_topk_select", fval.data_ptr(), fhead.data_ptr(), nb, N, K, L.ptr(ho), L.ptr(hist_items),
+                       rank, Wd, idx[b0:b1].data_ptr(), val[b0:b1].data_ptr(), hsrc[b0:b1].data_ptr(), L.stream())
+        else:
+            if user_chunk is None:
+                user_chunk = max(1, min(Ball, int((8 << 30) // max(1, H * N * 4))))
+            for b0 in range(0, Ball, user_chunk):
+                b1 = min(Ball, b0 + user_chunk)
+                nb = b1 - b0
+                scores = torch.empty((nb * H, N), dtype=torch.float32, device=dev)
+                L.gemm(U[b0:b1].reshape(nb * H, D), table, scores, nb * H, N, D, lda=D, ldb=D, ldc=N)
+                ws_bytes = L.lib().b200rec_topk_workspace_bytes(nb, N)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                ho = hist_off[b0:b1 + 1].contiguous() if hist_off is not None else None
+                L.call("b200rec_score_mask_topk", scores.data_ptr(), N, nb, H, N, K, L.ptr(head_cat), L.ptr(bits),
+                       L.ptr(head_on[b0:b1].contiguous() if head_on is not None else None), L.ptr(ho),
+                       L.ptr(hist_items), mode, rank, Wd, idx[b0:b1].data_ptr(), val[b0:b1].data_ptr(),
+                       hsrc[b0:b1].data_ptr(), ws.data_ptr(), ws_bytes, L.stream())
         if Wd == 1:
             return idx, val, hsrc
         # exchange: block w of my lists (users of rank w) goes to rank w; I receive every shard's list of my users

@@ -244,3 +244,58 @@ def test_sharded_table_world1_equals_replicated(name):
     from oracle import hstu_oracle as orc
     ref_idx, _, _ = orc.collect_topk(fx["scores"], max(cfg["topk"]), cfg["split_mode"])
     assert np.array_equal(idx.cpu().numpy(), ref_idx)
+
+
+@pytest.mark.parametrize("name", ["prior_additive", "prior_mult", "prior_event_given", "nce_single"])
+def test_fused_eval_epilogue_bf16_matches_unfused(name):
+    """GEMM fold-heads epilogue (no [B,H,N] tensor) == scoring GEMM + fold kernel, same bf16 operands."""
+    fx = load_golden(name)
+    cfg, model = build(fx, torch.bfloat16)
+    ev, all_item_tags, _ = _eval_inputs(fx, cfg)
+    feat = model.compute_item_all()
+    hu, hi = ev["history_index"]
+    args = (ev["item_seq"].to(dev()), feat, all_item_tags, ev["target_tags"].to(dev()))
+    kw = dict(history_index=(hu.to(dev()), hi.to(dev())), K=max(cfg["topk"]))
+    model.use_fused_eval = True
+    i1, v1, h1 = model.predict_topk(*args, **kw)
+    model.use_fused_eval = False
+    i2, v2, h2 = model.predict_topk(*args, **kw)
+    assert torch.equal(i1, i2) and torch.equal(h1, h2)
+    assert torch.allclose(v1, v2, rtol=0, atol=1e-6) or torch.equal(torch.isinf(v1), torch.isinf(v2))
+
+
+def test_fused_eval_large_random():
+    """Fold epilogue against torch on a multi-tile problem (N not a tile multiple, 12 heads -> hp 16)."""
+    from b200rec import _lib as L
+    B, H, N, D, K = 37, 12, 10000, 128, 100
+    g = torch.Generator().manual_seed(5)
+    U = torch.randn(B, H, D, generator=g).to(torch.bfloat16).to(dev())
+    table = torch.randn(N, D, generator=g).to(torch.bfloat16).to(dev())
+    C = 8
+    tags = torch.rand(N, C, generator=g) < 0.4
+    bits = (tags.long() * (1 << torch.arange(C))).sum(1).to(torch.int32).to(dev())
+    cat = torch.tensor([-1] * 4 + list(range(8)), dtype=torch.int32, device=dev())
+    hp = 16
+    Up = torch.zeros(B, hp, D, dtype=torch.bfloat16, device=dev())
+    Up[:, :H] = U
+    on = torch.zeros(B, hp, dtype=torch.uint8, device=dev())
+    on[:, :H] = (torch.rand(B, H, generator=g) < 0.85).to(torch.uint8).to(dev())
+    catp = torch.full((hp,), -1, dtype=torch.int32, device=dev())
+    catp[:H] = cat
+    fval = torch.empty(B, N, device=dev())
+    fhead = torch.empty(B, N, dtype=torch.uint8, device=dev())
+    L.gemm(Up.view(B * hp, D), table, fval, B * hp, N, D, lda=D, ldb=D, ldc=N, epilogue=L.EPI_FOLD_HEADS, C2=fhead,
+           ldc2=N, fold=(hp, on.view(-1), catp, bits, 0, 1))
+    s = (U.float() @ table.float().t())                           # [B, H, N]
+    tg = tags.to(dev())
+    for h in range(H):
+        if int(cat[h]) >= 0:
+            s[:, h, ~tg[:, int(cat[h])]] = float("-inf")
+    s.masked_fill_(~on[:, :H].bool().unsqueeze(-1), float("-inf"))
+    s[:, :, 0] = float("-inf")
+    mx, am = s.max(dim=1)
+    assert torch.equal(torch.isinf(fval), torch.isinf(mx))
+    fin = torch.isfinite(mx)
+    assert (fval[fin] - mx[fin]).abs().max().item() < 2e-2
+    agree = (fhead.long() == am)[fin].float().mean().item()
+    assert agree > 0.999          # arg-max head may differ only on near-ties of bf16 products
