@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--eval-users", type=int, default=256)
+    ap.add_argument("--no-graph", action="store_true", help="run the eager step instead of the CUDA-graph step")
     ap.add_argument("--replicate-table", action="store_true", help="N>1: keep the item table replicated")
     ap.add_argument("--profile", action="store_true", help="print a per-kernel time table of one step (torch.profiler)")
     return ap.parse_args()
@@ -175,7 +176,9 @@ def main():
                             f"{cfg['num_prior_head']} {cfg['head_interaction']} negatives={cfg['num_negatives']}/set "
                             f"items={cfg['item_num']}",
                 "per_gpu_batch": cfg["train_batch_size"], "global_batch": cfg["train_batch_size"] * world,
-                "parallelism": f"dp{world}" + ("+row-sharded-table(a2a)" if world > 1 and not args.replicate_table else ""), "l2": "working set >> 126 MB L2 (activations + 1.8 GB table); no flush"}}
+                "parallelism": f"dp{world}" + ("+row-sharded-table(a2a)" if world > 1 and not args.replicate_table else ""), "l2": "working set >> 126 MB L2 (activations + 1.8 GB table); no flush",
+                "step": "cuda-graph replay per 128-token bucket" if (world == 1 and not args.no_graph and not args.profile)
+                else "eager"}}
     if args.impl == "reference":
         if rank != 0:
             return
@@ -203,7 +206,8 @@ def main():
     dl = synth.make_dataload(cfg)
     torch.manual_seed(2020)
     model = HSTU(cfg, dl, compute_dtype=dtype).to(dev).eval()   # eval(): dropout off
-    opt = FusedAdamW(model, lr=1e-4, weight_decay=0.0)
+    use_graph = (world == 1) and not args.no_graph and not args.profile
+    opt = FusedAdamW(model, lr=1e-4, weight_decay=0.0, device_step=use_graph)
     if world > 1 and not args.replicate_table:
         model.shard_item_table()          # rows id % W == rank; lookups / gradient rows by all-to-all
     dp = parallel.DataParallel(model, opt) if world > 1 else None
@@ -215,7 +219,14 @@ def main():
     dev_batches = [tuple(t.to(dev) for t in b) for b in host_batches]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host_batches[0])
 
-    def step(batch):
+    Lc = cfg["MAX_ITEM_LIST_LENGTH"]
+    n_tok = [int(b[2][:, :Lc].sum()) for b in host_batches]     # host metadata (the collate fn knows it)
+    stepper = None
+    if use_graph:
+        from b200rec.graphed import GraphedTrainStep
+        stepper = GraphedTrainStep(model, opt, dev_batches[0], bucket=128)
+
+    def eager_step(batch):
         opt.zero_grad()
         out = model(batch)
         out["loss"].backward()
@@ -224,18 +235,23 @@ def main():
         opt.step()
         return out["loss"]
 
+    def step(batch, i=None):
+        if stepper is not None:
+            return stepper(batch, n_tok[i])["loss"]
+        return eager_step(batch)
+
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step(dev_batches[i % n_batches])
+    for i in range(max(args.warmup, n_batches if use_graph else 0)):   # graph mode: capture every bucket first
+        step(dev_batches[i % n_batches], i % n_batches)
     barrier()
     if args.profile and rank == 0:
         from torch.profiler import profile, ProfilerActivity
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
-            step(dev_batches[0])
+            step(dev_batches[0], 0)
             torch.cuda.synchronize()
         print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=60),
               file=sys.stderr)
@@ -243,13 +259,16 @@ def main():
     if sampler:
         sampler.start()
     # ---- timed region 1: batch resident in HBM
-    L.gemm_timing = []
     launches0 = L.launches
+    if not use_graph:
+        L.gemm_timing = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    t_host0 = time.perf_counter()
     for i in range(args.steps):
-        loss = step(dev_batches[i % n_batches])
+        loss = step(dev_batches[i % n_batches], i % n_batches)
+    host_ms = (time.perf_counter() - t_host0) * 1e3      # host enqueue time (no sync): > GPU time means launch-bound
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -262,11 +281,21 @@ def main():
     f0.record()
     last = None
     for i in range(args.steps):
-        b = tuple(t.to(dev, non_blocking=True) for t in host_batches[i % n_batches])
-        last = float(step(b).item())           # D2H read of the step's loss
+        j = i % n_batches
+        b = host_batches[j] if use_graph else tuple(t.to(dev, non_blocking=True) for t in host_batches[j])
+        last = float(step(b, j).item())        # H2D of the pinned batch inside step; D2H read of the loss
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    if use_graph:
+        # kernels inside a replayed graph cannot be bracketed by events: time every GEMM launch of the same
+        # step in an instrumented eager pass right after the timed regions (same kernels, same shapes)
+        L.gemm_timing = []
+        for i in range(args.steps):
+            eager_step(dev_batches[i % n_batches])
+        torch.cuda.synchronize()
+        gemm_events = L.gemm_timing
+        L.gemm_timing = None
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -291,11 +320,13 @@ def main():
         "value": value, "ms_per_step": ms / args.steps, "dtype": args.dtype,
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches,
+        "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms / args.steps,
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all GEMM launches of the step)",
                      "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
                      "traffic": None, "peak_source": pk_src + ", sustained bf16",
                      "gemm_ms_per_step": gms / args.steps, "gemm_share_of_step": gms / ms if ms else None,
+                     "timing": ("instrumented eager pass after the timed region (the timed region replays CUDA graphs)"
+                                if use_graph else "CUDA events around every GEMM launch inside the timed region"),
                      "gemm_launches_per_step": len(gemm_events) / args.steps},
         "model_flops_utilisation": train_flops_per_sample(cfg) * value / 1e12 / peak if peak else None,
         "clocks": sampler.summary() if sampler else None,

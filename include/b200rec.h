@@ -258,15 +258,23 @@ int b200rec_hit_matrix(const int64_t* topk_idx, const int64_t* positive_i, int B
 
 /* ------------------------------------------------------------------ optimizer (§8 f N1)
  * torch.optim.AdamW semantics (trainer.py:296-299), fused single pass, fp32 state. */
+/* coef_dev (nullable): device fp32[4] = {lr, 1-beta1^t, sqrt(1-beta2^t), t} overriding lr / step, advanced
+ * by b200rec_adamw_tick — lets a captured CUDA graph contain the optimizer step. */
 int b200rec_adamw(float* p, float* m, float* v, const float* g, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int step, float grad_scale,
-                  void* stream);
+                  const float* coef_dev, void* stream);
+int b200rec_adamw_tick(float* coef_dev, float beta1, float beta2, void* stream);
+/* One launch for many dense tensors: table_dev = array of {float* p, m, v; const float* g; int64 n},
+ * blocks_dev = int64 pairs {tensor index, first element of a 4096-element chunk}. */
+int b200rec_adamw_multi(const void* table_dev, const int64_t* blocks_dev, int n_blocks, float lr,
+                        float beta1, float beta2, float eps, float weight_decay, int step,
+                        float grad_scale, const float* coef_dev, void* stream);
 /* dense-equivalent AdamW over an embedding table whose gradient is given in compact form
  * (uniq_ids, uniq_rows, n_uniq): rows without gradient use g = 0 (momentum still moves them). */
 int b200rec_adamw_rows(float* p, float* m, float* v, int64_t n_rows, int D, const int64_t* uniq_ids,
                        const float* uniq_rows, const int32_t* n_uniq, int32_t* row_slot_ws, float lr,
                        float beta1, float beta2, float eps, float weight_decay, int step,
-                       float grad_scale, void* stream);
+                       float grad_scale, const float* coef_dev, void* stream);
 
 #ifdef __cplusplus
 }

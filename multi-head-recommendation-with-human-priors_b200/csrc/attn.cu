@@ -266,8 +266,8 @@ static int attn_fwd_launch(const void* q, const void* k, const void* v, int ld, 
                            const uint8_t* key_valid, int B, int n_heads, float inv_n, int max_len, float* out,
                            cudaStream_t st) {
   size_t smem = sizeof(AttnSmem<DH>);
-  B200_CUDA_OK(cudaFuncSetAttribute(hstu_attn_fwd_kernel<TA, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
+  { static bool once_1 = false; if (!once_1) { B200_CUDA_OK(cudaFuncSetAttribute(hstu_attn_fwd_kernel<TA, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem)); once_1 = true; } }
   dim3 grid(ceil_div_i(max_len, AT), n_heads, B);
   hstu_attn_fwd_kernel<TA, DH><<<grid, 256, smem, st>>>((const TA*)q, (const TA*)k, (const TA*)v, ld, seq_off,
                                                         key_valid, inv_n, out, n_heads * DH);
@@ -281,10 +281,10 @@ static int attn_bwd_launch(const void* q, const void* k, const void* v, const vo
                            int n_heads, float inv_n, int max_len, const void* d_out, void* d_pre_q, void* d_pre_k,
                            void* d_pre_v, cudaStream_t st) {
   size_t smem = sizeof(AttnSmem<DH>);
-  B200_CUDA_OK(cudaFuncSetAttribute(hstu_attn_bwd_dq_kernel<TA, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
-  B200_CUDA_OK(cudaFuncSetAttribute(hstu_attn_bwd_dkv_kernel<TA, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
+  { static bool once_2 = false; if (!once_2) { B200_CUDA_OK(cudaFuncSetAttribute(hstu_attn_bwd_dq_kernel<TA, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem)); once_2 = true; } }
+  { static bool once_3 = false; if (!once_3) { B200_CUDA_OK(cudaFuncSetAttribute(hstu_attn_bwd_dkv_kernel<TA, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem)); once_3 = true; } }
   dim3 grid(ceil_div_i(max_len, AT), n_heads, B);
   hstu_attn_bwd_dq_kernel<TA, DH><<<grid, 256, smem, st>>>((const TA*)q, (const TA*)k, (const TA*)v,
                                                            (const TA*)pre_q, ld, seq_off, key_valid, inv_n,

@@ -430,7 +430,7 @@ static int attn_tc_fwd_launch(const bf16* act_base, int64_t ld, const int32_t* s
   CUtensorMap m128;
   if (b200_make_map_bf16(&m128, act_base, (uint64_t)ld, (uint64_t)T, (uint64_t)ld, DH, 128, DH * 2)) return 1;
   size_t smem = 3 * 128 * DH * 2 + 32768 + 256 + 1024;
-  B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  { static bool once_1 = false; if (!once_1) { B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); once_1 = true; } }
   dim3 grid(ceil_div_i(T, 128), n_heads);
   attn_tc_fwd_kernel<DH><<<grid, 128, smem, st>>>(m128, seq_off, B, key_valid, T, D, inv_n, out);
   B200_LAUNCH_OK();
@@ -449,10 +449,10 @@ static int attn_tc_bwd_launch(const bf16* act_base, const bf16* pre_base, int64_
   if (b200_make_map_bf16(&do64, d_out, (uint64_t)D, (uint64_t)T, (uint64_t)D, DH, 64, DH * 2)) return 1;
   size_t smem_q = 3 * 128 * DH * 2 + 16384 + 256 + 1024;
   size_t smem_kv = 3 * 128 * DH * 2 + 32768 + 256 + 1024;
-  B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_bwd_dq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem_q));
-  B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_bwd_dkv_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem_kv));
+  { static bool once_2 = false; if (!once_2) { B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_bwd_dq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem_q)); once_2 = true; } }
+  { static bool once_3 = false; if (!once_3) { B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_bwd_dkv_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem_kv)); once_3 = true; } }
   dim3 grid(ceil_div_i(T, 128), n_heads);
   // column slices of the [T, 4D] buffers: u | v | q | k
   attn_tc_bwd_dq_kernel<DH><<<grid, 128, smem_q, st>>>(m128, m64, do128, seq_off, B, key_valid, T, D, inv_n,

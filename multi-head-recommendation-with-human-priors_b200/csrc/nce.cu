@@ -433,8 +433,8 @@ int b200rec_nce_loss_fwd(const float* logits, int64_t ld_logits, int n_neg, cons
   size_t smem = (size_t)(n_neg + D) * sizeof(float);
   B200_CHECK_ARG(smem <= 200 * 1024, "nce_loss_fwd: n_neg=%d too large for the shared-memory row cache", n_neg);
   DISPATCH_ACT(act_dtype, TA, {
-    B200_CUDA_OK(cudaFuncSetAttribute(nce_loss_fwd_kernel<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
+    { static bool once_1 = false; if (!once_1) { B200_CUDA_OK(cudaFuncSetAttribute(nce_loss_fwd_kernel<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem)); once_1 = true; } }
     nce_loss_fwd_kernel<TA><<<T, NCE_THREADS, smem, (cudaStream_t)stream>>>(
         logits, ld_logits, n_neg, same_bits, (const TA*)q_hat, ldq, (const TA*)t_hat, D, tok_b, tok_pos, LP, P,
         p_mask, tok_ok, tok_ok_ld, tok_ok_col, coef, logit_scale, loss, g0, dscale, rank0, nvalid, (TA*)G, ldg);

@@ -5,7 +5,17 @@
 
 struct AdamCoef {
   float lr, b1, b2, eps, wd, bc1, bc2_sqrt, gs;
+  const float* dev;  // optional device override {lr, bc1, bc2_sqrt, step}: lets a captured CUDA graph advance the step
 };
+
+__device__ __forceinline__ AdamCoef adam_resolve(AdamCoef c) {
+  if (c.dev) {
+    c.lr = c.dev[0];
+    c.bc1 = c.dev[1];
+    c.bc2_sqrt = c.dev[2];
+  }
+  return c;
+}
 
 __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, const AdamCoef& c) {
   g *= c.gs;
@@ -21,12 +31,14 @@ static AdamCoef make_coef(float lr, float b1, float b2, float eps, float wd, int
   c.lr = lr; c.b1 = b1; c.b2 = b2; c.eps = eps; c.wd = wd; c.gs = gs;
   c.bc1 = 1.f - powf(b1, (float)step);
   c.bc2_sqrt = sqrtf(1.f - powf(b2, (float)step));
+  c.dev = nullptr;
   return c;
 }
 
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ m,
                                                     float* __restrict__ v, const float* __restrict__ g, int64_t n,
-                                                    AdamCoef c) {
+                                                    AdamCoef c_in) {
+  const AdamCoef c = adam_resolve(c_in);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = n / 4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -49,16 +61,18 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
 
 __global__ void __launch_bounds__(256) adamw_scalar_kernel(float* __restrict__ p, float* __restrict__ m,
                                                            float* __restrict__ v, const float* __restrict__ g,
-                                                           int64_t n, AdamCoef c) {
+                                                           int64_t n, AdamCoef c_in) {
+  const AdamCoef c = adam_resolve(c_in);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     adam_update(p[i], m[i], v[i], g[i], c);
 }
 
 int b200rec_adamw(float* p, float* m, float* v, const float* g, int64_t n, float lr, float beta1, float beta2,
-                  float eps, float weight_decay, int step, float grad_scale, void* stream) {
+                  float eps, float weight_decay, int step, float grad_scale, const float* coef_dev, void* stream) {
   if (n == 0) return 0;
   AdamCoef c = make_coef(lr, beta1, beta2, eps, weight_decay, step, grad_scale);
+  c.dev = coef_dev;
   if ((((uintptr_t)p | (uintptr_t)m | (uintptr_t)v | (uintptr_t)g) & 15) != 0) {  // unaligned view: scalar path
     adamw_scalar_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(p, m, v, g,
                                                                                                            n, c);
@@ -80,7 +94,8 @@ __global__ void row_slot_kernel(const int64_t* __restrict__ uniq_ids, const int3
 __global__ void __launch_bounds__(256) adamw_rows_kernel(float* __restrict__ p, float* __restrict__ m,
                                                          float* __restrict__ v, int64_t n_vec, int D4,
                                                          const int32_t* __restrict__ row_slot,
-                                                         const float* __restrict__ uniq_rows, AdamCoef c) {
+                                                         const float* __restrict__ uniq_rows, AdamCoef c_in) {
+  const AdamCoef c = adam_resolve(c_in);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
     int64_t r = i / D4;
@@ -101,17 +116,60 @@ __global__ void __launch_bounds__(256) adamw_rows_kernel(float* __restrict__ p, 
 
 int b200rec_adamw_rows(float* p, float* m, float* v, int64_t n_rows, int D, const int64_t* uniq_ids,
                        const float* uniq_rows, const int32_t* n_uniq, int32_t* row_slot_ws, float lr, float beta1,
-                       float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
+                       float beta2, float eps, float weight_decay, int step, float grad_scale, const float* coef_dev,
+                       void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   B200_CHECK_ARG(D % 4 == 0, "adamw_rows: D=%d must be a multiple of 4", D);
   if (n_rows == 0) return 0;
   AdamCoef c = make_coef(lr, beta1, beta2, eps, weight_decay, step, grad_scale);
+  c.dev = coef_dev;
   B200_CUDA_OK(cudaMemsetAsync(row_slot_ws, 0xff, (size_t)n_rows * 4, st));
   // n_uniq lives on the device: launch for the worst case (every row touched)
   row_slot_kernel<<<ceil_div_i(n_rows, 256), 256, 0, st>>>(uniq_ids, n_uniq, row_slot_ws);
   int64_t n_vec = n_rows * (D / 4);
   int blocks = (int)std::min<int64_t>((n_vec + 255) / 256, 148 * 16);
   adamw_rows_kernel<<<blocks, 256, 0, st>>>(p, m, v, n_vec, D / 4, row_slot_ws, uniq_rows, c);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+// ---- device-side step counter: coef = {lr, bc1, bc2_sqrt, step}; a captured graph replays this tick ----------
+__global__ void adamw_tick_kernel(float* coef, float b1, float b2) {
+  float step = coef[3] + 1.f;
+  coef[3] = step;
+  coef[1] = 1.f - powf(b1, step);
+  coef[2] = sqrtf(1.f - powf(b2, step));
+}
+
+extern "C" int b200rec_adamw_tick(float* coef_dev, float beta1, float beta2, void* stream) {
+  adamw_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(coef_dev, beta1, beta2);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+// ---- multi-tensor AdamW: one launch for every dense parameter ---------------------------------------------
+// table[t] = {p, m, v, g, n}; blocks[b] = {tensor index, first element of the 4096-element chunk}
+struct AdamTensor {
+  float *p, *m, *v;
+  const float* g;
+  int64_t n;
+};
+__global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamTensor* __restrict__ table,
+                                                          const int64_t* __restrict__ blocks, AdamCoef c_in) {
+  const AdamCoef c = adam_resolve(c_in);
+  const AdamTensor t = table[blocks[2 * blockIdx.x]];
+  const int64_t beg = blocks[2 * blockIdx.x + 1];
+  const int64_t end = min(t.n, beg + 4096);
+  for (int64_t i = beg + threadIdx.x; i < end; i += 256) adam_update(t.p[i], t.m[i], t.v[i], t.g[i], c);
+}
+
+extern "C" int b200rec_adamw_multi(const void* table_dev, const int64_t* blocks_dev, int n_blocks, float lr,
+                                   float beta1, float beta2, float eps, float weight_decay, int step,
+                                   float grad_scale, const float* coef_dev, void* stream) {
+  if (n_blocks == 0) return 0;
+  AdamCoef c = make_coef(lr, beta1, beta2, eps, weight_decay, step, grad_scale);
+  c.dev = coef_dev;
+  adamw_multi_kernel<<<n_blocks, 256, 0, (cudaStream_t)stream>>>((const AdamTensor*)table_dev, blocks_dev, c);
   B200_LAUNCH_OK();
   return 0;
 }

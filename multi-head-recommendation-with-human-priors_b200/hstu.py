@@ -293,6 +293,26 @@ class HSTU(nn.Module):
         key_valid = valid[idx[:, 0], idx[:, 1]].to(torch.uint8).contiguous()
         return tok_b, tok_pos, seq_off, key_valid, int(idx.shape[0])
 
+    @staticmethod
+    def _tokens_static(valid, T):
+        """Sync-free jagged index with exactly T token slots.  `valid` is [B+1, L] whose LAST row is the
+        all-False dummy row; slots beyond the real tokens become dummy tokens (b = B, pos = 0, key masked)
+        that form one trailing dummy sequence.  T must be >= the number of valid positions."""
+        Bx, Lx = valid.shape
+        assert T <= (Bx - 1) * Lx + Lx, "n_tokens exceeds the number of context positions"
+        flat = valid.reshape(-1)
+        order = torch.argsort((~flat).to(torch.int8), stable=True)     # valid positions first, in (b, pos) order
+        sel = order[:T]
+        real = flat[sel]
+        tok_b = torch.where(real, torch.div(sel, Lx, rounding_mode="floor"), torch.full_like(sel, Bx - 1))
+        tok_pos = torch.where(real, sel % Lx, torch.zeros_like(sel))
+        counts = valid.sum(1)
+        counts[Bx - 1] = T - counts.sum()
+        seq_off = torch.zeros(Bx + 1, dtype=torch.int32, device=valid.device)
+        seq_off[1:] = counts.cumsum(0).to(torch.int32)
+        return (tok_b.to(torch.int32).contiguous(), tok_pos.to(torch.int32).contiguous(), seq_off,
+                real.to(torch.uint8).contiguous(), T)
+
     # ------------------------------------------------------------------ body (hstu.py:221-328)
     def _body_forward(self, x, w, seq_off, key_valid, B, T, n_pad, max_len, save):
         D, nh, dh = self._hstu_embedding_dim, self._num_heads, self._dqk
@@ -402,7 +422,10 @@ class HSTU(nn.Module):
         return hd, z, yb
 
     # ------------------------------------------------------------------ training (hstu.py:631-872)
-    def forward(self, interaction):
+    def forward(self, interaction, n_tokens=None):
+        """`n_tokens` (optional host int >= number of valid context tokens, e.g. from the collate fn): builds
+        the jagged index with static shapes and no host sync, padding with dummy tokens up to n_tokens — the
+        form a CUDA graph can capture (see graphed.GraphedTrainStep)."""
         items, neg_items, mask, tags = interaction
         if not items.is_cuda:
             raise L.B200RecError("b200rec.HSTU.forward needs CUDA tensors (there is no CPU path)")
@@ -411,15 +434,22 @@ class HSTU(nn.Module):
                                       "or hidden_dropout_prob=0 (parity runs do the same, SURVEY App. C)")
         params = [p for p in self.parameters()]
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        loss = _TrainStep.apply(self, need_grad, items, neg_items, mask, tags, *params)
+        loss = _TrainStep.apply(self, (need_grad, n_tokens), items, neg_items, mask, tags, *params)
         out = defaultdict(float)
         out.update(self._last_logs)
         out["loss"] = loss
         return out
 
-    def _train_forward(self, items, neg_items, mask, tags, need_grad):
+    def _train_forward(self, items, neg_items, mask, tags, need_grad, n_tokens=None):
         dev = items.device
         D, P, Lc = self._hstu_embedding_dim, self.pred_len, self.max_seq_length
+        if n_tokens is not None:
+            # static-shape mode: one all-padding dummy row (index B) owns the dummy tokens; it has no valid
+            # position, so it contributes no loss, no gradient and no attention keys.
+            items = torch.cat([items, torch.zeros_like(items[:1])], dim=0)
+            mask = torch.cat([mask, torch.zeros_like(mask[:1])], dim=0)
+            if tags.numel() > 0:
+                tags = torch.cat([tags, torch.zeros_like(tags[:1])], dim=0)
         B, LP = items.shape
         assert LP == Lc + P, f"items must be [B, L+P] = [B, {Lc + P}], got {tuple(items.shape)}"
         act, a_dt, st = self._act(), L.dt(self._act()), L.stream()
@@ -434,7 +464,10 @@ class HSTU(nn.Module):
         W, items, neg_ids, uniq_rows_ids = self._table_rows(items, neg_ids)
         ctx = {}
         # ---- jagged token index (valid context positions only)
-        tok_b, tok_pos, seq_off, key_valid, T = self._tokens(m[:, :Lc])
+        if n_tokens is None:
+            tok_b, tok_pos, seq_off, key_valid, T = self._tokens(m[:, :Lc])
+        else:
+            tok_b, tok_pos, seq_off, key_valid, T = self._tokens_static(m[:, :Lc], int(n_tokens))
         tok_index = torch.full((B * LP,), -1, dtype=torch.int32, device=dev)
         tok_index[tok_b.long() * LP + tok_pos.long()] = torch.arange(T, dtype=torch.int32, device=dev)
         C = self.num_prior_head
@@ -892,8 +925,9 @@ class _TrainStep(torch.autograd.Function):
     the hand-written backward and hands one gradient per parameter to autograd."""
 
     @staticmethod
-    def forward(ctx, model, need_grad, items, neg_items, mask, tags, *params):
-        loss, logs, saved = model._train_forward(items, neg_items, mask, tags, need_grad)
+    def forward(ctx, model, flags, items, neg_items, mask, tags, *params):
+        need_grad, n_tokens = flags
+        loss, logs, saved = model._train_forward(items, neg_items, mask, tags, need_grad, n_tokens)
         ctx.model, ctx.saved, ctx.params = model, saved, params
         ctx.set_materialize_grads(False)
         model._last_logs = logs

@@ -1,22 +1,31 @@
 """Fused AdamW over the HSTU parameters (torch.optim.AdamW maths, reference trainer.py:292-299).
 
-Dense parameters take one fused pass each.  The item-embedding table takes the dense-equivalent
-row kernel fed by the compact (unique id, row) gradient of the sorted-segment scatter-add, so the
-[N, D] dense gradient is never materialised (set `sparse_embedding_grad=True` on the model).
+Dense parameters are updated by ONE multi-tensor launch; the item-embedding table takes the
+dense-equivalent row kernel fed by the compact (unique id, row) gradient of the sorted-segment
+scatter-add, so the [N, D] dense gradient is never materialised (`sparse_embedding_grad=True`).
+With `device_step=True` the step counter / bias corrections / lr live in device memory and are
+advanced by a tick kernel, so the whole optimizer step can sit inside a captured CUDA graph.
 """
+import struct
+
 import torch
 
 from . import _lib as L
 
 
 class FusedAdamW(object):
-    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, device_step=False):
         self.model = model
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.step_count = 0
         self.state = {}
         self.param_groups = [dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)]
         self._row_slot = None
+        self.device_step = device_step
+        self._coef = None          # device fp32[4] = {lr, bc1, bc2_sqrt, step}
+        self._table_key = None
+        self._table = self._blocks = None
+        self._keepalive = []
 
     def _st(self, p):
         s = self.state.get(p)
@@ -30,6 +39,32 @@ class FusedAdamW(object):
             p.grad = None
         self.model.emb_grad = None
 
+    def set_lr(self, lr):
+        self.param_groups[0]["lr"] = lr
+        if self._coef is not None:
+            self._coef[0:1].fill_(lr)
+
+    def _dense_table(self, dense):
+        """Device pointer table for the multi-tensor kernel; rebuilt only when a pointer changes."""
+        key = tuple((p.data_ptr(), p.grad.data_ptr(), p.numel()) for p in dense)
+        if key != self._table_key:
+            recs, blocks = [], []
+            for t, p in enumerate(dense):
+                m, v = self._st(p)
+                recs.append(struct.pack("QQQQq", p.data_ptr(), m.data_ptr(), v.data_ptr(), p.grad.data_ptr(), p.numel()))
+                for beg in range(0, p.numel(), 4096):
+                    blocks += [t, beg]
+            dev = dense[0].device
+            # pinned staging buffers: legal inside CUDA-graph capture (the copy becomes a memcpy node that
+            # re-reads the pinned buffer at replay, so the buffers are kept alive for the optimizer's life)
+            raw_h = torch.frombuffer(bytearray(b"".join(recs)), dtype=torch.uint8).pin_memory()
+            blk_h = torch.tensor(blocks, dtype=torch.int64).pin_memory()
+            self._keepalive.append((raw_h, blk_h))
+            self._table = raw_h.to(dev, non_blocking=True)
+            self._blocks = blk_h.to(dev, non_blocking=True)
+            self._table_key = key
+        return self._table, self._blocks
+
     @torch.no_grad()
     def step(self, grad_scale=1.0):
         self.step_count += 1
@@ -37,6 +72,13 @@ class FusedAdamW(object):
         lr, (b1, b2), eps, wd = g["lr"], g["betas"], g["eps"], g["weight_decay"]
         st = L.stream()
         emb = self.model.item_embedding.weight
+        coef = None
+        if self.device_step:
+            if self._coef is None:
+                self._coef = torch.tensor([lr, 0.0, 0.0, float(self.step_count - 1)], dtype=torch.float32, device=emb.device)
+            L.call("b200rec_adamw_tick", self._coef.data_ptr(), b1, b2, st)
+            coef = self._coef.data_ptr()
+        dense = []
         for p in self.model.parameters():
             if p is emb and p.grad is None and self.model.emb_grad is not None:
                 m, v = self._st(p)
@@ -46,13 +88,14 @@ class FusedAdamW(object):
                     self._row_slot = torch.empty(N, dtype=torch.int32, device=p.device)
                 L.call("b200rec_adamw_rows", p.data_ptr(), m.data_ptr(), v.data_ptr(), N, D, uniq_ids.data_ptr(),
                        uniq_rows.data_ptr(), n_uniq.data_ptr(), self._row_slot.data_ptr(), lr, b1, b2, eps, wd,
-                       self.step_count, grad_scale, st)
+                       self.step_count, grad_scale, coef, st)
                 continue
             if p.grad is None:
                 continue
-            m, v = self._st(p)
-            gr = p.grad.contiguous()
-            if gr.dtype != torch.float32:
-                gr = gr.float()
-            L.call("b200rec_adamw", p.data_ptr(), m.data_ptr(), v.data_ptr(), gr.data_ptr(), p.numel(), lr, b1, b2,
-                   eps, wd, self.step_count, grad_scale, st)
+            if p.grad.dtype != torch.float32 or not p.grad.is_contiguous():
+                p.grad = p.grad.float().contiguous()
+            dense.append(p)
+        if dense:
+            table, blocks = self._dense_table(dense)
+            L.call("b200rec_adamw_multi", table.data_ptr(), blocks.data_ptr(), blocks.numel() // 2, lr, b1, b2, eps, wd,
+                   self.step_count, grad_scale, coef, st)

@@ -299,3 +299,51 @@ def test_fused_eval_large_random():
     assert (fval[fin] - mx[fin]).abs().max().item() < 2e-2
     agree = (fhead.long() == am)[fin].float().mean().item()
     assert agree > 0.999          # arg-max head may differ only on near-ties of bf16 products
+
+
+def test_static_token_mode_equals_eager():
+    """n_tokens (static shapes + dummy tokens) changes nothing: same loss, same gradients."""
+    fx = load_golden("prior_additive")
+    cfg, model = build(fx, torch.float32)
+    batch = to_dev(fx["train_batch"])
+    out1 = model(batch)
+    out1["loss"].backward()
+    g1 = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    model.zero_grad()
+    n_tok = int(fx["train_batch"][2][:, :cfg["MAX_ITEM_LIST_LENGTH"]].sum())
+    cap = fx["train_batch"][0].shape[0] * cfg["MAX_ITEM_LIST_LENGTH"]
+    for T in (n_tok, min(cap, n_tok + 5), min(cap, (n_tok + 15) // 16 * 16)):
+        out2 = model(batch, n_tokens=T)
+        out2["loss"].backward()
+        assert abs(float(out1["loss"]) - float(out2["loss"])) < 1e-6
+        for k, p in model.named_parameters():
+            if k in g1:
+                assert (p.grad - g1[k]).abs().max().item() <= 1e-6 * max(1.0, g1[k].abs().max().item()), (T, k)
+        for k in out1:
+            if k != "loss":
+                assert abs(float(out1[k]) - float(out2[k])) < 1e-5, k
+        model.zero_grad()
+
+
+def test_graphed_train_step_matches_eager_training():
+    from b200rec.graphed import GraphedTrainStep
+    fx = load_golden("prior_mult")
+    cfg, model_a = build(fx, torch.float32, sparse_embedding_grad=True)
+    _, model_b = build(fx, torch.float32, sparse_embedding_grad=True)
+    opt_a = FusedAdamW(model_a, lr=1e-3, weight_decay=0.01, device_step=True)
+    opt_b = FusedAdamW(model_b, lr=1e-3, weight_decay=0.01)
+    L_ = cfg["MAX_ITEM_LIST_LENGTH"]
+    batches = [synth.make_train_batch(cfg, seed=70 + i, item_tags=fx["item_tags"], zipf=False) for i in range(4)]
+    stepper = GraphedTrainStep(model_a, opt_a, to_dev(batches[0]), bucket=16)
+    for i in range(6):
+        b = batches[i % 4]
+        n_tok = int(b[2][:, :L_].sum())
+        la = float(stepper(tuple(t.pin_memory() for t in b), n_tok)["loss"])
+        opt_b.zero_grad()
+        lb = model_b(to_dev(b))["loss"]
+        lb.backward()
+        opt_b.step()
+        assert abs(la - float(lb)) < 1e-4 * max(1.0, abs(float(lb))), (i, la, float(lb))
+    for (k, pa), (_, pb) in zip(model_a.named_parameters(), model_b.named_parameters()):
+        assert torch.allclose(pa, pb, rtol=1e-4, atol=1e-6), k
+    assert len(stepper.graphs) >= 1

@@ -413,7 +413,7 @@ def test_adamw_matches_torch():
         opt.step()
         gs = (g * step).contiguous()
         L.call("b200rec_adamw", p.data_ptr(), m.data_ptr(), v.data_ptr(), gs.data_ptr(), p.numel(), 1e-2, 0.9, 0.999,
-               1e-8, 0.1, step, 1.0, L.stream())
+               1e-8, 0.1, step, 1.0, None, L.stream())
     assert torch.allclose(p, p_ref.data, rtol=1e-5, atol=1e-6)
 
 
@@ -434,7 +434,7 @@ def test_adamw_rows_dense_equivalent():
         opt.step()
         r = (rows * step).contiguous()
         L.call("b200rec_adamw_rows", p.data_ptr(), m.data_ptr(), v.data_ptr(), N, D, ids.data_ptr(), r.data_ptr(),
-               nu.data_ptr(), slot.data_ptr(), 1e-2, 0.9, 0.999, 1e-8, 0.01, step, 1.0, L.stream())
+               nu.data_ptr(), slot.data_ptr(), 1e-2, 0.9, 0.999, 1e-8, 0.01, step, 1.0, None, L.stream())
     assert torch.allclose(p, p_ref.data, rtol=1e-5, atol=1e-6)
 
 
