@@ -131,7 +131,7 @@ def cpu_reference_run(cfg, batch_size, steps, warmup=1):
     if rh.available():
         kind = "reference"
         model = rh.build_reference_model(dict(c), c["item_num"], dl.category_counts, dl.category_to_int)
-        model.eval()  # dropout off, as in the parity runs
+        model.train()  # training mode (dropout at the preset's rate), like the GPU arm
         params = [p for p in model.parameters() if p.requires_grad]
         step_fn = lambda: model(batch)["loss"]
     else:
@@ -182,6 +182,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        base["config"]["step"] = "cpu eager (reference algorithm on host cores)"
         r = cpu_reference_run(cfg, args.cpu_batch, max(1, args.steps), warmup=max(1, min(args.warmup, 1)))
         line = dict(base)
         line.update({"impl": "reference", "value": r["value"], "ms_per_step": r["ms_per_step"], "dtype": "f32",
@@ -205,7 +206,7 @@ def main():
     cfg["sparse_embedding_grad"] = True
     dl = synth.make_dataload(cfg)
     torch.manual_seed(2020)
-    model = HSTU(cfg, dl, compute_dtype=dtype).to(dev).eval()   # eval(): dropout off
+    model = HSTU(cfg, dl, compute_dtype=dtype).to(dev).train()  # training mode: Philox dropout at the preset's rate
     use_graph = (world == 1) and not args.no_graph and not args.profile
     opt = FusedAdamW(model, lr=1e-4, weight_decay=0.0, device_step=use_graph)
     if world > 1 and not args.replicate_table:

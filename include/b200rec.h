@@ -88,13 +88,19 @@ int b200rec_layernorm_bwd(const void* dy, int dy_dtype, int ldy, const float* x,
                           void* stream);
 /* hstu.py:277 o_input = u * LN(attn): oin = u * LN(a).  u has leading dimension ldu (it is a column
  * slice of the uvqk activation). */
+/* dropout_p > 0 applies F.dropout to oin (hstu.py:281-285) with a stateless Philox4x32-10 keep-mask keyed by
+ * (seed, layer, *rng_step_dev, element): statistically equivalent to torch's, not bit-matched; the backward
+ * regenerates the same mask.  rng_step_dev is a device counter (b200rec_counter_add) so graph replays differ. */
 int b200rec_gate_ln_fwd(const void* u, int ldu, const float* a, int T, int D, float eps, void* oin,
-                        int act_dtype, float* mean, float* rstd, void* stream);
+                        int act_dtype, float* mean, float* rstd, float dropout_p, uint32_t seed,
+                        uint32_t layer, const int64_t* rng_step_dev, void* stream);
+int b200rec_counter_add(int64_t* counter_dev, int64_t v, void* stream);
 /* backward: du = d_oin*LN(a) ; da = LN'(a; d_oin*u) (act dtype).  Writes d_pre_u = du * silu'(pre_u) directly
  * (pre_u = pre-activation slice, ld ldu) into d_pre_u (ld ldu). */
 int b200rec_gate_ln_bwd(const void* d_oin, const void* u, const void* pre_u, int ldu, const float* a,
                         const float* mean, const float* rstd, int T, int D, void* d_pre_u, void* da,
-                        int act_dtype, void* stream);
+                        int act_dtype, float dropout_p, uint32_t seed, uint32_t layer,
+                        const int64_t* rng_step_dev, void* stream);
 /* y = cast(x) elementwise, n elements (fp32 -> act dtype). */
 int b200rec_cast(const float* x, int64_t n, void* y, int y_dtype, void* stream);
 /* col_sum[j] = sum_i x[i, j]  (deterministic two-stage: 256-row slabs, then slabs in ascending

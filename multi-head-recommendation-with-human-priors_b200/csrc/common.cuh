@@ -112,6 +112,37 @@ __device__ __forceinline__ void store4(T* p, const float (&o)[4]) {
   *reinterpret_cast<typename Vec4<T>::type*>(p) = v;
 }
 
+// ---- counter-based RNG for dropout: Philox4x32-10 (Salmon et al. 2011), stateless -------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// keep-mask of 4 consecutive elements: element group `idx4` of stream (seed, step, layer)
+struct DropCfg {
+  float p;                 // drop probability (0 disables)
+  uint32_t seed, layer;
+  const int64_t* step;     // device counter advanced once per forward (graph-replay safe); may be null
+};
+__device__ __forceinline__ void dropout4(const DropCfg& d, uint64_t idx4, float (&v)[4]) {
+  if (d.p <= 0.f) return;
+  const uint64_t st = d.step ? (uint64_t)*d.step : 0ull;
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)idx4, (uint32_t)(idx4 >> 32), (uint32_t)st, (uint32_t)(st >> 32)),
+                                make_uint2(d.seed, d.layer));
+  const uint32_t thr = (uint32_t)fminf(d.p * 4294967296.f, 4294967295.f);
+  const float sc = 1.f / (1.f - d.p);
+  v[0] = r.x >= thr ? v[0] * sc : 0.f;
+  v[1] = r.y >= thr ? v[1] * sc : 0.f;
+  v[2] = r.z >= thr ? v[2] * sc : 0.f;
+  v[3] = r.w >= thr ? v[3] * sc : 0.f;
+}
+
 #define DISPATCH_ACT(dtype, T, ...)                       \
   do {                                                    \
     if ((dtype) == B200REC_F32) {                         \

@@ -139,7 +139,7 @@ template <typename TA, int MAXV>
 __global__ void __launch_bounds__(256) gate_ln_fwd_kernel(const TA* __restrict__ u, int64_t ldu,
                                                           const float* __restrict__ a, int T, int D4, float eps,
                                                           TA* __restrict__ oin, float* __restrict__ mean,
-                                                          float* __restrict__ rstd) {
+                                                          float* __restrict__ rstd, DropCfg drop) {
   int lane = threadIdx.x & 31;
   int r = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= T) return;
@@ -181,26 +181,29 @@ __global__ void __launch_bounds__(256) gate_ln_fwd_kernel(const TA* __restrict__
       load4<TA>(u + (int64_t)r * ldu + c * 4, uu);
 #pragma unroll
       for (int k = 0; k < 4; ++k) v[k4][k] = (v[k4][k] - mu) * rs * uu[k];
+      dropout4(drop, (uint64_t)r * D4 + c, v[k4]);   // F.dropout on the O-proj input (hstu.py:281-285)
       store4<TA>(oin + ((int64_t)r * D4 + c) * 4, v[k4]);
     }
   }
 }
 
 int b200rec_gate_ln_fwd(const void* u, int ldu, const float* a, int T, int D, float eps, void* oin, int act_dtype,
-                        float* mean, float* rstd, void* stream) {
+                        float* mean, float* rstd, float dropout_p, uint32_t seed, uint32_t layer,
+                        const int64_t* rng_step_dev, void* stream) {
+  DropCfg drop = {dropout_p, seed, layer, rng_step_dev};
   B200_CHECK_ARG(D % 4 == 0 && D <= 2048 && ldu % 4 == 0, "gate_ln_fwd: bad D=%d ldu=%d", D, ldu);
   if (T == 0) return 0;
   int blocks = ceil_div_i(T, ROWS_PER_BLOCK);
   DISPATCH_ACT(act_dtype, TA, {
     if (D <= 512)
       gate_ln_fwd_kernel<TA, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TA*)u, ldu, a, T, D / 4, eps,
-                                                                          (TA*)oin, mean, rstd);
+                                                                          (TA*)oin, mean, rstd, drop);
     else if (D <= 1024)
       gate_ln_fwd_kernel<TA, 8><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TA*)u, ldu, a, T, D / 4, eps,
-                                                                          (TA*)oin, mean, rstd);
+                                                                          (TA*)oin, mean, rstd, drop);
     else
       gate_ln_fwd_kernel<TA, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TA*)u, ldu, a, T, D / 4, eps,
-                                                                          (TA*)oin, mean, rstd);
+                                                                          (TA*)oin, mean, rstd, drop);
   });
   B200_LAUNCH_OK();
   return 0;
@@ -211,7 +214,8 @@ __global__ void __launch_bounds__(256) gate_ln_bwd_kernel(const TA* __restrict__
                                                           const TA* __restrict__ pre_u, int64_t ldu,
                                                           const float* __restrict__ a, const float* __restrict__ mean,
                                                           const float* __restrict__ rstd, int T, int D4,
-                                                          TA* __restrict__ d_pre_u, TA* __restrict__ da) {
+                                                          TA* __restrict__ d_pre_u, TA* __restrict__ da,
+                                                          DropCfg drop) {
   int lane = threadIdx.x & 31;
   int r = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= T) return;
@@ -225,6 +229,7 @@ __global__ void __launch_bounds__(256) gate_ln_bwd_kernel(const TA* __restrict__
       float go[4], uu[4], pu[4], dpu[4];
       load4<float>(a + ((int64_t)r * D4 + c) * 4, lna[k4]);
       load4<TA>(d_oin + ((int64_t)r * D4 + c) * 4, go);
+      dropout4(drop, (uint64_t)r * D4 + c, go);       // same keep-mask as the forward
       load4<TA>(u + (int64_t)r * ldu + c * 4, uu);
       load4<TA>(pre_u + (int64_t)r * ldu + c * 4, pu);
 #pragma unroll
@@ -255,20 +260,21 @@ __global__ void __launch_bounds__(256) gate_ln_bwd_kernel(const TA* __restrict__
 
 int b200rec_gate_ln_bwd(const void* d_oin, const void* u, const void* pre_u, int ldu, const float* a,
                         const float* mean, const float* rstd, int T, int D, void* d_pre_u, void* da, int act_dtype,
-                        void* stream) {
+                        float dropout_p, uint32_t seed, uint32_t layer, const int64_t* rng_step_dev, void* stream) {
+  DropCfg drop = {dropout_p, seed, layer, rng_step_dev};
   B200_CHECK_ARG(D % 4 == 0 && D <= 2048 && ldu % 4 == 0, "gate_ln_bwd: bad D=%d ldu=%d", D, ldu);
   if (T == 0) return 0;
   int blocks = ceil_div_i(T, ROWS_PER_BLOCK);
   DISPATCH_ACT(act_dtype, TA, {
     if (D <= 512)
       gate_ln_bwd_kernel<TA, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>(
-          (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, (TA*)da);
+          (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, (TA*)da, drop);
     else if (D <= 1024)
       gate_ln_bwd_kernel<TA, 8><<<blocks, 256, 0, (cudaStream_t)stream>>>(
-          (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, (TA*)da);
+          (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, (TA*)da, drop);
     else
       gate_ln_bwd_kernel<TA, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>(
-          (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, (TA*)da);
+          (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, (TA*)da, drop);
   });
   B200_LAUNCH_OK();
   return 0;
@@ -368,6 +374,13 @@ __global__ void __launch_bounds__(1024) reduce_sum_kernel(const float* __restric
 
 int b200rec_reduce_sum(const float* x, int64_t n, float scale, float* out, int accumulate, void* stream) {
   reduce_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, scale, out, accumulate);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+__global__ void counter_add_kernel(int64_t* c, int64_t v) { *c += v; }
+extern "C" int b200rec_counter_add(int64_t* counter_dev, int64_t v, void* stream) {
+  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter_dev, v);
   B200_LAUNCH_OK();
   return 0;
 }

@@ -179,6 +179,9 @@ class HSTU(nn.Module):
         self.use_tc_attention = bool(config.get("tc_attention", True))
         self.use_fused_eval = bool(config.get("fused_eval", True))
         self.share_negatives = bool(config.get("share_negatives", True))   # all-gather negatives across ranks
+        self.dropout_seed = int(config.get("seed", 2020)) & 0xffffffff
+        self._rng_step = None      # device counter feeding the Philox dropout stream
+        self._drop_p_last = 0.0
         self.sharded_table = None  # parallel.ShardedTable once shard_item_table() was called
         self.emb_grad = None       # (uniq_ids, uniq_rows, n_uniq) of the last backward
         self._table_cache = None   # normalised compute-dtype item table for predict
@@ -320,6 +323,12 @@ class HSTU(nn.Module):
         a_dt = L.dt(act)
         saved = []
         st = L.stream()
+        drop_p = float(self._linear_dropout_rate) if (self.training and save) else 0.0
+        if drop_p > 0:
+            if self._rng_step is None or self._rng_step.device != dev:
+                self._rng_step = torch.zeros(1, dtype=torch.int64, device=dev)
+            L.call("b200rec_counter_add", self._rng_step.data_ptr(), 1, st)   # new keep-masks every forward
+        self._drop_p_last = drop_p
         for i in range(self._num_blocks):
             blk = self._hstu._attention_layers[i]
             n = torch.empty((T, D), dtype=act, device=dev)
@@ -344,7 +353,7 @@ class HSTU(nn.Module):
             mean2 = torch.empty(T, dtype=torch.float32, device=dev)
             rstd2 = torch.empty(T, dtype=torch.float32, device=dev)
             L.call("b200rec_gate_ln_fwd", u.data_ptr(), 4 * D, a.data_ptr(), T, D, LN_EPS, oin.data_ptr(), a_dt,
-                   mean2.data_ptr(), rstd2.data_ptr(), st)
+                   mean2.data_ptr(), rstd2.data_ptr(), drop_p, self.dropout_seed, i, L.ptr(self._rng_step), st)
             x_next = torch.empty((T, D), dtype=torch.float32, device=dev)
             L.gemm(oin, w[f"o{i}"], x_next, T, D, D, lda=D, ldb=D, ldc=D, epilogue=L.EPI_BIAS_RESID,
                    bias=blk._o.bias.data, resid=x, ldr=D)
@@ -358,6 +367,7 @@ class HSTU(nn.Module):
         act, dev = self._act(), dx.device
         a_dt = L.dt(act)
         st = L.stream()
+        drop_p = self._drop_p_last
         for i in reversed(range(self._num_blocks)):
             blk = self._hstu._attention_layers[i]
             x, mean1, rstd1, n, actv, pre, a, mean2, rstd2, oin = saved[i]
@@ -377,7 +387,8 @@ class HSTU(nn.Module):
             d_pre = torch.empty((T, 4 * D), dtype=act, device=dev)
             da = torch.empty((T, D), dtype=act, device=dev)
             L.call("b200rec_gate_ln_bwd", d_oin.data_ptr(), actv.data_ptr(), pre.data_ptr(), 4 * D, a.data_ptr(),
-                   mean2.data_ptr(), rstd2.data_ptr(), T, D, d_pre.data_ptr(), da.data_ptr(), a_dt, st)
+                   mean2.data_ptr(), rstd2.data_ptr(), T, D, d_pre.data_ptr(), da.data_ptr(), a_dt, drop_p,
+                   self.dropout_seed, i, L.ptr(self._rng_step), st)
             sl = lambda t, j: t[:, j * D:(j + 1) * D]
             if self._tc_attention():
                 L.call("b200rec_hstu_attn_tc_bwd", actv.data_ptr(), pre.data_ptr(), 4 * D, seq_off.data_ptr(),
@@ -429,9 +440,6 @@ class HSTU(nn.Module):
         items, neg_items, mask, tags = interaction
         if not items.is_cuda:
             raise L.B200RecError("b200rec.HSTU.forward needs CUDA tensors (there is no CPU path)")
-        if self.training and self._linear_dropout_rate > 0:
-            raise NotImplementedError("hidden_dropout_prob > 0 in training mode is not built; use model.eval() "
-                                      "or hidden_dropout_prob=0 (parity runs do the same, SURVEY App. C)")
         params = [p for p in self.parameters()]
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         loss = _TrainStep.apply(self, (need_grad, n_tokens), items, neg_items, mask, tags, *params)

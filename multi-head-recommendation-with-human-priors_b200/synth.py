@@ -63,21 +63,22 @@ PRESETS = {
               num_segment_head=4, num_prior_head=8, head_interaction="additive",
               loss="prior", neg_sample_by_cat=True, weighted_prior_loss=True, eval_num_cats=8,
               train_batch_size=128, num_negatives=8192, item_num=450000, eval_batch_size=256,
-              given_prior_len=8, prior_given_at_test=False),
+              given_prior_len=8, prior_given_at_test=False, hidden_dropout_prob=0.2),   # IDNet/hstu-size4.yaml
     # C: MerRec-prior (reproduce/HSTU-merrec-prior.slurm:33-66)
     "C": dict(n_layers=16, n_heads=16, item_embedding_size=1024, hstu_embedding_size=1024,
               MAX_ITEM_LIST_LENGTH=400, pred_len=1, eval_pred_len=1, medusa_num_layers=1,
               num_segment_head=1, num_prior_head=6, head_interaction="multiplicative",
               loss="prior", neg_sample_by_cat=False, weighted_prior_loss=True, eval_num_cats=6,
               train_batch_size=64, num_negatives=4096, item_num=5000000, eval_batch_size=256,
-              fix_temp=True, category_by="event", prior_given_at_test=True, given_prior_len=1),
+              fix_temp=True, category_by="event", prior_given_at_test=True, given_prior_len=1,
+              hidden_dropout_prob=0.2),
     # D: EB-NeRD prior-mult (reproduce/HSTU-EBNerd-prior-mult.slurm:33-66)
     "D": dict(n_layers=8, n_heads=8, item_embedding_size=256, hstu_embedding_size=256,
               MAX_ITEM_LIST_LENGTH=50, pred_len=8, eval_pred_len=8, medusa_num_layers=1,
               num_segment_head=1, num_prior_head=7, head_interaction="multiplicative",
               loss="prior", neg_sample_by_cat=True, weighted_prior_loss=True, eval_num_cats=7,
               train_batch_size=128, num_negatives=8192, item_num=200000, eval_batch_size=256,
-              given_prior_len=8, prior_given_at_test=False, eval_by_cat=False),
+              given_prior_len=8, prior_given_at_test=False, eval_by_cat=False, hidden_dropout_prob=0.1),  # size2
 }
 
 

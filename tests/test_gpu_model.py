@@ -192,7 +192,7 @@ def test_medium_shapes_against_oracle():
     """A config-B-shaped slice big enough to exercise multi-tile GEMMs (D=256, L=50, P=8, 12 heads)."""
     from oracle import hstu_oracle as orc
     cfg = synth.make_config("B", n_layers=2, n_heads=4, item_embedding_size=256, hstu_embedding_size=256,
-                            train_batch_size=16, num_negatives=16 * 24, item_num=5000)
+                            train_batch_size=16, num_negatives=16 * 24, item_num=5000, hidden_dropout_prob=0.0)
     dl = synth.make_dataload(cfg)
     torch.manual_seed(2020)
     model = HSTU(cfg, dl, compute_dtype=torch.float32)
@@ -347,3 +347,67 @@ def test_graphed_train_step_matches_eager_training():
     for (k, pa), (_, pb) in zip(model_a.named_parameters(), model_b.named_parameters()):
         assert torch.allclose(pa, pb, rtol=1e-4, atol=1e-6), k
     assert len(stepper.graphs) >= 1
+
+
+def test_training_mode_dropout_runs_and_is_seeded():
+    fx = load_golden("prior_mult")
+    cfg, model = build(fx, torch.float32, hidden_dropout_prob=0.2)
+    model.train()
+    batch = to_dev(fx["train_batch"])
+    l1 = float(model(batch)["loss"])
+    out = model(batch)
+    out["loss"].backward()
+    l2 = float(out["loss"])
+    assert l1 != l2 and abs(l1 - fx["loss"]) < 0.5 and abs(l2 - fx["loss"]) < 0.5   # different masks, same ballpark
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+    model.eval()
+    assert abs(float(model(batch)["loss"]) - fx["loss"]) <= 2e-5 * max(1.0, abs(fx["loss"]))
+
+
+@pytest.mark.parametrize("preset,over", [
+    # config C shape (MerRec: long sequences, event priors, fixed temperature, global negatives) scaled down
+    ("C", dict(n_layers=2, n_heads=2, item_embedding_size=128, hstu_embedding_size=128, MAX_ITEM_LIST_LENGTH=200,
+               train_batch_size=6, num_negatives=6 * 32, item_num=3000, hidden_dropout_prob=0.0)),
+    # config D shape (EB-NeRD: dh = 32, 7 multiplicative prior heads, per-category negatives)
+    ("D", dict(n_layers=2, n_heads=4, item_embedding_size=128, hstu_embedding_size=128, train_batch_size=12,
+               num_negatives=12 * 16, item_num=3000, hidden_dropout_prob=0.0)),
+], ids=["bf16-merrec", "bf16-ebnerd"])
+def test_config_c_d_shapes_against_oracle(preset, over):
+    from oracle import hstu_oracle as orc
+    cfg = synth.make_config(preset, **over)
+    dl = synth.make_dataload(cfg)
+    torch.manual_seed(2020)
+    model = HSTU(cfg, dl, compute_dtype=torch.float32)
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    batch = synth.make_train_batch(cfg, seed=4)
+    ref = orc.OracleHSTU(cfg, sd, dl.category_counts, dl.category_to_int).forward(batch)
+    ref["loss"].backward()
+    item_tags = synth.make_item_tags(cfg, torch.Generator().manual_seed(4242))
+    ev = synth.make_eval_batch(cfg, seed=6, batch_size=8, item_tags=item_tags)
+    C = cfg["eval_num_cats"]
+    tags_cn = item_tags.t().contiguous() if cfg["category_by"] == "item" else torch.ones(C, cfg["item_num"], dtype=torch.bool)
+    o = orc.OracleHSTU(cfg, {k: v.detach() for k, v in sd.items()}, dl.category_counts, dl.category_to_int)
+    scores, _, _, _ = o.predict(ev["item_seq"], None, o.compute_item_all(), tags_cn, ev["target_tags"])
+    scores = orc.post_mask_scores(scores, ev["history_index"])
+    ref_idx, _, _ = orc.collect_topk(scores, 50, "combine")
+    for dtype, ltol, ctol in [(torch.float32, 2e-5, 0.9999), (torch.bfloat16, 1e-2, 0.99)]:
+        m = HSTU(cfg, dl, compute_dtype=dtype)
+        m.load_state_dict(model.state_dict())
+        m = m.to(dev()).eval()
+        out = m(to_dev(batch))
+        assert abs(float(out["loss"]) - float(ref["loss"])) <= ltol * abs(float(ref["loss"])), dtype
+        out["loss"].backward()
+        for k, p in m.named_parameters():
+            if sd[k].grad is None or sd[k].grad.numel() < 2:
+                continue
+            g, r = p.grad.cpu().flatten().double(), sd[k].grad.flatten().double()
+            cos = float((g @ r) / (g.norm() * r.norm() + 1e-30))
+            assert cos > ctol, (dtype, k, cos)
+        hu, hi = ev["history_index"]
+        idx, val, hs = m.predict_topk(ev["item_seq"].to(dev()), m.compute_item_all(), tags_cn.to(dev()),
+                                      ev["target_tags"].to(dev()), history_index=(hu.to(dev()), hi.to(dev())), K=50)
+        if dtype == torch.float32:
+            assert np.array_equal(idx.cpu().numpy(), ref_idx)
+        else:   # bf16 scoring may swap near-ties: require >= 96 % overlap of the top-50 sets
+            ov = np.mean([len(set(a) & set(b)) / 50.0 for a, b in zip(idx.cpu().numpy(), ref_idx)])
+            assert ov >= 0.96, ov

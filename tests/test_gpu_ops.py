@@ -144,7 +144,7 @@ def test_gate_ln_fwd_bwd(T, D):
     oin = torch.empty(T, D, device=dev())
     mean, rstd = torch.empty(T, device=dev()), torch.empty(T, device=dev())
     L.call("b200rec_gate_ln_fwd", act.data_ptr(), 4 * D, a.data_ptr(), T, D, 1e-6, oin.data_ptr(), L.F32,
-           mean.data_ptr(), rstd.data_ptr(), L.stream())
+           mean.data_ptr(), rstd.data_ptr(), 0.0, 0, 0, None, L.stream())
     pr = pre[:, :D].clone().requires_grad_(True)
     ar = a.clone().requires_grad_(True)
     # reference: u = silu(pre_u) would tie u and pre; the kernel takes u and pre_u separately, so build
@@ -157,7 +157,7 @@ def test_gate_ln_fwd_bwd(T, D):
     d_pre = torch.zeros(T, 4 * D, device=dev())
     da = torch.empty(T, D, device=dev())
     L.call("b200rec_gate_ln_bwd", g.data_ptr(), act.data_ptr(), pre.data_ptr(), 4 * D, a.data_ptr(), mean.data_ptr(),
-           rstd.data_ptr(), T, D, d_pre.data_ptr(), da.data_ptr(), L.F32, L.stream())
+           rstd.data_ptr(), T, D, d_pre.data_ptr(), da.data_ptr(), L.F32, 0.0, 0, 0, None, L.stream())
     sg = torch.sigmoid(pre[:, :D])
     silu_grad = sg * (1 + pre[:, :D] * (1 - sg))
     assert torch.allclose(da, ar.grad, rtol=1e-4, atol=1e-5)
@@ -474,3 +474,37 @@ def test_hstu_attention_tensor_core_fwd_bwd(nh, dh, lens):
         err = (a - b).abs().max().item() / max(b.abs().max().item(), 1e-6)
         cos = float((a.flatten() @ b.flatten()) / (a.norm() * b.norm() + 1e-30))
         assert err < 5e-2 and cos > 0.999, (name, err, cos)
+
+
+def test_dropout_mask_statistics_and_fwd_bwd_consistency():
+    """Philox dropout on the O-proj input (hstu.py:281-285): keep rate, 1/(1-p) scaling, a new mask per step,
+    and the backward reuses the forward's mask."""
+    T, D, p = 512, 256, 0.2
+    act, pre, a = rnd(T, 4 * D, seed=101), rnd(T, 4 * D, seed=102), rnd(T, D, seed=103)
+    step = torch.zeros(1, dtype=torch.int64, device=dev())
+    mean, rstd = torch.empty(T, device=dev()), torch.empty(T, device=dev())
+    outs = []
+    for it in range(2):
+        L.call("b200rec_counter_add", step.data_ptr(), 1, L.stream())
+        oin = torch.empty(T, D, device=dev())
+        L.call("b200rec_gate_ln_fwd", act.data_ptr(), 4 * D, a.data_ptr(), T, D, 1e-6, oin.data_ptr(), L.F32,
+               mean.data_ptr(), rstd.data_ptr(), p, 1234, 3, step.data_ptr(), L.stream())
+        outs.append(oin)
+    ref = act[:, :D] * torch.nn.functional.layer_norm(a, [D], eps=1e-6)
+    keep = outs[1] != 0
+    rate = keep.float().mean().item()
+    assert abs(rate - (1 - p)) < 0.01
+    assert torch.allclose(outs[1][keep], ref[keep] / (1 - p), rtol=1e-5, atol=1e-5)
+    assert (keep != (outs[0] != 0)).float().mean().item() > 0.2            # masks differ between steps
+    g = rnd(T, D, seed=104)
+    d_pre = torch.zeros(T, 4 * D, device=dev())
+    da = torch.empty(T, D, device=dev())
+    L.call("b200rec_gate_ln_bwd", g.data_ptr(), act.data_ptr(), pre.data_ptr(), 4 * D, a.data_ptr(), mean.data_ptr(),
+           rstd.data_ptr(), T, D, d_pre.data_ptr(), da.data_ptr(), L.F32, p, 1234, 3, step.data_ptr(), L.stream())
+    ar = a.clone().requires_grad_(True)
+    u = act[:, :D].clone().requires_grad_(True)
+    out = u * torch.nn.functional.layer_norm(ar, [D], eps=1e-6) * keep / (1 - p)
+    out.backward(g)
+    sg = torch.sigmoid(pre[:, :D])
+    assert torch.allclose(da, ar.grad, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(d_pre[:, :D], u.grad * sg * (1 + pre[:, :D] * (1 - sg)), rtol=1e-4, atol=1e-5)
