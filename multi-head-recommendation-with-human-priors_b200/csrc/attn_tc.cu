@@ -68,54 +68,81 @@ __device__ __forceinline__ uint64_t desc_p(uint32_t tile, int ks) {
 }
 
 // --------------------------------------------------------------------------------------- forward
+// zero a 32-column chunk of a row (fully masked chunk: no TMEM read, no SiLU)
+__device__ __forceinline__ void put_zero32_sw128(uint32_t tile, int R, int row, int col0) {
+  const uint32_t base = tile + (uint32_t)(col0 >> 6) * (uint32_t)(R * 128) + (uint32_t)row * 128u;
+  const int cin = (col0 & 63) >> 3;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t addr = base + (uint32_t)(((cin + q) ^ (row & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
+  }
+}
+__device__ __forceinline__ int warp_min_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_max_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// 128 queries x 64-key tiles: 48 KB of shared memory and 128 TMEM columns per CTA -> 4 CTAs per SM hide the
+// TMA -> MMA -> SiLU -> MMA latency chain of one another (the kernel is latency-, not throughput-bound).
 template <int DH>
 __global__ void __launch_bounds__(128)
-attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const int32_t* __restrict__ seq_off, int B,
-                   const uint8_t* __restrict__ key_valid, int T, int D, float inv_n, float* __restrict__ out) {
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map64,
+                   const int32_t* __restrict__ seq_off, int B, const uint8_t* __restrict__ key_valid, int T, int D,
+                   float inv_n, float* __restrict__ out) {
   using C = AtCfg<DH>;
   constexpr uint32_t TILE = 128 * C::SWZ;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = base, sK = sQ + TILE, sV = sK + TILE, sP = sV + TILE;  // sP: 2 x 16 KB
-  const uint32_t bars = sP + 32768;
+  const uint32_t sQ = base, sK = sQ + TILE, sV = sK + TILE / 2, sP = sV + TILE / 2;  // sP: 128 x 128 B
+  const uint32_t bars = sP + 16384;
   const uint32_t bar_q = bars, bar_kv = bars + 8, bar_s = bars + 16, bar_o = bars + 24, tslot = bars + 32;
-  __shared__ uint8_t s_kvalid[128];
+  __shared__ uint8_t s_kvalid[64];
   const int tid = threadIdx.x, warp = tid >> 5;
   const int q0 = blockIdx.x * 128, h = blockIdx.y;
   const int ti = q0 + tid;
   if (tid == 0) {
     tma_prefetch_desc(&map128);
+    tma_prefetch_desc(&map64);
     mbar_init(bar_q, 1); mbar_init(bar_kv, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc(tslot, 256);
+  if (warp == 0) tmem_alloc(tslot, 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot));
   const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
-  const uint32_t tS = 0, tO = 128;  // TMEM columns
+  const uint32_t tS = 0, tO = 64;  // TMEM columns
 
   const int my_start = ti < T ? seq_off[find_seq(seq_off, B, ti)] : INT_MAX;
-  const int kt_first = seq_off[find_seq(seq_off, B, q0)] >> 7;
-  const int kt_last = blockIdx.x;
+  const int w_min_start = warp_min_i(my_start);           // earliest key any row of this warp may see
+  const int w_max_t = min(q0 + warp * 32 + 31, T - 1);    // latest key (causal) any row of this warp may see
+  const int kt_first = seq_off[find_seq(seq_off, B, q0)] >> 6;
+  const int kt_last = min(q0 + 127, T - 1) >> 6;
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_q, TILE);
     tma_load_2d(sQ, &map128, bar_q, 2 * D + h * DH, q0);
   }
-  const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+  const uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
   const uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);
   uint32_t ph = 0;
   for (int kt = kt_first; kt <= kt_last; ++kt, ph ^= 1u) {
-    const int k0 = kt * 128;
+    const int k0 = kt * 64;
     if (tid == 0) {
       if (kt > kt_first) mbar_wait(bar_o, ph ^ 1u);  // previous P*V retired: K, V and P buffers are free
-      mbar_arrive_expect_tx(bar_kv, 2 * TILE);
-      tma_load_2d(sK, &map128, bar_kv, 3 * D + h * DH, k0);
-      tma_load_2d(sV, &map128, bar_kv, 1 * D + h * DH, k0);
+      mbar_arrive_expect_tx(bar_kv, TILE);
+      tma_load_2d(sK, &map64, bar_kv, 3 * D + h * DH, k0);
+      tma_load_2d(sV, &map64, bar_kv, 1 * D + h * DH, k0);
     }
-    s_kvalid[tid] = (k0 + tid < T) ? key_valid[k0 + tid] : 0;
+    if (tid < 64) s_kvalid[tid] = (k0 + tid < T) ? key_valid[k0 + tid] : 0;
     if (tid == 0) {
       if (kt == kt_first) mbar_wait(bar_q, 0);
       mbar_wait(bar_kv, ph);
@@ -129,12 +156,17 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const int32_t* __
     mbar_wait(bar_s, ph);
     tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
+      const int c0 = k0 + c * 32;
+      if (c0 > w_max_t || c0 + 31 < w_min_start) {   // warp-uniform: whole chunk masked for these 32 rows
+        put_zero32_sw128(sP, 128, tid, c * 32);
+        continue;
+      }
       float v[32];
       tmem_ld_32x32(t_lane + tS + c * 32, v);
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
-        const int tj = k0 + c * 32 + e;
+        const int tj = c0 + e;
         const bool keep = (tj <= ti) && (tj >= my_start) && s_kvalid[c * 32 + e];
         v[e] = keep ? silu_f(v[e]) * inv_n : 0.f;
       }
@@ -146,7 +178,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const int32_t* __
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks)
+      for (int ks = 0; ks < 4; ++ks)
         umma_bf16(tmem + tO, desc_p(sP, ks), C::desc_mn(sV, ks), idesc_o, (kt > kt_first || ks > 0));
       umma_commit(bar_o);
     }
@@ -170,7 +202,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const int32_t* __
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem, 256);
+    tmem_dealloc(tmem, 128);
   }
 }
 
@@ -207,6 +239,8 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap map128, const __grid_c
   const uint32_t tS = 0, tdA = 64, tdQ = 128;
 
   const int my_start = ti < T ? seq_off[find_seq(seq_off, B, ti)] : INT_MAX;
+  const int w_min_start = warp_min_i(my_start);
+  const int w_max_t = min(q0 + warp * 32 + 31, T - 1);
   const int kt_first = seq_off[find_seq(seq_off, B, q0)] >> 6;
   const int kt_last = min(q0 + 127, T - 1) >> 6;
   if (tid == 0) {
@@ -243,6 +277,10 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap map128, const __grid_c
     tc_fence_after();
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
+      if (k0 + c * 32 > w_max_t || k0 + c * 32 + 31 < w_min_start) {  // warp-uniform: chunk fully masked
+        put_zero32_sw128(sdS, 128, tid, c * 32);
+        continue;
+      }
       float s[32], da[32];
       tmem_ld_32x32(t_lane + tS + c * 32, s);
       tmem_ld_32x32(t_lane + tdA + c * 32, da);
@@ -363,6 +401,11 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map128, const __grid_
     tc_fence_after();
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
+      if (i0 + c * 32 + 31 < k0 + warp * 32) {   // warp-uniform: every query of the chunk precedes every key
+        put_zero32_sw128(sPT, 128, tid, c * 32);
+        put_zero32_sw128(sdST, 128, tid, c * 32);
+        continue;
+      }
       float s[32], da[32];
       tmem_ld_32x32(t_lane + tS + c * 32, s);
       tmem_ld_32x32(t_lane + tdA + c * 32, da);
@@ -427,12 +470,13 @@ template <int DH>
 static int attn_tc_fwd_launch(const bf16* act_base, int64_t ld, const int32_t* seq_off, int B, const uint8_t* key_valid,
                               int T, int n_heads, float inv_n, float* out, cudaStream_t st) {
   const int D = n_heads * DH;
-  CUtensorMap m128;
+  CUtensorMap m128, m64;
   if (b200_make_map_bf16(&m128, act_base, (uint64_t)ld, (uint64_t)T, (uint64_t)ld, DH, 128, DH * 2)) return 1;
-  size_t smem = 3 * 128 * DH * 2 + 32768 + 256 + 1024;
+  if (b200_make_map_bf16(&m64, act_base, (uint64_t)ld, (uint64_t)T, (uint64_t)ld, DH, 64, DH * 2)) return 1;
+  size_t smem = 2 * 128 * DH * 2 + 16384 + 256 + 1024;
   { static bool once_1 = false; if (!once_1) { B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); once_1 = true; } }
   dim3 grid(ceil_div_i(T, 128), n_heads);
-  attn_tc_fwd_kernel<DH><<<grid, 128, smem, st>>>(m128, seq_off, B, key_valid, T, D, inv_n, out);
+  attn_tc_fwd_kernel<DH><<<grid, 128, smem, st>>>(m128, m64, seq_off, B, key_valid, T, D, inv_n, out);
   B200_LAUNCH_OK();
   return 0;
 }

@@ -28,7 +28,10 @@ struct TcParams {
   int num_m, num_n;
 };
 
-template <int MODE>
+// CTAS = 1: one CTA per 128 x BN tile.  CTAS = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN
+// tile: each CTA stages its own 128 A rows and HALF of the B tile, so per-CTA shared-memory and L2 operand
+// traffic per flop drop by a third and the epilogue's transpose traffic fits beside the mainloop.
+template <int MODE, int CTAS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcParams p, const EpiParams ep_in) {
@@ -37,8 +40,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024B alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const int bn_cta = p.BN / CTAS;                       // B rows staged by this CTA
   const uint32_t a_bytes = TC_BM * 128u;
-  const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t b_bytes = (uint32_t)bn_cta * 128u;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t bar_base = smem_base + (uint32_t)p.stages * stage_bytes;
   // barrier layout: full[stages], empty[stages], tmem_full[2], tmem_empty[2], tmem_ptr
@@ -58,45 +63,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), TC_EPI_WARPS);
+      mbar_init(tempty_bar(a), TC_EPI_WARPS * CTAS);   // pair: the peer's epilogue warps arrive remotely
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TC_TMEM_COLS);
+  if (CTAS == 2) cluster_sync_all();                   // peer barriers exist before anyone signals them
+  if (warp == 1) {
+    if (CTAS == 2) tmem_alloc_2sm(tmem_slot, TC_TMEM_COLS); else tmem_alloc(tmem_slot, TC_TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();                   // both halves of the pair own their TMEM columns
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int num_tiles = p.num_m * p.num_n;
+  const int num_tiles = p.num_m * p.num_n;             // p.num_m counts (128*CTAS)-row tiles
   const int num_k = (p.K + TC_BK - 1) / TC_BK;
+  const int tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % p.num_m) * TC_BM;
-        const int n0 = (tile / p.num_m) * p.BN;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int m0 = (tile % p.num_m) * (TC_BM * CTAS) + (int)rank * TC_BM;
+        const int n0 = (tile / p.num_m) * p.BN + (int)rank * bn_cta;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
           const uint32_t sb = sa + a_bytes;
-          mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+          // pair: both CTAs credit the LEADER's full barrier (it gates the leader's MMA issue)
+          const uint32_t fb = CTAS == 2 ? mapa_shared(full_bar(s), 0) : full_bar(s);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(s), stage_bytes * CTAS);
           const int k0 = kb * TC_BK;
+          auto load = [&](uint32_t dst, const CUtensorMap* mp, int c0, int c1) {
+            if (CTAS == 2) tma_load_2d_2sm(dst, mp, fb, c0, c1); else tma_load_2d(dst, mp, fb, c0, c1);
+          };
           if (!p.a_mn) {
-            tma_load_2d(sa, &map_a, full_bar(s), k0, m0);  // box {64 k, 128 m}
+            load(sa, &map_a, k0, m0);                      // box {64 k, 128 m}
           } else {
             for (int j = 0; j < TC_BM / 64; ++j)          // boxes {64 m, 64 k}
-              tma_load_2d(sa + j * 8192u, &map_a, full_bar(s), m0 + 64 * j, k0);
+              load(sa + j * 8192u, &map_a, m0 + 64 * j, k0);
           }
           if (!p.b_mn) {
-            tma_load_2d(sb, &map_b, full_bar(s), k0, n0);  // box {64 k, BN n}
+            load(sb, &map_b, k0, n0);                      // box {64 k, BN/CTAS n}
           } else {
-            for (int j = 0; j < p.BN / 64; ++j)
-              tma_load_2d(sb + j * 8192u, &map_b, full_bar(s), n0 + 64 * j, k0);
+            for (int j = 0; j < bn_cta / 64; ++j)
+              load(sb + j * 8192u, &map_b, n0 + 64 * j, k0);
           }
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
@@ -104,13 +119,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(TC_BM, p.BN, p.a_mn, p.b_mn);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(TC_BM * CTAS, p.BN, p.a_mn, p.b_mn);
       int s = 0;
       uint32_t ph = 0;
       int acc = 0;
       uint32_t acc_ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * (uint32_t)p.BN;
@@ -127,12 +142,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                        : umma_smem_desc(sa + k * 32u, 16u, 1024u);
             const uint64_t db = p.b_mn ? umma_smem_desc(sb + k * 2048u, 8192u, 1024u)
                                        : umma_smem_desc(sb + k * 32u, 16u, 1024u);
-            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CTAS == 2) umma_bf16_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
+          // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+          if (CTAS == 2) umma_commit_2sm(empty_bar(s)); else umma_commit(empty_bar(s));
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (CTAS == 2) umma_commit_2sm(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
       }
     }
@@ -145,8 +163,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int cg = lane & 7, sub = lane >> 3;
     int acc = 0;
     uint32_t acc_ph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % p.num_m) * TC_BM;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      const int m0 = (tile % p.num_m) * (TC_BM * CTAS) + (int)rank * TC_BM;
       const int n0 = (tile / p.num_m) * p.BN;
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
@@ -282,15 +300,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (CTAS == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0)); else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) cluster_sync_all();                   // the peer may still be reading operands / TMEM
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    if (CTAS == 2) tmem_dealloc_2sm(tmem_base, TC_TMEM_COLS); else tmem_dealloc(tmem_base, TC_TMEM_COLS);
   }
 }
 
@@ -339,9 +360,11 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, u
 }
 
 static int g_num_sms = 0;
-static int g_force_bn = 0;  // test hook
+static int g_force_bn = 0;    // test hook
+static int g_force_ctas = 0;  // test hook: 1 = never use CTA pairs
 
 extern "C" void b200rec_gemm_force_bn(int bn) { g_force_bn = bn; }
+extern "C" void b200rec_gemm_force_ctas(int ctas) { g_force_ctas = ctas; }
 
 int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep, cudaStream_t st) {
   B200_CHECK_ARG(((uintptr_t)a->A & 15) == 0 && ((uintptr_t)a->B & 15) == 0, "gemm: A/B must be 16-byte aligned");
@@ -350,32 +373,40 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep, cudaStream_t
     int dev = 0;
     B200_CUDA_OK(cudaGetDevice(&dev));
     B200_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
-    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
-    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
-    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
-    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
-    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
-    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
   }
   TcParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.a_mn = a->a_major; p.b_mn = a->b_major;
+  // CTA pairs whenever there are at least two 128-row tiles (and the test hook does not forbid it)
+  const int ctas = (a->M > TC_BM && g_force_ctas != 1) ? 2 : 1;
+  const int units = g_num_sms / ctas;                   // concurrently resident tiles
   {
-    // wave quantisation: cost ~ waves x tile width; take the cheaper of the two tile widths
-    const int64_t nm = ceil_div_i(a->M, TC_BM);
-    const int64_t w256 = (nm * ceil_div_i(a->N, 256) + g_num_sms - 1) / g_num_sms * 2;
-    const int64_t w128 = (nm * ceil_div_i(a->N, 128) + g_num_sms - 1) / g_num_sms;
-    // the 128-wide tile reads 128 B/clk of shared memory per MMA (the port limit) -> 15% handicap
-    p.BN = (a->N > 128 && w256 * 100 <= w128 * 160) ? 256 : 128;
+    // measured on B200 (scripts/gemm_probe.py, SWEEP=1): the 256-wide tile wins on every shape of the path
+    // (the 128-wide one is shared-memory-port bound) unless it leaves more than half of the SMs without a tile
+    const int64_t tiles256 = (int64_t)ceil_div_i(a->M, TC_BM * ctas) * ceil_div_i(a->N, 256);
+    p.BN = (a->N > 128 && tiles256 * 2 >= units) ? 256 : 128;
   }
   if (g_force_bn == 128 || g_force_bn == 256) p.BN = g_force_bn;
   if (a->n_split > 0)
     B200_CHECK_ARG(a->n_split % 32 == 0, "gemm: n_split must be a multiple of 32");
-  const uint32_t stage_bytes = TC_BM * 128u + (uint32_t)p.BN * 128u;
+  const uint32_t stage_bytes = TC_BM * 128u + (uint32_t)(p.BN / ctas) * 128u;
   p.stages = (TC_SMEM_LIMIT - 1024 - 256 - TC_STAGE_BYTES) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
-  p.num_m = ceil_div_i(a->M, TC_BM);
+  p.num_m = ceil_div_i(a->M, TC_BM * ctas);
   p.num_n = ceil_div_i(a->N, p.BN);
   CUtensorMap ma, mb;
   if (!p.a_mn) {
@@ -384,23 +415,41 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep, cudaStream_t
     if (make_map(&ma, a->A, (uint64_t)a->M, (uint64_t)a->K, (uint64_t)a->lda, 64, 64)) return 1;
   }
   if (!p.b_mn) {
-    if (make_map(&mb, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, 64, (uint32_t)p.BN)) return 1;
+    if (make_map(&mb, a->B, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldb, 64, (uint32_t)(p.BN / ctas))) return 1;
   } else {
     if (make_map(&mb, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, 64)) return 1;
   }
   int tiles = p.num_m * p.num_n;
-  int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  int grid = (tiles < units ? tiles : units) * ctas;
   size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256 + TC_STAGE_BYTES;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = ctas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+#define TC_LAUNCH(MODE_)                                                                                   \
+  do {                                                                                                     \
+    if (ctas == 2) B200_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE_, 2>, ma, mb, p, ep));        \
+    else B200_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE_, 1>, ma, mb, p, ep));                  \
+  } while (0)
   switch (ep.mode) {
-    case B200REC_EPI_STORE: gemm_tc_kernel<0><<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep); break;
-    case B200REC_EPI_ACCUM: gemm_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep); break;
-    case B200REC_EPI_SILU_DUAL: gemm_tc_kernel<2><<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep); break;
-    case B200REC_EPI_BIAS_RESID: gemm_tc_kernel<3><<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep); break;
-    case B200REC_EPI_RESBLOCK: gemm_tc_kernel<4><<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep); break;
-    case B200REC_EPI_GT_BITS: gemm_tc_kernel<5><<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep); break;
-    case B200REC_EPI_FOLD_HEADS: gemm_tc_kernel<6><<<grid, TC_THREADS, smem, st>>>(ma, mb, p, ep); break;
+    case B200REC_EPI_STORE: TC_LAUNCH(0); break;
+    case B200REC_EPI_ACCUM: TC_LAUNCH(1); break;
+    case B200REC_EPI_SILU_DUAL: TC_LAUNCH(2); break;
+    case B200REC_EPI_BIAS_RESID: TC_LAUNCH(3); break;
+    case B200REC_EPI_RESBLOCK: TC_LAUNCH(4); break;
+    case B200REC_EPI_GT_BITS: TC_LAUNCH(5); break;
+    case B200REC_EPI_FOLD_HEADS: TC_LAUNCH(6); break;
     default: b200rec_set_error("gemm: bad epilogue %d", ep.mode); return 1;
   }
+#undef TC_LAUNCH
   B200_LAUNCH_OK();
   return 0;
 }

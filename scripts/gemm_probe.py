@@ -25,9 +25,16 @@ cases = [
     ("eval scores f32", 3072, 450000, D, 0, 0, L.EPI_STORE, torch.float32),
 ]
 only = sys.argv[1] if len(sys.argv) > 1 else None
+sweep = os.environ.get("SWEEP")
 res = []
-for name, M, N, K, am, bm, epi, cdt in cases:
+configs = [(0, 0)] if not sweep else [(1, 256), (2, 256), (1, 128), (2, 128)]
+for name, M, N, K, am, bm, epi, cdt in [c + () for c in cases for _ in configs]:
+    cfg_i = len([r for r in res if r[0] == name])
+    ctas_f, bn_f = configs[cfg_i % len(configs)]
+    L.lib().b200rec_gemm_force_ctas(ctas_f if ctas_f == 1 else 0)
+    L.lib().b200rec_gemm_force_bn(bn_f)
     if only and only not in name:
+        res.append((name,))
         continue
     A = torch.randn((M, K) if am == 0 else (K, M), device=dev).to(bf)
     B = torch.randn((N, K) if bm == 0 else (K, N), device=dev).to(bf)
@@ -54,5 +61,5 @@ for name, M, N, K, am, bm, epi, cdt in cases:
     ms = e0.elapsed_time(e1) / reps
     tf = 2.0 * M * N * K / ms / 1e9
     res.append((name, M, N, K, ms, tf))
-    print(f"{name:28s} M={M:6d} N={N:6d} K={K:6d}  {ms*1e3:9.1f} us  {tf:7.1f} TF/s", flush=True)
+    print(f"{name:28s} M={M:6d} N={N:6d} K={K:6d}  {ms*1e3:9.1f} us  {tf:7.1f} TF/s  ctas={ctas_f} bn={bn_f}", flush=True)
     del A, B, C, C2
