@@ -150,6 +150,10 @@ typedef struct {
    * of a [T, H*D] output).  If additionally c_split_stride > 0, column n is stored at
    * C + (n / n_split) * c_split_stride + m*ldc + n % n_split (per-head [H, T, D] blocks). */
   int n_split; int64_t c_split_stride; int64_t c2_split_stride;
+  /* optional split-K workspace (fp32): when the output has few tiles and K is long (weight gradients) the
+   * tcgen05 path splits each tile's k-range over idle SMs and sums the partials in fixed order.  Requires
+   * epilogue STORE, fp32 C, ldc == N % 4 == 0 contiguous rows; NULL disables. */
+  void* splitk_ws; size_t splitk_ws_bytes;
   /* B200REC_EPI_FOLD_HEADS only */
   int fold_hp;
   const uint8_t* fold_head_on; const int32_t* fold_head_cat; const uint32_t* fold_item_tags;

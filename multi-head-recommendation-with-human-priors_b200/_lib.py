@@ -37,6 +37,7 @@ class GemmArgs(C.Structure):
         ("bias", C.c_void_p),
         ("resid", C.c_void_p), ("ldr", C.c_int64),
         ("n_split", C.c_int), ("c_split_stride", C.c_int64), ("c2_split_stride", C.c_int64),
+        ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_size_t),
         ("fold_hp", C.c_int),
         ("fold_head_on", C.c_void_p), ("fold_head_cat", C.c_void_p), ("fold_item_tags", C.c_void_p),
         ("fold_id_offset", C.c_int64), ("fold_id_stride", C.c_int64),
@@ -142,7 +143,8 @@ def call(name, *args):
 
 
 def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epilogue=EPI_STORE, alpha=1.0,
-         alpha_dev=None, bias=None, resid=None, ldr=0, C2=None, ldc2=0, n_split=0, c_dtype=None, fold=None):
+         alpha_dev=None, bias=None, resid=None, ldr=0, C2=None, ldc2=0, n_split=0, c_dtype=None, fold=None,
+         splitk_ws=None):
     """C[M,N] = epi(A[M,K] @ B[N,K]^T).  A/B are tensors (or views) whose data_ptr is element (0,0)."""
     global launches
     a = GemmArgs()
@@ -157,6 +159,8 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epilogue=
     a.c_dtype = F32 if raw_out else (dt(C_out) if c_dtype is None else c_dtype)
     a.C2, a.ldc2 = ptr(C2), ldc2
     a.c2_dtype = dt(C2) if (C2 is not None and not raw_out) else F32
+    if splitk_ws is not None and ldc == N:
+        a.splitk_ws, a.splitk_ws_bytes = splitk_ws.data_ptr(), splitk_ws.numel() * splitk_ws.element_size()
     if fold is not None:   # (hp, head_on u8[M], head_cat i32[hp] or None, item_tags u32[N] or None, id_offset, id_stride)
         a.fold_hp, a.fold_head_on, a.fold_head_cat, a.fold_item_tags = fold[0], ptr(fold[1]), ptr(fold[2]), ptr(fold[3])
         a.fold_id_offset, a.fold_id_stride = fold[4], fold[5]

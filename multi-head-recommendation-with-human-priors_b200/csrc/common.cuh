@@ -42,6 +42,13 @@ template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __f
 // sigmoid via ex2 + approximate reciprocal (2 MUFU ops, no IEEE-division slow path): rel. error ~1e-6
 __device__ __forceinline__ float sigmoid_f(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
 __device__ __forceinline__ float silu_f(float z) { return z * sigmoid_f(z); }
+// one-MUFU SiLU for the bf16 tensor-core epilogues: z * sigmoid(z) = z/2 * (1 + tanh(z/2)); tanh.approx has
+// ~2^-11 relative error, far below bf16 resolution (the fp32 verification path keeps silu_f)
+__device__ __forceinline__ float silu_fast_f(float z) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+  return 0.5f * z * (1.f + t);
+}
 __device__ __forceinline__ float silu_grad_f(float z) {
   float s = sigmoid_f(z);
   return s * (1.f + z * (1.f - s));

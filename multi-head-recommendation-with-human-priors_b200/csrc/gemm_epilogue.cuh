@@ -221,7 +221,7 @@ __device__ __forceinline__ void epi_apply_vec4(const EpiParams& p, int m, int n,
   } else if (MODE == B200REC_EPI_SILU_DUAL) {
     store4_dt(p.C2, p.c2_dtype, epi_offset(p, m, n, p.ldc2, p.c2_split_stride), v);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = silu_f(v[i]);
+    for (int i = 0; i < 4; ++i) v[i] = silu_fast_f(v[i]);
     store4_dt(p.C, p.c_dtype, epi_offset(p, m, n, p.ldc, p.c_split_stride), v);
   } else if (MODE == B200REC_EPI_BIAS_RESID) {
     if (p.bias) {
@@ -249,7 +249,7 @@ __device__ __forceinline__ void epi_apply_vec4(const EpiParams& p, int m, int n,
     float r[4];
     load4<float>(p.resid + (int64_t)m * p.ldr + nr, r);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = r[i] + silu_f(v[i]);
+    for (int i = 0; i < 4; ++i) v[i] = r[i] + silu_fast_f(v[i]);
     store4_dt(p.C, p.c_dtype, epi_offset(p, m, n, p.ldc, p.c_split_stride), v);
   }
 }
@@ -293,7 +293,7 @@ __device__ __forceinline__ void epi_finish_vec4(const EpiParams& p, int m, int n
     for (int i = 0; i < 4; ++i) v[i] += b[i];
     if (p.C2) store4_dt(p.C2, p.c2_dtype, epi_offset(p, m, n, p.ldc2, p.c2_split_stride), v);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = r[i] + silu_f(v[i]);
+    for (int i = 0; i < 4; ++i) v[i] = r[i] + silu_fast_f(v[i]);
     store4_dt(p.C, p.c_dtype, epi_offset(p, m, n, p.ldc, p.c_split_stride), v);
   }
 }

@@ -26,6 +26,8 @@ struct TcParams {
   int stages;
   int a_mn, b_mn;  // 1 = MN-major operand
   int num_m, num_n;
+  int split_k, kb_per_split;      // split-K: work item = (tile, k-range); partial tiles go to a workspace
+  int64_t split_stride;           // elements between consecutive partial outputs
 };
 
 // CTAS = 1: one CTA per 128 x BN tile.  CTAS = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN
@@ -81,16 +83,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int num_tiles = p.num_m * p.num_n;             // p.num_m counts (128*CTAS)-row tiles
   const int num_k = (p.K + TC_BK - 1) / TC_BK;
   const int tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
+  const int num_items = num_tiles * p.split_k;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      for (int item = tile0; item < num_items; item += tile_step) {
+        const int tile = item % num_tiles, split = item / num_tiles;
         const int m0 = (tile % p.num_m) * (TC_BM * CTAS) + (int)rank * TC_BM;
         const int n0 = (tile / p.num_m) * p.BN + (int)rank * bn_cta;
-        for (int kb = 0; kb < num_k; ++kb) {
+        const int kb_beg = split * p.kb_per_split, kb_end = min(num_k, kb_beg + p.kb_per_split);
+        for (int kb = kb_beg; kb < kb_end; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
           const uint32_t sb = sa + a_bytes;
@@ -125,11 +130,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t ph = 0;
       int acc = 0;
       uint32_t acc_ph = 0;
-      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      for (int item = tile0; item < num_items; item += tile_step) {
+        const int split = item / num_tiles;
+        const int kb_beg = split * p.kb_per_split, kb_end = min(num_k, kb_beg + p.kb_per_split);
         mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * (uint32_t)p.BN;
-        for (int kb = 0; kb < num_k; ++kb) {
+        for (int kb = kb_beg; kb < kb_end; ++kb) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
@@ -142,8 +149,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                                        : umma_smem_desc(sa + k * 32u, 16u, 1024u);
             const uint64_t db = p.b_mn ? umma_smem_desc(sb + k * 2048u, 8192u, 1024u)
                                        : umma_smem_desc(sb + k * 32u, 16u, 1024u);
-            if (CTAS == 2) umma_bf16_2sm(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            const uint32_t accum = (kb > kb_beg || k > 0) ? 1u : 0u;
+            if (CTAS == 2) umma_bf16_2sm(d_tmem, da, db, idesc, accum);
+            else umma_bf16(d_tmem, da, db, idesc, accum);
           }
           // frees the smem stage (in both CTAs of a pair) when these MMAs retire
           if (CTAS == 2) umma_commit_2sm(empty_bar(s)); else umma_commit(empty_bar(s));
@@ -163,9 +171,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int cg = lane & 7, sub = lane >> 3;
     int acc = 0;
     uint32_t acc_ph = 0;
-    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+    const EpiParams ep_base = ep;
+    for (int item = tile0; item < num_items; item += tile_step) {
+      const int tile = item % num_tiles, split = item / num_tiles;
       const int m0 = (tile % p.num_m) * (TC_BM * CTAS) + (int)rank * TC_BM;
       const int n0 = (tile / p.num_m) * p.BN;
+      if (p.split_k > 1) ep.C = (float*)ep_base.C + (int64_t)split * p.split_stride;   // partial tile of this k-range
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * (uint32_t)p.BN;
@@ -315,6 +326,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
+// sums the split-K partial outputs in ascending split order (deterministic)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int split_k, int64_t stride,
+                                                            int64_t n4, float* __restrict__ out, float alpha,
+                                                            const float* __restrict__ alpha_dev) {
+  if (alpha_dev) alpha *= *alpha_dev;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < split_k; ++s) {
+      float v[4];
+      load4<float>(ws + (int64_t)s * stride + i * 4, v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] += v[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] *= alpha;
+    store4<float>(out + i * 4, acc);
+  }
+}
+
 // ------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -366,7 +396,7 @@ static int g_force_ctas = 0;  // test hook: 1 = never use CTA pairs
 extern "C" void b200rec_gemm_force_bn(int bn) { g_force_bn = bn; }
 extern "C" void b200rec_gemm_force_ctas(int ctas) { g_force_ctas = ctas; }
 
-int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep, cudaStream_t st) {
+int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep_in, cudaStream_t st) {
   B200_CHECK_ARG(((uintptr_t)a->A & 15) == 0 && ((uintptr_t)a->B & 15) == 0, "gemm: A/B must be 16-byte aligned");
   B200_CHECK_ARG(a->lda % 8 == 0 && a->ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 (16-byte pitch)");
   if (g_num_sms == 0) {
@@ -401,6 +431,21 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep, cudaStream_t
     p.BN = (a->N > 128 && tiles256 * 2 >= units) ? 256 : 128;
   }
   if (g_force_bn == 128 || g_force_bn == 256) p.BN = g_force_bn;
+  p.split_k = 1;
+  const int num_k_host = ceil_div_i(a->K, TC_BK);
+  if (a->splitk_ws != nullptr && ep_in.mode == B200REC_EPI_STORE && a->c_dtype == B200REC_F32 && a->n_split == 0 &&
+      g_force_bn == 0 && a->N > 128) {
+    // few output tiles but a long K (weight gradients): spread the k-range of each tile over idle SMs
+    const int64_t tiles256 = (int64_t)ceil_div_i(a->M, TC_BM * ctas) * ceil_div_i(a->N, 256);
+    int sk = (int)std::min<int64_t>(std::min<int64_t>(units / std::max<int64_t>(tiles256, 1), num_k_host / 8), 8);
+    if (sk >= 2 && (size_t)sk * a->M * a->ldc * sizeof(float) <= a->splitk_ws_bytes) {
+      p.BN = 256;
+      p.kb_per_split = ceil_div_i(num_k_host, sk);
+      p.split_k = ceil_div_i(num_k_host, p.kb_per_split);
+      p.split_stride = (int64_t)a->M * a->ldc;
+    }
+  }
+  if (p.split_k == 1) p.kb_per_split = num_k_host;
   if (a->n_split > 0)
     B200_CHECK_ARG(a->n_split % 32 == 0, "gemm: n_split must be a multiple of 32");
   const uint32_t stage_bytes = TC_BM * 128u + (uint32_t)(p.BN / ctas) * 128u;
@@ -419,8 +464,15 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep, cudaStream_t
   } else {
     if (make_map(&mb, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, 64)) return 1;
   }
-  int tiles = p.num_m * p.num_n;
+  int tiles = p.num_m * p.num_n * p.split_k;
   int grid = (tiles < units ? tiles : units) * ctas;
+  EpiParams ep = ep_in;
+  if (p.split_k > 1) {        // partial sums go to the workspace (alpha applied by the final reduction)
+    ep.C = a->splitk_ws;
+    ep.alpha = 1.f;
+    ep.alpha_dev = nullptr;
+    ep.vec_ok = 1;
+  }
   size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256 + TC_STAGE_BYTES;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -450,6 +502,11 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep, cudaStream_t
     default: b200rec_set_error("gemm: bad epilogue %d", ep.mode); return 1;
   }
 #undef TC_LAUNCH
+  if (p.split_k > 1) {
+    const int64_t n4 = (int64_t)a->M * a->ldc / 4;
+    splitk_reduce_kernel<<<(int)std::min<int64_t>((n4 + 255) / 256, 148 * 8), 256, 0, st>>>(
+        (const float*)a->splitk_ws, p.split_k, p.split_stride, n4, (float*)a->C, ep_in.alpha, ep_in.alpha_dev);
+  }
   B200_LAUNCH_OK();
   return 0;
 }

@@ -24,6 +24,36 @@ __device__ __forceinline__ void stats_merge(Stats& a, const Stats& b) {
   a.cnt += b.cnt;
 }
 
+__device__ __forceinline__ void stats_merge2(Stats& a, const Stats& b) {   // log2-domain variant
+  float m = fmaxf(a.m, b.m);
+  float fa = a.m == -INFINITY ? 0.f : exp2f(a.m - m);
+  float fb = b.m == -INFINITY ? 0.f : exp2f(b.m - m);
+  a.s = a.s * fa + b.s * fb;
+  a.w = a.w * fa + b.w * fb;
+  a.m = m;
+  a.gt += b.gt;
+  a.cnt += b.cnt;
+}
+__device__ Stats block_stats2(Stats v, Stats* red) {
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Stats t;
+    t.m = __shfl_xor_sync(0xffffffffu, v.m, o);
+    t.s = __shfl_xor_sync(0xffffffffu, v.s, o);
+    t.w = __shfl_xor_sync(0xffffffffu, v.w, o);
+    t.gt = __shfl_xor_sync(0xffffffffu, v.gt, o);
+    t.cnt = __shfl_xor_sync(0xffffffffu, v.cnt, o);
+    if (lane & o) { Stats u = t; stats_merge2(u, v); v = u; } else { stats_merge2(v, t); }
+  }
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  Stats r = red[0];
+  for (int i = 1; i < nw; ++i) stats_merge2(r, red[i]);
+  return r;
+}
+
 // deterministic block reduction of Stats (fixed tree), result broadcast
 __device__ Stats block_stats(Stats v, Stats* red) {
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -284,9 +314,12 @@ nce_loss_fwd_reg_kernel(const float* __restrict__ logits, int64_t ld_logits, int
     }
     return;
   }
-  // the row: thread owns vectors tid, tid+256, ...
+  // the row: thread owns vectors tid, tid+256, ...   z2 = tau * log2(e) * cos  (exp(z - m) == exp2(z2 - m2))
+  const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+  const float tau2 = tau * LOG2E;
   float z[NCE_RV][4];
-  float m = -INFINITY;
+  float m2 = -INFINITY;
+  int n_mine = 0;
 #pragma unroll
   for (int k = 0; k < NCE_RV; ++k) {
     int v = tid + k * 256;
@@ -294,103 +327,116 @@ nce_loss_fwd_reg_kernel(const float* __restrict__ logits, int64_t ld_logits, int
       load4<float>(logits + (int64_t)t * ld_logits + v * 4, z[k]);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        z[k][e] *= tau;
-        m = fmaxf(m, z[k][e]);
+        z[k][e] *= tau2;
+        m2 = fmaxf(m2, z[k][e]);
       }
+      n_mine += 4;
     }
   }
-  const float pos0 = s_valid[0] ? s_pos[0] : INFINITY;
-  Stats loc;
-  loc.m = m; loc.s = 0.f; loc.w = 0.f; loc.gt = 0; loc.cnt = 0;
+  const float pos0_2 = s_valid[0] ? s_pos[0] * LOG2E : INFINITY;
+  Stats loc;   // in the log2 domain: m = max z2, s = sum 2^(z2-m), w = sum 2^(z2-m) * z2
+  loc.m = m2; loc.s = 0.f; loc.w = 0.f; loc.gt = 0; loc.cnt = n_mine;
 #pragma unroll
   for (int k = 0; k < NCE_RV; ++k) {
     int v = tid + k * 256;
     if (v < n_vec) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        float ex = __expf(z[k][e] - m);
+        float ex = exp2f(z[k][e] - m2);
         loc.s += ex;
-        loc.w += ex * z[k][e];
-        loc.gt += z[k][e] > pos0;
-        loc.cnt += 1;
+        loc.w = fmaf(ex, z[k][e], loc.w);
+        loc.gt += z[k][e] > pos0_2;
       }
     }
   }
-  const Stats all = block_stats(loc, red_stats);
-  float a_common = 0.f;
+  const Stats all = block_stats2(loc, red_stats);
+
+  // exact pass for offsets whose target filters some negatives (rare): block-wide, one offset at a time
+  __shared__ Stats s_st[NCE_MAXP];
   for (int p = 0; p < P; ++p) {
+    if (!(s_valid[p] && s_masked[p])) continue;   // block-uniform
+    const uint32_t* bits = same_bits + (r0 + p) * n_words;
+    const float posp_2 = s_pos[p] * LOG2E;
+    float mm = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < NCE_RV; ++k) {
+      int v = tid + k * 256;
+      if (v < n_vec) {
+        uint32_t wbits = bits[(v * 4) >> 5] >> ((v * 4) & 31);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (!((wbits >> e) & 1u)) mm = fmaxf(mm, z[k][e]);
+      }
+    }
+    Stats l2;
+    l2.m = mm; l2.s = 0.f; l2.w = 0.f; l2.gt = 0; l2.cnt = 0;
+#pragma unroll
+    for (int k = 0; k < NCE_RV; ++k) {
+      int v = tid + k * 256;
+      if (v < n_vec) {
+        uint32_t wbits = bits[(v * 4) >> 5] >> ((v * 4) & 31);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (!((wbits >> e) & 1u)) {
+            float ex = exp2f(z[k][e] - mm);
+            l2.s += ex;
+            l2.w = fmaf(ex, z[k][e], l2.w);
+            l2.gt += z[k][e] > posp_2;
+            l2.cnt += 1;
+          }
+      }
+    }
+    const Stats st = block_stats2(l2, red_stats);
+    if (tid == 0) s_st[p] = st;
+  }
+  __syncthreads();
+  // per-offset scalars: thread p owns offset p (instead of every thread repeating all of them)
+  __shared__ float s_acoef[NCE_MAXP];
+  if (tid < P) {
+    const int p = tid;
+    float acoef = 0.f;
     if (!s_valid[p]) {
-      if (tid == 0) {
-        loss[(int64_t)t * P + p] = 0.f;
-        g0[(int64_t)t * P + p] = 0.f;
-        dscale[(int64_t)t * P + p] = 0.f;
-        rank0[(int64_t)t * P + p] = -1;
-        nvalid[(int64_t)t * P + p] = 0;
-      }
-      continue;
-    }
-    Stats st = all;
-    if (s_masked[p]) {  // exact pass over the negatives this target does not filter
-      const uint32_t* bits = same_bits + (r0 + p) * n_words;
-      float mm = -INFINITY;
-#pragma unroll
-      for (int k = 0; k < NCE_RV; ++k) {
-        int v = tid + k * 256;
-        if (v < n_vec) {
-          uint32_t wbits = bits[(v * 4) >> 5] >> ((v * 4) & 31);
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (!((wbits >> e) & 1u)) mm = fmaxf(mm, z[k][e]);
-        }
-      }
-      Stats l2;
-      l2.m = mm; l2.s = 0.f; l2.w = 0.f; l2.gt = 0; l2.cnt = 0;
-#pragma unroll
-      for (int k = 0; k < NCE_RV; ++k) {
-        int v = tid + k * 256;
-        if (v < n_vec) {
-          uint32_t wbits = bits[(v * 4) >> 5] >> ((v * 4) & 31);
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (!((wbits >> e) & 1u)) {
-              float ex = __expf(z[k][e] - mm);
-              l2.s += ex;
-              l2.w += ex * z[k][e];
-              l2.gt += z[k][e] > s_pos[p];
-              l2.cnt += 1;
-            }
-        }
-      }
-      st = block_stats(l2, red_stats);
-    }
-    const float zp = s_pos[p];
-    const float M = fmaxf(st.m, zp);
-    const float en = st.m == -INFINITY ? 0.f : __expf(st.m - M);
-    const float ep = __expf(zp - M);
-    const float denom = st.s * en + ep;
-    const float lse = M + __logf(denom);
-    const float c = s_coef[p];
-    if (tid == 0) {
-      s_lse[p] = lse;
-      loss[(int64_t)t * P + p] = c * (lse - zp);
-      g0[(int64_t)t * P + p] = c * (ep / denom - 1.f);
-      dscale[(int64_t)t * P + p] = c * ((st.w * en + ep * zp) / denom - zp);
+      loss[(int64_t)t * P + p] = 0.f;
+      g0[(int64_t)t * P + p] = 0.f;
+      dscale[(int64_t)t * P + p] = 0.f;
+      rank0[(int64_t)t * P + p] = -1;
+      nvalid[(int64_t)t * P + p] = 0;
+    } else {
+      const Stats st = s_masked[p] ? s_st[p] : all;
+      const float zp2 = s_pos[p] * LOG2E;               // positive logit, log2 domain
+      const float M = fmaxf(st.m, zp2);
+      const float en = st.m == -INFINITY ? 0.f : exp2f(st.m - M);
+      const float ep = exp2f(zp2 - M);
+      const float denom = st.s * en + ep;
+      const float lse2 = M + __log2f(denom);
+      const float c = s_coef[p];
+      s_lse[p] = lse2;
+      loss[(int64_t)t * P + p] = c * (lse2 - zp2) * LN2;
+      g0[(int64_t)t * P + p] = c * (__fdividef(ep, denom) - 1.f);
+      // d loss / d logit_scale = sum_k softmax_k z_k - z_0   (natural-log logits = z2 * ln2)
+      dscale[(int64_t)t * P + p] = c * (__fdividef(st.w * en + ep * zp2, denom) - zp2) * LN2;
       rank0[(int64_t)t * P + p] = (p == 0 || s_masked[p]) ? st.gt : -1;
       nvalid[(int64_t)t * P + p] = st.cnt + 1;
+      if (!s_masked[p]) acoef = c * exp2f(all.m - lse2);
     }
-    if (!s_masked[p]) a_common += c * __expf(all.m - lse);
+    s_acoef[p] = acoef;
   }
   if (G == nullptr) return;
   __syncthreads();
+  float a_common = 0.f;  // sum over unfiltered offsets of coef_p * exp(m_all - lse_p)
   int any_masked = 0;
-  for (int p = 0; p < P; ++p) any_masked |= (s_valid[p] && s_masked[p]);
+  for (int p = 0; p < P; ++p) {
+    a_common += s_acoef[p];
+    any_masked |= (s_valid[p] && s_masked[p]);
+  }
+  a_common *= tau;
 #pragma unroll
   for (int k = 0; k < NCE_RV; ++k) {
     int v = tid + k * 256;
     if (v < n_vec) {
       float g[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) g[e] = a_common * __expf(z[k][e] - all.m);
+      for (int e = 0; e < 4; ++e) g[e] = a_common * exp2f(z[k][e] - all.m);
       if (any_masked) {
         for (int p = 0; p < P; ++p) {
           if (s_valid[p] && s_masked[p]) {
@@ -398,12 +444,10 @@ nce_loss_fwd_reg_kernel(const float* __restrict__ logits, int64_t ld_logits, int
             uint32_t wbits = bits[(v * 4) >> 5] >> ((v * 4) & 31);
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              if (!((wbits >> e) & 1u)) g[e] += s_coef[p] * __expf(z[k][e] - s_lse[p]);
+              if (!((wbits >> e) & 1u)) g[e] += tau * s_coef[p] * exp2f(z[k][e] - s_lse[p]);
           }
         }
       }
-#pragma unroll
-      for (int e = 0; e < 4; ++e) g[e] *= tau;
       store4<TA>(G + (int64_t)t * ldg + v * 4, g);
     }
   }

@@ -368,6 +368,7 @@ class HSTU(nn.Module):
         a_dt = L.dt(act)
         st = L.stream()
         drop_p = self._drop_p_last
+        skws = torch.empty(8 * D * 4 * D, dtype=torch.float32, device=dev) if act != torch.float32 else None
         for i in reversed(range(self._num_blocks)):
             blk = self._hstu._attention_layers[i]
             x, mean1, rstd1, n, actv, pre, a, mean2, rstd2, oin = saved[i]
@@ -381,7 +382,7 @@ class HSTU(nn.Module):
             L.gemm(dxb, w[f"o{i}"], d_oin, T, D, D, lda=D, ldb=D, b_major=1, ldc=D)
             # dW_o[Dout, Din] = dx^T @ oin  (both operands MN-major, K = T)
             dWo = torch.empty((D, D), dtype=torch.float32, device=dev)
-            L.gemm(dxb, oin, dWo, D, D, T, lda=D, a_major=1, ldb=D, b_major=1, ldc=D)
+            L.gemm(dxb, oin, dWo, D, D, T, lda=D, a_major=1, ldb=D, b_major=1, ldc=D, splitk_ws=skws)
             dbo = torch.empty(D, dtype=torch.float32, device=dev)
             L.colsum(dx, T, D, D, dbo)
             d_pre = torch.empty((T, 4 * D), dtype=act, device=dev)
@@ -400,7 +401,7 @@ class HSTU(nn.Module):
                    sl(d_pre, 2).data_ptr(), sl(d_pre, 3).data_ptr(), sl(d_pre, 1).data_ptr(), st)
             # dW_uvqk[D, 4D] = n^T @ d_pre  (both MN-major, K = T)
             dWu = torch.empty((D, 4 * D), dtype=torch.float32, device=dev)
-            L.gemm(n, d_pre, dWu, D, 4 * D, T, lda=D, a_major=1, ldb=4 * D, b_major=1, ldc=4 * D)
+            L.gemm(n, d_pre, dWu, D, 4 * D, T, lda=D, a_major=1, ldb=4 * D, b_major=1, ldc=4 * D, splitk_ws=skws)
             # dn = d_pre @ W_uvqk^T  (W [D, 4D] = [N, K] -> K-major B)
             dn = torch.empty((T, D), dtype=act, device=dev)
             L.gemm(d_pre, w[f"uvqk{i}"], dn, T, D, 4 * D, lda=4 * D, ldb=4 * D, ldc=D)

@@ -508,3 +508,18 @@ def test_dropout_mask_statistics_and_fwd_bwd_consistency():
     sg = torch.sigmoid(pre[:, :D])
     assert torch.allclose(da, ar.grad, rtol=1e-4, atol=1e-5)
     assert torch.allclose(d_pre[:, :D], u.grad * sg * (1 + pre[:, :D] * (1 - sg)), rtol=1e-4, atol=1e-5)
+
+
+def test_gemm_split_k_weight_gradient_shape():
+    """dW = X^T dY with few output tiles and long K goes through the split-K path (deterministic reduce)."""
+    M, N, K = 512, 512, 6400
+    A, B = _mk_operands(M, N, K, 1, 1, torch.bfloat16, seed=120)
+    ws = torch.empty(8 * M * N, device=dev())
+    outs = []
+    for _ in range(2):
+        Cm = torch.full((M, N), float("nan"), device=dev())
+        L.gemm(A, B, Cm, M, N, K, lda=M, ldb=N, ldc=N, a_major=1, b_major=1, splitk_ws=ws, alpha=0.5)
+        outs.append(Cm)
+    ref = 0.5 * _gemm_ref(A, B, 1, 1)
+    assert (outs[0] - ref).abs().max().item() / ref.abs().max().item() < 2e-3
+    assert torch.equal(outs[0], outs[1])
