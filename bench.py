@@ -177,8 +177,10 @@ def main():
                             f"items={cfg['item_num']}",
                 "per_gpu_batch": cfg["train_batch_size"], "global_batch": cfg["train_batch_size"] * world,
                 "parallelism": f"dp{world}" + ("+row-sharded-table(a2a)" if world > 1 and not args.replicate_table else ""), "l2": "working set >> 126 MB L2 (activations + 1.8 GB table); no flush",
-                "step": "cuda-graph replay per 128-token bucket" if (world == 1 and not args.no_graph and not args.profile)
-                else "eager"}}
+                "step": ("eager" if (args.no_graph or args.profile or (world > 1 and args.replicate_table)) else
+                         "cuda-graph replay per 128-token bucket" if world == 1 else
+                         "eager id exchange + row fetch, cuda-graph fwd/bwd per 128-token bucket, eager all-reduce / "
+                         "gradient-row push / AdamW")}}
     if args.impl == "reference":
         if rank != 0:
             return
@@ -207,8 +209,8 @@ def main():
     dl = synth.make_dataload(cfg)
     torch.manual_seed(2020)
     model = HSTU(cfg, dl, compute_dtype=dtype).to(dev).train()  # training mode: Philox dropout at the preset's rate
-    use_graph = (world == 1) and not args.no_graph and not args.profile
-    opt = FusedAdamW(model, lr=1e-4, weight_decay=0.0, device_step=use_graph)
+    use_graph = not args.no_graph and not args.profile and not (world > 1 and args.replicate_table)
+    opt = FusedAdamW(model, lr=1e-4, weight_decay=0.0, device_step=use_graph and world == 1)
     if world > 1 and not args.replicate_table:
         model.shard_item_table()          # rows id % W == rank; lookups / gradient rows by all-to-all
     dp = parallel.DataParallel(model, opt) if world > 1 else None
@@ -224,8 +226,8 @@ def main():
     n_tok = [int(b[2][:, :Lc].sum()) for b in host_batches]     # host metadata (the collate fn knows it)
     stepper = None
     if use_graph:
-        from b200rec.graphed import GraphedTrainStep
-        stepper = GraphedTrainStep(model, opt, dev_batches[0], bucket=128)
+        from b200rec.graphed import GraphedTrainStep, GraphedShardedStep
+        stepper = (GraphedTrainStep if world == 1 else GraphedShardedStep)(model, opt, dev_batches[0], bucket=128)
 
     def eager_step(batch):
         opt.zero_grad()

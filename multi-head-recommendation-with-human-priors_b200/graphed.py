@@ -57,7 +57,7 @@ class GraphedTrainStep(object):
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         n0 = L.launches
-        with torch.cuda.graph(g, pool=self.pool):
+        with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
             out = self._eager(T_b)
         if self.pool is None:
             self.pool = g.pool()
@@ -79,4 +79,105 @@ class GraphedTrainStep(object):
         g.replay()
         self.opt.step_count += 1
         L.launches += n_launch
+        return out
+
+
+class GraphedShardedStep(object):
+    """Multi-GPU step with a row-sharded item table (`HSTU.shard_item_table`), split in three:
+
+      pre   (eager)  negative-id all-gather, unique, all-to-all row fetch into a fixed-capacity row cache
+                     (`HSTU.prepare_rows`): collectives and data-dependent sizes live here;
+      graph (replay) forward + backward on static buffers -> dense gradients in ONE flat buffer shared by
+                     all buckets, and one gradient row per cache row;
+      post  (eager)  flat all-reduce of the dense gradients, all-to-all push of the cache-row gradients to
+                     their owners (deterministic segment reduce there), fused AdamW with grad_scale = 1/W.
+
+    The eager part is ~40 launches instead of ~1200, so the ranks stay GPU-bound.
+    """
+
+    def __init__(self, model, optimizer, example_batch, bucket=128, warmup=2, group=None):
+        import torch.distributed as dist
+        assert model.sharded_table is not None, "call model.shard_item_table() first"
+        assert not optimizer.device_step, "the optimizer runs eagerly here: FusedAdamW(device_step=False)"
+        self.dist, self.group = dist, group
+        self.model, self.opt, self.bucket, self.warmup = model, optimizer, bucket, warmup
+        items, neg, mask, tags = example_batch
+        dev = items.device
+        self.world = model.sharded_table.W
+        B, LP = items.shape
+        n_sets = neg.shape[1]
+        n_neg = neg.shape[0] * neg.shape[2] * (self.world if model.share_negatives else 1)
+        D = model.item_embedding.weight.shape[1]
+        self.cap = (B + 1) * LP + n_sets * n_neg             # every requested id distinct
+        self.static = tuple(torch.empty_like(t) for t in example_batch)
+        i64 = dict(dtype=torch.int64, device=dev)
+        self.prep = dict(W=torch.zeros((self.cap, D), dtype=torch.float32, device=dev),
+                         items_idx=torch.zeros((B + 1, LP), **i64), neg_idx=torch.zeros((n_sets, n_neg), **i64),
+                         gl_items=torch.zeros((B + 1, LP), **i64), gl_neg=torch.zeros((n_sets, n_neg), **i64),
+                         cached=True, push=False, n_rows=None)
+        self.graphs = {}
+        self.pool = None
+        self.max_tokens = B * model.max_seq_length
+        self.dense = self.flat = self.views = None
+
+    def _fill(self, batch):
+        for s, t in zip(self.static, batch):
+            s.copy_(t, non_blocking=True)
+        p = self.model.prepare_rows(self.static[0], self.static[1], static=True)
+        U = p["n_rows"]
+        self.prep["W"][:U].copy_(p["W"])
+        for k in ("items_idx", "neg_idx", "gl_items", "gl_neg"):
+            self.prep[k].copy_(p[k])
+        return U
+
+    def _fwd_bwd(self, T_b):
+        self.opt.zero_grad()
+        out = self.model(self.static, n_tokens=T_b, prepared=self.prep)
+        out["loss"].backward()
+        if self.flat is None:
+            emb = self.model.item_embedding.weight
+            self.dense = [p for p in self.model.parameters() if p is not emb and p.grad is not None]
+            sizes = [(p.numel() + 3) // 4 * 4 for p in self.dense]    # 16-byte aligned views
+            self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=emb.device)
+            self.views, off = [], 0
+            for p, n in zip(self.dense, sizes):
+                self.views.append(self.flat[off:off + p.numel()].view_as(p))
+                off += n
+        torch._foreach_copy_(self.views, [p.grad for p in self.dense])
+        return out, self.model.cache_grad
+
+    def _capture(self, T_b):
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(self.warmup):
+                self._fwd_bwd(T_b)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        n0 = L.launches
+        with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
+            out, cache_grad = self._fwd_bwd(T_b)
+        if self.pool is None:
+            self.pool = g.pool()
+        return g, out, cache_grad, L.launches - n0
+
+    def __call__(self, batch, n_tokens):
+        T_b = min(self.max_tokens, max(self.bucket, (int(n_tokens) + self.bucket - 1) // self.bucket * self.bucket))
+        U = self._fill(batch)
+        entry = self.graphs.get(T_b)
+        if entry is None:
+            entry = self._capture(T_b)
+            self.graphs[T_b] = entry
+        g, out, cache_grad, n_launch = entry
+        g.replay()
+        L.launches += n_launch
+        model, W = self.model, self.world
+        for p, v in zip(self.dense, self.views):
+            p.grad = v
+        model.item_embedding.weight.grad = None
+        if W > 1:
+            self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.SUM, group=self.group)
+        model.emb_grad = model.sharded_table.push_grads(cache_grad[:U], scale=1.0)
+        self.opt.step(grad_scale=1.0 / W)
         return out

@@ -280,6 +280,23 @@ class HSTU(nn.Module):
         cache = self.sharded_table.fetch(uniq)
         return cache, inv[:B * LP].view(B, LP).contiguous(), inv[B * LP:].view(neg_ids.shape).contiguous(), uniq
 
+    def prepare_rows(self, items, neg_items, static=False):
+        """Everything of a training step that needs collectives or data-dependent shapes, so it can run
+        eagerly in front of a captured graph: the dummy row of static-shape mode, the cross-rank negative
+        id all-gather (hstu.py:673,755) and, for a row-sharded table, the all-to-all fetch of the unique
+        requested rows.  Returns the table the kernels read and the row indices into it."""
+        if static:
+            items = torch.cat([items, torch.zeros_like(items[:1])], dim=0)
+        items = items.contiguous()
+        if self.share_negatives:
+            neg_items = parallel.gather_negative_ids(neg_items)      # [W*B, sets, n]
+        n_sets = neg_items.shape[1]
+        n_neg = neg_items.shape[0] * neg_items.shape[2]
+        neg_ids = neg_items.permute(1, 0, 2).contiguous().view(n_sets, n_neg)   # set-major id lists
+        W, items_idx, neg_idx, uniq = self._table_rows(items, neg_ids)
+        return dict(W=W, items_idx=items_idx, neg_idx=neg_idx, gl_items=items, gl_neg=neg_ids,
+                    cached=uniq is not None, n_rows=(uniq.numel() if uniq is not None else None))
+
     @staticmethod
     def _tokens(valid, force_last=False):
         """Jagged index of a [B, L] validity mask.  force_last adds position L-1 of every sequence as a
@@ -434,7 +451,7 @@ class HSTU(nn.Module):
         return hd, z, yb
 
     # ------------------------------------------------------------------ training (hstu.py:631-872)
-    def forward(self, interaction, n_tokens=None):
+    def forward(self, interaction, n_tokens=None, prepared=None):
         """`n_tokens` (optional host int >= number of valid context tokens, e.g. from the collate fn): builds
         the jagged index with static shapes and no host sync, padding with dummy tokens up to n_tokens — the
         form a CUDA graph can capture (see graphed.GraphedTrainStep)."""
@@ -443,34 +460,32 @@ class HSTU(nn.Module):
             raise L.B200RecError("b200rec.HSTU.forward needs CUDA tensors (there is no CPU path)")
         params = [p for p in self.parameters()]
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        loss = _TrainStep.apply(self, (need_grad, n_tokens), items, neg_items, mask, tags, *params)
+        loss = _TrainStep.apply(self, (need_grad, n_tokens, prepared), items, neg_items, mask, tags, *params)
         out = defaultdict(float)
         out.update(self._last_logs)
         out["loss"] = loss
         return out
 
-    def _train_forward(self, items, neg_items, mask, tags, need_grad, n_tokens=None):
+    def _train_forward(self, items, neg_items, mask, tags, need_grad, n_tokens=None, prepared=None):
         dev = items.device
         D, P, Lc = self._hstu_embedding_dim, self.pred_len, self.max_seq_length
-        if n_tokens is not None:
+        static = n_tokens is not None
+        if prepared is None:
+            prepared = self.prepare_rows(items, neg_items, static)
+        if static:
             # static-shape mode: one all-padding dummy row (index B) owns the dummy tokens; it has no valid
             # position, so it contributes no loss, no gradient and no attention keys.
-            items = torch.cat([items, torch.zeros_like(items[:1])], dim=0)
             mask = torch.cat([mask, torch.zeros_like(mask[:1])], dim=0)
             if tags.numel() > 0:
                 tags = torch.cat([tags, torch.zeros_like(tags[:1])], dim=0)
+        W, items, neg_ids = prepared["W"], prepared["items_idx"], prepared["neg_idx"]
+        gl_items, gl_neg_ids = prepared["gl_items"], prepared["gl_neg"]
+        uniq_rows_ids = prepared["cached"] or None
         B, LP = items.shape
         assert LP == Lc + P, f"items must be [B, L+P] = [B, {Lc + P}], got {tuple(items.shape)}"
         act, a_dt, st = self._act(), L.dt(self._act()), L.stream()
-        items = items.contiguous()
         m = mask.bool()
-        if self.share_negatives:
-            neg_items = parallel.gather_negative_ids(neg_items)      # [W*B, sets, n], hstu.py:673,755
-        n_sets = neg_items.shape[1]
-        n_neg = neg_items.shape[0] * neg_items.shape[2]
-        neg_ids = neg_items.permute(1, 0, 2).contiguous().view(n_sets, n_neg)   # set-major id lists
-        gl_items, gl_neg_ids = items, neg_ids                                   # global item ids
-        W, items, neg_ids, uniq_rows_ids = self._table_rows(items, neg_ids)
+        n_sets, n_neg = neg_ids.shape
         ctx = {}
         # ---- jagged token index (valid context positions only)
         if n_tokens is None:
@@ -601,7 +616,8 @@ class HSTU(nn.Module):
                        tok_index=tok_index, w=w, saved=saved, hd=hd, z=z, yb=yb, qhat=qhat, qinv=qinv, that=that,
                        tinv=tinv, nhat=nhat, ninv=ninv, neg_ids=neg_ids, job_out=job_out, scale=scale, half=half,
                        items=items, mask=m, n_neg=n_neg, ld_neg=ld_neg, Hx=Hx, used_sets=used_sets,
-                       gl_items=gl_items, gl_neg_ids=gl_neg_ids, uniq_rows_ids=uniq_rows_ids)
+                       gl_items=gl_items, gl_neg_ids=gl_neg_ids, uniq_rows_ids=uniq_rows_ids,
+                       n_cache_rows=W.shape[0], push=prepared.get("push", True))
         return loss, logs, ctx
 
     def _train_backward(self, ctx, gscale):
@@ -702,12 +718,14 @@ class HSTU(nn.Module):
             ids = torch.where(gl == 0, torch.zeros_like(ids), ids)
         uniq_ids, uniq_rows, n_uniq = parallel.cuda_segment_reduce(ids, rows)
         if sharded:
-            # one gradient row per fetched id, sent to the owners; the owner reduces over ranks (mean)
-            U = ctx["uniq_rows_ids"].numel()
+            # one gradient row per fetched (cache) row, sent to the owners; the owner reduces over ranks (mean)
+            U = ctx["n_cache_rows"]
             g = torch.zeros((U, D), dtype=torch.float32, device=dev)
             L.call("b200rec_rows_to_dense", (uniq_ids - 1).contiguous().data_ptr(), uniq_rows.data_ptr(),
                    n_uniq.data_ptr(), n_rows, D, g.data_ptr(), 0, st)
-            self.emb_grad = self.sharded_table.push_grads(g, scale=1.0 / self.sharded_table.W)
+            self.cache_grad = g
+            if ctx["push"]:
+                self.emb_grad = self.sharded_table.push_grads(g, scale=1.0 / self.sharded_table.W)
             return grads
         self.emb_grad = (uniq_ids, uniq_rows, n_uniq)
         if not self.sparse_embedding_grad:
@@ -935,8 +953,8 @@ class _TrainStep(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, flags, items, neg_items, mask, tags, *params):
-        need_grad, n_tokens = flags
-        loss, logs, saved = model._train_forward(items, neg_items, mask, tags, need_grad, n_tokens)
+        need_grad, n_tokens, prepared = flags
+        loss, logs, saved = model._train_forward(items, neg_items, mask, tags, need_grad, n_tokens, prepared)
         ctx.model, ctx.saved, ctx.params = model, saved, params
         ctx.set_materialize_grads(False)
         model._last_logs = logs

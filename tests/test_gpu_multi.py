@@ -95,3 +95,76 @@ def test_two_gpu_sharded_training_and_eval():
     ref_idx, _, _ = orc.collect_topk(fx["scores"], max(cfg["topk"]), cfg["split_mode"])
     for r, *_, idx in res:
         assert (idx.numpy() == ref_idx).all()
+
+
+def _graph_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    q.put((rank, _graphed_vs_eager(dev, rank, world)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _graphed_vs_eager(dev, rank, world, steps=3):
+    """Max relative parameter difference after `steps` AdamW steps: eager sharded step vs pre/graph/post."""
+    from b200rec import synth, parallel
+    from b200rec.hstu import HSTU
+    from b200rec.optim import FusedAdamW
+    from b200rec.graphed import GraphedShardedStep
+    fx = load_golden("prior_additive")
+    cfg = synth.Config(fx["cfg"])
+    cfg["sparse_embedding_grad"] = True
+    dl = synth.Dataload(cfg["item_num"], fx["category_counts"], fx["category_to_int"])
+    batches = [tuple(t.to(dev) for t in synth.make_train_batch(cfg, seed=70 + 10 * i + rank, item_tags=fx["item_tags"],
+                                                                 zipf=False)) for i in range(steps)]
+    Lc = cfg["MAX_ITEM_LIST_LENGTH"]
+    models = []
+    for mode in ("eager", "graph"):
+        model = HSTU(cfg, dl, compute_dtype=torch.float32)
+        model.load_state_dict(fx["state_dict"])
+        model = model.to(dev).eval()
+        model.shard_item_table()
+        opt = FusedAdamW(model, lr=1e-2, weight_decay=0.01)
+        if mode == "eager":
+            dp = parallel.DataParallel(model, opt)
+            for b in batches:
+                opt.zero_grad()
+                model(b)["loss"].backward()
+                dp.sync_gradients()
+                opt.step()
+        else:
+            stepper = GraphedShardedStep(model, opt, batches[0], bucket=32)
+            for b in batches:
+                stepper(b, int(b[2][:, :Lc].sum()))
+        models.append(model)
+    torch.cuda.synchronize()
+    worst = 0.0
+    for (n, a), (_, b) in zip(models[0].named_parameters(), models[1].named_parameters()):
+        worst = max(worst, (a - b).abs().max().item() / max(a.abs().max().item(), 1e-6))
+    return worst
+
+
+def test_graphed_sharded_step_single_gpu():
+    assert _graphed_vs_eager(torch.device("cuda:0"), 0, 1) < 2e-4
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_graphed_sharded_step_two_gpus():
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    W = 2
+    procs = [ctx.Process(target=_graph_worker, args=(r, W, port, q)) for r in range(W)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(W)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, worst in res:
+        assert worst < 2e-4
