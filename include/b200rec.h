@@ -186,6 +186,18 @@ int b200rec_hstu_attn_tc_bwd(const void* act, const void* pre, int ld, const int
                              const uint8_t* key_valid, int B, int T, int n_heads, int dh, float inv_n,
                              const void* d_out, void* d_pre, void* stream);
 
+/* Short-sequence variants (bf16, dh in {32, 64}, every real sequence <= max_len <= 64 tokens): one CTA
+ * per (sequence, head), warp-level mma.sync on register-resident score blocks, backward (dq, dk, dv)
+ * in ONE launch without atomics.  Same buffers as the _tc_ variants.  A sequence longer than 64 tokens
+ * is only legal if none of its keys is valid (the all-padding dummy row of static-shape mode); its
+ * outputs / gradients are zeros. */
+int b200rec_hstu_attn_seq_fwd(const void* act, int ld, const int32_t* seq_off, const uint8_t* key_valid,
+                              int B, int T, int n_heads, int dh, float inv_n, int max_len, float* out,
+                              void* stream);
+int b200rec_hstu_attn_seq_bwd(const void* act, const void* pre, int ld, const int32_t* seq_off,
+                              const uint8_t* key_valid, int B, int T, int n_heads, int dh, float inv_n,
+                              int max_len, const void* d_out, void* d_pre, void* stream);
+
 /* ------------------------------------------------------------------ NCE / sampled softmax (a9-a12)
  * hstu.py:600-619 nce_loss + :697 cross_entropy + :704-713 per-offset means, restructured:
  * one query row per (head, token) shared by all offsets p (SURVEY A.4 dedup identity).

@@ -75,6 +75,8 @@ _SIGS = {
                                         _P, _P, _P, _P]),
     "b200rec_hstu_attn_tc_fwd": (C.c_int, [_P, _I, _P, _P, _I, _I, _I, _I, _F, _P, _P]),
     "b200rec_hstu_attn_tc_bwd": (C.c_int, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P]),
+    "b200rec_hstu_attn_seq_fwd": (C.c_int, [_P, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P]),
+    "b200rec_hstu_attn_seq_bwd": (C.c_int, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P, _P]),
     "b200rec_nce_loss_fwd": (C.c_int, [_P, _L, _I, _P, _P, _P, _P, _L, _P, _I, _I, _P, _P, _I, _I, _I, C.c_uint32,
                                        _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
     "b200rec_nce_count": (C.c_int, [_P, _P, _I, _I, _I, _P, _I, _I, _P, _P]),

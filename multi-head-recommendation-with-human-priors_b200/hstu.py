@@ -360,7 +360,10 @@ class HSTU(nn.Module):
                    epilogue=L.EPI_SILU_DUAL, C2=pre, ldc2=4 * D)
             a = torch.empty((T, D), dtype=torch.float32, device=dev)
             u, v, q, k = actv[:, 0:D], actv[:, D:2 * D], actv[:, 2 * D:3 * D], actv[:, 3 * D:4 * D]
-            if self._tc_attention():
+            if self._tc_attention() and max_len <= 64:
+                L.call("b200rec_hstu_attn_seq_fwd", actv.data_ptr(), 4 * D, seq_off.data_ptr(), key_valid.data_ptr(), B,
+                       T, nh, dh, 1.0 / n_pad, max_len, a.data_ptr(), st)
+            elif self._tc_attention():
                 L.call("b200rec_hstu_attn_tc_fwd", actv.data_ptr(), 4 * D, seq_off.data_ptr(), key_valid.data_ptr(), B,
                        T, nh, dh, 1.0 / n_pad, a.data_ptr(), st)
             else:
@@ -408,7 +411,10 @@ class HSTU(nn.Module):
                    mean2.data_ptr(), rstd2.data_ptr(), T, D, d_pre.data_ptr(), da.data_ptr(), a_dt, drop_p,
                    self.dropout_seed, i, L.ptr(self._rng_step), st)
             sl = lambda t, j: t[:, j * D:(j + 1) * D]
-            if self._tc_attention():
+            if self._tc_attention() and max_len <= 64:
+                L.call("b200rec_hstu_attn_seq_bwd", actv.data_ptr(), pre.data_ptr(), 4 * D, seq_off.data_ptr(),
+                       key_valid.data_ptr(), B, T, nh, dh, 1.0 / n_pad, max_len, da.data_ptr(), d_pre.data_ptr(), st)
+            elif self._tc_attention():
                 L.call("b200rec_hstu_attn_tc_bwd", actv.data_ptr(), pre.data_ptr(), 4 * D, seq_off.data_ptr(),
                        key_valid.data_ptr(), B, T, nh, dh, 1.0 / n_pad, da.data_ptr(), d_pre.data_ptr(), st)
             else:

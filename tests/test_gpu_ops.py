@@ -440,14 +440,25 @@ def test_adamw_rows_dense_equivalent():
 
 # ------------------------------------------------------------------------------------ tcgen05 attention
 @pytest.mark.parametrize("nh,dh,lens", [(2, 64, [50, 33, 50, 2, 64, 65, 1, 0, 128, 7]), (4, 32, [50] * 9 + [17, 3]),
-                                        (1, 64, [400, 150, 390]), (3, 64, [5])], ids=["bf16-a", "bf16-b", "bf16-c", "bf16-d"])
-def test_hstu_attention_tensor_core_fwd_bwd(nh, dh, lens):
+                                        (1, 64, [400, 150, 390]), (3, 64, [5]),
+                                        (2, 64, [50, 33, 50, 2, 64, 1, 0, 16, 17, 48, 49, 100]),
+                                        (4, 32, [50] * 9 + [17, 3, 64, 31, 32, 33])],
+                         ids=["bf16-a", "bf16-b", "bf16-c", "bf16-d", "seq-a", "seq-b"])
+def test_hstu_attention_tensor_core_fwd_bwd(nh, dh, lens, request):
+    """ids bf16-*: tcgen05 kernels (any length); seq-*: the one-CTA-per-(sequence, head) mma.sync kernels for
+    sequences <= 64 tokens (the 100-token sequence of seq-a is an all-padding dummy row)."""
+    seq = request.node.callspec.id.startswith("seq")
+    kind, extra = ("seq", (64,)) if seq else ("tc", ())
     D = nh * dh
     T = sum(lens)
     B = len(lens)
     n_pad = max(lens)
     seq_off = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev())
     key_valid = (torch.rand(T, generator=torch.Generator().manual_seed(90)) < 0.9).to(torch.uint8).to(dev())
+    if seq:
+        for b, n in enumerate(lens):
+            if n > 64:
+                key_valid[int(seq_off[b]):int(seq_off[b + 1])] = 0
     pre = rnd(T, 4 * D, seed=91, scale=0.7).to(torch.bfloat16)
     pre_r = pre.float().clone().requires_grad_(True)
     act_r = torch.nn.functional.silu(pre_r)
@@ -456,8 +467,8 @@ def test_hstu_attention_tensor_core_fwd_bwd(nh, dh, lens):
     act_q = act.float().clone().requires_grad_(True)
     ref = _attn_ref(act_q, seq_off, key_valid, nh, dh, n_pad)
     out = torch.full((T, D), float("nan"), device=dev())
-    L.call("b200rec_hstu_attn_tc_fwd", act.data_ptr(), 4 * D, seq_off.data_ptr(), key_valid.data_ptr(), B, T, nh, dh,
-           1.0 / n_pad, out.data_ptr(), L.stream())
+    L.call(f"b200rec_hstu_attn_{kind}_fwd", act.data_ptr(), 4 * D, seq_off.data_ptr(), key_valid.data_ptr(), B, T, nh, dh,
+           1.0 / n_pad, *extra, out.data_ptr(), L.stream())
     scale = ref.detach().abs().max().item()
     assert (out - ref.detach()).abs().max().item() < 2e-2 * scale + 1e-4
     g = rnd(T, D, seed=92).to(torch.bfloat16)
@@ -466,8 +477,8 @@ def test_hstu_attention_tensor_core_fwd_bwd(nh, dh, lens):
     silu_grad = sg * (1 + pre.float() * (1 - sg))
     want = act_q.grad * silu_grad                      # d_pre = d_act * silu'(pre)
     d_pre = torch.zeros(T, 4 * D, dtype=torch.bfloat16, device=dev())
-    L.call("b200rec_hstu_attn_tc_bwd", act.data_ptr(), pre.data_ptr(), 4 * D, seq_off.data_ptr(), key_valid.data_ptr(),
-           B, T, nh, dh, 1.0 / n_pad, g.data_ptr(), d_pre.data_ptr(), L.stream())
+    L.call(f"b200rec_hstu_attn_{kind}_bwd", act.data_ptr(), pre.data_ptr(), 4 * D, seq_off.data_ptr(), key_valid.data_ptr(),
+           B, T, nh, dh, 1.0 / n_pad, *extra, g.data_ptr(), d_pre.data_ptr(), L.stream())
     assert float(d_pre[:, :D].float().abs().sum()) == 0.0
     for j, name in [(1, "dv"), (2, "dq"), (3, "dk")]:
         a, b = d_pre[:, j * D:(j + 1) * D].float(), want[:, j * D:(j + 1) * D]
