@@ -160,6 +160,12 @@ typedef struct {
   int64_t fold_id_offset; int64_t fold_id_stride;
 } b200rec_gemm_args;
 int b200rec_gemm(const b200rec_gemm_args* args, void* stream);
+/* n_groups independent problems args[0..n_groups).  Problems of identical shape / layout / dtypes with a
+ * plain STORE or ACCUM epilogue (the per-head NCE GEMMs of hstu.py:697, the per-layer weight gradients)
+ * run as ONE persistent tcgen05 launch (16 problems per launch), so that small problems share waves
+ * instead of each paying its own tail; anything else is executed problem by problem.  Outputs must not
+ * alias each other. */
+int b200rec_gemm_grouped(const b200rec_gemm_args* args, int n_groups, void* stream);
 
 /* ------------------------------------------------------------------ HSTU attention (a3,a5)
  * hstu.py:137-160: per head, A = silu(q k^T) / n_pad * [key valid & j <= i], out = A v.

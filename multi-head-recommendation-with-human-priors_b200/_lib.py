@@ -68,6 +68,7 @@ _SIGS = {
     "b200rec_colsum": (C.c_int, [_P, _I, _I, _I, _I, _P, _I, _P, _Z, _P]),
     "b200rec_reduce_sum": (C.c_int, [_P, _L, _F, _P, _I, _P]),
     "b200rec_gemm": (C.c_int, [C.POINTER(GemmArgs), _P]),
+    "b200rec_gemm_grouped": (C.c_int, [C.POINTER(GemmArgs), _I, _P]),
     "b200rec_gemm_force_bn": (None, [_I]),
     "b200rec_gemm_force_ctas": (None, [_I]),
     "b200rec_hstu_attn_fwd": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P]),
@@ -179,6 +180,36 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epilogue=
         gemm_timing.append((e0, e1, 2.0 * M * N * K))
         return
     _check(lib().b200rec_gemm(C.byref(a), stream()), "b200rec_gemm")
+
+
+def gemm_grouped(problems, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epilogue=EPI_STORE, alpha=1.0,
+                 alpha_dev=None):
+    """Same-shape problems [(A, B, C), ...] with non-aliasing outputs in ONE persistent launch (16 per launch):
+    C_g[M,N] = epi(A_g[M,K] @ B_g[N,K]^T), epilogue STORE or ACCUM."""
+    global launches
+    n = len(problems)
+    if n == 0:
+        return
+    arr = (GemmArgs * n)()
+    for a, (A, B, C_out) in zip(arr, problems):
+        a.M, a.N, a.K = M, N, K
+        a.A, a.lda, a.a_major = A.data_ptr(), lda, a_major
+        a.B, a.ldb, a.b_major = B.data_ptr(), ldb, b_major
+        a.in_dtype = dt(A)
+        if dt(B) != a.in_dtype:
+            raise B200RecError("gemm: A and B dtypes differ")
+        a.C, a.ldc, a.c_dtype = C_out.data_ptr(), ldc, dt(C_out)
+        a.c2_dtype = F32
+        a.epilogue, a.alpha, a.alpha_dev = epilogue, alpha, ptr(alpha_dev)
+    launches += (n + 15) // 16 if arr[0].in_dtype == BF16 else n
+    if gemm_timing is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _check(lib().b200rec_gemm_grouped(arr, n, stream()), "b200rec_gemm_grouped")
+        e1.record()
+        gemm_timing.append((e0, e1, 2.0 * M * N * K * n))
+        return
+    _check(lib().b200rec_gemm_grouped(arr, n, stream()), "b200rec_gemm_grouped")
 
 
 def colsum(x, rows, cols, ldx, out, accumulate=False):

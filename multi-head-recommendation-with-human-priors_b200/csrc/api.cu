@@ -26,6 +26,55 @@ int b200rec_device_is_sm100(void) {
 int gemm_simt_launch(const b200rec_gemm_args* a, const EpiParams& ep, cudaStream_t st);
 int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep, cudaStream_t st);
 
+int gemm_tc_launch_grouped(const b200rec_gemm_args* a, int n, const EpiParams& ep, cudaStream_t st);
+
+static bool gemm_groupable(const b200rec_gemm_args* a, int n) {
+  const b200rec_gemm_args& f = a[0];
+  if (f.in_dtype != B200REC_BF16 || (f.epilogue != B200REC_EPI_STORE && f.epilogue != B200REC_EPI_ACCUM)) return false;
+  if (f.bias || f.resid || f.n_split != 0 || f.C2 != nullptr) return false;
+  for (int g = 0; g < n; ++g) {
+    const b200rec_gemm_args& x = a[g];
+    if (x.M != f.M || x.N != f.N || x.K != f.K || x.a_major != f.a_major || x.b_major != f.b_major ||
+        x.in_dtype != f.in_dtype || x.c_dtype != f.c_dtype || x.epilogue != f.epilogue || x.ldc != f.ldc ||
+        x.alpha != f.alpha || x.alpha_dev != f.alpha_dev || x.bias || x.resid || x.n_split != 0 || x.C2 != nullptr)
+      return false;
+    uintptr_t al = x.c_dtype == B200REC_F32 ? 16 : 8;
+    if (((uintptr_t)x.C % al) != 0 || ((uintptr_t)x.A & 15) != 0 || ((uintptr_t)x.B & 15) != 0 || x.lda % 8 != 0 ||
+        x.ldb % 8 != 0 || x.C == nullptr)
+      return false;
+  }
+  return true;
+}
+
+int b200rec_gemm_grouped(const b200rec_gemm_args* a, int n_groups, void* stream) {
+  B200_CHECK_ARG(a != nullptr && n_groups >= 0, "gemm_grouped: bad args");
+  int done = 0;
+  while (done < n_groups) {
+    const int n = n_groups - done < 16 ? n_groups - done : 16;
+    const b200rec_gemm_args* f = a + done;
+    if (n >= 2 && f->M > 0 && f->N > 0 && f->K > 0 && gemm_groupable(f, n)) {
+      EpiParams ep;
+      memset(&ep, 0, sizeof(ep));
+      ep.C = f->C; ep.ldc = f->ldc; ep.c_dtype = f->c_dtype;
+      ep.mode = f->epilogue; ep.alpha = f->alpha; ep.alpha_dev = f->alpha_dev;
+      ep.M = f->M; ep.N = f->N;
+      ep.vec_ok = (f->ldc % 4) == 0;
+      ep.fold_id_stride = 1;
+      if (f->epilogue == B200REC_EPI_ACCUM) B200_CHECK_ARG(f->c_dtype == B200REC_F32, "gemm: ACCUM needs fp32 C");
+      int rc = gemm_tc_launch_grouped(f, n, ep, (cudaStream_t)stream);
+      if (rc) return rc;
+    } else {
+      // heterogeneous / fp32-verification / fused-epilogue problems: same results, one launch each
+      for (int g = 0; g < n; ++g) {
+        int rc = b200rec_gemm(f + g, stream);
+        if (rc) return rc;
+      }
+    }
+    done += n;
+  }
+  return 0;
+}
+
 int b200rec_gemm(const b200rec_gemm_args* a, void* stream) {
   B200_CHECK_ARG(a != nullptr, "gemm: null args");
   B200_CHECK_ARG(a->M >= 0 && a->N >= 0 && a->K > 0, "gemm: bad shape %d %d %d", a->M, a->N, a->K);

@@ -6,6 +6,8 @@
 // Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..9 = epilogue (two warps per TMEM lane
 // quarter).  Epilogue = TMEM -> registers (lane = row) -> swizzled smem transpose -> lanes along the row
 // -> fused math + fully coalesced 16-byte global accesses (8 lanes cover 128 contiguous bytes).
+#include <string.h>
+
 #include <mutex>
 #include <unordered_map>
 
@@ -28,15 +30,24 @@ struct TcParams {
   int num_m, num_n;
   int split_k, kb_per_split;      // split-K: work item = (tile, k-range); partial tiles go to a workspace
   int64_t split_stride;           // elements between consecutive partial outputs
+  int groups;                     // grouped launch: `groups` independent problems of identical shape
+};
+
+// Grouped launch (one persistent kernel over several same-shape problems, so that small problems share
+// waves instead of each paying its own tail): per-group operand maps and output pointers, by value.
+#define TC_MAX_GROUPS 16
+struct TcGroupArgs {
+  CUtensorMap a[TC_MAX_GROUPS];
+  CUtensorMap b[TC_MAX_GROUPS];
+  void* C[TC_MAX_GROUPS];
 };
 
 // CTAS = 1: one CTA per 128 x BN tile.  CTAS = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN
 // tile: each CTA stages its own 128 A rows and HALF of the B tile, so per-CTA shared-memory and L2 operand
 // traffic per flop drop by a third and the epilogue's transpose traffic fits beside the mainloop.
 template <int MODE, int CTAS>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const TcParams p, const EpiParams ep_in) {
+__device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CUtensorMap* maps_b, const TcParams& p,
+                                             const EpiParams& ep_in, void* const* group_C) {
   EpiParams ep = ep_in;
   if (ep.alpha_dev && (ep.mode == B200REC_EPI_STORE || ep.mode == B200REC_EPI_ACCUM)) ep.alpha *= *ep.alpha_dev;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -57,8 +68,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t epi_stage_base = bar_base + 256u;  // TC_EPI_WARPS x 4 KB transpose buffers
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a);
-    tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(maps_a);
+    tma_prefetch_desc(maps_b);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -80,7 +91,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int num_tiles = p.num_m * p.num_n;             // p.num_m counts (128*CTAS)-row tiles
+  const int tiles_pg = p.num_m * p.num_n;              // p.num_m counts (128*CTAS)-row tiles
+  const int num_tiles = tiles_pg * p.groups;
   const int num_k = (p.K + TC_BK - 1) / TC_BK;
   const int tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
   const int num_items = num_tiles * p.split_k;
@@ -91,7 +103,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int s = 0;
       uint32_t ph = 0;
       for (int item = tile0; item < num_items; item += tile_step) {
-        const int tile = item % num_tiles, split = item / num_tiles;
+        const int gtile = item % num_tiles, split = item / num_tiles;
+        const int grp = gtile / tiles_pg, tile = gtile - grp * tiles_pg;
+        const CUtensorMap* map_a = maps_a + grp;
+        const CUtensorMap* map_b = maps_b + grp;
         const int m0 = (tile % p.num_m) * (TC_BM * CTAS) + (int)rank * TC_BM;
         const int n0 = (tile / p.num_m) * p.BN + (int)rank * bn_cta;
         const int kb_beg = split * p.kb_per_split, kb_end = min(num_k, kb_beg + p.kb_per_split);
@@ -107,16 +122,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (CTAS == 2) tma_load_2d_2sm(dst, mp, fb, c0, c1); else tma_load_2d(dst, mp, fb, c0, c1);
           };
           if (!p.a_mn) {
-            load(sa, &map_a, k0, m0);                      // box {64 k, 128 m}
+            load(sa, map_a, k0, m0);                       // box {64 k, 128 m}
           } else {
             for (int j = 0; j < TC_BM / 64; ++j)          // boxes {64 m, 64 k}
-              load(sa + j * 8192u, &map_a, m0 + 64 * j, k0);
+              load(sa + j * 8192u, map_a, m0 + 64 * j, k0);
           }
           if (!p.b_mn) {
-            load(sb, &map_b, k0, n0);                      // box {64 k, BN/CTAS n}
+            load(sb, map_b, k0, n0);                       // box {64 k, BN/CTAS n}
           } else {
             for (int j = 0; j < bn_cta / 64; ++j)
-              load(sb + j * 8192u, &map_b, n0 + 64 * j, k0);
+              load(sb + j * 8192u, map_b, n0 + 64 * j, k0);
           }
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
@@ -173,9 +188,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint32_t acc_ph = 0;
     const EpiParams ep_base = ep;
     for (int item = tile0; item < num_items; item += tile_step) {
-      const int tile = item % num_tiles, split = item / num_tiles;
+      const int gtile = item % num_tiles, split = item / num_tiles;
+      const int grp = gtile / tiles_pg, tile = gtile - grp * tiles_pg;
       const int m0 = (tile % p.num_m) * (TC_BM * CTAS) + (int)rank * TC_BM;
       const int n0 = (tile / p.num_m) * p.BN;
+      if (group_C) ep.C = group_C[grp];
       if (p.split_k > 1) ep.C = (float*)ep_base.C + (int64_t)split * p.split_stride;   // partial tile of this k-range
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
@@ -326,6 +343,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
+template <int MODE, int CTAS>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const TcParams p, const EpiParams ep_in) {
+  gemm_tc_body<MODE, CTAS>(&map_a, &map_b, p, ep_in, nullptr);
+}
+
+template <int MODE, int CTAS>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_grouped_kernel(const __grid_constant__ TcGroupArgs ga, const TcParams p, const EpiParams ep_in) {
+  gemm_tc_body<MODE, CTAS>(ga.a, ga.b, p, ep_in, ga.C);
+}
+
 // sums the split-K partial outputs in ascending split order (deterministic)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int split_k, int64_t stride,
                                                             int64_t n4, float* __restrict__ out, float alpha,
@@ -432,6 +462,7 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep_in, cudaStrea
   }
   if (g_force_bn == 128 || g_force_bn == 256) p.BN = g_force_bn;
   p.split_k = 1;
+  p.groups = 1;
   const int num_k_host = ceil_div_i(a->K, TC_BK);
   if (a->splitk_ws != nullptr && ep_in.mode == B200REC_EPI_STORE && a->c_dtype == B200REC_F32 && a->n_split == 0 &&
       g_force_bn == 0 && a->N > 128) {
@@ -506,6 +537,83 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep_in, cudaStrea
     const int64_t n4 = (int64_t)a->M * a->ldc / 4;
     splitk_reduce_kernel<<<(int)std::min<int64_t>((n4 + 255) / 256, 148 * 8), 256, 0, st>>>(
         (const float*)a->splitk_ws, p.split_k, p.split_stride, n4, (float*)a->C, ep_in.alpha, ep_in.alpha_dev);
+  }
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+// Grouped launch: n (<= TC_MAX_GROUPS) problems with identical shape / layout / epilogue (STORE or ACCUM, no bias /
+// residual), different A, B, C.  The caller guarantees that the outputs do not alias.
+int gemm_tc_launch_grouped(const b200rec_gemm_args* a, int n, const EpiParams& ep_in, cudaStream_t st) {
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    B200_CUDA_OK(cudaGetDevice(&dev));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_grouped_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_grouped_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_grouped_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_grouped_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  TcParams p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.a_mn = a->a_major; p.b_mn = a->b_major;
+  const int ctas = (a->M > TC_BM && g_force_ctas != 1) ? 2 : 1;
+  const int units = num_sms / ctas;
+  p.BN = a->N > 128 ? 256 : 128;
+  if (g_force_bn == 128 || g_force_bn == 256) p.BN = g_force_bn;
+  p.split_k = 1;
+  p.kb_per_split = ceil_div_i(a->K, TC_BK);
+  p.split_stride = 0;
+  p.groups = n;
+  const uint32_t stage_bytes = TC_BM * 128u + (uint32_t)(p.BN / ctas) * 128u;
+  p.stages = (TC_SMEM_LIMIT - 1024 - 256 - TC_STAGE_BYTES) / stage_bytes;
+  if (p.stages > 8) p.stages = 8;
+  p.num_m = ceil_div_i(a->M, TC_BM * ctas);
+  p.num_n = ceil_div_i(a->N, p.BN);
+  TcGroupArgs ga;
+  memset(&ga, 0, sizeof(ga));
+  for (int g = 0; g < n; ++g) {
+    const b200rec_gemm_args* x = a + g;
+    B200_CHECK_ARG(((uintptr_t)x->A & 15) == 0 && ((uintptr_t)x->B & 15) == 0, "gemm_grouped: A/B must be 16-byte aligned");
+    B200_CHECK_ARG(x->lda % 8 == 0 && x->ldb % 8 == 0, "gemm_grouped: lda/ldb must be multiples of 8");
+    if (!p.a_mn) {
+      if (make_map(&ga.a[g], x->A, (uint64_t)x->K, (uint64_t)x->M, (uint64_t)x->lda, 64, TC_BM)) return 1;
+    } else {
+      if (make_map(&ga.a[g], x->A, (uint64_t)x->M, (uint64_t)x->K, (uint64_t)x->lda, 64, 64)) return 1;
+    }
+    if (!p.b_mn) {
+      if (make_map(&ga.b[g], x->B, (uint64_t)x->K, (uint64_t)x->N, (uint64_t)x->ldb, 64, (uint32_t)(p.BN / ctas))) return 1;
+    } else {
+      if (make_map(&ga.b[g], x->B, (uint64_t)x->N, (uint64_t)x->K, (uint64_t)x->ldb, 64, 64)) return 1;
+    }
+    ga.C[g] = x->C;
+  }
+  const int tiles = p.num_m * p.num_n * n;
+  const int grid = (tiles < units ? tiles : units) * ctas;
+  size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256 + TC_STAGE_BYTES;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = ctas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  EpiParams ep = ep_in;
+  if (ep.mode == B200REC_EPI_STORE) {
+    if (ctas == 2) B200_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_grouped_kernel<0, 2>, ga, p, ep));
+    else B200_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_grouped_kernel<0, 1>, ga, p, ep));
+  } else if (ep.mode == B200REC_EPI_ACCUM) {
+    if (ctas == 2) B200_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_grouped_kernel<1, 2>, ga, p, ep));
+    else B200_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_grouped_kernel<1, 1>, ga, p, ep));
+  } else {
+    b200rec_set_error("gemm_grouped: epilogue %d not supported (STORE / ACCUM)", ep.mode);
+    return 1;
   }
   B200_LAUNCH_OK();
   return 0;

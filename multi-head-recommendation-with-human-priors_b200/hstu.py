@@ -388,7 +388,9 @@ class HSTU(nn.Module):
         a_dt = L.dt(act)
         st = L.stream()
         drop_p = self._drop_p_last
-        skws = torch.empty(8 * D * 4 * D, dtype=torch.float32, device=dev) if act != torch.float32 else None
+        # weight gradients are off the critical path: they are collected and run as two grouped launches
+        # (all layers' dW_o, all layers' dW_uvqk) after the chain, where 16 small problems fill the machine
+        dwo_jobs, dwu_jobs = [], []
         for i in reversed(range(self._num_blocks)):
             blk = self._hstu._attention_layers[i]
             x, mean1, rstd1, n, actv, pre, a, mean2, rstd2, oin = saved[i]
@@ -402,7 +404,7 @@ class HSTU(nn.Module):
             L.gemm(dxb, w[f"o{i}"], d_oin, T, D, D, lda=D, ldb=D, b_major=1, ldc=D)
             # dW_o[Dout, Din] = dx^T @ oin  (both operands MN-major, K = T)
             dWo = torch.empty((D, D), dtype=torch.float32, device=dev)
-            L.gemm(dxb, oin, dWo, D, D, T, lda=D, a_major=1, ldb=D, b_major=1, ldc=D, splitk_ws=skws)
+            dwo_jobs.append((dxb, oin, dWo))
             dbo = torch.empty(D, dtype=torch.float32, device=dev)
             L.colsum(dx, T, D, D, dbo)
             d_pre = torch.empty((T, 4 * D), dtype=act, device=dev)
@@ -424,7 +426,7 @@ class HSTU(nn.Module):
                    sl(d_pre, 2).data_ptr(), sl(d_pre, 3).data_ptr(), sl(d_pre, 1).data_ptr(), st)
             # dW_uvqk[D, 4D] = n^T @ d_pre  (both MN-major, K = T)
             dWu = torch.empty((D, 4 * D), dtype=torch.float32, device=dev)
-            L.gemm(n, d_pre, dWu, D, 4 * D, T, lda=D, a_major=1, ldb=4 * D, b_major=1, ldc=4 * D, splitk_ws=skws)
+            dwu_jobs.append((n, d_pre, dWu))
             # dn = d_pre @ W_uvqk^T  (W [D, 4D] = [N, K] -> K-major B)
             dn = torch.empty((T, D), dtype=act, device=dev)
             L.gemm(d_pre, w[f"uvqk{i}"], dn, T, D, 4 * D, lda=4 * D, ldb=4 * D, ldc=D)
@@ -436,6 +438,8 @@ class HSTU(nn.Module):
             grads[blk._o.bias] = dbo
             dx = dx_prev
             saved[i] = None
+        L.gemm_grouped(dwo_jobs, D, D, T, lda=D, a_major=1, ldb=D, b_major=1, ldc=D)
+        L.gemm_grouped(dwu_jobs, D, 4 * D, T, lda=D, a_major=1, ldb=4 * D, b_major=1, ldc=4 * D)
         return dx
 
     # ------------------------------------------------------------------ heads (hstu.py:652-667)
@@ -554,11 +558,14 @@ class HSTU(nn.Module):
         scale = self.logit_scale.data.to(torch.float32)
         job_out = []
         pos_ws = torch.empty(T * P, dtype=torch.float32, device=dev)
-        for j in self._jobs:
-            hq = j.head if self.medusa_num_layers > 0 else 0
-            q_h = qhat.view(T, Hx * D)[:, hq * D:(hq + 1) * D]
-            logits = torch.empty((T, ld_neg), dtype=torch.float32, device=dev)
-            L.gemm(q_h, nhat[j.nset], logits, T, n_neg, D, lda=Hx * D, ldb=D, ldc=ld_neg)
+        # all (head, negative set) logit GEMMs in one persistent launch (hstu.py:697: one matmul per head)
+        qv = qhat.view(T, Hx * D)
+        hqs = [j.head if self.medusa_num_layers > 0 else 0 for j in self._jobs]
+        all_logits = [torch.empty((T, ld_neg), dtype=torch.float32, device=dev) for _ in self._jobs]
+        L.gemm_grouped([(qv[:, hq * D:(hq + 1) * D], nhat[j.nset], lg) for j, hq, lg in zip(self._jobs, hqs, all_logits)],
+                       T, n_neg, D, lda=Hx * D, ldb=D, ldc=ld_neg)
+        for j, hq, logits in zip(self._jobs, hqs, all_logits):
+            q_h = qv[:, hq * D:(hq + 1) * D]
             lossv = torch.empty((T, P), dtype=torch.float32, device=dev)
             g0 = torch.empty((T, P), dtype=torch.float32, device=dev)
             dsc = torch.empty((T, P), dtype=torch.float32, device=dev)
@@ -574,7 +581,7 @@ class HSTU(nn.Module):
             per_p = torch.empty(P, dtype=torch.float32, device=dev)
             L.colsum(lossv, T, P, P, per_p)
             job_out.append(dict(job=j, per_p=per_p, g0=g0, dsc=dsc, rank0=rank0, nval=nval, G=G, hq=hq))
-            del logits
+        del all_logits
         # ---- total loss + logging scalars (tiny [P] vectors)
         half = 0.5 if (self.loss == "prior" and self.head_interaction == "additive") else 1.0   # hstu.py:870
         total = torch.zeros((), dtype=torch.float32, device=dev)
@@ -639,26 +646,41 @@ class HSTU(nn.Module):
         dqhat = torch.zeros((T, Hx * D), dtype=torch.float32, device=dev)
         dthat = torch.zeros((B * LP, D), dtype=torch.float32, device=dev)
         dnhat = {}
-        written = set()
         dscale_sum = torch.zeros((), dtype=torch.float32, device=dev)
-        for o in ctx["job_out"]:
-            j, G, g0, hq = o["job"], o["G"], o["g0"], o["hq"]
+        outs = ctx["job_out"]
+
+        def rounds(keys):
+            """Jobs with the same output accumulate in job order; jobs of one round have distinct outputs."""
+            rs = []
+            for idx, k in enumerate(keys):
+                for r in rs:
+                    if k not in r:
+                        r[k] = idx
+                        break
+                else:
+                    rs.append({k: idx})
+            return [list(r.values()) for r in rs]
+
+        # dq_hat = G @ nhat   (nhat [n_neg, D] = [K, N] -> MN-major B): one grouped launch per round
+        for r, idxs in enumerate(rounds([o["hq"] for o in outs])):
+            L.gemm_grouped([(outs[i]["G"], ctx["nhat"][outs[i]["job"].nset], dqhat[:, outs[i]["hq"] * D:(outs[i]["hq"] + 1) * D])
+                            for i in idxs], T, D, n_neg, lda=ld_neg, ldb=D, b_major=1, ldc=Hx * D,
+                           epilogue=L.EPI_STORE if r == 0 else L.EPI_ACCUM, alpha_dev=gscale)
+        # dn_hat += G^T @ q_hat   (both MN-major, K = T)
+        for o in outs:
+            if o["job"].nset not in dnhat:
+                dnhat[o["job"].nset] = torch.empty((n_neg, D), dtype=torch.float32, device=dev)
+        for r, idxs in enumerate(rounds([o["job"].nset for o in outs])):
+            L.gemm_grouped([(outs[i]["G"], qhat2[:, outs[i]["hq"] * D:(outs[i]["hq"] + 1) * D], dnhat[outs[i]["job"].nset])
+                            for i in idxs], n_neg, D, T, lda=ld_neg, a_major=1, ldb=Hx * D, b_major=1, ldc=D,
+                           epilogue=L.EPI_STORE if r == 0 else L.EPI_ACCUM, alpha_dev=gscale)
+        for o in outs:
+            j, g0, hq = o["job"], o["g0"], o["hq"]
             q_h = qhat2[:, hq * D:(hq + 1) * D]
             dq_h = dqhat[:, hq * D:(hq + 1) * D]
-            nh_ = ctx["nhat"][j.nset]
-            # dq_hat = G @ nhat   (nhat [n_neg, D] = [K, N] -> MN-major B)
-            L.gemm(G, nh_, dq_h, T, D, n_neg, lda=ld_neg, ldb=D, b_major=1, ldc=Hx * D,
-                   epilogue=L.EPI_ACCUM if hq in written else L.EPI_STORE, alpha_dev=gscale)
-            written.add(hq)
             L.call("b200rec_nce_pos_bwd_q", g0.data_ptr(), ctx["that"].data_ptr(), a_dt, D, ctx["tok_b"].data_ptr(),
                    ctx["tok_pos"].data_ptr(), T, LP, P, ctx["scale"].data_ptr(), gscale.data_ptr(), dq_h.data_ptr(),
                    Hx * D, st)
-            # dn_hat += G^T @ q_hat   (both MN-major, K = T)
-            first = j.nset not in dnhat
-            if first:
-                dnhat[j.nset] = torch.empty((n_neg, D), dtype=torch.float32, device=dev)
-            L.gemm(G, q_h, dnhat[j.nset], n_neg, D, T, lda=ld_neg, a_major=1, ldb=Hx * D, b_major=1, ldc=D,
-                   epilogue=L.EPI_STORE if first else L.EPI_ACCUM, alpha_dev=gscale)
             L.call("b200rec_nce_pos_bwd_t", g0.data_ptr(), q_h.data_ptr(), Hx * D, a_dt, D,
                    ctx["tok_index"].data_ptr(), B, LP, P, ctx["scale"].data_ptr(), gscale.data_ptr(),
                    dthat.data_ptr(), st)

@@ -5,7 +5,7 @@ import torch
 from b200rec import _lib as L
 
 dev = torch.device("cuda:0")
-T, D, NN, H = 6400, 1024, 8192, 12
+T, D, NN, H = int(os.environ.get("T", "5248")), 1024, 8192, 12
 bf = torch.bfloat16
 cases = [
     # name, M, N, K, a_major, b_major, epilogue, c dtype
@@ -46,6 +46,8 @@ for name, M, N, K, am, bm, epi, cdt in [c + () for c in cases for _ in configs]:
     kw = dict(lda=A.shape[1], ldb=B.shape[1], ldc=ldc, a_major=am, b_major=bm, epilogue=epi, alpha=0.99 if epi == L.EPI_GT_BITS else 1.0)
     if C2 is not None:
         kw.update(C2=C2, ldc2=N)
+    if name.startswith("dWo") or name.startswith("dWuvqk"):
+        kw.update(splitk_ws=torch.empty(8 * M * N, device=dev))
     if resid is not None:
         kw.update(bias=bias, resid=resid, ldr=resid.shape[1], n_split=D if epi == L.EPI_RESBLOCK else 0)
     for _ in range(2):

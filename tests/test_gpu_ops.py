@@ -534,3 +534,38 @@ def test_gemm_split_k_weight_gradient_shape():
     ref = 0.5 * _gemm_ref(A, B, 1, 1)
     assert (outs[0] - ref).abs().max().item() / ref.abs().max().item() < 2e-3
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("am,bm,epi", [(0, 0, "store"), (1, 1, "store"), (0, 1, "accum")], ids=["kk", "mnmn", "kmn-accum"])
+def test_gemm_grouped_matches_single_launches(am, bm, epi):
+    """b200rec_gemm_grouped: 5 same-shape problems in one persistent launch == 5 single launches (bit-exact:
+    same tiles, same k order), including ragged edges and a device-side alpha."""
+    M, N, K, G = 704, 520, 328, 5
+    alpha_dev = torch.tensor([0.5], device=dev())
+    mode = L.EPI_STORE if epi == "store" else L.EPI_ACCUM
+    probs, single = [], []
+    for g in range(G):
+        A, B = _mk_operands(M, N, K, am, bm, torch.bfloat16, seed=200 + g)
+        base = rnd(M, N, seed=300 + g)
+        probs.append((A, B, base.clone()))
+        single.append((A, B, base.clone()))
+    kw = dict(lda=probs[0][0].shape[1], ldb=probs[0][1].shape[1], ldc=N, a_major=am, b_major=bm, epilogue=mode,
+              alpha_dev=alpha_dev)
+    L.gemm_grouped(probs, M, N, K, **kw)
+    for A, B, Cm in single:
+        L.gemm(A, B, Cm, M, N, K, **kw)
+    for g in range(G):
+        ref = 0.5 * _gemm_ref(probs[g][0], probs[g][1], am, bm) + (rnd(M, N, seed=300 + g) if epi == "accum" else 0)
+        assert (probs[g][2] - ref).abs().max().item() / ref.abs().max().item() < 5e-3
+        assert torch.equal(probs[g][2], single[g][2])
+
+
+def test_gemm_grouped_fp32_falls_back_to_single_problems():
+    M, N, K = 96, 72, 40
+    probs = []
+    for g in range(3):
+        A, B = _mk_operands(M, N, K, 0, 0, torch.float32, seed=400 + g)
+        probs.append((A, B, torch.empty(M, N, device=dev())))
+    L.gemm_grouped(probs, M, N, K, lda=K, ldb=K, ldc=N)
+    for A, B, Cm in probs:
+        assert torch.allclose(Cm, A @ B.t(), rtol=1e-4, atol=1e-4)
