@@ -82,10 +82,11 @@ int b200rec_rows_to_dense(const int64_t* uniq_ids, const float* uniq_rows, const
  * hstu.py:213-219 F.layer_norm(x,[D],eps) without affine. */
 int b200rec_layernorm_fwd(const float* x, int T, int D, float eps, void* y, int y_dtype,
                           float* mean, float* rstd, void* stream);
-/* dx = LN'(x; dy) (+ residual_grad if not NULL).  dy in act dtype, leading dimension ldy. */
+/* dx = LN'(x; dy) (+ residual_grad if not NULL).  dy in act dtype, leading dimension ldy.  If dx_act is
+ * not NULL it receives a copy of dx in the dy dtype (the GEMM operand of the next block's backward). */
 int b200rec_layernorm_bwd(const void* dy, int dy_dtype, int ldy, const float* x, const float* mean,
                           const float* rstd, int T, int D, const float* residual_grad, float* dx,
-                          void* stream);
+                          void* dx_act, void* stream);
 /* hstu.py:277 o_input = u * LN(attn): oin = u * LN(a).  u has leading dimension ldu (it is a column
  * slice of the uvqk activation). */
 /* dropout_p > 0 applies F.dropout to oin (hstu.py:281-285) with a stateless Philox4x32-10 keep-mask keyed by
@@ -292,8 +293,10 @@ int b200rec_adamw(float* p, float* m, float* v, const float* g, int64_t n, float
                   float beta2, float eps, float weight_decay, int step, float grad_scale,
                   const float* coef_dev, void* stream);
 int b200rec_adamw_tick(float* coef_dev, float beta1, float beta2, void* stream);
-/* One launch for many dense tensors: table_dev = array of {float* p, m, v; const float* g; int64 n},
- * blocks_dev = int64 pairs {tensor index, first element of a 4096-element chunk}. */
+/* One launch for many dense tensors: table_dev = array of {float* p, m, v; const float* g; bf16* shadow;
+ * int64 n}, blocks_dev = int64 pairs {tensor index, first element of a 4096-element chunk}.  `shadow`
+ * (nullable) receives the updated parameter rounded to bf16 — the GEMM operand of the next step, so the
+ * weights are never re-cast. */
 int b200rec_adamw_multi(const void* table_dev, const int64_t* blocks_dev, int n_blocks, float lr,
                         float beta1, float beta2, float eps, float weight_decay, int step,
                         float grad_scale, const float* coef_dev, void* stream);

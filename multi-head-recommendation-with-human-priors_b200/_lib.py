@@ -58,7 +58,7 @@ _SIGS = {
     "b200rec_scatter_add_sorted": (C.c_int, [_P, _L, _P, _I, _P, _P, _P, _P, _Z, _P]),
     "b200rec_rows_to_dense": (C.c_int, [_P, _P, _P, _L, _I, _P, _I, _P]),
     "b200rec_layernorm_fwd": (C.c_int, [_P, _I, _I, _F, _P, _I, _P, _P, _P]),
-    "b200rec_layernorm_bwd": (C.c_int, [_P, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P]),
+    "b200rec_layernorm_bwd": (C.c_int, [_P, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "b200rec_gate_ln_fwd": (C.c_int, [_P, _I, _P, _I, _I, _F, _P, _I, _P, _P, _F, C.c_uint32, C.c_uint32, _P, _P]),
     "b200rec_gate_ln_bwd": (C.c_int, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _P, _P, _I, _F, C.c_uint32, C.c_uint32, _P,
                                       _P]),

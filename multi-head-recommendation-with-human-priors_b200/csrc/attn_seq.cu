@@ -46,16 +46,26 @@ struct Tile {
   bf16 m[SEQ_MAX][DH + 8];  // +16 bytes per row: the 8 row addresses of an ldmatrix hit 8 different bank groups
 };
 
-// rows [t0, t0+n) x DH columns starting at src -> padded tile; rows >= n are zero
+// rows [t0, t0+n) x DH columns starting at src -> padded tile; rows >= n are zero.  Asynchronous 16-byte
+// copies (LDGSTS): every load of the CTA is in flight before the single wait in load_wait().
 template <int DH>
 __device__ __forceinline__ void load_rows(Tile<DH>& dst, const bf16* __restrict__ src, int64_t ld, int n) {
   constexpr int V = DH / 8;
   for (int idx = threadIdx.x; idx < SEQ_MAX * V; idx += blockDim.x) {
     int r = idx / V, c = idx - r * V;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (r < n) v = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)r * ld + c * 8));
-    *reinterpret_cast<uint4*>(&dst.m[r][c * 8]) = v;
+    if (r < n) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(&dst.m[r][c * 8])),
+                   "l"(src + (int64_t)r * ld + c * 8)
+                   : "memory");
+    } else {
+      *reinterpret_cast<uint4*>(&dst.m[r][c * 8]) = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
+}
+__device__ __forceinline__ void load_wait() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
 }
 
 // acc[nt] (16 x 8 blocks nt = 0..7 over 64 columns) = X[r0.., :] * Y[:, :]^T, both [row][DH] tiles.
@@ -141,7 +151,7 @@ __global__ void __launch_bounds__(128) attn_seq_fwd_kernel(const bf16* __restric
   load_rows<DH>(sq, base + 2 * D, ld, n);
   load_rows<DH>(sk, base + 3 * D, ld, n);
   if (threadIdx.x < SEQ_MAX) kv[threadIdx.x] = threadIdx.x < n ? key_valid[t0 + threadIdx.x] : 0;
-  __syncthreads();
+  load_wait();
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int i0 = 16 * w;
   if (i0 >= n) return;
@@ -214,7 +224,7 @@ __global__ void __launch_bounds__(128) attn_seq_bwd_kernel(const bf16* __restric
   load_rows<DH>(sk, act + row0 + 3 * D, ld, n);
   load_rows<DH>(sd, d_out + (int64_t)t0 * D + h * DH, D, n);
   if (threadIdx.x < SEQ_MAX) kv[threadIdx.x] = threadIdx.x < n ? key_valid[t0 + threadIdx.x] : 0;
-  __syncthreads();
+  load_wait();
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int r0 = 16 * w;
   if (r0 >= n) return;

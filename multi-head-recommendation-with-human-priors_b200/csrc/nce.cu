@@ -268,6 +268,12 @@ __global__ void __launch_bounds__(256) nce_pos_kernel(const TA* __restrict__ q_h
 
 #define NCE_RV 8  // float4 vectors per thread -> up to 8192 negatives per row
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <typename TA>
 __global__ void __launch_bounds__(256, 4)
 nce_loss_fwd_reg_kernel(const float* __restrict__ logits, int64_t ld_logits, int n_neg,
@@ -280,14 +286,14 @@ nce_loss_fwd_reg_kernel(const float* __restrict__ logits, int64_t ld_logits, int
   __shared__ Stats red_stats[8];
   __shared__ float s_pos[NCE_MAXP], s_lse[NCE_MAXP], s_coef[NCE_MAXP];
   __shared__ int s_valid[NCE_MAXP], s_masked[NCE_MAXP];
-  __shared__ int s_any;
+  __shared__ int s_any, s_anym;
   const int t = blockIdx.x;
   const int tid = threadIdx.x;
   const int64_t r0 = (int64_t)tok_b[t] * LP + tok_pos[t] + 1;
   const float tau = __expf(fminf(fmaxf(*logit_scale, 0.f), 4.605170185988092f));
   const int n_words = (n_neg + 31) >> 5;
   const int n_vec = n_neg >> 2;
-  if (tid == 0) s_any = 0;
+  if (tid == 0) { s_any = 0; s_anym = 0; }
   __syncthreads();
   if (tid < NCE_MAXP) {
     int p = tid;
@@ -298,6 +304,7 @@ nce_loss_fwd_reg_kernel(const float* __restrict__ logits, int64_t ld_logits, int
     s_masked[p] = (ok && row_any[r0 + p]) ? 1 : 0;
     s_coef[p] = p < P ? coef[p] : 0.f;
     if (ok) s_any = 1;
+    if (s_masked[p]) s_anym = 1;
   }
   __syncthreads();
   if (!s_any) {
@@ -317,8 +324,9 @@ nce_loss_fwd_reg_kernel(const float* __restrict__ logits, int64_t ld_logits, int
   // the row: thread owns vectors tid, tid+256, ...   z2 = tau * log2(e) * cos  (exp(z - m) == exp2(z2 - m2))
   const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   const float tau2 = tau * LOG2E;
+  const bool lean = !s_anym;   // block-uniform: no offset of this row filters negatives (the common case)
   float z[NCE_RV][4];
-  float m2 = -INFINITY;
+  float mraw = -INFINITY;
   int n_mine = 0;
 #pragma unroll
   for (int k = 0; k < NCE_RV; ++k) {
@@ -326,26 +334,48 @@ nce_loss_fwd_reg_kernel(const float* __restrict__ logits, int64_t ld_logits, int
     if (v < n_vec) {
       load4<float>(logits + (int64_t)t * ld_logits + v * 4, z[k]);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        z[k][e] *= tau2;
-        m2 = fmaxf(m2, z[k][e]);
-      }
+      for (int e = 0; e < 4; ++e) mraw = fmaxf(mraw, z[k][e]);
       n_mine += 4;
     }
   }
+  const float m2 = mraw * tau2;            // tau2 > 0: max commutes with the scaling
   const float pos0_2 = s_valid[0] ? s_pos[0] * LOG2E : INFINITY;
   Stats loc;   // in the log2 domain: m = max z2, s = sum 2^(z2-m), w = sum 2^(z2-m) * z2
   loc.m = m2; loc.s = 0.f; loc.w = 0.f; loc.gt = 0; loc.cnt = n_mine;
+  if (lean) {
+    // ~9 instructions per logit: the register row is overwritten by 2^(z2 - m2), which is all the
+    // gradient pass needs (g_j = const * 2^(z2_j - m2))
+    const float thr = s_valid[0] ? s_pos[0] * LOG2E / tau2 : INFINITY;   // rank threshold on the raw cosine
+    float wraw = 0.f;
 #pragma unroll
-  for (int k = 0; k < NCE_RV; ++k) {
-    int v = tid + k * 256;
-    if (v < n_vec) {
+    for (int k = 0; k < NCE_RV; ++k) {
+      int v = tid + k * 256;
+      if (v < n_vec) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float ex = exp2f(z[k][e] - m2);
-        loc.s += ex;
-        loc.w = fmaf(ex, z[k][e], loc.w);
-        loc.gt += z[k][e] > pos0_2;
+        for (int e = 0; e < 4; ++e) {
+          const float raw = z[k][e];
+          const float ex = ex2_approx(fmaf(raw, tau2, -m2));
+          loc.s += ex;
+          wraw = fmaf(ex, raw, wraw);
+          loc.gt += raw > thr;
+          z[k][e] = ex;
+        }
+      }
+    }
+    loc.w = wraw * tau2;
+  } else {
+#pragma unroll
+    for (int k = 0; k < NCE_RV; ++k) {
+      int v = tid + k * 256;
+      if (v < n_vec) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          z[k][e] *= tau2;
+          float ex = exp2f(z[k][e] - m2);
+          loc.s += ex;
+          loc.w = fmaf(ex, z[k][e], loc.w);
+          loc.gt += z[k][e] > pos0_2;
+        }
       }
     }
   }
@@ -353,7 +383,7 @@ nce_loss_fwd_reg_kernel(const float* __restrict__ logits, int64_t ld_logits, int
 
   // exact pass for offsets whose target filters some negatives (rare): block-wide, one offset at a time
   __shared__ Stats s_st[NCE_MAXP];
-  for (int p = 0; p < P; ++p) {
+  for (int p = 0; p < P && !lean; ++p) {
     if (!(s_valid[p] && s_masked[p])) continue;   // block-uniform
     const uint32_t* bits = same_bits + (r0 + p) * n_words;
     const float posp_2 = s_pos[p] * LOG2E;
@@ -430,6 +460,20 @@ nce_loss_fwd_reg_kernel(const float* __restrict__ logits, int64_t ld_logits, int
     any_masked |= (s_valid[p] && s_masked[p]);
   }
   a_common *= tau;
+  if (lean) {
+    const float f = a_common * ex2_approx(m2 - all.m);   // per-thread rescale from the local to the row maximum
+#pragma unroll
+    for (int k = 0; k < NCE_RV; ++k) {
+      int v = tid + k * 256;
+      if (v < n_vec) {
+        float g[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) g[e] = f * z[k][e];
+        store4<TA>(G + (int64_t)t * ldg + v * 4, g);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < NCE_RV; ++k) {
     int v = tid + k * 256;

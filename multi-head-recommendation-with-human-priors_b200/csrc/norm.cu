@@ -2,10 +2,12 @@
 // is held in registers between the statistics pass and the write (single HBM read of each input).
 #include "common.cuh"
 
-#define ROWS_PER_BLOCK 8  // 256 threads
+// one warp per row; small blocks so that ~5 blocks (20 rows) are resident per SM and the last wave is short
+#define ROWS_PER_BLOCK 4
+#define ROW_THREADS (32 * ROWS_PER_BLOCK)
 
 template <typename TY, int MAXV>
-__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, int T, int D4, float eps,
+__global__ void __launch_bounds__(ROW_THREADS) layernorm_fwd_kernel(const float* __restrict__ x, int T, int D4, float eps,
                                                             TY* __restrict__ y, float* __restrict__ mean,
                                                             float* __restrict__ rstd) {
   int lane = threadIdx.x & 31;
@@ -59,22 +61,23 @@ int b200rec_layernorm_fwd(const float* x, int T, int D, float eps, void* y, int 
   int blocks = ceil_div_i(T, ROWS_PER_BLOCK);
   DISPATCH_ACT(y_dtype, TY, {
     if (D <= 512)
-      layernorm_fwd_kernel<TY, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, T, D / 4, eps, (TY*)y, mean, rstd);
+      layernorm_fwd_kernel<TY, 4><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>(x, T, D / 4, eps, (TY*)y, mean, rstd);
     else if (D <= 1024)
-      layernorm_fwd_kernel<TY, 8><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, T, D / 4, eps, (TY*)y, mean, rstd);
+      layernorm_fwd_kernel<TY, 8><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>(x, T, D / 4, eps, (TY*)y, mean, rstd);
     else
-      layernorm_fwd_kernel<TY, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, T, D / 4, eps, (TY*)y, mean, rstd);
+      layernorm_fwd_kernel<TY, 16><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>(x, T, D / 4, eps, (TY*)y, mean, rstd);
   });
   B200_LAUNCH_OK();
   return 0;
 }
 
 template <typename TG, int MAXV>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TG* __restrict__ dy, int64_t ldy,
+__global__ void __launch_bounds__(ROW_THREADS) layernorm_bwd_kernel(const TG* __restrict__ dy, int64_t ldy,
                                                             const float* __restrict__ x,
                                                             const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, int T, int D4,
-                                                            const float* __restrict__ resid, float* __restrict__ dx) {
+                                                            const float* __restrict__ resid, float* __restrict__ dx,
+                                                            TG* __restrict__ dx_act) {
   int lane = threadIdx.x & 31;
   int r = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= T) return;
@@ -110,25 +113,26 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TG* __restrict
         o[k] = resid ? o[k] + d : d;
       }
       store4<float>(dx + ((int64_t)r * D4 + c) * 4, o);
+      if (dx_act) store4<TG>(dx_act + ((int64_t)r * D4 + c) * 4, o);
     }
   }
 }
 
 int b200rec_layernorm_bwd(const void* dy, int dy_dtype, int ldy, const float* x, const float* mean, const float* rstd,
-                          int T, int D, const float* residual_grad, float* dx, void* stream) {
+                          int T, int D, const float* residual_grad, float* dx, void* dx_act, void* stream) {
   B200_CHECK_ARG(D % 4 == 0 && D <= 2048 && ldy % 4 == 0, "layernorm_bwd: bad D=%d ldy=%d", D, ldy);
   if (T == 0) return 0;
   int blocks = ceil_div_i(T, ROWS_PER_BLOCK);
   DISPATCH_ACT(dy_dtype, TG, {
     if (D <= 512)
-      layernorm_bwd_kernel<TG, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TG*)dy, ldy, x, mean, rstd, T,
-                                                                            D / 4, residual_grad, dx);
+      layernorm_bwd_kernel<TG, 4><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>((const TG*)dy, ldy, x, mean, rstd, T,
+                                                                            D / 4, residual_grad, dx, (TG*)dx_act);
     else if (D <= 1024)
-      layernorm_bwd_kernel<TG, 8><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TG*)dy, ldy, x, mean, rstd, T,
-                                                                            D / 4, residual_grad, dx);
+      layernorm_bwd_kernel<TG, 8><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>((const TG*)dy, ldy, x, mean, rstd, T,
+                                                                            D / 4, residual_grad, dx, (TG*)dx_act);
     else
-      layernorm_bwd_kernel<TG, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TG*)dy, ldy, x, mean, rstd, T,
-                                                                            D / 4, residual_grad, dx);
+      layernorm_bwd_kernel<TG, 16><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>((const TG*)dy, ldy, x, mean, rstd, T,
+                                                                            D / 4, residual_grad, dx, (TG*)dx_act);
   });
   B200_LAUNCH_OK();
   return 0;
@@ -136,7 +140,7 @@ int b200rec_layernorm_bwd(const void* dy, int dy_dtype, int ldy, const float* x,
 
 // ---------------------------------------------------------------- gate: oin = u * LN(a)
 template <typename TA, int MAXV>
-__global__ void __launch_bounds__(256) gate_ln_fwd_kernel(const TA* __restrict__ u, int64_t ldu,
+__global__ void __launch_bounds__(ROW_THREADS) gate_ln_fwd_kernel(const TA* __restrict__ u, int64_t ldu,
                                                           const float* __restrict__ a, int T, int D4, float eps,
                                                           TA* __restrict__ oin, float* __restrict__ mean,
                                                           float* __restrict__ rstd, DropCfg drop) {
@@ -196,13 +200,13 @@ int b200rec_gate_ln_fwd(const void* u, int ldu, const float* a, int T, int D, fl
   int blocks = ceil_div_i(T, ROWS_PER_BLOCK);
   DISPATCH_ACT(act_dtype, TA, {
     if (D <= 512)
-      gate_ln_fwd_kernel<TA, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TA*)u, ldu, a, T, D / 4, eps,
+      gate_ln_fwd_kernel<TA, 4><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>((const TA*)u, ldu, a, T, D / 4, eps,
                                                                           (TA*)oin, mean, rstd, drop);
     else if (D <= 1024)
-      gate_ln_fwd_kernel<TA, 8><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TA*)u, ldu, a, T, D / 4, eps,
+      gate_ln_fwd_kernel<TA, 8><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>((const TA*)u, ldu, a, T, D / 4, eps,
                                                                           (TA*)oin, mean, rstd, drop);
     else
-      gate_ln_fwd_kernel<TA, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TA*)u, ldu, a, T, D / 4, eps,
+      gate_ln_fwd_kernel<TA, 16><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>((const TA*)u, ldu, a, T, D / 4, eps,
                                                                           (TA*)oin, mean, rstd, drop);
   });
   B200_LAUNCH_OK();
@@ -210,7 +214,7 @@ int b200rec_gate_ln_fwd(const void* u, int ldu, const float* a, int T, int D, fl
 }
 
 template <typename TA, int MAXV>
-__global__ void __launch_bounds__(256) gate_ln_bwd_kernel(const TA* __restrict__ d_oin, const TA* __restrict__ u,
+__global__ void __launch_bounds__(ROW_THREADS) gate_ln_bwd_kernel(const TA* __restrict__ d_oin, const TA* __restrict__ u,
                                                           const TA* __restrict__ pre_u, int64_t ldu,
                                                           const float* __restrict__ a, const float* __restrict__ mean,
                                                           const float* __restrict__ rstd, int T, int D4,
@@ -267,13 +271,13 @@ int b200rec_gate_ln_bwd(const void* d_oin, const void* u, const void* pre_u, int
   int blocks = ceil_div_i(T, ROWS_PER_BLOCK);
   DISPATCH_ACT(act_dtype, TA, {
     if (D <= 512)
-      gate_ln_bwd_kernel<TA, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      gate_ln_bwd_kernel<TA, 4><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>(
           (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, (TA*)da, drop);
     else if (D <= 1024)
-      gate_ln_bwd_kernel<TA, 8><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      gate_ln_bwd_kernel<TA, 8><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>(
           (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, (TA*)da, drop);
     else
-      gate_ln_bwd_kernel<TA, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      gate_ln_bwd_kernel<TA, 16><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>(
           (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, (TA*)da, drop);
   });
   B200_LAUNCH_OK();

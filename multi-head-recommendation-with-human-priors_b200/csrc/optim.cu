@@ -152,6 +152,7 @@ extern "C" int b200rec_adamw_tick(float* coef_dev, float beta1, float beta2, voi
 struct AdamTensor {
   float *p, *m, *v;
   const float* g;
+  bf16* shadow;   // optional compute-dtype copy of p, refreshed in the same pass (NULL: none)
   int64_t n;
 };
 __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamTensor* __restrict__ table,
@@ -160,7 +161,44 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamTensor* __re
   const AdamTensor t = table[blocks[2 * blockIdx.x]];
   const int64_t beg = blocks[2 * blockIdx.x + 1];
   const int64_t end = min(t.n, beg + 4096);
-  for (int64_t i = beg + threadIdx.x; i < end; i += 256) adam_update(t.p[i], t.m[i], t.v[i], t.g[i], c);
+  const bool vec = ((((uintptr_t)t.p | (uintptr_t)t.m | (uintptr_t)t.v | (uintptr_t)t.g) & 15) == 0) &&
+                   (((uintptr_t)t.shadow & 7) == 0);
+  if (vec) {
+    // 4 x 16-byte vectors per thread and array, every load issued before the first use
+    const int64_t n4 = (end - beg) >> 2;
+    float pp[4][4], mm[4][4], vv[4][4], gg[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t i = threadIdx.x + k * 256;
+      if (i < n4) {
+        load4<float>(t.p + beg + i * 4, pp[k]);
+        load4<float>(t.m + beg + i * 4, mm[k]);
+        load4<float>(t.v + beg + i * 4, vv[k]);
+        load4<float>(t.g + beg + i * 4, gg[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t i = threadIdx.x + k * 256;
+      if (i < n4) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) adam_update(pp[k][e], mm[k][e], vv[k][e], gg[k][e], c);
+        store4<float>(t.p + beg + i * 4, pp[k]);
+        store4<float>(t.m + beg + i * 4, mm[k]);
+        store4<float>(t.v + beg + i * 4, vv[k]);
+        if (t.shadow) store4<bf16>(t.shadow + beg + i * 4, pp[k]);
+      }
+    }
+    for (int64_t i = beg + n4 * 4 + threadIdx.x; i < end; i += 256) {
+      adam_update(t.p[i], t.m[i], t.v[i], t.g[i], c);
+      if (t.shadow) t.shadow[i] = __float2bfloat16_rn(t.p[i]);
+    }
+    return;
+  }
+  for (int64_t i = beg + threadIdx.x; i < end; i += 256) {
+    adam_update(t.p[i], t.m[i], t.v[i], t.g[i], c);
+    if (t.shadow) t.shadow[i] = __float2bfloat16_rn(t.p[i]);
+  }
 }
 
 extern "C" int b200rec_adamw_multi(const void* table_dev, const int64_t* blocks_dev, int n_blocks, float lr,

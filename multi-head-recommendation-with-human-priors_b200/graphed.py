@@ -64,6 +64,9 @@ class GraphedTrainStep(object):
         for t, c in zip(state, snap):
             t.copy_(c)
         self.opt.step_count = step0
+        # the bf16 weight shadows followed the warm-up updates: re-cast them from the restored masters
+        self.model.invalidate_shadows()
+        self.model._cast_weights()
         return g, out, L.launches - n0
 
     def __call__(self, batch, n_tokens):
@@ -76,6 +79,9 @@ class GraphedTrainStep(object):
             entry = self._capture(T_b)
             self.graphs[T_b] = entry
         g, out, n_launch = entry
+        if self.model.shadows_stale():           # parameters changed outside the graph (load_state_dict, ...)
+            self.model.invalidate_shadows()
+            self.model._cast_weights()
         g.replay()
         self.opt.step_count += 1
         L.launches += n_launch
@@ -170,6 +176,9 @@ class GraphedShardedStep(object):
             entry = self._capture(T_b)
             self.graphs[T_b] = entry
         g, out, cache_grad, n_launch = entry
+        if self.model.shadows_stale():
+            self.model.invalidate_shadows()
+            self.model._cast_weights()
         g.replay()
         L.launches += n_launch
         model, W = self.model, self.world

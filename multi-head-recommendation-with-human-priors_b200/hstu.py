@@ -183,6 +183,7 @@ class HSTU(nn.Module):
         self._rng_step = None      # device counter feeding the Philox dropout stream
         self._drop_p_last = 0.0
         self.sharded_table = None  # parallel.ShardedTable once shard_item_table() was called
+        self._shadow_buf, self._shadow_state, self._shadow_view = {}, {}, {}
         self.emb_grad = None       # (uniq_ids, uniq_rows, n_uniq) of the last backward
         self._table_cache = None   # normalised compute-dtype item table for predict
         self._verbose = False
@@ -229,33 +230,68 @@ class HSTU(nn.Module):
         return self.medusa_num_heads if self.medusa_num_layers > 0 else 1
 
     def _cast_weights(self):
-        """Compute-dtype copies of the dense weights for this step (fp32 masters stay in the Parameters)."""
+        """Compute-dtype copies of the dense weights (fp32 masters stay in the Parameters).  The bf16 copies are
+        persistent "shadows": FusedAdamW rewrites them in its update pass, so a weight is only re-cast here when
+        its Parameter changed by other means (load_state_dict, another optimizer, .to()) — detected through the
+        tensor version counter and data pointer."""
         act = self._act()
         D = self._hstu_embedding_dim
         w = {}
-        for i, blk in enumerate(self._hstu._attention_layers):
-            if act == torch.float32:
+        if act == torch.float32:
+            for i, blk in enumerate(self._hstu._attention_layers):
                 w[f"uvqk{i}"], w[f"o{i}"] = blk._uvqk.data, blk._o.weight.data
-            else:
-                u = torch.empty((D, 4 * D), dtype=act, device=blk._uvqk.device)
-                o = torch.empty((D, D), dtype=act, device=blk._uvqk.device)
-                L.call("b200rec_cast", blk._uvqk.data_ptr(), u.numel(), u.data_ptr(), L.dt(u), L.stream())
-                L.call("b200rec_cast", blk._o.weight.data_ptr(), o.numel(), o.data_ptr(), L.dt(o), L.stream())
-                w[f"uvqk{i}"], w[f"o{i}"] = u, o
+        else:
+            for i, blk in enumerate(self._hstu._attention_layers):
+                w[f"uvqk{i}"] = self._shadow_get(blk._uvqk, f"uvqk{i}", (D, 4 * D))
+                w[f"o{i}"] = self._shadow_get(blk._o.weight, f"o{i}", (D, D))
         if self.medusa_num_layers > 0:
             H = self.medusa_num_heads
             dev = self.item_embedding.weight.device
-            wc = torch.empty((H * D, D), dtype=act, device=dev)
+            if act == torch.float32:
+                wc = torch.empty((H * D, D), dtype=act, device=dev)
+                for h in range(H):
+                    wc[h * D:(h + 1) * D].copy_(self.medusa_head[h][0].linear.weight.data)
+            else:
+                for h in range(H):
+                    self._shadow_get(self.medusa_head[h][0].linear.weight, "heads_w", (H * D, D), row0=h * D)
+                wc = self._shadow_buf["heads_w"]
             bc = torch.empty((H * D,), dtype=torch.float32, device=dev)
             for h in range(H):
-                lin = self.medusa_head[h][0].linear
-                if act == torch.float32:
-                    wc[h * D:(h + 1) * D].copy_(lin.weight.data)
-                else:
-                    L.call("b200rec_cast", lin.weight.data_ptr(), D * D, wc[h * D:].data_ptr(), L.dt(wc), L.stream())
-                bc[h * D:(h + 1) * D].copy_(lin.bias.data)
+                bc[h * D:(h + 1) * D].copy_(self.medusa_head[h][0].linear.bias.data)
             w["heads_w"], w["heads_b"] = wc, bc
         return w
+
+    def _shadow_get(self, p, name, shape, row0=0):
+        """bf16 shadow of Parameter p = rows [row0, row0 + p.shape[0]) of the persistent buffer `name`."""
+        buf = self._shadow_buf.get(name)
+        if buf is None or buf.device != p.device or buf.dtype != self._act():
+            buf = torch.empty(shape, dtype=self._act(), device=p.device)
+            self._shadow_buf[name] = buf
+            self._shadow_state = {k: v for k, v in self._shadow_state.items() if v[2] != name}
+        view = buf[row0:row0 + p.shape[0]] if p.dim() == 2 else buf
+        state = (p._version, p.data_ptr(), name)
+        if self._shadow_state.get(p) != state:
+            L.call("b200rec_cast", p.data_ptr(), p.numel(), view.data_ptr(), L.dt(view), L.stream())
+            self._shadow_state[p] = state
+            self._shadow_view[p] = view
+        return view
+
+    def shadow_of(self, p):
+        """The bf16 shadow the optimizer must refresh when it updates p in place (None: p has none)."""
+        st = self._shadow_state.get(p)
+        if st is None or st[:2] != (p._version, p.data_ptr()):
+            self._shadow_state.pop(p, None)      # stale: the next forward re-casts
+            return None
+        return self._shadow_view[p]
+
+    def shadows_stale(self):
+        """True if a shadowed Parameter changed since its shadow was written (a captured graph contains no cast)."""
+        return any(st[:2] != (p._version, p.data_ptr()) for p, st in self._shadow_state.items())
+
+    def invalidate_shadows(self):
+        """Force a re-cast of every weight at the next forward (call after changing parameter memory through
+        raw pointers, e.g. restoring a snapshot with copy_ on .data does this automatically)."""
+        self._shadow_state.clear()
 
     def shard_item_table(self, group=None):
         """Keep only the rows `id % world == rank` of the item table on this rank.  Call after
@@ -391,12 +427,13 @@ class HSTU(nn.Module):
         # weight gradients are off the critical path: they are collected and run as two grouped launches
         # (all layers' dW_o, all layers' dW_uvqk) after the chain, where 16 small problems fill the machine
         dwo_jobs, dwu_jobs = [], []
+        dxb = None   # act-dtype copy of dx: written by the previous block's LayerNorm backward
         for i in reversed(range(self._num_blocks)):
             blk = self._hstu._attention_layers[i]
             x, mean1, rstd1, n, actv, pre, a, mean2, rstd2, oin = saved[i]
             if act == torch.float32:
                 dxb = dx
-            else:
+            elif dxb is None:
                 dxb = torch.empty((T, D), dtype=act, device=dev)
                 L.call("b200rec_cast", dx.data_ptr(), dx.numel(), dxb.data_ptr(), a_dt, st)
             # d_oin = dx @ W_o   (W_o [Dout, Din] = [K, N] -> MN-major B)
@@ -431,8 +468,9 @@ class HSTU(nn.Module):
             dn = torch.empty((T, D), dtype=act, device=dev)
             L.gemm(d_pre, w[f"uvqk{i}"], dn, T, D, 4 * D, lda=4 * D, ldb=4 * D, ldc=D)
             dx_prev = torch.empty((T, D), dtype=torch.float32, device=dev)
+            dxb = torch.empty((T, D), dtype=act, device=dev) if (act != torch.float32 and i > 0) else None
             L.call("b200rec_layernorm_bwd", dn.data_ptr(), a_dt, D, x.data_ptr(), mean1.data_ptr(), rstd1.data_ptr(),
-                   T, D, dx.data_ptr(), dx_prev.data_ptr(), st)
+                   T, D, dx.data_ptr(), dx_prev.data_ptr(), L.ptr(dxb), st)
             grads[blk._uvqk] = dWu
             grads[blk._o.weight] = dWo
             grads[blk._o.bias] = dbo

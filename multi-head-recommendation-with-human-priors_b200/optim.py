@@ -46,12 +46,17 @@ class FusedAdamW(object):
 
     def _dense_table(self, dense):
         """Device pointer table for the multi-tensor kernel; rebuilt only when a pointer changes."""
-        key = tuple((p.data_ptr(), p.grad.data_ptr(), p.numel()) for p in dense)
+        shadow_of = getattr(self.model, "shadow_of", lambda p: None)
+        shadows = [shadow_of(p) for p in dense]
+        key = tuple((p.data_ptr(), p.grad.data_ptr(), p.numel(), 0 if sh is None else sh.data_ptr())
+                    for p, sh in zip(dense, shadows))
         if key != self._table_key:
             recs, blocks = [], []
             for t, p in enumerate(dense):
                 m, v = self._st(p)
-                recs.append(struct.pack("QQQQq", p.data_ptr(), m.data_ptr(), v.data_ptr(), p.grad.data_ptr(), p.numel()))
+                sh = shadows[t]
+                recs.append(struct.pack("QQQQQq", p.data_ptr(), m.data_ptr(), v.data_ptr(), p.grad.data_ptr(),
+                                        0 if sh is None else sh.data_ptr(), p.numel()))
                 for beg in range(0, p.numel(), 4096):
                     blocks += [t, beg]
             dev = dense[0].device

@@ -128,8 +128,15 @@ def test_layernorm_fwd_bwd(T, D):
     ref.backward(dy)
     dx = torch.empty(T, D, device=dev())
     L.call("b200rec_layernorm_bwd", dy.data_ptr(), L.F32, D, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), T, D,
-           res.data_ptr(), dx.data_ptr(), L.stream())
+           res.data_ptr(), dx.data_ptr(), None, L.stream())
     assert torch.allclose(dx, xr.grad + res, rtol=1e-4, atol=1e-5)
+    # bf16 dy: the act-dtype copy of dx is the rounded fp32 result
+    dyb = dy.to(torch.bfloat16)
+    dx2, dx2b = torch.empty(T, D, device=dev()), torch.empty(T, D, dtype=torch.bfloat16, device=dev())
+    L.call("b200rec_layernorm_bwd", dyb.data_ptr(), L.BF16, D, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), T, D,
+           res.data_ptr(), dx2.data_ptr(), dx2b.data_ptr(), L.stream())
+    assert torch.equal(dx2b, dx2.to(torch.bfloat16))
+    assert torch.allclose(dx2, dx, rtol=2e-2, atol=2e-2)
     yb = torch.empty(T, D, dtype=torch.bfloat16, device=dev())
     L.call("b200rec_layernorm_fwd", x.data_ptr(), T, D, 1e-6, yb.data_ptr(), L.BF16, mean.data_ptr(), rstd.data_ptr(),
            L.stream())
