@@ -161,6 +161,10 @@ def cpu_reference_run(cfg, batch_size, steps, warmup=1):
                       f"{n_per} negatives/sample/set, fp32, dense AdamW)", "ms_per_step": sec * 1e3}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum summed over the GEMM launches of one training step (ncu, round 1)
+GEMM_DRAM_BYTES_PER_STEP = {"B": 14.4e9}
+
+
 # ------------------------------------------------------------------------------------- GPU arm
 def main():
     args = parse()
@@ -326,7 +330,10 @@ def main():
         "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms / args.steps,
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all GEMM launches of the step)",
                      "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
-                     "traffic": None, "peak_source": pk_src + ", sustained bf16",
+                     "traffic": GEMM_DRAM_BYTES_PER_STEP.get(cfg["name"]) if world == 1 else None,
+                     "traffic_note": "dram read+write bytes of all GEMM launches of one step, ncu launch list "
+                                     "profiles/r01_launches_dram_metrics.csv (profiles/r01_kernel_evidence.md)",
+                     "peak_source": pk_src + ", sustained bf16",
                      "gemm_ms_per_step": gms / args.steps, "gemm_share_of_step": gms / ms if ms else None,
                      "timing": ("instrumented eager pass after the timed region (the timed region replays CUDA graphs)"
                                 if use_graph else "CUDA events around every GEMM launch inside the timed region"),
