@@ -197,6 +197,7 @@ int b200rec_l2norm_bwd(const void* x_hat, int act_dtype, const float* inv_norm, 
 struct ScatterWs {
   uint32_t *keys_in, *keys_out;
   int32_t *pos_in, *pos_out, *seg, *seg_start;
+  int32_t* long_list;
   void* cub_tmp;
   size_t cub_bytes;
   size_t total;
@@ -219,6 +220,7 @@ static ScatterWs scatter_layout(int64_t n, void* base) {
   w.pos_out = (int32_t*)take(n * 4);
   w.seg = (int32_t*)take(n * 4);
   w.seg_start = (int32_t*)take((n + 1) * 4);
+  w.long_list = (int32_t*)take((n / 32 + 2) * 4);   // [0] = count, then ids of segments longer than 32 rows
   size_t sort_bytes = 0, scan_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int32_t*)nullptr,
                                   (int32_t*)nullptr, (int)n);
@@ -271,34 +273,131 @@ __global__ void scatter_bounds_kernel(const uint32_t* __restrict__ keys, const i
   if (i == 0 && !valid) *n_uniq = 0;
 }
 
-// one block per unique id; thread owns float4 columns; rows added in ascending input position
-__global__ void __launch_bounds__(128) scatter_reduce_kernel(const int32_t* __restrict__ seg_start,
-                                                             const int32_t* __restrict__ pos_sorted,
-                                                             const int32_t* __restrict__ n_uniq,
-                                                             const float* __restrict__ grad_rows, int D4,
-                                                             float* __restrict__ uniq_rows) {
-  int nu = *n_uniq;
-  for (int s = blockIdx.x; s < nu; s += gridDim.x) {
-    int beg = seg_start[s], end = seg_start[s + 1];
-    for (int c = threadIdx.x; c < D4; c += blockDim.x) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      int i = beg;
-      for (; i + 4 <= end; i += 4) {
-        float v[4][4];
+// Deterministic segment sums.  Summation order (part of the contract, tests replicate it):
+//   * a segment of <= 32 rows: rows added one by one in ascending input position;
+//   * a longer segment: cut into chunks of 32 consecutive rows; chunk j is summed row by row; warp w (0..7) adds
+//     the chunk sums j = w, w+8, w+16, ... in ascending j; the 8 warp totals are added in order w = 0..7.
+// Short segments take one warp each (a lane owns every 32nd float4 column, 4 rows of loads in flight); long ones
+// (hot items of a Zipf catalogue) take a whole block so that one id cannot serialise the kernel.
+#define SEG_CH 32
+
+template <int MAXV>
+__device__ __forceinline__ void seg_sum_rows(const float* __restrict__ grad_rows, const int32_t* __restrict__ pos_sorted,
+                                             int beg, int end, int D4, int c0, float (&acc)[MAXV][4]) {
+  const int lane = threadIdx.x & 31;
+  int i = beg;
+  for (; i + 4 <= end; i += 4) {
+    float v[4][MAXV][4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) load4<float>(grad_rows + ((int64_t)pos_sorted[i + u] * D4 + c) * 4, v[u]);
+    for (int r = 0; r < 4; ++r) {
+      const float* row = grad_rows + (int64_t)pos_sorted[i + r] * D4 * 4;
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) acc[k] += v[u][k];
+      for (int u = 0; u < MAXV; ++u) {
+        const int c = c0 + lane + 32 * u;
+        if (c < D4) load4<float>(row + c * 4, v[r][u]);
       }
-      for (; i < end; ++i) {
-        float v[4];
-        load4<float>(grad_rows + ((int64_t)pos_sorted[i] * D4 + c) * 4, v);
+    }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) acc[k] += v[k];
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int u = 0; u < MAXV; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[u][k] += v[r][u][k];
+  }
+  for (; i < end; ++i) {
+    const float* row = grad_rows + (int64_t)pos_sorted[i] * D4 * 4;
+    float v[MAXV][4];
+#pragma unroll
+    for (int u = 0; u < MAXV; ++u) {
+      const int c = c0 + lane + 32 * u;
+      if (c < D4) load4<float>(row + c * 4, v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < MAXV; ++u)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[u][k] += v[u][k];
+  }
+}
+
+#define SEG_V 4   // float4 columns per lane and pass: 4 rows x 4 vectors x 16 B in flight per lane
+
+__global__ void __launch_bounds__(256) scatter_reduce_short_kernel(const int32_t* __restrict__ seg_start,
+                                                                   const int32_t* __restrict__ pos_sorted,
+                                                                   const int32_t* __restrict__ n_uniq,
+                                                                   const float* __restrict__ grad_rows, int D4,
+                                                                   float* __restrict__ uniq_rows,
+                                                                   int32_t* __restrict__ long_list) {
+  const int nu = *n_uniq;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < nu; s += warps) {
+    const int beg = seg_start[s], end = seg_start[s + 1];
+    if (end - beg > SEG_CH) {
+      if (lane == 0) long_list[1 + atomicAdd(&long_list[0], 1)] = s;   // list order does not affect any sum
+      continue;
+    }
+    for (int c0 = 0; c0 < D4; c0 += 32 * SEG_V) {
+      float acc[SEG_V][4];
+#pragma unroll
+      for (int u = 0; u < SEG_V; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[u][k] = 0.f;
+      seg_sum_rows<SEG_V>(grad_rows, pos_sorted, beg, end, D4, c0, acc);
+#pragma unroll
+      for (int u = 0; u < SEG_V; ++u) {
+        const int c = c0 + lane + 32 * u;
+        if (c < D4) store4<float>(uniq_rows + ((int64_t)s * D4 + c) * 4, acc[u]);
       }
-      store4<float>(uniq_rows + ((int64_t)s * D4 + c) * 4, acc);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) scatter_reduce_long_kernel(const int32_t* __restrict__ seg_start,
+                                                                  const int32_t* __restrict__ pos_sorted,
+                                                                  const float* __restrict__ grad_rows, int D4,
+                                                                  float* __restrict__ uniq_rows,
+                                                                  const int32_t* __restrict__ long_list) {
+  __shared__ float part[8][32 * SEG_V * 4];
+  const int n_long = long_list[0];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int q = blockIdx.x; q < n_long; q += gridDim.x) {
+    const int s = long_list[1 + q];
+    const int beg = seg_start[s], end = seg_start[s + 1];
+    const int n_chunks = (end - beg + SEG_CH - 1) / SEG_CH;
+    for (int c0 = 0; c0 < D4; c0 += 32 * SEG_V) {
+      float tot[SEG_V][4];
+#pragma unroll
+      for (int u = 0; u < SEG_V; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tot[u][k] = 0.f;
+      for (int j = w; j < n_chunks; j += 8) {
+        float acc[SEG_V][4];
+#pragma unroll
+        for (int u = 0; u < SEG_V; ++u)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[u][k] = 0.f;
+        const int cb = beg + j * SEG_CH;
+        seg_sum_rows<SEG_V>(grad_rows, pos_sorted, cb, min(end, cb + SEG_CH), D4, c0, acc);
+#pragma unroll
+        for (int u = 0; u < SEG_V; ++u)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tot[u][k] += acc[u][k];
+      }
+#pragma unroll
+      for (int u = 0; u < SEG_V; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) part[w][(lane + 32 * u) * 4 + k] = tot[u][k];
+      __syncthreads();
+      for (int e = threadIdx.x; e < 32 * SEG_V * 4; e += blockDim.x) {
+        const int col = c0 * 4 + e;
+        if (col < D4 * 4) {
+          float sum = part[0][e];
+#pragma unroll
+          for (int ww = 1; ww < 8; ++ww) sum += part[ww][e];
+          uniq_rows[(int64_t)s * D4 * 4 + col] = sum;
+        }
+      }
+      __syncthreads();
     }
   }
 }
@@ -325,8 +424,12 @@ int b200rec_scatter_add_sorted(const int64_t* ids, int64_t n_ids, const float* g
   tmp = w.cub_bytes;
   B200_CUDA_OK(cub::DeviceScan::InclusiveSum(w.cub_tmp, tmp, w.pos_in, w.seg, n, st));
   scatter_bounds_kernel<<<blocks, 256, 0, st>>>(w.keys_out, w.seg, n, w.seg_start, uniq_ids, n_uniq);
-  int rblocks = std::min(n, 148 * 16);
-  scatter_reduce_kernel<<<rblocks, 128, 0, st>>>(w.seg_start, w.pos_out, n_uniq, grad_rows, D / 4, uniq_rows);
+  B200_CUDA_OK(cudaMemsetAsync(w.long_list, 0, 4, st));
+  int rblocks = std::min(ceil_div_i(n, 8), 148 * 8);
+  scatter_reduce_short_kernel<<<rblocks, 256, 0, st>>>(w.seg_start, w.pos_out, n_uniq, grad_rows, D / 4, uniq_rows,
+                                                       w.long_list);
+  scatter_reduce_long_kernel<<<std::min(n / SEG_CH + 1, 148 * 2), 256, 0, st>>>(w.seg_start, w.pos_out, grad_rows, D / 4,
+                                                                               uniq_rows, w.long_list);
   B200_LAUNCH_OK();
   return 0;
 }

@@ -64,82 +64,163 @@ __global__ void suppress_history_kernel(const int32_t* __restrict__ hist_off, co
 // ---- pass 2: per-user radix select + sort ---------------------------------------------------------
 #define SEL_THREADS 1024
 #define SEL_MAXK 1024
+#define SEL_BINS 2048      // first pass: top 11 bits of the order key
+#define SEL_CAND2 4096     // capacity for the elements of the threshold bin
+
+// visits every element of the row once; 16-byte loads when the row allows it
+template <typename F>
+__device__ __forceinline__ void sel_for_each(const float* __restrict__ row, int64_t N, F f) {
+  const int tid = threadIdx.x;
+  if ((N & 3) == 0 && (((uintptr_t)row) & 15) == 0) {
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    for (int64_t i = tid; i < (N >> 2); i += SEL_THREADS) {
+      float4 v = __ldg(r4 + i);
+      f(v.x, i * 4); f(v.y, i * 4 + 1); f(v.z, i * 4 + 2); f(v.w, i * 4 + 3);
+    }
+  } else {
+    for (int64_t i = tid; i < N; i += SEL_THREADS) f(row[i], i);
+  }
+}
+
+// block-wide bitonic sort (ascending) of n_pad (power of two) 64-bit keys in shared memory
+__device__ __forceinline__ void sel_bitonic(unsigned long long* a, int n_pad) {
+  for (int size = 2; size <= n_pad; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < n_pad; i += SEL_THREADS) {
+        int j = i ^ stride;
+        if (j > i) {
+          bool up = (i & size) == 0;
+          unsigned long long x = a[i], y = a[j];
+          if ((x > y) == up) { a[i] = y; a[j] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
 
 __global__ void __launch_bounds__(SEL_THREADS)
 select_topk_kernel(const float* __restrict__ fval, const uint8_t* __restrict__ fhead, int64_t N, int K,
                    int64_t id_offset, int64_t id_stride, int64_t* __restrict__ topk_idx, float* __restrict__ topk_val, int32_t* __restrict__ topk_head) {
-  __shared__ unsigned int hist[256];
+  // cand2 holds the elements of the threshold bin; the 11-bit histogram of the first pass aliases it
+  __shared__ unsigned long long cand2[SEL_CAND2];
   __shared__ unsigned long long cand[SEL_MAXK];
-  __shared__ unsigned int s_prefix, s_remaining, s_count, s_scan[SEL_THREADS / 32 + 1];
+  __shared__ unsigned int s_prefix, s_remaining, s_count, s_count2, s_scan[SEL_THREADS / 32 + 1];
+  unsigned int* hist = reinterpret_cast<unsigned int*>(cand2);
   const int b = blockIdx.x;
   const float* row = fval + (int64_t)b * N;
   const int tid = threadIdx.x;
 
-  // 4 x 8-bit MSD radix passes: find key T* of the K-th largest element
-  uint32_t prefix = 0, mask = 0;
-  uint32_t remaining = (uint32_t)K;
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    if (tid < 256) hist[tid] = 0;
+  // ---- read 1: 11-bit histogram -> threshold bin d (the bin holding the K-th largest), rem = how many of its
+  //      elements belong to the top-K
+  for (int i = tid; i < SEL_BINS; i += SEL_THREADS) hist[i] = 0;
+  __syncthreads();
+  sel_for_each(row, N, [&](float v, int64_t) { atomicAdd(&hist[order_key(v) >> 21], 1u); });
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t rem = (uint32_t)K, d = SEL_BINS - 1;
+    for (;; --d) {
+      uint32_t c = hist[d];
+      if (c >= rem || d == 0) break;
+      rem -= c;
+    }
+    s_prefix = d;
+    s_remaining = rem;
+    s_count2 = hist[d];
+    s_count = 0;
+  }
+  __syncthreads();
+  const uint32_t bin = s_prefix, rem_bin = s_remaining, n_bin = s_count2;
+  __syncthreads();   // hist (aliasing cand2) is dead from here
+
+  if (n_bin <= SEL_CAND2) {
+    // ---- read 2: elements above the bin are in the top-K; elements of the bin go to cand2
+    if (tid == 0) s_count2 = 0;
     __syncthreads();
+    sel_for_each(row, N, [&](float v, int64_t i) {
+      const uint32_t k = order_key(v), top = k >> 21;
+      if (top > bin) {
+        unsigned int slot = atomicAdd(&s_count, 1u);
+        cand[slot] = ((unsigned long long)(~k) << 32) | (unsigned long long)(uint32_t)i;
+      } else if (top == bin) {
+        unsigned int slot = atomicAdd(&s_count2, 1u);
+        cand2[slot] = ((unsigned long long)(~k) << 32) | (unsigned long long)(uint32_t)i;
+      }
+    });
+    __syncthreads();
+    const uint32_t base = s_count;
+    // order the bin by (value desc, id asc) and take its first rem_bin elements
+    int n2 = 1;
+    while (n2 < (int)n_bin) n2 <<= 1;
+    for (int i = n_bin + tid; i < n2; i += SEL_THREADS) cand2[i] = 0xffffffffffffffffull;
+    __syncthreads();
+    sel_bitonic(cand2, n2);
+    for (uint32_t i = tid; i < rem_bin && base + i < (uint32_t)K; i += SEL_THREADS) cand[base + i] = cand2[i];
+    __syncthreads();
+  } else {
+    // ---- crowded threshold bin (heavily tied / quantised scores): exact 4 x 8-bit MSD radix passes
+    uint32_t prefix = 0, mask = 0;
+    uint32_t remaining = (uint32_t)K;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      if (tid < 256) hist[tid] = 0;
+      __syncthreads();
+      for (int64_t i = tid; i < N; i += SEL_THREADS) {
+        uint32_t k = order_key(row[i]);
+        if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t rem = remaining, d = 255;
+        for (;; --d) {  // walk digits from the largest
+          uint32_t c = hist[d];
+          if (c >= rem || d == 0) break;
+          rem -= c;
+        }
+        s_prefix = prefix | (d << shift);
+        s_remaining = rem;
+      }
+      __syncthreads();
+      prefix = s_prefix;
+      remaining = s_remaining;
+      mask |= 255u << shift;
+      __syncthreads();
+    }
+    const uint32_t kth = prefix;       // key of the K-th largest
+    const uint32_t quota = remaining;  // how many elements equal to kth belong to the top-K
+    // collect strictly-greater elements (unordered) ...
     for (int64_t i = tid; i < N; i += SEL_THREADS) {
       uint32_t k = order_key(row[i]);
-      if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
-    }
-    __syncthreads();
-    if (tid == 0) {
-      uint32_t rem = remaining, d = 255;
-      for (;; --d) {  // walk digits from the largest
-        uint32_t c = hist[d];
-        if (c >= rem || d == 0) break;
-        rem -= c;
+      if (k > kth) {
+        unsigned int slot = atomicAdd(&s_count, 1u);
+        if (slot < SEL_MAXK) cand[slot] = ((unsigned long long)(~k) << 32) | (unsigned long long)(uint32_t)i;
       }
-      s_prefix = prefix | (d << shift);
-      s_remaining = rem;
     }
     __syncthreads();
-    prefix = s_prefix;
-    remaining = s_remaining;
-    mask |= 255u << shift;
-    __syncthreads();
-  }
-  const uint32_t kth = prefix;       // key of the K-th largest
-  const uint32_t quota = remaining;  // how many elements equal to kth belong to the top-K
-
-  // collect strictly-greater elements (unordered) ...
-  if (tid == 0) s_count = 0;
-  __syncthreads();
-  for (int64_t i = tid; i < N; i += SEL_THREADS) {
-    uint32_t k = order_key(row[i]);
-    if (k > kth) {
-      unsigned int slot = atomicAdd(&s_count, 1u);
-      if (slot < SEL_MAXK) cand[slot] = ((unsigned long long)(~k) << 32) | (unsigned long long)(uint32_t)i;
-    }
-  }
-  __syncthreads();
-  // ... then the `quota` smallest ids among the ties at kth (ordered compaction, id ascending)
-  uint32_t base = s_count;
-  uint32_t taken = 0;
-  for (int64_t i0 = 0; i0 < N && taken < quota; i0 += SEL_THREADS) {
-    int64_t i = i0 + tid;
-    uint32_t flag = (i < N && order_key(row[i]) == kth) ? 1u : 0u;
-    uint32_t ball = __ballot_sync(0xffffffffu, flag);
-    int lane = tid & 31, w = tid >> 5;
-    if (lane == 0) s_scan[w] = __popc(ball);
-    __syncthreads();
-    if (tid == 0) {
-      uint32_t run = 0;
-      for (int x = 0; x < SEL_THREADS / 32; ++x) {
-        uint32_t c = s_scan[x];
-        s_scan[x] = run;
-        run += c;
+    // ... then the `quota` smallest ids among the ties at kth (ordered compaction, id ascending)
+    uint32_t base = s_count;
+    uint32_t taken = 0;
+    for (int64_t i0 = 0; i0 < N && taken < quota; i0 += SEL_THREADS) {
+      int64_t i = i0 + tid;
+      uint32_t flag = (i < N && order_key(row[i]) == kth) ? 1u : 0u;
+      uint32_t ball = __ballot_sync(0xffffffffu, flag);
+      int lane = tid & 31, w = tid >> 5;
+      if (lane == 0) s_scan[w] = __popc(ball);
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t run = 0;
+        for (int x = 0; x < SEL_THREADS / 32; ++x) {
+          uint32_t c = s_scan[x];
+          s_scan[x] = run;
+          run += c;
+        }
+        s_scan[SEL_THREADS / 32] = run;
       }
-      s_scan[SEL_THREADS / 32] = run;
+      __syncthreads();
+      uint32_t rank = taken + s_scan[w] + __popc(ball & ((1u << lane) - 1u));
+      if (flag && rank < quota) cand[base + rank] = ((unsigned long long)(~kth) << 32) | (unsigned long long)(uint32_t)i;
+      taken += s_scan[SEL_THREADS / 32];
+      __syncthreads();
     }
-    __syncthreads();
-    uint32_t rank = taken + s_scan[w] + __popc(ball & ((1u << lane) - 1u));
-    if (flag && rank < quota) cand[base + rank] = ((unsigned long long)(~kth) << 32) | (unsigned long long)(uint32_t)i;
-    taken += s_scan[SEL_THREADS / 32];
-    __syncthreads();
   }
   // pad and bitonic sort ascending on (~key, id): value desc, id asc
   int n_pad = 1;
@@ -147,19 +228,7 @@ select_topk_kernel(const float* __restrict__ fval, const uint8_t* __restrict__ f
   for (int i = tid; i < n_pad; i += SEL_THREADS)
     if (i >= K) cand[i] = 0xffffffffffffffffull;
   __syncthreads();
-  for (int size = 2; size <= n_pad; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = tid; i < n_pad; i += SEL_THREADS) {
-        int j = i ^ stride;
-        if (j > i) {
-          bool up = (i & size) == 0;
-          unsigned long long a = cand[i], c = cand[j];
-          if ((a > c) == up) { cand[i] = c; cand[j] = a; }
-        }
-      }
-      __syncthreads();
-    }
-  }
+  sel_bitonic(cand, n_pad);
   for (int i = tid; i < K; i += SEL_THREADS) {
     unsigned long long c = cand[i];
     uint32_t id = (uint32_t)(c & 0xffffffffull);

@@ -98,13 +98,31 @@ def test_scatter_add_sorted_rows_and_determinism(n, N, D):
     dense = torch.zeros(N, D, device=dev(), dtype=torch.float64)
     dense.index_add_(0, ids[valid], rows[valid].double())
     assert torch.allclose(outs[0][1].double(), dense[ref_ids], rtol=1e-5, atol=1e-5)
-    # sequential in-order fp32 sum is the stated summation order: check one multi-row id exactly
+    # the stated summation order (embed.cu): <= 32 rows sequential in input order; longer: 32-row chunks summed
+    # sequentially, chunk sums j = w, w+8, ... added per "warp" w, the 8 totals added in order.  Check the most
+    # frequent id (long) and a short multi-row id exactly.
     cnt = torch.bincount(ids[valid], minlength=N)
-    j = int(torch.argmax(cnt))
-    acc = torch.zeros(D, device=dev())
-    for r in rows[ids == j]:
-        acc = acc + r
-    assert torch.equal(outs[0][1][(ref_ids == j).nonzero()[0, 0]], acc)
+
+    def stated_sum(rs):
+        def seq(block):
+            acc = torch.zeros(D, device=dev())
+            for r in block:
+                acc = acc + r
+            return acc
+        if rs.shape[0] <= 32:
+            return seq(rs)
+        chunks = [seq(rs[i:i + 32]) for i in range(0, rs.shape[0], 32)]
+        tot = None
+        for w in range(8):
+            tw = torch.zeros(D, device=dev())
+            for ch in chunks[w::8]:
+                tw = tw + ch
+            tot = tw if tot is None else tot + tw
+        return tot
+
+    short = (cnt >= 2) & (cnt <= 32)
+    for j in [int(torch.argmax(cnt))] + ([int(short.nonzero()[0, 0])] if bool(short.any()) else []):
+        assert torch.equal(outs[0][1][(ref_ids == j).nonzero()[0, 0]], stated_sum(rows[ids == j]))
     d2 = torch.zeros(N, D, device=dev())
     nu = torch.tensor([ref_ids.numel()], dtype=torch.int32, device=dev())
     L.call("b200rec_rows_to_dense", outs[0][0].data_ptr(), outs[0][1].data_ptr(), nu.data_ptr(), n, D, d2.data_ptr(),
@@ -388,6 +406,35 @@ def test_topk_ties_and_neg_inf_rule():
            idx.data_ptr(), val.data_ptr(), hs.data_ptr(), ws.data_ptr(), wsb, L.stream())
     assert idx[0].tolist() == [300, 7, 9] + [i for i in range(N) if i not in (7, 9, 300)][:K - 3]
     assert idx[1].tolist() == list(range(10, 10 + K))
+
+
+@pytest.mark.parametrize("kind", ["smooth", "quantised", "few_finite", "odd_n"])
+def test_topk_select_both_paths_large_rows(kind):
+    """select_topk: two-read path (threshold bin fits the candidate buffer) and the exact radix fallback (crowded
+    bin: quantised scores, or fewer finite scores than K) against a (value desc, id asc) lexicographic sort."""
+    B, N, K = 3, 60000 if kind != "odd_n" else 60001, 200
+    g = torch.Generator().manual_seed(65)
+    if kind in ("smooth", "odd_n"):
+        sc = torch.randn(B, N, generator=g) * 0.03
+    elif kind == "quantised":
+        sc = torch.randint(0, 6, (B, N), generator=g).float() * 0.125          # ~10 k-way ties in the threshold bin
+    else:
+        sc = torch.full((B, N), float("-inf"))
+        sc[:, 1000:1050] = torch.randn(B, 50, generator=g)
+    sc = sc.to(dev())
+    fval = sc.clone()
+    fhead = torch.zeros(B, N, dtype=torch.uint8, device=dev())
+    idx = torch.empty(B, K, dtype=torch.int64, device=dev())
+    val = torch.empty(B, K, device=dev())
+    hs = torch.empty(B, K, dtype=torch.int32, device=dev())
+    L.call("b200rec_topk_select", fval.data_ptr(), fhead.data_ptr(), B, N, K, None, None, 0, 1, idx.data_ptr(),
+           val.data_ptr(), hs.data_ptr(), L.stream())
+    ids = torch.arange(N, device=dev()).expand(B, N)
+    o1 = torch.argsort(ids, dim=1, stable=True)
+    o2 = torch.argsort(sc.gather(1, o1), dim=1, descending=True, stable=True)      # value desc, ties keep id asc
+    want = o1.gather(1, o2)[:, :K]
+    assert torch.equal(idx, want)
+    assert torch.equal(val, sc.gather(1, want))
 
 
 def test_hit_matrix_quirks():
