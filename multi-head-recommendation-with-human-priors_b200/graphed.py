@@ -104,6 +104,7 @@ class GraphedShardedStep(object):
     def __init__(self, model, optimizer, example_batch, bucket=128, warmup=2, group=None):
         import torch.distributed as dist
         assert model.sharded_table is not None, "call model.shard_item_table() first"
+        assert not model._has_tower(), "item_id_proj_tower: use the eager sharded step"
         assert not optimizer.device_step, "the optimizer runs eagerly here: FusedAdamW(device_step=False)"
         self.dist, self.group = dist, group
         self.model, self.opt, self.bucket, self.warmup = model, optimizer, bucket, warmup

@@ -95,8 +95,7 @@ class HSTU(nn.Module):
         self.item_num = dataload.item_num
         D_item = config["item_embedding_size"]
         D = config["hstu_embedding_size"]
-        if D_item != D:
-            raise NotImplementedError("item_embedding_size != hstu_embedding_size (item_id_proj_tower) is not built")
+        self._item_embedding_dim = D_item
         self._hstu_embedding_dim = D
         self.max_seq_length = config["MAX_ITEM_LIST_LENGTH"]
         self.pred_len = config["pred_len"]
@@ -113,8 +112,6 @@ class HSTU(nn.Module):
         else:
             raise ValueError(f'Unknown head_interaction: {config["head_interaction"]}')
         self.medusa_num_layers = config["medusa_num_layers"]
-        if self.medusa_num_layers > 1:
-            raise NotImplementedError("medusa_num_layers > 1 is not built in this round")
         self.category_by = config["category_by"]
         self._num_blocks = config["n_layers"]
         self._num_heads = config["n_heads"]
@@ -131,7 +128,8 @@ class HSTU(nn.Module):
             blocks.append(_STU(D, rb))
         self._hstu = _Body(blocks)
         self.item_embedding = nn.Embedding(self.item_num, D_item, padding_idx=0)
-        self.item_id_proj_tower = nn.Identity()
+        # hstu.py:414: bias-free Linear when the table is narrower / wider than the HSTU width
+        self.item_id_proj_tower = nn.Identity() if D_item == D else nn.Linear(D_item, D, bias=False)
         self.loss = config["loss"]
         self.neg_sample_by_cat = bool(config["neg_sample_by_cat"]) and self.loss == "prior"
         if (config["pos_sample_mix_ratio"] or 0) > 0:
@@ -184,6 +182,7 @@ class HSTU(nn.Module):
         self._drop_p_last = 0.0
         self.sharded_table = None  # parallel.ShardedTable once shard_item_table() was called
         self._shadow_buf, self._shadow_state, self._shadow_view = {}, {}, {}
+        self._heads_upper = []     # (input, pre-activation) of the weight-tied decode-head layers above the first
         self.emb_grad = None       # (uniq_ids, uniq_rows, n_uniq) of the last backward
         self._table_cache = None   # normalised compute-dtype item table for predict
         self._verbose = False
@@ -304,17 +303,50 @@ class HSTU(nn.Module):
         self._table_cache = None
         return self
 
+    def _has_tower(self):
+        return isinstance(self.item_id_proj_tower, nn.Linear)
+
+    def _project_rows(self, raw, fp32=False):
+        """item_id_proj_tower (hstu.py:414,637,670): fp32 rows [R, D_item] -> fp32 [R, D]; also returns the
+        compute-dtype copy of the input rows (the dW operand of the backward).  fp32=True keeps the contraction
+        in fp32 (compute_item_all: once per evaluation, feeds the normalised catalogue)."""
+        R, Di = raw.shape
+        D, act = self._hstu_embedding_dim, (torch.float32 if fp32 else self._act())
+        Wt = self.item_id_proj_tower.weight.data                      # [D, D_item] = [N, K]
+        if act == torch.float32:
+            raw_a, W_a = raw, Wt
+        else:
+            raw_a = torch.empty((R, Di), dtype=act, device=raw.device)
+            L.call("b200rec_cast", raw.data_ptr(), raw.numel(), raw_a.data_ptr(), L.dt(act), L.stream())
+            W_a = self._shadow_get(self.item_id_proj_tower.weight, "tower", (D, Di))
+        out = torch.empty((R, D), dtype=torch.float32, device=raw.device)
+        L.gemm(raw_a, W_a, out, R, D, Di, lda=Di, ldb=Di, ldc=D)
+        return out, raw_a, W_a
+
     def _table_rows(self, items, neg_ids):
-        """Returns (table, item_index [B, LP], neg_index [sets, n_neg], uniq_ids or None): the tensor the
-        gather kernels read and the row indices into it.  Replicated table: the table itself and the ids.
-        Sharded table: the unique requested rows fetched by all-to-all and positions in that cache."""
-        if self.sharded_table is None:
+        """Returns (table, item_index [B, LP], neg_index [sets, n_neg], cache info or None): the tensor the
+        gather kernels read and the row indices into it.
+          replicated table, no tower: the table itself and the ids (info None);
+          sharded table: the unique requested rows fetched by all-to-all, positions in that cache;
+          projection tower: a row cache holding proj(W[id]) — one row per requested position (static shapes,
+          no sync) with a replicated table, one row per unique id on top of the sharded fetch."""
+        tower = self._has_tower()
+        if self.sharded_table is None and not tower:
             return self.item_embedding.weight.data, items, neg_ids, None
         B, LP = items.shape
         all_ids = torch.cat([items.reshape(-1), neg_ids.reshape(-1)])
-        uniq, inv = torch.unique(all_ids, return_inverse=True)
-        cache = self.sharded_table.fetch(uniq)
-        return cache, inv[:B * LP].view(B, LP).contiguous(), inv[B * LP:].view(neg_ids.shape).contiguous(), uniq
+        info = dict(raw_a=None, W_a=None)
+        if self.sharded_table is not None:
+            uniq, inv = torch.unique(all_ids, return_inverse=True)
+            cache = self.sharded_table.fetch(uniq)
+            info["ids"] = uniq
+        else:
+            cache = parallel.cuda_row_gather(self.item_embedding.weight.data, all_ids)
+            inv = torch.arange(all_ids.numel(), dtype=torch.int64, device=items.device)
+            info["ids"] = all_ids
+        if tower:
+            cache, info["raw_a"], info["W_a"] = self._project_rows(cache)
+        return cache, inv[:B * LP].view(B, LP).contiguous(), inv[B * LP:].view(neg_ids.shape).contiguous(), info
 
     def prepare_rows(self, items, neg_items, static=False):
         """Everything of a training step that needs collectives or data-dependent shapes, so it can run
@@ -329,9 +361,9 @@ class HSTU(nn.Module):
         n_sets = neg_items.shape[1]
         n_neg = neg_items.shape[0] * neg_items.shape[2]
         neg_ids = neg_items.permute(1, 0, 2).contiguous().view(n_sets, n_neg)   # set-major id lists
-        W, items_idx, neg_idx, uniq = self._table_rows(items, neg_ids)
+        W, items_idx, neg_idx, info = self._table_rows(items, neg_ids)
         return dict(W=W, items_idx=items_idx, neg_idx=neg_idx, gl_items=items, gl_neg=neg_ids,
-                    cached=uniq is not None, n_rows=(uniq.numel() if uniq is not None else None))
+                    cached=info is not None, n_rows=(W.shape[0] if info is not None else None), info=info)
 
     @staticmethod
     def _tokens(valid, force_last=False):
@@ -485,6 +517,7 @@ class HSTU(nn.Module):
         """y fp32 [rows, D] -> hd fp32 [rows, Hx, D], z (pre-activation, act) or None, yb (act copy)."""
         D, Hx = self._hstu_embedding_dim, self._phys_heads()
         act, dev = self._act(), y.device
+        self._heads_upper = []
         if self.medusa_num_layers == 0:
             return y.view(rows, 1, D), None, None
         if act == torch.float32:
@@ -496,6 +529,25 @@ class HSTU(nn.Module):
         z = torch.empty((rows, Hx, D), dtype=act, device=dev)
         L.gemm(yb, w["heads_w"], hd, rows, Hx * D, D, lda=D, ldb=D, ldc=Hx * D, epilogue=L.EPI_RESBLOCK,
                bias=w["heads_b"], resid=y, ldr=D, C2=z, ldc2=Hx * D, n_split=D)
+        # medusa_num_layers > 1: the SAME ResBlock is applied again (hstu.py:486-493 builds `[ResBlock] * n`, i.e.
+        # weight-tied layers): in_l[h] = hd_{l-1}[h], one GEMM per head with the head's own input
+        self._heads_upper = []
+        for _ in range(1, self.medusa_num_layers):
+            if act == torch.float32:
+                hin = hd
+            else:
+                hin = torch.empty((rows, Hx, D), dtype=act, device=dev)
+                L.call("b200rec_cast", hd.data_ptr(), hd.numel(), hin.data_ptr(), L.dt(act), L.stream())
+            hd2 = torch.empty((rows, Hx, D), dtype=torch.float32, device=dev)
+            z2 = torch.empty((rows, Hx, D), dtype=act, device=dev)
+            hin2, hd_2, hdo2, z_2 = hin.view(rows, Hx * D), hd.view(rows, Hx * D), hd2.view(rows, Hx * D), z2.view(rows, Hx * D)
+            for h in range(Hx):
+                sl = slice(h * D, (h + 1) * D)
+                L.gemm(hin2[:, sl], w["heads_w"][sl], hdo2[:, sl], rows, D, D, lda=Hx * D, ldb=D, ldc=Hx * D,
+                       epilogue=L.EPI_RESBLOCK, bias=w["heads_b"][sl], resid=hd_2[:, sl], ldr=Hx * D, C2=z_2[:, sl],
+                       ldc2=Hx * D, n_split=D)
+            self._heads_upper.append((hin, z2))
+            hd = hd2
         return hd, z, yb
 
     # ------------------------------------------------------------------ training (hstu.py:631-872)
@@ -664,11 +716,11 @@ class HSTU(nn.Module):
         loss = total * half
         if need_grad:
             ctx = dict(B=B, LP=LP, T=T, tok_b=tok_b, tok_pos=tok_pos, seq_off=seq_off, key_valid=key_valid,
-                       tok_index=tok_index, w=w, saved=saved, hd=hd, z=z, yb=yb, qhat=qhat, qinv=qinv, that=that,
+                       tok_index=tok_index, w=w, saved=saved, hd=hd, z=z, yb=yb, heads_upper=list(self._heads_upper), qhat=qhat, qinv=qinv, that=that,
                        tinv=tinv, nhat=nhat, ninv=ninv, neg_ids=neg_ids, job_out=job_out, scale=scale, half=half,
                        items=items, mask=m, n_neg=n_neg, ld_neg=ld_neg, Hx=Hx, used_sets=used_sets,
                        gl_items=gl_items, gl_neg_ids=gl_neg_ids, uniq_rows_ids=uniq_rows_ids,
-                       n_cache_rows=W.shape[0], push=prepared.get("push", True))
+                       n_cache_rows=W.shape[0], push=prepared.get("push", True), cache_info=prepared.get("info"))
         return loss, logs, ctx
 
     def _train_backward(self, ctx, gscale):
@@ -732,16 +784,32 @@ class HSTU(nn.Module):
                d_hd.data_ptr(), 0, st)
         dy = torch.empty((T, D), dtype=torch.float32, device=dev)
         if self.medusa_num_layers > 0:
+            dWc = torch.empty((Hx * D, D), dtype=torch.float32, device=dev)
+            dbc = torch.empty(Hx * D, dtype=torch.float32, device=dev)
+            upper = ctx["heads_upper"]
+            for li, (hin, z_l) in enumerate(reversed(upper)):
+                # weight-tied upper layers: d_in[h] = d_out[h] + (d_out[h] * silu'(z_l[h])) @ W_h ; dW_h, db_h accumulate
+                dz_l = torch.empty((T, Hx * D), dtype=act, device=dev)
+                d_in = torch.empty((T * Hx, D), dtype=torch.float32, device=dev)
+                L.call("b200rec_resblock_bwd", d_hd.data_ptr(), z_l.data_ptr(), a_dt, T * Hx, 1, D, dz_l.data_ptr(),
+                       d_in.data_ptr(), st)
+                d_in2, hin2 = d_in.view(T, Hx * D), hin.view(T, Hx * D)
+                sls = [slice(h * D, (h + 1) * D) for h in range(Hx)]
+                L.gemm_grouped([(dz_l[:, sl], w["heads_w"][sl], d_in2[:, sl]) for sl in sls], T, D, D, lda=Hx * D,
+                               ldb=D, b_major=1, ldc=Hx * D, epilogue=L.EPI_ACCUM)
+                L.gemm_grouped([(dz_l[:, sl], hin2[:, sl], dWc[sl]) for sl in sls], D, D, T, lda=Hx * D, a_major=1,
+                               ldb=Hx * D, b_major=1, ldc=D, epilogue=L.EPI_STORE if li == 0 else L.EPI_ACCUM)
+                L.colsum(dz_l, T, Hx * D, Hx * D, dbc, accumulate=li > 0)
+                d_hd = d_in
             dz = torch.empty((T, Hx * D), dtype=act, device=dev)
             L.call("b200rec_resblock_bwd", d_hd.data_ptr(), ctx["z"].data_ptr(), a_dt, T, Hx, D, dz.data_ptr(),
                    dy.data_ptr(), st)
             # dy += dz @ Wcat   (Wcat [H*D, D] = [K, N] -> MN-major B)
             L.gemm(dz, w["heads_w"], dy, T, D, Hx * D, lda=Hx * D, ldb=D, b_major=1, ldc=D, epilogue=L.EPI_ACCUM)
-            # dWcat[H*D, D] = dz^T @ yb  (both MN-major, K = T)
-            dWc = torch.empty((Hx * D, D), dtype=torch.float32, device=dev)
-            L.gemm(dz, ctx["yb"], dWc, Hx * D, D, T, lda=Hx * D, a_major=1, ldb=D, b_major=1, ldc=D)
-            dbc = torch.empty(Hx * D, dtype=torch.float32, device=dev)
-            L.colsum(dz, T, Hx * D, Hx * D, dbc)
+            # dWcat[H*D, D] (+)= dz^T @ yb  (both MN-major, K = T)
+            L.gemm(dz, ctx["yb"], dWc, Hx * D, D, T, lda=Hx * D, a_major=1, ldb=D, b_major=1, ldc=D,
+                   epilogue=L.EPI_ACCUM if upper else L.EPI_STORE)
+            L.colsum(dz, T, Hx * D, Hx * D, dbc, accumulate=bool(upper))
             for h in range(Hx):
                 lin = self.medusa_head[h][0].linear
                 grads[lin.weight] = dWc[h * D:(h + 1) * D]
@@ -784,31 +852,66 @@ class HSTU(nn.Module):
             ids = torch.where(gl == 0, torch.zeros_like(ids), ids)
         uniq_ids, uniq_rows, n_uniq = parallel.cuda_segment_reduce(ids, rows)
         if sharded:
-            # one gradient row per fetched (cache) row, sent to the owners; the owner reduces over ranks (mean)
+            # one gradient row per cache row (fetched / projected rows)
             U = ctx["n_cache_rows"]
             g = torch.zeros((U, D), dtype=torch.float32, device=dev)
             L.call("b200rec_rows_to_dense", (uniq_ids - 1).contiguous().data_ptr(), uniq_rows.data_ptr(),
                    n_uniq.data_ptr(), n_rows, D, g.data_ptr(), 0, st)
+            info = ctx["cache_info"] or {}
+            if info.get("raw_a") is not None:
+                # projection tower backward: d_raw = g @ W (W [D, D_item] = [K, N] -> MN-major B),
+                # dW[D, D_item] = g^T @ raw (both MN-major, K = cache rows)
+                Di = self._item_embedding_dim
+                if act == torch.float32:
+                    g_a = g
+                else:
+                    g_a = torch.empty((U, D), dtype=act, device=dev)
+                    L.call("b200rec_cast", g.data_ptr(), g.numel(), g_a.data_ptr(), a_dt, st)
+                d_raw = torch.empty((U, Di), dtype=torch.float32, device=dev)
+                L.gemm(g_a, info["W_a"], d_raw, U, Di, D, lda=D, ldb=Di, b_major=1, ldc=Di)
+                dWt = torch.empty((D, Di), dtype=torch.float32, device=dev)
+                L.gemm(g_a, info["raw_a"], dWt, D, Di, U, lda=D, a_major=1, ldb=Di, b_major=1, ldc=Di)
+                grads[self.item_id_proj_tower.weight] = dWt
+                g = d_raw
             self.cache_grad = g
-            if ctx["push"]:
-                self.emb_grad = self.sharded_table.push_grads(g, scale=1.0 / self.sharded_table.W)
-            return grads
+            if self.sharded_table is not None:
+                if ctx["push"]:
+                    self.emb_grad = self.sharded_table.push_grads(g, scale=1.0 / self.sharded_table.W)
+                return grads
+            # replicated table behind a tower: cache row -> item id, untouched cache rows carry no gradient
+            touched = torch.zeros(U + 1, dtype=torch.bool, device=dev)
+            k = n_uniq.to(torch.int64)
+            sel = torch.arange(uniq_ids.numel(), device=dev) < k
+            touched[torch.where(sel, uniq_ids, torch.zeros_like(uniq_ids))] = True      # keys are cache row + 1
+            ids_g = torch.where(touched[1:], info["ids"], torch.zeros_like(info["ids"]))
+            uniq_ids, uniq_rows, n_uniq = parallel.cuda_segment_reduce(ids_g, g)
+            n_rows = U
         self.emb_grad = (uniq_ids, uniq_rows, n_uniq)
         if not self.sparse_embedding_grad:
             dense = torch.zeros_like(self.item_embedding.weight.data)
-            L.call("b200rec_rows_to_dense", uniq_ids.data_ptr(), uniq_rows.data_ptr(), n_uniq.data_ptr(), n_rows, D,
-                   dense.data_ptr(), 0, st)
+            L.call("b200rec_rows_to_dense", uniq_ids.data_ptr(), uniq_rows.data_ptr(), n_uniq.data_ptr(), n_rows,
+                   uniq_rows.shape[1], dense.data_ptr(), 0, st)
             grads[self.item_embedding.weight] = dense
         return grads
 
     # ------------------------------------------------------------------ eval (hstu.py:874-1021)
     @torch.no_grad()
     def compute_item_all(self):
+        """hstu.py:1018-1021: L2-normalised (projected) item table, fp32 [N, D]."""
         W = self.item_embedding.weight.data
-        N, D = W.shape
+        N = W.shape[0]
+        D = self._hstu_embedding_dim
         out = torch.empty((N, D), dtype=torch.float32, device=W.device)
         inv = torch.empty(N, dtype=torch.float32, device=W.device)
-        L.call("b200rec_gather_l2norm", None, W.data_ptr(), D, None, N, out.data_ptr(), L.F32, inv.data_ptr(), L.stream())
+        if not self._has_tower():
+            L.call("b200rec_gather_l2norm", None, W.data_ptr(), D, None, N, out.data_ptr(), L.F32, inv.data_ptr(), L.stream())
+            return out
+        step = 1 << 16                                   # project the table in slabs, normalise in place
+        for r0 in range(0, N, step):
+            r1 = min(N, r0 + step)
+            proj, _, _ = self._project_rows(W[r0:r1], fp32=True)
+            L.call("b200rec_gather_l2norm", None, proj.data_ptr(), D, None, r1 - r0, out[r0:r1].data_ptr(), L.F32,
+                   inv[r0:r1].data_ptr(), L.stream())
         return out
 
     @torch.no_grad()
@@ -828,6 +931,11 @@ class HSTU(nn.Module):
         if self.sharded_table is not None:
             uniq, inv = torch.unique(item_seq.reshape(-1), return_inverse=True)
             table, seq_idx = self.sharded_table.fetch(uniq), inv.view(B, Ls).contiguous()
+            if self._has_tower():
+                table = self._project_rows(table)[0]
+        elif self._has_tower():
+            table = self._project_rows(parallel.cuda_row_gather(table, item_seq.reshape(-1)))[0]
+            seq_idx = torch.arange(B * Ls, dtype=torch.int64, device=dev).view(B, Ls)
         L.call("b200rec_embed_tokens", table.data_ptr(), self.position_embedding.weight.data_ptr(),
                seq_idx.data_ptr(), tok_b.data_ptr(), tok_pos.data_ptr(), T, Ls, D, x.data_ptr(), st)
         y, _ = self._body_forward(x, w, seq_off, key_valid, B, T, Ls, Ls, False)

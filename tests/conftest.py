@@ -17,7 +17,8 @@ def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
 
 
-GOLDEN_CASES = ["nce_single", "nce_2attn", "prior_additive", "prior_mult", "prior_event_given", "nce_pred4"]
+GOLDEN_CASES = ["nce_single", "nce_2attn", "prior_additive", "prior_mult", "prior_event_given", "nce_pred4",
+                "tower_additive", "mult_2layers"]
 
 
 def load_golden(name):

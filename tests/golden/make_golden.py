@@ -27,6 +27,10 @@ CASES = {
     "prior_mult": ("D", dict(TINY)),
     "prior_event_given": ("C", dict(TINY, MAX_ITEM_LIST_LENGTH=16)),
     "nce_pred4": ("A2", dict(TINY, pred_len=4, eval_pred_len=4, medusa_num_layers=1, num_segment_head=2)),
+    # item_id_proj_tower (table width 24 -> HSTU width 32) under the additive prior heads
+    "tower_additive": ("B", dict(TINY, item_embedding_size=24)),
+    # weight-tied two-layer decode heads (`[ResBlock] * 2`, hstu.py:486-493)
+    "mult_2layers": ("D", dict(TINY, medusa_num_layers=2)),
 }
 TOPK = [1, 5, 10, 20]
 
@@ -85,5 +89,7 @@ def run_case(name, preset, over):
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
     for name, (preset, over) in CASES.items():
-        run_case(name, preset, over)
+        if not only or name in only:
+            run_case(name, preset, over)
