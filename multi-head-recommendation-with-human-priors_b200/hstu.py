@@ -71,10 +71,13 @@ class _Body(nn.Module):
 class _ResBlock(nn.Module):
     """Parameter holder for llm_heads.ResBlock (llm_heads.py:16-24): linear [D, D] + bias."""
 
-    def __init__(self, D):
+    def __init__(self, D, zero_init=True):
         super().__init__()
         self.linear = nn.Linear(D, D)
-        nn.init.zeros_(self.linear.weight)
+        if zero_init:
+            nn.init.zeros_(self.linear.weight)
+        else:                                   # llm_heads.py:24-25 (same RNG consumption as the reference)
+            nn.init.trunc_normal_(self.linear.weight, std=0.02)
 
 
 class _Job:
@@ -108,7 +111,10 @@ class HSTU(nn.Module):
         elif self.head_interaction == "additive":
             self.medusa_num_heads = self.num_segment_head + self.num_prior_head
         elif self.head_interaction == "hierarchical":
-            raise NotImplementedError("head_interaction='hierarchical' is not built in this round")
+            self.medusa_num_heads = self.num_segment_head * self.num_prior_head
+            for k in ("head_norm", "cat_bottleneck", "share_seg_weights", "segment_embed"):
+                if config.get(k, False):
+                    raise NotImplementedError(f"hierarchical heads with {k}=True are not built")
         else:
             raise ValueError(f'Unknown head_interaction: {config["head_interaction"]}')
         self.medusa_num_layers = config["medusa_num_layers"]
@@ -151,8 +157,17 @@ class HSTU(nn.Module):
             self.medusa_head = nn.ModuleList([nn.Identity() for _ in range(self.medusa_num_heads)])
             self.prior_loss_weight = [1 / self.num_prior_head] * self.num_prior_head
         else:
-            self.medusa_head = nn.ModuleList(
-                [nn.Sequential(*([_ResBlock(D)] * self.medusa_num_layers)) for _ in range(self.medusa_num_heads)])
+            if self.head_interaction == "hierarchical":
+                # hstu.py:443-483: per-category block, then per-(category, segment) block; distinct ResBlocks per layer
+                nl = self.medusa_num_layers
+                self.medusa_cat_head = nn.ModuleList(
+                    [nn.Sequential(*[_ResBlock(D, zero_init=False) for _ in range(nl)]) for _ in range(self.num_prior_head)])
+                self.medusa_seg_head = nn.ModuleList(
+                    [nn.ModuleList([nn.Sequential(*[_ResBlock(D, zero_init=False) for _ in range(nl)])
+                                    for _ in range(self.num_segment_head)]) for _ in range(self.num_prior_head)])
+            else:
+                self.medusa_head = nn.ModuleList(
+                    [nn.Sequential(*([_ResBlock(D)] * self.medusa_num_layers)) for _ in range(self.medusa_num_heads)])
             self.weighted_prior_loss = config["weighted_prior_loss"]
             if self.loss != "prior":
                 assert self.num_prior_head == 1, "Only prior loss is allowed for num_prior_head > 1"
@@ -243,7 +258,7 @@ class HSTU(nn.Module):
             for i, blk in enumerate(self._hstu._attention_layers):
                 w[f"uvqk{i}"] = self._shadow_get(blk._uvqk, f"uvqk{i}", (D, 4 * D))
                 w[f"o{i}"] = self._shadow_get(blk._o.weight, f"o{i}", (D, D))
-        if self.medusa_num_layers > 0:
+        if self.medusa_num_layers > 0 and self.head_interaction != "hierarchical":
             H = self.medusa_num_heads
             dev = self.item_embedding.weight.device
             if act == torch.float32:
@@ -520,6 +535,8 @@ class HSTU(nn.Module):
         self._heads_upper = []
         if self.medusa_num_layers == 0:
             return y.view(rows, 1, D), None, None
+        if self.head_interaction == "hierarchical":
+            return self._hier_forward(y, rows), None, None
         if act == torch.float32:
             yb = y
         else:
@@ -549,6 +566,75 @@ class HSTU(nn.Module):
             self._heads_upper.append((hin, z2))
             hd = hd2
         return hd, z, yb
+
+    # ---- hierarchical heads (hstu.py:652-663): head[s*C + c] = seg[c][s](cat[c](y)), every block a chain of
+    # ResBlocks.  A non-shipped variant of the HSTU scripts: one tcgen05 GEMM (ResBlock epilogue) per block
+    # application, recorded on a tape that the backward walks in reverse.
+    def _hier_apply(self, lin, x, out=None, ld_out=None, head=None):
+        rows, D = x.shape
+        act, dev = self._act(), x.device
+        if act == torch.float32:
+            xa, Wa = x, lin.weight.data
+        else:
+            xa = torch.empty((rows, D), dtype=act, device=dev)
+            L.call("b200rec_cast", x.data_ptr(), x.numel(), xa.data_ptr(), L.dt(act), L.stream())
+            Wa = self._shadow_get(lin.weight, f"hier{id(lin)}", (D, D))
+        if out is None:
+            out, ld_out = torch.empty((rows, D), dtype=torch.float32, device=dev), D
+        z = torch.empty((rows, D), dtype=act, device=dev)
+        L.gemm(xa, Wa, out, rows, D, D, lda=D, ldb=D, ldc=ld_out, epilogue=L.EPI_RESBLOCK, bias=lin.bias.data, resid=x,
+               ldr=D, C2=z, ldc2=D, n_split=D)
+        self._hier_tape.append((lin, x, xa, Wa, z, out, head))
+        return out
+
+    def _hier_forward(self, y, rows):
+        D, S, C = self._hstu_embedding_dim, self.num_segment_head, self.num_prior_head
+        H = S * C
+        self._hier_tape = []
+        hd = torch.empty((rows, H, D), dtype=torch.float32, device=y.device)
+        hd2 = hd.view(rows, H * D)
+        for c in range(C):
+            x = y
+            for blk in self.medusa_cat_head[c]:
+                x = self._hier_apply(blk.linear, x)
+            for s_ in range(S):
+                xs = x
+                blocks = list(self.medusa_seg_head[c][s_])
+                for blk in blocks[:-1]:
+                    xs = self._hier_apply(blk.linear, xs)
+                h = s_ * C + c
+                self._hier_apply(blocks[-1].linear, xs, out=hd2[:, h * D:(h + 1) * D], ld_out=H * D, head=h)
+        return hd
+
+    def _hier_backward(self, d_hd, tape, y, grads):
+        """d_hd fp32 [rows, H, D] -> dy fp32 [rows, D]; fills grads of every ResBlock on the tape."""
+        rows, D = y.shape
+        H = self.num_segment_head * self.num_prior_head
+        act, a_dt, st, dev = self._act(), L.dt(self._act()), L.stream(), y.device
+        d_hd2 = d_hd.view(rows, H * D)
+        gmap = {}      # data_ptr of a tape tensor -> accumulated fp32 gradient
+        for lin, x, xa, Wa, z, out, head in reversed(tape):
+            if head is None:
+                d_out = gmap.pop(out.data_ptr())
+            else:      # the last block of head `head`: its slice of d_hd
+                d_out = d_hd2[:, head * D:(head + 1) * D].contiguous()
+            dz = torch.empty((rows, D), dtype=act, device=dev)
+            d_in = torch.empty((rows, D), dtype=torch.float32, device=dev)
+            L.call("b200rec_resblock_bwd", d_out.data_ptr(), z.data_ptr(), a_dt, rows, 1, D, dz.data_ptr(),
+                   d_in.data_ptr(), st)                                   # dz = d_out * silu'(z) ; d_in = d_out
+            # d_in += dz @ W   (W [Dout, Din] = [K, N] -> MN-major B)
+            L.gemm(dz, Wa, d_in, rows, D, D, lda=D, ldb=D, b_major=1, ldc=D, epilogue=L.EPI_ACCUM)
+            dW = torch.empty((D, D), dtype=torch.float32, device=dev)
+            L.gemm(dz, xa, dW, D, D, rows, lda=D, a_major=1, ldb=D, b_major=1, ldc=D)
+            db = torch.empty(D, dtype=torch.float32, device=dev)
+            L.colsum(dz, rows, D, D, db)
+            grads[lin.weight], grads[lin.bias] = dW, db
+            key = x.data_ptr()
+            if key in gmap:
+                gmap[key].add_(d_in)
+            else:
+                gmap[key] = d_in
+        return gmap.pop(y.data_ptr())
 
     # ------------------------------------------------------------------ training (hstu.py:631-872)
     def forward(self, interaction, n_tokens=None, prepared=None):
@@ -716,7 +802,7 @@ class HSTU(nn.Module):
         loss = total * half
         if need_grad:
             ctx = dict(B=B, LP=LP, T=T, tok_b=tok_b, tok_pos=tok_pos, seq_off=seq_off, key_valid=key_valid,
-                       tok_index=tok_index, w=w, saved=saved, hd=hd, z=z, yb=yb, heads_upper=list(self._heads_upper), qhat=qhat, qinv=qinv, that=that,
+                       tok_index=tok_index, w=w, saved=saved, hd=hd, z=z, yb=yb, heads_upper=list(self._heads_upper), hier_tape=getattr(self, "_hier_tape", None), y=y, qhat=qhat, qinv=qinv, that=that,
                        tinv=tinv, nhat=nhat, ninv=ninv, neg_ids=neg_ids, job_out=job_out, scale=scale, half=half,
                        items=items, mask=m, n_neg=n_neg, ld_neg=ld_neg, Hx=Hx, used_sets=used_sets,
                        gl_items=gl_items, gl_neg_ids=gl_neg_ids, uniq_rows_ids=uniq_rows_ids,
@@ -783,7 +869,9 @@ class HSTU(nn.Module):
         L.call("b200rec_l2norm_bwd", ctx["qhat"].data_ptr(), a_dt, ctx["qinv"].data_ptr(), dqhat.data_ptr(), T * Hx, D,
                d_hd.data_ptr(), 0, st)
         dy = torch.empty((T, D), dtype=torch.float32, device=dev)
-        if self.medusa_num_layers > 0:
+        if self.medusa_num_layers > 0 and self.head_interaction == "hierarchical":
+            dy = self._hier_backward(d_hd, ctx["hier_tape"], ctx["y"], grads)
+        elif self.medusa_num_layers > 0:
             dWc = torch.empty((Hx * D, D), dtype=torch.float32, device=dev)
             dbc = torch.empty(Hx * D, dtype=torch.float32, device=dev)
             upper = ctx["heads_upper"]

@@ -132,7 +132,9 @@ class OracleHSTU:
             self.prior_w = [1.0 / self.C] * self.C
         self.int_to_category = cfg["int_to_category"]
         if self.inter == "hierarchical":
-            raise NotImplementedError("oracle covers multiplicative/additive heads")
+            for k in ("head_norm", "cat_bottleneck", "share_seg_weights", "segment_embed"):
+                if cfg_get(cfg, k, False):
+                    raise NotImplementedError(f"oracle covers hierarchical heads with {k}=False")
 
     # ---- pieces -----------------------------------------------------------------
     def embed(self, ids):
@@ -152,6 +154,15 @@ class OracleHSTU:
     def heads(self, y):
         """y [..., D] -> [H, ..., D]; head h = x + silu(W_h x + b_h), weight-tied when
         medusa_num_layers > 1 (hstu.py:486-493, llm_heads.py:26-40)."""
+        if self.inter == "hierarchical":                                          # hstu.py:652-663, 915-925
+            def chain(x, prefix):
+                for l in range(self.mlayers):                                     # distinct ResBlocks per layer (:460,468)
+                    W, b = self.p[f"{prefix}.{l}.linear.weight"], self.p[f"{prefix}.{l}.linear.bias"]
+                    x = x + F.silu(x @ W.t() + b)
+                return x
+            cat = [chain(y, f"medusa_cat_head.{c}") for c in range(self.C)]
+            outs = [chain(cat[c], f"medusa_seg_head.{c}.{s}") for s in range(self.S) for c in range(self.C)]
+            return torch.stack(outs, dim=0)                                       # h = s*C + c
         outs = []
         for h in range(self.H):
             z = y

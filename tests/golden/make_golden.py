@@ -31,6 +31,9 @@ CASES = {
     "tower_additive": ("B", dict(TINY, item_embedding_size=24)),
     # weight-tied two-layer decode heads (`[ResBlock] * 2`, hstu.py:486-493)
     "mult_2layers": ("D", dict(TINY, medusa_num_layers=2)),
+    # hierarchical heads seg[c][s](cat[c](x)) (hstu.py:443-483, 652-663), 2 segments x 7 categories, 2 layers each
+    "hier_2x7": ("D", dict(TINY, head_interaction="hierarchical", num_segment_head=2, pred_len=4, eval_pred_len=4,
+                           medusa_num_layers=2)),
 }
 TOPK = [1, 5, 10, 20]
 
