@@ -310,6 +310,15 @@ def main():
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
+    eval_res = None
+    if not args.no_eval:
+        # every rank takes part: with a row-sharded table the eval path exchanges users and merges top-K lists
+        try:
+            eval_res = eval_bench(cfg, model, item_tags, dev, args.eval_users, rank, world)
+        except Exception as ex:  # eval is a secondary number; never lose the train line
+            if world > 1:
+                raise
+            eval_res = {"error": repr(ex)[:200]}
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -344,11 +353,8 @@ def main():
     })
     if args.layers:
         line["invalid"] = "n_layers overridden (debug run)"
-    if not args.no_eval:
-        try:
-            line["eval"] = eval_bench(cfg, model, item_tags, dev, args.eval_users)
-        except Exception as ex:  # eval is a secondary number; never lose the train line
-            line["eval"] = {"error": repr(ex)[:200]}
+    if eval_res is not None:
+        line["eval"] = eval_res
     if not args.no_cpu:
         r = cpu_reference_run(cfg, args.cpu_batch, args.cpu_steps)
         line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -357,14 +363,18 @@ def main():
         torch.distributed.destroy_process_group()
 
 
-def eval_bench(cfg, model, item_tags, dev, users):
-    """Secondary metric: eval users/s = predict + masks + cross-head merge + top-200 + hit matrix."""
+def eval_bench(cfg, model, item_tags, dev, users, rank=0, world=1):
+    """Secondary metric: eval users/s = predict + masks + cross-head merge + top-200 + hit matrix.  `users` per
+    rank; with a row-sharded table every rank scores all ranks' users against its rows and the per-shard top-K
+    lists are merged."""
     from b200rec import synth
     from b200rec.evaluator import Collector
-    ev = synth.make_eval_batch(cfg, seed=3, batch_size=users, item_tags=item_tags)
+    ev = synth.make_eval_batch(cfg, seed=3 + rank, batch_size=users, item_tags=item_tags)
     C = cfg["eval_num_cats"]
     tags = item_tags.t().contiguous().to(dev) if cfg["category_by"] == "item" else \
         torch.ones(C, cfg["item_num"], dtype=torch.bool, device=dev)
+    if model.sharded_table is not None:
+        tags = tags[:, rank::world].contiguous()
     feat = model.compute_item_all()
     seq, tt = ev["item_seq"].to(dev), ev["target_tags"].to(dev)
     hist = (ev["history_index"][0].to(dev), ev["history_index"][1].to(dev))
@@ -392,8 +402,14 @@ def eval_bench(cfg, model, item_tags, dev, users):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
-    return {"metric": "eval_users_per_sec", "value": users / (ms / 1e3), "unit": "users/s", "users_per_batch": users,
-            "items": cfg["item_num"], "heads": model.medusa_num_heads, "K": max(cfg["topk"]), "ms_per_batch": ms}
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t[0])
+    return {"metric": "eval_users_per_sec", "value": users * world / (ms / 1e3), "unit": "users/s",
+            "users_per_batch": users * world, "items": cfg["item_num"], "heads": model.medusa_num_heads,
+            "K": max(cfg["topk"]), "ms_per_batch": ms,
+            "sharding": "item rows id % W, cross-GPU top-K merge" if model.sharded_table is not None else "none"}
 
 
 if __name__ == "__main__":
