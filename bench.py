@@ -255,11 +255,16 @@ def main():
     for i in range(max(args.warmup, n_batches if use_graph else 0)):   # graph mode: capture every bucket first
         step(dev_batches[i % n_batches], i % n_batches)
     barrier()
-    if args.profile and rank == 0:
+    if (args.profile or os.environ.get("B200REC_PROFILE_STEP")) and (rank == 0 or world > 1):
         from torch.profiler import profile, ProfilerActivity
-        with profile(activities=[ProfilerActivity.CUDA]) as prof:
-            step(dev_batches[0], 0)
+        acts = [ProfilerActivity.CUDA] + ([ProfilerActivity.CPU] if os.environ.get("B200REC_PROFILE_STEP") else [])
+        with profile(activities=acts) as prof:
+            for i in range(2):
+                step(dev_batches[i], i)
             torch.cuda.synchronize()
+        if rank == 0 and os.environ.get("B200REC_PROFILE_STEP"):
+            prof.export_chrome_trace("gpurun_out/trace_rank0.json")
+    if args.profile and rank == 0:
         print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=60),
               file=sys.stderr)
     sampler = ClockSampler(local_rank) if rank == 0 else None

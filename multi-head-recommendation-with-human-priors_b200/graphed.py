@@ -130,9 +130,8 @@ class GraphedShardedStep(object):
     def _fill(self, batch):
         for s, t in zip(self.static, batch):
             s.copy_(t, non_blocking=True)
-        p = self.model.prepare_rows(self.static[0], self.static[1], static=True)
-        U = p["n_rows"]
-        self.prep["W"][:U].copy_(p["W"])
+        p = self.model.prepare_rows(self.static[0], self.static[1], static=True, cache_out=self.prep["W"])
+        U = p["n_rows"]                                   # rows were fetched straight into the static cache
         for k in ("items_idx", "neg_idx", "gl_items", "gl_neg"):
             self.prep[k].copy_(p[k])
         return U
@@ -186,8 +185,14 @@ class GraphedShardedStep(object):
         for p, v in zip(self.dense, self.views):
             p.grad = v
         model.item_embedding.weight.grad = None
-        if W > 1:
-            self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.SUM, group=self.group)
+        # gradient rows to their owners first, then the dense all-reduce runs on the NCCL stream WHILE the owner
+        # reduces its rows and updates its table shard (HBM-bound); the dense update waits for the all-reduce
         model.emb_grad = model.sharded_table.push_grads(cache_grad[:U], scale=1.0)
-        self.opt.step(grad_scale=1.0 / W)
+        work = None
+        if W > 1:
+            work = self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self.opt.step(grad_scale=1.0 / W, dense=False)
+        if work is not None:
+            work.wait()
+        self.opt.step(grad_scale=1.0 / W, rows=False)
         return out

@@ -338,7 +338,7 @@ class HSTU(nn.Module):
         L.gemm(raw_a, W_a, out, R, D, Di, lda=Di, ldb=Di, ldc=D)
         return out, raw_a, W_a
 
-    def _table_rows(self, items, neg_ids):
+    def _table_rows(self, items, neg_ids, cache_out=None):
         """Returns (table, item_index [B, LP], neg_index [sets, n_neg], cache info or None): the tensor the
         gather kernels read and the row indices into it.
           replicated table, no tower: the table itself and the ids (info None);
@@ -353,7 +353,7 @@ class HSTU(nn.Module):
         info = dict(raw_a=None, W_a=None)
         if self.sharded_table is not None:
             uniq, inv = torch.unique(all_ids, return_inverse=True)
-            cache = self.sharded_table.fetch(uniq)
+            cache = self.sharded_table.fetch(uniq, out=None if tower else cache_out)
             info["ids"] = uniq
         else:
             cache = parallel.cuda_row_gather(self.item_embedding.weight.data, all_ids)
@@ -363,7 +363,7 @@ class HSTU(nn.Module):
             cache, info["raw_a"], info["W_a"] = self._project_rows(cache)
         return cache, inv[:B * LP].view(B, LP).contiguous(), inv[B * LP:].view(neg_ids.shape).contiguous(), info
 
-    def prepare_rows(self, items, neg_items, static=False):
+    def prepare_rows(self, items, neg_items, static=False, cache_out=None):
         """Everything of a training step that needs collectives or data-dependent shapes, so it can run
         eagerly in front of a captured graph: the dummy row of static-shape mode, the cross-rank negative
         id all-gather (hstu.py:673,755) and, for a row-sharded table, the all-to-all fetch of the unique
@@ -376,7 +376,7 @@ class HSTU(nn.Module):
         n_sets = neg_items.shape[1]
         n_neg = neg_items.shape[0] * neg_items.shape[2]
         neg_ids = neg_items.permute(1, 0, 2).contiguous().view(n_sets, n_neg)   # set-major id lists
-        W, items_idx, neg_idx, info = self._table_rows(items, neg_ids)
+        W, items_idx, neg_idx, info = self._table_rows(items, neg_ids, cache_out)
         return dict(W=W, items_idx=items_idx, neg_idx=neg_idx, gl_items=items, gl_neg=neg_ids,
                     cached=info is not None, n_rows=(W.shape[0] if info is not None else None), info=info)
 

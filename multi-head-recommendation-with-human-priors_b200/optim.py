@@ -26,6 +26,7 @@ class FusedAdamW(object):
         self._table_key = None
         self._table = self._blocks = None
         self._keepalive = []
+        self._half_done = False
 
     def _st(self, p):
         s = self.state.get(p)
@@ -71,8 +72,14 @@ class FusedAdamW(object):
         return self._table, self._blocks
 
     @torch.no_grad()
-    def step(self, grad_scale=1.0):
-        self.step_count += 1
+    def step(self, grad_scale=1.0, rows=True, dense=True):
+        """rows / dense select the item-table pass and the multi-tensor pass; a caller that overlaps the dense
+        all-reduce with the table update calls step(dense=False) then step(rows=False) (ONE optimizer step: the
+        counter advances on the first of the two calls)."""
+        first_half = rows or not self._half_done
+        if first_half:
+            self.step_count += 1
+        self._half_done = rows and not dense
         g = self.param_groups[0]
         lr, (b1, b2), eps, wd = g["lr"], g["betas"], g["eps"], g["weight_decay"]
         st = L.stream()
@@ -81,11 +88,14 @@ class FusedAdamW(object):
         if self.device_step:
             if self._coef is None:
                 self._coef = torch.tensor([lr, 0.0, 0.0, float(self.step_count - 1)], dtype=torch.float32, device=emb.device)
-            L.call("b200rec_adamw_tick", self._coef.data_ptr(), b1, b2, st)
+            if first_half:
+                L.call("b200rec_adamw_tick", self._coef.data_ptr(), b1, b2, st)
             coef = self._coef.data_ptr()
-        dense = []
+        dense_list = []
         for p in self.model.parameters():
             if p is emb and p.grad is None and self.model.emb_grad is not None:
+                if not rows:
+                    continue
                 m, v = self._st(p)
                 uniq_ids, uniq_rows, n_uniq = self.model.emb_grad
                 N, D = p.shape
@@ -99,8 +109,9 @@ class FusedAdamW(object):
                 continue
             if p.grad.dtype != torch.float32 or not p.grad.is_contiguous():
                 p.grad = p.grad.float().contiguous()
-            dense.append(p)
-        if dense:
+            dense_list.append(p)
+        if dense_list and dense:
+            dense = dense_list
             table, blocks = self._dense_table(dense)
             L.call("b200rec_adamw_multi", table.data_ptr(), blocks.data_ptr(), blocks.numel() // 2, lr, b1, b2, eps, wd,
                    self.step_count, grad_scale, coef, st)

@@ -122,7 +122,8 @@ class ShardedTable(object):
     def shard_of(full_weight, W, rank):
         return full_weight[rank::W].contiguous()
 
-    def fetch(self, ids):
+    def fetch(self, ids, out=None):
+        """Rows of `ids` (deduplicated by the caller) in the order of `ids`; written into out[:len(ids)] if given."""
         W = self.W
         owner = ids % W
         order = torch.argsort(owner, stable=True)
@@ -138,7 +139,7 @@ class ShardedTable(object):
         local_idx = torch.div(req, W, rounding_mode="floor")
         rows = self.row_gather(self.weight, local_idx)
         back = _a2a(rows, rc, sc, self.group) if W > 1 else rows
-        out = torch.empty_like(back)
+        out = torch.empty_like(back) if out is None else out[:back.shape[0]]
         out[order] = back
         self.plan = (order, sc, rc, local_idx)
         return out
