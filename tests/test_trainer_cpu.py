@@ -1,0 +1,71 @@
+"""Host logic of the train/eval harness (b200rec.trainer): LR schedules against torch's LambdaLR driven by the
+reference formulas (utils/lr_scheduler.py:44-116), early stopping and valid-score selection (utils/utils.py:60-122)."""
+import math
+
+import torch
+
+from b200rec import trainer as T
+
+
+def _lambda_lr_values(fn, base_lr, steps):
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([p], lr=base_lr)
+    sch = torch.optim.lr_scheduler.LambdaLR(opt, fn)
+    vals = []
+    for _ in range(steps):
+        vals.append(opt.param_groups[0]["lr"])
+        opt.step()
+        sch.step()
+    return vals
+
+
+def test_schedules_match_lambda_lr():
+    warm, total, base = 12.5, 100, 3e-3
+
+    def ref_cos(step):                                   # lr_scheduler.py:105-113
+        if step < warm:
+            return float(step) / float(max(1, warm))
+        progress = float(step - warm) / float(max(1, total - warm))
+        return max(0.0, 0.5 * (1.0 + math.cos(math.pi * 0.5 * 2.0 * progress)))
+
+    def ref_lin(step):                                   # lr_scheduler.py:66-74
+        if step < warm:
+            return float(step) / float(max(1, warm))
+        return max(0.0, float(total - step) / float(max(1, total - warm)))
+
+    for ref, mine in ((ref_cos, T.cosine_schedule_with_warmup), (ref_lin, T.linear_schedule_with_warmup)):
+        want = _lambda_lr_values(ref, base, total)
+        got = [base * mine(s, warm, total) for s in range(total)]
+        assert max(abs(a - b) for a, b in zip(want, got)) < 1e-12
+
+
+def test_trainer_lr_at_uses_warmup_fraction():
+    cfg = dict(optim_args=dict(learning_rate=1e-2, weight_decay=0.0), scheduler_args=dict(type="cosine", warmup=0.1),
+               total_iters=50, metrics_pred_len_list=[0], eval_pred_len=1)
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(2))
+            self.sharded_table = None
+
+    tr = T.Trainer(cfg, M(), optimizer=object(), use_graph=False)
+    assert tr.lr_at(0) == 0.0 and abs(tr.lr_at(5) - 1e-2) < 1e-15
+    assert abs(tr.lr_at(50) - 0.0) < 1e-12 and tr.lr_at(20) < tr.lr_at(10)
+
+
+def test_early_stopping_contract():
+    best, cur, stop, upd = T.early_stopping(0.5, -float("inf"), 0, max_step=1, bigger=True)
+    assert (best, cur, stop, upd) == (0.5, 0, False, True)
+    best, cur, stop, upd = T.early_stopping(0.4, best, cur, max_step=1, bigger=True)
+    assert (best, cur, stop, upd) == (0.5, 1, False, False)
+    best, cur, stop, upd = T.early_stopping(0.3, best, cur, max_step=1, bigger=True)
+    assert stop and not upd and cur == 2
+    best, cur, stop, upd = T.early_stopping(0.2, 0.3, 0, max_step=3, bigger=False)
+    assert upd and best == 0.2
+
+
+def test_calculate_valid_score_picks_last_offset():
+    res = {"pred_0": {"recall@10": 0.1, "ndcg@10": 0.05}, "pred_3": {"recall@10": 0.4, "ndcg@10": 0.2}}
+    assert T.calculate_valid_score(res, 4, "NDCG@10") == 0.2
+    assert T.calculate_valid_score(res, 4, None) == 0.4
