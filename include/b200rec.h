@@ -285,6 +285,36 @@ int b200rec_apply_score_masks(float* scores, int64_t ld_scores, int B, int H, in
 int b200rec_hit_matrix(const int64_t* topk_idx, const int64_t* positive_i, int B, int K, int Pe,
                        const int32_t* pred_list_host, int n_p, int32_t* out, void* stream);
 
+/* ------------------------------------------------------------------ batch construction (§8 f N2)
+ * One kernel per batch instead of the reference's per-sample Python in DataLoader workers
+ * (data/dataset/trainset.py:70-177, evalset.py:81-155, collate_fn.py:59-90).
+ * Interaction data in CSR form: user_seq[user_off[u] .. user_off[u+1]) = item ids of user u (event_seq: the
+ * parallel event types, nullable), train_len[u] = length of the training prefix, samples = (uid, context_end)
+ * pairs (dataload.valid_sample_locations), batch_index[B] picks the samples of this batch.
+ * Train row: [pad x (L-ctx) | seq[start:end+pred] | pad x (P-pred)]; pads are distinct random items outside the
+ * row (pad_random) or 0; mask 1 on real positions; neg_items[b, s, :] = n_neg DISTINCT items drawn uniformly
+ * from pool s (category pools cat_items[cat_off[s]..cat_off[s+1]) for s < n_pools, then the global pool
+ * [1, item_num)), none of them in the padded row; with probability neg_sample_mix_ratio a category set draws
+ * from the global pool (trainset.py:72-78).  tags[b, pos, c] = item_tags[item, c] (u8 [N, C], pads included,
+ * trainset.py:165-167) or, when item_tags is NULL and event_seq is not, the one-hot event type at real
+ * positions (trainset.py:147-153); tags may be NULL.  Randomness: Philox4x32-10 keyed on (seed, step, row, slot). */
+int b200rec_build_train_batch(const int64_t* user_seq, const int64_t* user_off, const int32_t* train_len,
+                              const int32_t* event_seq, const int64_t* sample_uid, const int32_t* sample_end,
+                              const int64_t* batch_index, int B, int L, int P, int pad_random, int64_t item_num,
+                              int n_sets, int n_neg, const int64_t* cat_items, const int64_t* cat_off, int n_pools,
+                              float neg_sample_mix_ratio, const uint8_t* item_tags, int C, uint64_t seed,
+                              uint64_t step, int64_t* items, int64_t* neg_items, int64_t* mask, int64_t* tags,
+                              void* stream);
+/* Eval rows: phase 0 (valid) history = seq[:train_len], targets = the next Pe items; phase 1 (test) history =
+ * seq[:-Pe], targets = the last Pe.  item_seq[b] = last L history items left-padded with 0; (hist_u, hist_i) =
+ * (row, item) for EVERY history item, written at hist_off[b] (host-side prefix sum of the history lengths);
+ * target_tags like `tags` above (nullable). */
+int b200rec_build_eval_batch(const int64_t* user_seq, const int64_t* user_off, const int32_t* train_len,
+                             const int32_t* event_seq, const int64_t* uids, int B, int L, int Pe, int phase,
+                             const uint8_t* item_tags, int C, const int64_t* hist_off, int64_t* item_seq,
+                             int64_t* item_target, int64_t* target_tags, int64_t* hist_u, int64_t* hist_i,
+                             void* stream);
+
 /* ------------------------------------------------------------------ optimizer (§8 f N1)
  * torch.optim.AdamW semantics (trainer.py:296-299), fused single pass, fp32 state. */
 /* coef_dev (nullable): device fp32[4] = {lr, 1-beta1^t, sqrt(1-beta2^t), t} overriding lr / step, advanced
