@@ -32,8 +32,8 @@ WORKLOADS = {"A": "HSTU-Pixel8M-base-small (A)", "A2": "HSTU-Pixel8M-base-small 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--config", default="B")
     ap.add_argument("--impl", default="b200rec", choices=["b200rec", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])

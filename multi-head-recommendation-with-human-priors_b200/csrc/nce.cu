@@ -34,23 +34,46 @@ __device__ __forceinline__ void stats_merge2(Stats& a, const Stats& b) {   // lo
   a.gt += b.gt;
   a.cnt += b.cnt;
 }
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Block reduction of log2-domain Stats: maximum first, ONE rescale per partial, then plain fixed-tree sums
+// (a merge-by-merge tree spends ~25 instructions and 2 MUFU per step; this is ~1/3 of the instructions).
 __device__ Stats block_stats2(Stats v, Stats* red) {
-  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float m = v.m;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const float f = v.m == -INFINITY ? 0.f : ex2_ftz(v.m - m);
+  float s = v.s * f, w = v.w * f;
+  int gt = v.gt, cnt = v.cnt;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    Stats t;
-    t.m = __shfl_xor_sync(0xffffffffu, v.m, o);
-    t.s = __shfl_xor_sync(0xffffffffu, v.s, o);
-    t.w = __shfl_xor_sync(0xffffffffu, v.w, o);
-    t.gt = __shfl_xor_sync(0xffffffffu, v.gt, o);
-    t.cnt = __shfl_xor_sync(0xffffffffu, v.cnt, o);
-    if (lane & o) { Stats u = t; stats_merge2(u, v); v = u; } else { stats_merge2(v, t); }
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    w += __shfl_xor_sync(0xffffffffu, w, o);
+    gt += __shfl_xor_sync(0xffffffffu, gt, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   }
   __syncthreads();
-  if (lane == 0) red[wid] = v;
+  if (lane == 0) {
+    Stats r;
+    r.m = m; r.s = s; r.w = w; r.gt = gt; r.cnt = cnt;
+    red[wid] = r;
+  }
   __syncthreads();
-  Stats r = red[0];
-  for (int i = 1; i < nw; ++i) stats_merge2(r, red[i]);
+  float M = red[0].m;
+  for (int i = 1; i < nw; ++i) M = fmaxf(M, red[i].m);
+  Stats r;
+  r.m = M; r.s = 0.f; r.w = 0.f; r.gt = 0; r.cnt = 0;
+  for (int i = 0; i < nw; ++i) {
+    const float fi = red[i].m == -INFINITY ? 0.f : ex2_ftz(red[i].m - M);
+    r.s = fmaf(red[i].s, fi, r.s);
+    r.w = fmaf(red[i].w, fi, r.w);
+    r.gt += red[i].gt;
+    r.cnt += red[i].cnt;
+  }
   return r;
 }
 
@@ -274,7 +297,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <typename TA>
+template <typename TA, bool FULL>   // FULL: n_neg == 8192 exactly (every thread owns 8 vectors, no range predicates)
 __global__ void __launch_bounds__(256, 4)
 nce_loss_fwd_reg_kernel(const float* __restrict__ logits, int64_t ld_logits, int n_neg,
                         const uint32_t* __restrict__ same_bits, const uint8_t* __restrict__ row_any,
@@ -331,7 +354,7 @@ nce_loss_fwd_reg_kernel(const float* __restrict__ logits, int64_t ld_logits, int
 #pragma unroll
   for (int k = 0; k < NCE_RV; ++k) {
     int v = tid + k * 256;
-    if (v < n_vec) {
+    if (FULL || v < n_vec) {
       load4<float>(logits + (int64_t)t * ld_logits + v * 4, z[k]);
 #pragma unroll
       for (int e = 0; e < 4; ++e) mraw = fmaxf(mraw, z[k][e]);
@@ -350,7 +373,7 @@ nce_loss_fwd_reg_kernel(const float* __restrict__ logits, int64_t ld_logits, int
 #pragma unroll
     for (int k = 0; k < NCE_RV; ++k) {
       int v = tid + k * 256;
-      if (v < n_vec) {
+      if (FULL || v < n_vec) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float raw = z[k][e];
@@ -367,7 +390,7 @@ nce_loss_fwd_reg_kernel(const float* __restrict__ logits, int64_t ld_logits, int
 #pragma unroll
     for (int k = 0; k < NCE_RV; ++k) {
       int v = tid + k * 256;
-      if (v < n_vec) {
+      if (FULL || v < n_vec) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           z[k][e] *= tau2;
@@ -391,7 +414,7 @@ nce_loss_fwd_reg_kernel(const float* __restrict__ logits, int64_t ld_logits, int
 #pragma unroll
     for (int k = 0; k < NCE_RV; ++k) {
       int v = tid + k * 256;
-      if (v < n_vec) {
+      if (FULL || v < n_vec) {
         uint32_t wbits = bits[(v * 4) >> 5] >> ((v * 4) & 31);
 #pragma unroll
         for (int e = 0; e < 4; ++e)
@@ -403,7 +426,7 @@ nce_loss_fwd_reg_kernel(const float* __restrict__ logits, int64_t ld_logits, int
 #pragma unroll
     for (int k = 0; k < NCE_RV; ++k) {
       int v = tid + k * 256;
-      if (v < n_vec) {
+      if (FULL || v < n_vec) {
         uint32_t wbits = bits[(v * 4) >> 5] >> ((v * 4) & 31);
 #pragma unroll
         for (int e = 0; e < 4; ++e)
@@ -465,7 +488,7 @@ nce_loss_fwd_reg_kernel(const float* __restrict__ logits, int64_t ld_logits, int
 #pragma unroll
     for (int k = 0; k < NCE_RV; ++k) {
       int v = tid + k * 256;
-      if (v < n_vec) {
+      if (FULL || v < n_vec) {
         float g[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) g[e] = f * z[k][e];
@@ -477,7 +500,7 @@ nce_loss_fwd_reg_kernel(const float* __restrict__ logits, int64_t ld_logits, int
 #pragma unroll
   for (int k = 0; k < NCE_RV; ++k) {
     int v = tid + k * 256;
-    if (v < n_vec) {
+    if (FULL || v < n_vec) {
       float g[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) g[e] = a_common * exp2f(z[k][e] - all.m);
@@ -511,9 +534,14 @@ int b200rec_nce_loss_fwd(const float* logits, int64_t ld_logits, int n_neg, cons
       nce_pos_kernel<TA><<<ceil_div_i((int64_t)T * P, 8), 256, 0, (cudaStream_t)stream>>>(
           (const TA*)q_hat, ldq, (const TA*)t_hat, D / 4, tok_b, tok_pos, T, LP, P, p_mask, tok_ok, tok_ok_ld,
           tok_ok_col, pos_ws);
-      nce_loss_fwd_reg_kernel<TA><<<T, 256, 0, (cudaStream_t)stream>>>(
-          logits, ld_logits, n_neg, same_bits, row_any, pos_ws, tok_b, tok_pos, LP, P, coef, logit_scale, loss, g0,
-          dscale, rank0, nvalid, (TA*)G, ldg);
+      if (n_neg == NCE_RV * 256 * 4)
+        nce_loss_fwd_reg_kernel<TA, true><<<T, 256, 0, (cudaStream_t)stream>>>(
+            logits, ld_logits, n_neg, same_bits, row_any, pos_ws, tok_b, tok_pos, LP, P, coef, logit_scale, loss, g0,
+            dscale, rank0, nvalid, (TA*)G, ldg);
+      else
+        nce_loss_fwd_reg_kernel<TA, false><<<T, 256, 0, (cudaStream_t)stream>>>(
+            logits, ld_logits, n_neg, same_bits, row_any, pos_ws, tok_b, tok_pos, LP, P, coef, logit_scale, loss, g0,
+            dscale, rank0, nvalid, (TA*)G, ldg);
     });
     B200_LAUNCH_OK();
     return 0;
