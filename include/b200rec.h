@@ -270,8 +270,9 @@ int b200rec_score_mask_topk(const float* scores, int64_t ld_scores, int B, int H
                             int64_t id_stride, int64_t* topk_idx, float* topk_val, int32_t* topk_head,
                             void* workspace, size_t workspace_bytes, void* stream);
 /* Second half of b200rec_score_mask_topk for scores already folded over heads (B200REC_EPI_FOLD_HEADS):
- * history suppression on fval, then per-user radix select + sort.  Same tie rule and id mapping. */
-int b200rec_topk_select(float* fval, const uint8_t* fhead, int B, int64_t N, int K,
+ * history suppression on fval, then per-user radix select + sort.  Same tie rule and id mapping.
+ * fval / fhead rows have leading dimension ld >= N (a multiple of 4 keeps the 16-byte loads). */
+int b200rec_topk_select(float* fval, const uint8_t* fhead, int B, int64_t N, int64_t ld, int K,
                         const int32_t* hist_off, const int64_t* hist_items, int64_t id_offset,
                         int64_t id_stride, int64_t* topk_idx, float* topk_val, int32_t* topk_head,
                         void* stream);

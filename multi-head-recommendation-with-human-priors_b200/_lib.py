@@ -90,7 +90,7 @@ _SIGS = {
     "b200rec_build_train_batch": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _I, _I, _P, _P, _I, _F, _P, _I,
                                             C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P]),
     "b200rec_build_eval_batch": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P]),
-    "b200rec_topk_select": (C.c_int, [_P, _P, _I, _L, _I, _P, _P, _L, _L, _P, _P, _P, _P]),
+    "b200rec_topk_select": (C.c_int, [_P, _P, _I, _L, _L, _I, _P, _P, _L, _L, _P, _P, _P, _P]),
     "b200rec_apply_score_masks": (C.c_int, [_P, _L, _I, _I, _L, _P, _P, _P, _P]),
     "b200rec_hit_matrix": (C.c_int, [_P, _P, _I, _I, _I, _P, _I, _P, _P]),
     "b200rec_adamw": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P, _P]),

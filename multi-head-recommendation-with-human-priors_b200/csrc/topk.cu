@@ -50,14 +50,14 @@ fold_heads_kernel(const float* __restrict__ scores, int64_t ld, int H, int64_t N
 
 // history suppression (trainer.py:725-726): fval[b, item] = -inf
 __global__ void suppress_history_kernel(const int32_t* __restrict__ hist_off, const int64_t* __restrict__ hist_items,
-                                        int B, int64_t N, float* __restrict__ fval, int split_mode,
+                                        int B, int64_t N, int64_t ld, float* __restrict__ fval, int split_mode,
                                         int64_t id_offset, int64_t id_stride) {
   int b = blockIdx.x;
   for (int i = hist_off[b] + threadIdx.x; i < hist_off[b + 1]; i += blockDim.x) {
     int64_t g = hist_items[i] - id_offset;  // global id -> row of this shard (if it lives here)
     if (g < 0 || g % id_stride != 0) continue;
     int64_t it = g / id_stride;
-    if (it < N) fval[(int64_t)b * N + it] = split_mode == 1 ? 0.f : -INFINITY;
+    if (it < N) fval[(int64_t)b * ld + it] = split_mode == 1 ? 0.f : -INFINITY;
   }
 }
 
@@ -71,12 +71,13 @@ __global__ void suppress_history_kernel(const int32_t* __restrict__ hist_off, co
 template <typename F>
 __device__ __forceinline__ void sel_for_each(const float* __restrict__ row, int64_t N, F f) {
   const int tid = threadIdx.x;
-  if ((N & 3) == 0 && (((uintptr_t)row) & 15) == 0) {
+  if ((((uintptr_t)row) & 15) == 0) {
     const float4* r4 = reinterpret_cast<const float4*>(row);
     for (int64_t i = tid; i < (N >> 2); i += SEL_THREADS) {
       float4 v = __ldg(r4 + i);
       f(v.x, i * 4); f(v.y, i * 4 + 1); f(v.z, i * 4 + 2); f(v.w, i * 4 + 3);
     }
+    for (int64_t i = (N & ~(int64_t)3) + tid; i < N; i += SEL_THREADS) f(row[i], i);
   } else {
     for (int64_t i = tid; i < N; i += SEL_THREADS) f(row[i], i);
   }
@@ -100,7 +101,7 @@ __device__ __forceinline__ void sel_bitonic(unsigned long long* a, int n_pad) {
 }
 
 __global__ void __launch_bounds__(SEL_THREADS)
-select_topk_kernel(const float* __restrict__ fval, const uint8_t* __restrict__ fhead, int64_t N, int K,
+select_topk_kernel(const float* __restrict__ fval, const uint8_t* __restrict__ fhead, int64_t N, int64_t ld, int K,
                    int64_t id_offset, int64_t id_stride, int64_t* __restrict__ topk_idx, float* __restrict__ topk_val, int32_t* __restrict__ topk_head) {
   // cand2 holds the elements of the threshold bin; the 11-bit histogram of the first pass aliases it
   __shared__ unsigned long long cand2[SEL_CAND2];
@@ -108,7 +109,7 @@ select_topk_kernel(const float* __restrict__ fval, const uint8_t* __restrict__ f
   __shared__ unsigned int s_prefix, s_remaining, s_count, s_count2, s_scan[SEL_THREADS / 32 + 1];
   unsigned int* hist = reinterpret_cast<unsigned int*>(cand2);
   const int b = blockIdx.x;
-  const float* row = fval + (int64_t)b * N;
+  const float* row = fval + (int64_t)b * ld;
   const int tid = threadIdx.x;
 
   // ---- read 1: 11-bit histogram -> threshold bin d (the bin holding the K-th largest), rem = how many of its
@@ -234,7 +235,7 @@ select_topk_kernel(const float* __restrict__ fval, const uint8_t* __restrict__ f
     uint32_t id = (uint32_t)(c & 0xffffffffull);
     topk_idx[(int64_t)b * K + i] = (int64_t)id * id_stride + id_offset;
     topk_val[(int64_t)b * K + i] = row[id];
-    topk_head[(int64_t)b * K + i] = fhead[(int64_t)b * N + id];
+    topk_head[(int64_t)b * K + i] = fhead[(int64_t)b * ld + id];
   }
 }
 
@@ -261,21 +262,21 @@ int b200rec_score_mask_topk(const float* scores, int64_t ld_scores, int B, int H
   dim3 grid((unsigned)std::min<int64_t>((N + 255) / 256, 148 * 8), B);
   fold_heads_kernel<<<grid, 256, 0, st>>>(scores, ld_scores, H, N, head_cat, item_tag_bits, head_on, split_mode,
                                           id_offset, id_stride, fval, fhead);
-  if (hist_off && hist_items) suppress_history_kernel<<<B, 128, 0, st>>>(hist_off, hist_items, B, N, fval, split_mode, id_offset, id_stride);
-  select_topk_kernel<<<B, SEL_THREADS, 0, st>>>(fval, fhead, N, K, id_offset, id_stride, topk_idx, topk_val, topk_head);
+  if (hist_off && hist_items) suppress_history_kernel<<<B, 128, 0, st>>>(hist_off, hist_items, B, N, N, fval, split_mode, id_offset, id_stride);
+  select_topk_kernel<<<B, SEL_THREADS, 0, st>>>(fval, fhead, N, N, K, id_offset, id_stride, topk_idx, topk_val, topk_head);
   B200_LAUNCH_OK();
   return 0;
 }
 
-int b200rec_topk_select(float* fval, const uint8_t* fhead, int B, int64_t N, int K, const int32_t* hist_off,
+int b200rec_topk_select(float* fval, const uint8_t* fhead, int B, int64_t N, int64_t ld, int K, const int32_t* hist_off,
                         const int64_t* hist_items, int64_t id_offset, int64_t id_stride, int64_t* topk_idx,
                         float* topk_val, int32_t* topk_head, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   B200_CHECK_ARG(K >= 1 && K <= SEL_MAXK && K <= N, "topk_select: K=%d not in [1,%d] or > N", K, SEL_MAXK);
-  B200_CHECK_ARG(N < (1ll << 32) && id_stride >= 1 && id_offset >= 0, "topk_select: bad N / id mapping");
+  B200_CHECK_ARG(N < (1ll << 32) && id_stride >= 1 && id_offset >= 0 && ld >= N, "topk_select: bad N / ld / id mapping");
   if (B == 0) return 0;
-  if (hist_off && hist_items) suppress_history_kernel<<<B, 128, 0, st>>>(hist_off, hist_items, B, N, fval, 0, id_offset, id_stride);
-  select_topk_kernel<<<B, SEL_THREADS, 0, st>>>(fval, fhead, N, K, id_offset, id_stride, topk_idx, topk_val, topk_head);
+  if (hist_off && hist_items) suppress_history_kernel<<<B, 128, 0, st>>>(hist_off, hist_items, B, N, ld, fval, 0, id_offset, id_stride);
+  select_topk_kernel<<<B, SEL_THREADS, 0, st>>>(fval, fhead, N, ld, K, id_offset, id_stride, topk_idx, topk_val, topk_head);
   B200_LAUNCH_OK();
   return 0;
 }

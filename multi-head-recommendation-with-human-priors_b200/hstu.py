@@ -1146,7 +1146,8 @@ class HSTU(nn.Module):
         val = torch.empty((Ball, K), dtype=torch.float32, device=dev)
         hsrc = torch.empty((Ball, K), dtype=torch.int32, device=dev)
         mode = 1 if (split_mode == "average" and H > 1) else 0
-        fused = self._act() == torch.bfloat16 and mode == 0 and H <= 32 and N % 4 == 0 and self.use_fused_eval
+        fused = self._act() == torch.bfloat16 and mode == 0 and H <= 32 and self.use_fused_eval
+        ldn = (N + 3) // 4 * 4                     # padded row pitch: 16-byte stores / loads for any shard size
         if fused:
             # scoring GEMM with the fold-heads epilogue: [Ball*hp, D] x [N, D]^T -> (max, argmax head) per item;
             # the [B, H, N] score tensor is never written.
@@ -1166,13 +1167,13 @@ class HSTU(nn.Module):
             for b0 in range(0, Ball, user_chunk):
                 b1 = min(Ball, b0 + user_chunk)
                 nb = b1 - b0
-                fval = torch.empty((nb, N), dtype=torch.float32, device=dev)
-                fhead = torch.empty((nb, N), dtype=torch.uint8, device=dev)
-                L.gemm(Up[b0:b1].reshape(nb * hp, D), table, fval, nb * hp, N, D, lda=D, ldb=D, ldc=N,
-                       epilogue=L.EPI_FOLD_HEADS, C2=fhead, ldc2=N,
+                fval = torch.empty((nb, ldn), dtype=torch.float32, device=dev)
+                fhead = torch.empty((nb, ldn), dtype=torch.uint8, device=dev)
+                L.gemm(Up[b0:b1].reshape(nb * hp, D), table, fval, nb * hp, N, D, lda=D, ldb=D, ldc=ldn,
+                       epilogue=L.EPI_FOLD_HEADS, C2=fhead, ldc2=ldn,
                        fold=(hp, on[b0:b1].reshape(-1).contiguous(), cat, bits, rank, Wd))
                 ho = hist_off[b0:b1 + 1].contiguous() if hist_off is not None else None
-                L.call("b200rec_topk_select", fval.data_ptr(), fhead.data_ptr(), nb, N, K, L.ptr(ho), L.ptr(hist_items),
+                L.call("b200rec_topk_select", fval.data_ptr(), fhead.data_ptr(), nb, N, ldn, K, L.ptr(ho), L.ptr(hist_items),
                        rank, Wd, idx[b0:b1].data_ptr(), val[b0:b1].data_ptr(), hsrc[b0:b1].data_ptr(), L.stream())
         else:
             if user_chunk is None:

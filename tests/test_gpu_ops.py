@@ -408,13 +408,14 @@ def test_topk_ties_and_neg_inf_rule():
     assert idx[1].tolist() == list(range(10, 10 + K))
 
 
-@pytest.mark.parametrize("kind", ["smooth", "quantised", "few_finite", "odd_n"])
+@pytest.mark.parametrize("kind", ["smooth", "quantised", "few_finite", "odd_n", "padded_ld"])
 def test_topk_select_both_paths_large_rows(kind):
     """select_topk: two-read path (threshold bin fits the candidate buffer) and the exact radix fallback (crowded
     bin: quantised scores, or fewer finite scores than K) against a (value desc, id asc) lexicographic sort."""
-    B, N, K = 3, 60000 if kind != "odd_n" else 60001, 200
+    B, N, K = 3, {"odd_n": 60001, "padded_ld": 60002}.get(kind, 60000), 200
+    ld = (N + 3) // 4 * 4 if kind == "padded_ld" else N
     g = torch.Generator().manual_seed(65)
-    if kind in ("smooth", "odd_n"):
+    if kind in ("smooth", "odd_n", "padded_ld"):
         sc = torch.randn(B, N, generator=g) * 0.03
     elif kind == "quantised":
         sc = torch.randint(0, 6, (B, N), generator=g).float() * 0.125          # ~10 k-way ties in the threshold bin
@@ -422,12 +423,13 @@ def test_topk_select_both_paths_large_rows(kind):
         sc = torch.full((B, N), float("-inf"))
         sc[:, 1000:1050] = torch.randn(B, 50, generator=g)
     sc = sc.to(dev())
-    fval = sc.clone()
-    fhead = torch.zeros(B, N, dtype=torch.uint8, device=dev())
+    fval = torch.full((B, ld), float("nan"), device=dev())
+    fval[:, :N] = sc
+    fhead = torch.zeros(B, ld, dtype=torch.uint8, device=dev())
     idx = torch.empty(B, K, dtype=torch.int64, device=dev())
     val = torch.empty(B, K, device=dev())
     hs = torch.empty(B, K, dtype=torch.int32, device=dev())
-    L.call("b200rec_topk_select", fval.data_ptr(), fhead.data_ptr(), B, N, K, None, None, 0, 1, idx.data_ptr(),
+    L.call("b200rec_topk_select", fval.data_ptr(), fhead.data_ptr(), B, N, ld, K, None, None, 0, 1, idx.data_ptr(),
            val.data_ptr(), hs.data_ptr(), L.stream())
     ids = torch.arange(N, device=dev()).expand(B, N)
     o1 = torch.argsort(ids, dim=1, stable=True)
