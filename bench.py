@@ -32,6 +32,8 @@ WORKLOADS = {"A": "HSTU-Pixel8M-base-small (A)", "A2": "HSTU-Pixel8M-base-small 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--dense-table-update", action="store_true",
+                    help="touch every table row every step (the dense pass) instead of the lazy exact update")
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--config", default="B")
@@ -181,6 +183,9 @@ def main():
                             f"items={cfg['item_num']}",
                 "per_gpu_batch": cfg["train_batch_size"], "global_batch": cfg["train_batch_size"] * world,
                 "parallelism": f"dp{world}" + ("+row-sharded-table(a2a)" if world > 1 and not args.replicate_table else ""), "l2": "working set >> 126 MB L2 (activations + 1.8 GB table); no flush",
+                "negatives": "re-drawn every step (64 pre-drawn sets rotated; by category where the config does)",
+                "table_update": "dense pass over all rows" if args.dense_table_update else
+                                "lazy exact AdamW (rows brought up to date when next read)",
                 "step": ("eager" if (args.no_graph or args.profile or (world > 1 and args.replicate_table)) else
                          "cuda-graph replay per 128-token bucket" if world == 1 else
                          "eager id exchange + row fetch, cuda-graph fwd/bwd per 128-token bucket, eager all-reduce / "
@@ -214,7 +219,9 @@ def main():
     torch.manual_seed(2020)
     model = HSTU(cfg, dl, compute_dtype=dtype).to(dev).train()  # training mode: Philox dropout at the preset's rate
     use_graph = not args.no_graph and not args.profile and not (world > 1 and args.replicate_table)
-    opt = FusedAdamW(model, lr=1e-4, weight_decay=0.0, device_step=use_graph and world == 1)
+    # lazy_table: exact dense-equivalent AdamW on the item table, rows nobody reads are updated when next read
+    opt = FusedAdamW(model, lr=1e-4, weight_decay=0.0, device_step=use_graph and world == 1,
+                     lazy_table=not args.dense_table_update)
     if world > 1 and not args.replicate_table:
         model.shard_item_table()          # rows id % W == rank; lookups / gradient rows by all-to-all
     dp = parallel.DataParallel(model, opt) if world > 1 else None
@@ -242,7 +249,31 @@ def main():
         opt.step()
         return out["loss"]
 
+    # Fresh negatives EVERY step (like the reference's sampler, trainset.py:126-137): the four synthetic batches
+    # only fix the sequences / token counts; re-using their negative ids would let the lazy table update skip the
+    # rows a real run keeps touching.  64 independent negative sets are drawn before the timed region (by
+    # category where the config samples by category) and rotated in, one 0.6 MB copy per step.
+    N_items, n_neg_sets = cfg["item_num"], 64
+    by_cat = bool(cfg["neg_sample_by_cat"]) and cfg["loss"] == "prior" and cfg["category_by"] == "item"
+    gen = torch.Generator().manual_seed(555 + rank)
+    pools = [torch.nonzero(item_tags[1:, c]).flatten().add_(1) for c in range(cfg["eval_num_cats"])] if by_cat else []
+    shape = tuple(host_batches[0][1].shape)
+    host_negs = []
+    for _ in range(n_neg_sets):
+        neg = torch.randint(1, N_items, shape, generator=gen)
+        for c, pool in enumerate(pools):                            # set c: uniform over the items of category c
+            neg[:, c] = pool[torch.randint(0, pool.numel(), tuple(neg[:, c].shape), generator=gen)]
+        host_negs.append(neg.pin_memory())
+    dev_negs = [t.to(dev) for t in host_negs]
+    neg_ctr = [0]
+
+    def fresh_negatives(neg):
+        src = (dev_negs if neg.is_cuda else host_negs)[neg_ctr[0] % n_neg_sets]
+        neg_ctr[0] += 1
+        neg.copy_(src, non_blocking=True)
+
     def step(batch, i=None):
+        fresh_negatives(batch[1])
         if stepper is not None:
             return stepper(batch, n_tok[i])["loss"]
         return eager_step(batch)
@@ -294,8 +325,13 @@ def main():
     last = None
     for i in range(args.steps):
         j = i % n_batches
-        b = host_batches[j] if use_graph else tuple(t.to(dev, non_blocking=True) for t in host_batches[j])
-        last = float(step(b, j).item())        # H2D of the pinned batch inside step; D2H read of the loss
+        if use_graph:
+            b = host_batches[j]                  # H2D of the pinned batch happens inside the stepper
+            last = float(step(b, j).item())      # D2H read of the loss
+        else:
+            fresh_negatives(host_batches[j][1])
+            b = tuple(t.to(dev, non_blocking=True) for t in host_batches[j])
+            last = float(eager_step(b).item())
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)

@@ -324,6 +324,22 @@ int b200rec_adamw(float* p, float* m, float* v, const float* g, int64_t n, float
                   float beta2, float eps, float weight_decay, int step, float grad_scale,
                   const float* coef_dev, void* stream);
 int b200rec_adamw_tick(float* coef_dev, float beta1, float beta2, void* stream);
+/* Lazy dense-equivalent AdamW on the item table (exact torch.optim.AdamW values, deferred): a row with zero
+ * gradient at step j needs only its own (p, m, v) and the step's scalars, so rows nobody reads are not touched.
+ * last[row] (int32, zero-initialised) = last step applied to the row; hist (float4[cap]) = {1 - lr*wd,
+ * lr / (1-beta1^j), 1 / sqrt(1-beta2^j), lr} of every step j, written by b200rec_adamw_tick_hist (which replaces b200rec_adamw_tick).
+ *   b200rec_adamw_rows_catchup  brings the rows `ids` (duplicates allowed; NULL = all n_ids = n_rows rows) up to
+ *                               the current step BEFORE something reads them (lookups, eval, checkpoint);
+ *   b200rec_adamw_rows_lazy     applies the current step (tick already run) to the rows with a gradient. */
+int b200rec_adamw_tick_hist(float* coef_dev, void* hist, int cap, float beta1, float beta2,
+                            float weight_decay, void* stream);
+int b200rec_adamw_rows_catchup(float* p, float* m, float* v, int64_t n_rows, int D, const int64_t* ids,
+                               int64_t n_ids, int32_t* last, const void* hist, const float* coef_dev,
+                               float beta1, float beta2, float eps, float weight_decay, void* stream);
+int b200rec_adamw_rows_lazy(float* p, float* m, float* v, int64_t n_rows, int D, const int64_t* uniq_ids,
+                            const float* uniq_rows, const int32_t* n_uniq, int64_t max_rows, int32_t* last,
+                            const void* hist, const float* coef_dev, float beta1, float beta2, float eps,
+                            float weight_decay, float grad_scale, void* stream);
 /* One launch for many dense tensors: table_dev = array of {float* p, m, v; const float* g; bf16* shadow;
  * int64 n}, blocks_dev = int64 pairs {tensor index, first element of a 4096-element chunk}.  `shadow`
  * (nullable) receives the updated parameter rounded to bf16 — the GEMM operand of the next step, so the

@@ -26,6 +26,32 @@ __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float 
   p -= (c.lr / c.bc1) * (m / denom);
 }
 
+// Table-row variant: the per-step scalars are folded once (decay, step size, 1/bias-correction) and sqrt / divide
+// use the MUFU approximations (rel. error ~2^-22): ~9 instructions per element instead of ~25, which is what the
+// lazy catch-up loop is bound by.  The dense-equivalent rows pass and the lazy pass share this function, so they stay
+// bit-identical to each other; against torch.optim.AdamW the table differs by ~1e-7 relative per step.
+struct RowStep {
+  float decay, step_size, inv_bc2;
+};
+__device__ __forceinline__ RowStep row_step(float lr, float bc1, float bc2_sqrt, float wd) {
+  RowStep r;
+  r.decay = 1.f - lr * wd;
+  r.step_size = lr / bc1;
+  r.inv_bc2 = 1.f / bc2_sqrt;
+  return r;
+}
+__device__ __forceinline__ void adam_update_row(float& p, float& m, float& v, float g, const RowStep& r, float b1,
+                                                float b2, float eps) {
+  p *= r.decay;
+  m = b1 * m + (1.f - b1) * g;
+  v = b2 * v + (1.f - b2) * g * g;
+  float sq, rc;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(v));
+  const float denom = fmaf(sq, r.inv_bc2, eps);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(denom));
+  p = fmaf(-r.step_size * m, rc, p);
+}
+
 static AdamCoef make_coef(float lr, float b1, float b2, float eps, float wd, int step, float gs) {
   AdamCoef c;
   c.lr = lr; c.b1 = b1; c.b2 = b2; c.eps = eps; c.wd = wd; c.gs = gs;
@@ -106,8 +132,9 @@ __global__ void __launch_bounds__(256) adamw_rows_kernel(float* __restrict__ p, 
     load4<float>(m + i * 4, mm);
     load4<float>(v + i * 4, vv);
     if (slot >= 0) load4<float>(uniq_rows + ((int64_t)slot * D4 + col) * 4, gg);
+    const RowStep rs = row_step(c.lr, c.bc1, c.bc2_sqrt, c.wd);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) adam_update(pp[k], mm[k], vv[k], gg[k], c);
+    for (int k = 0; k < 4; ++k) adam_update_row(pp[k], mm[k], vv[k], gg[k] * c.gs, rs, c.b1, c.b2, c.eps);
     store4<float>(p + i * 4, pp);
     store4<float>(m + i * 4, mm);
     store4<float>(v + i * 4, vv);
@@ -208,6 +235,152 @@ extern "C" int b200rec_adamw_multi(const void* table_dev, const int64_t* blocks_
   AdamCoef c = make_coef(lr, beta1, beta2, eps, weight_decay, step, grad_scale);
   c.dev = coef_dev;
   adamw_multi_kernel<<<n_blocks, 256, 0, (cudaStream_t)stream>>>((const AdamTensor*)table_dev, blocks_dev, c);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+
+// ---- lazy dense-equivalent AdamW on the item table ----------------------------------------------------------
+// The dense-equivalent update touches all N rows every step (11 GB at N = 450 k, D = 1024) although a step reads
+// ~80 k of them.  A row whose gradient is zero at step j only needs  m *= b1, v *= b2, p = f_j(p, m, v)  with the
+// step's scalars: nothing but its own (p, m, v).  So the updates of rows nobody looks at are DEFERRED: last[row]
+// is the last step applied to the row, hist[j] = {lr_j, bc1_j, bc2_sqrt_j} keeps every step's scalars, and a row is
+// brought up to date (the same per-step formula, in the same order, with g = 0: bit-identical to the dense pass)
+// when something is about to read it: the lookups of the next step, evaluation, a checkpoint.  Exact torch.optim.AdamW
+// semantics, ~6x less HBM traffic per step.
+__global__ void adamw_tick_hist_kernel(float* coef, float4* hist, int cap, float b1, float b2, float wd) {
+  float step = coef[3] + 1.f;
+  coef[3] = step;
+  coef[1] = 1.f - powf(b1, step);
+  coef[2] = sqrtf(1.f - powf(b2, step));
+  int j = (int)step;
+  const RowStep r = row_step(coef[0], coef[1], coef[2], wd);
+  if (j < cap) hist[j] = make_float4(r.decay, r.step_size, r.inv_bc2, coef[0]);
+}
+
+extern "C" int b200rec_adamw_tick_hist(float* coef_dev, void* hist, int cap, float beta1, float beta2,
+                                       float weight_decay, void* stream) {
+  adamw_tick_hist_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(coef_dev, (float4*)hist, cap, beta1, beta2, weight_decay);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+template <int MAXV>
+__device__ __forceinline__ void lazy_catch_up(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                              int64_t row, int D4, int from, int to, const float4* __restrict__ hist,
+                                              AdamCoef c, const float* __restrict__ grow, bool with_grad) {
+  // steps from+1 .. to with zero gradient; if with_grad, step to+1 follows with gradient row `grow`
+  const int lane = threadIdx.x & 31;
+  for (int c0 = 0; c0 < D4; c0 += 32 * MAXV) {
+    float pp[MAXV][4], mm[MAXV][4], vv[MAXV][4];
+#pragma unroll
+    for (int u = 0; u < MAXV; ++u) {
+      const int col = c0 + lane + 32 * u;
+      if (col < D4) {
+        load4<float>(p + (row * D4 + col) * 4, pp[u]);
+        load4<float>(m + (row * D4 + col) * 4, mm[u]);
+        load4<float>(v + (row * D4 + col) * 4, vv[u]);
+      }
+    }
+    for (int j = from + 1; j <= to; ++j) {
+      const float4 h = __ldg(hist + j);
+      RowStep rs;
+      rs.decay = h.x; rs.step_size = h.y; rs.inv_bc2 = h.z;
+#pragma unroll
+      for (int u = 0; u < MAXV; ++u)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) adam_update_row(pp[u][k], mm[u][k], vv[u][k], 0.f, rs, c.b1, c.b2, c.eps);
+    }
+    if (with_grad) {
+      const float4 h = __ldg(hist + to + 1);
+      RowStep rs;
+      rs.decay = h.x; rs.step_size = h.y; rs.inv_bc2 = h.z;
+#pragma unroll
+      for (int u = 0; u < MAXV; ++u) {
+        const int col = c0 + lane + 32 * u;
+        if (col < D4) {
+          float gg[4];
+          load4<float>(grow + col * 4, gg);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) adam_update_row(pp[u][k], mm[u][k], vv[u][k], gg[k] * c.gs, rs, c.b1, c.b2, c.eps);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < MAXV; ++u) {
+      const int col = c0 + lane + 32 * u;
+      if (col < D4) {
+        store4<float>(p + (row * D4 + col) * 4, pp[u]);
+        store4<float>(m + (row * D4 + col) * 4, mm[u]);
+        store4<float>(v + (row * D4 + col) * 4, vv[u]);
+      }
+    }
+  }
+}
+
+// one warp per requested id (duplicates allowed: the first claimant does the work, kernel boundaries order the reads)
+__global__ void __launch_bounds__(256) adamw_rows_catchup_kernel(float* __restrict__ p, float* __restrict__ m,
+                                                                 float* __restrict__ v, int64_t N, int D4,
+                                                                 const int64_t* __restrict__ ids, int64_t n_ids,
+                                                                 int32_t* __restrict__ last,
+                                                                 const float4* __restrict__ hist, AdamCoef c) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int S = (int)c.dev[3];                                  // completed optimizer steps
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_ids; i += warps) {
+    const int64_t row = ids ? ids[i] : i;
+    if (row < 0 || row >= N) continue;
+    int old = 0;
+    if (lane == 0) old = atomicExch(last + row, S);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old >= S) continue;
+    lazy_catch_up<4>(p, m, v, row, D4, old, S, hist, c, nullptr, false);
+  }
+}
+
+__global__ void __launch_bounds__(256) adamw_rows_lazy_kernel(float* __restrict__ p, float* __restrict__ m,
+                                                              float* __restrict__ v, int D4,
+                                                              const int64_t* __restrict__ uniq_ids,
+                                                              const float* __restrict__ uniq_rows,
+                                                              const int32_t* __restrict__ n_uniq,
+                                                              int32_t* __restrict__ last,
+                                                              const float4* __restrict__ hist, AdamCoef c) {
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int S1 = (int)c.dev[3];                                 // the step being applied (tick already ran)
+  const int nu = *n_uniq;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nu; i += warps) {
+    const int64_t row = uniq_ids[i];                             // unique: no claim needed
+    const int old = last[row];
+    lazy_catch_up<4>(p, m, v, row, D4, min(old, S1 - 1), S1 - 1, hist, c, uniq_rows + i * D4 * 4, true);
+    if ((threadIdx.x & 31) == 0) last[row] = S1;
+  }
+}
+
+extern "C" int b200rec_adamw_rows_catchup(float* p, float* m, float* v, int64_t n_rows, int D, const int64_t* ids,
+                                          int64_t n_ids, int32_t* last, const void* hist, const float* coef_dev,
+                                          float beta1, float beta2, float eps, float weight_decay, void* stream) {
+  B200_CHECK_ARG(D % 4 == 0 && coef_dev != nullptr && hist != nullptr && last != nullptr, "adamw_rows_catchup: bad args");
+  if (n_ids == 0) return 0;
+  AdamCoef c = make_coef(0.f, beta1, beta2, eps, weight_decay, 1, 1.f);
+  c.dev = coef_dev;
+  int blocks = (int)std::min<int64_t>((n_ids + 7) / 8, 148 * 8);
+  adamw_rows_catchup_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, m, v, n_rows, D / 4, ids, n_ids, last,
+                                                                      (const float4*)hist, c);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int b200rec_adamw_rows_lazy(float* p, float* m, float* v, int64_t n_rows, int D, const int64_t* uniq_ids,
+                                       const float* uniq_rows, const int32_t* n_uniq, int64_t max_rows, int32_t* last,
+                                       const void* hist, const float* coef_dev, float beta1, float beta2, float eps,
+                                       float weight_decay, float grad_scale, void* stream) {
+  B200_CHECK_ARG(D % 4 == 0 && coef_dev != nullptr && hist != nullptr && last != nullptr, "adamw_rows_lazy: bad args");
+  if (max_rows == 0 || n_rows == 0) return 0;
+  AdamCoef c = make_coef(0.f, beta1, beta2, eps, weight_decay, 1, grad_scale);
+  c.dev = coef_dev;
+  int blocks = (int)std::min<int64_t>((max_rows + 7) / 8, 148 * 8);
+  adamw_rows_lazy_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, m, v, D / 4, uniq_ids, uniq_rows, n_uniq, last,
+                                                                   (const float4*)hist, c);
   B200_LAUNCH_OK();
   return 0;
 }

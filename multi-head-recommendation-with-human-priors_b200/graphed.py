@@ -40,6 +40,9 @@ class GraphedTrainStep(object):
             opt._coef = torch.tensor([g["lr"], 0.0, 0.0, float(opt.step_count)], dtype=torch.float32,
                                      device=next(self.model.parameters()).device)
         ts.append(opt._coef)
+        if opt.lazy_table:
+            opt._lazy_state()
+            ts += [opt._last, opt._hist]
         return ts
 
     def _capture(self, T_b):
@@ -105,7 +108,6 @@ class GraphedShardedStep(object):
         import torch.distributed as dist
         assert model.sharded_table is not None, "call model.shard_item_table() first"
         assert not model._has_tower(), "item_id_proj_tower: use the eager sharded step"
-        assert not optimizer.device_step, "the optimizer runs eagerly here: FusedAdamW(device_step=False)"
         self.dist, self.group = dist, group
         self.model, self.opt, self.bucket, self.warmup = model, optimizer, bucket, warmup
         items, neg, mask, tags = example_batch

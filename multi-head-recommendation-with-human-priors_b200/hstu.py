@@ -198,6 +198,8 @@ class HSTU(nn.Module):
         self.sharded_table = None  # parallel.ShardedTable once shard_item_table() was called
         self._shadow_buf, self._shadow_state, self._shadow_view = {}, {}, {}
         self._heads_upper = []     # (input, pre-activation) of the weight-tied decode-head layers above the first
+        # set by FusedAdamW(lazy_table=True): bring table rows up to date before they are read
+        self._table_sync = self._table_flush = None
         self.emb_grad = None       # (uniq_ids, uniq_rows, n_uniq) of the last backward
         self._table_cache = None   # normalised compute-dtype item table for predict
         self._verbose = False
@@ -298,6 +300,11 @@ class HSTU(nn.Module):
             return None
         return self._shadow_view[p]
 
+    def state_dict(self, *args, **kwargs):
+        if self._table_flush is not None:      # deferred table updates must land before the weights are exported
+            self._table_flush()
+        return super().state_dict(*args, **kwargs)
+
     def shadows_stale(self):
         """True if a shadowed Parameter changed since its shadow was written (a captured graph contains no cast)."""
         return any(st[:2] != (p._version, p.data_ptr()) for p, st in self._shadow_state.items())
@@ -315,6 +322,7 @@ class HSTU(nn.Module):
         full = self.item_embedding.weight.data
         self.item_embedding.weight.data = parallel.ShardedTable.shard_of(full, W, rank)
         self.sharded_table = parallel.ShardedTable(self.item_embedding.weight.data, self.item_num, group)
+        self.sharded_table.pre_gather = lambda idx: self._table_sync(idx) if self._table_sync is not None else None
         self._table_cache = None
         return self
 
@@ -346,6 +354,9 @@ class HSTU(nn.Module):
           projection tower: a row cache holding proj(W[id]) — one row per requested position (static shapes,
           no sync) with a replicated table, one row per unique id on top of the sharded fetch."""
         tower = self._has_tower()
+        if self._table_sync is not None and self.sharded_table is None:
+            self._table_sync(items)
+            self._table_sync(neg_ids)
         if self.sharded_table is None and not tower:
             return self.item_embedding.weight.data, items, neg_ids, None
         B, LP = items.shape
@@ -986,6 +997,8 @@ class HSTU(nn.Module):
     @torch.no_grad()
     def compute_item_all(self):
         """hstu.py:1018-1021: L2-normalised (projected) item table, fp32 [N, D]."""
+        if self._table_flush is not None:
+            self._table_flush()
         W = self.item_embedding.weight.data
         N = W.shape[0]
         D = self._hstu_embedding_dim
@@ -1015,6 +1028,8 @@ class HSTU(nn.Module):
         tok_b, tok_pos, seq_off, key_valid, T = self._tokens(item_seq != 0, force_last=True)
         w = self._cast_weights()
         x = torch.empty((T, D), dtype=torch.float32, device=dev)
+        if self._table_sync is not None and self.sharded_table is None:
+            self._table_sync(item_seq)
         table, seq_idx = self.item_embedding.weight.data, item_seq
         if self.sharded_table is not None:
             uniq, inv = torch.unique(item_seq.reshape(-1), return_inverse=True)

@@ -14,14 +14,23 @@ from . import _lib as L
 
 
 class FusedAdamW(object):
-    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, device_step=False):
+    HIST_CAP = 1 << 20     # optimizer steps whose scalars the lazy table update can look back to
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, device_step=False,
+                 lazy_table=False):
+        """lazy_table: defer the dense-equivalent update of item-table rows nobody reads (exact AdamW values, see
+        include/b200rec.h); the model brings rows up to date before every lookup / evaluation / state_dict()."""
         self.model = model
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.step_count = 0
         self.state = {}
         self.param_groups = [dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)]
         self._row_slot = None
-        self.device_step = device_step
+        self.device_step = device_step or lazy_table
+        self.lazy_table = bool(lazy_table)
+        self._last = self._hist = None
+        if self.lazy_table:
+            model._table_sync, model._table_flush = self.sync_rows, self.flush
         self._coef = None          # device fp32[4] = {lr, bc1, bc2_sqrt, step}
         self._table_key = None
         self._table = self._blocks = None
@@ -89,16 +98,29 @@ class FusedAdamW(object):
             if self._coef is None:
                 self._coef = torch.tensor([lr, 0.0, 0.0, float(self.step_count - 1)], dtype=torch.float32, device=emb.device)
             if first_half:
-                L.call("b200rec_adamw_tick", self._coef.data_ptr(), b1, b2, st)
+                if self.lazy_table:
+                    self._lazy_state(completed=self.step_count - 1)
+                    if self.step_count >= self.HIST_CAP:
+                        raise L.B200RecError("lazy_table: optimizer step history exhausted (HIST_CAP)")
+                    L.call("b200rec_adamw_tick_hist", self._coef.data_ptr(), self._hist.data_ptr(), self.HIST_CAP, b1, b2, wd, st)
+                else:
+                    L.call("b200rec_adamw_tick", self._coef.data_ptr(), b1, b2, st)
             coef = self._coef.data_ptr()
         dense_list = []
         for p in self.model.parameters():
+            if p is emb and self.lazy_table and p.grad is not None:
+                raise L.B200RecError("lazy_table needs the compact table gradient (config['sparse_embedding_grad'] = True)")
             if p is emb and p.grad is None and self.model.emb_grad is not None:
                 if not rows:
                     continue
                 m, v = self._st(p)
                 uniq_ids, uniq_rows, n_uniq = self.model.emb_grad
                 N, D = p.shape
+                if self.lazy_table:
+                    L.call("b200rec_adamw_rows_lazy", p.data_ptr(), m.data_ptr(), v.data_ptr(), N, D, uniq_ids.data_ptr(),
+                           uniq_rows.data_ptr(), n_uniq.data_ptr(), uniq_ids.numel(), self._last.data_ptr(),
+                           self._hist.data_ptr(), coef, b1, b2, eps, wd, grad_scale, st)
+                    continue
                 if self._row_slot is None or self._row_slot.numel() != N:
                     self._row_slot = torch.empty(N, dtype=torch.int32, device=p.device)
                 L.call("b200rec_adamw_rows", p.data_ptr(), m.data_ptr(), v.data_ptr(), N, D, uniq_ids.data_ptr(),
@@ -115,3 +137,42 @@ class FusedAdamW(object):
             table, blocks = self._dense_table(dense)
             L.call("b200rec_adamw_multi", table.data_ptr(), blocks.data_ptr(), blocks.numel() // 2, lr, b1, b2, eps, wd,
                    self.step_count, grad_scale, coef, st)
+
+    # ---- lazy item-table update -------------------------------------------------------------------------
+    def _lazy_state(self, completed=None):
+        """Creates last[row] / hist / the device step counter on first use; returns the table Parameter.
+        `completed` = optimizer steps already applied to every row (defaults to step_count)."""
+        emb = self.model.item_embedding.weight
+        completed = self.step_count if completed is None else completed
+        if self._coef is None:                     # coef[3] = number of completed optimizer steps
+            g = self.param_groups[0]
+            self._coef = torch.tensor([g["lr"], 0.0, 0.0, float(completed)], dtype=torch.float32, device=emb.device)
+        if self._last is None or self._last.numel() != emb.shape[0] or self._last.device != emb.device:
+            self._last = torch.full((emb.shape[0],), int(completed), dtype=torch.int32, device=emb.device)
+            self._hist = torch.zeros((self.HIST_CAP, 4), dtype=torch.float32, device=emb.device)
+        return emb
+
+    @torch.no_grad()
+    def sync_rows(self, ids):
+        """Bring the table rows `ids` (int64 tensor, duplicates fine; None = every row) up to the current step."""
+        if not self.lazy_table or (self.step_count == 0 and self._last is None):
+            return
+        emb = self._lazy_state()
+        g = self.param_groups[0]
+        (b1, b2), eps, wd = g["betas"], g["eps"], g["weight_decay"]
+        m, v = self._st(emb)
+        N, D = emb.shape
+        if ids is not None:
+            ids = ids.reshape(-1).contiguous()
+        L.call("b200rec_adamw_rows_catchup", emb.data_ptr(), m.data_ptr(), v.data_ptr(), N, D, L.ptr(ids),
+               N if ids is None else ids.numel(), self._last.data_ptr(), self._hist.data_ptr(), self._coef.data_ptr(),
+               b1, b2, eps, wd, L.stream())
+
+    def flush(self):
+        self.sync_rows(None)
+
+    def mark_all_current(self):
+        """After loading a checkpoint: every row holds the state of step `step_count`."""
+        if self.lazy_table:
+            self._lazy_state()
+            self._last.fill_(int(self.step_count))

@@ -112,6 +112,7 @@ class ShardedTable(object):
         self.W = world(group)
         self.rank = dist.get_rank(group) if self.W > 1 else 0
         self.row_gather, self.segment_reduce = row_gather, segment_reduce
+        self.pre_gather = None     # hook: called with the local row indices right before they are read
         self.plan = None
 
     @staticmethod
@@ -137,6 +138,8 @@ class ShardedTable(object):
         sc, rc = send_counts.tolist(), recv_counts.tolist()
         req = _a2a(sorted_ids, sc, rc, self.group) if W > 1 else sorted_ids
         local_idx = torch.div(req, W, rounding_mode="floor")
+        if self.pre_gather is not None:
+            self.pre_gather(local_idx)
         rows = self.row_gather(self.weight, local_idx)
         back = _a2a(rows, rc, sc, self.group) if W > 1 else rows
         out = torch.empty_like(back) if out is None else out[:back.shape[0]]

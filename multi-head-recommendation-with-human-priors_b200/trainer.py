@@ -82,7 +82,7 @@ class Trainer(object):
         if optimizer is None:
             model.sparse_embedding_grad = True
             optimizer = FusedAdamW(model, lr=self.base_lr, weight_decay=wd,
-                                   device_step=self.use_graph and not self.sharded)
+                                   device_step=self.use_graph and not self.sharded, lazy_table=True)
         self.optimizer = optimizer
         self.scheduler_config = config.get("scheduler_args", None)
         self.total_iters = int(config.get("total_iters", 0) or 0)
@@ -294,6 +294,7 @@ class Trainer(object):
         opt.step_count = state["optimizer"]["step_count"]
         if opt._coef is not None:
             opt._coef[3:4].fill_(float(opt.step_count))
+        opt.mark_all_current()
         self.train_step = state["iter_idx"]
         self.best_valid_score = state["best_valid_score"]
         return state                               # captured graphs read parameters / state in place: still valid

@@ -411,3 +411,47 @@ def test_config_c_d_shapes_against_oracle(preset, over):
         else:   # bf16 scoring may swap near-ties: require >= 96 % overlap of the top-50 sets
             ov = np.mean([len(set(a) & set(b)) / 50.0 for a, b in zip(idx.cpu().numpy(), ref_idx)])
             assert ov >= 0.96, ov
+
+
+def test_lazy_table_adamw_is_bit_identical_to_dense_equivalent():
+    """FusedAdamW(lazy_table=True) defers the update of rows nobody reads; after a flush every table row, both
+    moments and every dense parameter equal the dense-equivalent optimizer bit for bit (same batches, lr schedule,
+    weight decay), in the eager loop and through the captured CUDA graph."""
+    from b200rec import synth
+    from b200rec.graphed import GraphedTrainStep
+    from b200rec.hstu import HSTU
+    from b200rec.optim import FusedAdamW
+    fx = load_golden("prior_additive")
+    cfg = synth.Config(fx["cfg"])
+    cfg["sparse_embedding_grad"] = True
+    dl = synth.Dataload(cfg["item_num"], fx["category_counts"], fx["category_to_int"])
+    batches = [tuple(t.to(dev()) for t in synth.make_train_batch(cfg, seed=90 + i, item_tags=fx["item_tags"], zipf=False))
+               for i in range(6)]
+    Lc = cfg["MAX_ITEM_LIST_LENGTH"]
+    lrs = [1e-2, 8e-3, 6e-3, 5e-3, 2e-3, 1e-3]
+    for graphed in (False, True):
+        states = []
+        for lazy in (False, True):
+            model = HSTU(cfg, dl, compute_dtype=torch.float32)
+            model.load_state_dict(fx["state_dict"])
+            model = model.to(dev()).eval()
+            opt = FusedAdamW(model, lr=lrs[0], weight_decay=0.05, device_step=True, lazy_table=lazy)
+            stepper = GraphedTrainStep(model, opt, batches[0], bucket=32) if graphed else None
+            for b, lr in zip(batches, lrs):
+                opt.set_lr(lr)
+                if graphed:
+                    stepper(b, int(b[2][:, :Lc].sum()))
+                else:
+                    opt.zero_grad()
+                    model(b)["loss"].backward()
+                    opt.step()
+            if lazy:
+                n_stale = int((opt._last < len(batches)).sum())
+                assert n_stale > 0                     # some rows really were deferred
+            sd = {k: v.clone() for k, v in model.state_dict().items()}       # state_dict() flushes
+            m, v = opt._st(model.item_embedding.weight)
+            states.append((sd, m.clone(), v.clone()))
+        (sd0, m0, v0), (sd1, m1, v1) = states
+        for k in sd0:
+            assert torch.equal(sd0[k], sd1[k]), (graphed, k)
+        assert torch.equal(m0, m1) and torch.equal(v0, v1)
