@@ -335,6 +335,8 @@ def main():
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    if stepper is not None and hasattr(stepper, "flush"):
+        stepper.flush()                          # pending dense update of the sharded step (overlapped all-reduce)
     if use_graph:
         # kernels inside a replayed graph cannot be bracketed by events: time every GEMM launch of the same
         # step in an instrumented eager pass right after the timed regions (same kernels, same shapes)

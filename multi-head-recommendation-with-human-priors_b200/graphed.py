@@ -98,8 +98,11 @@ class GraphedShardedStep(object):
                      (`HSTU.prepare_rows`): collectives and data-dependent sizes live here;
       graph (replay) forward + backward on static buffers -> dense gradients in ONE flat buffer shared by
                      all buckets, and one gradient row per cache row;
-      post  (eager)  flat all-reduce of the dense gradients, all-to-all push of the cache-row gradients to
-                     their owners (deterministic segment reduce there), fused AdamW with grad_scale = 1/W.
+      post  (eager)  all-to-all push of the cache-row gradients to their owners (deterministic segment reduce
+                     there) and the table update; the flat all-reduce of the dense gradients is launched on its
+                     own communicator and the dense AdamW of step k runs at the start of step k+1, AFTER that
+                     step's pre-phase: the all-reduce hides behind the id exchange / row fetch, which only need
+                     the table.  `flush()` applies the pending dense update (call it before evaluating or saving).
 
     The eager part is ~40 launches instead of ~1200, so the ranks stay GPU-bound.
     """
@@ -128,6 +131,8 @@ class GraphedShardedStep(object):
         self.pool = None
         self.max_tokens = B * model.max_seq_length
         self.dense = self.flat = self.views = None
+        self._pending = None                     # async all-reduce of the previous step's dense gradients
+        self.ar_group = dist.new_group() if (self.world > 1 and group is None) else group
 
     def _fill(self, batch):
         for s, t in zip(self.static, batch):
@@ -170,9 +175,18 @@ class GraphedShardedStep(object):
             self.pool = g.pool()
         return g, out, cache_grad, L.launches - n0
 
+    def flush(self):
+        """Dense AdamW of the last step (its all-reduce was left running)."""
+        if self._pending is not None:
+            work, self._pending = self._pending, None
+            if work is not True:
+                work.wait()
+            self.opt.step(grad_scale=1.0 / self.world, rows=False)
+
     def __call__(self, batch, n_tokens):
         T_b = min(self.max_tokens, max(self.bucket, (int(n_tokens) + self.bucket - 1) // self.bucket * self.bucket))
-        U = self._fill(batch)
+        U = self._fill(batch)                    # pre-phase: needs the table only
+        self.flush()                             # previous step's dense update (its all-reduce ran meanwhile)
         entry = self.graphs.get(T_b)
         if entry is None:
             entry = self._capture(T_b)
@@ -190,11 +204,8 @@ class GraphedShardedStep(object):
         # gradient rows to their owners first, then the dense all-reduce runs on the NCCL stream WHILE the owner
         # reduces its rows and updates its table shard (HBM-bound); the dense update waits for the all-reduce
         model.emb_grad = model.sharded_table.push_grads(cache_grad[:U], scale=1.0)
-        work = None
-        if W > 1:
-            work = self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)
         self.opt.step(grad_scale=1.0 / W, dense=False)
-        if work is not None:
-            work.wait()
-        self.opt.step(grad_scale=1.0 / W, rows=False)
+        self._pending = True
+        if W > 1:
+            self._pending = self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.SUM, group=self.ar_group, async_op=True)
         return out

@@ -106,6 +106,13 @@ class FusedAdamW(object):
                 else:
                     L.call("b200rec_adamw_tick", self._coef.data_ptr(), b1, b2, st)
             coef = self._coef.data_ptr()
+        if self.device_step and rows and not dense:
+            # the dense half may run after the next step's lr was set: it keeps the scalars of ITS step
+            if getattr(self, "_coef_pending", None) is None:
+                self._coef_pending = torch.empty_like(self._coef)
+            self._coef_pending.copy_(self._coef)
+        elif self.device_step and dense and not rows and getattr(self, "_coef_pending", None) is not None:
+            coef = self._coef_pending.data_ptr()
         dense_list = []
         for p in self.model.parameters():
             if p is emb and self.lazy_table and p.grad is not None:

@@ -186,16 +186,22 @@ class Trainer(object):
                     self._log(f"Finished training, best eval result at step "
                               f"{self.train_step - self.no_improve_times * self.eval_interval}")
                     break
+        self._flush_step()
         self.model.eval()
         return self.best_valid_score, self.best_valid_result
 
     # ------------------------------------------------------------------ evaluate (trainer.py:698-729, 826-1153)
+    def _flush_step(self):
+        if self._stepper is not None and hasattr(self._stepper, "flush"):
+            self._stepper.flush()                  # pending dense update of the sharded step
+
     @torch.no_grad()
     def evaluate(self, eval_data, all_item_tags=None, all_tags_NC=None):
         """Full-sort evaluation.  all_item_tags [C, N] (bool / 0-1; this rank's columns when the table is sharded)
         masks items per prior head; all_tags_NC [N, C] feeds the Entropy metric.  Returns
         {'pred_p': {metric: mean over users}} (+ 'shared')."""
         model, cfg = self.model, self.config
+        self._flush_step()
         model.eval()
         dev = next(model.parameters()).device
         self.item_feature = model.compute_item_all()                       # trainer.py:790
@@ -258,6 +264,7 @@ class Trainer(object):
         return sd
 
     def save_checkpoint(self, path=None):
+        self._flush_step()
         sd = self._full_state_dict()
         opt = self.optimizer
         if self.rank != 0 and not self.sharded:

@@ -139,6 +139,7 @@ def _graphed_vs_eager(dev, rank, world, steps=3):
             stepper = GraphedShardedStep(model, opt, batches[0], bucket=32)
             for b in batches:
                 stepper(b, int(b[2][:, :Lc].sum()))
+            stepper.flush()
         models.append(model)
     torch.cuda.synchronize()
     worst = 0.0
