@@ -18,7 +18,11 @@ SMALL = dict(n_layers=2, n_heads=2, item_embedding_size=32, hstu_embedding_size=
     ("A", dict(train_batch_size=16, num_negatives=64, item_num=500)),
     ("B", SMALL), ("D", SMALL), ("C", SMALL),
     ("D", dict(SMALL, num_segment_head=2, pred_len=4, eval_pred_len=4)),
-])
+    ("B", dict(SMALL, item_embedding_size=24)),                                     # item_id_proj_tower
+    ("D", dict(SMALL, medusa_num_layers=2)),                                        # weight-tied 2-layer heads
+    ("D", dict(SMALL, head_interaction="hierarchical", num_segment_head=2, pred_len=4, eval_pred_len=4,
+               medusa_num_layers=2)),                                              # seg[c][s](cat[c](x))
+], ids=["nce", "additive", "mult", "event", "mult-2seg", "tower", "tied-2layer", "hierarchical"])
 def test_train_step_matches_reference(preset, over):
     cfg = synth.make_config(preset, **over)
     dl = synth.make_dataload(cfg)
