@@ -104,8 +104,14 @@ def _shard_worker(rank, world, port, q):
                                row_gather=_torch_row_gather, segment_reduce=_torch_segment_reduce)
     g = torch.Generator().manual_seed(7 + rank)
     ids = torch.unique(torch.randint(0, N, (11,), generator=g))
-    rows = st.fetch(ids)
-    ok_fetch = torch.equal(rows, full[ids])
+    seen = []
+    st.pre_gather = lambda idx: seen.append(idx.clone())          # hook of the lazy table update
+    cache = torch.full((N, D), -1.0)
+    rows = st.fetch(ids, out=cache)                                # rows land in the caller's static cache
+    ok_fetch = torch.equal(rows, full[ids]) and rows.data_ptr() == cache.data_ptr() \
+        and torch.equal(cache[ids.numel():], torch.full((N - ids.numel(), D), -1.0))
+    # the owner was told exactly which local rows it is about to read (requests of BOTH ranks, local indices)
+    ok_fetch = ok_fetch and len(seen) == 1 and bool((seen[0] * world + rank < N).all())
     grads = torch.randn(ids.numel(), D, generator=g)
     lid, lrows, nu = st.push_grads(grads, scale=0.5)
     negs = parallel.gather_negative_ids(torch.full((2, 3, 2), rank, dtype=torch.int64))
@@ -154,3 +160,43 @@ def test_merge_topk_tie_rule():
     h = torch.zeros(1, 3, dtype=torch.int32)
     idx, val, _ = parallel.merge_topk([v0, v1], [i0, i1], [h, h], 4)
     assert idx.tolist() == [[1, 4, 7, 2]] and val.tolist() == [[5.0, 5.0, 4.0, 3.0]]
+
+
+# ---------------------------------------------------------------------------- trainer metric reduction
+def _reduce_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from b200rec import trainer as T
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(2))
+            self.sharded_table = None
+
+    cfg = dict(optim_args=dict(learning_rate=1e-2, weight_decay=0.0), total_iters=10, metrics_pred_len_list=[0],
+               eval_pred_len=1, metric_decimal_place=4)
+    tr = T.Trainer(cfg, M(), optimizer=object(), use_graph=False)
+    # per-rank SUMS over users (metrics.py) + per-category (sum, count) tuples -> global means (trainer.py:1097-1123)
+    res = {"recall@10": 3.0 + rank, "cat0-recall@10": (1.0 + rank, 2 + rank)}
+    q.put((rank, tr._reduce(res, num_total=10 + 10 * rank)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_trainer_metric_reduction_world2():
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_reduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, out in res:
+        assert out == {"recall@10": round(7.0 / 30.0, 4), "cat0-recall@10": round(3.0 / 5.0, 4)}
