@@ -16,7 +16,6 @@ Restructurings relative to the reference (each proven equal on valid rows, SURVE
 Not implemented (raise): head_interaction='hierarchical', prior_switch, medusa_num_layers > 1,
 item_embedding_size != hstu_embedding_size, dropout > 0 in training mode.
 """
-import math
 from collections import defaultdict
 from logging import getLogger
 

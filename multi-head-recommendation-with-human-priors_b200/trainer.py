@@ -16,7 +16,6 @@ import time
 import torch
 import torch.distributed as dist
 
-from . import _lib as L
 from .evaluator import Collector, Evaluator
 from .optim import FusedAdamW
 
