@@ -199,6 +199,7 @@ class HSTU(nn.Module):
         self._heads_upper = []     # (input, pre-activation) of the weight-tied decode-head layers above the first
         # set by FusedAdamW(lazy_table=True): bring table rows up to date before they are read
         self._table_sync = self._table_flush = None
+        self._simt_len = 0         # extra sequence-length bound for the SIMT attention launch (static-token mode)
         self.emb_grad = None       # (uniq_ids, uniq_rows, n_uniq) of the last backward
         self._table_cache = None   # normalised compute-dtype item table for predict
         self._verbose = False
@@ -460,8 +461,11 @@ class HSTU(nn.Module):
                 L.call("b200rec_hstu_attn_tc_fwd", actv.data_ptr(), 4 * D, seq_off.data_ptr(), key_valid.data_ptr(), B,
                        T, nh, dh, 1.0 / n_pad, a.data_ptr(), st)
             else:
+                # the launch geometry must cover the LONGEST sequence: in static-token mode the trailing dummy
+                # sequence can be longer than the model's max_seq_length (self._simt_len bounds it by T)
                 L.call("b200rec_hstu_attn_fwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), 4 * D, a_dt,
-                       seq_off.data_ptr(), key_valid.data_ptr(), B, T, nh, dh, 1.0 / n_pad, max_len, a.data_ptr(), st)
+                       seq_off.data_ptr(), key_valid.data_ptr(), B, T, nh, dh, 1.0 / n_pad,
+                       max(max_len, self._simt_len), a.data_ptr(), st)
             oin = torch.empty((T, D), dtype=act, device=dev)
             mean2 = torch.empty(T, dtype=torch.float32, device=dev)
             rstd2 = torch.empty(T, dtype=torch.float32, device=dev)
@@ -516,7 +520,8 @@ class HSTU(nn.Module):
             else:
               L.call("b200rec_hstu_attn_bwd", sl(actv, 2).data_ptr(), sl(actv, 3).data_ptr(), sl(actv, 1).data_ptr(),
                    sl(pre, 2).data_ptr(), sl(pre, 3).data_ptr(), sl(pre, 1).data_ptr(), 4 * D, a_dt,
-                   seq_off.data_ptr(), key_valid.data_ptr(), B, T, nh, dh, 1.0 / n_pad, max_len, da.data_ptr(),
+                   seq_off.data_ptr(), key_valid.data_ptr(), B, T, nh, dh, 1.0 / n_pad,
+                   max(max_len, self._simt_len), da.data_ptr(),
                    sl(d_pre, 2).data_ptr(), sl(d_pre, 3).data_ptr(), sl(d_pre, 1).data_ptr(), st)
             # dW_uvqk[D, 4D] = n^T @ d_pre  (both MN-major, K = T)
             dWu = torch.empty((D, 4 * D), dtype=torch.float32, device=dev)
@@ -701,6 +706,7 @@ class HSTU(nn.Module):
         x = torch.empty((T, D), dtype=torch.float32, device=dev)
         L.call("b200rec_embed_tokens", W.data_ptr(), self.position_embedding.weight.data_ptr(), items.data_ptr(),
                tok_b.data_ptr(), tok_pos.data_ptr(), T, LP, D, x.data_ptr(), st)
+        self._simt_len = T if static else 0      # dummy sequence of static-token mode: up to T tokens long
         y, saved = self._body_forward(x, w, seq_off, key_valid, B, T, Lc, Lc, need_grad)
         hd, z, yb = self._heads_forward(y, w, T)
         Hx = hd.shape[1]
@@ -812,7 +818,8 @@ class HSTU(nn.Module):
         loss = total * half
         if need_grad:
             ctx = dict(B=B, LP=LP, T=T, tok_b=tok_b, tok_pos=tok_pos, seq_off=seq_off, key_valid=key_valid,
-                       tok_index=tok_index, w=w, saved=saved, hd=hd, z=z, yb=yb, heads_upper=list(self._heads_upper), hier_tape=getattr(self, "_hier_tape", None), y=y, qhat=qhat, qinv=qinv, that=that,
+                       tok_index=tok_index, w=w, saved=saved, hd=hd, z=z, yb=yb, heads_upper=list(self._heads_upper), hier_tape=getattr(self, "_hier_tape", None), y=y,
+                       simt_len=self._simt_len, qhat=qhat, qinv=qinv, that=that,
                        tinv=tinv, nhat=nhat, ninv=ninv, neg_ids=neg_ids, job_out=job_out, scale=scale, half=half,
                        items=items, mask=m, n_neg=n_neg, ld_neg=ld_neg, Hx=Hx, used_sets=used_sets,
                        gl_items=gl_items, gl_neg_ids=gl_neg_ids, uniq_rows_ids=uniq_rows_ids,
@@ -915,6 +922,7 @@ class HSTU(nn.Module):
         else:
             L.call("b200rec_resblock_bwd", d_hd.data_ptr(), None, a_dt, T, Hx, D, None, dy.data_ptr(), st)
         # ---- body
+        self._simt_len = ctx["simt_len"]
         dx0 = self._body_backward(dy, ctx["saved"], w, ctx["seq_off"], ctx["key_valid"], B, T, Lc, Lc, grads)
         # ---- position embedding (rows 0..L-1 used; row L never, hstu.py:380,640-643)
         dpos = torch.zeros_like(self.position_embedding.weight.data)
@@ -1040,6 +1048,7 @@ class HSTU(nn.Module):
             seq_idx = torch.arange(B * Ls, dtype=torch.int64, device=dev).view(B, Ls)
         L.call("b200rec_embed_tokens", table.data_ptr(), self.position_embedding.weight.data_ptr(),
                seq_idx.data_ptr(), tok_b.data_ptr(), tok_pos.data_ptr(), T, Ls, D, x.data_ptr(), st)
+        self._simt_len = 0
         y, _ = self._body_forward(x, w, seq_off, key_valid, B, T, Ls, Ls, False)
         last = (seq_off[1:] - 1).long()
         y_last = torch.empty((B, D), dtype=torch.float32, device=dev)
