@@ -19,7 +19,7 @@ class InteractionData(object):
     """
 
     def __init__(self, user_seq, train_seq_len, item_num, max_seq_length, item_tags=None, event_seq=None,
-                 device="cuda"):
+                 device="cuda", sample_last_only=False, pred_len=1, include_empty_context=False):
         self.device = torch.device(device)
         self.item_num, self.L = int(item_num), int(max_seq_length)
         lens = np.asarray([len(s) for s in user_seq], dtype=np.int64)
@@ -48,16 +48,27 @@ class InteractionData(object):
             np.cumsum([p.numel() for p in pools], out=co[1:])
             self.cat_items = torch.cat(pools).to(torch.int64).to(self.device)
             self.cat_off = torch.from_numpy(co).to(self.device)
-        # valid_sample_locations (dataload.py:180-194): non-overlapping windows of stride L+1 anchored at the end
-        # of each user's training prefix
+        # valid_sample_locations (dataload.py:165-194; the reference's max_item_list_len is L + 1): one window for
+        # a short training prefix, else non-overlapping windows of stride L + 1 anchored at the end of the prefix
+        # (the first of them may have an empty context: context_end == 0 when (n - 1) % (L + 1) == 0)
         uid, end = [], []
+        stride = self.L + 1
         for u in range(1, len(user_seq)):
             n = int(self.h_train_len[u])
-            e = n - 1
-            while e >= 1:
-                uid.append(u)
-                end.append(e)
-                e -= self.L + 1
+            if n <= 1:
+                continue
+            if sample_last_only:                                  # dataload.py:173-177 (Amazon Books)
+                locs = [n - 1] if n < pred_len + 3 else [n - pred_len]
+            elif n <= stride:
+                locs = [n - 1]
+            else:
+                locs = list(range((n - 1) % stride, n, stride))
+            if not include_empty_context:
+                # a window with context_end == 0 has no query position: it adds no loss term and no gradient, only an
+                # idle batch row.  Dropped by default; include_empty_context=True reproduces the reference's list.
+                locs = [e for e in locs if e > 0]
+            uid += [u] * len(locs)
+            end += locs
         self.h_sample_uid = np.asarray(uid, dtype=np.int64)
         self.h_sample_end = np.asarray(end, dtype=np.int32)
         self.sample_uid = torch.from_numpy(self.h_sample_uid).to(self.device)

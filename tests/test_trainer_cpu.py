@@ -69,3 +69,23 @@ def test_calculate_valid_score_picks_last_offset():
     res = {"pred_0": {"recall@10": 0.1, "ndcg@10": 0.05}, "pred_3": {"recall@10": 0.4, "ndcg@10": 0.2}}
     assert T.calculate_valid_score(res, 4, "NDCG@10") == 0.2
     assert T.calculate_valid_score(res, 4, None) == 0.4
+
+
+def test_interaction_data_host_layout():
+    """b200rec.batcher.InteractionData (host side, no kernels): CSR layout, per-category pools without id 0 and the
+    reference's training-window locations (dataload.py:165-194 with max_item_list_len = L + 1)."""
+    from b200rec.batcher import InteractionData
+    L = 4
+    user_seq = [[], list(range(1, 3)), list(range(1, 6)), list(range(1, 12)), list(range(1, 14)), [7]]
+    train_len = [0, 2, 5, 11, 13, 1]
+    tags = torch.tensor([[1, 0], [1, 0], [0, 1], [1, 1]] + [[0, 1]] * 10, dtype=torch.bool)   # item 0 tagged: must not enter pools
+    d = InteractionData(user_seq, train_len, 14, L, item_tags=tags, device="cpu", include_empty_context=True)
+    assert d.user_off.tolist() == [0, 0, 2, 7, 18, 31, 32] and d.user_seq[2:7].tolist() == [1, 2, 3, 4, 5]
+    # n=2 -> (1, 1); n=5 <= L+1 -> (2, 4); n=11 -> offset 0: 0, 5, 10; n=13 -> offset 2: 2, 7, 12; n=1 -> none
+    want = [(1, 1), (2, 4), (3, 0), (3, 5), (3, 10), (4, 2), (4, 7), (4, 12)]
+    assert list(zip(d.h_sample_uid.tolist(), d.h_sample_end.tolist())) == want and len(d) == 8
+    assert d.cat_off.tolist() == [0, 2, 14] and d.cat_items[:2].tolist() == [1, 3] and d.cat_items[2:].tolist() == list(range(2, 14))
+    d3 = InteractionData(user_seq, train_len, 14, L, device="cpu")            # default: the empty-context window is dropped
+    assert list(zip(d3.h_sample_uid.tolist(), d3.h_sample_end.tolist())) == [w for w in want if w[1] > 0]
+    d2 = InteractionData(user_seq, train_len, 14, L, device="cpu", sample_last_only=True, pred_len=2)
+    assert list(zip(d2.h_sample_uid.tolist(), d2.h_sample_end.tolist())) == [(1, 1), (2, 3), (3, 9), (4, 11)]
