@@ -1006,6 +1006,7 @@ class HSTU(nn.Module):
         """hstu.py:1018-1021: L2-normalised (projected) item table, fp32 [N, D]."""
         if self._table_flush is not None:
             self._table_flush()
+        self._table_cache = None        # the cached compute-dtype catalogue of predict() belongs to the previous table
         W = self.item_embedding.weight.data
         N = W.shape[0]
         D = self._hstu_embedding_dim

@@ -74,7 +74,10 @@ class FusedAdamW(object):
             # re-reads the pinned buffer at replay, so the buffers are kept alive for the optimizer's life)
             raw_h = torch.frombuffer(bytearray(b"".join(recs)), dtype=torch.uint8).pin_memory()
             blk_h = torch.tensor(blocks, dtype=torch.int64).pin_memory()
-            self._keepalive.append((raw_h, blk_h))
+            if torch.cuda.is_current_stream_capturing():
+                self._keepalive.append((raw_h, blk_h))     # a graph re-reads its staging buffers at every replay
+            else:
+                self._eager_staging = (raw_h, blk_h)       # eager: the host allocator defers reuse until the copy ran
             self._table = raw_h.to(dev, non_blocking=True)
             self._blocks = blk_h.to(dev, non_blocking=True)
             self._table_key = key
