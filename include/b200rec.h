@@ -330,15 +330,17 @@ int b200rec_adamw_tick(float* coef_dev, float beta1, float beta2, void* stream);
  * lr / (1-beta1^j), 1 / sqrt(1-beta2^j), lr} of every step j, written by b200rec_adamw_tick_hist (which replaces b200rec_adamw_tick).
  *   b200rec_adamw_rows_catchup  brings the rows `ids` (duplicates allowed; NULL = all n_ids = n_rows rows) up to
  *                               the current step BEFORE something reads them (lookups, eval, checkpoint);
- *   b200rec_adamw_rows_lazy     applies the current step (tick already run) to the rows with a gradient. */
+ *   b200rec_adamw_rows_lazy     applies the current step (tick already run) to the rows with a gradient.
+ * hist is a RING of hist_cap (a power of two) entries indexed by step & (hist_cap - 1): the caller must bring every
+ * row up to date (catchup with ids = NULL) at least once per hist_cap - 1 steps, so no row ever looks back further. */
 int b200rec_adamw_tick_hist(float* coef_dev, void* hist, int cap, float beta1, float beta2,
                             float weight_decay, void* stream);
 int b200rec_adamw_rows_catchup(float* p, float* m, float* v, int64_t n_rows, int D, const int64_t* ids,
-                               int64_t n_ids, int32_t* last, const void* hist, const float* coef_dev,
+                               int64_t n_ids, int32_t* last, const void* hist, int hist_cap, const float* coef_dev,
                                float beta1, float beta2, float eps, float weight_decay, void* stream);
 int b200rec_adamw_rows_lazy(float* p, float* m, float* v, int64_t n_rows, int D, const int64_t* uniq_ids,
                             const float* uniq_rows, const int32_t* n_uniq, int64_t max_rows, int32_t* last,
-                            const void* hist, const float* coef_dev, float beta1, float beta2, float eps,
+                            const void* hist, int hist_cap, const float* coef_dev, float beta1, float beta2, float eps,
                             float weight_decay, float grad_scale, void* stream);
 /* One launch for many dense tensors: table_dev = array of {float* p, m, v; const float* g; bf16* shadow;
  * int64 n}, blocks_dev = int64 pairs {tensor index, first element of a 4096-element chunk}.  `shadow`

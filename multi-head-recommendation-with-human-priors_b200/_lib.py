@@ -88,8 +88,8 @@ _SIGS = {
     "b200rec_score_mask_topk": (C.c_int, [_P, _L, _I, _I, _L, _I, _P, _P, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _Z,
                                           _P]),
     "b200rec_adamw_tick_hist": (C.c_int, [_P, _P, _I, _F, _F, _F, _P]),
-    "b200rec_adamw_rows_catchup": (C.c_int, [_P, _P, _P, _L, _I, _P, _L, _P, _P, _P, _F, _F, _F, _F, _P]),
-    "b200rec_adamw_rows_lazy": (C.c_int, [_P, _P, _P, _L, _I, _P, _P, _P, _L, _P, _P, _P, _F, _F, _F, _F, _F, _P]),
+    "b200rec_adamw_rows_catchup": (C.c_int, [_P, _P, _P, _L, _I, _P, _L, _P, _P, _I, _P, _F, _F, _F, _F, _P]),
+    "b200rec_adamw_rows_lazy": (C.c_int, [_P, _P, _P, _L, _I, _P, _P, _P, _L, _P, _P, _I, _P, _F, _F, _F, _F, _F, _P]),
     "b200rec_build_train_batch": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _I, _I, _P, _P, _I, _F, _P, _I,
                                             C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P]),
     "b200rec_build_eval_batch": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P]),

@@ -255,7 +255,7 @@ __global__ void adamw_tick_hist_kernel(float* coef, float4* hist, int cap, float
   coef[2] = sqrtf(1.f - powf(b2, step));
   int j = (int)step;
   const RowStep r = row_step(coef[0], coef[1], coef[2], wd);
-  if (j < cap) hist[j] = make_float4(r.decay, r.step_size, r.inv_bc2, coef[0]);
+  hist[j & (cap - 1)] = make_float4(r.decay, r.step_size, r.inv_bc2, coef[0]);   // ring: cap is a power of two
 }
 
 extern "C" int b200rec_adamw_tick_hist(float* coef_dev, void* hist, int cap, float beta1, float beta2,
@@ -268,7 +268,7 @@ extern "C" int b200rec_adamw_tick_hist(float* coef_dev, void* hist, int cap, flo
 template <int MAXV>
 __device__ __forceinline__ void lazy_catch_up(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                                               int64_t row, int D4, int from, int to, const float4* __restrict__ hist,
-                                              AdamCoef c, const float* __restrict__ grow, bool with_grad) {
+                                              int hmask, AdamCoef c, const float* __restrict__ grow, bool with_grad) {
   // steps from+1 .. to with zero gradient; if with_grad, step to+1 follows with gradient row `grow`
   const int lane = threadIdx.x & 31;
   for (int c0 = 0; c0 < D4; c0 += 32 * MAXV) {
@@ -283,7 +283,7 @@ __device__ __forceinline__ void lazy_catch_up(float* __restrict__ p, float* __re
       }
     }
     for (int j = from + 1; j <= to; ++j) {
-      const float4 h = __ldg(hist + j);
+      const float4 h = __ldg(hist + (j & hmask));
       RowStep rs;
       rs.decay = h.x; rs.step_size = h.y; rs.inv_bc2 = h.z;
 #pragma unroll
@@ -292,7 +292,7 @@ __device__ __forceinline__ void lazy_catch_up(float* __restrict__ p, float* __re
         for (int k = 0; k < 4; ++k) adam_update_row(pp[u][k], mm[u][k], vv[u][k], 0.f, rs, c.b1, c.b2, c.eps);
     }
     if (with_grad) {
-      const float4 h = __ldg(hist + to + 1);
+      const float4 h = __ldg(hist + ((to + 1) & hmask));
       RowStep rs;
       rs.decay = h.x; rs.step_size = h.y; rs.inv_bc2 = h.z;
 #pragma unroll
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(256) adamw_rows_catchup_kernel(float* __restri
                                                                  float* __restrict__ v, int64_t N, int D4,
                                                                  const int64_t* __restrict__ ids, int64_t n_ids,
                                                                  int32_t* __restrict__ last,
-                                                                 const float4* __restrict__ hist, AdamCoef c) {
+                                                                 const float4* __restrict__ hist, int hmask, AdamCoef c) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int S = (int)c.dev[3];                                  // completed optimizer steps
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(256) adamw_rows_catchup_kernel(float* __restri
     if (lane == 0) old = atomicExch(last + row, S);
     old = __shfl_sync(0xffffffffu, old, 0);
     if (old >= S) continue;
-    lazy_catch_up<4>(p, m, v, row, D4, old, S, hist, c, nullptr, false);
+    lazy_catch_up<4>(p, m, v, row, D4, old, S, hist, hmask, c, nullptr, false);
   }
 }
 
@@ -344,43 +344,45 @@ __global__ void __launch_bounds__(256) adamw_rows_lazy_kernel(float* __restrict_
                                                               const float* __restrict__ uniq_rows,
                                                               const int32_t* __restrict__ n_uniq,
                                                               int32_t* __restrict__ last,
-                                                              const float4* __restrict__ hist, AdamCoef c) {
+                                                              const float4* __restrict__ hist, int hmask, AdamCoef c) {
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int S1 = (int)c.dev[3];                                 // the step being applied (tick already ran)
   const int nu = *n_uniq;
   for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nu; i += warps) {
     const int64_t row = uniq_ids[i];                             // unique: no claim needed
     const int old = last[row];
-    lazy_catch_up<4>(p, m, v, row, D4, min(old, S1 - 1), S1 - 1, hist, c, uniq_rows + i * D4 * 4, true);
+    lazy_catch_up<4>(p, m, v, row, D4, min(old, S1 - 1), S1 - 1, hist, hmask, c, uniq_rows + i * D4 * 4, true);
     if ((threadIdx.x & 31) == 0) last[row] = S1;
   }
 }
 
 extern "C" int b200rec_adamw_rows_catchup(float* p, float* m, float* v, int64_t n_rows, int D, const int64_t* ids,
-                                          int64_t n_ids, int32_t* last, const void* hist, const float* coef_dev,
-                                          float beta1, float beta2, float eps, float weight_decay, void* stream) {
-  B200_CHECK_ARG(D % 4 == 0 && coef_dev != nullptr && hist != nullptr && last != nullptr, "adamw_rows_catchup: bad args");
+                                          int64_t n_ids, int32_t* last, const void* hist, int hist_cap,
+                                          const float* coef_dev, float beta1, float beta2, float eps, float weight_decay, void* stream) {
+  B200_CHECK_ARG(D % 4 == 0 && coef_dev != nullptr && hist != nullptr && last != nullptr && hist_cap > 0 &&
+                     (hist_cap & (hist_cap - 1)) == 0, "adamw_rows_catchup: bad args (hist_cap must be a power of two)");
   if (n_ids == 0) return 0;
   AdamCoef c = make_coef(0.f, beta1, beta2, eps, weight_decay, 1, 1.f);
   c.dev = coef_dev;
   int blocks = (int)std::min<int64_t>((n_ids + 7) / 8, 148 * 8);
   adamw_rows_catchup_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, m, v, n_rows, D / 4, ids, n_ids, last,
-                                                                      (const float4*)hist, c);
+                                                                      (const float4*)hist, hist_cap - 1, c);
   B200_LAUNCH_OK();
   return 0;
 }
 
 extern "C" int b200rec_adamw_rows_lazy(float* p, float* m, float* v, int64_t n_rows, int D, const int64_t* uniq_ids,
                                        const float* uniq_rows, const int32_t* n_uniq, int64_t max_rows, int32_t* last,
-                                       const void* hist, const float* coef_dev, float beta1, float beta2, float eps,
-                                       float weight_decay, float grad_scale, void* stream) {
-  B200_CHECK_ARG(D % 4 == 0 && coef_dev != nullptr && hist != nullptr && last != nullptr, "adamw_rows_lazy: bad args");
+                                       const void* hist, int hist_cap, const float* coef_dev, float beta1, float beta2,
+                                       float eps, float weight_decay, float grad_scale, void* stream) {
+  B200_CHECK_ARG(D % 4 == 0 && coef_dev != nullptr && hist != nullptr && last != nullptr && hist_cap > 0 &&
+                     (hist_cap & (hist_cap - 1)) == 0, "adamw_rows_lazy: bad args (hist_cap must be a power of two)");
   if (max_rows == 0 || n_rows == 0) return 0;
   AdamCoef c = make_coef(0.f, beta1, beta2, eps, weight_decay, 1, grad_scale);
   c.dev = coef_dev;
   int blocks = (int)std::min<int64_t>((max_rows + 7) / 8, 148 * 8);
   adamw_rows_lazy_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, m, v, D / 4, uniq_ids, uniq_rows, n_uniq, last,
-                                                                   (const float4*)hist, c);
+                                                                   (const float4*)hist, hist_cap - 1, c);
   B200_LAUNCH_OK();
   return 0;
 }

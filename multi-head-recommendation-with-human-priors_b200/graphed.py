@@ -15,6 +15,11 @@ from . import _lib as L
 class GraphedTrainStep(object):
     def __init__(self, model, optimizer, example_batch, bucket=128, warmup=2):
         assert optimizer.device_step, "GraphedTrainStep needs FusedAdamW(device_step=True)"
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            # the captured step holds no gradient exchange: replicas would silently diverge
+            raise L.B200RecError("GraphedTrainStep is single-GPU; with several ranks shard the table and use "
+                                 "GraphedShardedStep, or run the eager step with parallel.DataParallel")
         self.model, self.opt, self.bucket = model, optimizer, bucket
         self.static = tuple(torch.empty_like(t) for t in example_batch)
         self.graphs = {}
@@ -85,6 +90,7 @@ class GraphedTrainStep(object):
         if self.model.shadows_stale():           # parameters changed outside the graph (load_state_dict, ...)
             self.model.invalidate_shadows()
             self.model._cast_weights()
+        self.opt.rebase_if_due(self.opt.step_count)   # lazy table: the history ring wraps every HIST_CAP steps
         g.replay()
         self.opt.step_count += 1
         L.launches += n_launch

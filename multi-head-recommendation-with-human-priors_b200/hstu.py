@@ -13,8 +13,7 @@ Restructurings relative to the reference (each proven equal on valid rows, SURVE
     target position (hstu.py:600-619 recomputes both per (b, p, l));
   * deterministic sorted-segment embedding gradient instead of atomic index_add;
   * eval: top-K of the max over heads == the collector's per-head top-K + sort + dedupe.
-Not implemented (raise): head_interaction='hierarchical', prior_switch, medusa_num_layers > 1,
-item_embedding_size != hstu_embedding_size, dropout > 0 in training mode.
+Not implemented (raise at construction, never a silent fallback): see DESIGN.md section 6.
 """
 from collections import defaultdict
 from logging import getLogger
@@ -1143,18 +1142,35 @@ class HSTU(nn.Module):
                 dist.all_gather(out, t.contiguous(), group=g)
                 return torch.cat(out, dim=0)
 
-            U = gather_cat(U)
+            # ranks may hold different numbers of users (last batch of a strided sampler): pad to the largest
+            bt = torch.tensor([B], device=dev)
+            bts = [torch.zeros_like(bt) for _ in range(Wd)]
+            dist.all_gather(bts, bt, group=g)
+            Bmax = max(int(b.item()) for b in bts)
+
+            def pad_rows(t, fill=0):
+                if t.shape[0] == Bmax:
+                    return t
+                out = torch.full((Bmax,) + tuple(t.shape[1:]), fill, dtype=t.dtype, device=dev)
+                out[:t.shape[0]] = t
+                return out
+
+            U = gather_cat(pad_rows(U))
             if head_on is not None:
-                head_on = gather_cat(head_on)
-            if hu is not None:   # ragged (user, item) pairs: pad to the max count, shift users by rank*B
-                cnt = torch.tensor([hu.numel()], device=dev)
-                cnts = [torch.zeros_like(cnt) for _ in range(Wd)]
-                dist.all_gather(cnts, cnt, group=g)
-                mx = max(int(c.item()) for c in cnts)
+                head_on = gather_cat(pad_rows(head_on))
+            # ragged (user, item) pairs: pad to the max count, shift users by rank * Bmax; every rank takes part in
+            # the exchange even when it passes no history (collectives must match across ranks)
+            n_h = 0 if hu is None else hu.numel()
+            cnt = torch.tensor([n_h, 0 if hu is None else 1], device=dev)
+            cnts = [torch.zeros_like(cnt) for _ in range(Wd)]
+            dist.all_gather(cnts, cnt, group=g)
+            if any(int(c[1].item()) for c in cnts):
+                mx = max(1, max(int(c[0].item()) for c in cnts))
                 pu = torch.full((mx,), -1, dtype=torch.int64, device=dev)
                 pi = torch.zeros((mx,), dtype=torch.int64, device=dev)
-                pu[:hu.numel()] = hu + rank * B
-                pi[:hi.numel()] = hi
+                if n_h:
+                    pu[:n_h] = hu + rank * Bmax
+                    pi[:n_h] = hi
                 pu, pi = gather_cat(pu), gather_cat(pi)
                 hu, hi = pu[pu >= 0], pi[pu >= 0]
         Ball = U.shape[0]
@@ -1222,7 +1238,7 @@ class HSTU(nn.Module):
         for t in (val, idx, hsrc):
             r = torch.empty_like(t)
             dist.all_to_all_single(r, t.contiguous(), group=st_.group)
-            outs.append(r.view(Wd, B, K))
+            outs.append(r.view(Wd, Bmax, K)[:, :B])
         v, i, h = outs
         return parallel.merge_topk(list(v), list(i), list(h), K)
 

@@ -14,7 +14,9 @@ from . import _lib as L
 
 
 class FusedAdamW(object):
-    HIST_CAP = 1 << 20     # optimizer steps whose scalars the lazy table update can look back to
+    # The lazy table update keeps the scalars of the last HIST_CAP optimizer steps in a ring; every HIST_CAP // 2 steps
+    # all rows are brought up to date (one dense pass) so that no row ever needs an entry that was overwritten.
+    HIST_CAP = 1 << 16
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, device_step=False,
                  lazy_table=False):
@@ -103,8 +105,7 @@ class FusedAdamW(object):
             if first_half:
                 if self.lazy_table:
                     self._lazy_state(completed=self.step_count - 1)
-                    if self.step_count >= self.HIST_CAP:
-                        raise L.B200RecError("lazy_table: optimizer step history exhausted (HIST_CAP)")
+                    self.rebase_if_due(self.step_count - 1)
                     L.call("b200rec_adamw_tick_hist", self._coef.data_ptr(), self._hist.data_ptr(), self.HIST_CAP, b1, b2, wd, st)
                 else:
                     L.call("b200rec_adamw_tick", self._coef.data_ptr(), b1, b2, st)
@@ -129,7 +130,7 @@ class FusedAdamW(object):
                 if self.lazy_table:
                     L.call("b200rec_adamw_rows_lazy", p.data_ptr(), m.data_ptr(), v.data_ptr(), N, D, uniq_ids.data_ptr(),
                            uniq_rows.data_ptr(), n_uniq.data_ptr(), uniq_ids.numel(), self._last.data_ptr(),
-                           self._hist.data_ptr(), coef, b1, b2, eps, wd, grad_scale, st)
+                           self._hist.data_ptr(), self.HIST_CAP, coef, b1, b2, eps, wd, grad_scale, st)
                     continue
                 if self._row_slot is None or self._row_slot.numel() != N:
                     self._row_slot = torch.empty(N, dtype=torch.int32, device=p.device)
@@ -175,11 +176,18 @@ class FusedAdamW(object):
         if ids is not None:
             ids = ids.reshape(-1).contiguous()
         L.call("b200rec_adamw_rows_catchup", emb.data_ptr(), m.data_ptr(), v.data_ptr(), N, D, L.ptr(ids),
-               N if ids is None else ids.numel(), self._last.data_ptr(), self._hist.data_ptr(), self._coef.data_ptr(),
-               b1, b2, eps, wd, L.stream())
+               N if ids is None else ids.numel(), self._last.data_ptr(), self._hist.data_ptr(), self.HIST_CAP,
+               self._coef.data_ptr(), b1, b2, eps, wd, L.stream())
 
     def flush(self):
         self.sync_rows(None)
+
+    def rebase_if_due(self, completed):
+        """Called (outside any graph capture / replay) before step `completed + 1`: when half of the history ring
+        has been consumed since the last full pass, every row is brought up to date so the ring can wrap."""
+        if self.lazy_table and completed > 0 and completed % (self.HIST_CAP // 2) == 0 and \
+                not torch.cuda.is_current_stream_capturing():
+            self.flush()
 
     def mark_all_current(self):
         """After loading a checkpoint: every row holds the state of step `step_count`."""

@@ -25,11 +25,11 @@ def constant_schedule(step, warmup_steps=0, total_steps=0):
     return 1.0
 
 
-def linear_schedule_with_warmup(step, warmup_steps, total_steps):
-    """lr_scheduler.py:44-76 (lr_end = 0)."""
+def linear_schedule_with_warmup(step, warmup_steps, total_steps, lr_end=1e-7):
+    """lr_scheduler.py:44-76 (the multiplier never drops below lr_end = 1e-7)."""
     if step < warmup_steps:
         return float(step) / float(max(1, warmup_steps))
-    return max(0.0, float(total_steps - step) / float(max(1, total_steps - warmup_steps)))
+    return max(lr_end, float(total_steps - step) / float(max(1, total_steps - warmup_steps)))
 
 
 def cosine_schedule_with_warmup(step, warmup_steps, total_steps, num_cycles=0.5):
@@ -78,6 +78,10 @@ class Trainer(object):
         wd = float(oa.get("weight_decay", config.get("weight_decay", 0.0) or 0.0))
         self.sharded = getattr(model, "sharded_table", None) is not None
         self.use_graph = bool(use_graph) and next(model.parameters()).is_cuda
+        if self.world > 1 and not self.sharded:
+            # replicated table on several ranks: the captured single-GPU step contains no gradient exchange (and would
+            # capture the negative-id all-gather); only the eager step synchronises gradients (DataParallel)
+            self.use_graph = False
         if optimizer is None:
             model.sparse_embedding_grad = True
             optimizer = FusedAdamW(model, lr=self.base_lr, weight_decay=wd,
@@ -213,7 +217,24 @@ class Trainer(object):
             collector.set_all_tags(all_tags_NC)
         num_total = 0
         K = max(cfg["topk"])
-        for ev in eval_data:
+        lockstep = self.sharded and self.world > 1       # sharded predict_topk is a collective: ranks stay in step
+        it = iter(eval_data)
+        while True:
+            ev = next(it, None)
+            if lockstep:
+                more = torch.tensor([0 if ev is None else 1], dtype=torch.int32, device=dev)
+                dist.all_reduce(more, op=dist.ReduceOp.MAX)
+                if int(more.item()) == 0:
+                    break
+            elif ev is None:
+                break
+            if ev is None:
+                # this rank ran out of users first: it still scores the other ranks' users against its rows
+                Pe = cfg["eval_pred_len"]
+                seq = torch.zeros((1, model.max_seq_length), dtype=torch.int64, device=dev)
+                tt = torch.ones((1, Pe, C), dtype=torch.int64, device=dev)
+                model.predict_topk(seq, self.item_feature, all_item_tags, tt, history_index=None, K=K)
+                continue
             seq = ev["item_seq"].to(dev)
             tt = ev["target_tags"].to(dev)
             hu, hi = ev["history_index"]
@@ -274,7 +295,10 @@ class Trainer(object):
         state = {"model": {k: v.cpu() for k, v in sd.items()},
                  "optimizer": {"state": opt_state, "step_count": opt.step_count, "shard": (self.rank, self.world)},
                  "config": dict(self.config), "iter_idx": self.train_step,
-                 "best_valid_score": self.best_valid_score, "rng_state": torch.get_rng_state()}
+                 "best_valid_score": self.best_valid_score, "rng_state": torch.get_rng_state(),
+                 # trainer.py:362-363 restores both generators; the Philox dropout stream is keyed by a step counter
+                 "cuda_rng_state": torch.cuda.get_rng_state() if torch.cuda.is_available() else None,
+                 "dropout_step": None if self.model._rng_step is None else int(self.model._rng_step.item())}
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
         torch.save(state, path)
         return path
@@ -303,4 +327,13 @@ class Trainer(object):
         opt.mark_all_current()
         self.train_step = state["iter_idx"]
         self.best_valid_score = state["best_valid_score"]
+        if state.get("rng_state") is not None:
+            torch.set_rng_state(state["rng_state"])
+        if state.get("cuda_rng_state") is not None and torch.cuda.is_available():
+            torch.cuda.set_rng_state(state["cuda_rng_state"])
+        if state.get("dropout_step") is not None:
+            dev = next(model.parameters()).device
+            if model._rng_step is None or model._rng_step.device != dev:
+                model._rng_step = torch.zeros(1, dtype=torch.int64, device=dev)
+            model._rng_step.fill_(int(state["dropout_step"]))      # in place: captured graphs read this buffer
         return state                               # captured graphs read parameters / state in place: still valid

@@ -122,3 +122,85 @@ def test_batcher_feeds_the_model():
     out["loss"].backward()
     assert torch.isfinite(out["loss"]) and model.item_embedding.weight.grad.abs().sum() > 0
     assert batch[1].shape[1] == C + 1
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Against the LIVE reference datasets: tests/golden/data_layer.pt holds every row SEQTrainDataset.__getitem__
+# (trainset.py:99-177) and SeqEvalDataset + seq_eval_collate (evalset.py:81-155, collate_fn.py:59-90) produced for
+# a synthetic interaction set (tests/golden/make_golden_data.py).  Deterministic fields must be identical; the
+# sampled fields (random pads, negatives: numpy RNG there, Philox here) must obey the same law on both sides.
+def _fixture():
+    import os
+    from conftest import ROOT
+    return torch.load(os.path.join(ROOT, "tests", "golden", "data_layer.pt"), weights_only=False)["data_layer"]
+
+
+def _fixture_data(d, variant):
+    from b200rec.batcher import InteractionData
+    ev = variant == "event"
+    return InteractionData(d["user_seq"], d["train_seq_len"], d["N"], d["L"], item_tags=None if ev else d["item_tags"],
+                           event_seq=d["event_seq"] if ev else None, pred_len=d["P"], include_empty_context=True)
+
+
+def _check_sampling_law(items, neg, mask, tags_table, N, by_cat):
+    real = mask.bool()
+    for r in range(items.shape[0]):
+        row = items[r].tolist()
+        seen = set(items[r][real[r]].tolist())
+        pads = items[r][~real[r]].tolist()
+        assert all(1 <= x < N for x in pads) and not (set(pads) & seen)          # trainset.py:111-122
+        for s_ in range(neg.shape[1]):
+            ns = neg[r, s_].tolist()
+            assert len(set(ns)) == len(ns) and all(1 <= x < N for x in ns)        # rng.choice(replace=False)
+            assert not (set(ns) & set(row))                                       # blacklist = the padded row (:126-131)
+            if by_cat and s_ < neg.shape[1] - 1:
+                assert all(bool(tags_table[x, s_]) for x in ns)                   # category pool s_
+
+
+@pytest.mark.parametrize("variant", ["item_bycat", "event", "nce"])
+def test_train_batch_matches_reference_dataset_rows(variant):
+    from b200rec.batcher import GpuTrainBatcher
+    d = _fixture()
+    ref = d["train"][variant]
+    cfg = dict(ref["config"])
+    cfg["seed"] = 9
+    data = _fixture_data(d, variant)
+    assert len(data) == ref["items"].shape[0]
+    (items, neg, mask, tg), n_tok = GpuTrainBatcher(data, cfg).batch(np.arange(len(data)), step=0)
+    items, neg, mask, tg = items.cpu(), neg.cpu(), mask.cpu(), tg.cpu()
+    assert torch.equal(mask, ref["mask"])                                          # trainset.py:133-134
+    real = mask.bool()
+    assert torch.equal(items[real], ref["items"][real])                            # the user's own items, in place
+    assert neg.shape == ref["neg"].shape
+    assert n_tok == int(mask[:, :d["L"]].sum())
+    by_cat = variant == "item_bycat"
+    for side in ((items, neg), (ref["items"], ref["neg"])):                        # same law on both sides
+        _check_sampling_law(side[0], side[1], mask, d["item_tags"], d["N"], by_cat)
+    if variant == "event":
+        assert torch.equal(tg, ref["tags"])                                        # one-hot events, zero on pads (:147-153)
+    elif variant == "item_bycat":
+        assert torch.equal(tg[real], ref["tags"][real])
+        assert torch.equal(tg, d["item_tags"][items].to(torch.int64))              # pads carry their own item's tags (:165-167)
+        assert torch.equal(ref["tags"], d["item_tags"][ref["items"]].to(torch.int64))
+    # marginal law of the global negative set: both samplers are uniform over [1, N)
+    for ng in (neg[:, -1], ref["neg"][:, -1]):
+        cnt = torch.bincount(ng.reshape(-1), minlength=d["N"]).float()
+        mean = float(cnt[1:].mean())
+        assert cnt[0] == 0 and float((cnt[1:] - mean).abs().max()) < 6.0 * max(1.0, mean) ** 0.5
+
+
+@pytest.mark.parametrize("variant", ["item_bycat", "event"])
+@pytest.mark.parametrize("phase", ["valid", "test"])
+def test_eval_batch_matches_reference_collate_fixture(variant, phase):
+    from b200rec.batcher import GpuEvalBatcher
+    d = _fixture()
+    ref = d["eval"][(variant, phase)]
+    cfg = dict(d["train"][variant]["config"])
+    data = _fixture_data(d, variant)
+    out = GpuEvalBatcher(data, cfg).batch(ref["user_ids"].numpy(), phase)
+    assert torch.equal(out["item_seq"].cpu(), ref["item_seq"])
+    assert torch.equal(out["item_target"].cpu(), ref["item_target"])
+    assert torch.equal(out["history_index"][0].cpu(), ref["history_u"])
+    assert torch.equal(out["history_index"][1].cpu(), ref["history_i"])
+    assert torch.equal(out["positive_u"], ref["positive_u"])
+    assert torch.equal(out["target_tags"].cpu(), ref["target_tags"].to(torch.int64))

@@ -455,3 +455,38 @@ def test_lazy_table_adamw_is_bit_identical_to_dense_equivalent():
         for k in sd0:
             assert torch.equal(sd0[k], sd1[k]), (graphed, k)
         assert torch.equal(m0, m1) and torch.equal(v0, v1)
+
+
+def test_lazy_table_history_ring_wraps():
+    """The lazy table keeps per-step scalars in a ring of HIST_CAP entries and brings every row up to date each
+    HIST_CAP // 2 steps (ADVICE r1: the old fixed-size history silently read out of bounds after 2^20 steps).
+    With a ring of 8 entries and 30 steps the result is still bit-identical to the dense-equivalent pass, in the
+    eager loop and through the captured graph."""
+    from b200rec.graphed import GraphedTrainStep
+    fx = load_golden("prior_additive")
+    cfg = synth.Config(fx["cfg"])
+    cfg["sparse_embedding_grad"] = True
+    dl = synth.Dataload(cfg["item_num"], fx["category_counts"], fx["category_to_int"])
+    batches = [tuple(t.to(dev()) for t in synth.make_train_batch(cfg, seed=190 + i, item_tags=fx["item_tags"], zipf=False))
+               for i in range(5)]
+    Lc = cfg["MAX_ITEM_LIST_LENGTH"]
+    for graphed in (False, True):
+        states = []
+        for lazy in (False, True):
+            model = HSTU(cfg, dl, compute_dtype=torch.float32)
+            model.load_state_dict(fx["state_dict"])
+            model = model.to(dev()).eval()
+            opt = FusedAdamW(model, lr=5e-3, weight_decay=0.05, device_step=True, lazy_table=lazy)
+            opt.HIST_CAP = 8
+            stepper = GraphedTrainStep(model, opt, batches[0], bucket=32) if graphed else None
+            for i in range(30):
+                b = batches[i % 5]
+                if graphed:
+                    stepper(b, int(b[2][:, :Lc].sum()))
+                else:
+                    opt.zero_grad()
+                    model(b)["loss"].backward()
+                    opt.step()
+            states.append({k: v.clone() for k, v in model.state_dict().items()})
+        for k in states[0]:
+            assert torch.equal(states[0][k], states[1][k]), (graphed, k)
