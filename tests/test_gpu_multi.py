@@ -157,7 +157,9 @@ def _check_against_reference(name, res, sharded=True):
     from oracle import hstu_oracle as orc
     fx, mfx = load_golden(name), _multi(name)
     g_ref = mfx["grads"]
-    emb_ref = g_ref["item_embedding.weight"]
+    # item table: the NCCL branch's reduce-scatter SUM semantics (`grads_rs`, see make_golden_multi.py: torch's gloo
+    # emulation of the all_gather backward mis-delivers element-wise gradients, so the gloo run pins everything but this)
+    emb_ref = mfx["grads_rs"]["item_embedding.weight"]
     for r in range(W):
         want = mfx["logs"][r]
         got = res[r]["logs"]
