@@ -17,6 +17,13 @@ EPI_STORE, EPI_ACCUM, EPI_SILU_DUAL, EPI_BIAS_RESID, EPI_RESBLOCK, EPI_GT_BITS, 
 _lib = None
 launches = 0  # number of C-ABI kernel entry points invoked (bench.py's gpu_launches claim)
 gemm_timing = None  # bench.py sets this to a list: (start_event, end_event, flops) per GEMM launch
+gemm_timing_external = False  # True while capturing an instrumented CUDA graph: events become external record nodes
+
+
+def _timing_events():
+    if gemm_timing_external:
+        return (torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True))
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
 
 class B200RecError(RuntimeError):
@@ -179,7 +186,7 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epilogue=
     a.n_split, a.c_split_stride, a.c2_split_stride = n_split, 0, 0
     launches += 1
     if gemm_timing is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1 = _timing_events()
         e0.record()
         _check(lib().b200rec_gemm(C.byref(a), stream()), "b200rec_gemm")
         e1.record()
@@ -209,7 +216,7 @@ def gemm_grouped(problems, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epil
         a.epilogue, a.alpha, a.alpha_dev = epilogue, alpha, ptr(alpha_dev)
     launches += (n + 15) // 16 if arr[0].in_dtype == BF16 else n
     if gemm_timing is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1 = _timing_events()
         e0.record()
         _check(lib().b200rec_gemm_grouped(arr, n, stream()), "b200rec_gemm_grouped")
         e1.record()

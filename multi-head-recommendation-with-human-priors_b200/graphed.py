@@ -13,8 +13,12 @@ from . import _lib as L
 
 
 class GraphedTrainStep(object):
-    def __init__(self, model, optimizer, example_batch, bucket=128, warmup=2):
+    def __init__(self, model, optimizer, example_batch, bucket=128, warmup=2, instrument=False):
+        """instrument=True captures an external CUDA event pair around every GEMM launch (bench.py reads them after a
+        replay with `gemm_times()`): kernel times of the REPLAYED graph, not of an eager re-run."""
         assert optimizer.device_step, "GraphedTrainStep needs FusedAdamW(device_step=True)"
+        self.instrument = instrument
+        self.gemm_events = {}
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             # the captured step holds no gradient exchange: replicas would silently diverge
@@ -65,8 +69,15 @@ class GraphedTrainStep(object):
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         n0 = L.launches
-        with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
-            out = self._eager(T_b)
+        if self.instrument:
+            L.gemm_timing, L.gemm_timing_external = [], True
+        try:
+            with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
+                out = self._eager(T_b)
+        finally:
+            if self.instrument:
+                self.gemm_events[T_b] = L.gemm_timing
+                L.gemm_timing, L.gemm_timing_external = None, False
         if self.pool is None:
             self.pool = g.pool()
         for t, c in zip(state, snap):
@@ -76,6 +87,10 @@ class GraphedTrainStep(object):
         self.model.invalidate_shadows()
         self.model._cast_weights()
         return g, out, L.launches - n0
+
+    def gemm_times(self, n_tokens):
+        T_b = min(self.max_tokens, max(self.bucket, (int(n_tokens) + self.bucket - 1) // self.bucket * self.bucket))
+        return _read_gemm_events(self.gemm_events[T_b])
 
     def __call__(self, batch, n_tokens):
         """batch: (items, neg_items, mask, tags) on host (pinned) or device; n_tokens: host int."""
@@ -97,6 +112,11 @@ class GraphedTrainStep(object):
         return out
 
 
+def _read_gemm_events(events):
+    """[(ms, flops)] of the GEMM launches of the last replay (call after a synchronize)."""
+    return [(e0.elapsed_time(e1), fl) for (e0, e1, fl) in events]
+
+
 class GraphedShardedStep(object):
     """Multi-GPU step with a row-sharded item table (`HSTU.shard_item_table`), split in three:
 
@@ -113,8 +133,10 @@ class GraphedShardedStep(object):
     The eager part is ~40 launches instead of ~1200, so the ranks stay GPU-bound.
     """
 
-    def __init__(self, model, optimizer, example_batch, bucket=128, warmup=2, group=None):
+    def __init__(self, model, optimizer, example_batch, bucket=128, warmup=2, group=None, instrument=False):
         import torch.distributed as dist
+        self.instrument = instrument
+        self.gemm_events = {}
         assert model.sharded_table is not None, "call model.shard_item_table() first"
         assert not model._has_tower(), "item_id_proj_tower: use the eager sharded step"
         self.dist, self.group = dist, group
@@ -175,11 +197,22 @@ class GraphedShardedStep(object):
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         n0 = L.launches
-        with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
-            out, cache_grad = self._fwd_bwd(T_b)
+        if self.instrument:
+            L.gemm_timing, L.gemm_timing_external = [], True
+        try:
+            with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
+                out, cache_grad = self._fwd_bwd(T_b)
+        finally:
+            if self.instrument:
+                self.gemm_events[T_b] = L.gemm_timing
+                L.gemm_timing, L.gemm_timing_external = None, False
         if self.pool is None:
             self.pool = g.pool()
         return g, out, cache_grad, L.launches - n0
+
+    def gemm_times(self, n_tokens):
+        T_b = min(self.max_tokens, max(self.bucket, (int(n_tokens) + self.bucket - 1) // self.bucket * self.bucket))
+        return _read_gemm_events(self.gemm_events[T_b])
 
     def flush(self):
         """Dense AdamW of the last step (its all-reduce was left running)."""

@@ -202,6 +202,7 @@ class HSTU(nn.Module):
         self.emb_grad = None       # (uniq_ids, uniq_rows, n_uniq) of the last backward
         self._table_cache = None   # normalised compute-dtype item table for predict
         self._verbose = False
+        self._debug = None         # dict: when set, forward / backward stash clones of key intermediates (diagnostics)
         self.reset_params()
         self._jobs = self._build_jobs()
 
@@ -815,6 +816,9 @@ class HSTU(nn.Module):
         if cur is not None:
             logs.update(cur)
         loss = total * half
+        if self._debug is not None:
+            self._debug.update(x0=x.clone(), y=y.clone(), hd=hd.clone(), qhat=qhat.clone(), that=that.clone(),
+                               per_p=[o["per_p"].clone() for o in job_out])
         if need_grad:
             ctx = dict(B=B, LP=LP, T=T, tok_b=tok_b, tok_pos=tok_pos, seq_off=seq_off, key_valid=key_valid,
                        tok_index=tok_index, w=w, saved=saved, hd=hd, z=z, yb=yb, heads_upper=list(self._heads_upper), hier_tape=getattr(self, "_hier_tape", None), y=y,
@@ -881,6 +885,8 @@ class HSTU(nn.Module):
         if isinstance(self.logit_scale, nn.Parameter):
             grads[self.logit_scale] = (dscale_sum * gscale).reshape(self.logit_scale.shape)
         # ---- through the L2 normalisation of the heads, the ResBlocks, into dy
+        if self._debug is not None:
+            self._debug.update(dqhat=dqhat.clone(), dthat=dthat.clone())
         d_hd = torch.empty((T * Hx, D), dtype=torch.float32, device=dev)
         L.call("b200rec_l2norm_bwd", ctx["qhat"].data_ptr(), a_dt, ctx["qinv"].data_ptr(), dqhat.data_ptr(), T * Hx, D,
                d_hd.data_ptr(), 0, st)
@@ -921,8 +927,12 @@ class HSTU(nn.Module):
         else:
             L.call("b200rec_resblock_bwd", d_hd.data_ptr(), None, a_dt, T, Hx, D, None, dy.data_ptr(), st)
         # ---- body
+        if self._debug is not None:
+            self._debug.update(d_hd=d_hd.clone(), dy=dy.clone())
         self._simt_len = ctx["simt_len"]
         dx0 = self._body_backward(dy, ctx["saved"], w, ctx["seq_off"], ctx["key_valid"], B, T, Lc, Lc, grads)
+        if self._debug is not None:
+            self._debug.update(dx0=dx0.clone())
         # ---- position embedding (rows 0..L-1 used; row L never, hstu.py:380,640-643)
         dpos = torch.zeros_like(self.position_embedding.weight.data)
         L.call("b200rec_pos_emb_grad", dx0.data_ptr(), ctx["tok_index"].data_ptr(), B, LP, Lc, D, dpos.data_ptr(), st)

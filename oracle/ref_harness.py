@@ -9,9 +9,10 @@ It imports /root/reference/code/REC/model/IDNet/hstu.py (HSTU) and
 by stubbing the four logging-only modules that are not installed in this image
 (colorlog, colorama, tensorboardX, pytz) and starting a 1-rank gloo group
 (hstu.py:555 calls torch.distributed.get_rank(); basemodel.py:15 calls
-get_world_size()).  /root/reference only exists in the build container, so
-`available()` is False on the GPU box and callers fall back to the committed
-golden fixtures / the restated oracle.
+get_world_size()).  /root/reference only exists in the build container; on the GPU box
+the verbatim copy under oracle/_ref/ (oracle/build_ref.py, git-ignored) is used, and if
+that is absent too `available()` is False and callers fall back to the committed golden
+fixtures / the restated oracle.
 """
 import contextlib
 import io
@@ -20,7 +21,19 @@ import os
 import sys
 import types
 
-REFERENCE_CODE = os.environ.get("B200REC_REFERENCE", "/root/reference/code")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_VENDORED = os.path.join(_HERE, "_ref", "code")          # written by oracle/build_ref.py (git-ignored, travels to the GPU box)
+
+
+def _pick():
+    env = os.environ.get("B200REC_REFERENCE")
+    for cand in ([env] if env else []) + ["/root/reference/code", _VENDORED]:
+        if cand and os.path.isfile(os.path.join(cand, "REC", "model", "IDNet", "hstu.py")):
+            return cand
+    return "/root/reference/code"
+
+
+REFERENCE_CODE = _pick()
 
 
 def available() -> bool:
