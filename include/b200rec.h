@@ -74,6 +74,24 @@ size_t b200rec_scatter_add_workspace_bytes(int64_t n_ids);
 int b200rec_scatter_add_sorted(const int64_t* ids, int64_t n_ids, const float* grad_rows, int D,
                                int64_t* uniq_ids, float* uniq_rows, int32_t* n_uniq,
                                void* workspace, size_t workspace_bytes, void* stream);
+/* Owner-side gradient reduction of a ROW-SHARDED table inside one NVLink node (replaces the reference's dense-gradient
+ * reduce of trainer.py:434-453 / an all-to-all of gradient rows): ids[W * n_per] are the global ids behind the gradient
+ * rows of all W ranks (rank-major), src_ptrs_dev[r] is rank r's gradient-row buffer [n_per, D] mapped with CUDA IPC
+ * (b200rec_ipc_import).  Keeps the ids this rank owns (id % W == rank, id > 0), returns their LOCAL rows id / W in
+ * uniq_ids and the per-id sums in ascending (rank, index) order: the rows are read over NVLink while they are summed. */
+int b200rec_scatter_add_sorted_peer(const int64_t* ids, int64_t n_per, int W, int rank, const void* src_ptrs_dev, int D,
+                                    int64_t* uniq_ids, float* uniq_rows, int32_t* n_uniq, void* workspace,
+                                    size_t workspace_bytes, void* stream);
+/* Row lookup in a row-sharded table (global id g lives on rank g % W at local row g / W): shard_ptrs_dev[r] = rank r's
+ * shard mapped with CUDA IPC; out[i,:] = shard[ids[i] % W][ids[i] / W, :], zero row for ids[i] < 0.  Replaces the
+ * embedding gather of hstu.py:637,670,752 when the table does not fit / is not replicated; no host sync, fixed size. */
+int b200rec_gather_rows_sharded(const void* shard_ptrs_dev, int W, int D, const int64_t* ids, int64_t n_ids,
+                                float* out, void* stream);
+/* CUDA IPC plumbing for the two calls above: export = (64-byte cudaIpcMemHandle_t of the cudaMalloc block containing
+ * ptr, byte offset of ptr inside it); import maps a peer's block and returns its base; close unmaps it. */
+int b200rec_ipc_export(const void* ptr, void* handle64_out, int64_t* offset_out);
+int b200rec_ipc_import(const void* handle64, void** base_out);
+int b200rec_ipc_close(void* base);
 /* dense[uniq_ids[i],:] (+)= uniq_rows[i,:] for i < *n_uniq (rows are unique -> deterministic). */
 int b200rec_rows_to_dense(const int64_t* uniq_ids, const float* uniq_rows, const int32_t* n_uniq,
                           int64_t max_rows, int D, float* dense, int accumulate, void* stream);
@@ -331,13 +349,16 @@ int b200rec_adamw_tick(float* coef_dev, float beta1, float beta2, void* stream);
  *   b200rec_adamw_rows_catchup  brings the rows `ids` (duplicates allowed; NULL = all n_ids = n_rows rows) up to
  *                               the current step BEFORE something reads them (lookups, eval, checkpoint);
  *   b200rec_adamw_rows_lazy     applies the current step (tick already run) to the rows with a gradient.
+ * id_stride > 1 (catchup only): `ids` are GLOBAL ids of a row-sharded table; ids with id % id_stride != id_offset
+ * are skipped and the others address local row id / id_stride (every rank can pass the same all-gathered list).
  * hist is a RING of hist_cap (a power of two) entries indexed by step & (hist_cap - 1): the caller must bring every
  * row up to date (catchup with ids = NULL) at least once per hist_cap - 1 steps, so no row ever looks back further. */
 int b200rec_adamw_tick_hist(float* coef_dev, void* hist, int cap, float beta1, float beta2,
                             float weight_decay, void* stream);
 int b200rec_adamw_rows_catchup(float* p, float* m, float* v, int64_t n_rows, int D, const int64_t* ids,
                                int64_t n_ids, int32_t* last, const void* hist, int hist_cap, const float* coef_dev,
-                               float beta1, float beta2, float eps, float weight_decay, void* stream);
+                               float beta1, float beta2, float eps, float weight_decay, int64_t id_stride,
+                               int64_t id_offset, void* stream);
 int b200rec_adamw_rows_lazy(float* p, float* m, float* v, int64_t n_rows, int D, const int64_t* uniq_ids,
                             const float* uniq_rows, const int32_t* n_uniq, int64_t max_rows, int32_t* last,
                             const void* hist, int hist_cap, const float* coef_dev, float beta1, float beta2, float eps,

@@ -63,6 +63,11 @@ _SIGS = {
     "b200rec_resblock_bwd": (C.c_int, [_P, _P, _I, _L, _I, _I, _P, _P, _P]),
     "b200rec_scatter_add_workspace_bytes": (_Z, [_L]),
     "b200rec_scatter_add_sorted": (C.c_int, [_P, _L, _P, _I, _P, _P, _P, _P, _Z, _P]),
+    "b200rec_scatter_add_sorted_peer": (C.c_int, [_P, _L, _I, _I, _P, _I, _P, _P, _P, _P, _Z, _P]),
+    "b200rec_gather_rows_sharded": (C.c_int, [_P, _I, _I, _P, _L, _P, _P]),
+    "b200rec_ipc_export": (C.c_int, [_P, _P, _P]),
+    "b200rec_ipc_import": (C.c_int, [_P, _P]),
+    "b200rec_ipc_close": (C.c_int, [_P]),
     "b200rec_rows_to_dense": (C.c_int, [_P, _P, _P, _L, _I, _P, _I, _P]),
     "b200rec_layernorm_fwd": (C.c_int, [_P, _I, _I, _F, _P, _I, _P, _P, _P]),
     "b200rec_layernorm_bwd": (C.c_int, [_P, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
@@ -95,7 +100,7 @@ _SIGS = {
     "b200rec_score_mask_topk": (C.c_int, [_P, _L, _I, _I, _L, _I, _P, _P, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _Z,
                                           _P]),
     "b200rec_adamw_tick_hist": (C.c_int, [_P, _P, _I, _F, _F, _F, _P]),
-    "b200rec_adamw_rows_catchup": (C.c_int, [_P, _P, _P, _L, _I, _P, _L, _P, _P, _I, _P, _F, _F, _F, _F, _P]),
+    "b200rec_adamw_rows_catchup": (C.c_int, [_P, _P, _P, _L, _I, _P, _L, _P, _P, _I, _P, _F, _F, _F, _F, _L, _L, _P]),
     "b200rec_adamw_rows_lazy": (C.c_int, [_P, _P, _P, _L, _I, _P, _P, _P, _L, _P, _P, _I, _P, _F, _F, _F, _F, _F, _P]),
     "b200rec_build_train_batch": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _I, _I, _P, _P, _I, _F, _P, _I,
                                             C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P]),

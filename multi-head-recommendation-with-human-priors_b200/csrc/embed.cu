@@ -281,8 +281,21 @@ __global__ void scatter_bounds_kernel(const uint32_t* __restrict__ keys, const i
 // (hot items of a Zipf catalogue) take a whole block so that one id cannot serialise the kernel.
 #define SEG_CH 32
 
+// Where gradient row `pos` lives: one local array, or (peer variant) W equally long arrays -- one per rank, mapped
+// through CUDA IPC -- addressed src-major: pos = src * n_per + index.
+struct RowSrc {
+  const float* base;
+  const float* const* srcs;
+  int n_per;
+  __device__ __forceinline__ const float* row(int pos, int D4) const {
+    if (srcs == nullptr) return base + (int64_t)pos * D4 * 4;
+    const int s = pos / n_per;
+    return srcs[s] + (int64_t)(pos - s * n_per) * D4 * 4;
+  }
+};
+
 template <int MAXV>
-__device__ __forceinline__ void seg_sum_rows(const float* __restrict__ grad_rows, const int32_t* __restrict__ pos_sorted,
+__device__ __forceinline__ void seg_sum_rows(const RowSrc grad_rows, const int32_t* __restrict__ pos_sorted,
                                              int beg, int end, int D4, int c0, float (&acc)[MAXV][4]) {
   const int lane = threadIdx.x & 31;
   int i = beg;
@@ -290,7 +303,7 @@ __device__ __forceinline__ void seg_sum_rows(const float* __restrict__ grad_rows
     float v[4][MAXV][4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const float* row = grad_rows + (int64_t)pos_sorted[i + r] * D4 * 4;
+      const float* row = grad_rows.row(pos_sorted[i + r], D4);
 #pragma unroll
       for (int u = 0; u < MAXV; ++u) {
         const int c = c0 + lane + 32 * u;
@@ -305,7 +318,7 @@ __device__ __forceinline__ void seg_sum_rows(const float* __restrict__ grad_rows
         for (int k = 0; k < 4; ++k) acc[u][k] += v[r][u][k];
   }
   for (; i < end; ++i) {
-    const float* row = grad_rows + (int64_t)pos_sorted[i] * D4 * 4;
+    const float* row = grad_rows.row(pos_sorted[i], D4);
     float v[MAXV][4];
 #pragma unroll
     for (int u = 0; u < MAXV; ++u) {
@@ -324,7 +337,7 @@ __device__ __forceinline__ void seg_sum_rows(const float* __restrict__ grad_rows
 __global__ void __launch_bounds__(256) scatter_reduce_short_kernel(const int32_t* __restrict__ seg_start,
                                                                    const int32_t* __restrict__ pos_sorted,
                                                                    const int32_t* __restrict__ n_uniq,
-                                                                   const float* __restrict__ grad_rows, int D4,
+                                                                   const RowSrc grad_rows, int D4,
                                                                    float* __restrict__ uniq_rows,
                                                                    int32_t* __restrict__ long_list) {
   const int nu = *n_uniq;
@@ -354,7 +367,7 @@ __global__ void __launch_bounds__(256) scatter_reduce_short_kernel(const int32_t
 
 __global__ void __launch_bounds__(256) scatter_reduce_long_kernel(const int32_t* __restrict__ seg_start,
                                                                   const int32_t* __restrict__ pos_sorted,
-                                                                  const float* __restrict__ grad_rows, int D4,
+                                                                  const RowSrc grad_rows, int D4,
                                                                   float* __restrict__ uniq_rows,
                                                                   const int32_t* __restrict__ long_list) {
   __shared__ float part[8][32 * SEG_V * 4];
@@ -402,10 +415,20 @@ __global__ void __launch_bounds__(256) scatter_reduce_long_kernel(const int32_t*
   }
 }
 
-int b200rec_scatter_add_sorted(const int64_t* ids, int64_t n_ids, const float* grad_rows, int D, int64_t* uniq_ids,
-                               float* uniq_rows, int32_t* n_uniq, void* workspace, size_t workspace_bytes,
-                               void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
+// keys of the sharded variant: global id g owned by `rank` (g % W == rank, g != 0) -> local row g / W; everything
+// else (other ranks' ids, padding id 0, negative fillers) is parked behind the real keys
+__global__ void scatter_prep_sharded_kernel(const int64_t* __restrict__ ids, int n, int W, int rank, uint32_t* keys,
+                                            int32_t* pos) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t id = ids[i];
+  const bool mine = id > 0 && (int)(id % W) == rank && id / W < 0xffffffffll;
+  keys[i] = mine ? (uint32_t)(id / W) : 0xffffffffu;
+  pos[i] = i;
+}
+
+static int scatter_add_run(const int64_t* ids, int64_t n_ids, RowSrc src, int W, int rank, int D, int64_t* uniq_ids,
+                           float* uniq_rows, int32_t* n_uniq, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   B200_CHECK_ARG(D % 4 == 0, "scatter_add_sorted: D=%d must be a multiple of 4", D);
   B200_CHECK_ARG(n_ids < (1ll << 31), "scatter_add_sorted: too many ids");
   if (n_ids == 0) {
@@ -416,7 +439,8 @@ int b200rec_scatter_add_sorted(const int64_t* ids, int64_t n_ids, const float* g
   B200_CHECK_ARG(workspace_bytes >= w.total, "scatter_add_sorted: workspace %zu < %zu", workspace_bytes, w.total);
   int n = (int)n_ids;
   int blocks = ceil_div_i(n, 256);
-  scatter_prep_kernel<<<blocks, 256, 0, st>>>(ids, n, w.keys_in, w.pos_in);
+  if (W > 0) scatter_prep_sharded_kernel<<<blocks, 256, 0, st>>>(ids, n, W, rank, w.keys_in, w.pos_in);
+  else scatter_prep_kernel<<<blocks, 256, 0, st>>>(ids, n, w.keys_in, w.pos_in);
   size_t tmp = w.cub_bytes;
   B200_CUDA_OK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.keys_in, w.keys_out, w.pos_in, w.pos_out, n, 0, 32,
                                                st));
@@ -426,12 +450,35 @@ int b200rec_scatter_add_sorted(const int64_t* ids, int64_t n_ids, const float* g
   scatter_bounds_kernel<<<blocks, 256, 0, st>>>(w.keys_out, w.seg, n, w.seg_start, uniq_ids, n_uniq);
   B200_CUDA_OK(cudaMemsetAsync(w.long_list, 0, 4, st));
   int rblocks = std::min(ceil_div_i(n, 8), 148 * 8);
-  scatter_reduce_short_kernel<<<rblocks, 256, 0, st>>>(w.seg_start, w.pos_out, n_uniq, grad_rows, D / 4, uniq_rows,
+  scatter_reduce_short_kernel<<<rblocks, 256, 0, st>>>(w.seg_start, w.pos_out, n_uniq, src, D / 4, uniq_rows,
                                                        w.long_list);
-  scatter_reduce_long_kernel<<<std::min(n / SEG_CH + 1, 148 * 2), 256, 0, st>>>(w.seg_start, w.pos_out, grad_rows, D / 4,
+  scatter_reduce_long_kernel<<<std::min(n / SEG_CH + 1, 148 * 2), 256, 0, st>>>(w.seg_start, w.pos_out, src, D / 4,
                                                                                uniq_rows, w.long_list);
   B200_LAUNCH_OK();
   return 0;
+}
+
+int b200rec_scatter_add_sorted(const int64_t* ids, int64_t n_ids, const float* grad_rows, int D, int64_t* uniq_ids,
+                               float* uniq_rows, int32_t* n_uniq, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  RowSrc src;
+  src.base = grad_rows; src.srcs = nullptr; src.n_per = 0;
+  return scatter_add_run(ids, n_ids, src, 0, 0, D, uniq_ids, uniq_rows, n_uniq, workspace, workspace_bytes,
+                         (cudaStream_t)stream);
+}
+
+// Owner-side reduction of a row-sharded table's gradient: ids = the global ids behind the W x n_per gradient rows of
+// all ranks (rank-major), src_ptrs_dev[r] = rank r's gradient-row buffer [n_per, D] mapped through CUDA IPC.  Keeps the
+// ids this rank owns (id % W == rank, id != 0), returns LOCAL row indices (id / W) in uniq_ids and sums the rows of
+// each in ascending (rank, index) order -- the rows are read over NVLink while they are summed.
+int b200rec_scatter_add_sorted_peer(const int64_t* ids, int64_t n_per, int W, int rank, const void* src_ptrs_dev, int D,
+                                    int64_t* uniq_ids, float* uniq_rows, int32_t* n_uniq, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  B200_CHECK_ARG(W >= 1 && rank >= 0 && rank < W && n_per * W < (1ll << 31), "scatter_add_sorted_peer: bad W / rank / n");
+  RowSrc src;
+  src.base = nullptr; src.srcs = (const float* const*)src_ptrs_dev; src.n_per = (int)n_per;
+  return scatter_add_run(ids, n_per * W, src, W, rank, D, uniq_ids, uniq_rows, n_uniq, workspace, workspace_bytes,
+                         (cudaStream_t)stream);
 }
 
 __global__ void __launch_bounds__(256) rows_to_dense_kernel(const int64_t* __restrict__ uniq_ids,

@@ -323,12 +323,17 @@ __global__ void __launch_bounds__(256) adamw_rows_catchup_kernel(float* __restri
                                                                  float* __restrict__ v, int64_t N, int D4,
                                                                  const int64_t* __restrict__ ids, int64_t n_ids,
                                                                  int32_t* __restrict__ last,
-                                                                 const float4* __restrict__ hist, int hmask, AdamCoef c) {
+                                                                 const float4* __restrict__ hist, int hmask, AdamCoef c,
+                                                                 int64_t id_stride, int64_t id_offset) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int S = (int)c.dev[3];                                  // completed optimizer steps
   for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_ids; i += warps) {
-    const int64_t row = ids ? ids[i] : i;
+    int64_t row = ids ? ids[i] : i;
+    if (ids && id_stride > 1) {                                 // global ids of a row-sharded table: keep my rows
+      if (row < 0 || row % id_stride != id_offset) continue;
+      row /= id_stride;
+    }
     if (row < 0 || row >= N) continue;
     int old = 0;
     if (lane == 0) old = atomicExch(last + row, S);
@@ -358,7 +363,8 @@ __global__ void __launch_bounds__(256) adamw_rows_lazy_kernel(float* __restrict_
 
 extern "C" int b200rec_adamw_rows_catchup(float* p, float* m, float* v, int64_t n_rows, int D, const int64_t* ids,
                                           int64_t n_ids, int32_t* last, const void* hist, int hist_cap,
-                                          const float* coef_dev, float beta1, float beta2, float eps, float weight_decay, void* stream) {
+                                          const float* coef_dev, float beta1, float beta2, float eps, float weight_decay,
+                                          int64_t id_stride, int64_t id_offset, void* stream) {
   B200_CHECK_ARG(D % 4 == 0 && coef_dev != nullptr && hist != nullptr && last != nullptr && hist_cap > 0 &&
                      (hist_cap & (hist_cap - 1)) == 0, "adamw_rows_catchup: bad args (hist_cap must be a power of two)");
   if (n_ids == 0) return 0;
@@ -366,7 +372,8 @@ extern "C" int b200rec_adamw_rows_catchup(float* p, float* m, float* v, int64_t 
   c.dev = coef_dev;
   int blocks = (int)std::min<int64_t>((n_ids + 7) / 8, 148 * 8);
   adamw_rows_catchup_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, m, v, n_rows, D / 4, ids, n_ids, last,
-                                                                      (const float4*)hist, hist_cap - 1, c);
+                                                                      (const float4*)hist, hist_cap - 1, c,
+                                                                      id_stride < 1 ? 1 : id_stride, id_offset);
   B200_LAUNCH_OK();
   return 0;
 }

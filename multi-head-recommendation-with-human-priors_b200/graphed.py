@@ -118,43 +118,68 @@ def _read_gemm_events(events):
 
 
 class GraphedShardedStep(object):
-    """Multi-GPU step with a row-sharded item table (`HSTU.shard_item_table`), split in three:
+    """Multi-GPU step with a row-sharded item table (`HSTU.shard_item_table`), one NVLink / NVSwitch node, with NO host
+    synchronisation and no data-dependent shapes (the old id / row / gradient all-to-alls with
+    host-read split sizes serialised the ranks).  Every rank maps its peers' table shards and gradient-row buffers
+    once with CUDA IPC (`parallel.PeerMap`); per step:
 
-      pre   (eager)  negative-id all-gather, unique, all-to-all row fetch into a fixed-capacity row cache
-                     (`HSTU.prepare_rows`): collectives and data-dependent sizes live here;
-      graph (replay) forward + backward on static buffers -> dense gradients in ONE flat buffer shared by
-                     all buckets, and one gradient row per cache row;
-      post  (eager)  all-to-all push of the cache-row gradients to their owners (deterministic segment reduce
-                     there) and the table update; the flat all-reduce of the dense gradients is launched on its
-                     own communicator and the dense AdamW of step k runs at the start of step k+1, AFTER that
-                     step's pre-phase: the all-reduce hides behind the id exchange / row fetch, which only need
-                     the table.  `flush()` applies the pending dense update (call it before evaluating or saving).
+      pre   one fixed-size all-gather of this rank's ids (items + its own negatives); the owners bring the requested
+            rows up to date (lazy AdamW catch-up over the gathered list, filtered by id % W); a one-element all-reduce
+            orders that against the readers; `gather_rows_sharded` then reads every needed row straight out of its
+            owner's HBM over NVLink into the step's row cache (one row per requested position: no unique, no sort);
+      graph forward + backward on static buffers -> dense gradients in one flat buffer, one gradient row per cache row
+            in the peer-mapped buffer `g`;
+      post  a one-element all-reduce (all ranks' `g` complete), then each owner reduces the gradient rows of ITS ids by
+            reading them out of every rank's `g` while summing (`scatter_add_sorted_peer`, deterministic (rank, index)
+            order) and runs the fused AdamW on its shard; the flat all-reduce of the dense gradients runs on its own
+            communicator and the dense AdamW of step k is applied at the start of step k+1 after that step's
+            pre-phase, so it hides behind the id gather / row fetch (`flush()` before evaluating / saving).
 
-    The eager part is ~40 launches instead of ~1200, so the ranks stay GPU-bound.
-    """
+    The collectives that remain are the reference's own (negative sharing, basemodel.py:11-22; gradient averaging,
+    trainer.py:434-453) plus two one-element barriers; the host only enqueues (~30 launches) and runs ahead."""
 
     def __init__(self, model, optimizer, example_batch, bucket=128, warmup=2, group=None, instrument=False):
         import torch.distributed as dist
-        self.instrument = instrument
-        self.gemm_events = {}
+        from . import parallel
         assert model.sharded_table is not None, "call model.shard_item_table() first"
         assert not model._has_tower(), "item_id_proj_tower: use the eager sharded step"
-        self.dist, self.group = dist, group
+        assert model.share_negatives, "the sharded step shares negatives across ranks (reference semantics)"
+        self.instrument = instrument
+        self.gemm_events = {}
+        self.dist, self.group, self.parallel = dist, group, parallel
         self.model, self.opt, self.bucket, self.warmup = model, optimizer, bucket, warmup
         items, neg, mask, tags = example_batch
         dev = items.device
-        self.world = model.sharded_table.W
+        st = model.sharded_table
+        self.world, self.rank = st.W, st.rank
+        W = self.world
         B, LP = items.shape
-        n_sets = neg.shape[1]
-        n_neg = neg.shape[0] * neg.shape[2] * (self.world if model.share_negatives else 1)
+        n_sets, n = neg.shape[1], neg.shape[2]
+        self.B, self.LP, self.n_sets = B, LP, n_sets
+        self.n_items = (B + 1) * LP                          # +1: the all-padding dummy row of static-token mode
+        self.n_negloc = n_sets * B * n                       # this rank's negatives, set-major
+        self.n_neg = W * B * n                               # global negatives per set
+        self.U = self.n_items + n_sets * self.n_neg          # row-cache rows = gradient rows per rank
         D = model.item_embedding.weight.shape[1]
-        self.cap = (B + 1) * LP + n_sets * n_neg             # every requested id distinct
+        self.D = D
         self.static = tuple(torch.empty_like(t) for t in example_batch)
         i64 = dict(dtype=torch.int64, device=dev)
-        self.prep = dict(W=torch.zeros((self.cap, D), dtype=torch.float32, device=dev),
-                         items_idx=torch.zeros((B + 1, LP), **i64), neg_idx=torch.zeros((n_sets, n_neg), **i64),
-                         gl_items=torch.zeros((B + 1, LP), **i64), gl_neg=torch.zeros((n_sets, n_neg), **i64),
-                         cached=True, push=False, n_rows=None)
+        self.id_block = torch.zeros(self.n_items + self.n_negloc, **i64)
+        self.id_all = torch.zeros((W, self.n_items + self.n_negloc), **i64)
+        self.cache_ids = torch.zeros(self.U, **i64)          # global id behind every cache row of THIS rank
+        self.cache_ids_all = torch.zeros((W, self.U), **i64)  # ... of every rank (the owner-side reduction reads it)
+        self.g = torch.zeros((self.U, D), dtype=torch.float32, device=dev)
+        self.peers = parallel.PeerMap(group)
+        self.shard_ptrs = self.peers.table(model.item_embedding.weight.data)
+        self.g_ptrs = self.peers.table(self.g)
+        self._shard_ptr0 = model.item_embedding.weight.data_ptr()
+        idx_items = torch.arange(self.n_items, **i64).view(B + 1, LP)
+        idx_neg = (self.n_items + torch.arange(n_sets * self.n_neg, **i64)).view(n_sets, self.n_neg)
+        self.prep = dict(W=torch.zeros((self.U, D), dtype=torch.float32, device=dev), items_idx=idx_items,
+                         neg_idx=idx_neg, gl_items=torch.zeros((B + 1, LP), **i64),
+                         gl_neg=torch.zeros((n_sets, self.n_neg), **i64), cached=True, push=False, n_rows=self.U,
+                         grad_out=self.g, info=None)
+        self.token = torch.zeros(1, dtype=torch.float32, device=dev)
         self.graphs = {}
         self.pool = None
         self.max_tokens = B * model.max_seq_length
@@ -162,14 +187,38 @@ class GraphedShardedStep(object):
         self._pending = None                     # async all-reduce of the previous step's dense gradients
         self.ar_group = dist.new_group() if (self.world > 1 and group is None) else group
 
+    def _barrier(self):
+        """Stream-ordered cross-rank ordering point (one-element all-reduce): when it completes on this rank, every
+        rank's stream has reached it, i.e. everything they enqueued before it has finished."""
+        if self.world > 1:
+            self.dist.all_reduce(self.token, op=self.dist.ReduceOp.SUM, group=self.group)
+
     def _fill(self, batch):
+        model, W = self.model, self.world
+        assert model.item_embedding.weight.data_ptr() == self._shard_ptr0, "the table shard moved: rebuild the stepper"
         for s, t in zip(self.static, batch):
             s.copy_(t, non_blocking=True)
-        p = self.model.prepare_rows(self.static[0], self.static[1], static=True, cache_out=self.prep["W"])
-        U = p["n_rows"]                                   # rows were fetched straight into the static cache
-        for k in ("items_idx", "neg_idx", "gl_items", "gl_neg"):
-            self.prep[k].copy_(p[k])
-        return U
+        items, neg = self.static[0], self.static[1]
+        B, LP, ni = self.B, self.LP, self.n_items
+        # my id block: items (+ dummy row of zeros) | my negatives, set-major
+        self.id_block[:B * LP].copy_(items.reshape(-1))
+        self.id_block[ni:].copy_(neg.permute(1, 0, 2).reshape(-1))
+        if W > 1:
+            self.dist.all_gather(list(self.id_all.unbind(0)), self.id_block, group=self.group)
+        else:
+            self.id_all[0].copy_(self.id_block)
+        # global negative set per category, rank-major (the order of the reference's all_gather, basemodel.py:17-18)
+        gl_neg = self.id_all[:, ni:].reshape(W, self.n_sets, -1).permute(1, 0, 2).reshape(self.n_sets, self.n_neg)
+        self.prep["gl_neg"].copy_(gl_neg)
+        self.prep["gl_items"].copy_(self.id_all[self.rank, :ni].view(B + 1, LP))
+        self.cache_ids_all[:, :ni].copy_(self.id_all[:, :ni])
+        self.cache_ids_all[:, ni:].copy_(gl_neg.reshape(1, -1).expand(W, -1))
+        self.cache_ids.copy_(self.cache_ids_all[self.rank])
+        # owners bring every row somebody is about to read up to date (lazy exact AdamW), then all ranks may read
+        if model._table_sync is not None:
+            self.opt.sync_rows(self.id_all, id_stride=W, id_offset=self.rank)
+        self._barrier()
+        self.parallel.cuda_gather_rows_sharded(self.shard_ptrs, W, self.D, self.cache_ids, self.prep["W"])
 
     def _fwd_bwd(self, T_b):
         self.opt.zero_grad()
@@ -185,7 +234,8 @@ class GraphedShardedStep(object):
                 self.views.append(self.flat[off:off + p.numel()].view_as(p))
                 off += n
         torch._foreach_copy_(self.views, [p.grad for p in self.dense])
-        return out, self.model.cache_grad
+        assert self.model.cache_grad.data_ptr() == self.g.data_ptr()
+        return out
 
     def _capture(self, T_b):
         s = torch.cuda.Stream()
@@ -201,14 +251,14 @@ class GraphedShardedStep(object):
             L.gemm_timing, L.gemm_timing_external = [], True
         try:
             with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
-                out, cache_grad = self._fwd_bwd(T_b)
+                out = self._fwd_bwd(T_b)
         finally:
             if self.instrument:
                 self.gemm_events[T_b] = L.gemm_timing
                 L.gemm_timing, L.gemm_timing_external = None, False
         if self.pool is None:
             self.pool = g.pool()
-        return g, out, cache_grad, L.launches - n0
+        return g, out, L.launches - n0
 
     def gemm_times(self, n_tokens):
         T_b = min(self.max_tokens, max(self.bucket, (int(n_tokens) + self.bucket - 1) // self.bucket * self.bucket))
@@ -224,13 +274,13 @@ class GraphedShardedStep(object):
 
     def __call__(self, batch, n_tokens):
         T_b = min(self.max_tokens, max(self.bucket, (int(n_tokens) + self.bucket - 1) // self.bucket * self.bucket))
-        U = self._fill(batch)                    # pre-phase: needs the table only
+        self._fill(batch)                        # pre-phase: needs the table only
         self.flush()                             # previous step's dense update (its all-reduce ran meanwhile)
         entry = self.graphs.get(T_b)
         if entry is None:
             entry = self._capture(T_b)
             self.graphs[T_b] = entry
-        g, out, cache_grad, n_launch = entry
+        g, out, n_launch = entry
         if self.model.shadows_stale():
             self.model.invalidate_shadows()
             self.model._cast_weights()
@@ -240,9 +290,12 @@ class GraphedShardedStep(object):
         for p, v in zip(self.dense, self.views):
             p.grad = v
         model.item_embedding.weight.grad = None
-        # gradient rows to their owners first, then the dense all-reduce runs on the NCCL stream WHILE the owner
-        # reduces its rows and updates its table shard (HBM-bound); the dense update waits for the all-reduce
-        model.emb_grad = model.sharded_table.push_grads(cache_grad[:U], scale=1.0)
+        # every rank's gradient rows are complete -> each owner reduces the rows of ITS ids out of all ranks' buffers
+        # (NVLink reads inside the reduction) and updates its shard; the dense all-reduce runs on its own communicator
+        # meanwhile and the dense update waits for it at the start of the next step
+        self._barrier()
+        model.emb_grad = self.parallel.cuda_segment_reduce_peer(self.cache_ids_all, self.U, W, self.rank, self.g_ptrs,
+                                                                self.D, model.item_embedding.weight.shape[0])
         self.opt.step(grad_scale=1.0 / W, dense=False)
         self._pending = True
         if W > 1:

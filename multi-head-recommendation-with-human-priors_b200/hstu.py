@@ -826,7 +826,8 @@ class HSTU(nn.Module):
                        tinv=tinv, nhat=nhat, ninv=ninv, neg_ids=neg_ids, job_out=job_out, scale=scale, half=half,
                        items=items, mask=m, n_neg=n_neg, ld_neg=ld_neg, Hx=Hx, used_sets=used_sets,
                        gl_items=gl_items, gl_neg_ids=gl_neg_ids, uniq_rows_ids=uniq_rows_ids,
-                       n_cache_rows=W.shape[0], push=prepared.get("push", True), cache_info=prepared.get("info"))
+                       n_cache_rows=W.shape[0], push=prepared.get("push", True), cache_info=prepared.get("info"),
+                       grad_out=prepared.get("grad_out"))
         return loss, logs, ctx
 
     def _train_backward(self, ctx, gscale):
@@ -969,7 +970,12 @@ class HSTU(nn.Module):
         if sharded:
             # one gradient row per cache row (fetched / projected rows)
             U = ctx["n_cache_rows"]
-            g = torch.zeros((U, D), dtype=torch.float32, device=dev)
+            g = ctx.get("grad_out")              # caller-owned buffer (peer-mapped by the sharded step), else a fresh one
+            if g is None:
+                g = torch.zeros((U, D), dtype=torch.float32, device=dev)
+            else:
+                assert tuple(g.shape) == (U, D) and g.dtype == torch.float32
+                g.zero_()
             L.call("b200rec_rows_to_dense", (uniq_ids - 1).contiguous().data_ptr(), uniq_rows.data_ptr(),
                    n_uniq.data_ptr(), n_rows, D, g.data_ptr(), 0, st)
             info = ctx["cache_info"] or {}

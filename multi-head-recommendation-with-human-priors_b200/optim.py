@@ -164,8 +164,9 @@ class FusedAdamW(object):
         return emb
 
     @torch.no_grad()
-    def sync_rows(self, ids):
-        """Bring the table rows `ids` (int64 tensor, duplicates fine; None = every row) up to the current step."""
+    def sync_rows(self, ids, id_stride=1, id_offset=0):
+        """Bring the table rows `ids` (int64 tensor, duplicates fine; None = every row) up to the current step.
+        id_stride > 1: `ids` are global ids of a row-sharded table; only ids % id_stride == id_offset are mine."""
         if not self.lazy_table or (self.step_count == 0 and self._last is None):
             return
         emb = self._lazy_state()
@@ -177,7 +178,7 @@ class FusedAdamW(object):
             ids = ids.reshape(-1).contiguous()
         L.call("b200rec_adamw_rows_catchup", emb.data_ptr(), m.data_ptr(), v.data_ptr(), N, D, L.ptr(ids),
                N if ids is None else ids.numel(), self._last.data_ptr(), self._hist.data_ptr(), self.HIST_CAP,
-               self._coef.data_ptr(), b1, b2, eps, wd, L.stream())
+               self._coef.data_ptr(), b1, b2, eps, wd, int(id_stride), int(id_offset), L.stream())
 
     def flush(self):
         self.sync_rows(None)

@@ -163,6 +163,81 @@ class ShardedTable(object):
         return uid - 1, urows, nu
 
 
+# ------------------------------------------------------------------------------- peer (CUDA IPC) access
+_IPC_OPENED = {}     # process-wide: handle bytes -> mapped base (a handle can be opened once per process)
+
+
+class PeerMap(object):
+    """Maps same-shaped device buffers of every rank into this process with CUDA IPC (one NVLink / NVSwitch node).
+
+    `table(t)` returns a device int64[W] tensor of pointers: entry r addresses rank r's buffer (entry `rank` is the
+    local pointer).  Kernels index it directly (b200rec_gather_rows_sharded, b200rec_scatter_add_sorted_peer), so
+    lookups and gradient rows cross NVLink inside our own kernels: no all-to-all, no host-synchronised split sizes.
+    The exchange of the 72-byte (handle, offset) records is the only collective, once per buffer."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.W = world(group)
+        self.rank = dist.get_rank(group) if self.W > 1 else 0
+        self._opened = _IPC_OPENED
+        self._keep = []            # exported tensors must outlive the peers' mappings
+
+    def table(self, t):
+        import ctypes as C
+        assert t.is_cuda and t.is_contiguous()
+        self._keep.append(t)
+        ptrs = [0] * self.W
+        ptrs[self.rank] = t.data_ptr()
+        if self.W > 1:
+            handle = (C.c_char * 64)()
+            off = C.c_int64(0)
+            L.call("b200rec_ipc_export", t.data_ptr(), C.addressof(handle), C.addressof(off))
+            rec = torch.frombuffer(bytearray(bytes(handle) + int(off.value).to_bytes(8, "little")), dtype=torch.uint8)
+            rec = rec.to(t.device)
+            recs = [torch.empty_like(rec) for _ in range(self.W)]
+            dist.all_gather(recs, rec, group=self.group)
+            for r in range(self.W):
+                if r == self.rank:
+                    continue
+                raw = bytes(recs[r].cpu().numpy().tobytes())
+                h, o = raw[:64], int.from_bytes(raw[64:72], "little")
+                base = self._opened.get(h)
+                if base is None:
+                    out = C.c_void_p(0)
+                    hb = (C.c_char * 64).from_buffer_copy(h)
+                    L.call("b200rec_ipc_import", C.addressof(hb), C.addressof(out))
+                    base = int(out.value)
+                    self._opened[h] = base
+                ptrs[r] = base + o
+        return torch.tensor(ptrs, dtype=torch.int64, device=t.device)
+
+    def release(self):
+        """Drops the references that keep the exported buffers alive (mappings stay until the process exits)."""
+        self._keep.clear()
+
+
+def cuda_gather_rows_sharded(shard_ptrs, W, D, ids, out):
+    """out[i] = shard[ids[i] % W][ids[i] // W] over the peer pointer table (ids < 0: zero row)."""
+    L.call("b200rec_gather_rows_sharded", shard_ptrs.data_ptr(), W, D, ids.data_ptr(), ids.numel(), out.data_ptr(),
+           L.stream())
+    return out
+
+
+def cuda_segment_reduce_peer(ids_all, n_per, W, rank, src_ptrs, D, max_uniq):
+    """Owner-side reduction over every rank's gradient-row buffer (see b200rec_scatter_add_sorted_peer).
+    Returns (local_row_ids, rows, n_uniq)."""
+    n = n_per * W
+    dev = ids_all.device
+    ws_bytes = L.lib().b200rec_scatter_add_workspace_bytes(max(n, 1))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    uid = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    urows = torch.empty((max(1, min(n, max_uniq)), D), dtype=torch.float32, device=dev)
+    nu = torch.zeros(1, dtype=torch.int32, device=dev)
+    L.call("b200rec_scatter_add_sorted_peer", ids_all.data_ptr(), n_per, W, rank, src_ptrs.data_ptr(), D, uid.data_ptr(),
+           urows.data_ptr(), nu.data_ptr(), ws.data_ptr(), ws_bytes, L.stream())
+    return uid, urows, nu
+
+
 # ------------------------------------------------------------------------------- data parallel
 class DataParallel(object):
     """Gradient synchronisation for one training step (call between backward and optimizer.step)."""
