@@ -152,6 +152,9 @@ enum {
                                  fold_head_cat[h] (category gating head h, -1 none) against
                                  fold_item_tags[n] (bit c = item n has tag c), global item id 0
                                  (n*fold_id_stride + fold_id_offset == 0).  bf16 (tcgen05) path only. */
+  ,
+  B200REC_EPI_NCE_EXP = 7     /* fused sampled-softmax forward: C = bf16 softmax numerators + per-row partial
+                                 sums (nce_* fields, described below b200rec_gemm).  bf16 (tcgen05) path only. */
 };
 typedef struct {
   int M, N, K;
@@ -177,8 +180,22 @@ typedef struct {
   int fold_hp;
   const uint8_t* fold_head_on; const int32_t* fold_head_cat; const uint32_t* fold_item_tags;
   int64_t fold_id_offset; int64_t fold_id_stride;
+  /* STORE / ACCUM: optional per-row factor, C[m,:] (+)= alpha * row_scale[m] * acc[m,:] (fp32[M]; NULL = 1). */
+  const float* row_scale;
+  /* B200REC_EPI_NCE_EXP only (fused sampled-softmax forward, hstu.py:600-619 + cross_entropy): see below. */
+  const float* nce_mref; const float* nce_thr; float* nce_stats; const float* nce_logit_scale;
 } b200rec_gemm_args;
 int b200rec_gemm(const b200rec_gemm_args* args, void* stream);
+/* B200REC_EPI_NCE_EXP (bf16 tcgen05 path): the logits GEMM of the sampled-softmax loss with the softmax numerators
+ * produced in the epilogue, so that no [T, Nneg] fp32 logits tensor ever reaches HBM.  With acc = q_hat . n_hat (cosine),
+ * tau2 = exp(clamp(*nce_logit_scale, 0, ln 100)) * log2(e) and a per-row reference nce_mref[m] (log2 domain):
+ *     E[m, n]  = bf16( 2^(tau2 * acc - nce_mref[m]) )                      -> C (bf16 [M, ldc])
+ *     nce_stats[m, part, 0..3] = { sum E, sum E * acc, #(acc > nce_thr[m]), 0 } over the columns of `part`,
+ * part = 2 * (n / BN) + (which of the two epilogue warps), n_parts = b200rec_gemm_nce_parts(N).  Sums use the ROUNDED
+ * E so that later subtractive corrections (false-negative filter) stay consistent with the stored tile.  The combine
+ * step (b200rec_nce_combine) turns the partials into per-offset log-sum-exp / loss / gradient scalars; the backward
+ * GEMMs consume E directly: dq = row_scale * (E @ n_hat), dn = E^T @ (row_scale * q_hat). */
+int b200rec_gemm_nce_parts(int N);
 /* n_groups independent problems args[0..n_groups).  Problems of identical shape / layout / dtypes with a
  * plain STORE or ACCUM epilogue (the per-head NCE GEMMs of hstu.py:697, the per-layer weight gradients)
  * run as ONE persistent tcgen05 launch (16 problems per launch), so that small problems share waves
@@ -250,6 +267,26 @@ int b200rec_nce_loss_fwd(const float* logits, int64_t ld_logits, int n_neg,
 /* gscale (nullable device scalar) multiplies the upstream gradient in the two pos_bwd calls. */
 /* coef[p] = lam[p] * w / max(cnt[p], 1)   (hstu.py:708-712, 850-852) */
 int b200rec_nce_coef(const int32_t* cnt, const float* lam, float w, int P, float* coef, void* stream);
+/* Fused sampled-softmax path (bf16 production mode; replaces hstu.py:600-629 + cross_entropy without any fp32
+ * [T, Nneg] tensor in HBM).  Order: b200rec_nce_pos_ref -> logits GEMM with B200REC_EPI_NCE_EXP -> b200rec_nce_combine.
+ *   nce_pos_ref: pos_cos[T,P] (NaN = offset not served by this head / invalid token), mref[T] = reference exponent of the
+ *                row (max valid positive logit in the log2 domain, floored at tau2 - 100; tau2 for unused rows),
+ *                thr[T] = cosine of the offset-0 positive (+inf if absent): rank threshold of the top-k logging.
+ *   nce_combine: from the GEMM's partial sums: loss / g0 (= d loss / d positive logit / tau) / dscale / rank0 / nvalid
+ *                per (token, offset) exactly as b200rec_nce_loss_fwd returns them; row_scale[T] with
+ *                d loss / d cos-logit[t, j] = row_scale[t] * E[t, j]; offsets whose target filters negatives
+ *                (same_bits / row_any from the GT_BITS GEMM) subtract those stored numerators and E is patched at the
+ *                filtered entries; qs[T, D] (bf16, nullable) = row_scale[t] * q_hat[t, :], the B operand of dn. */
+int b200rec_nce_pos_ref(const void* q_hat, int64_t ldq, const void* t_hat, int D, const int32_t* tok_b,
+                        const int32_t* tok_pos, int T, int LP, int P, uint32_t p_mask, const uint8_t* tok_ok,
+                        int tok_ok_ld, int tok_ok_col, const float* logit_scale, float* pos_cos, float* mref,
+                        float* thr, void* stream);
+int b200rec_nce_combine(const float* stats, int n_parts, void* E, int64_t lde, int n_neg,
+                        const uint32_t* same_bits, const uint8_t* row_any, const float* pos_cos,
+                        const float* mref, const void* q_hat, int64_t ldq, int D, const int32_t* tok_b,
+                        const int32_t* tok_pos, int T, int LP, int P, const float* coef,
+                        const float* logit_scale, float* loss, float* g0, float* dscale, int32_t* rank0,
+                        int32_t* nvalid, float* row_scale, void* qs, int64_t ldqs, void* stream);
 /* cnt[p] = #valid tokens at offset p for this (head / category):  (hstu.py:705-707) */
 int b200rec_nce_count(const int32_t* tok_b, const int32_t* tok_pos, int T, int LP, int P,
                       const uint8_t* tok_ok, int tok_ok_ld, int tok_ok_col, int32_t* cnt,

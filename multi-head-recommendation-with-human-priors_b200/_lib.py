@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200rec.so")
 
 F32, BF16 = 0, 1
-EPI_STORE, EPI_ACCUM, EPI_SILU_DUAL, EPI_BIAS_RESID, EPI_RESBLOCK, EPI_GT_BITS, EPI_FOLD_HEADS = range(7)
+EPI_STORE, EPI_ACCUM, EPI_SILU_DUAL, EPI_BIAS_RESID, EPI_RESBLOCK, EPI_GT_BITS, EPI_FOLD_HEADS, EPI_NCE_EXP = range(8)
 
 _lib = None
 launches = 0  # number of C-ABI kernel entry points invoked (bench.py's gpu_launches claim)
@@ -48,6 +48,8 @@ class GemmArgs(C.Structure):
         ("fold_hp", C.c_int),
         ("fold_head_on", C.c_void_p), ("fold_head_cat", C.c_void_p), ("fold_item_tags", C.c_void_p),
         ("fold_id_offset", C.c_int64), ("fold_id_stride", C.c_int64),
+        ("row_scale", C.c_void_p),
+        ("nce_mref", C.c_void_p), ("nce_thr", C.c_void_p), ("nce_stats", C.c_void_p), ("nce_logit_scale", C.c_void_p),
     ]
 
 
@@ -92,6 +94,10 @@ _SIGS = {
     "b200rec_hstu_attn_seq_bwd": (C.c_int, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P, _P]),
     "b200rec_nce_loss_fwd": (C.c_int, [_P, _L, _I, _P, _P, _P, _P, _L, _P, _I, _I, _P, _P, _I, _I, _I, C.c_uint32,
                                        _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
+    "b200rec_gemm_nce_parts": (C.c_int, [_I]),
+    "b200rec_nce_pos_ref": (C.c_int, [_P, _L, _P, _I, _P, _P, _I, _I, _I, C.c_uint32, _P, _I, _I, _P, _P, _P, _P, _P]),
+    "b200rec_nce_combine": (C.c_int, [_P, _I, _P, _L, _I, _P, _P, _P, _P, _P, _L, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P,
+                                      _P, _P, _P, _P, _P, _L, _P]),
     "b200rec_nce_count": (C.c_int, [_P, _P, _I, _I, _I, _P, _I, _I, _P, _P]),
     "b200rec_nce_coef": (C.c_int, [_P, _P, _F, _I, _P, _P]),
     "b200rec_nce_pos_bwd_q": (C.c_int, [_P, _P, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P, _L, _P]),
@@ -201,9 +207,10 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epilogue=
 
 
 def gemm_grouped(problems, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epilogue=EPI_STORE, alpha=1.0,
-                 alpha_dev=None):
+                 alpha_dev=None, row_scales=None, nce=None, nce_logit_scale=None):
     """Same-shape problems [(A, B, C), ...] with non-aliasing outputs in ONE persistent launch (16 per launch):
-    C_g[M,N] = epi(A_g[M,K] @ B_g[N,K]^T), epilogue STORE or ACCUM."""
+    C_g[M,N] = epi(A_g[M,K] @ B_g[N,K]^T), epilogue STORE or ACCUM (optional per-row factors `row_scales[g]`), or
+    NCE_EXP with nce[g] = (mref, thr, stats) and the logit_scale device scalar."""
     global launches
     n = len(problems)
     if n == 0:
@@ -219,6 +226,13 @@ def gemm_grouped(problems, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epil
         a.C, a.ldc, a.c_dtype = C_out.data_ptr(), ldc, dt(C_out)
         a.c2_dtype = F32
         a.epilogue, a.alpha, a.alpha_dev = epilogue, alpha, ptr(alpha_dev)
+    if row_scales is not None:
+        for a, rs in zip(arr, row_scales):
+            a.row_scale = ptr(rs)
+    if nce is not None:
+        for a, (mref, thr, stats) in zip(arr, nce):
+            a.nce_mref, a.nce_thr, a.nce_stats = mref.data_ptr(), thr.data_ptr(), stats.data_ptr()
+            a.nce_logit_scale = nce_logit_scale.data_ptr()
     launches += (n + 15) // 16 if arr[0].in_dtype == BF16 else n
     if gemm_timing is not None:
         e0, e1 = _timing_events()

@@ -28,16 +28,24 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep, cudaStream_t
 
 int gemm_tc_launch_grouped(const b200rec_gemm_args* a, int n, const EpiParams& ep, cudaStream_t st);
 
+static bool nce_args_ok(const b200rec_gemm_args& x) {
+  return x.nce_mref && x.nce_thr && x.nce_stats && x.nce_logit_scale && x.c_dtype == B200REC_BF16 &&
+         ((uintptr_t)x.nce_stats & 15) == 0 && x.in_dtype == B200REC_BF16;
+}
+
 static bool gemm_groupable(const b200rec_gemm_args* a, int n) {
   const b200rec_gemm_args& f = a[0];
-  if (f.in_dtype != B200REC_BF16 || (f.epilogue != B200REC_EPI_STORE && f.epilogue != B200REC_EPI_ACCUM)) return false;
+  if (f.in_dtype != B200REC_BF16 || (f.epilogue != B200REC_EPI_STORE && f.epilogue != B200REC_EPI_ACCUM &&
+                                      f.epilogue != B200REC_EPI_NCE_EXP)) return false;
   if (f.bias || f.resid || f.n_split != 0 || f.C2 != nullptr) return false;
   for (int g = 0; g < n; ++g) {
     const b200rec_gemm_args& x = a[g];
     if (x.M != f.M || x.N != f.N || x.K != f.K || x.a_major != f.a_major || x.b_major != f.b_major ||
         x.in_dtype != f.in_dtype || x.c_dtype != f.c_dtype || x.epilogue != f.epilogue || x.ldc != f.ldc ||
-        x.alpha != f.alpha || x.alpha_dev != f.alpha_dev || x.bias || x.resid || x.n_split != 0 || x.C2 != nullptr)
+        x.alpha != f.alpha || x.alpha_dev != f.alpha_dev || x.bias || x.resid || x.n_split != 0 || x.C2 != nullptr ||
+        x.nce_logit_scale != f.nce_logit_scale || (x.row_scale == nullptr) != (f.row_scale == nullptr))
       return false;
+    if (x.epilogue == B200REC_EPI_NCE_EXP && !nce_args_ok(x)) return false;
     uintptr_t al = x.c_dtype == B200REC_F32 ? 16 : 8;
     if (((uintptr_t)x.C % al) != 0 || ((uintptr_t)x.A & 15) != 0 || ((uintptr_t)x.B & 15) != 0 || x.lda % 8 != 0 ||
         x.ldb % 8 != 0 || x.C == nullptr)
@@ -60,6 +68,8 @@ int b200rec_gemm_grouped(const b200rec_gemm_args* a, int n_groups, void* stream)
       ep.M = f->M; ep.N = f->N;
       ep.vec_ok = (f->ldc % 4) == 0;
       ep.fold_id_stride = 1;
+      ep.nce_logit_scale = f->nce_logit_scale;
+      ep.nce_parts = b200rec_gemm_nce_parts(f->N);
       if (f->epilogue == B200REC_EPI_ACCUM) B200_CHECK_ARG(f->c_dtype == B200REC_F32, "gemm: ACCUM needs fp32 C");
       int rc = gemm_tc_launch_grouped(f, n, ep, (cudaStream_t)stream);
       if (rc) return rc;
@@ -98,6 +108,12 @@ int b200rec_gemm(const b200rec_gemm_args* a, void* stream) {
                 ok(a->resid, a->ldr, B200REC_F32) && (a->n_split % 4 == 0) && a->c_split_stride % 4 == 0 &&
                 a->c2_split_stride % 4 == 0 && a->epilogue != B200REC_EPI_GT_BITS;
   }
+  ep.row_scale = a->row_scale;
+  ep.nce_mref = a->nce_mref; ep.nce_thr = a->nce_thr; ep.nce_stats = a->nce_stats;
+  ep.nce_logit_scale = a->nce_logit_scale; ep.nce_parts = b200rec_gemm_nce_parts(a->N);
+  if (a->epilogue == B200REC_EPI_NCE_EXP)
+    B200_CHECK_ARG(nce_args_ok(*a), "gemm: NCE_EXP needs bf16 operands / output and nce_mref, nce_thr, nce_stats "
+                                    "(16-byte aligned), nce_logit_scale");
   ep.fold_hp = a->fold_hp; ep.fold_head_on = a->fold_head_on; ep.fold_head_cat = a->fold_head_cat;
   ep.fold_item_tags = a->fold_item_tags; ep.fold_id_offset = a->fold_id_offset; ep.fold_id_stride = a->fold_id_stride;
   if (a->epilogue == B200REC_EPI_FOLD_HEADS) {

@@ -16,6 +16,10 @@ struct EpiParams {
   int fold_hp;
   const uint8_t* fold_head_on; const int32_t* fold_head_cat; const uint32_t* fold_item_tags;
   int64_t fold_id_offset, fold_id_stride;
+  // STORE / ACCUM: optional per-row factor (fp32[M])
+  const float* row_scale;
+  // B200REC_EPI_NCE_EXP
+  const float* nce_mref; const float* nce_thr; float* nce_stats; const float* nce_logit_scale; int nce_parts;
 };
 
 __device__ __forceinline__ void epi_store_scalar(void* base, int dtype, int64_t off, float v) {
@@ -35,12 +39,14 @@ __device__ __forceinline__ int64_t epi_offset(const EpiParams& p, int m, int n, 
 __device__ __forceinline__ void epi_apply_scalar(const EpiParams& p, int m, int n, float acc) {
   if (m >= p.M || n >= p.N) return;
   switch (p.mode) {
+    case B200REC_EPI_NCE_EXP:     // the exponentials were taken in the TMEM phase: plain store
     case B200REC_EPI_STORE:
-      epi_store_scalar(p.C, p.c_dtype, epi_offset(p, m, n, p.ldc, p.c_split_stride), p.alpha * acc);
+      epi_store_scalar(p.C, p.c_dtype, epi_offset(p, m, n, p.ldc, p.c_split_stride),
+                       p.alpha * (p.row_scale ? p.row_scale[m] : 1.f) * acc);
       break;
     case B200REC_EPI_ACCUM: {
       float* c = (float*)p.C + epi_offset(p, m, n, p.ldc, p.c_split_stride);
-      *c += p.alpha * acc;
+      *c += p.alpha * (p.row_scale ? p.row_scale[m] : 1.f) * acc;
       break;
     }
     case B200REC_EPI_SILU_DUAL:
@@ -207,16 +213,20 @@ __device__ __forceinline__ void epi_apply_vec4(const EpiParams& p, int m, int n,
     epi_apply_tail4(p, m, n, v[0], v[1], v[2], v[3]);
     return;
   }
-  if (MODE == B200REC_EPI_STORE) {
+  if (MODE == B200REC_EPI_NCE_EXP) {
+    store4_dt(p.C, p.c_dtype, epi_offset(p, m, n, p.ldc, p.c_split_stride), v);
+  } else if (MODE == B200REC_EPI_STORE) {
+    const float a = p.row_scale ? p.alpha * __ldg(p.row_scale + m) : p.alpha;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] *= p.alpha;
+    for (int i = 0; i < 4; ++i) v[i] *= a;
     store4_dt(p.C, p.c_dtype, epi_offset(p, m, n, p.ldc, p.c_split_stride), v);
   } else if (MODE == B200REC_EPI_ACCUM) {
     float* c = (float*)p.C + epi_offset(p, m, n, p.ldc, p.c_split_stride);
+    const float a = p.row_scale ? p.alpha * __ldg(p.row_scale + m) : p.alpha;
     float o[4];
     load4<float>(c, o);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) o[i] += p.alpha * v[i];
+    for (int i = 0; i < 4; ++i) o[i] += a * v[i];
     store4<float>(c, o);
   } else if (MODE == B200REC_EPI_SILU_DUAL) {
     store4_dt(p.C2, p.c2_dtype, epi_offset(p, m, n, p.ldc2, p.c2_split_stride), v);
@@ -280,9 +290,10 @@ template <int MODE>
 __device__ __forceinline__ void epi_finish_vec4(const EpiParams& p, int m, int n, float (&v)[4], const float (&r)[4],
                                                 const float (&b)[4]) {
   if (MODE == B200REC_EPI_ACCUM) {
+    const float a = p.row_scale ? p.alpha * __ldg(p.row_scale + m) : p.alpha;
     float o[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) o[i] = r[i] + p.alpha * v[i];
+    for (int i = 0; i < 4; ++i) o[i] = r[i] + a * v[i];
     store4<float>((float*)p.C + epi_offset(p, m, n, p.ldc, p.c_split_stride), o);
   } else if (MODE == B200REC_EPI_BIAS_RESID) {
 #pragma unroll

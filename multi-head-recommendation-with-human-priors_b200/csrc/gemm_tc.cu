@@ -40,6 +40,10 @@ struct TcGroupArgs {
   CUtensorMap a[TC_MAX_GROUPS];
   CUtensorMap b[TC_MAX_GROUPS];
   void* C[TC_MAX_GROUPS];
+  const float* row_scale[TC_MAX_GROUPS];   // STORE / ACCUM (nullable)
+  const float* nce_mref[TC_MAX_GROUPS];    // NCE_EXP
+  const float* nce_thr[TC_MAX_GROUPS];
+  float* nce_stats[TC_MAX_GROUPS];
 };
 
 // CTAS = 1: one CTA per 128 x BN tile.  CTAS = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN
@@ -47,7 +51,7 @@ struct TcGroupArgs {
 // traffic per flop drop by a third and the epilogue's transpose traffic fits beside the mainloop.
 template <int MODE, int CTAS>
 __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CUtensorMap* maps_b, const TcParams& p,
-                                             const EpiParams& ep_in, void* const* group_C) {
+                                             const EpiParams& ep_in, const TcGroupArgs* ga) {
   EpiParams ep = ep_in;
   if (ep.alpha_dev && (ep.mode == B200REC_EPI_STORE || ep.mode == B200REC_EPI_ACCUM)) ep.alpha *= *ep.alpha_dev;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -192,7 +196,18 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
       const int grp = gtile / tiles_pg, tile = gtile - grp * tiles_pg;
       const int m0 = (tile % p.num_m) * (TC_BM * CTAS) + (int)rank * TC_BM;
       const int n0 = (tile / p.num_m) * p.BN;
-      if (group_C) ep.C = group_C[grp];
+      if (ga) {
+        ep.C = ga->C[grp];
+        ep.row_scale = ga->row_scale[grp];
+        ep.nce_mref = ga->nce_mref[grp]; ep.nce_thr = ga->nce_thr[grp]; ep.nce_stats = ga->nce_stats[grp];
+      }
+      // NCE_EXP: this lane's row constants and the partial sums of the columns this warp converts in this tile
+      float nce_mref = 0.f, nce_thr = INFINITY, nce_tau2 = 0.f, nce_s = 0.f, nce_w = 0.f, nce_gt = 0.f;
+      if (MODE == B200REC_EPI_NCE_EXP) {
+        const int m = m0 + quarter * 32 + lane;
+        if (m < ep.M) { nce_mref = __ldg(ep.nce_mref + m); nce_thr = __ldg(ep.nce_thr + m); }
+        nce_tau2 = __expf(fminf(fmaxf(__ldg(ep.nce_logit_scale), 0.f), 4.605170185988092f)) * 1.4426950408889634f;
+      }
       if (p.split_k > 1) ep.C = (float*)ep_base.C + (int64_t)split * p.split_stride;   // partial tile of this k-range
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
@@ -200,6 +215,22 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
       for (int c = half; c < p.BN / 32; c += 2) {
         float v[32];
         tmem_ld_32x32(t_row + (uint32_t)c * 32u, v);
+        if (MODE == B200REC_EPI_NCE_EXP) {
+          // softmax numerators relative to the row's reference: e = 2^(tau2 * cos - mref), rounded to bf16 BEFORE it is
+          // summed (the stored tile and the partial sums stay consistent); columns beyond N contribute nothing
+          const int nn = n0 + c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float cosv = v[i];
+            float e;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(cosv, nce_tau2, -nce_mref)));
+            e = (nn + i < ep.N) ? __bfloat162float(__float2bfloat16_rn(e)) : 0.f;
+            nce_s += e;
+            nce_w = fmaf(e, cosv, nce_w);
+            nce_gt += (nn + i < ep.N && cosv > nce_thr) ? 1.f : 0.f;
+            v[i] = e;
+          }
+        }
         if (MODE == B200REC_EPI_GT_BITS) {
           uint32_t wbits = 0;
 #pragma unroll
@@ -326,6 +357,14 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
         }
         __syncwarp();
       }
+      if (MODE == B200REC_EPI_NCE_EXP) {
+        const int m = m0 + quarter * 32 + lane;
+        if (m < ep.M) {
+          const int part = (tile / p.num_m) * 2 + half;
+          float st4[4] = {nce_s, nce_w, nce_gt, 0.f};
+          store4<float>(ep.nce_stats + ((int64_t)m * ep.nce_parts + part) * 4, st4);
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -353,7 +392,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 template <int MODE, int CTAS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_grouped_kernel(const __grid_constant__ TcGroupArgs ga, const TcParams p, const EpiParams ep_in) {
-  gemm_tc_body<MODE, CTAS>(ga.a, ga.b, p, ep_in, ga.C);
+  gemm_tc_body<MODE, CTAS>(ga.a, ga.b, p, ep_in, &ga);
 }
 
 // sums the split-K partial outputs in ascending split order (deterministic)
@@ -424,6 +463,8 @@ static int g_force_bn = 0;    // test hook
 static int g_force_ctas = 0;  // test hook: 1 = never use CTA pairs
 
 extern "C" void b200rec_gemm_force_bn(int bn) { g_force_bn = bn; }
+// partial-sum slots per row of the NCE_EXP epilogue: two epilogue warps per BN-wide column tile
+extern "C" int b200rec_gemm_nce_parts(int N) { return 2 * ceil_div_i(N, N > 128 ? 256 : 128); }
 extern "C" void b200rec_gemm_force_ctas(int ctas) { g_force_ctas = ctas; }
 
 int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep_in, cudaStream_t st) {
@@ -447,6 +488,8 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep_in, cudaStrea
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
   }
   TcParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
@@ -459,8 +502,9 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep_in, cudaStrea
     // (the 128-wide one is shared-memory-port bound) unless it leaves more than half of the SMs without a tile
     const int64_t tiles256 = (int64_t)ceil_div_i(a->M, TC_BM * ctas) * ceil_div_i(a->N, 256);
     p.BN = (a->N > 128 && tiles256 * 2 >= units) ? 256 : 128;
+    if (ep_in.mode == B200REC_EPI_NCE_EXP) p.BN = a->N > 128 ? 256 : 128;   // nce_parts is a function of N alone
   }
-  if (g_force_bn == 128 || g_force_bn == 256) p.BN = g_force_bn;
+  if ((g_force_bn == 128 || g_force_bn == 256) && ep_in.mode != B200REC_EPI_NCE_EXP) p.BN = g_force_bn;
   p.split_k = 1;
   p.groups = 1;
   const int num_k_host = ceil_div_i(a->K, TC_BK);
@@ -530,6 +574,7 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep_in, cudaStrea
     case B200REC_EPI_RESBLOCK: TC_LAUNCH(4); break;
     case B200REC_EPI_GT_BITS: TC_LAUNCH(5); break;
     case B200REC_EPI_FOLD_HEADS: TC_LAUNCH(6); break;
+    case B200REC_EPI_NCE_EXP: TC_LAUNCH(7); break;
     default: b200rec_set_error("gemm: bad epilogue %d", ep.mode); return 1;
   }
 #undef TC_LAUNCH
@@ -553,6 +598,8 @@ int gemm_tc_launch_grouped(const b200rec_gemm_args* a, int n, const EpiParams& e
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_grouped_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_grouped_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_grouped_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_grouped_kernel<7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_grouped_kernel<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     B200_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   TcParams p;
@@ -561,7 +608,7 @@ int gemm_tc_launch_grouped(const b200rec_gemm_args* a, int n, const EpiParams& e
   const int ctas = (a->M > TC_BM && g_force_ctas != 1) ? 2 : 1;
   const int units = num_sms / ctas;
   p.BN = a->N > 128 ? 256 : 128;
-  if (g_force_bn == 128 || g_force_bn == 256) p.BN = g_force_bn;
+  if ((g_force_bn == 128 || g_force_bn == 256) && ep_in.mode != B200REC_EPI_NCE_EXP) p.BN = g_force_bn;
   p.split_k = 1;
   p.kb_per_split = ceil_div_i(a->K, TC_BK);
   p.split_stride = 0;
@@ -588,6 +635,8 @@ int gemm_tc_launch_grouped(const b200rec_gemm_args* a, int n, const EpiParams& e
       if (make_map(&ga.b[g], x->B, (uint64_t)x->N, (uint64_t)x->K, (uint64_t)x->ldb, 64, 64)) return 1;
     }
     ga.C[g] = x->C;
+    ga.row_scale[g] = x->row_scale;
+    ga.nce_mref[g] = x->nce_mref; ga.nce_thr[g] = x->nce_thr; ga.nce_stats[g] = x->nce_stats;
   }
   const int tiles = p.num_m * p.num_n * n;
   const int grid = (tiles < units ? tiles : units) * ctas;
@@ -611,8 +660,11 @@ int gemm_tc_launch_grouped(const b200rec_gemm_args* a, int n, const EpiParams& e
   } else if (ep.mode == B200REC_EPI_ACCUM) {
     if (ctas == 2) B200_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_grouped_kernel<1, 2>, ga, p, ep));
     else B200_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_grouped_kernel<1, 1>, ga, p, ep));
+  } else if (ep.mode == B200REC_EPI_NCE_EXP) {
+    if (ctas == 2) B200_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_grouped_kernel<7, 2>, ga, p, ep));
+    else B200_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_grouped_kernel<7, 1>, ga, p, ep));
   } else {
-    b200rec_set_error("gemm_grouped: epilogue %d not supported (STORE / ACCUM)", ep.mode);
+    b200rec_set_error("gemm_grouped: epilogue %d not supported (STORE / ACCUM / NCE_EXP)", ep.mode);
     return 1;
   }
   B200_LAUNCH_OK();

@@ -692,3 +692,235 @@ int b200rec_nce_pos_bwd_t(const float* g0, const void* q_hat, int64_t ldq, int a
   B200_LAUNCH_OK();
   return 0;
 }
+
+
+// =============================================================================================================
+// Fused path (bf16 production mode): the logits GEMM writes softmax numerators E = 2^(tau2 cos - mref) and per-row
+// partial sums (B200REC_EPI_NCE_EXP); nothing of size [T, Nneg] in fp32 ever reaches HBM and the old row kernel
+// (logits read + G write) is gone.
+//   nce_pos_ref  before the GEMM: positive cosines of every offset, the row's reference exponent mref and the p = 0
+//                cosine (threshold of the top-k logging count)
+//   nce_combine  after the GEMM: per-offset log-sum-exp / loss / positive-logit gradient / d(logit_scale) / rank from the
+//                partial sums; offsets whose target filters negatives (hstu.py:613-614) subtract exactly those stored
+//                numerators; the gradient w.r.t. the cosine logits is  G = row_scale[t] * E  (E patched at the few
+//                filtered entries), consumed by the backward GEMMs as  dq = row_scale * (E n_hat),
+//                dn = E^T (row_scale * q_hat)  -- the scaled query copy `qs` is written here.
+// Range: mref = max over the row's valid offsets of the positive logit (log2 domain), floored at tau2 - 100, so
+// E <= 2^100 (fp32 sums of 8192 terms cannot overflow) and the positive term never underflows against it; numerators
+// more than 2^-126 below the reference flush to zero, i.e. softmax weights below 1e-38 are dropped.
+// =============================================================================================================
+template <int MAXV>
+__global__ void __launch_bounds__(256) nce_pos_ref_kernel(const bf16* __restrict__ q_hat, int64_t ldq,
+                                                          const bf16* __restrict__ t_hat, int D4,
+                                                          const int32_t* __restrict__ tok_b,
+                                                          const int32_t* __restrict__ tok_pos, int T, int LP, int P,
+                                                          uint32_t p_mask, const uint8_t* __restrict__ tok_ok,
+                                                          int tok_ok_ld, int tok_ok_col,
+                                                          const float* __restrict__ logit_scale,
+                                                          float* __restrict__ pos_cos, float* __restrict__ mref,
+                                                          float* __restrict__ thr) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  const float tau2 = __expf(fminf(fmaxf(*logit_scale, 0.f), 4.605170185988092f)) * 1.4426950408889634f;
+  float q[MAXV][4];
+#pragma unroll
+  for (int u = 0; u < MAXV; ++u) {
+    const int c = lane + 32 * u;
+    if (c < D4) load4<bf16>(q_hat + (int64_t)t * ldq + c * 4, q[u]);
+  }
+  const int64_t r0 = (int64_t)tok_b[t] * LP + tok_pos[t] + 1;
+  float best = -INFINITY, first = INFINITY;
+  for (int p = 0; p < P; ++p) {
+    float acc = 0.f;
+    const bool ok = ((p_mask >> p) & 1u) && tok_ok[(r0 + p) * tok_ok_ld + tok_ok_col] != 0;   // warp-uniform
+    if (ok) {
+#pragma unroll
+      for (int u = 0; u < MAXV; ++u) {
+        const int c = lane + 32 * u;
+        if (c < D4) {
+          float b[4];
+          load4<bf16>(t_hat + ((r0 + p) * D4 + c) * 4, b);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc = fmaf(q[u][k], b[k], acc);
+        }
+      }
+      acc = warp_sum(acc);
+      best = fmaxf(best, acc);
+      if (p == 0) first = acc;
+    }
+    if (lane == 0) pos_cos[(int64_t)t * P + p] = ok ? acc : __int_as_float(0x7fc00000);  // NaN: offset not served
+  }
+  if (lane == 0) {
+    // unused rows (no valid offset): reference = tau2, every numerator <= 1, the row is multiplied by row_scale = 0
+    mref[t] = best == -INFINITY ? tau2 : fmaxf(best * tau2, tau2 - 100.f);
+    thr[t] = first;
+  }
+}
+
+extern "C" int b200rec_nce_pos_ref(const void* q_hat, int64_t ldq, const void* t_hat, int D, const int32_t* tok_b,
+                                   const int32_t* tok_pos, int T, int LP, int P, uint32_t p_mask, const uint8_t* tok_ok,
+                                   int tok_ok_ld, int tok_ok_col, const float* logit_scale, float* pos_cos, float* mref,
+                                   float* thr, void* stream) {
+  B200_CHECK_ARG(P >= 1 && P <= NCE_MAXP, "nce_pos_ref: pred_len %d not in [1,%d]", P, NCE_MAXP);
+  B200_CHECK_ARG(D % 4 == 0 && ldq % 4 == 0 && D <= 2048, "nce_pos_ref: D=%d must be a multiple of 4, <= 2048", D);
+  if (T == 0) return 0;
+  const int blocks = ceil_div_i(T, 8);
+  if (D <= 512)
+    nce_pos_ref_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)q_hat, ldq, (const bf16*)t_hat, D / 4,
+                                                                    tok_b, tok_pos, T, LP, P, p_mask, tok_ok, tok_ok_ld,
+                                                                    tok_ok_col, logit_scale, pos_cos, mref, thr);
+  else
+    nce_pos_ref_kernel<16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)q_hat, ldq, (const bf16*)t_hat, D / 4,
+                                                                     tok_b, tok_pos, T, LP, P, p_mask, tok_ok, tok_ok_ld,
+                                                                     tok_ok_col, logit_scale, pos_cos, mref, thr);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) nce_combine_kernel(
+    const float* __restrict__ stats, int n_parts, bf16* __restrict__ E, int64_t lde, int n_neg,
+    const uint32_t* __restrict__ same_bits, const uint8_t* __restrict__ row_any, const float* __restrict__ pos_cos,
+    const float* __restrict__ mref_a, const bf16* __restrict__ q_hat, int64_t ldq, int D4,
+    const int32_t* __restrict__ tok_b, const int32_t* __restrict__ tok_pos, int T, int LP, int P,
+    const float* __restrict__ coef, const float* __restrict__ logit_scale, float* __restrict__ loss,
+    float* __restrict__ g0, float* __restrict__ dscale, int32_t* __restrict__ rank0, int32_t* __restrict__ nvalid,
+    float* __restrict__ row_scale, bf16* __restrict__ qs, int64_t ldqs) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+  const float tau = __expf(fminf(fmaxf(*logit_scale, 0.f), 4.605170185988092f));
+  const float tau2 = tau * LOG2E;
+  const float mref = mref_a[t];
+  const int64_t r0 = (int64_t)tok_b[t] * LP + tok_pos[t] + 1;
+  const int n_words = (n_neg + 31) >> 5;
+  // row totals of the stored numerators: fixed lane assignment + fixed shuffle tree -> deterministic
+  float S = 0.f, Wr = 0.f, GT = 0.f;
+  for (int q = lane; q < n_parts; q += 32) {
+    float st4[4];
+    load4<float>(stats + ((int64_t)t * n_parts + q) * 4, st4);
+    S += st4[0]; Wr += st4[1]; GT += st4[2];
+  }
+  S = warp_sum(S); Wr = warp_sum(Wr); GT = warp_sum(GT);
+  const float pc0 = pos_cos[(int64_t)t * P];            // NaN when offset 0 is not served
+  float cp[NCE_MAXP];
+  uint32_t masked_set = 0;
+  float Csum = 0.f;
+#pragma unroll
+  for (int p = 0; p < NCE_MAXP; ++p) {
+    cp[p] = 0.f;
+    if (p >= P) continue;
+    const float pc = pos_cos[(int64_t)t * P + p];
+    const bool valid = pc == pc;                           // warp-uniform
+    float l_ = 0.f, g_ = 0.f, d_ = 0.f;
+    int rk = -1, nv = 0;
+    if (valid) {
+      float Sp = S, Wp = Wr, gtp = GT;
+      int cnt = n_neg;
+      const bool masked = row_any[r0 + p] != 0;
+      if (masked) {
+        // subtract exactly the stored numerators of the filtered negatives (rare: a negative that IS this target)
+        const uint32_t* bits = same_bits + (r0 + p) * n_words;
+        float ds = 0.f, dw = 0.f, dg = 0.f;
+        int dc = 0;
+        for (int w = lane; w < n_words; w += 32) {
+          uint32_t b = bits[w];
+          while (b) {
+            const int j = (w << 5) + __ffs(b) - 1;
+            b &= b - 1;
+            if (j < n_neg) {
+              const float e = __bfloat162float(E[(int64_t)t * lde + j]);
+              dc += 1;
+              if (e > 0.f) {
+                const float cosj = (__log2f(e) + mref) / tau2;
+                ds += e;
+                dw = fmaf(e, cosj, dw);
+                dg += (p == 0 && cosj > pc0) ? 1.f : 0.f;
+              }
+            }
+          }
+        }
+        ds = warp_sum(ds); dw = warp_sum(dw); dg = warp_sum(dg);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dc += __shfl_xor_sync(0xffffffffu, dc, o);
+        Sp = fmaxf(S - ds, 0.f); Wp = Wr - dw; gtp = GT - dg; cnt = n_neg - dc;
+        masked_set |= 1u << p;
+      }
+      const float zp2 = tau2 * pc;
+      const float a = Sp > 0.f ? mref + __log2f(Sp) : -INFINITY;
+      const float M = fmaxf(a, zp2);
+      const float lse2 = M + __log2f(exp2f(a - M) + exp2f(zp2 - M));
+      const float c = coef[p];
+      const float sm0 = exp2f(zp2 - lse2);
+      const float wn = exp2f(mref - lse2);                 // weight of a unit numerator in this offset's softmax
+      l_ = c * (lse2 - zp2) * LN2;
+      g_ = c * (sm0 - 1.f);
+      // d loss / d logit_scale = sum_k softmax_k z_k - z_0 with natural-log logits z = tau * cos
+      d_ = c * (tau * Wp * wn + sm0 * tau * pc - tau * pc);
+      rk = (p == 0 || masked) ? (int)(gtp + 0.5f) : -1;
+      nv = cnt + 1;
+      cp[p] = c * wn;
+      Csum += cp[p];
+    }
+    if (lane == 0) {
+      loss[(int64_t)t * P + p] = l_;
+      g0[(int64_t)t * P + p] = g_;
+      dscale[(int64_t)t * P + p] = d_;
+      rank0[(int64_t)t * P + p] = rk;
+      nvalid[(int64_t)t * P + p] = nv;
+    }
+  }
+  const float rs = tau * Csum;                             // G[t, j] = rs * E[t, j] for every unfiltered (t, j)
+  if (lane == 0) row_scale[t] = rs;
+  if (masked_set && Csum > 0.f) {
+    // a filtered (offset, negative) pair takes no gradient from that offset: scale the stored numerator by the share of
+    // the remaining offsets, so that rs * E'[t, j] is exactly the gradient w.r.t. logit (t, j)
+    for (int w = lane; w < n_words; w += 32) {
+      uint32_t wb[NCE_MAXP];
+      uint32_t any = 0;
+#pragma unroll
+      for (int p = 0; p < NCE_MAXP; ++p) {
+        wb[p] = ((masked_set >> p) & 1u) ? same_bits[(r0 + p) * n_words + w] : 0u;
+        any |= wb[p];
+      }
+      while (any) {
+        const int bit = __ffs(any) - 1;
+        any &= any - 1;
+        const int j = (w << 5) + bit;
+        if (j >= n_neg) continue;
+        float sc = 0.f;
+#pragma unroll
+        for (int p = 0; p < NCE_MAXP; ++p) sc += ((wb[p] >> bit) & 1u) ? cp[p] : 0.f;
+        const float f = fmaxf(1.f - sc / Csum, 0.f);
+        const int64_t at = (int64_t)t * lde + j;
+        E[at] = __float2bfloat16_rn(__bfloat162float(E[at]) * f);
+      }
+    }
+  }
+  if (qs != nullptr) {
+    for (int c = lane; c < D4; c += 32) {
+      float v[4];
+      load4<bf16>(q_hat + (int64_t)t * ldq + c * 4, v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] *= rs;
+      store4<bf16>(qs + (int64_t)t * ldqs + c * 4, v);
+    }
+  }
+}
+
+extern "C" int b200rec_nce_combine(const float* stats, int n_parts, void* E, int64_t lde, int n_neg,
+                                   const uint32_t* same_bits, const uint8_t* row_any, const float* pos_cos,
+                                   const float* mref, const void* q_hat, int64_t ldq, int D, const int32_t* tok_b,
+                                   const int32_t* tok_pos, int T, int LP, int P, const float* coef,
+                                   const float* logit_scale, float* loss, float* g0, float* dscale, int32_t* rank0,
+                                   int32_t* nvalid, float* row_scale, void* qs, int64_t ldqs, void* stream) {
+  B200_CHECK_ARG(P >= 1 && P <= NCE_MAXP, "nce_combine: pred_len %d not in [1,%d]", P, NCE_MAXP);
+  B200_CHECK_ARG(D % 4 == 0 && ldq % 4 == 0 && ldqs % 4 == 0 && n_parts >= 1, "nce_combine: bad D / ld / n_parts");
+  if (T == 0) return 0;
+  nce_combine_kernel<<<ceil_div_i(T, 8), 256, 0, (cudaStream_t)stream>>>(
+      stats, n_parts, (bf16*)E, lde, n_neg, same_bits, row_any, pos_cos, mref, (const bf16*)q_hat, ldq, D / 4, tok_b,
+      tok_pos, T, LP, P, coef, logit_scale, loss, g0, dscale, rank0, nvalid, row_scale, (bf16*)qs, ldqs);
+  B200_LAUNCH_OK();
+  return 0;
+}

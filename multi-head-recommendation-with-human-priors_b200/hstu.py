@@ -189,6 +189,7 @@ class HSTU(nn.Module):
         self.sparse_embedding_grad = bool(config.get("sparse_embedding_grad", False))
         self.use_tc_attention = bool(config.get("tc_attention", True))
         self.use_fused_eval = bool(config.get("fused_eval", True))
+        self.use_fused_nce = bool(config.get("fused_nce", True))     # bf16 mode: softmax numerators from the GEMM epilogue
         self.share_negatives = bool(config.get("share_negatives", True))   # all-gather negatives across ranks
         self.dropout_seed = int(config.get("seed", 2020)) & 0xffffffff
         self._rng_step = None      # device counter feeding the Philox dropout stream
@@ -749,31 +750,72 @@ class HSTU(nn.Module):
         # ---- NCE jobs
         scale = self.logit_scale.data.to(torch.float32)
         job_out = []
-        pos_ws = torch.empty(T * P, dtype=torch.float32, device=dev)
-        # all (head, negative set) logit GEMMs in one persistent launch (hstu.py:697: one matmul per head)
         qv = qhat.view(T, Hx * D)
         hqs = [j.head if self.medusa_num_layers > 0 else 0 for j in self._jobs]
-        all_logits = [torch.empty((T, ld_neg), dtype=torch.float32, device=dev) for _ in self._jobs]
-        L.gemm_grouped([(qv[:, hq * D:(hq + 1) * D], nhat[j.nset], lg) for j, hq, lg in zip(self._jobs, hqs, all_logits)],
-                       T, n_neg, D, lda=Hx * D, ldb=D, ldc=ld_neg)
-        for j, hq, logits in zip(self._jobs, hqs, all_logits):
-            q_h = qv[:, hq * D:(hq + 1) * D]
-            lossv = torch.empty((T, P), dtype=torch.float32, device=dev)
-            g0 = torch.empty((T, P), dtype=torch.float32, device=dev)
-            dsc = torch.empty((T, P), dtype=torch.float32, device=dev)
-            rank0 = torch.empty((T, P), dtype=torch.int32, device=dev)
-            nval = torch.empty((T, P), dtype=torch.int32, device=dev)
-            G = torch.empty((T, ld_neg), dtype=act, device=dev) if need_grad else None
-            L.call("b200rec_nce_loss_fwd", logits.data_ptr(), ld_neg, n_neg, bits[j.nset].data_ptr(),
-                   row_any[j.nset].data_ptr(), pos_ws.data_ptr(), q_h.data_ptr(),
-                   Hx * D, that.data_ptr(), a_dt, D, tok_b.data_ptr(), tok_pos.data_ptr(), T, LP, P, j.p_mask,
-                   tok_ok.data_ptr(), n_col, j.col, coefs[(j.col, j.w)].data_ptr(), scale.data_ptr(),
-                   lossv.data_ptr(), g0.data_ptr(), dsc.data_ptr(), rank0.data_ptr(), nval.data_ptr(), L.ptr(G),
-                   ld_neg, st)
-            per_p = torch.empty(P, dtype=torch.float32, device=dev)
-            L.colsum(lossv, T, P, P, per_p)
-            job_out.append(dict(job=j, per_p=per_p, g0=g0, dsc=dsc, rank0=rank0, nval=nval, G=G, hq=hq))
-        del all_logits
+        fused = act == torch.bfloat16 and self.use_fused_nce and D % 4 == 0 and D <= 2048
+        if fused:
+            # fused path: no fp32 [T, Nneg] logits in HBM.  positives + row reference -> ONE grouped
+            # GEMM whose epilogue writes bf16 softmax numerators E and per-row partial sums -> combine (loss, scalars,
+            # row_scale with dL/dlogit = row_scale * E, scaled query copy for the dn GEMM)
+            n_parts = L.lib().b200rec_gemm_nce_parts(n_neg)
+            pre = []
+            for j, hq in zip(self._jobs, hqs):
+                q_h = qv[:, hq * D:(hq + 1) * D]
+                pos_cos = torch.empty((T, P), dtype=torch.float32, device=dev)
+                mref = torch.empty(T, dtype=torch.float32, device=dev)
+                thr = torch.empty(T, dtype=torch.float32, device=dev)
+                L.call("b200rec_nce_pos_ref", q_h.data_ptr(), Hx * D, that.data_ptr(), D, tok_b.data_ptr(),
+                       tok_pos.data_ptr(), T, LP, P, j.p_mask, tok_ok.data_ptr(), n_col, j.col, scale.data_ptr(),
+                       pos_cos.data_ptr(), mref.data_ptr(), thr.data_ptr(), st)
+                E = torch.empty((T, ld_neg), dtype=act, device=dev)
+                stats = torch.empty((T, n_parts, 4), dtype=torch.float32, device=dev)
+                pre.append((q_h, pos_cos, mref, thr, E, stats))
+            L.gemm_grouped([(q_h, nhat[j.nset], E) for j, (q_h, _, _, _, E, _) in zip(self._jobs, pre)],
+                           T, n_neg, D, lda=Hx * D, ldb=D, ldc=ld_neg, epilogue=L.EPI_NCE_EXP,
+                           nce=[(mref, thr, stats) for (_, _, mref, thr, _, stats) in pre], nce_logit_scale=scale)
+            for j, hq, (q_h, pos_cos, mref, thr, E, stats) in zip(self._jobs, hqs, pre):
+                lossv = torch.empty((T, P), dtype=torch.float32, device=dev)
+                g0 = torch.empty((T, P), dtype=torch.float32, device=dev)
+                dsc = torch.empty((T, P), dtype=torch.float32, device=dev)
+                rank0 = torch.empty((T, P), dtype=torch.int32, device=dev)
+                nval = torch.empty((T, P), dtype=torch.int32, device=dev)
+                rscale = torch.empty(T, dtype=torch.float32, device=dev)
+                qs = torch.empty((T, D), dtype=act, device=dev) if need_grad else None
+                L.call("b200rec_nce_combine", stats.data_ptr(), n_parts, E.data_ptr(), ld_neg, n_neg,
+                       bits[j.nset].data_ptr(), row_any[j.nset].data_ptr(), pos_cos.data_ptr(), mref.data_ptr(),
+                       q_h.data_ptr(), Hx * D, D, tok_b.data_ptr(), tok_pos.data_ptr(), T, LP, P,
+                       coefs[(j.col, j.w)].data_ptr(), scale.data_ptr(), lossv.data_ptr(), g0.data_ptr(), dsc.data_ptr(),
+                       rank0.data_ptr(), nval.data_ptr(), rscale.data_ptr(), L.ptr(qs), D, st)
+                per_p = torch.empty(P, dtype=torch.float32, device=dev)
+                L.colsum(lossv, T, P, P, per_p)
+                job_out.append(dict(job=j, per_p=per_p, g0=g0, dsc=dsc, rank0=rank0, nval=nval, hq=hq,
+                                    G=E if need_grad else None, rscale=rscale, qs=qs))
+            del pre
+        else:
+            pos_ws = torch.empty(T * P, dtype=torch.float32, device=dev)
+            # all (head, negative set) logit GEMMs in one persistent launch (hstu.py:697: one matmul per head)
+            all_logits = [torch.empty((T, ld_neg), dtype=torch.float32, device=dev) for _ in self._jobs]
+            L.gemm_grouped([(qv[:, hq * D:(hq + 1) * D], nhat[j.nset], lg) for j, hq, lg in zip(self._jobs, hqs, all_logits)],
+                           T, n_neg, D, lda=Hx * D, ldb=D, ldc=ld_neg)
+            for j, hq, logits in zip(self._jobs, hqs, all_logits):
+                q_h = qv[:, hq * D:(hq + 1) * D]
+                lossv = torch.empty((T, P), dtype=torch.float32, device=dev)
+                g0 = torch.empty((T, P), dtype=torch.float32, device=dev)
+                dsc = torch.empty((T, P), dtype=torch.float32, device=dev)
+                rank0 = torch.empty((T, P), dtype=torch.int32, device=dev)
+                nval = torch.empty((T, P), dtype=torch.int32, device=dev)
+                G = torch.empty((T, ld_neg), dtype=act, device=dev) if need_grad else None
+                L.call("b200rec_nce_loss_fwd", logits.data_ptr(), ld_neg, n_neg, bits[j.nset].data_ptr(),
+                       row_any[j.nset].data_ptr(), pos_ws.data_ptr(), q_h.data_ptr(),
+                       Hx * D, that.data_ptr(), a_dt, D, tok_b.data_ptr(), tok_pos.data_ptr(), T, LP, P, j.p_mask,
+                       tok_ok.data_ptr(), n_col, j.col, coefs[(j.col, j.w)].data_ptr(), scale.data_ptr(),
+                       lossv.data_ptr(), g0.data_ptr(), dsc.data_ptr(), rank0.data_ptr(), nval.data_ptr(), L.ptr(G),
+                       ld_neg, st)
+                per_p = torch.empty(P, dtype=torch.float32, device=dev)
+                L.colsum(lossv, T, P, P, per_p)
+                job_out.append(dict(job=j, per_p=per_p, g0=g0, dsc=dsc, rank0=rank0, nval=nval, G=G, hq=hq,
+                                    rscale=None, qs=None))
+            del all_logits
         # ---- total loss + logging scalars (tiny [P] vectors)
         half = 0.5 if (self.loss == "prior" and self.head_interaction == "additive") else 1.0   # hstu.py:870
         total = torch.zeros((), dtype=torch.float32, device=dev)
@@ -858,18 +900,27 @@ class HSTU(nn.Module):
                     rs.append({k: idx})
             return [list(r.values()) for r in rs]
 
-        # dq_hat = G @ nhat   (nhat [n_neg, D] = [K, N] -> MN-major B): one grouped launch per round
+        # dq_hat = G @ nhat   (nhat [n_neg, D] = [K, N] -> MN-major B): one grouped launch per round.  Fused path:
+        # G = row_scale * E, the row factor is applied in the GEMM epilogue (dq) / folded into the query copy qs (dn)
+        fused = outs[0]["rscale"] is not None
         for r, idxs in enumerate(rounds([o["hq"] for o in outs])):
             L.gemm_grouped([(outs[i]["G"], ctx["nhat"][outs[i]["job"].nset], dqhat[:, outs[i]["hq"] * D:(outs[i]["hq"] + 1) * D])
                             for i in idxs], T, D, n_neg, lda=ld_neg, ldb=D, b_major=1, ldc=Hx * D,
-                           epilogue=L.EPI_STORE if r == 0 else L.EPI_ACCUM, alpha_dev=gscale)
+                           epilogue=L.EPI_STORE if r == 0 else L.EPI_ACCUM, alpha_dev=gscale,
+                           row_scales=[outs[i]["rscale"] for i in idxs] if fused else None)
         # dn_hat += G^T @ q_hat   (both MN-major, K = T)
         for o in outs:
             if o["job"].nset not in dnhat:
                 dnhat[o["job"].nset] = torch.empty((n_neg, D), dtype=torch.float32, device=dev)
         for r, idxs in enumerate(rounds([o["job"].nset for o in outs])):
-            L.gemm_grouped([(outs[i]["G"], qhat2[:, outs[i]["hq"] * D:(outs[i]["hq"] + 1) * D], dnhat[outs[i]["job"].nset])
-                            for i in idxs], n_neg, D, T, lda=ld_neg, a_major=1, ldb=Hx * D, b_major=1, ldc=D,
+            if fused:
+                probs = [(outs[i]["G"], outs[i]["qs"], dnhat[outs[i]["job"].nset]) for i in idxs]
+                ldq_ = D
+            else:
+                probs = [(outs[i]["G"], qhat2[:, outs[i]["hq"] * D:(outs[i]["hq"] + 1) * D], dnhat[outs[i]["job"].nset])
+                         for i in idxs]
+                ldq_ = Hx * D
+            L.gemm_grouped(probs, n_neg, D, T, lda=ld_neg, a_major=1, ldb=ldq_, b_major=1, ldc=D,
                            epilogue=L.EPI_STORE if r == 0 else L.EPI_ACCUM, alpha_dev=gscale)
         for o in outs:
             j, g0, hq = o["job"], o["g0"], o["hq"]
@@ -882,7 +933,7 @@ class HSTU(nn.Module):
                    ctx["tok_index"].data_ptr(), B, LP, P, ctx["scale"].data_ptr(), gscale.data_ptr(),
                    dthat.data_ptr(), st)
             L.call("b200rec_reduce_sum", o["dsc"].data_ptr(), T * P, 1.0, dscale_sum.data_ptr(), 1, st)
-            o["G"] = None
+            o["G"] = o["qs"] = None
         if isinstance(self.logit_scale, nn.Parameter):
             grads[self.logit_scale] = (dscale_sum * gscale).reshape(self.logit_scale.shape)
         # ---- through the L2 normalisation of the heads, the ResBlocks, into dy

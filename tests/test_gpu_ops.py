@@ -625,3 +625,46 @@ def test_gemm_grouped_fp32_falls_back_to_single_problems():
     L.gemm_grouped(probs, M, N, K, lda=K, ldb=K, ldc=N)
     for A, B, Cm in probs:
         assert torch.allclose(Cm, A @ B.t(), rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------ row-sharded table kernels
+@pytest.mark.parametrize("W,N,D,n", [(1, 1000, 64, 5000), (4, 10001, 128, 20000), (8, 4500, 1024, 3000)])
+def test_gather_rows_sharded_over_pointer_table(W, N, D, n):
+    """out[i] = shard[id % W][id // W]: the pointer table holds W local tensors here (the multi-GPU step fills it with
+    CUDA-IPC mappings of the peers' shards; the kernel cannot tell the difference)."""
+    from b200rec import parallel
+    table = rnd(N, D, seed=3)
+    shards = [table[r::W].contiguous() for r in range(W)]
+    ptrs = torch.tensor([s.data_ptr() for s in shards], dtype=torch.int64, device=dev())
+    ids = torch.randint(0, N, (n,), generator=torch.Generator().manual_seed(4)).to(dev())
+    ids[::17] = -1                                                   # fillers -> zero rows
+    out = torch.full((n, D), 3.0, device=dev())
+    parallel.cuda_gather_rows_sharded(ptrs, W, D, ids, out)
+    want = table[ids.clamp_min(0)]
+    want[ids < 0] = 0
+    assert torch.equal(out, want)
+
+
+@pytest.mark.parametrize("W,N,D,n_per", [(1, 300, 64, 2000), (2, 1001, 128, 5000), (8, 400, 256, 1500)])
+def test_scatter_add_sorted_peer_matches_index_add_and_is_deterministic(W, N, D, n_per):
+    """Owner-side reduction over W gradient-row buffers: for every rank, the rows of the ids it owns (id % W == rank,
+    id > 0) summed over ALL buffers in (rank, index) order; equals index_add up to fp32 reassociation, bit-reproducible."""
+    from b200rec import parallel
+    g = torch.Generator().manual_seed(11)
+    bufs = [(torch.randn(n_per, D, generator=g)).to(dev()) for _ in range(W)]
+    ids_all = torch.randint(0, N, (W, n_per), generator=g).to(dev())
+    ids_all[:, ::13] = 0                                             # padding id: no gradient
+    ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=dev())
+    dense = torch.zeros(N, D, dtype=torch.float64, device=dev())
+    dense.index_add_(0, ids_all.reshape(-1), torch.cat(bufs).double())
+    dense[0] = 0
+    for rank in range(W):
+        n_local = (N - rank + W - 1) // W
+        uid, rows, nu = parallel.cuda_segment_reduce_peer(ids_all, n_per, W, rank, ptrs, D, n_local)
+        uid2, rows2, nu2 = parallel.cuda_segment_reduce_peer(ids_all, n_per, W, rank, ptrs, D, n_local)
+        k = int(nu.item())
+        assert k == int(nu2.item()) and torch.equal(uid[:k], uid2[:k]) and torch.equal(rows[:k], rows2[:k])
+        owned = torch.unique(ids_all[(ids_all > 0) & (ids_all % W == rank)])
+        assert torch.equal(uid[:k] * W + rank, owned)                # LOCAL row indices, ascending
+        want = dense[owned].float()
+        assert (rows[:k] - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item())
