@@ -180,6 +180,12 @@ typedef struct {
   int fold_hp;
   const uint8_t* fold_head_on; const int32_t* fold_head_cat; const uint32_t* fold_item_tags;
   int64_t fold_id_offset; int64_t fold_id_stride;
+  /* FOLD_HEADS, streamed variant (fold_thr != NULL): nothing of size users x items is written.  A folded score that is
+   * finite and >= fold_thr[user] is appended to the user's candidate list instead: slot = atomicAdd(fold_cnt[user]),
+   * fold_keys[user * fold_cap + slot] = (~order_key(score) << 32) | (local item index << 5) | arg-max head, so that an
+   * ascending sort of the keys IS the tie rule (value desc, item id asc, head asc); N < 2^27 rows per shard.  Slots >=
+   * fold_cap are dropped; fold_cnt still counts them so the caller can detect the overflow.  C / C2 unused. */
+  const float* fold_thr; uint32_t* fold_cnt; uint64_t* fold_keys; int fold_cap;
   /* STORE / ACCUM: optional per-row factor, C[m,:] (+)= alpha * row_scale[m] * acc[m,:] (fp32[M]; NULL = 1). */
   const float* row_scale;
   /* B200REC_EPI_NCE_EXP only (fused sampled-softmax forward, hstu.py:600-619 + cross_entropy): see below. */
@@ -324,6 +330,14 @@ int b200rec_score_mask_topk(const float* scores, int64_t ld_scores, int B, int H
                             const int64_t* hist_items, int split_mode, int64_t id_offset,
                             int64_t id_stride, int64_t* topk_idx, float* topk_val, int32_t* topk_head,
                             void* workspace, size_t workspace_bytes, void* stream);
+/* Last stage of the STREAMED eval (collector.py:191-275 without any users x items tensor): per user, the candidates the
+ * FOLD_HEADS epilogue appended (keys / cnt, capacity cap) minus history items and global id 0, ordered by
+ * (value desc, item id asc); writes the first K.  overflow[0] is set to 1 if any user's count exceeded cap or fewer
+ * than K candidates survived (the caller then re-runs that batch through the materialising path). */
+int b200rec_topk_from_candidates(const uint64_t* keys, const uint32_t* cnt, int cap, int B, int K,
+                                 const int32_t* hist_off, const int64_t* hist_items, int64_t id_offset,
+                                 int64_t id_stride, int64_t* topk_idx, float* topk_val, int32_t* topk_head,
+                                 int32_t* overflow, void* stream);
 /* Second half of b200rec_score_mask_topk for scores already folded over heads (B200REC_EPI_FOLD_HEADS):
  * history suppression on fval, then per-user radix select + sort.  Same tie rule and id mapping.
  * fval / fhead rows have leading dimension ld >= N (a multiple of 4 keeps the 16-byte loads). */

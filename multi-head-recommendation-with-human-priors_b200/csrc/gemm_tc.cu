@@ -304,7 +304,25 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
             if ((sub % subs_per_user) == 0) {
               const int row_first = sub * 8 + g * grp;
               const int64_t user = (int64_t)(mrow0 + row_first) / hp;
-              if (mrow0 + row_first < ep.M && ncol < ep.N) {
+              if (ep.fold_thr != nullptr) {
+                // streamed eval: only scores that can still enter the user's top-K leave the SM
+                if (mrow0 + row_first < ep.M && ncol < ep.N) {
+                  const float thr = __ldg(ep.fold_thr + user);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    if (ncol + i < ep.N && best[i] >= thr && best[i] > -INFINITY) {
+                      const uint32_t slot = atomicAdd(ep.fold_cnt + user, 1u);
+                      if (slot < (uint32_t)ep.fold_cap) {
+                        uint32_t u = __float_as_uint(best[i]);
+                        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);          // ascending-order-preserving key
+                        ep.fold_keys[user * ep.fold_cap + slot] =
+                            ((unsigned long long)(~u) << 32) |
+                            (unsigned long long)(((uint32_t)(ncol + i) << 5) | (uint32_t)bh[i]);   // item < 2^27, head < 32
+                      }
+                    }
+                  }
+                }
+              } else if (mrow0 + row_first < ep.M && ncol < ep.N) {
                 float* fv = (float*)ep.C + user * ep.ldc + ncol;
                 uint8_t* fh = (uint8_t*)ep.C2 + user * ep.ldc2 + ncol;
                 if (ncol + 4 <= ep.N) {

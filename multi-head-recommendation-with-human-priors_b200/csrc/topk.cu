@@ -281,6 +281,77 @@ int b200rec_topk_select(float* fval, const uint8_t* fhead, int B, int64_t N, int
   return 0;
 }
 
+// ---- streamed eval: final order of the candidates appended by the scoring GEMM's epilogue ----------------------
+// key = (~order_key(score) << 32) | (local item << 5) | head: ascending key order = value desc, item asc, head asc
+__global__ void __launch_bounds__(SEL_THREADS)
+topk_from_candidates_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ cnt, int cap,
+                            int n_pad, int K, const int32_t* __restrict__ hist_off,
+                            const int64_t* __restrict__ hist_items, int64_t id_offset, int64_t id_stride,
+                            int64_t* __restrict__ topk_idx, float* __restrict__ topk_val,
+                            int32_t* __restrict__ topk_head, int32_t* __restrict__ overflow) {
+  extern __shared__ unsigned long long sc[];             // [n_pad]
+  __shared__ int s_valid;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const uint32_t n_all = cnt[b];
+  const int n = (int)min(n_all, (uint32_t)cap);
+  if (tid == 0) {
+    s_valid = 0;
+    if (n_all > (uint32_t)cap) overflow[0] = 1;
+  }
+  __syncthreads();
+  const unsigned long long* kb = keys + (int64_t)b * cap;
+  const int h0 = hist_off ? hist_off[b] : 0, h1 = hist_off ? hist_off[b + 1] : 0;
+  int mine = 0;
+  for (int i = tid; i < n_pad; i += SEL_THREADS) {
+    unsigned long long k = 0xffffffffffffffffull;
+    if (i < n) {
+      const unsigned long long c = kb[i];
+      const int64_t gid = (int64_t)((uint32_t)(c & 0xffffffffull) >> 5) * id_stride + id_offset;
+      bool drop = gid == 0;                                // trainer.py:724
+      for (int h = h0; h < h1 && !drop; ++h) drop = hist_items[h] == gid;   // trainer.py:725-726
+      if (!drop) { k = c; ++mine; }
+    }
+    sc[i] = k;
+  }
+  if (mine) atomicAdd(&s_valid, mine);
+  __syncthreads();
+  sel_bitonic(sc, n_pad);
+  if (tid == 0 && s_valid < K) overflow[0] = 1;
+  for (int i = tid; i < K; i += SEL_THREADS) {
+    const unsigned long long c = i < n_pad ? sc[i] : 0xffffffffffffffffull;
+    const bool ok = c != 0xffffffffffffffffull;
+    const uint32_t low = (uint32_t)(c & 0xffffffffull);
+    uint32_t u = ~(uint32_t)(c >> 32);
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;        // inverse of order_key
+    topk_idx[(int64_t)b * K + i] = ok ? (int64_t)(low >> 5) * id_stride + id_offset : 0;
+    topk_val[(int64_t)b * K + i] = ok ? __uint_as_float(u) : -INFINITY;
+    topk_head[(int64_t)b * K + i] = ok ? (int)(low & 31u) : 0;
+  }
+}
+
+int b200rec_topk_from_candidates(const uint64_t* keys, const uint32_t* cnt, int cap, int B, int K,
+                                 const int32_t* hist_off, const int64_t* hist_items, int64_t id_offset,
+                                 int64_t id_stride, int64_t* topk_idx, float* topk_val, int32_t* topk_head,
+                                 int32_t* overflow, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CHECK_ARG(K >= 1 && K <= cap && cap <= 16384 && id_stride >= 1 && id_offset >= 0,
+                 "topk_from_candidates: K=%d / cap=%d (<= 16384) / id mapping", K, cap);
+  if (B == 0) return 0;
+  int n_pad = 1;
+  while (n_pad < cap) n_pad <<= 1;
+  const size_t smem = (size_t)n_pad * 8;
+  static bool once = false;
+  if (!once) {
+    B200_CUDA_OK(cudaFuncSetAttribute(topk_from_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+    once = true;
+  }
+  topk_from_candidates_kernel<<<B, SEL_THREADS, smem, st>>>((const unsigned long long*)keys, cnt, cap, n_pad, K, hist_off,
+                                                             hist_items, id_offset, id_stride, topk_idx, topk_val,
+                                                             topk_head, overflow);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
 // ---- hit matrix (collector.py:300-316) -----------------------------------------------------------
 __global__ void hit_matrix_kernel(const int64_t* __restrict__ topk_idx, const int64_t* __restrict__ positive_i, int B,
                                   int K, int Pe, int p, int32_t* __restrict__ out) {

@@ -189,7 +189,8 @@ class HSTU(nn.Module):
         self.sparse_embedding_grad = bool(config.get("sparse_embedding_grad", False))
         self.use_tc_attention = bool(config.get("tc_attention", True))
         self.use_fused_eval = bool(config.get("fused_eval", True))
-        self.use_fused_nce = bool(config.get("fused_nce", True))     # bf16 mode: softmax numerators from the GEMM epilogue
+        self.use_fused_nce = bool(config.get("fused_nce", True))
+        self.use_streamed_eval = bool(config.get("streamed_eval", True))   # top-K candidates filtered in the scoring GEMM     # bf16 mode: softmax numerators from the GEMM epilogue
         self.share_negatives = bool(config.get("share_negatives", True))   # all-gather negatives across ranks
         self.dropout_seed = int(config.get("seed", 2020)) & 0xffffffff
         self._rng_step = None      # device counter feeding the Philox dropout stream
@@ -1269,10 +1270,8 @@ class HSTU(nn.Module):
             if head_cat is not None:
                 cat = torch.full((hp,), -1, dtype=torch.int32, device=dev)
                 cat[:H] = head_cat
-            if user_chunk is None:
-                user_chunk = max(1, min(Ball, int((8 << 30) // max(1, N * 5))))
-            for b0 in range(0, Ball, user_chunk):
-                b1 = min(Ball, b0 + user_chunk)
+            def materialised(b0, b1):
+                """fold-heads epilogue -> (max, arg-max head) per (user, item) in HBM -> two-read select."""
                 nb = b1 - b0
                 fval = torch.empty((nb, ldn), dtype=torch.float32, device=dev)
                 fhead = torch.empty((nb, ldn), dtype=torch.uint8, device=dev)
@@ -1282,6 +1281,41 @@ class HSTU(nn.Module):
                 ho = hist_off[b0:b1 + 1].contiguous() if hist_off is not None else None
                 L.call("b200rec_topk_select", fval.data_ptr(), fhead.data_ptr(), nb, N, ldn, K, L.ptr(ho), L.ptr(hist_items),
                        rank, Wd, idx[b0:b1].data_ptr(), val[b0:b1].data_ptr(), hsrc[b0:b1].data_ptr(), L.stream())
+
+            # STREAMED path: the table is read once per user batch and nothing of size users x items
+            # reaches HBM.  (1) the first N0 rows go through the materialising path: the K-th best masked score there is
+            # a lower bound thr[u] of the K-th best overall; (2) one scoring GEMM over ALL rows whose epilogue keeps only
+            # folded scores >= thr[u] (~K * N / N0 per user) in per-user candidate lists; (3) a per-user sort of the
+            # candidates (history / id 0 dropped) gives the list.  A rare overflow (counts beyond the capacity: a
+            # catalogue whose first rows are unrepresentative) re-runs the batch through the materialising path.
+            N0 = min(N, max(32768, ((N + 15) // 16 + 255) // 256 * 256))
+            cap = 8192
+            streamed = self.use_streamed_eval and N >= 4 * N0 and K <= N0 and N < (1 << 27) and user_chunk is None
+            if streamed:
+                ldn0 = (N0 + 3) // 4 * 4
+                fval = torch.empty((Ball, ldn0), dtype=torch.float32, device=dev)
+                fhead = torch.empty((Ball, ldn0), dtype=torch.uint8, device=dev)
+                onf = on.reshape(-1).contiguous()
+                L.gemm(Up.reshape(Ball * hp, D), table, fval, Ball * hp, N0, D, lda=D, ldb=D, ldc=ldn0,
+                       epilogue=L.EPI_FOLD_HEADS, C2=fhead, ldc2=ldn0, fold=(hp, onf, cat, bits, rank, Wd))
+                L.call("b200rec_topk_select", fval.data_ptr(), fhead.data_ptr(), Ball, N0, ldn0, K, L.ptr(hist_off),
+                       L.ptr(hist_items), rank, Wd, idx.data_ptr(), val.data_ptr(), hsrc.data_ptr(), L.stream())
+                thr = val[:, K - 1].contiguous()
+                cnt = torch.zeros(Ball, dtype=torch.int32, device=dev)
+                keys = torch.empty((Ball, cap), dtype=torch.int64, device=dev)
+                ovf = torch.zeros(1, dtype=torch.int32, device=dev)
+                L.gemm(Up.reshape(Ball * hp, D), table, fval, Ball * hp, N, D, lda=D, ldb=D, ldc=ldn0,
+                       epilogue=L.EPI_FOLD_HEADS, fold=(hp, onf, cat, bits, rank, Wd, thr, cnt, keys, cap))
+                L.call("b200rec_topk_from_candidates", keys.data_ptr(), cnt.data_ptr(), cap, Ball, K, L.ptr(hist_off),
+                       L.ptr(hist_items), rank, Wd, idx.data_ptr(), val.data_ptr(), hsrc.data_ptr(), ovf.data_ptr(),
+                       L.stream())
+                if int(ovf.item()) != 0:                # also the point where eval hands results to the host anyway
+                    streamed = False
+            if not streamed:
+                if user_chunk is None:
+                    user_chunk = max(1, min(Ball, int((8 << 30) // max(1, N * 5))))
+                for b0 in range(0, Ball, user_chunk):
+                    materialised(b0, min(Ball, b0 + user_chunk))
         else:
             if user_chunk is None:
                 user_chunk = max(1, min(Ball, int((8 << 30) // max(1, H * N * 4))))

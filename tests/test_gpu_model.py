@@ -490,3 +490,36 @@ def test_lazy_table_history_ring_wraps():
             states.append({k: v.clone() for k, v in model.state_dict().items()})
         for k in states[0]:
             assert torch.equal(states[0][k], states[1][k]), (graphed, k)
+
+
+@pytest.mark.parametrize("H,cats", [(12, True), (1, False), (7, True)])
+def test_streamed_eval_equals_materialised(H, cats):
+    """Streamed top-K (candidates filtered in the scoring GEMM's epilogue, nothing of size users x items in HBM)
+    returns exactly the list of the materialising path: same ids, same order, same values, same arg-max heads —
+    with prior masks, prior_given_at_test-style head switches, history suppression and id 0."""
+    from b200rec import _lib as L
+    N, D, B, K = 150000, 64, 37, 200
+    preset = "B" if H == 12 else ("A" if H == 1 else "D")
+    cfg = synth.make_config(preset, n_layers=1, n_heads=1, item_embedding_size=D, hstu_embedding_size=D,
+                            MAX_ITEM_LIST_LENGTH=12, item_num=N, hidden_dropout_prob=0.0)
+    dl = synth.make_dataload(cfg)
+    torch.manual_seed(5)
+    model = HSTU(cfg, dl, compute_dtype=torch.bfloat16).to(dev()).eval()
+    assert model.medusa_num_heads == H
+    item_tags = synth.make_item_tags(cfg, torch.Generator().manual_seed(4242))
+    ev = synth.make_eval_batch(cfg, seed=9, batch_size=B, item_tags=item_tags)
+    C = cfg["eval_num_cats"]
+    tags = item_tags.t().contiguous().to(dev()) if cats else torch.ones(C, N, dtype=torch.bool, device=dev())
+    feat = model.compute_item_all()
+    hu, hi = ev["history_index"]
+    args = (ev["item_seq"].to(dev()), feat, tags, ev["target_tags"].to(dev()))
+    kw = dict(history_index=(hu.to(dev()), hi.to(dev())), K=K)
+    model.use_streamed_eval = True
+    n0 = L.launches
+    i1, v1, h1 = model.predict_topk(*args, **kw)
+    used_streamed = L.launches - n0
+    model.use_streamed_eval = False
+    n0 = L.launches
+    i2, v2, h2 = model.predict_topk(*args, **kw)
+    assert used_streamed != L.launches - n0                       # the streamed path really ran (3 stages vs 1)
+    assert torch.equal(i1, i2) and torch.equal(v1, v2) and torch.equal(h1, h2)
