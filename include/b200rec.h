@@ -186,6 +186,10 @@ typedef struct {
    * ascending sort of the keys IS the tie rule (value desc, item id asc, head asc); N < 2^27 rows per shard.  Slots >=
    * fold_cap are dropped; fold_cnt still counts them so the caller can detect the overflow.  C / C2 unused. */
   const float* fold_thr; uint32_t* fold_cnt; uint64_t* fold_keys; int fold_cap;
+  /* GT_BITS: optional rank-1 addend, bit = acc + gt_row[m] * gt_col[n] > alpha (fp32[M], fp32[N]; both or neither).
+   * Used for the PRUNED false-negative filter: a K = 64 prefix product plus the product of the tail norms is an upper
+   * bound of the full cosine (Cauchy-Schwarz), b200rec_gt_bits_verify then settles the few surviving pairs exactly. */
+  const float* gt_row; const float* gt_col;
   /* STORE / ACCUM: optional per-row factor, C[m,:] (+)= alpha * row_scale[m] * acc[m,:] (fp32[M]; NULL = 1). */
   const float* row_scale;
   /* B200REC_EPI_NCE_EXP only (fused sampled-softmax forward, hstu.py:600-619 + cross_entropy): see below. */
@@ -202,6 +206,14 @@ int b200rec_gemm(const b200rec_gemm_args* args, void* stream);
  * step (b200rec_nce_combine) turns the partials into per-offset log-sum-exp / loss / gradient scalars; the backward
  * GEMMs consume E directly: dq = row_scale * (E @ n_hat), dn = E^T @ (row_scale * q_hat). */
 int b200rec_gemm_nce_parts(int N);
+/* Pruned false-negative filter (hstu.py:613-614: fix_logits = target @ neg^T > nce_thres), exact result, ~16x fewer
+ * FLOPs than the full product:  tail_norm[r] = || x_hat[r, k0:] ||  (bf16 rows);  GT_BITS GEMM over the first k0
+ * columns with gt_row / gt_col = the tail norms marks every pair whose cosine CAN exceed the threshold;
+ * gt_bits_verify recomputes the full fp32 dot product of each marked pair, clears the bits that fail and sets
+ * row_any[m] = 1 for rows that keep a bit (zero row_any first). */
+int b200rec_tail_norm(const void* x_hat, int64_t n, int D, int k0, float* out, void* stream);
+int b200rec_gt_bits_verify(uint32_t* bits, int64_t M, int n_words, int N, const void* a_hat, const void* b_hat, int D,
+                           float thres, uint8_t* row_any, void* stream);
 /* n_groups independent problems args[0..n_groups).  Problems of identical shape / layout / dtypes with a
  * plain STORE or ACCUM epilogue (the per-head NCE GEMMs of hstu.py:697, the per-layer weight gradients)
  * run as ONE persistent tcgen05 launch (16 problems per launch), so that small problems share waves

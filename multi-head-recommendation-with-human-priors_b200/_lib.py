@@ -49,6 +49,7 @@ class GemmArgs(C.Structure):
         ("fold_head_on", C.c_void_p), ("fold_head_cat", C.c_void_p), ("fold_item_tags", C.c_void_p),
         ("fold_id_offset", C.c_int64), ("fold_id_stride", C.c_int64),
         ("fold_thr", C.c_void_p), ("fold_cnt", C.c_void_p), ("fold_keys", C.c_void_p), ("fold_cap", C.c_int),
+        ("gt_row", C.c_void_p), ("gt_col", C.c_void_p),
         ("row_scale", C.c_void_p),
         ("nce_mref", C.c_void_p), ("nce_thr", C.c_void_p), ("nce_stats", C.c_void_p), ("nce_logit_scale", C.c_void_p),
     ]
@@ -96,6 +97,8 @@ _SIGS = {
     "b200rec_nce_loss_fwd": (C.c_int, [_P, _L, _I, _P, _P, _P, _P, _L, _P, _I, _I, _P, _P, _I, _I, _I, C.c_uint32,
                                        _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
     "b200rec_gemm_nce_parts": (C.c_int, [_I]),
+    "b200rec_tail_norm": (C.c_int, [_P, _L, _I, _I, _P, _P]),
+    "b200rec_gt_bits_verify": (C.c_int, [_P, _L, _I, _I, _P, _P, _I, _F, _P, _P]),
     "b200rec_nce_pos_ref": (C.c_int, [_P, _L, _P, _I, _P, _P, _I, _I, _I, C.c_uint32, _P, _I, _I, _P, _P, _P, _P, _P]),
     "b200rec_nce_combine": (C.c_int, [_P, _I, _P, _L, _I, _P, _P, _P, _P, _P, _L, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P,
                                       _P, _P, _P, _P, _P, _L, _P]),
@@ -173,7 +176,7 @@ def call(name, *args):
 
 def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epilogue=EPI_STORE, alpha=1.0,
          alpha_dev=None, bias=None, resid=None, ldr=0, C2=None, ldc2=0, n_split=0, c_dtype=None, fold=None,
-         splitk_ws=None):
+         splitk_ws=None, gt=None):
     """C[M,N] = epi(A[M,K] @ B[N,K]^T).  A/B are tensors (or views) whose data_ptr is element (0,0)."""
     global launches
     a = GemmArgs()
@@ -195,6 +198,8 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epilogue=
         a.fold_id_offset, a.fold_id_stride = fold[4], fold[5]
         if len(fold) > 6:      # streamed variant: (thr f32[users], cnt u32[users], keys u64[users, cap], cap)
             a.fold_thr, a.fold_cnt, a.fold_keys, a.fold_cap = ptr(fold[6]), ptr(fold[7]), ptr(fold[8]), fold[9]
+    if gt is not None:     # GT_BITS upper-bound variant: (row vector fp32[M], column vector fp32[N])
+        a.gt_row, a.gt_col = gt[0].data_ptr(), gt[1].data_ptr()
     a.epilogue, a.alpha = epilogue, alpha
     a.alpha_dev = ptr(alpha_dev)
     a.bias, a.resid, a.ldr = ptr(bias), ptr(resid), ldr

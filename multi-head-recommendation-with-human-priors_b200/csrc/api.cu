@@ -109,6 +109,10 @@ int b200rec_gemm(const b200rec_gemm_args* a, void* stream) {
                 a->c2_split_stride % 4 == 0 && a->epilogue != B200REC_EPI_GT_BITS;
   }
   ep.row_scale = a->row_scale;
+  ep.gt_row = a->gt_row; ep.gt_col = a->gt_col;
+  B200_CHECK_ARG((a->gt_row == nullptr) == (a->gt_col == nullptr), "gemm: gt_row and gt_col go together");
+  B200_CHECK_ARG(a->gt_row == nullptr || (a->epilogue == B200REC_EPI_GT_BITS && a->in_dtype == B200REC_BF16),
+                 "gemm: gt_row / gt_col belong to the bf16 GT_BITS epilogue");
   ep.nce_mref = a->nce_mref; ep.nce_thr = a->nce_thr; ep.nce_stats = a->nce_stats;
   ep.nce_logit_scale = a->nce_logit_scale; ep.nce_parts = b200rec_gemm_nce_parts(a->N);
   if (a->epilogue == B200REC_EPI_NCE_EXP)

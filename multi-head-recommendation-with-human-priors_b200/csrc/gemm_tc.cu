@@ -233,9 +233,18 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
         }
         if (MODE == B200REC_EPI_GT_BITS) {
           uint32_t wbits = 0;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) wbits |= (v[i] > ep.alpha) ? (1u << i) : 0u;
           const int m = m0 + quarter * 32 + lane, nn = n0 + c * 32;
+          if (ep.gt_row != nullptr) {             // upper-bound variant: prefix product + product of the tail norms
+            const float ra = m < ep.M ? __ldg(ep.gt_row + m) : 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float cb = nn + i < ep.N ? __ldg(ep.gt_col + nn + i) : 0.f;
+              wbits |= (fmaf(ra, cb, v[i]) > ep.alpha) ? (1u << i) : 0u;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) wbits |= (v[i] > ep.alpha) ? (1u << i) : 0u;
+          }
           if (m < ep.M && nn < ep.N) {
             if (nn + 32 > ep.N) wbits &= (1u << (ep.N - nn)) - 1u;
             ((uint32_t*)ep.C)[(int64_t)m * ep.ldc + (nn >> 5)] = wbits;

@@ -924,3 +924,99 @@ extern "C" int b200rec_nce_combine(const float* stats, int n_parts, void* E, int
   B200_LAUNCH_OK();
   return 0;
 }
+
+
+// ---- pruned false-negative filter: tail norms + exact verification of the pairs the bound could not exclude ----
+__global__ void __launch_bounds__(256) tail_norm_kernel(const bf16* __restrict__ x, int64_t n, int D4, int k04,
+                                                        float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n) return;
+  float ss = 0.f;
+  for (int c = k04 + lane; c < D4; c += 32) {
+    float v[4];
+    load4<bf16>(x + (r * D4 + c) * 4, v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ss = fmaf(v[k], v[k], ss);
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) out[r] = sqrtf(ss) * (1.f + 1e-6f);     // never below the true norm of the rounded row
+}
+
+extern "C" int b200rec_tail_norm(const void* x_hat, int64_t n, int D, int k0, float* out, void* stream) {
+  B200_CHECK_ARG(D % 4 == 0 && k0 % 4 == 0 && k0 >= 0 && k0 <= D, "tail_norm: bad D / k0");
+  if (n == 0) return 0;
+  tail_norm_kernel<<<ceil_div_i(n, 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)x_hat, n, D / 4, k0 / 4, out);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+template <int MAXV>
+__global__ void __launch_bounds__(256) gt_bits_verify_kernel(uint32_t* __restrict__ bits, int64_t M, int n_words, int N,
+                                                             const bf16* __restrict__ a, const bf16* __restrict__ b,
+                                                             int D4, float thres, uint8_t* __restrict__ row_any) {
+  const int lane = threadIdx.x & 31;
+  const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  // cheap exit: most rows carry no candidate at all
+  uint32_t anyw = 0;
+  for (int w = lane; w < n_words; w += 32) anyw |= bits[m * n_words + w];
+  if (__ballot_sync(0xffffffffu, anyw != 0) == 0) return;
+  float av[MAXV][4];
+#pragma unroll
+  for (int u = 0; u < MAXV; ++u) {
+    const int c = lane + 32 * u;
+    if (c < D4) load4<bf16>(a + (m * D4 + c) * 4, av[u]);
+  }
+  bool keep_any = false;
+  for (int w0 = 0; w0 < n_words; w0 += 32) {
+    const int w = w0 + lane;
+    uint32_t word = w < n_words ? bits[m * n_words + w] : 0u;
+    uint32_t pending = __ballot_sync(0xffffffffu, word != 0);
+    while (pending) {
+      const int src = __ffs(pending) - 1;
+      pending &= pending - 1;
+      uint32_t cur = __shfl_sync(0xffffffffu, word, src);
+      uint32_t kept = cur;
+      while (cur) {
+        const int bit = __ffs(cur) - 1;
+        cur &= cur - 1;
+        const int64_t j = (int64_t)(w0 + src) * 32 + bit;
+        float acc = 0.f;
+        if (j < N) {
+#pragma unroll
+          for (int u = 0; u < MAXV; ++u) {
+            const int c = lane + 32 * u;
+            if (c < D4) {
+              float bv[4];
+              load4<bf16>(b + (j * D4 + c) * 4, bv);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) acc = fmaf(av[u][k], bv[k], acc);
+            }
+          }
+        }
+        acc = warp_sum(acc);
+        if (!(j < N && acc > thres)) kept &= ~(1u << bit);
+      }
+      if (lane == src) word = kept;
+    }
+    if (w < n_words) bits[m * n_words + w] = word;
+    keep_any |= __ballot_sync(0xffffffffu, word != 0) != 0;
+  }
+  if (lane == 0 && keep_any) row_any[m] = 1;
+}
+
+extern "C" int b200rec_gt_bits_verify(uint32_t* bits, int64_t M, int n_words, int N, const void* a_hat,
+                                      const void* b_hat, int D, float thres, uint8_t* row_any, void* stream) {
+  B200_CHECK_ARG(D % 4 == 0 && D <= 2048 && n_words * 32 >= N, "gt_bits_verify: bad D / n_words");
+  if (M == 0) return 0;
+  const int blocks = ceil_div_i(M, 8);
+  if (D <= 512)
+    gt_bits_verify_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(bits, M, n_words, N, (const bf16*)a_hat,
+                                                                       (const bf16*)b_hat, D / 4, thres, row_any);
+  else
+    gt_bits_verify_kernel<16><<<blocks, 256, 0, (cudaStream_t)stream>>>(bits, M, n_words, N, (const bf16*)a_hat,
+                                                                        (const bf16*)b_hat, D / 4, thres, row_any);
+  B200_LAUNCH_OK();
+  return 0;
+}

@@ -190,7 +190,8 @@ class HSTU(nn.Module):
         self.use_tc_attention = bool(config.get("tc_attention", True))
         self.use_fused_eval = bool(config.get("fused_eval", True))
         self.use_fused_nce = bool(config.get("fused_nce", True))
-        self.use_streamed_eval = bool(config.get("streamed_eval", True))   # top-K candidates filtered in the scoring GEMM     # bf16 mode: softmax numerators from the GEMM epilogue
+        self.use_streamed_eval = bool(config.get("streamed_eval", True))
+        self.use_pruned_filter = bool(config.get("pruned_filter", True))   # false-negative filter via an upper bound   # top-K candidates filtered in the scoring GEMM     # bf16 mode: softmax numerators from the GEMM epilogue
         self.share_negatives = bool(config.get("share_negatives", True))   # all-gather negatives across ranks
         self.dropout_seed = int(config.get("seed", 2020)) & 0xffffffff
         self._rng_step = None      # device counter feeding the Philox dropout stream
@@ -725,6 +726,10 @@ class HSTU(nn.Module):
         ld_neg = n_words * 32
         used_sets = sorted({j.nset for j in self._jobs})
         nhat, ninv, bits, row_any = {}, {}, {}, {}
+        prune_k0 = 64 if (act == torch.bfloat16 and self.use_pruned_filter and D >= 256 and D <= 2048) else 0
+        if prune_k0:
+            t_tail = torch.empty(B * LP, dtype=torch.float32, device=dev)
+            L.call("b200rec_tail_norm", that.data_ptr(), B * LP, D, prune_k0, t_tail.data_ptr(), st)
         for s in used_sets:
             nh_ = torch.empty((n_neg, D), dtype=act, device=dev)
             ni_ = torch.empty(n_neg, dtype=torch.float32, device=dev)
@@ -733,8 +738,18 @@ class HSTU(nn.Module):
             bt = torch.empty((B * LP, n_words), dtype=torch.int32, device=dev)
             # false-negative filter bits: that @ nhat^T > nce_thres   (hstu.py:613-614)
             ra = torch.zeros(B * LP + P + 1, dtype=torch.uint8, device=dev)
-            L.gemm(that, nh_, bt, B * LP, n_neg, D, lda=D, ldb=D, ldc=n_words, epilogue=L.EPI_GT_BITS,
-                   alpha=float(self.nce_thres), C2=ra)
+            if prune_k0:
+                # exact, ~16x fewer FLOPs: cos <= <prefix of k0 dims> + |tail_t| |tail_n| (Cauchy-Schwarz) marks the pairs
+                # that CAN pass; the full dot product is recomputed only for those (duplicates of a target)
+                tn_ = torch.empty(n_neg, dtype=torch.float32, device=dev)
+                L.call("b200rec_tail_norm", nh_.data_ptr(), n_neg, D, prune_k0, tn_.data_ptr(), st)
+                L.gemm(that, nh_, bt, B * LP, n_neg, prune_k0, lda=D, ldb=D, ldc=n_words, epilogue=L.EPI_GT_BITS,
+                       alpha=float(self.nce_thres) - 1e-5, gt=(t_tail, tn_))
+                L.call("b200rec_gt_bits_verify", bt.data_ptr(), B * LP, n_words, n_neg, that.data_ptr(), nh_.data_ptr(), D,
+                       float(self.nce_thres), ra.data_ptr(), st)
+            else:
+                L.gemm(that, nh_, bt, B * LP, n_neg, D, lda=D, ldb=D, ldc=n_words, epilogue=L.EPI_GT_BITS,
+                       alpha=float(self.nce_thres), C2=ra)
             nhat[s], ninv[s], bits[s], row_any[s] = nh_, ni_, bt, ra
         # ---- per-offset token counts -> loss coefficients (hstu.py:704-712, 846-852)
         lam = self.horizon_discount.to(torch.float32)
