@@ -186,6 +186,11 @@ typedef struct {
    * ascending sort of the keys IS the tie rule (value desc, item id asc, head asc); N < 2^27 rows per shard.  Slots >=
    * fold_cap are dropped; fold_cnt still counts them so the caller can detect the overflow.  C / C2 unused. */
   const float* fold_thr; uint32_t* fold_cnt; uint64_t* fold_keys; int fold_cap;
+  /* streamed variant only: fold_groups = G > 1 lets a user own G groups of fold_hp heads (rows ordered (user, group,
+   * head); head index = group * fold_hp + h <= 31), so H = 12 runs as 3 x 4 without padding to 16.  Every group appends
+   * to the SAME user's list: an item may then appear once per group, b200rec_topk_from_candidates(dedupe = 1) keeps the
+   * best entry (value desc, head asc). */
+  int fold_groups;
   /* GT_BITS: optional rank-1 addend, bit = acc + gt_row[m] * gt_col[n] > alpha (fp32[M], fp32[N]; both or neither).
    * Used for the PRUNED false-negative filter: a K = 64 prefix product plus the product of the tail norms is an upper
    * bound of the full cosine (Cauchy-Schwarz), b200rec_gt_bits_verify then settles the few surviving pairs exactly. */
@@ -346,7 +351,7 @@ int b200rec_score_mask_topk(const float* scores, int64_t ld_scores, int B, int H
  * FOLD_HEADS epilogue appended (keys / cnt, capacity cap) minus history items and global id 0, ordered by
  * (value desc, item id asc); writes the first K.  overflow[0] is set to 1 if any user's count exceeded cap or fewer
  * than K candidates survived (the caller then re-runs that batch through the materialising path). */
-int b200rec_topk_from_candidates(const uint64_t* keys, const uint32_t* cnt, int cap, int B, int K,
+int b200rec_topk_from_candidates(const uint64_t* keys, const uint32_t* cnt, int cap, int B, int K, int dedupe,
                                  const int32_t* hist_off, const int64_t* hist_items, int64_t id_offset,
                                  int64_t id_stride, int64_t* topk_idx, float* topk_val, int32_t* topk_head,
                                  int32_t* overflow, void* stream);

@@ -49,6 +49,7 @@ class GemmArgs(C.Structure):
         ("fold_head_on", C.c_void_p), ("fold_head_cat", C.c_void_p), ("fold_item_tags", C.c_void_p),
         ("fold_id_offset", C.c_int64), ("fold_id_stride", C.c_int64),
         ("fold_thr", C.c_void_p), ("fold_cnt", C.c_void_p), ("fold_keys", C.c_void_p), ("fold_cap", C.c_int),
+        ("fold_groups", C.c_int),
         ("gt_row", C.c_void_p), ("gt_col", C.c_void_p),
         ("row_scale", C.c_void_p),
         ("nce_mref", C.c_void_p), ("nce_thr", C.c_void_p), ("nce_stats", C.c_void_p), ("nce_logit_scale", C.c_void_p),
@@ -115,7 +116,7 @@ _SIGS = {
     "b200rec_build_train_batch": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _L, _I, _I, _P, _P, _I, _F, _P, _I,
                                             C.c_uint64, C.c_uint64, _P, _P, _P, _P, _P]),
     "b200rec_build_eval_batch": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P]),
-    "b200rec_topk_from_candidates": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _L, _L, _P, _P, _P, _P, _P]),
+    "b200rec_topk_from_candidates": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _L, _L, _P, _P, _P, _P, _P]),
     "b200rec_topk_select": (C.c_int, [_P, _P, _I, _L, _L, _I, _P, _P, _L, _L, _P, _P, _P, _P]),
     "b200rec_apply_score_masks": (C.c_int, [_P, _L, _I, _I, _L, _P, _P, _P, _P]),
     "b200rec_hit_matrix": (C.c_int, [_P, _P, _I, _I, _I, _P, _I, _P, _P]),
@@ -198,6 +199,7 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epilogue=
         a.fold_id_offset, a.fold_id_stride = fold[4], fold[5]
         if len(fold) > 6:      # streamed variant: (thr f32[users], cnt u32[users], keys u64[users, cap], cap)
             a.fold_thr, a.fold_cnt, a.fold_keys, a.fold_cap = ptr(fold[6]), ptr(fold[7]), ptr(fold[8]), fold[9]
+            a.fold_groups = fold[10] if len(fold) > 10 else 1
     if gt is not None:     # GT_BITS upper-bound variant: (row vector fp32[M], column vector fp32[N])
         a.gt_row, a.gt_col = gt[0].data_ptr(), gt[1].data_ptr()
     a.epilogue, a.alpha = epilogue, alpha

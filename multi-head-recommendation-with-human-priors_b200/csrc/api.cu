@@ -121,12 +121,15 @@ int b200rec_gemm(const b200rec_gemm_args* a, void* stream) {
   ep.fold_hp = a->fold_hp; ep.fold_head_on = a->fold_head_on; ep.fold_head_cat = a->fold_head_cat;
   ep.fold_item_tags = a->fold_item_tags; ep.fold_id_offset = a->fold_id_offset; ep.fold_id_stride = a->fold_id_stride;
   ep.fold_thr = a->fold_thr; ep.fold_cnt = a->fold_cnt; ep.fold_keys = (unsigned long long*)a->fold_keys;
-  ep.fold_cap = a->fold_cap;
+  ep.fold_cap = a->fold_cap; ep.fold_groups = a->fold_groups < 1 ? 1 : a->fold_groups;
   if (a->epilogue == B200REC_EPI_FOLD_HEADS) {
     const int hp = a->fold_hp;
     B200_CHECK_ARG(a->in_dtype == B200REC_BF16, "gemm: FOLD_HEADS runs on the tcgen05 path only");
     B200_CHECK_ARG(hp >= 1 && hp <= 32 && (hp & (hp - 1)) == 0 && a->M % hp == 0, "gemm: bad fold_hp %d", hp);
     B200_CHECK_ARG(a->fold_head_on != nullptr && a->fold_id_stride >= 1, "gemm: FOLD_HEADS args");
+    B200_CHECK_ARG(a->fold_groups <= 1 || (a->fold_thr != nullptr && a->M % (hp * a->fold_groups) == 0 &&
+                                           hp * a->fold_groups <= 32),
+                   "gemm: fold_groups > 1 needs the streamed variant, M %% (hp * groups) == 0 and <= 32 heads");
     if (a->fold_thr != nullptr) {
       B200_CHECK_ARG(a->fold_cnt && a->fold_keys && a->fold_cap > 0 && a->N < (1 << 27),
                      "gemm: streamed FOLD_HEADS needs fold_cnt / fold_keys / fold_cap and N < 2^27 rows per shard");

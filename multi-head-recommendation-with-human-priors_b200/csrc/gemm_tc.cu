@@ -292,7 +292,9 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
                            : "r"(addr)
                            : "memory");
               const bool on = m < ep.M && __ldg(ep.fold_head_on + m) != 0;
-              const int cat = ep.fold_head_cat ? __ldg(ep.fold_head_cat + h) : -1;
+              // streamed variant with G groups of hp heads per user: row m = (user, group, h), head = group * hp + h
+              const int hfull = ep.fold_groups > 1 ? ((m / hp) % ep.fold_groups) * hp + h : h;
+              const int cat = ep.fold_head_cat ? __ldg(ep.fold_head_cat + hfull) : -1;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const bool keep = on && colok[i] && (cat < 0 || ((tg[i] >> cat) & 1u));
@@ -316,6 +318,9 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
               if (ep.fold_thr != nullptr) {
                 // streamed eval: only scores that can still enter the user's top-K leave the SM
                 if (mrow0 + row_first < ep.M && ncol < ep.N) {
+                  const int grp = ep.fold_groups > 1 ? (int)(user % ep.fold_groups) : 0;
+                  const int64_t vuser = user;
+                  const int64_t user = ep.fold_groups > 1 ? vuser / ep.fold_groups : vuser;
                   const float thr = __ldg(ep.fold_thr + user);
 #pragma unroll
                   for (int i = 0; i < 4; ++i) {
@@ -326,7 +331,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
                         u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);          // ascending-order-preserving key
                         ep.fold_keys[user * ep.fold_cap + slot] =
                             ((unsigned long long)(~u) << 32) |
-                            (unsigned long long)(((uint32_t)(ncol + i) << 5) | (uint32_t)bh[i]);   // item < 2^27, head < 32
+                            (unsigned long long)(((uint32_t)(ncol + i) << 5) | (uint32_t)(grp * hp + bh[i]));  // item < 2^27, head < 32
                       }
                     }
                   }

@@ -282,18 +282,23 @@ int b200rec_topk_select(float* fval, const uint8_t* fhead, int B, int64_t N, int
 }
 
 // ---- streamed eval: final order of the candidates appended by the scoring GEMM's epilogue ----------------------
-// key = (~order_key(score) << 32) | (local item << 5) | head: ascending key order = value desc, item asc, head asc
+// key = (~order_key(score) << 32) | (local item << 5) | head: ascending key order = value desc, item asc, head asc.
+// The sort covers the next power of two above THIS user's count, not the capacity.  dedupe (several head groups per
+// user): a first sort by (item, value desc, head) puts the copies of an item next to each other, all but the first of
+// each run are dropped, the second sort restores the final order.
 __global__ void __launch_bounds__(SEL_THREADS)
 topk_from_candidates_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ cnt, int cap,
-                            int n_pad, int K, const int32_t* __restrict__ hist_off,
+                            int K, int dedupe, const int32_t* __restrict__ hist_off,
                             const int64_t* __restrict__ hist_items, int64_t id_offset, int64_t id_stride,
                             int64_t* __restrict__ topk_idx, float* __restrict__ topk_val,
                             int32_t* __restrict__ topk_head, int32_t* __restrict__ overflow) {
-  extern __shared__ unsigned long long sc[];             // [n_pad]
+  extern __shared__ unsigned long long sc[];             // [next pow2 >= cap]
   __shared__ int s_valid;
   const int b = blockIdx.x, tid = threadIdx.x;
   const uint32_t n_all = cnt[b];
   const int n = (int)min(n_all, (uint32_t)cap);
+  int n_pad = 1;
+  while (n_pad < n || n_pad < K) n_pad <<= 1;
   if (tid == 0) {
     s_valid = 0;
     if (n_all > (uint32_t)cap) overflow[0] = 1;
@@ -301,7 +306,6 @@ topk_from_candidates_kernel(const unsigned long long* __restrict__ keys, const u
   __syncthreads();
   const unsigned long long* kb = keys + (int64_t)b * cap;
   const int h0 = hist_off ? hist_off[b] : 0, h1 = hist_off ? hist_off[b + 1] : 0;
-  int mine = 0;
   for (int i = tid; i < n_pad; i += SEL_THREADS) {
     unsigned long long k = 0xffffffffffffffffull;
     if (i < n) {
@@ -309,12 +313,44 @@ topk_from_candidates_kernel(const unsigned long long* __restrict__ keys, const u
       const int64_t gid = (int64_t)((uint32_t)(c & 0xffffffffull) >> 5) * id_stride + id_offset;
       bool drop = gid == 0;                                // trainer.py:724
       for (int h = h0; h < h1 && !drop; ++h) drop = hist_items[h] == gid;   // trainer.py:725-726
-      if (!drop) { k = c; ++mine; }
+      if (!drop) {
+        // dedupe: first order by (item, ~value key, head) = swap the two 27 / 32-bit fields
+        k = dedupe ? ((unsigned long long)((uint32_t)(c & 0xffffffffull) >> 5) << 37) | ((c >> 32) << 5) | (c & 31ull) : c;
+      }
     }
     sc[i] = k;
   }
-  if (mine) atomicAdd(&s_valid, mine);
   __syncthreads();
+  if (dedupe) {
+    sel_bitonic(sc, n_pad);
+    // keep the first (= best) entry of each item, convert back to the final key
+    unsigned long long mine[8];                            // n_pad <= 16384 = 16 x 1024: two rounds of 8 would be needed
+    for (int base = 0; base < n_pad; base += 8 * SEL_THREADS) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * SEL_THREADS + tid;
+        unsigned long long k = 0xffffffffffffffffull;
+        if (i < n_pad) {
+          const unsigned long long c = sc[i];
+          if (c != 0xffffffffffffffffull) {
+            const bool first = i == 0 || (sc[i - 1] >> 37) != (c >> 37);
+            if (first) k = (((c >> 5) & 0xffffffffull) << 32) | ((c >> 37) << 5) | (c & 31ull);
+          }
+        }
+        mine[u] = k;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * SEL_THREADS + tid;
+        if (i < n_pad) sc[i] = mine[u];
+      }
+      __syncthreads();
+    }
+  }
+  int cntv = 0;
+  for (int i = tid; i < n_pad; i += SEL_THREADS) cntv += sc[i] != 0xffffffffffffffffull;
+  if (cntv) atomicAdd(&s_valid, cntv);
   sel_bitonic(sc, n_pad);
   if (tid == 0 && s_valid < K) overflow[0] = 1;
   for (int i = tid; i < K; i += SEL_THREADS) {
@@ -329,7 +365,7 @@ topk_from_candidates_kernel(const unsigned long long* __restrict__ keys, const u
   }
 }
 
-int b200rec_topk_from_candidates(const uint64_t* keys, const uint32_t* cnt, int cap, int B, int K,
+int b200rec_topk_from_candidates(const uint64_t* keys, const uint32_t* cnt, int cap, int B, int K, int dedupe,
                                  const int32_t* hist_off, const int64_t* hist_items, int64_t id_offset,
                                  int64_t id_stride, int64_t* topk_idx, float* topk_val, int32_t* topk_head,
                                  int32_t* overflow, void* stream) {
@@ -345,7 +381,7 @@ int b200rec_topk_from_candidates(const uint64_t* keys, const uint32_t* cnt, int 
     B200_CUDA_OK(cudaFuncSetAttribute(topk_from_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
     once = true;
   }
-  topk_from_candidates_kernel<<<B, SEL_THREADS, smem, st>>>((const unsigned long long*)keys, cnt, cap, n_pad, K, hist_off,
+  topk_from_candidates_kernel<<<B, SEL_THREADS, smem, st>>>((const unsigned long long*)keys, cnt, cap, K, dedupe, hist_off,
                                                              hist_items, id_offset, id_stride, topk_idx, topk_val,
                                                              topk_head, overflow);
   B200_LAUNCH_OK();

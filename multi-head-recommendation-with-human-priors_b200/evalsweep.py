@@ -62,10 +62,19 @@ def topk_point(table, U, K, rank, W, tag_bits=None, head_cat=None, streamed=True
         cnt = torch.zeros(B, dtype=torch.int32, device=dev)
         keys = torch.empty((B, cap), dtype=torch.int64, device=dev)
         ovf = torch.zeros(1, dtype=torch.int32, device=dev)
-        L.gemm(Up.view(B * hp, D), table, fval, B * hp, N, D, lda=D, ldb=D, ldc=ldn0, epilogue=L.EPI_FOLD_HEADS,
-               fold=(hp, onf, cat, tag_bits, rank, W, thr, cnt, keys, cap))
-        L.call("b200rec_topk_from_candidates", keys.data_ptr(), cnt.data_ptr(), cap, B, K, None, None, rank, W,
-               idx.data_ptr(), val.data_ptr(), hsrc.data_ptr(), ovf.data_ptr(), L.stream())
+        hs, G = min(((g_ * h_, -h_, h_, g_) for h_ in (8, 4, 2, 1) for g_ in [(H + h_ - 1) // h_]))[2:]
+        Ug = torch.zeros((B, G * hs, D), dtype=U.dtype, device=dev)
+        Ug[:, :H] = U
+        ong = torch.zeros((B, G * hs), dtype=torch.uint8, device=dev)
+        ong[:, :H] = 1
+        catg = None
+        if head_cat is not None:
+            catg = torch.full((G * hs,), -1, dtype=torch.int32, device=dev)
+            catg[:H] = head_cat
+        L.gemm(Ug.view(B * G * hs, D), table, fval, B * G * hs, N, D, lda=D, ldb=D, ldc=ldn0, epilogue=L.EPI_FOLD_HEADS,
+               fold=(hs, ong.reshape(-1), catg, tag_bits, rank, W, thr, cnt, keys, cap, G))
+        L.call("b200rec_topk_from_candidates", keys.data_ptr(), cnt.data_ptr(), cap, B, K, 1 if G > 1 else 0, None, None,
+               rank, W, idx.data_ptr(), val.data_ptr(), hsrc.data_ptr(), ovf.data_ptr(), L.stream())
         return (idx, val, hsrc), 1.0 + N0 / N, ovf
     # materialising path, user-chunked so that fval + fhead stay below 8 GB: the table is re-streamed per chunk
     ldn = (N + 3) // 4 * 4

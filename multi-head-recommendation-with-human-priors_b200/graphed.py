@@ -290,14 +290,15 @@ class GraphedShardedStep(object):
         for p, v in zip(self.dense, self.views):
             p.grad = v
         model.item_embedding.weight.grad = None
+        # the flat all-reduce of the dense gradients starts as soon as the graph is done, on its own communicator: it
+        # runs under this step's table update AND the next step's pre-phase; the dense update waits for it in flush()
+        self._pending = True
+        if W > 1:
+            self._pending = self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.SUM, group=self.ar_group, async_op=True)
         # every rank's gradient rows are complete -> each owner reduces the rows of ITS ids out of all ranks' buffers
-        # (NVLink reads inside the reduction) and updates its shard; the dense all-reduce runs on its own communicator
-        # meanwhile and the dense update waits for it at the start of the next step
+        # (NVLink reads inside the reduction) and updates its shard
         self._barrier()
         model.emb_grad = self.parallel.cuda_segment_reduce_peer(self.cache_ids_all, self.U, W, self.rank, self.g_ptrs,
                                                                 self.D, model.item_embedding.weight.shape[0])
         self.opt.step(grad_scale=1.0 / W, dense=False)
-        self._pending = True
-        if W > 1:
-            self._pending = self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.SUM, group=self.ar_group, async_op=True)
         return out

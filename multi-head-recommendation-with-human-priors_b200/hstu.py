@@ -1319,11 +1319,27 @@ class HSTU(nn.Module):
                 cnt = torch.zeros(Ball, dtype=torch.int32, device=dev)
                 keys = torch.empty((Ball, cap), dtype=torch.int64, device=dev)
                 ovf = torch.zeros(1, dtype=torch.int32, device=dev)
-                L.gemm(Up.reshape(Ball * hp, D), table, fval, Ball * hp, N, D, lda=D, ldb=D, ldc=ldn0,
-                       epilogue=L.EPI_FOLD_HEADS, fold=(hp, onf, cat, bits, rank, Wd, thr, cnt, keys, cap))
-                L.call("b200rec_topk_from_candidates", keys.data_ptr(), cnt.data_ptr(), cap, Ball, K, L.ptr(hist_off),
-                       L.ptr(hist_items), rank, Wd, idx.data_ptr(), val.data_ptr(), hsrc.data_ptr(), ovf.data_ptr(),
-                       L.stream())
+                # no padding to a power of two: G groups of hs heads per user (H = 12 -> 3 x 4), one scoring pass; every
+                # group appends to the user's list, the candidate sort keeps the best copy of an item
+                hs, G = min(((g_ * h_, -h_, h_, g_) for h_ in (8, 4, 2, 1) for g_ in [(H + h_ - 1) // h_]))[2:]
+                if G == 1:
+                    Ug, ong, catg = Up if hs == hp else Up[:, :hs].contiguous(), on[:, :hs].contiguous(), \
+                        (cat[:hs].contiguous() if cat is not None else None)
+                else:
+                    Ug = torch.zeros((Ball, G * hs, D), dtype=U.dtype, device=dev)
+                    Ug[:, :H] = U
+                    ong = torch.zeros((Ball, G * hs), dtype=torch.uint8, device=dev)
+                    ong[:, :H] = on[:, :H]
+                    catg = None
+                    if cat is not None:
+                        catg = torch.full((G * hs,), -1, dtype=torch.int32, device=dev)
+                        catg[:H] = cat[:H]
+                L.gemm(Ug.reshape(Ball * G * hs, D), table, fval, Ball * G * hs, N, D, lda=D, ldb=D, ldc=ldn0,
+                       epilogue=L.EPI_FOLD_HEADS,
+                       fold=(hs, ong.reshape(-1).contiguous(), catg, bits, rank, Wd, thr, cnt, keys, cap, G))
+                L.call("b200rec_topk_from_candidates", keys.data_ptr(), cnt.data_ptr(), cap, Ball, K, 1 if G > 1 else 0,
+                       L.ptr(hist_off), L.ptr(hist_items), rank, Wd, idx.data_ptr(), val.data_ptr(), hsrc.data_ptr(),
+                       ovf.data_ptr(), L.stream())
                 if int(ovf.item()) != 0:                # also the point where eval hands results to the host anyway
                     streamed = False
             if not streamed:
