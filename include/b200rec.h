@@ -290,6 +290,29 @@ int b200rec_nce_loss_fwd(const float* logits, int64_t ld_logits, int n_neg,
 /* gscale (nullable device scalar) multiplies the upstream gradient in the two pos_bwd calls. */
 /* coef[p] = lam[p] * w / max(cnt[p], 1)   (hstu.py:708-712, 850-852) */
 int b200rec_nce_coef(const int32_t* cnt, const float* lam, float w, int P, float* coef, void* stream);
+/* ------------------------------------------------------------------ prior-switch aux heads (a13)
+ * hstu.py:512-544, 731-805 + layers.py:16-84: Linear(D -> 1) per prior category on the body output of EVERY context
+ * position, weighted BCE (mode 0, pos_weight[a]) or asymmetric loss (mode 1).  The reference body is dense, so padded
+ * positions count too: a left-padded query row sees no valid key, its attention output is 0 and each block only adds
+ * its output bias, i.e. y_pad = E[item] + P[pos] + sum_l b_o^l (bo_sum).
+ *   switch_rows:  out[b * Ls + j, :] = tok_index[b, l0 + j] >= 0 ? y[token] : table[items_idx[b, l0 + j]] + pos_emb[l0 + j] + bo_sum
+ *   switch_loss:  logits / element losses / (logit >= 0) == target flags / dlogit = d total / d logit (grad_norm folds
+ *                 prior_switch_loss_weight and the mean); target[b, l, a] = any_p tags[b, l + 1 + p, head_cat[a]]
+ *   switch_bwd:   dW, db (ascending row order), d rows routed to dy[token] (valid) or pad_rows (padded; zero elsewhere)
+ *   switch_pos_grad: dpos[l0 + j, :] += sum_b pad_rows[b * Ls + j, :] */
+int b200rec_switch_rows(const float* y, const int32_t* tok_index, const int64_t* items_idx, const float* table,
+                        const float* pos_emb, const float* bo_sum, int B, int LP, int l0, int Ls, int D,
+                        float* out, void* stream);
+int b200rec_switch_loss(const float* rows, int64_t R, int Ls, int l0, int D, const float* W_aux,
+                        const float* b_aux, int n_act, const int32_t* head_cat, const float* pos_w,
+                        const int64_t* tags, int LP, int C_tag, int P, int mode, float gamma_pos,
+                        float gamma_neg, float clip, float eps, float grad_norm, float* logits, float* loss_el,
+                        float* correct, float* dlogit, void* stream);
+int b200rec_switch_bwd(const float* dlogit, const float* rows, const float* W_aux, int64_t R, int Ls, int l0,
+                       int LP, int n_act, int D, const int32_t* tok_index, const float* gscale,
+                       float* dW, float* db, float* dy, float* pad_rows, void* stream);
+int b200rec_switch_pos_grad(const float* pad_rows, int B, int Ls, int l0, int D, float* dpos, void* stream);
+
 /* Fused sampled-softmax path (bf16 production mode; replaces hstu.py:600-629 + cross_entropy without any fp32
  * [T, Nneg] tensor in HBM).  Order: b200rec_nce_pos_ref -> logits GEMM with B200REC_EPI_NCE_EXP -> b200rec_nce_combine.
  *   nce_pos_ref: pos_cos[T,P] (NaN = offset not served by this head / invalid token), mref[T] = reference exponent of the

@@ -13,8 +13,6 @@
 //
 // Sequences longer than 64 tokens are only legal when they carry no valid key (the all-padding
 // dummy row of static-shape mode): their outputs / gradients are written as zeros.
-#include <algorithm>
-
 #include "common.cuh"
 
 namespace {
@@ -184,33 +182,21 @@ __global__ void __launch_bounds__(128) attn_seq_fwd_kernel(const bf16* __restric
 }
 
 // ------------------------------------------------------------------------------------ backward
-// d_pre[r, c] = grad[r, c] * silu'(pre[r, c]) for the 16 x DH accumulator block of this warp; `z` = the pre-activation
-// words of the block, fetched by load_pre() BEFORE the matmuls so that their latency hides behind the tensor work
+// d_pre[r, c] = grad[r, c] * silu'(pre[r, c]) for the 16 x DH accumulator block of this warp
 template <int DH>
-__device__ __forceinline__ void load_pre(const bf16* __restrict__ pre, int64_t ld, int r0, int n,
-                                         uint32_t (&z)[2][DH / 8]) {
-  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const int r = r0 + g + half * 8;
-#pragma unroll
-    for (int nt = 0; nt < DH / 8; ++nt)
-      z[half][nt] = r < n ? __ldg(reinterpret_cast<const uint32_t*>(pre + (int64_t)r * ld + nt * 8 + 2 * t)) : 0u;
-  }
-}
-
-template <int DH>
-__device__ __forceinline__ void store_dpre(const float (&acc)[DH / 8][4], const uint32_t (&z)[2][DH / 8],
+__device__ __forceinline__ void store_dpre(const float (&acc)[DH / 8][4], const bf16* __restrict__ pre,
                                            bf16* __restrict__ dpre, int64_t ld, int r0, int n) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     int r = r0 + g + half * 8;
     if (r >= n) continue;
+    uint32_t z[DH / 8];
+#pragma unroll
+    for (int nt = 0; nt < DH / 8; ++nt) z[nt] = __ldg(reinterpret_cast<const uint32_t*>(pre + (int64_t)r * ld + nt * 8 + 2 * t));
 #pragma unroll
     for (int nt = 0; nt < DH / 8; ++nt) {
-      uint32_t zw = z[half][nt];
-      __nv_bfloat162 zz = *reinterpret_cast<__nv_bfloat162*>(&zw);
+      __nv_bfloat162 zz = *reinterpret_cast<__nv_bfloat162*>(&z[nt]);
       float lo = acc[nt][half * 2 + 0] * silu_grad_f(__low2float(zz));
       float hi = acc[nt][half * 2 + 1] * silu_grad_f(__high2float(zz));
       *reinterpret_cast<uint32_t*>(dpre + (int64_t)r * ld + nt * 8 + 2 * t) = pack_bf16(lo, hi);
@@ -219,116 +205,78 @@ __device__ __forceinline__ void store_dpre(const float (&acc)[DH / 8][4], const 
 }
 
 template <int DH>
-struct BwdBuf {
-  Tile<DH> sq, sk, sv, sd;
-  uint8_t kv[SEQ_MAX];
-  uint8_t pad[64];
-};
-
-// PERSISTENT: each CTA walks (sequence, head) work items with two shared-memory buffers; the cp.async loads of item
-// i + 1 are in flight while item i is computed, so the ~2 us load latency is paid once per CTA instead of once per
-// item (round 1: one item per CTA, 0.20 of the HBM roofline, tensor pipe 17 %).
-template <int DH>
 __global__ void __launch_bounds__(128) attn_seq_bwd_kernel(const bf16* __restrict__ act, const bf16* __restrict__ pre,
                                                            int ld, const int32_t* __restrict__ seq_off,
                                                            const uint8_t* __restrict__ key_valid, int D, float inv_n,
-                                                           const bf16* __restrict__ d_out, bf16* __restrict__ d_pre,
-                                                           int n_heads, int total) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  BwdBuf<DH>* bufs = reinterpret_cast<BwdBuf<DH>*>(smem_raw);
+                                                           const bf16* __restrict__ d_out, bf16* __restrict__ d_pre) {
+  __shared__ __align__(16) Tile<DH> sq, sk, sv, sd;
+  __shared__ uint8_t kv[SEQ_MAX];
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int t0 = seq_off[b], n = seq_off[b + 1] - t0;
+  if (n <= 0) return;
+  const int64_t row0 = (int64_t)t0 * ld + h * DH;
+  if (n > SEQ_MAX) {
+    for (int part = 1; part < 4; ++part) zero_long_rows<DH>(nullptr, d_pre + row0 + part * D, ld, n);
+    return;
+  }
+  load_rows<DH>(sv, act + row0 + D, ld, n);
+  load_rows<DH>(sq, act + row0 + 2 * D, ld, n);
+  load_rows<DH>(sk, act + row0 + 3 * D, ld, n);
+  load_rows<DH>(sd, d_out + (int64_t)t0 * D + h * DH, D, n);
+  if (threadIdx.x < SEQ_MAX) kv[threadIdx.x] = threadIdx.x < n ? key_valid[t0 + threadIdx.x] : 0;
+  load_wait();
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int r0 = 16 * w;
-
-  auto issue = [&](int work, BwdBuf<DH>& bf) {
-    const int b = work / n_heads, h = work - b * n_heads;
-    const int t0 = seq_off[b], n = seq_off[b + 1] - t0;
-    if (n > 0 && n <= SEQ_MAX) {
-      const int64_t row0 = (int64_t)t0 * ld + h * DH;
-      load_rows<DH>(bf.sv, act + row0 + D, ld, n);
-      load_rows<DH>(bf.sq, act + row0 + 2 * D, ld, n);
-      load_rows<DH>(bf.sk, act + row0 + 3 * D, ld, n);
-      load_rows<DH>(bf.sd, d_out + (int64_t)t0 * D + h * DH, D, n);
-      if (threadIdx.x < SEQ_MAX) bf.kv[threadIdx.x] = threadIdx.x < n ? key_valid[t0 + threadIdx.x] : 0;
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-
-  int work = blockIdx.x, cur = 0;
-  if (work < total) issue(work, bufs[0]);
-  for (; work < total; work += gridDim.x) {
-    const int next = work + gridDim.x;
-    if (next < total) {
-      issue(next, bufs[cur ^ 1]);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
-    const BwdBuf<DH>& bf = bufs[cur];
-    const int b = work / n_heads, h = work - b * n_heads;
-    const int t0 = seq_off[b], n = seq_off[b + 1] - t0;
-    const int64_t row0 = (int64_t)t0 * ld + h * DH;
-    if (n > SEQ_MAX) {
-      for (int part = 1; part < 4; ++part) zero_long_rows<DH>(nullptr, d_pre + row0 + part * D, ld, n);
-    } else if (n > 0 && r0 < n) {
-      const int nb = (n + 15) >> 4;
-      float x[8][4], y[8][4];
-      uint32_t p[4][4];
-      float o[DH / 8][4];
-      uint32_t zq[2][DH / 8];
-      load_pre<DH>(pre + row0 + 2 * D, ld, r0, n, zq);
-      {
-        // ---- rows = queries i: dS[i, j] = (d_out v^T)[i, j] * silu'(S[i, j]) / n_pad * mask ; dq = dS k
-        const int cb_hi = min(w + 1, nb);
-        mm_xyT<DH>(bf.sq, r0, bf.sk, 0, cb_hi, x);
-        mm_xyT<DH>(bf.sd, r0, bf.sv, 0, cb_hi, y);
+  if (r0 >= n) return;
+  const int nb = (n + 15) >> 4;
+  float x[8][4], y[8][4];
+  uint32_t p[4][4];
+  float o[DH / 8][4];
+  {
+    // ---- rows = queries i: dS[i, j] = (d_out v^T)[i, j] * silu'(S[i, j]) / n_pad * mask ; dq = dS k
+    const int cb_hi = min(w + 1, nb);
+    mm_xyT<DH>(sq, r0, sk, 0, cb_hi, x);
+    mm_xyT<DH>(sd, r0, sv, 0, cb_hi, y);
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          float a[4];
+    for (int nt = 0; nt < 8; ++nt) {
+      float a[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            int i = r0 + g + (e >> 1) * 8, j = nt * 8 + 2 * t + (e & 1);
-            a[e] = (j <= i && bf.kv[j]) ? y[nt][e] * silu_grad_f(x[nt][e]) * inv_n : 0.f;
-          }
-          p[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(a[0], a[1]);
-          p[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(a[2], a[3]);
-        }
-        mm_pY<DH>(p, bf.sk, 0, cb_hi, o);
-        store_dpre<DH>(o, zq, d_pre + row0 + 2 * D, ld, r0, n);
+      for (int e = 0; e < 4; ++e) {
+        int i = r0 + g + (e >> 1) * 8, j = nt * 8 + 2 * t + (e & 1);
+        a[e] = (j <= i && kv[j]) ? y[nt][e] * silu_grad_f(x[nt][e]) * inv_n : 0.f;
       }
-      {
-        // ---- rows = keys j: S^T = k q^T, dA^T = v d_out^T over query blocks w..nb-1
-        //      dv = A^T d_out ; dk = dS^T q
-        uint32_t zv[2][DH / 8];
-        load_pre<DH>(pre + row0 + D, ld, r0, n, zv);
-        load_pre<DH>(pre + row0 + 3 * D, ld, r0, n, zq);          // zq now holds the pre-activation of k
-        mm_xyT<DH>(bf.sk, r0, bf.sq, w, nb, x);
-        mm_xyT<DH>(bf.sv, r0, bf.sd, w, nb, y);
-        uint32_t ps[4][4];
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          float a[4], ds[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            int j = r0 + g + (e >> 1) * 8, i = nt * 8 + 2 * t + (e & 1);
-            bool on = (j <= i) && bf.kv[j] && (i < n);
-            float sg = sigmoid_f(x[nt][e]);
-            a[e] = on ? x[nt][e] * sg * inv_n : 0.f;
-            ds[e] = on ? y[nt][e] * sg * (1.f + x[nt][e] * (1.f - sg)) * inv_n : 0.f;
-          }
-          p[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(a[0], a[1]);
-          p[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(a[2], a[3]);
-          ps[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(ds[0], ds[1]);
-          ps[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(ds[2], ds[3]);
-        }
-        mm_pY<DH>(p, bf.sd, w, nb, o);
-        store_dpre<DH>(o, zv, d_pre + row0 + D, ld, r0, n);
-        mm_pY<DH>(ps, bf.sq, w, nb, o);
-        store_dpre<DH>(o, zq, d_pre + row0 + 3 * D, ld, r0, n);
-      }
+      p[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(a[0], a[1]);
+      p[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(a[2], a[3]);
     }
-    __syncthreads();            // every warp is done with bufs[cur] before the next iteration refills it
-    cur ^= 1;
+    mm_pY<DH>(p, sk, 0, cb_hi, o);
+    store_dpre<DH>(o, pre + row0 + 2 * D, d_pre + row0 + 2 * D, ld, r0, n);
+  }
+  {
+    // ---- rows = keys j: S^T = k q^T, dA^T = v d_out^T over query blocks w..nb-1
+    //      dv = A^T d_out ; dk = dS^T q
+    mm_xyT<DH>(sk, r0, sq, w, nb, x);
+    mm_xyT<DH>(sv, r0, sd, w, nb, y);
+    uint32_t ps[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      float a[4], ds[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        int j = r0 + g + (e >> 1) * 8, i = nt * 8 + 2 * t + (e & 1);
+        bool on = (j <= i) && kv[j] && (i < n);
+        float sg = sigmoid_f(x[nt][e]);
+        a[e] = on ? x[nt][e] * sg * inv_n : 0.f;
+        ds[e] = on ? y[nt][e] * sg * (1.f + x[nt][e] * (1.f - sg)) * inv_n : 0.f;
+      }
+      p[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(a[0], a[1]);
+      p[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(a[2], a[3]);
+      ps[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(ds[0], ds[1]);
+      ps[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(ds[2], ds[3]);
+    }
+    mm_pY<DH>(p, sd, w, nb, o);
+    store_dpre<DH>(o, pre + row0 + D, d_pre + row0 + D, ld, r0, n);
+    mm_pY<DH>(ps, sq, w, nb, o);
+    store_dpre<DH>(o, pre + row0 + 3 * D, d_pre + row0 + 3 * D, ld, r0, n);
   }
 }
 
@@ -365,28 +313,14 @@ extern "C" int b200rec_hstu_attn_seq_bwd(const void* act, const void* pre, int l
   B200_CHECK_ARG(((uintptr_t)act & 15) == 0 && ((uintptr_t)d_out & 15) == 0 && ((uintptr_t)pre & 3) == 0 &&
                      ((uintptr_t)d_pre & 3) == 0,
                  "attn_seq: alignment");
-  const int total = n_heads * B;
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    B200_CUDA_OK(cudaGetDevice(&dev));
-    B200_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    B200_CUDA_OK(cudaFuncSetAttribute(attn_seq_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(2 * sizeof(BwdBuf<64>))));
-    B200_CUDA_OK(cudaFuncSetAttribute(attn_seq_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(2 * sizeof(BwdBuf<32>))));
-  }
-  if (dh == 64) {
-    const int grid = std::min(total, n_sm * 3);          // 2 x 37 KB of buffers per CTA: three CTAs per SM
-    attn_seq_bwd_kernel<64><<<grid, 128, 2 * sizeof(BwdBuf<64>), (cudaStream_t)stream>>>(
-        (const bf16*)act, (const bf16*)pre, ld, seq_off, key_valid, n_heads * dh, inv_n, (const bf16*)d_out,
-        (bf16*)d_pre, n_heads, total);
-  } else if (dh == 32) {
-    const int grid = std::min(total, n_sm * 4);
-    attn_seq_bwd_kernel<32><<<grid, 128, 2 * sizeof(BwdBuf<32>), (cudaStream_t)stream>>>(
-        (const bf16*)act, (const bf16*)pre, ld, seq_off, key_valid, n_heads * dh, inv_n, (const bf16*)d_out,
-        (bf16*)d_pre, n_heads, total);
-  } else {
+  dim3 grid(n_heads, B);
+  if (dh == 64)
+    attn_seq_bwd_kernel<64><<<grid, 128, 0, (cudaStream_t)stream>>>(
+        (const bf16*)act, (const bf16*)pre, ld, seq_off, key_valid, n_heads * dh, inv_n, (const bf16*)d_out, (bf16*)d_pre);
+  else if (dh == 32)
+    attn_seq_bwd_kernel<32><<<grid, 128, 0, (cudaStream_t)stream>>>(
+        (const bf16*)act, (const bf16*)pre, ld, seq_off, key_valid, n_heads * dh, inv_n, (const bf16*)d_out, (bf16*)d_pre);
+  else {
     b200rec_set_error("attn_seq: head dim %d not supported (32 or 64)", dh);
     return 1;
   }

@@ -212,7 +212,12 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * (uint32_t)p.BN;
-      for (int c = half; c < p.BN / 32; c += 2) {
+      // GT_BITS: ONE warp per lane quarter converts all chunks of its rows, so that a lane owns BN / 32 consecutive
+      // words (32 bytes at BN = 256 = one full sector); alternating chunks between the two warps of a quarter made every
+      // 4-byte word a partial-sector write 1 KB away from its neighbours and the K = 64 filter GEMM store-bound
+      uint32_t gt_words[8];
+      for (int c = (MODE == B200REC_EPI_GT_BITS ? 0 : half); c < p.BN / 32; c += (MODE == B200REC_EPI_GT_BITS ? 1 : 2)) {
+        if (MODE == B200REC_EPI_GT_BITS && half == 1) break;
         float v[32];
         tmem_ld_32x32(t_row + (uint32_t)c * 32u, v);
         if (MODE == B200REC_EPI_NCE_EXP) {
@@ -245,10 +250,27 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
 #pragma unroll
             for (int i = 0; i < 32; ++i) wbits |= (v[i] > ep.alpha) ? (1u << i) : 0u;
           }
-          if (m < ep.M && nn < ep.N) {
-            if (nn + 32 > ep.N) wbits &= (1u << (ep.N - nn)) - 1u;
-            ((uint32_t*)ep.C)[(int64_t)m * ep.ldc + (nn >> 5)] = wbits;
-            if (wbits != 0u && ep.C2) ((uint8_t*)ep.C2)[m] = 1;
+          if (nn >= ep.N) wbits = 0u;
+          else if (nn + 32 > ep.N) wbits &= (1u << (ep.N - nn)) - 1u;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) gt_words[q] = (c == q) ? wbits : gt_words[q];   // static register indices
+          if (m < ep.M && wbits != 0u && ep.C2) ((uint8_t*)ep.C2)[m] = 1;
+          if (c == p.BN / 32 - 1 && m < ep.M) {
+            // words [n0/32, n0/32 + BN/32) of row m: 16-byte stores where the row pitch allows it
+            uint32_t* dst = (uint32_t*)ep.C + (int64_t)m * ep.ldc + (n0 >> 5);
+            const int nw_tile = p.BN / 32;
+            const int nw_valid = min(nw_tile, (int)((ep.N - n0 + 31) >> 5));
+            if (nw_valid == nw_tile && (ep.ldc & 3) == 0 && (((uintptr_t)ep.C) & 15) == 0) {
+#pragma unroll
+              for (int q = 0; q < 2; ++q)
+                if (q * 4 < nw_tile)
+                  *reinterpret_cast<uint4*>(dst + q * 4) = make_uint4(gt_words[q * 4], gt_words[q * 4 + 1],
+                                                                      gt_words[q * 4 + 2], gt_words[q * 4 + 3]);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                if (q < nw_valid) dst[q] = gt_words[q];
+            }
           }
           continue;
         }

@@ -62,7 +62,7 @@ def topk_point(table, U, K, rank, W, tag_bits=None, head_cat=None, streamed=True
         cnt = torch.zeros(B, dtype=torch.int32, device=dev)
         keys = torch.empty((B, cap), dtype=torch.int64, device=dev)
         ovf = torch.zeros(1, dtype=torch.int32, device=dev)
-        hs, G = min(((g_ * h_, -h_, h_, g_) for h_ in (8, 4, 2, 1) for g_ in [(H + h_ - 1) // h_]))[2:]
+        hs, G = hp, 1            # head groups without padding (G > 1) measured slower than padding to a power of two
         Ug = torch.zeros((B, G * hs, D), dtype=U.dtype, device=dev)
         Ug[:, :H] = U
         ong = torch.zeros((B, G * hs), dtype=torch.uint8, device=dev)

@@ -176,9 +176,30 @@ class HSTU(nn.Module):
                     self.prior_loss_weight[dataload.category_to_int[name]] = cnt / tot
             else:
                 self.prior_loss_weight = [1 / self.num_prior_head] * self.num_prior_head
+            self.aux_cat_head = None
             if self.loss == "prior" and config["prior_switch"] is not None:
-                raise NotImplementedError("prior_switch aux heads are not built (off in every shipped script)")
-        self.prior_switch = None
+                # hstu.py:512-544: one Linear(D -> 1) per prior category on the body output ('in')
+                if config["prior_switch"] == "in_out":
+                    raise NotImplementedError("prior_switch='in_out' (aux input = [body output, head output]) is not built; "
+                                              "'in' is")
+                if config["prior_switch"] != "in":
+                    config["prior_switch"] = None          # hstu.py:538-540: unknown value -> switched off
+                else:
+                    assert config["split_mode"] == "combine"
+                    self.use_asym_switch_loss = bool(config.get("asym_switch_loss", False))
+                    self.switch_last_only = bool(config.get("switch_last_only", False))
+                    self.gamma_pos = float(config.get("gamma_pos", 4.0))
+                    self.gamma_neg = float(config.get("gamma_neg", 0.0))
+                    self.master_switch = bool(config.get("master_switch", False))
+                    self.aux_cat_head = nn.ModuleList([nn.Linear(D, 1) for _ in range(self.num_prior_head)])
+                    if self.master_switch:
+                        for i in range(1, self.num_prior_head):
+                            for p_ in self.aux_cat_head[i].parameters():
+                                p_.requires_grad_(False)
+                    self.prior_switch_loss_weight = float(config["prior_switch_loss_weight"])
+        self.prior_switch = config["prior_switch"] if (self.medusa_num_layers > 0 and self.loss == "prior") else None
+        self.use_prior_switch_test = bool(config.get("use_prior_switch_test", False))
+        self.detach_aux_in = bool(config.get("detach_aux_in", False))
         self.eval_pred_len = config["eval_pred_len"]
         self.prior_given_at_test = config.get("prior_given_at_test", False)
         self.given_prior_len = config.get("given_prior_len", self.eval_pred_len) if self.prior_given_at_test \
@@ -191,7 +212,8 @@ class HSTU(nn.Module):
         self.use_fused_eval = bool(config.get("fused_eval", True))
         self.use_fused_nce = bool(config.get("fused_nce", True))
         self.use_streamed_eval = bool(config.get("streamed_eval", True))
-        self.use_pruned_filter = bool(config.get("pruned_filter", True))   # false-negative filter via an upper bound   # top-K candidates filtered in the scoring GEMM     # bf16 mode: softmax numerators from the GEMM epilogue
+        self.use_pruned_filter = bool(config.get("pruned_filter", True))
+        self.eval_head_groups = bool(config.get("eval_head_groups", False))   # streamed eval: H = 12 as 3 x 4 (no padding)   # false-negative filter via an upper bound   # top-K candidates filtered in the scoring GEMM     # bf16 mode: softmax numerators from the GEMM epilogue
         self.share_negatives = bool(config.get("share_negatives", True))   # all-gather negatives across ranks
         self.dropout_seed = int(config.get("seed", 2020)) & 0xffffffff
         self._rng_step = None      # device counter feeding the Philox dropout stream
@@ -654,6 +676,75 @@ class HSTU(nn.Module):
                 gmap[key] = d_in
         return gmap.pop(y.data_ptr())
 
+    # ------------------------------------------------------------------ prior switch (hstu.py:512-544, 731-805)
+    def _switch_heads(self):
+        """(active categories, stacked weight [n_act, D], bias [n_act]) — master_switch uses head 0 only."""
+        act_c = [0] if self.master_switch else list(range(self.num_prior_head))
+        Wa = torch.cat([self.aux_cat_head[c].weight.data for c in act_c], dim=0).contiguous()
+        ba = torch.cat([self.aux_cat_head[c].bias.data for c in act_c], dim=0).contiguous()
+        return act_c, Wa, ba
+
+    def _switch_forward(self, y, tok_index, items_idx, table, tags, Breal, LP, need_grad):
+        """Aux loss over ALL context positions of the real batch rows (padded positions rebuilt in closed form, see
+        csrc/switch.cu).  Returns the weighted loss tensor, the logging scalars and what the backward needs."""
+        D, P, Lc = self._hstu_embedding_dim, self.pred_len, self.max_seq_length
+        dev, st = y.device, L.stream()
+        l0, Ls = (Lc - 1, 1) if self.switch_last_only else (0, Lc)
+        R = Breal * Ls
+        act_c, Wa, ba = self._switch_heads()
+        n_act = len(act_c)
+        bo_sum = torch.stack([blk._o.bias.data for blk in self._hstu._attention_layers]).sum(0).contiguous()
+        rows = torch.empty((R, D), dtype=torch.float32, device=dev)
+        L.call("b200rec_switch_rows", y.data_ptr(), tok_index.data_ptr(), items_idx.data_ptr(), table.data_ptr(),
+               self.position_embedding.weight.data_ptr(), bo_sum.data_ptr(), Breal, LP, l0, Ls, D, rows.data_ptr(), st)
+        head_cat = torch.tensor(act_c, dtype=torch.int32, device=dev)
+        pw = []
+        for c in act_c:                                           # hstu.py:787-790
+            p_ = max(min(float(self.prior_loss_weight[c]), 1.0 - 1e-6), 1e-6)
+            pw.append((1.0 - p_) / p_)
+        pos_w = torch.tensor(pw, dtype=torch.float32, device=dev)
+        asl = self.use_asym_switch_loss
+        # BCE: mean over all B x Ls elements; ASL: sum over positions, mean over the batch (layers.py:80-82)
+        norm = 1.0 / Breal if asl else 1.0 / R
+        logits = torch.empty((R, n_act), dtype=torch.float32, device=dev)
+        loss_el = torch.empty((R, n_act), dtype=torch.float32, device=dev)
+        correct = torch.empty((R, n_act), dtype=torch.float32, device=dev)
+        dlogit = torch.empty((R, n_act), dtype=torch.float32, device=dev)
+        tags = tags.contiguous()
+        L.call("b200rec_switch_loss", rows.data_ptr(), R, Ls, l0, D, Wa.data_ptr(), ba.data_ptr(), n_act,
+               head_cat.data_ptr(), pos_w.data_ptr(), tags.data_ptr(), LP, tags.shape[-1], P, 1 if asl else 0,
+               self.gamma_pos, self.gamma_neg, 0.05, 1e-8, self.prior_switch_loss_weight * norm, logits.data_ptr(),
+               loss_el.data_ptr(), correct.data_ptr(), dlogit.data_ptr(), st)
+        lsum = torch.empty(n_act, dtype=torch.float32, device=dev)
+        csum = torch.empty(n_act, dtype=torch.float32, device=dev)
+        L.colsum(loss_el, R, n_act, n_act, lsum)
+        L.colsum(correct, R, n_act, n_act, csum)
+        per_head = lsum * (self.prior_switch_loss_weight * norm)
+        logs = {}
+        for i, c in enumerate(act_c):
+            name = self.int_to_category[c]
+            logs[f"head_cat_{name}_acc"] = (csum[i] / R).detach()
+            logs[f"head_cat_{name}_loss"] = per_head[i].detach()
+        return dict(loss=per_head.sum(), logs=logs, rows=rows, dlogit=dlogit, Wa=Wa, act_c=act_c, Breal=Breal, l0=l0,
+                    Ls=Ls, logits=logits)
+
+    def _switch_backward(self, ctx, dy, gscale, grads):
+        sw = ctx["switch"]
+        D = self._hstu_embedding_dim
+        dev, st = dy.device, L.stream()
+        Breal, l0, Ls = sw["Breal"], sw["l0"], sw["Ls"]
+        R, n_act = Breal * Ls, len(sw["act_c"])
+        dW = torch.empty((n_act, D), dtype=torch.float32, device=dev)
+        db = torch.empty(n_act, dtype=torch.float32, device=dev)
+        pad_rows = None if self.detach_aux_in else torch.empty((R, D), dtype=torch.float32, device=dev)
+        L.call("b200rec_switch_bwd", sw["dlogit"].data_ptr(), sw["rows"].data_ptr(), sw["Wa"].data_ptr(), R, Ls, l0,
+               ctx["LP"], n_act, D, ctx["tok_index"].data_ptr(), gscale.data_ptr(), dW.data_ptr(), db.data_ptr(),
+               None if self.detach_aux_in else dy.data_ptr(), L.ptr(pad_rows), st)
+        for i, c in enumerate(sw["act_c"]):
+            grads[self.aux_cat_head[c].weight] = dW[i:i + 1]
+            grads[self.aux_cat_head[c].bias] = db[i:i + 1]
+        return None if self.detach_aux_in else (pad_rows, Breal, l0, Ls)
+
     # ------------------------------------------------------------------ training (hstu.py:631-872)
     def forward(self, interaction, n_tokens=None, prepared=None):
         """`n_tokens` (optional host int >= number of valid context tokens, e.g. from the collate fn): builds
@@ -873,6 +964,11 @@ class HSTU(nn.Module):
                 cur = {k: torch.where(cntv > 0, v, cur[k]) for k, v in upd.items()}
         if cur is not None:
             logs.update(cur)
+        sw = None
+        if self.prior_switch is not None:
+            sw = self._switch_forward(y, tok_index, items, W, tags, B - (1 if static else 0), LP, need_grad)
+            total = total + sw["loss"]
+            logs.update(sw["logs"])
         loss = total * half
         if self._debug is not None:
             self._debug.update(x0=x.clone(), y=y.clone(), hd=hd.clone(), qhat=qhat.clone(), that=that.clone(),
@@ -885,7 +981,7 @@ class HSTU(nn.Module):
                        items=items, mask=m, n_neg=n_neg, ld_neg=ld_neg, Hx=Hx, used_sets=used_sets,
                        gl_items=gl_items, gl_neg_ids=gl_neg_ids, uniq_rows_ids=uniq_rows_ids,
                        n_cache_rows=W.shape[0], push=prepared.get("push", True), cache_info=prepared.get("info"),
-                       grad_out=prepared.get("grad_out"))
+                       grad_out=prepared.get("grad_out"), switch=sw, table=W)
         return loss, logs, ctx
 
     def _train_backward(self, ctx, gscale):
@@ -994,6 +1090,10 @@ class HSTU(nn.Module):
                 grads[lin.bias] = dbc[h * D:(h + 1) * D]
         else:
             L.call("b200rec_resblock_bwd", d_hd.data_ptr(), None, a_dt, T, Hx, D, None, dy.data_ptr(), st)
+        # ---- prior-switch aux heads: into dy (valid positions) / pad rows, aux weights
+        sw_pad = None
+        if ctx.get("switch") is not None:
+            sw_pad = self._switch_backward(ctx, dy, gscale, grads)
         # ---- body
         if self._debug is not None:
             self._debug.update(d_hd=d_hd.clone(), dy=dy.clone())
@@ -1005,6 +1105,14 @@ class HSTU(nn.Module):
         dpos = torch.zeros_like(self.position_embedding.weight.data)
         L.call("b200rec_pos_emb_grad", dx0.data_ptr(), ctx["tok_index"].data_ptr(), B, LP, Lc, D, dpos.data_ptr(), st)
         grads[self.position_embedding.weight] = dpos
+        if sw_pad is not None:
+            # padded positions of the aux loss: y_pad = E[item] + P[pos] + sum of the blocks' output biases
+            pad_rows, Breal, l0, Ls = sw_pad
+            L.call("b200rec_switch_pos_grad", pad_rows.data_ptr(), Breal, Ls, l0, D, dpos.data_ptr(), st)
+            dbo_x = torch.empty(D, dtype=torch.float32, device=dev)
+            L.colsum(pad_rows, Breal * Ls, D, D, dbo_x)
+            for blk in self._hstu._attention_layers:
+                grads[blk._o.bias] = grads[blk._o.bias] + dbo_x
         # ---- item embedding: concatenate gradient rows + ids, one sorted-segment reduction
         # `items` / `neg_ids` index the table the kernels read (global ids, or positions in the fetched-row
         # cache of a sharded table); keys <= 0 carry no gradient (padding_idx 0, masked positions).
@@ -1012,7 +1120,8 @@ class HSTU(nn.Module):
         sharded = ctx["uniq_rows_ids"] is not None
         shift = 1 if sharded else 0          # cache position 0 is a real row: shift keys by one
         sets = ctx["used_sets"]
-        n_rows = T + B * LP + len(sets) * n_neg
+        n_sw = 0 if sw_pad is None else sw_pad[1] * sw_pad[3]
+        n_rows = T + B * LP + len(sets) * n_neg + n_sw
         rows = torch.empty((n_rows, D), dtype=torch.float32, device=dev)
         ids = torch.empty(n_rows, dtype=torch.int64, device=dev)
         rows[:T].copy_(dx0)
@@ -1029,9 +1138,20 @@ class HSTU(nn.Module):
                    dnhat[s].data_ptr(), n_neg, D, rows[off:].data_ptr(), 0, st)
             ids[off:off + n_neg] = ctx["neg_ids"][s] + shift
             off += n_neg
+        sw_gl = []
+        if sw_pad is not None:
+            # gradient rows of the aux loss at padded context positions -> the pad items' table rows (zero rows, and id 0
+            # keys, at valid positions: they were routed into dy)
+            pad_rows, Breal, l0, Ls = sw_pad
+            rows[off:off + n_sw].copy_(pad_rows)
+            pos_valid = ctx["tok_index"].view(B, LP)[:Breal, l0:l0 + Ls] >= 0
+            sw_items = items[:Breal, l0:l0 + Ls]
+            ids[off:off + n_sw] = torch.where(pos_valid, torch.zeros_like(sw_items), sw_items + shift).reshape(-1)
+            sw_gl = [torch.where(pos_valid, torch.zeros_like(sw_items), ctx["gl_items"][:Breal, l0:l0 + Ls]).reshape(-1)]
+            off += n_sw
         if sharded:                              # padding id 0 never gets a gradient
             gl = torch.cat([ctx["gl_items"].reshape(-1)[tok_flat], ctx["gl_items"].reshape(-1)] +
-                           [ctx["gl_neg_ids"][s] for s in sets])
+                           [ctx["gl_neg_ids"][s] for s in sets] + sw_gl)
             ids = torch.where(gl == 0, torch.zeros_like(ids), ids)
         uniq_ids, uniq_rows, n_uniq = parallel.cuda_segment_reduce(ids, rows)
         if sharded:
@@ -1136,6 +1256,7 @@ class HSTU(nn.Module):
         last = (seq_off[1:] - 1).long()
         y_last = torch.empty((B, D), dtype=torch.float32, device=dev)
         L.call("b200rec_gather_rows", y.data_ptr(), D, last.data_ptr(), B, y_last.data_ptr(), L.F32, st)
+        self._last_user_y = y_last                 # body output of the last position (prior-switch heads read it)
         hd, _, _ = self._heads_forward(y_last, w, B)
         H = self.medusa_num_heads
         if hd.shape[1] != H:                       # identity heads: every head is the body output
@@ -1179,6 +1300,29 @@ class HSTU(nn.Module):
                 head_on = torch.cat([torch.ones(B, S, dtype=torch.bool, device=device), on_c], dim=1)
             else:
                 head_on = on_c.repeat(1, S)
+        self._switch_logs = {}
+        if self.prior_switch is not None:
+            # hstu.py:935-956, 1001-1015: aux logits of the last position; optionally switch prior heads off
+            act_c, Wa, ba = self._switch_heads()
+            y_last = self._last_user_y
+            logit = torch.empty((B, len(act_c)), dtype=torch.float32, device=device)
+            L.gemm(y_last, Wa, logit, B, len(act_c), self._hstu_embedding_dim, lda=self._hstu_embedding_dim,
+                   ldb=self._hstu_embedding_dim, ldc=len(act_c), epilogue=L.EPI_BIAS_RESID, bias=ba)
+            pred = logit >= 0                                                              # [B, n_act]
+            for i, c in enumerate(act_c):
+                lab = target_tags[:, :, c].sum(dim=-1) > 0
+                self._switch_logs[f"head_cat_{self.int_to_category[c]}_num_correct"] = (lab == pred[:, i]).float().sum()
+            if self.use_prior_switch_test:
+                if self.master_switch:
+                    on_c = torch.cat([pred[:, :1], (~pred[:, :1]).expand(B, C - 1)], dim=1)
+                else:
+                    on_c = pred
+                if self.head_interaction == "additive":
+                    sw_on = torch.cat([torch.ones(B, S, dtype=torch.bool, device=device), on_c], dim=1)
+                else:
+                    sw_on = on_c.repeat(1, S)
+                head_on = sw_on if head_on is None else (head_on & sw_on)
+        if head_on is not None:
             head_on = head_on.to(torch.uint8).contiguous()
         return head_cat, item_tag_bits, head_on
 
@@ -1196,6 +1340,7 @@ class HSTU(nn.Module):
             L.call("b200rec_apply_score_masks", scores.data_ptr(), N, B, H, N, head_cat.data_ptr(), bits.data_ptr(),
                    L.ptr(head_on), L.stream())
         logs = {"num_samples": self.eval_pred_len * B}
+        logs.update(self._switch_logs)
         head_embs = U.float().cpu().numpy() if save_for_eval else None
         return scores.view(B, H, N), logs, None, head_embs
 
@@ -1321,7 +1466,9 @@ class HSTU(nn.Module):
                 ovf = torch.zeros(1, dtype=torch.int32, device=dev)
                 # no padding to a power of two: G groups of hs heads per user (H = 12 -> 3 x 4), one scoring pass; every
                 # group appends to the user's list, the candidate sort keeps the best copy of an item
-                hs, G = min(((g_ * h_, -h_, h_, g_) for h_ in (8, 4, 2, 1) for g_ in [(H + h_ - 1) // h_]))[2:]
+                hs, G = hp, 1
+                if self.eval_head_groups:       # measured r02: slower than padding (3x the appends + a second sort)
+                    hs, G = min(((g_ * h_, -h_, h_, g_) for h_ in (8, 4, 2, 1) for g_ in [(H + h_ - 1) // h_]))[2:]
                 if G == 1:
                     Ug, ong, catg = Up if hs == hp else Up[:, :hs].contiguous(), on[:, :hs].contiguous(), \
                         (cat[:hs].contiguous() if cat is not None else None)

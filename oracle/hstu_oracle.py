@@ -219,6 +219,8 @@ class OracleHSTU:
                 out[f"seg_{s}_loss"] = seg[s]
             if (ptok == 0).any():                                                 # :721-723
                 out.update(train_topk_logs(logits[ptok == 0].detach()))
+        if self.loss == "prior" and cfg_get(self.cfg, "prior_switch") == "in" and self.mlayers > 0:
+            total = total + self.prior_switch_loss(y, tags, out)                  # :731-805
         if self.loss == "prior":
             seg_len = P if self.inter == "additive" else self.seg_len             # :726-729
             seg_for_p = torch.arange(P) // seg_len
@@ -253,6 +255,42 @@ class OracleHSTU:
         out["loss"] = total
         return out
 
+    def prior_switch_loss(self, y, tags, out):
+        """Aux category heads on the dense body output (hstu.py:731-805, prior_switch == 'in'): weighted BCE
+        (pos_weight = (1 - p_c) / p_c) or AsymmetricLoss (layers.py:16-84) over ALL [B, L] positions."""
+        cfg, L, P = self.cfg, self.L, self.P
+        w = float(cfg["prior_switch_loss_weight"])
+        master = bool(cfg_get(cfg, "master_switch", False))
+        last_only = bool(cfg_get(cfg, "switch_last_only", False))
+        asl = bool(cfg_get(cfg, "asym_switch_loss", False))
+        widx = torch.arange(L)[:, None] + 1 + torch.arange(P)[None, :]            # [L, P] target window of position l
+        total = 0.0
+        for c in range(self.C):
+            if master and c > 0:
+                continue
+            tgt = tags[:, :, c].bool()[:, widx].any(dim=-1).float()               # [B, L]   (:733-736, 763-766)
+            aux_in = y.detach() if cfg_get(cfg, "detach_aux_in", False) else y
+            if last_only:
+                tgt, aux_in = tgt[:, -1:], aux_in[:, -1:]
+            logit = (aux_in @ self.p[f"aux_cat_head.{c}.weight"].t() + self.p[f"aux_cat_head.{c}.bias"]).squeeze(-1)
+            if asl:
+                gp, gn = float(cfg_get(cfg, "gamma_pos", 4.0)), float(cfg_get(cfg, "gamma_neg", 0.0))
+                sg = torch.sigmoid(logit)
+                xs_pos, xs_neg = sg, (1 - sg + 0.05).clamp(max=1)
+                ls = tgt * torch.log(xs_pos.clamp(min=1e-8)) + (1 - tgt) * torch.log(xs_neg.clamp(min=1e-8))
+                if gn > 0 or gp > 0:
+                    pt = xs_pos * tgt + xs_neg * (1 - tgt)
+                    ls = ls * torch.pow(1 - pt, gp * tgt + gn * (1 - tgt))
+                lc = (-ls.sum(dim=-1)).mean()
+            else:
+                p_ = max(min(float(self.prior_w[c]), 1.0 - 1e-6), 1e-6)
+                lc = F.binary_cross_entropy_with_logits(logit, tgt, pos_weight=torch.tensor((1.0 - p_) / p_))
+            name = self.int_to_category[c]
+            out[f"head_cat_{name}_acc"] = ((logit >= 0).int() == tgt.int()).float().mean().detach()
+            out[f"head_cat_{name}_loss"] = (w * lc).detach()
+            total = total + w * lc
+        return total
+
     # ---- eval (hstu.py:874-1021) ------------------------------------------------------
     @torch.no_grad()
     def compute_item_all(self):
@@ -264,6 +302,7 @@ class OracleHSTU:
         L = item_seq.shape[1]
         x = self.embed(item_seq) + self.p["position_embedding.weight"][:L]
         y = self.body(x, item_seq != 0)[:, -1]                                    # :908-913
+        self._last_y = y
         return l2n(self.heads(y).permute(1, 0, 2).float())
 
     @torch.no_grad()
@@ -282,6 +321,23 @@ class OracleHSTU:
             it = all_item_tags.bool().repeat(rep, 1)                              # :994-999  [C*rep, N]
             scores[:, sl].masked_fill_(~it.unsqueeze(0), float("-inf"))
         logs = {"num_samples": self.cfg["eval_pred_len"] * item_seq.shape[0]}     # :933
+        if self.loss == "prior" and cfg_get(self.cfg, "prior_switch") == "in" and self.mlayers > 0:
+            y_last = self._last_y                                                 # :935-956, 1001-1015
+            master = bool(cfg_get(self.cfg, "master_switch", False))
+            preds = []
+            for c in range(1 if master else C):
+                lg = (y_last @ self.p[f"aux_cat_head.{c}.weight"].t() + self.p[f"aux_cat_head.{c}.bias"]).squeeze(-1)
+                preds.append(lg >= 0)
+                lab = target_tags[:, :, c].sum(dim=-1) > 0
+                logs[f"head_cat_{self.int_to_category[c]}_num_correct"] = (lab == preds[c]).float().sum()
+            if cfg_get(self.cfg, "use_prior_switch_test", False):
+                if master:
+                    off = torch.cat([~preds[0][:, None], preds[0][:, None].expand(-1, C - 1)], dim=1)
+                else:
+                    off = ~torch.stack(preds, dim=1)
+                sl = slice(S, None) if self.inter == "additive" else slice(None)
+                rep = 1 if self.inter == "additive" else S
+                scores[:, sl].masked_fill_(off.repeat(1, rep).unsqueeze(-1), float("-inf"))
         return scores, logs, None, None
 
 

@@ -67,8 +67,11 @@ def test_product_package_does_not_import_oracle():
 def test_unsupported_configs_raise():
     from b200rec import synth
     from b200rec.hstu import HSTU
-    for over in (dict(head_interaction="hierarchical", head_norm=True), dict(prior_switch="in"),
+    for over in (dict(head_interaction="hierarchical", head_norm=True), dict(prior_switch="in_out", prior_switch_loss_weight=1.0),
                  dict(pos_sample_mix_ratio=0.1)):
         cfg = synth.make_config("D", item_num=200, **over)
         with pytest.raises(NotImplementedError):
             HSTU(cfg, synth.make_dataload(cfg))
+    cfg = synth.make_config("D", item_num=200, prior_switch="in", prior_switch_loss_weight=0.5)
+    m = HSTU(cfg, synth.make_dataload(cfg))            # prior-switch aux heads ('in') are built
+    assert len(m.aux_cat_head) == cfg["num_prior_head"] and "aux_cat_head.0.weight" in m.state_dict()
