@@ -290,6 +290,21 @@ int b200rec_nce_loss_fwd(const float* logits, int64_t ld_logits, int n_neg,
 /* gscale (nullable device scalar) multiplies the upstream gradient in the two pos_bwd calls. */
 /* coef[p] = lam[p] * w / max(cnt[p], 1)   (hstu.py:708-712, 850-852) */
 int b200rec_nce_coef(const int32_t* cnt, const float* lam, float w, int P, float* coef, void* stream);
+/* Relative position bias variant (north_star (b); reference hstu.py:74-134 builds the bias module but never applies it,
+ * so this path is OFF for parity and only runs when config['apply_relative_attention_bias'] is set):
+ *   A = silu(q k^T + bias_d[i - j]) / n_pad * mask,   bias_d fp32[max_len] indexed by the query-key distance.
+ * bwd additionally fills dbias_part [b200rec_hstu_attn_bias_ws_floats(B, n_heads, max_len) / max_len rows, max_len]
+ * (caller zero-fills); d bias_d = its column sums (fixed order: deterministic).  fp32 / bf16 SIMT kernels. */
+int b200rec_hstu_attn_bias_fwd(const void* q, const void* k, const void* v, int ld, int act_dtype,
+                               const int32_t* seq_off, const uint8_t* key_valid, int B, int T, int n_heads,
+                               int dh, float inv_n, int max_len, const float* bias_d, float* out, void* stream);
+size_t b200rec_hstu_attn_bias_ws_floats(int B, int n_heads, int max_len);
+int b200rec_hstu_attn_bias_bwd(const void* q, const void* k, const void* v, const void* pre_q,
+                               const void* pre_k, const void* pre_v, int ld, int act_dtype,
+                               const int32_t* seq_off, const uint8_t* key_valid, int B, int T, int n_heads,
+                               int dh, float inv_n, int max_len, const float* bias_d, const void* d_out,
+                               void* d_pre_q, void* d_pre_k, void* d_pre_v, float* dbias_part, void* stream);
+
 /* ------------------------------------------------------------------ prior-switch aux heads (a13)
  * hstu.py:512-544, 731-805 + layers.py:16-84: Linear(D -> 1) per prior category on the body output of EVERY context
  * position, weighted BCE (mode 0, pos_weight[a]) or asymmetric loss (mode 1).  The reference body is dense, so padded

@@ -91,6 +91,10 @@ _SIGS = {
     "b200rec_hstu_attn_fwd": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P]),
     "b200rec_hstu_attn_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P,
                                         _P, _P, _P, _P]),
+    "b200rec_hstu_attn_bias_fwd": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P, _P]),
+    "b200rec_hstu_attn_bias_ws_floats": (_Z, [_I, _I, _I]),
+    "b200rec_hstu_attn_bias_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P,
+                                             _P, _P, _P, _P, _P]),
     "b200rec_hstu_attn_tc_fwd": (C.c_int, [_P, _I, _P, _P, _I, _I, _I, _I, _F, _P, _P]),
     "b200rec_hstu_attn_tc_bwd": (C.c_int, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P]),
     "b200rec_hstu_attn_seq_fwd": (C.c_int, [_P, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P]),

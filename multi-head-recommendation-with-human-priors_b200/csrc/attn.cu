@@ -97,7 +97,9 @@ __global__ void __launch_bounds__(256) hstu_attn_fwd_kernel(const TA* __restrict
                                                             const TA* __restrict__ v, int64_t ld,
                                                             const int32_t* __restrict__ seq_off,
                                                             const uint8_t* __restrict__ key_valid, float inv_n,
-                                                            float* __restrict__ out, int D) {
+                                                            float* __restrict__ out, int D,
+                                                            const float* __restrict__ bias_d) {
+  // bias_d (nullable): relative position bias by query-key distance, A = silu(q k^T + bias_d[i - j]) / n_pad
   extern __shared__ __align__(16) uint8_t smem_raw[];
   AttnSmem<DH>& sm = *reinterpret_cast<AttnSmem<DH>*>(smem_raw);
   const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
@@ -128,7 +130,8 @@ __global__ void __launch_bounds__(256) hstu_attn_fwd_kernel(const TA* __restrict
       for (int bb = 0; bb < 4; ++bb) {
         int i = ty + 16 * a, j = tx + 16 * bb;
         bool keep = (k0 + j <= q0 + i) && sm.kvalid[j];
-        sm.s[i][j] = keep ? silu_f(acc[a][bb]) * inv_n : 0.f;
+        const float sb = (keep && bias_d) ? acc[a][bb] + __ldg(bias_d + (q0 + i) - (k0 + j)) : acc[a][bb];
+        sm.s[i][j] = keep ? silu_f(sb) * inv_n : 0.f;
       }
     __syncthreads();
     tile_sv<DH>(sm.s, sm.v, o);
@@ -149,7 +152,10 @@ __global__ void __launch_bounds__(256)
 hstu_attn_bwd_dq_kernel(const TA* __restrict__ q, const TA* __restrict__ k, const TA* __restrict__ v,
                         const TA* __restrict__ pre_q, int64_t ld, const int32_t* __restrict__ seq_off,
                         const uint8_t* __restrict__ key_valid, float inv_n, const TA* __restrict__ d_out, int D,
-                        TA* __restrict__ d_pre_q) {
+                        TA* __restrict__ d_pre_q, const float* __restrict__ bias_d, float* __restrict__ dbias_part,
+                        int max_len) {
+  // dbias_part (with bias_d): [gridDim.z * gridDim.y * gridDim.x, max_len] partial sums of dS by distance i - j, one
+  // row per block (summed afterwards in fixed order: deterministic)
   extern __shared__ __align__(16) uint8_t smem_raw[];
   AttnSmem<DH>& sm = *reinterpret_cast<AttnSmem<DH>*>(smem_raw);
   const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
@@ -182,10 +188,24 @@ hstu_attn_bwd_dq_kernel(const TA* __restrict__ q, const TA* __restrict__ k, cons
       for (int bb = 0; bb < 4; ++bb) {
         int i = ty + 16 * a, j = tx + 16 * bb;
         bool keep = (k0 + j <= q0 + i) && sm.kvalid[j];
-        sm.ds[i][j] = keep ? da[a][bb] * inv_n * silu_grad_f(s[a][bb]) : 0.f;
+        const float sb = (keep && bias_d) ? s[a][bb] + __ldg(bias_d + (q0 + i) - (k0 + j)) : s[a][bb];
+        sm.ds[i][j] = keep ? da[a][bb] * inv_n * silu_grad_f(sb) : 0.f;
       }
     __syncthreads();
     tile_sv<DH>(sm.ds, sm.k, dq);
+    if (dbias_part != nullptr) {
+      // distances of this tile pair: d = (q0 - k0) + (i - j) in [q0 - k0 - 63, q0 - k0 + 63]; thread x sums one diagonal
+      float* mine = dbias_part + (((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * max_len;
+      if (threadIdx.x < 2 * AT - 1) {
+        const int rel = (int)threadIdx.x - (AT - 1);           // i - j
+        const int d = q0 - k0 + rel;
+        if (d >= 0 && d < max_len) {
+          float acc_d = 0.f;
+          for (int i = max(0, rel); i < AT && i - rel < AT; ++i) acc_d += sm.ds[i][i - rel];
+          mine[d] += acc_d;                                    // each (block, d) is touched by one thread per key tile
+        }
+      }
+    }
   }
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
@@ -206,7 +226,8 @@ __global__ void __launch_bounds__(256)
 hstu_attn_bwd_dkv_kernel(const TA* __restrict__ q, const TA* __restrict__ k, const TA* __restrict__ v,
                          const TA* __restrict__ pre_k, const TA* __restrict__ pre_v, int64_t ld,
                          const int32_t* __restrict__ seq_off, const uint8_t* __restrict__ key_valid, float inv_n,
-                         const TA* __restrict__ d_out, int D, TA* __restrict__ d_pre_k, TA* __restrict__ d_pre_v) {
+                         const TA* __restrict__ d_out, int D, TA* __restrict__ d_pre_k, TA* __restrict__ d_pre_v,
+                         const float* __restrict__ bias_d) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   AttnSmem<DH>& sm = *reinterpret_cast<AttnSmem<DH>*>(smem_raw);
   const int b = blockIdx.z, h = blockIdx.y, kt = blockIdx.x;
@@ -240,8 +261,9 @@ hstu_attn_bwd_dkv_kernel(const TA* __restrict__ q, const TA* __restrict__ k, con
       for (int bb = 0; bb < 4; ++bb) {
         int i = ty + 16 * a, j = tx + 16 * bb;
         bool keep = (k0 + j <= q0 + i) && sm.kvalid[j] && i < nq;
-        sm.s[i][j] = keep ? silu_f(s[a][bb]) * inv_n : 0.f;
-        sm.ds[i][j] = keep ? da[a][bb] * inv_n * silu_grad_f(s[a][bb]) : 0.f;
+        const float sb = (keep && bias_d) ? s[a][bb] + __ldg(bias_d + (q0 + i) - (k0 + j)) : s[a][bb];
+        sm.s[i][j] = keep ? silu_f(sb) * inv_n : 0.f;
+        sm.ds[i][j] = keep ? da[a][bb] * inv_n * silu_grad_f(sb) : 0.f;
       }
     __syncthreads();
     tile_sTx<DH>(sm.s, sm.dout, dv);
@@ -264,13 +286,13 @@ hstu_attn_bwd_dkv_kernel(const TA* __restrict__ q, const TA* __restrict__ k, con
 template <typename TA, int DH>
 static int attn_fwd_launch(const void* q, const void* k, const void* v, int ld, const int32_t* seq_off,
                            const uint8_t* key_valid, int B, int n_heads, float inv_n, int max_len, float* out,
-                           cudaStream_t st) {
+                           const float* bias_d, cudaStream_t st) {
   size_t smem = sizeof(AttnSmem<DH>);
   { static bool once_1 = false; if (!once_1) { B200_CUDA_OK(cudaFuncSetAttribute(hstu_attn_fwd_kernel<TA, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem)); once_1 = true; } }
   dim3 grid(ceil_div_i(max_len, AT), n_heads, B);
   hstu_attn_fwd_kernel<TA, DH><<<grid, 256, smem, st>>>((const TA*)q, (const TA*)k, (const TA*)v, ld, seq_off,
-                                                        key_valid, inv_n, out, n_heads * DH);
+                                                        key_valid, inv_n, out, n_heads * DH, bias_d);
   B200_LAUNCH_OK();
   return 0;
 }
@@ -279,7 +301,7 @@ template <typename TA, int DH>
 static int attn_bwd_launch(const void* q, const void* k, const void* v, const void* pre_q, const void* pre_k,
                            const void* pre_v, int ld, const int32_t* seq_off, const uint8_t* key_valid, int B,
                            int n_heads, float inv_n, int max_len, const void* d_out, void* d_pre_q, void* d_pre_k,
-                           void* d_pre_v, cudaStream_t st) {
+                           void* d_pre_v, const float* bias_d, float* dbias_part, cudaStream_t st) {
   size_t smem = sizeof(AttnSmem<DH>);
   { static bool once_2 = false; if (!once_2) { B200_CUDA_OK(cudaFuncSetAttribute(hstu_attn_bwd_dq_kernel<TA, DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem)); once_2 = true; } }
@@ -288,11 +310,12 @@ static int attn_bwd_launch(const void* q, const void* k, const void* v, const vo
   dim3 grid(ceil_div_i(max_len, AT), n_heads, B);
   hstu_attn_bwd_dq_kernel<TA, DH><<<grid, 256, smem, st>>>((const TA*)q, (const TA*)k, (const TA*)v,
                                                            (const TA*)pre_q, ld, seq_off, key_valid, inv_n,
-                                                           (const TA*)d_out, n_heads * DH, (TA*)d_pre_q);
+                                                           (const TA*)d_out, n_heads * DH, (TA*)d_pre_q, bias_d,
+                                                           dbias_part, max_len);
   hstu_attn_bwd_dkv_kernel<TA, DH><<<grid, 256, smem, st>>>((const TA*)q, (const TA*)k, (const TA*)v,
                                                             (const TA*)pre_k, (const TA*)pre_v, ld, seq_off,
                                                             key_valid, inv_n, (const TA*)d_out, n_heads * DH,
-                                                            (TA*)d_pre_k, (TA*)d_pre_v);
+                                                            (TA*)d_pre_k, (TA*)d_pre_v, bias_d);
   B200_LAUNCH_OK();
   return 0;
 }
@@ -313,8 +336,45 @@ int b200rec_hstu_attn_fwd(const void* q, const void* k, const void* v, int ld, i
   B200_CHECK_ARG(ld % 4 == 0, "attention: ld=%d must be a multiple of 4", ld);
   DISPATCH_ACT(act_dtype, TA, {
     DISPATCH_DH(dh, DH, {
-      return attn_fwd_launch<TA, DH>(q, k, v, ld, seq_off, key_valid, B, n_heads, inv_n, max_len, out,
+      return attn_fwd_launch<TA, DH>(q, k, v, ld, seq_off, key_valid, B, n_heads, inv_n, max_len, out, nullptr,
                                      (cudaStream_t)stream);
+    });
+  });
+  return 0;
+}
+
+extern "C" int b200rec_hstu_attn_bias_fwd(const void* q, const void* k, const void* v, int ld, int act_dtype,
+                                          const int32_t* seq_off, const uint8_t* key_valid, int B, int T, int n_heads,
+                                          int dh, float inv_n, int max_len, const float* bias_d, float* out,
+                                          void* stream) {
+  if (T == 0 || B == 0) return 0;
+  B200_CHECK_ARG(ld % 4 == 0 && bias_d != nullptr, "attention(bias): ld=%d must be a multiple of 4, bias_d non-null", ld);
+  DISPATCH_ACT(act_dtype, TA, {
+    DISPATCH_DH(dh, DH, {
+      return attn_fwd_launch<TA, DH>(q, k, v, ld, seq_off, key_valid, B, n_heads, inv_n, max_len, out, bias_d,
+                                     (cudaStream_t)stream);
+    });
+  });
+  return 0;
+}
+
+extern "C" size_t b200rec_hstu_attn_bias_ws_floats(int B, int n_heads, int max_len) {
+  return (size_t)B * n_heads * ((max_len + AT - 1) / AT) * max_len;
+}
+
+// backward with the relative position bias: also returns dbias_part [B * n_heads * ceil(max_len / 64), max_len]
+// (ZERO-FILLED by the caller); d bias_d[d] = column sums of it.
+extern "C" int b200rec_hstu_attn_bias_bwd(const void* q, const void* k, const void* v, const void* pre_q,
+                                          const void* pre_k, const void* pre_v, int ld, int act_dtype,
+                                          const int32_t* seq_off, const uint8_t* key_valid, int B, int T, int n_heads,
+                                          int dh, float inv_n, int max_len, const float* bias_d, const void* d_out,
+                                          void* d_pre_q, void* d_pre_k, void* d_pre_v, float* dbias_part, void* stream) {
+  if (T == 0 || B == 0) return 0;
+  B200_CHECK_ARG(ld % 4 == 0 && bias_d != nullptr && dbias_part != nullptr, "attention(bias) bwd: bad args");
+  DISPATCH_ACT(act_dtype, TA, {
+    DISPATCH_DH(dh, DH, {
+      return attn_bwd_launch<TA, DH>(q, k, v, pre_q, pre_k, pre_v, ld, seq_off, key_valid, B, n_heads, inv_n, max_len,
+                                     d_out, d_pre_q, d_pre_k, d_pre_v, bias_d, dbias_part, (cudaStream_t)stream);
     });
   });
   return 0;
@@ -329,7 +389,7 @@ int b200rec_hstu_attn_bwd(const void* q, const void* k, const void* v, const voi
   DISPATCH_ACT(act_dtype, TA, {
     DISPATCH_DH(dh, DH, {
       return attn_bwd_launch<TA, DH>(q, k, v, pre_q, pre_k, pre_v, ld, seq_off, key_valid, B, n_heads, inv_n,
-                                     max_len, d_out, d_pre_q, d_pre_k, d_pre_v, (cudaStream_t)stream);
+                                     max_len, d_out, d_pre_q, d_pre_k, d_pre_v, nullptr, nullptr, (cudaStream_t)stream);
     });
   });
   return 0;

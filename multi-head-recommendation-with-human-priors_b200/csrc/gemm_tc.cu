@@ -215,9 +215,54 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
       // GT_BITS: ONE warp per lane quarter converts all chunks of its rows, so that a lane owns BN / 32 consecutive
       // words (32 bytes at BN = 256 = one full sector); alternating chunks between the two warps of a quarter made every
       // 4-byte word a partial-sector write 1 KB away from its neighbours and the K = 64 filter GEMM store-bound
-      uint32_t gt_words[8];
-      for (int c = (MODE == B200REC_EPI_GT_BITS ? 0 : half); c < p.BN / 32; c += (MODE == B200REC_EPI_GT_BITS ? 1 : 2)) {
-        if (MODE == B200REC_EPI_GT_BITS && half == 1) break;
+      if (MODE == B200REC_EPI_GT_BITS) {
+        // each warp converts BN / 64 CONSECUTIVE 32-column chunks of its rows: all TMEM loads are issued before one wait
+        // (the K = 64 filter GEMM is epilogue-latency bound), and a lane ends up with 2-4 consecutive words = one 8 / 16
+        // byte store instead of scattered 4-byte words
+        const int nch = p.BN / 64;                                   // 2 (BN = 128) or 4 (BN = 256)
+        const int m = m0 + quarter * 32 + lane;
+        uint32_t rr[4][32];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < nch) tmem_ld_32x32_nowait(t_row + (uint32_t)(half * nch + q) * 32u, rr[q]);
+        tmem_ld_wait();
+        const float ra = (ep.gt_row != nullptr && m < ep.M) ? __ldg(ep.gt_row + m) : 0.f;
+        uint32_t words[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (q >= nch) continue;
+          const int nn = n0 + (half * nch + q) * 32;
+          uint32_t wbits = 0;
+          if (nn < ep.N) {
+            if (ep.gt_row != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float cb = nn + i < ep.N ? __ldg(ep.gt_col + nn + i) : 0.f;
+                wbits |= (fmaf(ra, cb, __uint_as_float(rr[q][i])) > ep.alpha) ? (1u << i) : 0u;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) wbits |= (__uint_as_float(rr[q][i]) > ep.alpha) ? (1u << i) : 0u;
+            }
+            if (nn + 32 > ep.N) wbits &= (1u << (ep.N - nn)) - 1u;
+          }
+          words[q] = wbits;
+        }
+        if (m < ep.M) {
+          const int w0 = (n0 >> 5) + half * nch;
+          const int n_words_row = (ep.N + 31) >> 5;
+          uint32_t* dst = (uint32_t*)ep.C + (int64_t)m * ep.ldc + w0;
+          if (nch == 4 && w0 + 4 <= n_words_row && (ep.ldc & 3) == 0 && (((uintptr_t)ep.C) & 15) == 0) {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(words[0], words[1], words[2], words[3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (q < nch && w0 + q < n_words_row) dst[q] = words[q];
+          }
+          if ((words[0] | words[1] | words[2] | words[3]) != 0u && ep.C2) ((uint8_t*)ep.C2)[m] = 1;
+        }
+      }
+      for (int c = half; c < p.BN / 32 && MODE != B200REC_EPI_GT_BITS; c += 2) {
         float v[32];
         tmem_ld_32x32(t_row + (uint32_t)c * 32u, v);
         if (MODE == B200REC_EPI_NCE_EXP) {
@@ -235,44 +280,6 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
             nce_gt += (nn + i < ep.N && cosv > nce_thr) ? 1.f : 0.f;
             v[i] = e;
           }
-        }
-        if (MODE == B200REC_EPI_GT_BITS) {
-          uint32_t wbits = 0;
-          const int m = m0 + quarter * 32 + lane, nn = n0 + c * 32;
-          if (ep.gt_row != nullptr) {             // upper-bound variant: prefix product + product of the tail norms
-            const float ra = m < ep.M ? __ldg(ep.gt_row + m) : 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float cb = nn + i < ep.N ? __ldg(ep.gt_col + nn + i) : 0.f;
-              wbits |= (fmaf(ra, cb, v[i]) > ep.alpha) ? (1u << i) : 0u;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) wbits |= (v[i] > ep.alpha) ? (1u << i) : 0u;
-          }
-          if (nn >= ep.N) wbits = 0u;
-          else if (nn + 32 > ep.N) wbits &= (1u << (ep.N - nn)) - 1u;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) gt_words[q] = (c == q) ? wbits : gt_words[q];   // static register indices
-          if (m < ep.M && wbits != 0u && ep.C2) ((uint8_t*)ep.C2)[m] = 1;
-          if (c == p.BN / 32 - 1 && m < ep.M) {
-            // words [n0/32, n0/32 + BN/32) of row m: 16-byte stores where the row pitch allows it
-            uint32_t* dst = (uint32_t*)ep.C + (int64_t)m * ep.ldc + (n0 >> 5);
-            const int nw_tile = p.BN / 32;
-            const int nw_valid = min(nw_tile, (int)((ep.N - n0 + 31) >> 5));
-            if (nw_valid == nw_tile && (ep.ldc & 3) == 0 && (((uintptr_t)ep.C) & 15) == 0) {
-#pragma unroll
-              for (int q = 0; q < 2; ++q)
-                if (q * 4 < nw_tile)
-                  *reinterpret_cast<uint4*>(dst + q * 4) = make_uint4(gt_words[q * 4], gt_words[q * 4 + 1],
-                                                                      gt_words[q * 4 + 2], gt_words[q * 4 + 3]);
-            } else {
-#pragma unroll
-              for (int q = 0; q < 8; ++q)
-                if (q < nw_valid) dst[q] = gt_words[q];
-            }
-          }
-          continue;
         }
         // phase 1: lane owns row `lane`; 16-byte chunk q goes to physical chunk q ^ (lane & 7)
 #pragma unroll

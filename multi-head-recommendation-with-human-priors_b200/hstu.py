@@ -124,6 +124,11 @@ class HSTU(nn.Module):
             raise NotImplementedError("only hidden_act='silu' is built")
         self._linear_dropout_rate = config["hidden_dropout_prob"] or 0.0
         self._enable_relative_attention_bias = bool(config["enable_relative_attention_bias"])
+        # The reference builds the bias module and never applies it: parity = OFF.  This flag applies
+        # the position part, silu(q k^T + pos_w[N - 1 - (i - j)] + ts_w[0]) / n (timestamps are not part of the batch, so
+        # every pair falls into time bucket 0), through the SIMT attention kernels.
+        self.apply_rel_bias = bool(config.get("apply_relative_attention_bias", False)) and \
+            self._enable_relative_attention_bias
         # ---- parameters, created in the reference's order (hstu.py:380-425, 486-493) ----
         self.position_embedding = nn.Embedding(self.max_seq_length + 1, D)
         blocks = []
@@ -227,6 +232,7 @@ class HSTU(nn.Module):
         self.emb_grad = None       # (uniq_ids, uniq_rows, n_uniq) of the last backward
         self._table_cache = None   # normalised compute-dtype item table for predict
         self._verbose = False
+        self._switch_logs = {}
         self._debug = None         # dict: when set, forward / backward stash clones of key intermediates (diagnostics)
         self.reset_params()
         self._jobs = self._build_jobs()
@@ -479,7 +485,18 @@ class HSTU(nn.Module):
                    epilogue=L.EPI_SILU_DUAL, C2=pre, ldc2=4 * D)
             a = torch.empty((T, D), dtype=torch.float32, device=dev)
             u, v, q, k = actv[:, 0:D], actv[:, D:2 * D], actv[:, 2 * D:3 * D], actv[:, 3 * D:4 * D]
-            if self._tc_attention() and max_len <= 64:
+            bias_d = None
+            if self.apply_rel_bias:
+                rb = blk._rel_attn_bias
+                n_b = max(max_len, self._simt_len)
+                Nrb = (rb._pos_w.numel() + 1) // 2                      # module length N: pos_w has 2N - 1 entries
+                bias_d = torch.zeros(n_b, dtype=torch.float32, device=dev)
+                dd = torch.arange(min(n_b, Nrb), device=dev)
+                bias_d[:dd.numel()] = rb._pos_w.data[Nrb - 1 - dd] + rb._ts_w.data[0]
+                L.call("b200rec_hstu_attn_bias_fwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), 4 * D, a_dt,
+                       seq_off.data_ptr(), key_valid.data_ptr(), B, T, nh, dh, 1.0 / n_pad, n_b, bias_d.data_ptr(),
+                       a.data_ptr(), st)
+            elif self._tc_attention() and max_len <= 64:
                 L.call("b200rec_hstu_attn_seq_fwd", actv.data_ptr(), 4 * D, seq_off.data_ptr(), key_valid.data_ptr(), B,
                        T, nh, dh, 1.0 / n_pad, max_len, a.data_ptr(), st)
             elif self._tc_attention():
@@ -500,7 +517,7 @@ class HSTU(nn.Module):
             L.gemm(oin, w[f"o{i}"], x_next, T, D, D, lda=D, ldb=D, ldc=D, epilogue=L.EPI_BIAS_RESID,
                    bias=blk._o.bias.data, resid=x, ldr=D)
             if save:
-                saved.append((x, mean1, rstd1, n, actv, pre, a, mean2, rstd2, oin))
+                saved.append((x, mean1, rstd1, n, actv, pre, a, mean2, rstd2, oin, bias_d))
             x = x_next
         return x, saved
 
@@ -516,7 +533,7 @@ class HSTU(nn.Module):
         dxb = None   # act-dtype copy of dx: written by the previous block's LayerNorm backward
         for i in reversed(range(self._num_blocks)):
             blk = self._hstu._attention_layers[i]
-            x, mean1, rstd1, n, actv, pre, a, mean2, rstd2, oin = saved[i]
+            x, mean1, rstd1, n, actv, pre, a, mean2, rstd2, oin, bias_d = saved[i]
             if act == torch.float32:
                 dxb = dx
             elif dxb is None:
@@ -536,7 +553,26 @@ class HSTU(nn.Module):
                    mean2.data_ptr(), rstd2.data_ptr(), T, D, d_pre.data_ptr(), da.data_ptr(), a_dt, drop_p,
                    self.dropout_seed, i, L.ptr(self._rng_step), st)
             sl = lambda t, j: t[:, j * D:(j + 1) * D]
-            if self._tc_attention() and max_len <= 64:
+            if bias_d is not None:
+                n_b = bias_d.numel()
+                nws = L.lib().b200rec_hstu_attn_bias_ws_floats(B, nh, n_b)
+                part = torch.zeros((nws // n_b, n_b), dtype=torch.float32, device=dev)
+                L.call("b200rec_hstu_attn_bias_bwd", sl(actv, 2).data_ptr(), sl(actv, 3).data_ptr(), sl(actv, 1).data_ptr(),
+                       sl(pre, 2).data_ptr(), sl(pre, 3).data_ptr(), sl(pre, 1).data_ptr(), 4 * D, a_dt,
+                       seq_off.data_ptr(), key_valid.data_ptr(), B, T, nh, dh, 1.0 / n_pad, n_b, bias_d.data_ptr(),
+                       da.data_ptr(), sl(d_pre, 2).data_ptr(), sl(d_pre, 3).data_ptr(), sl(d_pre, 1).data_ptr(),
+                       part.data_ptr(), st)
+                dbias = torch.empty(n_b, dtype=torch.float32, device=dev)
+                L.colsum(part, part.shape[0], n_b, n_b, dbias)
+                rb = blk._rel_attn_bias
+                Nrb = (rb._pos_w.numel() + 1) // 2
+                dpw = torch.zeros_like(rb._pos_w.data)
+                dd = torch.arange(min(n_b, Nrb), device=dev)
+                dpw[Nrb - 1 - dd] = dbias[:dd.numel()]
+                dts = torch.zeros_like(rb._ts_w.data)
+                dts[0] = dbias[:dd.numel()].sum()
+                grads[rb._pos_w], grads[rb._ts_w] = dpw, dts
+            elif self._tc_attention() and max_len <= 64:
                 L.call("b200rec_hstu_attn_seq_bwd", actv.data_ptr(), pre.data_ptr(), 4 * D, seq_off.data_ptr(),
                        key_valid.data_ptr(), B, T, nh, dh, 1.0 / n_pad, max_len, da.data_ptr(), d_pre.data_ptr(), st)
             elif self._tc_attention():
@@ -1283,6 +1319,7 @@ class HSTU(nn.Module):
         """head_cat[H] (category whose item tags gate head h, -1 none), item_tag_bits[N] (bit c = tag c),
         head_on[B, H] (prior_given_at_test), per hstu.py:982-999."""
         H, S, C = self.medusa_num_heads, self.num_segment_head, self.num_prior_head
+        self._switch_logs = {}
         if self.loss != "prior":
             return None, None, None
         if self.head_interaction == "additive":

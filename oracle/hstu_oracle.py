@@ -47,9 +47,19 @@ def ln(x):
     return F.layer_norm(x, [x.shape[-1]], eps=LN_EPS)
 
 
-def hstu_block(x, keep, w_uvqk, w_o, b_o, n_heads):
+def rel_pos_bias(pos_w, ts_w, L):
+    """The position part of RelativeBucketedTimeAndPositionBasedBias.forward (hstu.py:99-134) for all-equal timestamps:
+    bias[i, j] = pos_w[N - 1 + (j - i)] + ts_w[bucket 0], N = (len(pos_w) + 1) / 2, cropped to [L, L].  The reference
+    never applies it; `apply_relative_attention_bias` turns it on in both oracle and CUDA path and is
+    pinned against the LIVE module's forward in tests/test_oracle_vs_reference.py."""
+    N = (pos_w.numel() + 1) // 2
+    i = torch.arange(L)
+    return pos_w[N - 1 + (i[None, :] - i[:, None])] + ts_w[0]                 # [L, L]
+
+
+def hstu_block(x, keep, w_uvqk, w_o, b_o, n_heads, bias=None):
     """One HSTU block (hstu.py:221-290 + 137-160), dropout off.
-    x [B,L,D]; keep bool [B,1,L,L] (hstu.py:1023-1028)."""
+    x [B,L,D]; keep bool [B,1,L,L] (hstu.py:1023-1028).  bias: optional [L, L] added to q k^T before SiLU."""
     B, L, D = x.shape
     dh = D // n_heads
     z = F.silu(ln(x) @ w_uvqk)                       # :241-245 (no bias)
@@ -57,7 +67,10 @@ def hstu_block(x, keep, w_uvqk, w_o, b_o, n_heads):
     qh = q.reshape(B, L, n_heads, dh).permute(0, 2, 1, 3)
     kh = k.reshape(B, L, n_heads, dh).permute(0, 2, 1, 3)
     vh = v.reshape(B, L, n_heads, dh).permute(0, 2, 1, 3)
-    a = F.silu(qh @ kh.transpose(-1, -2)) / L         # :148-153, divides by PADDED length
+    sc = qh @ kh.transpose(-1, -2)
+    if bias is not None:
+        sc = sc + bias
+    a = F.silu(sc) / L                                # :148-153, divides by PADDED length
     a = a * keep.to(a.dtype)                          # :154
     o = (a @ vh).permute(0, 2, 1, 3).reshape(B, L, D)  # :155-159
     return (u * ln(o)) @ w_o.t() + b_o + x            # :277-288
@@ -147,8 +160,11 @@ class OracleHSTU:
         keep = causal_keep(valid)
         for i in range(self.n_layers):                                            # :322-326
             pre = f"_hstu._attention_layers.{i}."
+            bias = None
+            if cfg_get(self.cfg, "apply_relative_attention_bias", False) and (pre + "_rel_attn_bias._pos_w") in self.p:
+                bias = rel_pos_bias(self.p[pre + "_rel_attn_bias._pos_w"], self.p[pre + "_rel_attn_bias._ts_w"], x.shape[1])
             x = hstu_block(x, keep, self.p[pre + "_uvqk"], self.p[pre + "_o.weight"],
-                           self.p[pre + "_o.bias"], self.n_heads)
+                           self.p[pre + "_o.bias"], self.n_heads, bias)
         return x
 
     def heads(self, y):

@@ -523,3 +523,44 @@ def test_streamed_eval_equals_materialised(H, cats):
     i2, v2, h2 = model.predict_topk(*args, **kw)
     assert used_streamed != L.launches - n0                       # the streamed path really ran (3 stages vs 1)
     assert torch.equal(i1, i2) and torch.equal(v1, v2) and torch.equal(h1, h2)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, None)], ids=["f32", "bf16"])
+def test_relative_position_bias_flag_matches_oracle(dtype, tol):
+    """north_star (b): 'with relative position/time bias'.  The reference never applies its bias module, so parity runs
+    keep it off; with config['apply_relative_attention_bias'] the CUDA path adds pos_w[N-1-(i-j)] + ts_w[0] to q k^T
+    (oracle: hstu_oracle.rel_pos_bias, pinned against the live module) and trains _pos_w / _ts_w."""
+    from oracle import hstu_oracle as orc
+    fx = load_golden("prior_mult")
+    cfg = synth.Config(fx["cfg"])
+    cfg["apply_relative_attention_bias"] = True
+    dl = synth.Dataload(cfg["item_num"], fx["category_counts"], fx["category_to_int"])
+    sd = {k: v.detach().clone() for k, v in fx["state_dict"].items()}
+    g = torch.Generator().manual_seed(3)
+    for k in sd:                                       # make the bias matter: std 0.02 -> 0.5
+        if "_rel_attn_bias" in k:
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.5
+    sdo = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    ref = orc.OracleHSTU(cfg, sdo, dl.category_counts, dl.category_to_int).forward(fx["train_batch"])
+    ref["loss"].backward()
+    assert abs(float(ref["loss"]) - fx["loss"]) > 1e-3          # the flag changes the function
+    m = HSTU(cfg, dl, compute_dtype=dtype)
+    m.load_state_dict(sd)
+    m = m.to(dev()).eval()
+    out = m(to_dev(fx["train_batch"]))
+    out["loss"].backward()
+    ltol = 2e-5 if dtype == torch.float32 else 1e-2
+    assert abs(float(out["loss"]) - float(ref["loss"])) <= ltol * abs(float(ref["loss"]))
+    for k, p in m.named_parameters():
+        r = sdo[k].grad
+        if r is None:
+            assert p.grad is None, k
+            continue
+        assert p.grad is not None, k
+        gq = p.grad.cpu()
+        if tol is not None:
+            assert (gq - r).abs().max().item() <= tol * max(1e-6, r.abs().max().item()), k
+        elif r.numel() > 1 and r.abs().max() > 0:
+            cos = float((gq.double().flatten() @ r.double().flatten()) / (gq.double().norm() * r.double().norm() + 1e-30))
+            assert cos > 0.99, (k, cos)
+    assert m._hstu._attention_layers[0]._rel_attn_bias._pos_w.grad.abs().sum() > 0

@@ -43,3 +43,20 @@ def test_train_step_matches_reference(preset, over):
     for k in out:
         if k != "loss":
             assert abs(float(out[k]) - float(o2[k])) < 1e-5, k
+
+
+def test_relative_position_bias_matches_live_module():
+    """the bias the reference BUILDS (and never applies, hstu.py:221-290) — the oracle's restatement of its
+    position part equals RelativeBucketedTimeAndPositionBasedBias.forward (hstu.py:99-134) for equal timestamps."""
+    import torch
+    from oracle import ref_harness as rh, hstu_oracle as orc
+    if not rh.available():
+        import pytest
+        pytest.skip("reference tree not mounted")
+    rh.load()
+    from REC.model.IDNet.hstu import RelativeBucketedTimeAndPositionBasedBias as RB
+    for N, L in ((24, 12), (100, 50)):
+        m = RB(max_seq_len=N, num_buckets=128,
+               bucketization_fn=lambda x: (torch.log(torch.abs(x).clamp(min=1)) / 0.301).long())
+        ref = m(torch.zeros(2, N, dtype=torch.long))[0, :L, :L]
+        assert torch.equal(ref, orc.rel_pos_bias(m._pos_w.data, m._ts_w.data, L))
