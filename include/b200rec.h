@@ -217,6 +217,9 @@ int b200rec_gemm_nce_parts(int N);
  * gt_bits_verify recomputes the full fp32 dot product of each marked pair, clears the bits that fail and sets
  * row_any[m] = 1 for rows that keep a bit (zero row_any first). */
 int b200rec_tail_norm(const void* x_hat, int64_t n, int D, int k0, float* out, void* stream);
+/* Same bound without an epilogue term: out bf16 [n, k0 + 16] = (x_hat[:, :k0], tail norm rounded UP to bf16, 15 zeros);
+ * a plain GT_BITS GEMM of two such operands (K = k0 + 16) computes prefix product + |tail_a| |tail_b| on the tensor cores. */
+int b200rec_prefix_aug(const void* x_hat, int64_t n, int D, int k0, void* out, void* stream);
 int b200rec_gt_bits_verify(uint32_t* bits, int64_t M, int n_words, int N, const void* a_hat, const void* b_hat, int D,
                            float thres, uint8_t* row_any, void* stream);
 /* n_groups independent problems args[0..n_groups).  Problems of identical shape / layout / dtypes with a

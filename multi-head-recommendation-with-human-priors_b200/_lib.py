@@ -108,6 +108,7 @@ _SIGS = {
     "b200rec_switch_pos_grad": (C.c_int, [_P, _I, _I, _I, _I, _P, _P]),
     "b200rec_gemm_nce_parts": (C.c_int, [_I]),
     "b200rec_tail_norm": (C.c_int, [_P, _L, _I, _I, _P, _P]),
+    "b200rec_prefix_aug": (C.c_int, [_P, _L, _I, _I, _P, _P]),
     "b200rec_gt_bits_verify": (C.c_int, [_P, _L, _I, _I, _P, _P, _I, _F, _P, _P]),
     "b200rec_nce_pos_ref": (C.c_int, [_P, _L, _P, _I, _P, _P, _I, _I, _I, C.c_uint32, _P, _I, _I, _P, _P, _P, _P, _P]),
     "b200rec_nce_combine": (C.c_int, [_P, _I, _P, _L, _I, _P, _P, _P, _P, _P, _L, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P,

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(128) attn_seq_fwd_kernel(const bf16* __restric
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       int i = i0 + g + (e >> 1) * 8, j = nt * 8 + 2 * t + (e & 1);
-      a[e] = (j <= i && kv[j]) ? silu_f(s[nt][e]) * inv_n : 0.f;
+      a[e] = (j <= i && kv[j]) ? silu_fast_f(s[nt][e]) * inv_n : 0.f;
     }
     p[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(a[0], a[1]);
     p[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(a[2], a[3]);
@@ -197,8 +197,8 @@ __device__ __forceinline__ void store_dpre(const float (&acc)[DH / 8][4], const 
 #pragma unroll
     for (int nt = 0; nt < DH / 8; ++nt) {
       __nv_bfloat162 zz = *reinterpret_cast<__nv_bfloat162*>(&z[nt]);
-      float lo = acc[nt][half * 2 + 0] * silu_grad_f(__low2float(zz));
-      float hi = acc[nt][half * 2 + 1] * silu_grad_f(__high2float(zz));
+      float lo = acc[nt][half * 2 + 0] * silu_grad_fast_f(__low2float(zz));
+      float hi = acc[nt][half * 2 + 1] * silu_grad_fast_f(__high2float(zz));
       *reinterpret_cast<uint32_t*>(dpre + (int64_t)r * ld + nt * 8 + 2 * t) = pack_bf16(lo, hi);
     }
   }
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(128) attn_seq_bwd_kernel(const bf16* __restric
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         int i = r0 + g + (e >> 1) * 8, j = nt * 8 + 2 * t + (e & 1);
-        a[e] = (j <= i && kv[j]) ? y[nt][e] * silu_grad_f(x[nt][e]) * inv_n : 0.f;
+        a[e] = (j <= i && kv[j]) ? y[nt][e] * silu_grad_fast_f(x[nt][e]) * inv_n : 0.f;
       }
       p[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(a[0], a[1]);
       p[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(a[2], a[3]);
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(128) attn_seq_bwd_kernel(const bf16* __restric
       for (int e = 0; e < 4; ++e) {
         int j = r0 + g + (e >> 1) * 8, i = nt * 8 + 2 * t + (e & 1);
         bool on = (j <= i) && kv[j] && (i < n);
-        float sg = sigmoid_f(x[nt][e]);
+        float sg = sigmoid_fast_f(x[nt][e]);
         a[e] = on ? x[nt][e] * sg * inv_n : 0.f;
         ds[e] = on ? y[nt][e] * sg * (1.f + x[nt][e] * (1.f - sg)) * inv_n : 0.f;
       }

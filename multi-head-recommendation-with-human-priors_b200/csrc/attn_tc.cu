@@ -168,7 +168,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
       for (int e = 0; e < 32; ++e) {
         const int tj = c0 + e;
         const bool keep = (tj <= ti) && (tj >= my_start) && s_kvalid[c * 32 + e];
-        v[e] = keep ? silu_f(v[e]) * inv_n : 0.f;
+        v[e] = keep ? silu_fast_f(v[e]) * inv_n : 0.f;
       }
       put_row32_sw128(sP, 128, tid, c * 32, v);
     }
@@ -288,7 +288,7 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap map128, const __grid_c
       for (int e = 0; e < 32; ++e) {
         const int tj = k0 + c * 32 + e;
         const bool keep = (tj <= ti) && (tj >= my_start) && s_kvalid[c * 32 + e];
-        s[e] = keep ? da[e] * inv_n * silu_grad_f(s[e]) : 0.f;
+        s[e] = keep ? da[e] * inv_n * silu_grad_fast_f(s[e]) : 0.f;
       }
       put_row32_sw128(sdS, 128, tid, c * 32, s);
     }
@@ -316,7 +316,7 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap map128, const __grid_c
         float p4[4], o4[4];
         load4<bf16>(pre_q + off + 4 * e, p4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) o4[k] = v[4 * e + k] * silu_grad_f(p4[k]);
+        for (int k = 0; k < 4; ++k) o4[k] = v[4 * e + k] * silu_grad_fast_f(p4[k]);
         store4<bf16>(d_pre_q + off + 4 * e, o4);
       }
     }
@@ -414,8 +414,9 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map128, const __grid_
         const int tq = i0 + c * 32 + e;
         const bool keep = kv_ok && (tj <= tq) && (tj >= s_qstart[c * 32 + e]);
         const float sv = s[e];
-        s[e] = keep ? silu_f(sv) * inv_n : 0.f;                       // P^T
-        da[e] = keep ? da[e] * inv_n * silu_grad_f(sv) : 0.f;         // dS^T
+        const float sg = sigmoid_fast_f(sv);                          // ONE MUFU for both P^T and dS^T
+        s[e] = keep ? sv * sg * inv_n : 0.f;                          // P^T
+        da[e] = keep ? da[e] * inv_n * sg * fmaf(sv, 1.f - sg, 1.f) : 0.f;   // dS^T
       }
       put_row32_sw128(sPT, 128, tid, c * 32, s);
       put_row32_sw128(sdST, 128, tid, c * 32, da);
@@ -448,11 +449,11 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map128, const __grid_
         float p4[4], o4[4];
         load4<bf16>(pre_k + off + 4 * e, p4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) o4[k] = gk[4 * e + k] * silu_grad_f(p4[k]);
+        for (int k = 0; k < 4; ++k) o4[k] = gk[4 * e + k] * silu_grad_fast_f(p4[k]);
         store4<bf16>(d_pre_k + off + 4 * e, o4);
         load4<bf16>(pre_v + off + 4 * e, p4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) o4[k] = gv[4 * e + k] * silu_grad_f(p4[k]);
+        for (int k = 0; k < 4; ++k) o4[k] = gv[4 * e + k] * silu_grad_fast_f(p4[k]);
         store4<bf16>(d_pre_v + off + 4 * e, o4);
       }
     }

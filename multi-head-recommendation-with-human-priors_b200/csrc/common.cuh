@@ -49,6 +49,17 @@ __device__ __forceinline__ float silu_fast_f(float z) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
   return 0.5f * z * (1.f + t);
 }
+// one-MUFU sigmoid / silu' for the bf16 attention kernels, where the pointwise SiLU of every score is the bound (two MUFU
+// per score cap dh = 64 attention at 1/4 of the tensor peak): sigmoid(z) = (1 + tanh(z/2)) / 2
+__device__ __forceinline__ float sigmoid_fast_f(float z) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+  return fmaf(0.5f, t, 0.5f);
+}
+__device__ __forceinline__ float silu_grad_fast_f(float z) {
+  const float s = sigmoid_fast_f(z);
+  return s * fmaf(z, 1.f - s, 1.f);
+}
 __device__ __forceinline__ float silu_grad_f(float z) {
   float s = sigmoid_f(z);
   return s * (1.f + z * (1.f - s));

@@ -943,6 +943,46 @@ __global__ void __launch_bounds__(256) tail_norm_kernel(const bf16* __restrict__
   if (lane == 0) out[r] = sqrtf(ss) * (1.f + 1e-6f);     // never below the true norm of the rounded row
 }
 
+// Augmented prefix operand of the pruned filter: out[r, 0:k0] = x[r, 0:k0], out[r, k0] = |x[r, k0:]| rounded UP to bf16,
+// out[r, k0+1 : k0+16] = 0.  The K = k0 + 16 GEMM of two such operands is  <prefixes> + |tail_a| |tail_b|  — the
+// Cauchy-Schwarz upper bound of the full cosine — straight out of the tensor cores: the plain GT_BITS epilogue applies
+// (a per-column factor in the epilogue cost more than the whole K = 64 GEMM).
+__global__ void __launch_bounds__(256) prefix_aug_kernel(const bf16* __restrict__ x, int64_t n, int D4, int k04,
+                                                         bf16* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n) return;
+  float ss = 0.f;
+  for (int c = k04 + lane; c < D4; c += 32) {
+    float v[4];
+    load4<bf16>(x + (r * D4 + c) * 4, v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ss = fmaf(v[k], v[k], ss);
+  }
+  ss = warp_sum(ss);
+  const int ko4 = k04 + 4;                                  // output row: k0 + 16 elements
+  for (int c = lane; c < ko4; c += 32) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c < k04) load4<bf16>(x + (r * D4 + c) * 4, v);
+    store4<bf16>(out + (r * ko4 + c) * 4, v);
+  }
+  if (lane == 0) {
+    // round up: the smallest bf16 >= the fp32 norm (so the product of two rounded norms bounds the true product)
+    const float nrm = sqrtf(ss) * (1.f + 1e-6f);
+    uint32_t u = __float_as_uint(nrm);
+    if (u & 0xffffu) u = (u | 0xffffu) + 1u;                // next multiple of 2^16 (positive floats: monotone)
+    out[r * ko4 * 4 + (int64_t)k04 * 4] = __float2bfloat16_rn(__uint_as_float(u));
+  }
+}
+
+extern "C" int b200rec_prefix_aug(const void* x_hat, int64_t n, int D, int k0, void* out, void* stream) {
+  B200_CHECK_ARG(D % 4 == 0 && k0 % 16 == 0 && k0 >= 16 && k0 < D, "prefix_aug: bad D / k0");
+  if (n == 0) return 0;
+  prefix_aug_kernel<<<ceil_div_i(n, 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)x_hat, n, D / 4, k0 / 4, (bf16*)out);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
 extern "C" int b200rec_tail_norm(const void* x_hat, int64_t n, int D, int k0, float* out, void* stream) {
   B200_CHECK_ARG(D % 4 == 0 && k0 % 4 == 0 && k0 >= 0 && k0 <= D, "tail_norm: bad D / k0");
   if (n == 0) return 0;

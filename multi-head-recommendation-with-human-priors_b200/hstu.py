@@ -855,8 +855,8 @@ class HSTU(nn.Module):
         nhat, ninv, bits, row_any = {}, {}, {}, {}
         prune_k0 = 64 if (act == torch.bfloat16 and self.use_pruned_filter and D >= 256 and D <= 2048) else 0
         if prune_k0:
-            t_tail = torch.empty(B * LP, dtype=torch.float32, device=dev)
-            L.call("b200rec_tail_norm", that.data_ptr(), B * LP, D, prune_k0, t_tail.data_ptr(), st)
+            t_aug = torch.empty((B * LP, prune_k0 + 16), dtype=act, device=dev)
+            L.call("b200rec_prefix_aug", that.data_ptr(), B * LP, D, prune_k0, t_aug.data_ptr(), st)
         for s in used_sets:
             nh_ = torch.empty((n_neg, D), dtype=act, device=dev)
             ni_ = torch.empty(n_neg, dtype=torch.float32, device=dev)
@@ -868,10 +868,10 @@ class HSTU(nn.Module):
             if prune_k0:
                 # exact, ~16x fewer FLOPs: cos <= <prefix of k0 dims> + |tail_t| |tail_n| (Cauchy-Schwarz) marks the pairs
                 # that CAN pass; the full dot product is recomputed only for those (duplicates of a target)
-                tn_ = torch.empty(n_neg, dtype=torch.float32, device=dev)
-                L.call("b200rec_tail_norm", nh_.data_ptr(), n_neg, D, prune_k0, tn_.data_ptr(), st)
-                L.gemm(that, nh_, bt, B * LP, n_neg, prune_k0, lda=D, ldb=D, ldc=n_words, epilogue=L.EPI_GT_BITS,
-                       alpha=float(self.nce_thres) - 1e-5, gt=(t_tail, tn_))
+                n_aug = torch.empty((n_neg, prune_k0 + 16), dtype=act, device=dev)
+                L.call("b200rec_prefix_aug", nh_.data_ptr(), n_neg, D, prune_k0, n_aug.data_ptr(), st)
+                L.gemm(t_aug, n_aug, bt, B * LP, n_neg, prune_k0 + 16, lda=prune_k0 + 16, ldb=prune_k0 + 16, ldc=n_words,
+                       epilogue=L.EPI_GT_BITS, alpha=float(self.nce_thres) - 1e-5)
                 L.call("b200rec_gt_bits_verify", bt.data_ptr(), B * LP, n_words, n_neg, that.data_ptr(), nh_.data_ptr(), D,
                        float(self.nce_thres), ra.data_ptr(), st)
             else:

@@ -206,10 +206,23 @@ def test_pruned_false_negative_filter_equals_full_product(M, N, D):
     cand = int(sum(bin(x & 0xffffffff).count("1") for x in pr.flatten().tolist())) if M * n_words < 50000 else None
     L.call("b200rec_gt_bits_verify", pr.data_ptr(), M, n_words, N, a.data_ptr(), b.data_ptr(), D, thres, ra.data_ptr(),
            L.stream())
+    # production variant: the bound comes out of the tensor cores (operands augmented with the rounded-up tail norm)
+    a_aug = torch.empty((M, 80), dtype=torch.bfloat16, device=DEV)
+    b_aug = torch.empty((N, 80), dtype=torch.bfloat16, device=DEV)
+    L.call("b200rec_prefix_aug", a.data_ptr(), M, D, 64, a_aug.data_ptr(), L.stream())
+    L.call("b200rec_prefix_aug", b.data_ptr(), N, D, 64, b_aug.data_ptr(), L.stream())
+    assert torch.equal(a_aug[:, :64], a[:, :64]) and (a_aug[:, 65:] == 0).all()
+    assert (a_aug[:, 64].float() >= a[:, 64:].float().norm(dim=1)).all()           # rounded UP
+    pr2 = torch.empty((M, n_words), dtype=torch.int32, device=DEV)
+    ra2 = torch.zeros(M, dtype=torch.uint8, device=DEV)
+    L.gemm(a_aug, b_aug, pr2, M, N, 80, lda=80, ldb=80, ldc=n_words, epilogue=L.EPI_GT_BITS, alpha=thres - 1e-5)
+    L.call("b200rec_gt_bits_verify", pr2.data_ptr(), M, n_words, N, a.data_ptr(), b.data_ptr(), D, thres, ra2.data_ptr(),
+           L.stream())
     cos = a.float() @ b.float().t()
     margin = (cos - thres).abs().min().item()
     assert margin > 2e-6, "a planted pair sits inside fp32 summation noise of the threshold: reseed"
     assert torch.equal(pr, full) and torch.equal(ra, ra_full)
+    assert torch.equal(pr2, full) and torch.equal(ra2, ra_full)
     assert int(ra.sum()) >= 3
     if cand is not None:                                            # the bound prunes: few candidates beyond the true pairs
         true_pairs = int((cos > thres).sum())
