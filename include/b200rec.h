@@ -210,6 +210,10 @@ int b200rec_gemm(const b200rec_gemm_args* args, void* stream);
  * E so that later subtractive corrections (false-negative filter) stay consistent with the stored tile.  The combine
  * step (b200rec_nce_combine) turns the partials into per-offset log-sum-exp / loss / gradient scalars; the backward
  * GEMMs consume E directly: dq = row_scale * (E @ n_hat), dn = E^T @ (row_scale * q_hat). */
+/* Programmatic dependent launch of the tcgen05 GEMM kernels (default on; env B200REC_PDL=0 disables): the kernel's
+ * prologue (barriers, TMEM allocation, tensor-map prefetch) overlaps the previous kernel's tail, every global access
+ * happens after griddepcontrol.wait. */
+void b200rec_gemm_use_pdl(int on);
 int b200rec_gemm_nce_parts(int N);
 /* Pruned false-negative filter (hstu.py:613-614: fix_logits = target @ neg^T > nce_thres), exact result, ~16x fewer
  * FLOPs than the full product:  tail_norm[r] = || x_hat[r, k0:] ||  (bf16 rows);  GT_BITS GEMM over the first k0

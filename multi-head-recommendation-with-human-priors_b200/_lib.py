@@ -88,6 +88,7 @@ _SIGS = {
     "b200rec_gemm_grouped": (C.c_int, [C.POINTER(GemmArgs), _I, _P]),
     "b200rec_gemm_force_bn": (None, [_I]),
     "b200rec_gemm_force_ctas": (None, [_I]),
+    "b200rec_gemm_use_pdl": (None, [_I]),
     "b200rec_hstu_attn_fwd": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P]),
     "b200rec_hstu_attn_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P,
                                         _P, _P, _P, _P]),

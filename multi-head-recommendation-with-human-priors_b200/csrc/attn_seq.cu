@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(128) attn_seq_fwd_kernel(const bf16* __restric
                                                            const int32_t* __restrict__ seq_off,
                                                            const uint8_t* __restrict__ key_valid, int D, float inv_n,
                                                            float* __restrict__ out) {
+  pdl_trigger();
   __shared__ __align__(16) Tile<DH> sq, sk, sv;
   __shared__ uint8_t kv[SEQ_MAX];
   const int h = blockIdx.x, b = blockIdx.y;
@@ -209,6 +210,7 @@ __global__ void __launch_bounds__(128) attn_seq_bwd_kernel(const bf16* __restric
                                                            int ld, const int32_t* __restrict__ seq_off,
                                                            const uint8_t* __restrict__ key_valid, int D, float inv_n,
                                                            const bf16* __restrict__ d_out, bf16* __restrict__ d_pre) {
+  pdl_trigger();
   __shared__ __align__(16) Tile<DH> sq, sk, sv, sd;
   __shared__ uint8_t kv[SEQ_MAX];
   const int h = blockIdx.x, b = blockIdx.y;

@@ -32,6 +32,13 @@ void b200rec_set_error(const char* fmt, ...);
 
 static inline int ceil_div_i(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
+// pdl_trigger(): the NEXT kernel in the stream, if it was launched with programmatic stream serialization (our GEMMs),
+// may be scheduled now; it runs its prologue (barriers, TMEM allocation, tensor-map prefetch) under this kernel's tail
+// and blocks in pdl_wait() until this grid has completed and flushed.  A no-op for ordinary successors.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- dtype helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }

@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(256) gather_l2norm_kernel(const float* __restr
                                                             const float* __restrict__ rows_in, int D4,
                                                             const int64_t* __restrict__ ids, int64_t n,
                                                             TO* __restrict__ out, float* __restrict__ inv_norm) {
+  pdl_trigger();
   int lane = threadIdx.x & 31;
   int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n) return;
@@ -138,6 +139,7 @@ template <typename TA, int MAXV>
 __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const TA* __restrict__ xh, const float* __restrict__ inv_norm,
                                                          const float* __restrict__ dxh, int64_t n, int D4,
                                                          float* __restrict__ dx, int accumulate) {
+  pdl_trigger();
   int lane = threadIdx.x & 31;
   int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n) return;
@@ -548,6 +550,7 @@ template <typename TA>
 __global__ void __launch_bounds__(256) resblock_bwd_kernel(const float* __restrict__ d_hd, const TA* __restrict__ z,
                                                            int64_t T, int H, int D4, TA* __restrict__ dz,
                                                            float* __restrict__ dy) {
+  pdl_trigger();
   const int64_t n_vec = T * D4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {

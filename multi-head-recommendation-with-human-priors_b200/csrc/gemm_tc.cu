@@ -6,6 +6,7 @@
 // Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..9 = epilogue (two warps per TMEM lane
 // quarter).  Epilogue = TMEM -> registers (lane = row) -> swizzled smem transpose -> lanes along the row
 // -> fused math + fully coalesced 16-byte global accesses (8 lanes cover 128 contiguous bytes).
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -94,6 +95,10 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // PDL: everything above (barriers, tensor-map prefetch, TMEM allocation, cluster syncs) ran under the previous
+  // kernel's tail; nothing below may touch global memory before that kernel has completed
+  pdl_trigger();
+  pdl_wait();
 
   const int tiles_pg = p.num_m * p.num_n;              // p.num_m counts (128*CTAS)-row tiles
   const int num_tiles = tiles_pg * p.groups;
@@ -522,6 +527,9 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, u
 static int g_num_sms = 0;
 static int g_force_bn = 0;    // test hook
 static int g_force_ctas = 0;  // test hook: 1 = never use CTA pairs
+static int g_use_pdl = 1;     // programmatic dependent launch of the GEMM kernels (B200REC_PDL=0 / b200rec_gemm_use_pdl(0))
+
+extern "C" void b200rec_gemm_use_pdl(int on) { g_use_pdl = on ? 1 : 0; }
 
 extern "C" void b200rec_gemm_force_bn(int bn) { g_force_bn = bn; }
 // partial-sum slots per row of the NCE_EXP epilogue: two epilogue warps per BN-wide column tile
@@ -535,6 +543,8 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep_in, cudaStrea
     int dev = 0;
     B200_CUDA_OK(cudaGetDevice(&dev));
     B200_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    const char* e = getenv("B200REC_PDL");
+    if (e != nullptr && e[0] == '0') g_use_pdl = 0;
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
@@ -615,13 +625,15 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep_in, cudaStrea
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = ctas;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_use_pdl ? 2 : 1;
 #define TC_LAUNCH(MODE_)                                                                                   \
   do {                                                                                                     \
     if (ctas == 2) B200_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE_, 2>, ma, mb, p, ep));        \
@@ -707,13 +719,15 @@ int gemm_tc_launch_grouped(const b200rec_gemm_args* a, int n, const EpiParams& e
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = ctas;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_use_pdl ? 2 : 1;
   EpiParams ep = ep_in;
   if (ep.mode == B200REC_EPI_STORE) {
     if (ctas == 2) B200_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_grouped_kernel<0, 2>, ga, p, ep));

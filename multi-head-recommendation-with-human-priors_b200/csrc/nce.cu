@@ -719,6 +719,7 @@ __global__ void __launch_bounds__(256) nce_pos_ref_kernel(const bf16* __restrict
                                                           const float* __restrict__ logit_scale,
                                                           float* __restrict__ pos_cos, float* __restrict__ mref,
                                                           float* __restrict__ thr) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= T) return;
@@ -786,6 +787,7 @@ __global__ void __launch_bounds__(256) nce_combine_kernel(
     const float* __restrict__ coef, const float* __restrict__ logit_scale, float* __restrict__ loss,
     float* __restrict__ g0, float* __restrict__ dscale, int32_t* __restrict__ rank0, int32_t* __restrict__ nvalid,
     float* __restrict__ row_scale, bf16* __restrict__ qs, int64_t ldqs) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= T) return;
@@ -949,6 +951,7 @@ __global__ void __launch_bounds__(256) tail_norm_kernel(const bf16* __restrict__
 // (a per-column factor in the epilogue cost more than the whole K = 64 GEMM).
 __global__ void __launch_bounds__(256) prefix_aug_kernel(const bf16* __restrict__ x, int64_t n, int D4, int k04,
                                                          bf16* __restrict__ out) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n) return;
@@ -995,6 +998,7 @@ template <int MAXV>
 __global__ void __launch_bounds__(256) gt_bits_verify_kernel(uint32_t* __restrict__ bits, int64_t M, int n_words, int N,
                                                              const bf16* __restrict__ a, const bf16* __restrict__ b,
                                                              int D4, float thres, uint8_t* __restrict__ row_any) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= M) return;

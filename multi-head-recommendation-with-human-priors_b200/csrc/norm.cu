@@ -10,6 +10,7 @@ template <typename TY, int MAXV>
 __global__ void __launch_bounds__(ROW_THREADS) layernorm_fwd_kernel(const float* __restrict__ x, int T, int D4, float eps,
                                                             TY* __restrict__ y, float* __restrict__ mean,
                                                             float* __restrict__ rstd) {
+  pdl_trigger();
   int lane = threadIdx.x & 31;
   int r = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= T) return;
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(ROW_THREADS) layernorm_bwd_kernel(const TG* __
                                                             const float* __restrict__ rstd, int T, int D4,
                                                             const float* __restrict__ resid, float* __restrict__ dx,
                                                             TG* __restrict__ dx_act) {
+  pdl_trigger();
   int lane = threadIdx.x & 31;
   int r = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= T) return;
@@ -144,6 +146,7 @@ __global__ void __launch_bounds__(ROW_THREADS) gate_ln_fwd_kernel(const TA* __re
                                                           const float* __restrict__ a, int T, int D4, float eps,
                                                           TA* __restrict__ oin, float* __restrict__ mean,
                                                           float* __restrict__ rstd, DropCfg drop) {
+  pdl_trigger();
   int lane = threadIdx.x & 31;
   int r = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= T) return;
@@ -220,6 +223,7 @@ __global__ void __launch_bounds__(ROW_THREADS) gate_ln_bwd_kernel(const TA* __re
                                                           const float* __restrict__ rstd, int T, int D4,
                                                           TA* __restrict__ d_pre_u, TA* __restrict__ da,
                                                           DropCfg drop) {
+  pdl_trigger();
   int lane = threadIdx.x & 31;
   int r = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= T) return;

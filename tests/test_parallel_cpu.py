@@ -46,7 +46,8 @@ def _worker(rank, world, port, q):
     dp = parallel.DataParallel(m)
     dp.sync_gradients()
     uniq, merged, nu = m.emb_grad
-    q.put((rank, m.lin.weight.grad.clone(), m.lin.bias.grad.clone(), uniq.clone(), merged.clone(), ids, rows))
+    # numpy payloads are pickled by value; torch tensors travel as shared-memory handles that can vanish with the worker
+    q.put((rank,) + tuple(t.detach().clone().numpy() for t in (m.lin.weight.grad, m.lin.bias.grad, uniq, merged, ids, rows)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -62,6 +63,7 @@ def test_dp_gradient_exchange_world2():
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda x: x[0])
+    res = [(r[0],) + tuple(torch.from_numpy(a) for a in r[1:]) for r in res]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -115,7 +117,7 @@ def _shard_worker(rank, world, port, q):
     grads = torch.randn(ids.numel(), D, generator=g)
     lid, lrows, nu = st.push_grads(grads, scale=0.5)
     negs = parallel.gather_negative_ids(torch.full((2, 3, 2), rank, dtype=torch.int64))
-    q.put((rank, ok_fetch, ids, grads, lid[: int(nu)], lrows[: int(nu)], negs))
+    q.put((rank, ok_fetch) + tuple(t.detach().clone().numpy() for t in (ids, grads, lid[: int(nu)], lrows[: int(nu)], negs)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -131,6 +133,7 @@ def test_sharded_table_fetch_and_push_world2():
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda x: x[0])
+    res = [r[:2] + tuple(torch.from_numpy(a) for a in r[2:]) for r in res]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
