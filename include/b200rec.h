@@ -155,6 +155,16 @@ enum {
   ,
   B200REC_EPI_NCE_EXP = 7     /* fused sampled-softmax forward: C = bf16 softmax numerators + per-row partial
                                  sums (nce_* fields, described below b200rec_gemm).  bf16 (tcgen05) path only. */
+  ,
+  B200REC_EPI_FOLD_ITEMS = 8  /* FOLD_HEADS with the operands swapped: A = item rows [M = items, K], B = user heads
+                                 [N = users * fold_hp, K] (fold_hp in {1, 2, 4, 8, 12, 16}: H = 12 needs no padding to
+                                 16).  An accumulator row is one item, so the masked max / arg-max over a user's heads
+                                 is taken in registers of one thread (no shuffles, no shared-memory transpose) and the
+                                 epilogue hides under the MMAs.  Outputs as FOLD_HEADS: C = fval fp32 [users, ldc >= M],
+                                 C2 = fhead u8 [users, ldc2 >= M], or the streamed candidate lists (fold_thr != NULL).
+                                 Masks: fold_on_bits[user] (bit h = head h on), fold_head_cat[h], fold_item_tags[m],
+                                 global item id m*fold_id_stride + fold_id_offset == 0.  Tile order: all user tiles of
+                                 one item tile run back to back (the table streams from HBM once).  bf16 path only. */
 };
 typedef struct {
   int M, N, K;
@@ -199,6 +209,8 @@ typedef struct {
   const float* row_scale;
   /* B200REC_EPI_NCE_EXP only (fused sampled-softmax forward, hstu.py:600-619 + cross_entropy): see below. */
   const float* nce_mref; const float* nce_thr; float* nce_stats; const float* nce_logit_scale;
+  /* B200REC_EPI_FOLD_ITEMS only: uint32[users], bit h set = head h of that user takes part (fold_head_on is unused). */
+  const uint32_t* fold_on_bits;
 } b200rec_gemm_args;
 int b200rec_gemm(const b200rec_gemm_args* args, void* stream);
 /* B200REC_EPI_NCE_EXP (bf16 tcgen05 path): the logits GEMM of the sampled-softmax loss with the softmax numerators

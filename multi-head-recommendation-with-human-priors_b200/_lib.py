@@ -12,7 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200rec.so")
 
 F32, BF16 = 0, 1
-EPI_STORE, EPI_ACCUM, EPI_SILU_DUAL, EPI_BIAS_RESID, EPI_RESBLOCK, EPI_GT_BITS, EPI_FOLD_HEADS, EPI_NCE_EXP = range(8)
+(EPI_STORE, EPI_ACCUM, EPI_SILU_DUAL, EPI_BIAS_RESID, EPI_RESBLOCK, EPI_GT_BITS, EPI_FOLD_HEADS, EPI_NCE_EXP,
+ EPI_FOLD_ITEMS) = range(9)
 
 _lib = None
 launches = 0  # number of C-ABI kernel entry points invoked (bench.py's gpu_launches claim)
@@ -53,6 +54,7 @@ class GemmArgs(C.Structure):
         ("gt_row", C.c_void_p), ("gt_col", C.c_void_p),
         ("row_scale", C.c_void_p),
         ("nce_mref", C.c_void_p), ("nce_thr", C.c_void_p), ("nce_stats", C.c_void_p), ("nce_logit_scale", C.c_void_p),
+        ("fold_on_bits", C.c_void_p),
     ]
 
 
@@ -188,7 +190,7 @@ def call(name, *args):
 
 def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epilogue=EPI_STORE, alpha=1.0,
          alpha_dev=None, bias=None, resid=None, ldr=0, C2=None, ldc2=0, n_split=0, c_dtype=None, fold=None,
-         splitk_ws=None, gt=None):
+         splitk_ws=None, gt=None, fold_items=None):
     """C[M,N] = epi(A[M,K] @ B[N,K]^T).  A/B are tensors (or views) whose data_ptr is element (0,0)."""
     global launches
     a = GemmArgs()
@@ -198,8 +200,8 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epilogue=
     a.in_dtype = dt(A)
     if dt(B) != a.in_dtype:
         raise B200RecError("gemm: A and B dtypes differ")
-    a.C, a.ldc = C_out.data_ptr(), ldc
-    raw_out = epilogue in (EPI_GT_BITS, EPI_FOLD_HEADS)
+    a.C, a.ldc = ptr(C_out), ldc
+    raw_out = epilogue in (EPI_GT_BITS, EPI_FOLD_HEADS, EPI_FOLD_ITEMS)
     a.c_dtype = F32 if raw_out else (dt(C_out) if c_dtype is None else c_dtype)
     a.C2, a.ldc2 = ptr(C2), ldc2
     a.c2_dtype = dt(C2) if (C2 is not None and not raw_out) else F32
@@ -211,6 +213,12 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epilogue=
         if len(fold) > 6:      # streamed variant: (thr f32[users], cnt u32[users], keys u64[users, cap], cap)
             a.fold_thr, a.fold_cnt, a.fold_keys, a.fold_cap = ptr(fold[6]), ptr(fold[7]), ptr(fold[8]), fold[9]
             a.fold_groups = fold[10] if len(fold) > 10 else 1
+    if fold_items is not None:   # (hp, on_bits u32[users], head_cat i32[hp] or None, item_tags u32[M] or None, id_offset,
+        f = fold_items           #  id_stride[, thr f32[users], cnt u32[users], keys u64[users, cap], cap])
+        a.fold_hp, a.fold_on_bits, a.fold_head_cat, a.fold_item_tags = f[0], ptr(f[1]), ptr(f[2]), ptr(f[3])
+        a.fold_id_offset, a.fold_id_stride = f[4], f[5]
+        if len(f) > 6:
+            a.fold_thr, a.fold_cnt, a.fold_keys, a.fold_cap = ptr(f[6]), ptr(f[7]), ptr(f[8]), f[9]
     if gt is not None:     # GT_BITS upper-bound variant: (row vector fp32[M], column vector fp32[N])
         a.gt_row, a.gt_col = gt[0].data_ptr(), gt[1].data_ptr()
     a.epilogue, a.alpha = epilogue, alpha

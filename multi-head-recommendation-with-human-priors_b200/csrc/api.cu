@@ -139,7 +139,22 @@ int b200rec_gemm(const b200rec_gemm_args* a, void* stream) {
                      "gemm: FOLD_HEADS needs ldc %% 4 == 0 and aligned outputs");
     }
   }
-  B200_CHECK_ARG(a->C != nullptr, "gemm: null C");
+  ep.fold_on_bits = a->fold_on_bits;
+  if (a->epilogue == B200REC_EPI_FOLD_ITEMS) {
+    const int hp = a->fold_hp;
+    B200_CHECK_ARG(a->in_dtype == B200REC_BF16, "gemm: FOLD_ITEMS runs on the tcgen05 path only");
+    B200_CHECK_ARG((hp == 1 || hp == 2 || hp == 4 || hp == 8 || hp == 12 || hp == 16) && a->N % hp == 0,
+                   "gemm: FOLD_ITEMS needs fold_hp in {1, 2, 4, 8, 12, 16} and N %% fold_hp == 0 (got %d)", hp);
+    B200_CHECK_ARG(a->fold_on_bits != nullptr && a->fold_id_stride >= 1 && a->a_major == 0 && a->b_major == 0,
+                   "gemm: FOLD_ITEMS needs fold_on_bits, fold_id_stride >= 1 and K-major operands");
+    if (a->fold_thr != nullptr) {
+      B200_CHECK_ARG(a->fold_cnt && a->fold_keys && a->fold_cap > 0 && a->M < (1 << 27),
+                     "gemm: streamed FOLD_ITEMS needs fold_cnt / fold_keys / fold_cap and M < 2^27 rows per shard");
+    } else {
+      B200_CHECK_ARG(a->C2 != nullptr && a->ldc >= a->M && a->ldc2 >= a->M, "gemm: FOLD_ITEMS needs C2 and ldc, ldc2 >= M");
+    }
+  }
+  B200_CHECK_ARG(a->C != nullptr || (a->epilogue == B200REC_EPI_FOLD_ITEMS && a->fold_thr != nullptr), "gemm: null C");
   if (a->epilogue == B200REC_EPI_SILU_DUAL) B200_CHECK_ARG(a->C2 != nullptr, "gemm: SILU_DUAL needs C2");
   if (a->epilogue == B200REC_EPI_RESBLOCK) B200_CHECK_ARG(a->resid != nullptr, "gemm: RESBLOCK needs resid");
   if (a->epilogue == B200REC_EPI_ACCUM) B200_CHECK_ARG(a->c_dtype == B200REC_F32, "gemm: ACCUM needs fp32 C");

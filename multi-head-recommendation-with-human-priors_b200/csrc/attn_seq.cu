@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(128) attn_seq_fwd_kernel(const bf16* __restric
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       int i = i0 + g + (e >> 1) * 8, j = nt * 8 + 2 * t + (e & 1);
-      a[e] = (j <= i && kv[j]) ? silu_fast_f(s[nt][e]) * inv_n : 0.f;
+      a[e] = (j <= i && kv[j]) ? silu_f(s[nt][e]) * inv_n : 0.f;
     }
     p[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(a[0], a[1]);
     p[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(a[2], a[3]);

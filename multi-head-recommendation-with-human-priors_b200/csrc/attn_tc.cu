@@ -168,7 +168,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
       for (int e = 0; e < 32; ++e) {
         const int tj = c0 + e;
         const bool keep = (tj <= ti) && (tj >= my_start) && s_kvalid[c * 32 + e];
-        v[e] = keep ? silu_fast_f(v[e]) * inv_n : 0.f;
+        v[e] = keep ? silu_f(v[e]) * inv_n : 0.f;
       }
       put_row32_sw128(sP, 128, tid, c * 32, v);
     }

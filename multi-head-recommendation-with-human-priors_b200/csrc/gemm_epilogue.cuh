@@ -17,6 +17,7 @@ struct EpiParams {
   const uint8_t* fold_head_on; const int32_t* fold_head_cat; const uint32_t* fold_item_tags;
   int64_t fold_id_offset, fold_id_stride;
   const float* fold_thr; uint32_t* fold_cnt; unsigned long long* fold_keys; int fold_cap; int fold_groups;
+  const uint32_t* fold_on_bits;   // FOLD_ITEMS: per-user bit mask of the heads that are on
   const float* gt_row; const float* gt_col;   // GT_BITS: bit = acc + gt_row[m] * gt_col[n] > alpha
   // STORE / ACCUM: optional per-row factor (fp32[M])
   const float* row_scale;

@@ -32,6 +32,7 @@ struct TcParams {
   int split_k, kb_per_split;      // split-K: work item = (tile, k-range); partial tiles go to a workspace
   int64_t split_stride;           // elements between consecutive partial outputs
   int groups;                     // grouped launch: `groups` independent problems of identical shape
+  int n_fastest;                  // tile order: consecutive tiles share the A (row) tile instead of the B tile
 };
 
 // Grouped launch (one persistent kernel over several same-shape problems, so that small problems share
@@ -46,6 +47,73 @@ struct TcGroupArgs {
   const float* nce_thr[TC_MAX_GROUPS];
   float* nce_stats[TC_MAX_GROUPS];
 };
+
+// B200REC_EPI_FOLD_ITEMS, one epilogue warp: lane = item row m, the warp's `cols` accumulator columns starting at column
+// nc0 (a multiple of HP) hold whole users of HP heads each.  NCH 32-column chunks are loaded per batch (NCH * 32 % HP == 0)
+// and every user's masked max / arg-max is taken over registers of ONE thread: no shuffles, no shared-memory transpose.
+template <int HP, int NCH>
+__device__ __forceinline__ void fold_items_warp(const EpiParams& ep, int cols, uint32_t t_addr, int m, int nc0) {
+  constexpr int UPB = NCH * 32 / HP;                       // users per batch
+  const int n_users = ep.N / HP;
+  const int64_t id = (int64_t)m * ep.fold_id_stride + ep.fold_id_offset;
+  const bool row_ok = m < ep.M;
+  uint32_t hmask = 0;                                      // bit h: head h may score this item
+  if (row_ok && id != 0) {
+    const uint32_t tg = ep.fold_item_tags ? __ldg(ep.fold_item_tags + m) : 0xffffffffu;
+#pragma unroll
+    for (int h = 0; h < HP; ++h) {
+      const int cat = ep.fold_head_cat ? __ldg(ep.fold_head_cat + h) : -1;
+      hmask |= ((cat < 0 || ((tg >> cat) & 1u)) ? 1u : 0u) << h;
+    }
+  }
+#pragma unroll 1
+  for (int b0 = 0; b0 < cols; b0 += NCH * 32) {
+    uint32_t rr[NCH][32];
+#pragma unroll
+    for (int q = 0; q < NCH; ++q) tmem_ld_32x32_nowait(t_addr + (uint32_t)(b0 + q * 32), rr[q]);
+    tmem_ld_wait();
+    const int user0 = (nc0 + b0) / HP;
+#pragma unroll
+    for (int u = 0; u < UPB; ++u) {
+      const int user = user0 + u;
+      if (user >= n_users) break;                          // warp-uniform
+      const uint32_t bits = hmask & __ldg(ep.fold_on_bits + user);
+      float best = -INFINITY;
+#pragma unroll
+      for (int h = 0; h < HP; ++h) {
+        const float x = __uint_as_float(rr[(u * HP + h) >> 5][(u * HP + h) & 31]);
+        best = fmaxf(best, ((bits >> h) & 1u) ? x : -INFINITY);
+      }
+      if (ep.fold_thr != nullptr) {
+        // streamed eval: only scores that can still enter the user's top-K leave the SM
+        if (best >= __ldg(ep.fold_thr + user) && best > -INFINITY) {
+          int bh = 0;
+#pragma unroll
+          for (int h = HP - 1; h >= 0; --h) {
+            const float x = __uint_as_float(rr[(u * HP + h) >> 5][(u * HP + h) & 31]);
+            if (((bits >> h) & 1u) && x == best) bh = h;   // lowest head wins ties
+          }
+          const uint32_t slot = atomicAdd(ep.fold_cnt + user, 1u);
+          if (slot < (uint32_t)ep.fold_cap) {
+            uint32_t k = __float_as_uint(best);
+            k = (k & 0x80000000u) ? ~k : (k | 0x80000000u);                      // ascending-order-preserving key
+            ep.fold_keys[(int64_t)user * ep.fold_cap + slot] =
+                ((unsigned long long)(~k) << 32) | (unsigned long long)(((uint32_t)m << 5) | (uint32_t)bh);
+          }
+        }
+      } else if (row_ok) {
+        int bh = 0;
+#pragma unroll
+        for (int h = HP - 1; h >= 0; --h) {
+          const float x = __uint_as_float(rr[(u * HP + h) >> 5][(u * HP + h) & 31]);
+          if (((bits >> h) & 1u) && x == best) bh = h;
+        }
+        ((float*)ep.C)[(int64_t)user * ep.ldc + m] = best;                       // lanes = consecutive items: coalesced
+        ((uint8_t*)ep.C2)[(int64_t)user * ep.ldc2 + m] = (uint8_t)bh;
+      }
+    }
+  }
+}
 
 // CTAS = 1: one CTA per 128 x BN tile.  CTAS = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN
 // tile: each CTA stages its own 128 A rows and HALF of the B tile, so per-CTA shared-memory and L2 operand
@@ -116,8 +184,10 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
         const int grp = gtile / tiles_pg, tile = gtile - grp * tiles_pg;
         const CUtensorMap* map_a = maps_a + grp;
         const CUtensorMap* map_b = maps_b + grp;
-        const int m0 = (tile % p.num_m) * (TC_BM * CTAS) + (int)rank * TC_BM;
-        const int n0 = (tile / p.num_m) * p.BN + (int)rank * bn_cta;
+        const int tm = p.n_fastest ? tile / p.num_n : tile % p.num_m;
+        const int tn = p.n_fastest ? tile % p.num_n : tile / p.num_m;
+        const int m0 = tm * (TC_BM * CTAS) + (int)rank * TC_BM;
+        const int n0 = tn * p.BN + (int)rank * bn_cta;
         const int kb_beg = split * p.kb_per_split, kb_end = min(num_k, kb_beg + p.kb_per_split);
         for (int kb = kb_beg; kb < kb_end; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
@@ -199,8 +269,10 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
     for (int item = tile0; item < num_items; item += tile_step) {
       const int gtile = item % num_tiles, split = item / num_tiles;
       const int grp = gtile / tiles_pg, tile = gtile - grp * tiles_pg;
-      const int m0 = (tile % p.num_m) * (TC_BM * CTAS) + (int)rank * TC_BM;
-      const int n0 = (tile / p.num_m) * p.BN;
+      const int tm = p.n_fastest ? tile / p.num_n : tile % p.num_m;
+      const int tn = p.n_fastest ? tile % p.num_n : tile / p.num_m;
+      const int m0 = tm * (TC_BM * CTAS) + (int)rank * TC_BM;
+      const int n0 = tn * p.BN;
       if (ga) {
         ep.C = ga->C[grp];
         ep.row_scale = ga->row_scale[grp];
@@ -267,7 +339,21 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
           if ((words[0] | words[1] | words[2] | words[3]) != 0u && ep.C2) ((uint8_t*)ep.C2)[m] = 1;
         }
       }
-      for (int c = half; c < p.BN / 32 && MODE != B200REC_EPI_GT_BITS; c += 2) {
+      if (MODE == B200REC_EPI_FOLD_ITEMS) {
+        // rows = items (lane = item), columns = (user, head): the fold over a user's heads is register-local
+        const int m = m0 + quarter * 32 + lane;
+        const uint32_t t_half = t_row + (uint32_t)(half * (p.BN / 2));
+        const int nc0 = n0 + half * (p.BN / 2);
+        switch (ep.fold_hp) {
+          case 1: fold_items_warp<1, 2>(ep, p.BN / 2, t_half, m, nc0); break;
+          case 2: fold_items_warp<2, 2>(ep, p.BN / 2, t_half, m, nc0); break;
+          case 4: fold_items_warp<4, 2>(ep, p.BN / 2, t_half, m, nc0); break;
+          case 8: fold_items_warp<8, 2>(ep, p.BN / 2, t_half, m, nc0); break;
+          case 12: fold_items_warp<12, 3>(ep, p.BN / 2, t_half, m, nc0); break;
+          default: fold_items_warp<16, 2>(ep, p.BN / 2, t_half, m, nc0); break;
+        }
+      }
+      for (int c = half; c < p.BN / 32 && MODE != B200REC_EPI_GT_BITS && MODE != B200REC_EPI_FOLD_ITEMS; c += 2) {
         float v[32];
         tmem_ld_32x32(t_row + (uint32_t)c * 32u, v);
         if (MODE == B200REC_EPI_NCE_EXP) {
@@ -426,7 +512,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
       if (MODE == B200REC_EPI_NCE_EXP) {
         const int m = m0 + quarter * 32 + lane;
         if (m < ep.M) {
-          const int part = (tile / p.num_m) * 2 + half;
+          const int part = tn * 2 + half;
           float st4[4] = {nce_s, nce_w, nce_gt, 0.f};
           store4<float>(ep.nce_stats + ((int64_t)m * ep.nce_parts + part) * 4, st4);
         }
@@ -561,6 +647,8 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep_in, cudaStrea
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
   }
   TcParams p;
   p.M = a->M; p.N = a->N; p.K = a->K;
@@ -576,6 +664,14 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep_in, cudaStrea
     if (ep_in.mode == B200REC_EPI_NCE_EXP) p.BN = a->N > 128 ? 256 : 128;   // nce_parts is a function of N alone
   }
   if ((g_force_bn == 128 || g_force_bn == 256) && ep_in.mode != B200REC_EPI_NCE_EXP) p.BN = g_force_bn;
+  p.n_fastest = 0;
+  if (ep_in.mode == B200REC_EPI_FOLD_ITEMS) {
+    // each epilogue warp owns BN / 2 columns = whole users of fold_hp heads: 12 heads -> 192-wide tiles (8 users per
+    // warp), powers of two -> 256 (or 128 when there are few users).  All user tiles of one item tile run back to back,
+    // so the item table streams from HBM once and the (small) user-head operand stays in L2.
+    p.BN = ep_in.fold_hp == 12 ? 192 : (a->N > 128 ? 256 : 128);
+    p.n_fastest = 1;
+  }
   p.split_k = 1;
   p.groups = 1;
   const int num_k_host = ceil_div_i(a->K, TC_BK);
@@ -648,6 +744,7 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep_in, cudaStrea
     case B200REC_EPI_GT_BITS: TC_LAUNCH(5); break;
     case B200REC_EPI_FOLD_HEADS: TC_LAUNCH(6); break;
     case B200REC_EPI_NCE_EXP: TC_LAUNCH(7); break;
+    case B200REC_EPI_FOLD_ITEMS: TC_LAUNCH(8); break;
     default: b200rec_set_error("gemm: bad epilogue %d", ep.mode); return 1;
   }
 #undef TC_LAUNCH
@@ -686,6 +783,7 @@ int gemm_tc_launch_grouped(const b200rec_gemm_args* a, int n, const EpiParams& e
   p.kb_per_split = ceil_div_i(a->K, TC_BK);
   p.split_stride = 0;
   p.groups = n;
+  p.n_fastest = 0;
   const uint32_t stage_bytes = TC_BM * 128u + (uint32_t)(p.BN / ctas) * 128u;
   p.stages = (TC_SMEM_LIMIT - 1024 - 256 - TC_STAGE_BYTES) / stage_bytes;
   if (p.stages > 8) p.stages = 8;

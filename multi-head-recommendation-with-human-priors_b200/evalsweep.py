@@ -34,14 +34,13 @@ def topk_point(table, U, K, rank, W, tag_bits=None, head_cat=None, streamed=True
     dev = U.device
     B, H, D = U.shape
     N = table.shape[0]
-    hp = 1
-    while hp < H:
-        hp *= 2
+    by_items = H <= 16                 # FOLD_ITEMS (rows = items): heads padded to a multiple of 4 only
+    hp = (H if H <= 2 else (H + 3) // 4 * 4) if by_items else 32
     Up = torch.zeros((B, hp, D), dtype=U.dtype, device=dev)
     Up[:, :H] = U
     on = torch.zeros((B, hp), dtype=torch.uint8, device=dev)
     on[:, :H] = 1
-    onf = on.reshape(-1)
+    on_bits = (on.to(torch.int64) << torch.arange(hp, device=dev)).sum(dim=1).to(torch.int32)
     cat = None
     if head_cat is not None:
         cat = torch.full((hp,), -1, dtype=torch.int32, device=dev)
@@ -49,31 +48,32 @@ def topk_point(table, U, K, rank, W, tag_bits=None, head_cat=None, streamed=True
     idx = torch.empty((B, K), dtype=torch.int64, device=dev)
     val = torch.empty((B, K), dtype=torch.float32, device=dev)
     hsrc = torch.empty((B, K), dtype=torch.int32, device=dev)
+
+    def fold_gemm(b0, b1, n_rows, fval, fhead, ld, stream_args=()):
+        nb = b1 - b0
+        if by_items:
+            L.gemm(table, Up[b0:b1].reshape(nb * hp, D), fval, n_rows, nb * hp, D, lda=D, ldb=D, ldc=ld,
+                   epilogue=L.EPI_FOLD_ITEMS, C2=fhead, ldc2=ld,
+                   fold_items=(hp, on_bits[b0:b1].contiguous(), cat, tag_bits, rank, W) + tuple(stream_args))
+        else:
+            L.gemm(Up[b0:b1].reshape(nb * hp, D), table, fval, nb * hp, n_rows, D, lda=D, ldb=D, ldc=ld,
+                   epilogue=L.EPI_FOLD_HEADS, C2=fhead, ldc2=ld,
+                   fold=(hp, on[b0:b1].reshape(-1).contiguous(), cat, tag_bits, rank, W) + tuple(stream_args))
+
     N0 = min(N, max(32768, ((N + 15) // 16 + 255) // 256 * 256))
     if streamed and N >= 4 * N0 and N < (1 << 27):
         ldn0 = (N0 + 3) // 4 * 4
         fval = torch.empty((B, ldn0), dtype=torch.float32, device=dev)
         fhead = torch.empty((B, ldn0), dtype=torch.uint8, device=dev)
-        L.gemm(Up.view(B * hp, D), table, fval, B * hp, N0, D, lda=D, ldb=D, ldc=ldn0, epilogue=L.EPI_FOLD_HEADS,
-               C2=fhead, ldc2=ldn0, fold=(hp, onf, cat, tag_bits, rank, W))
+        fold_gemm(0, B, N0, fval, fhead, ldn0)
         L.call("b200rec_topk_select", fval.data_ptr(), fhead.data_ptr(), B, N0, ldn0, K, None, None, rank, W,
                idx.data_ptr(), val.data_ptr(), hsrc.data_ptr(), L.stream())
         thr = val[:, K - 1].contiguous()
         cnt = torch.zeros(B, dtype=torch.int32, device=dev)
         keys = torch.empty((B, cap), dtype=torch.int64, device=dev)
         ovf = torch.zeros(1, dtype=torch.int32, device=dev)
-        hs, G = hp, 1            # head groups without padding (G > 1) measured slower than padding to a power of two
-        Ug = torch.zeros((B, G * hs, D), dtype=U.dtype, device=dev)
-        Ug[:, :H] = U
-        ong = torch.zeros((B, G * hs), dtype=torch.uint8, device=dev)
-        ong[:, :H] = 1
-        catg = None
-        if head_cat is not None:
-            catg = torch.full((G * hs,), -1, dtype=torch.int32, device=dev)
-            catg[:H] = head_cat
-        L.gemm(Ug.view(B * G * hs, D), table, fval, B * G * hs, N, D, lda=D, ldb=D, ldc=ldn0, epilogue=L.EPI_FOLD_HEADS,
-               fold=(hs, ong.reshape(-1), catg, tag_bits, rank, W, thr, cnt, keys, cap, G))
-        L.call("b200rec_topk_from_candidates", keys.data_ptr(), cnt.data_ptr(), cap, B, K, 1 if G > 1 else 0, None, None,
+        fold_gemm(0, B, N, fval, None, ldn0, (thr, cnt, keys, cap))
+        L.call("b200rec_topk_from_candidates", keys.data_ptr(), cnt.data_ptr(), cap, B, K, 0, None, None,
                rank, W, idx.data_ptr(), val.data_ptr(), hsrc.data_ptr(), ovf.data_ptr(), L.stream())
         return (idx, val, hsrc), 1.0 + N0 / N, ovf
     # materialising path, user-chunked so that fval + fhead stay below 8 GB: the table is re-streamed per chunk
@@ -85,8 +85,7 @@ def topk_point(table, U, K, rank, W, tag_bits=None, head_cat=None, streamed=True
         nb = b1 - b0
         fval = torch.empty((nb, ldn), dtype=torch.float32, device=dev)
         fhead = torch.empty((nb, ldn), dtype=torch.uint8, device=dev)
-        L.gemm(Up[b0:b1].reshape(nb * hp, D), table, fval, nb * hp, N, D, lda=D, ldb=D, ldc=ldn,
-               epilogue=L.EPI_FOLD_HEADS, C2=fhead, ldc2=ldn, fold=(hp, on[b0:b1].reshape(-1).contiguous(), cat, tag_bits, rank, W))
+        fold_gemm(b0, b1, N, fval, fhead, ldn)
         L.call("b200rec_topk_select", fval.data_ptr(), fhead.data_ptr(), nb, N, ldn, K, None, None, rank, W,
                idx[b0:b1].data_ptr(), val[b0:b1].data_ptr(), hsrc[b0:b1].data_ptr(), L.stream())
         passes += 1

@@ -215,10 +215,9 @@ class HSTU(nn.Module):
         self.sparse_embedding_grad = bool(config.get("sparse_embedding_grad", False))
         self.use_tc_attention = bool(config.get("tc_attention", True))
         self.use_fused_eval = bool(config.get("fused_eval", True))
-        self.use_fused_nce = bool(config.get("fused_nce", True))
-        self.use_streamed_eval = bool(config.get("streamed_eval", True))
-        self.use_pruned_filter = bool(config.get("pruned_filter", True))
-        self.eval_head_groups = bool(config.get("eval_head_groups", False))   # streamed eval: H = 12 as 3 x 4 (no padding)   # false-negative filter via an upper bound   # top-K candidates filtered in the scoring GEMM     # bf16 mode: softmax numerators from the GEMM epilogue
+        self.use_fused_nce = bool(config.get("fused_nce", True))            # bf16 mode: softmax numerators from the GEMM epilogue
+        self.use_streamed_eval = bool(config.get("streamed_eval", True))    # top-K candidates filtered in the scoring GEMM
+        self.use_pruned_filter = bool(config.get("pruned_filter", True))    # false-negative filter via an upper bound
         self.share_negatives = bool(config.get("share_negatives", True))   # all-gather negatives across ranks
         self.dropout_seed = int(config.get("seed", 2020)) & 0xffffffff
         self._rng_step = None      # device counter feeding the Philox dropout stream
@@ -1456,9 +1455,13 @@ class HSTU(nn.Module):
         if fused:
             # scoring GEMM with the fold-heads epilogue: [Ball*hp, D] x [N, D]^T -> (max, argmax head) per item;
             # the [B, H, N] score tensor is never written.
-            hp = 1
-            while hp < H:
-                hp *= 2
+            # H <= 16: item-row formulation (FOLD_ITEMS: rows = items, columns = (user, head); heads padded to a multiple
+            # of 4 only, the fold is register-local).  17..32 heads: (user, head) rows padded to 32 (FOLD_HEADS).
+            by_items = H <= 16
+            if by_items:
+                hp = H if H <= 2 else (H + 3) // 4 * 4
+            else:
+                hp = 32
             Up = torch.zeros((Ball, hp, D), dtype=U.dtype, device=dev)
             Up[:, :H] = U
             on = torch.zeros((Ball, hp), dtype=torch.uint8, device=dev)
@@ -1467,14 +1470,28 @@ class HSTU(nn.Module):
             if head_cat is not None:
                 cat = torch.full((hp,), -1, dtype=torch.int32, device=dev)
                 cat[:H] = head_cat
+            on_bits = None
+            if by_items:
+                on_bits = (on.to(torch.int64) << torch.arange(hp, device=dev)).sum(dim=1).to(torch.int32)
+
+            def fold_gemm(b0, b1, n_rows, fval, fhead, ld, stream_args=()):
+                """scores of users [b0, b1) against the first n_rows table rows, folded over heads in the epilogue"""
+                nb = b1 - b0
+                if by_items:
+                    L.gemm(table, Up[b0:b1].reshape(nb * hp, D), fval, n_rows, nb * hp, D, lda=D, ldb=D, ldc=ld,
+                           epilogue=L.EPI_FOLD_ITEMS, C2=fhead, ldc2=ld,
+                           fold_items=(hp, on_bits[b0:b1].contiguous(), cat, bits, rank, Wd) + tuple(stream_args))
+                else:
+                    L.gemm(Up[b0:b1].reshape(nb * hp, D), table, fval, nb * hp, n_rows, D, lda=D, ldb=D, ldc=ld,
+                           epilogue=L.EPI_FOLD_HEADS, C2=fhead, ldc2=ld,
+                           fold=(hp, on[b0:b1].reshape(-1).contiguous(), cat, bits, rank, Wd) + tuple(stream_args))
+
             def materialised(b0, b1):
-                """fold-heads epilogue -> (max, arg-max head) per (user, item) in HBM -> two-read select."""
+                """fold epilogue -> (max, arg-max head) per (user, item) in HBM -> two-read select."""
                 nb = b1 - b0
                 fval = torch.empty((nb, ldn), dtype=torch.float32, device=dev)
                 fhead = torch.empty((nb, ldn), dtype=torch.uint8, device=dev)
-                L.gemm(Up[b0:b1].reshape(nb * hp, D), table, fval, nb * hp, N, D, lda=D, ldb=D, ldc=ldn,
-                       epilogue=L.EPI_FOLD_HEADS, C2=fhead, ldc2=ldn,
-                       fold=(hp, on[b0:b1].reshape(-1).contiguous(), cat, bits, rank, Wd))
+                fold_gemm(b0, b1, N, fval, fhead, ldn)
                 ho = hist_off[b0:b1 + 1].contiguous() if hist_off is not None else None
                 L.call("b200rec_topk_select", fval.data_ptr(), fhead.data_ptr(), nb, N, ldn, K, L.ptr(ho), L.ptr(hist_items),
                        rank, Wd, idx[b0:b1].data_ptr(), val[b0:b1].data_ptr(), hsrc[b0:b1].data_ptr(), L.stream())
@@ -1492,36 +1509,15 @@ class HSTU(nn.Module):
                 ldn0 = (N0 + 3) // 4 * 4
                 fval = torch.empty((Ball, ldn0), dtype=torch.float32, device=dev)
                 fhead = torch.empty((Ball, ldn0), dtype=torch.uint8, device=dev)
-                onf = on.reshape(-1).contiguous()
-                L.gemm(Up.reshape(Ball * hp, D), table, fval, Ball * hp, N0, D, lda=D, ldb=D, ldc=ldn0,
-                       epilogue=L.EPI_FOLD_HEADS, C2=fhead, ldc2=ldn0, fold=(hp, onf, cat, bits, rank, Wd))
+                fold_gemm(0, Ball, N0, fval, fhead, ldn0)
                 L.call("b200rec_topk_select", fval.data_ptr(), fhead.data_ptr(), Ball, N0, ldn0, K, L.ptr(hist_off),
                        L.ptr(hist_items), rank, Wd, idx.data_ptr(), val.data_ptr(), hsrc.data_ptr(), L.stream())
                 thr = val[:, K - 1].contiguous()
                 cnt = torch.zeros(Ball, dtype=torch.int32, device=dev)
                 keys = torch.empty((Ball, cap), dtype=torch.int64, device=dev)
                 ovf = torch.zeros(1, dtype=torch.int32, device=dev)
-                # no padding to a power of two: G groups of hs heads per user (H = 12 -> 3 x 4), one scoring pass; every
-                # group appends to the user's list, the candidate sort keeps the best copy of an item
-                hs, G = hp, 1
-                if self.eval_head_groups:       # measured r02: slower than padding (3x the appends + a second sort)
-                    hs, G = min(((g_ * h_, -h_, h_, g_) for h_ in (8, 4, 2, 1) for g_ in [(H + h_ - 1) // h_]))[2:]
-                if G == 1:
-                    Ug, ong, catg = Up if hs == hp else Up[:, :hs].contiguous(), on[:, :hs].contiguous(), \
-                        (cat[:hs].contiguous() if cat is not None else None)
-                else:
-                    Ug = torch.zeros((Ball, G * hs, D), dtype=U.dtype, device=dev)
-                    Ug[:, :H] = U
-                    ong = torch.zeros((Ball, G * hs), dtype=torch.uint8, device=dev)
-                    ong[:, :H] = on[:, :H]
-                    catg = None
-                    if cat is not None:
-                        catg = torch.full((G * hs,), -1, dtype=torch.int32, device=dev)
-                        catg[:H] = cat[:H]
-                L.gemm(Ug.reshape(Ball * G * hs, D), table, fval, Ball * G * hs, N, D, lda=D, ldb=D, ldc=ldn0,
-                       epilogue=L.EPI_FOLD_HEADS,
-                       fold=(hs, ong.reshape(-1).contiguous(), catg, bits, rank, Wd, thr, cnt, keys, cap, G))
-                L.call("b200rec_topk_from_candidates", keys.data_ptr(), cnt.data_ptr(), cap, Ball, K, 1 if G > 1 else 0,
+                fold_gemm(0, Ball, N, fval, None, ldn0, (thr, cnt, keys, cap))
+                L.call("b200rec_topk_from_candidates", keys.data_ptr(), cnt.data_ptr(), cap, Ball, K, 0,
                        L.ptr(hist_off), L.ptr(hist_items), rank, Wd, idx.data_ptr(), val.data_ptr(), hsrc.data_ptr(),
                        ovf.data_ptr(), L.stream())
                 if int(ovf.item()) != 0:                # also the point where eval hands results to the host anyway

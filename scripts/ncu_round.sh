@@ -13,7 +13,7 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum 
     --log-file $OUT/${TAG}_launches.csv $BENCH > $OUT/${TAG}_launches.log 2>&1
 ncu --set full --clock-control none --import-source on \
     -k "regex:gemm_tc_grouped_kernel|gemm_tc_kernel|attn_seq_bwd|gate_ln_bwd|nce_combine|layernorm_bwd|scatter_reduce_short|topk_from_candidates" \
-    --launch-skip 1200 --launch-count 60 -o $OUT/${TAG}_kernels $BENCH > $OUT/${TAG}_kernels.log 2>&1
+    --launch-skip 170 --launch-count 170 -o $OUT/${TAG}_kernels $BENCH > $OUT/${TAG}_kernels.log 2>&1
 ncu -i $OUT/${TAG}_kernels.ncu-rep --page details > $OUT/${TAG}_kernels_details.txt 2>/dev/null
 ncu -i $OUT/${TAG}_kernels.ncu-rep --page raw --csv > $OUT/${TAG}_kernels_raw.csv 2>/dev/null
 echo done

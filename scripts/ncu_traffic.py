@@ -20,7 +20,7 @@ for r in rd:
     per[int(r["ID"])]["name"] = r["Kernel Name"]
     v = float(r["Metric Value"].replace(",", ""))
     unit = r["Metric Unit"]
-    scale = {"nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+    scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
     per[int(r["ID"])][r["Metric Name"]] = v * scale
 ids = sorted(per)
 # the bench runs 3 identical eager steps (warm-up, timed, e2e): take the middle third of the launches between the first

@@ -301,6 +301,81 @@ def test_fused_eval_large_random():
     assert agree > 0.999          # arg-max head may differ only on near-ties of bf16 products
 
 
+@pytest.mark.parametrize("H,B,N", [(12, 37, 10000), (1, 300, 5000), (2, 65, 4097), (7, 40, 9000), (16, 33, 7000),
+                                   (4, 9, 130), (12, 3, 257)])
+def test_fold_items_epilogue(H, B, N):
+    """FOLD_ITEMS (rows = items, register-local fold; 12 heads unpadded on 192-wide tiles) against torch and against the
+    FOLD_HEADS epilogue; streamed variant: the candidate lists hold exactly the (item, head, score) triples >= thr."""
+    from b200rec import _lib as L
+    D = 128
+    g = torch.Generator().manual_seed(50 + H)
+    U = torch.randn(B, H, D, generator=g).to(torch.bfloat16).to(dev())
+    table = torch.randn(N, D, generator=g).to(torch.bfloat16).to(dev())
+    Cn = 8
+    tags = torch.rand(N, Cn, generator=g) < 0.4
+    bits = (tags.long() * (1 << torch.arange(Cn))).sum(1).to(torch.int32).to(dev())
+    cat = torch.tensor(([-1] * 4 + list(range(8)) + [-1] * 4)[:H], dtype=torch.int32, device=dev())
+    hp = H if H <= 2 else (H + 3) // 4 * 4
+    Up = torch.zeros(B, hp, D, dtype=torch.bfloat16, device=dev())
+    Up[:, :H] = U
+    on = torch.zeros(B, hp, dtype=torch.uint8, device=dev())
+    on[:, :H] = (torch.rand(B, H, generator=g) < 0.85).to(torch.uint8).to(dev())
+    on_bits = (on.long() << torch.arange(hp, device=dev())).sum(1).to(torch.int32)
+    catp = torch.full((hp,), -1, dtype=torch.int32, device=dev())
+    catp[:H] = cat
+    ld = (N + 3) // 4 * 4
+    fval = torch.full((B, ld), float("nan"), device=dev())
+    fhead = torch.zeros(B, ld, dtype=torch.uint8, device=dev())
+    L.gemm(table, Up.view(B * hp, D), fval, N, B * hp, D, lda=D, ldb=D, ldc=ld, epilogue=L.EPI_FOLD_ITEMS, C2=fhead,
+           ldc2=ld, fold_items=(hp, on_bits, catp, bits, 0, 1))
+    s = (U.float() @ table.float().t())                           # [B, H, N]
+    tg = tags.to(dev())
+    for h in range(H):
+        if int(cat[h]) >= 0:
+            s[:, h, ~tg[:, int(cat[h])]] = float("-inf")
+    s.masked_fill_(~on[:, :H].bool().unsqueeze(-1), float("-inf"))
+    s[:, :, 0] = float("-inf")
+    mx, am = s.max(dim=1)
+    fv, fh = fval[:, :N], fhead[:, :N]
+    assert torch.equal(torch.isinf(fv), torch.isinf(mx))
+    fin = torch.isfinite(mx)
+    assert (fv[fin] - mx[fin]).abs().max().item() < 2e-2
+    assert (fh.long() == am)[fin].float().mean().item() > 0.999
+    # same numbers as the (user, head)-row epilogue: identical products, identical k order
+    hq = 1
+    while hq < H:
+        hq *= 2
+    Uq = torch.zeros(B, hq, D, dtype=torch.bfloat16, device=dev())
+    Uq[:, :H] = U
+    onq = torch.zeros(B, hq, dtype=torch.uint8, device=dev())
+    onq[:, :H] = on[:, :H]
+    catq = torch.full((hq,), -1, dtype=torch.int32, device=dev())
+    catq[:H] = cat
+    gval = torch.empty(B, ld, device=dev())
+    ghead = torch.empty(B, ld, dtype=torch.uint8, device=dev())
+    L.gemm(Uq.view(B * hq, D), table, gval, B * hq, N, D, lda=D, ldb=D, ldc=ld, epilogue=L.EPI_FOLD_HEADS, C2=ghead,
+           ldc2=ld, fold=(hq, onq.view(-1), catq, bits, 0, 1))
+    assert torch.equal(fv, gval[:, :N]) and torch.equal(fh, ghead[:, :N])
+    # streamed: threshold = each user's 20th best; candidates == every folded score >= thr, nothing else
+    kth = min(20, N - 1)
+    thr = torch.topk(fv, kth, dim=1).values[:, -1].contiguous()
+    thr = torch.where(torch.isfinite(thr), thr, torch.full_like(thr, -1e30))
+    cap = 256
+    cnt = torch.zeros(B, dtype=torch.int32, device=dev())
+    keys = torch.zeros(B, cap, dtype=torch.int64, device=dev())
+    L.gemm(table, Up.view(B * hp, D), None, N, B * hp, D, lda=D, ldb=D, ldc=ld, epilogue=L.EPI_FOLD_ITEMS,
+           fold_items=(hp, on_bits, catp, bits, 0, 1, thr, cnt, keys, cap))
+    want = (fv >= thr[:, None]) & torch.isfinite(fv)
+    assert torch.equal(cnt.long(), want.sum(1))
+    assert int(cnt.max()) <= cap
+    for b in range(B):
+        k = keys[b, : int(cnt[b])]
+        items = ((k & 0xffffffff) >> 5).sort().values
+        assert torch.equal(items, want[b].nonzero().flatten())
+        it = (k & 0xffffffff) >> 5
+        assert torch.equal((k & 31), fh[b, it].long())
+
+
 def test_static_token_mode_equals_eager():
     """n_tokens (static shapes + dummy tokens) changes nothing: same loss, same gradients."""
     fx = load_golden("prior_additive")
