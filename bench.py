@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--eval-users", type=int, default=256)
     ap.add_argument("--sustained-seconds", type=float, default=6.0, help="0 disables the sustained sub-record")
     ap.add_argument("--instrument-steps", type=int, default=8, help="replays of the event-instrumented graph")
+    ap.add_argument("--gemm-table", default="", help="write a per-shape table of the timed GEMM launches to this file")
     ap.add_argument("--no-graph", action="store_true", help="run the eager step instead of the CUDA-graph step")
     ap.add_argument("--replicate-table", action="store_true", help="N>1: keep the item table replicated")
     ap.add_argument("--profile", action="store_true", help="print a per-kernel time table of one step (torch.profiler)")
@@ -460,7 +461,7 @@ def main():
                     f"({args.instrument_steps} replays right after the sustained region)")
         del ins
     else:
-        gemm_events = [(s.elapsed_time(e), f) for (s, e, f) in (gemm_events or [])]
+        gemm_events = [(ev[0].elapsed_time(ev[1]), ev[2]) + tuple(ev[3:]) for ev in (gemm_events or [])]
         n_gemm_steps = args.steps
     if stepper is not None and hasattr(stepper, "flush"):
         stepper.flush()                          # pending dense update of the sharded step (overlapped all-reduce)
@@ -498,8 +499,19 @@ def main():
     value = B * world * args.steps / (ms / 1e3)
     e2e = B * world * args.steps / (ms_e2e / 1e3)
     pk, pk_src = peaks()
-    gflops = sum(f for (_, f) in gemm_events)
-    gms = sum(m_ for (m_, _) in gemm_events)
+    gflops = sum(ev[1] for ev in gemm_events)
+    gms = sum(ev[0] for ev in gemm_events)
+    if args.gemm_table:
+        # per-shape table of the in-graph GEMM launches (M, N, K, groups, epilogue, a_major, b_major)
+        tab = {}
+        for ev in gemm_events:
+            r = tab.setdefault(ev[2] if len(ev) > 2 else None, [0, 0.0, 0.0])
+            r[0] += 1; r[1] += ev[0]; r[2] += ev[1]
+        with open(args.gemm_table, "w") as fh:
+            fh.write("M N K groups epi a_major b_major | launches/step us/launch TF/s share_of_gemm\n")
+            for k, r in sorted(tab.items(), key=lambda kv: -kv[1][1]):
+                fh.write("%s | %.1f %.1f %.0f %.3f\n" % (" ".join(map(str, k)) if k else "?", r[0] / n_gemm_steps,
+                                                      r[1] / r[0] * 1e3, r[2] / (r[1] / 1e3) / 1e12, r[1] / gms))
     ach = gflops / (gms / 1e3) / 1e12 if gms > 0 else 0.0
     clk_gemm = None
     if sampler:

@@ -184,7 +184,8 @@ typedef struct {
   int n_split; int64_t c_split_stride; int64_t c2_split_stride;
   /* optional split-K workspace (fp32): when the output has few tiles and K is long (weight gradients) the
    * tcgen05 path splits each tile's k-range over idle SMs and sums the partials in fixed order.  Requires
-   * epilogue STORE, fp32 C, ldc == N % 4 == 0 contiguous rows; NULL disables. */
+   * epilogue STORE, fp32 C, ldc == N % 4 == 0 contiguous rows; NULL disables.  The same workspace serves the tail
+   * split (b200rec_gemm_use_tail_split below), which has no layout requirement on C. */
   void* splitk_ws; size_t splitk_ws_bytes;
   /* B200REC_EPI_FOLD_HEADS only */
   int fold_hp;
@@ -226,6 +227,12 @@ int b200rec_gemm(const b200rec_gemm_args* args, void* stream);
  * prologue (barriers, TMEM allocation, tensor-map prefetch) overlaps the previous kernel's tail, every global access
  * happens after griddepcontrol.wait. */
 void b200rec_gemm_use_pdl(int on);
+/* Tail split of the tcgen05 GEMM (default on; env B200REC_TAIL_SPLIT=0 disables).  When the output has a few tiles
+ * more than a whole number of waves (config B's O-proj / d_oin / dn: 84 tiles on 74 CTA pairs), the r tiles of the last
+ * wave are cut into s = units / r k-ranges, one per otherwise idle CTA (pair); the fp32 partial accumulators go to
+ * splitk_ws and a second small kernel sums them in ascending split order (deterministic) and applies the epilogue
+ * (STORE / ACCUM / SILU_DUAL / BIAS_RESID / RESBLOCK).  Needs splitk_ws (16-byte aligned, r * s tiles of fp32). */
+void b200rec_gemm_use_tail_split(int on);
 int b200rec_gemm_nce_parts(int N);
 /* Pruned false-negative filter (hstu.py:613-614: fix_logits = target @ neg^T > nce_thres), exact result, ~16x fewer
  * FLOPs than the full product:  tail_norm[r] = || x_hat[r, k0:] ||  (bf16 rows);  GT_BITS GEMM over the first k0

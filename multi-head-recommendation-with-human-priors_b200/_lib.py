@@ -91,6 +91,7 @@ _SIGS = {
     "b200rec_gemm_force_bn": (None, [_I]),
     "b200rec_gemm_force_ctas": (None, [_I]),
     "b200rec_gemm_use_pdl": (None, [_I]),
+    "b200rec_gemm_use_tail_split": (None, [_I]),
     "b200rec_hstu_attn_fwd": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P]),
     "b200rec_hstu_attn_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P,
                                         _P, _P, _P, _P]),
@@ -188,6 +189,21 @@ def call(name, *args):
     _check(getattr(lib(), name)(*args), name)
 
 
+_TAIL_WS = {}
+TAIL_WS_BYTES = 48 << 20
+
+
+def _tail_workspace(device):
+    """fp32 scratch for the GEMM tail split, one per device: the GEMMs of a process are issued in order (one compute
+    stream, or a graph replayed on it), so consecutive launches can share it; allocated on first use, which the
+    graphed steps reach in their eager warm-up, before any capture."""
+    key = device.index
+    ws = _TAIL_WS.get(key)
+    if ws is None:
+        ws = _TAIL_WS[key] = torch.empty(TAIL_WS_BYTES // 4, dtype=torch.float32, device=device)
+    return ws
+
+
 def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epilogue=EPI_STORE, alpha=1.0,
          alpha_dev=None, bias=None, resid=None, ldr=0, C2=None, ldc2=0, n_split=0, c_dtype=None, fold=None,
          splitk_ws=None, gt=None, fold_items=None):
@@ -207,6 +223,9 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epilogue=
     a.c2_dtype = dt(C2) if (C2 is not None and not raw_out) else F32
     if splitk_ws is not None and ldc == N:
         a.splitk_ws, a.splitk_ws_bytes = splitk_ws.data_ptr(), splitk_ws.numel() * splitk_ws.element_size()
+    elif a.in_dtype == BF16 and epilogue <= EPI_RESBLOCK and M > 128:
+        ws = _tail_workspace(A.device)     # tail split of the last partial wave (include/b200rec.h)
+        a.splitk_ws, a.splitk_ws_bytes = ws.data_ptr(), ws.numel() * 4
     if fold is not None:   # (hp, head_on u8[M], head_cat i32[hp] or None, item_tags u32[N] or None, id_offset, id_stride)
         a.fold_hp, a.fold_head_on, a.fold_head_cat, a.fold_item_tags = fold[0], ptr(fold[1]), ptr(fold[2]), ptr(fold[3])
         a.fold_id_offset, a.fold_id_stride = fold[4], fold[5]
@@ -231,7 +250,7 @@ def gemm(A, B, C_out, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epilogue=
         e0.record()
         _check(lib().b200rec_gemm(C.byref(a), stream()), "b200rec_gemm")
         e1.record()
-        gemm_timing.append((e0, e1, 2.0 * M * N * K))
+        gemm_timing.append((e0, e1, 2.0 * M * N * K, (M, N, K, 1, epilogue, a_major, b_major)))
         return
     _check(lib().b200rec_gemm(C.byref(a), stream()), "b200rec_gemm")
 
@@ -269,7 +288,7 @@ def gemm_grouped(problems, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epil
         e0.record()
         _check(lib().b200rec_gemm_grouped(arr, n, stream()), "b200rec_gemm_grouped")
         e1.record()
-        gemm_timing.append((e0, e1, 2.0 * M * N * K * n))
+        gemm_timing.append((e0, e1, 2.0 * M * N * K * n, (M, N, K, n, epilogue, a_major, b_major)))
         return
     _check(lib().b200rec_gemm_grouped(arr, n, stream()), "b200rec_gemm_grouped")
 

@@ -12,6 +12,7 @@
 // Backward = two deterministic passes (dQ per query tile; dK/dV per key tile, computed in the
 // transposed orientation so that keys sit on the TMEM lanes), each recomputing S (App. D.1).
 #include <limits.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -203,6 +204,207 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, 128);
+  }
+}
+
+
+// --------------------------------------------------------------------------------------- forward, pipelined
+// Same tiling (128 queries x 64-key tiles), but the per-key-tile chain  TMA -> S = Q K^T -> SiLU -> P -> O += P V  is
+// software-pipelined inside the CTA instead of relying on co-resident CTAs alone:
+//   * K / V double-buffered in shared memory: the TMA of tile it+2 (K) / it+1 (V) is issued as soon as the MMA that read
+//     the buffer has retired, a full iteration before it is needed;
+//   * TWO S accumulators in TMEM: S(it+1) is issued at the START of iteration it, so the tensor core computes it while
+//     the 256 threads run the SiLU of S(it); PV(it) is issued at the end of the iteration and retires under SiLU(it+1);
+//   * 256 threads, two per query row (each takes 32 of the 64 keys): half the dependent chain per thread;
+//   * chunks with no masked element (interior of a sequence, keys all valid) skip every compare / select;
+//   * 1/n_pad is applied once to the output row instead of to every probability.
+// The critical path of an iteration is tcgen05.ld -> SiLU -> st.shared -> barrier; the pointwise SiLU (one MUFU per
+// score against 256 tensor flops, dh = 64) bounds the kernel at 1/2 of the tensor peak.
+// 64 KB of shared memory and 256 TMEM columns (S0 | S1 | O) per CTA: two CTAs per SM.
+template <int DH>
+__global__ void __launch_bounds__(256)
+attn_tc_fwd_pipe_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map64,
+                        const int32_t* __restrict__ seq_off, int B, const uint8_t* __restrict__ key_valid, int T, int D,
+                        float inv_n, float* __restrict__ out) {
+  using C = AtCfg<DH>;
+  constexpr uint32_t TILE = 128 * C::SWZ;      // Q tile bytes; a 64-row K or V tile is TILE / 2
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base, sK0 = sQ + TILE, sV0 = sK0 + TILE, sP = sV0 + TILE;   // sK0 / sV0: two TILE/2 buffers each
+  const uint32_t bars = sP + 16384;
+  const uint32_t bar_q = bars, bar_k0 = bars + 8, bar_v0 = bars + 24, bar_s0 = bars + 40, bar_o = bars + 56,
+                 tslot = bars + 64;
+  __shared__ uint8_t s_kvalid[2][64];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quarter = warp & 3, colhalf = warp >> 2;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y;
+  const int row = quarter * 32 + lane;
+  const int ti = q0 + row;
+  if (tid == 0) {
+    tma_prefetch_desc(&map128);
+    tma_prefetch_desc(&map64);
+    mbar_init(bar_q, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_k0 + 8 * i, 1); mbar_init(bar_v0 + 8 * i, 1); mbar_init(bar_s0 + 8 * i, 1); }
+    mbar_init(bar_o, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tslot, 256);
+  const int kt_first = seq_off[find_seq(seq_off, B, q0)] >> 6;
+  const int kt_last = min(q0 + 127, T - 1) >> 6;
+  const int n_it = kt_last - kt_first + 1;
+  if (tid < 64) {
+    const int kk = kt_first * 64 + tid;
+    s_kvalid[0][tid] = kk < T ? key_valid[kk] : 0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot));
+  const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16);
+  const uint32_t tO = 128;  // TMEM columns: S0 = 0, S1 = 64, O = 128
+
+  const int my_start = ti < T ? seq_off[find_seq(seq_off, B, ti)] : INT_MAX;
+  const int w_min_start = warp_min_i(my_start);                       // earliest key any row of this warp may see
+  const int w_max_start = warp_max_i(ti < T ? my_start : INT_MIN);    // latest sequence start among the warp's rows
+  const int w_min_t = q0 + quarter * 32;                              // first row of the warp
+  const int w_max_t = min(q0 + quarter * 32 + 31, T - 1);             // latest key (causal) any row may see
+  const bool w_all_rows = q0 + quarter * 32 + 31 < T;
+  const uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+  const uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_q, TILE);
+    tma_load_2d(sQ, &map128, bar_q, 2 * D + h * DH, q0);
+    for (int i = 0; i < 2 && i < n_it; ++i) {
+      mbar_arrive_expect_tx(bar_k0 + 8 * i, TILE / 2);
+      tma_load_2d(sK0 + i * (TILE / 2), &map64, bar_k0 + 8 * i, 3 * D + h * DH, (kt_first + i) * 64);
+      mbar_arrive_expect_tx(bar_v0 + 8 * i, TILE / 2);
+      tma_load_2d(sV0 + i * (TILE / 2), &map64, bar_v0 + 8 * i, 1 * D + h * DH, (kt_first + i) * 64);
+    }
+    mbar_wait(bar_q, 0);
+    mbar_wait(bar_k0, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16(tmem + 0, C::desc_k(sQ, ks), C::desc_k(sK0, ks), idesc_s, ks > 0);
+    umma_commit(bar_s0);
+  }
+  for (int it = 0; it < n_it; ++it) {
+    const int b = it & 1;
+    const uint32_t use_ph = (uint32_t)(it >> 1) & 1u;          // parity of this use of the K / V / S buffers b
+    const int k0 = (kt_first + it) * 64;
+    if (tid == 0 && it + 1 < n_it) {
+      // S(it+1) into the other accumulator: it was last read by SiLU(it-1), which every thread finished before the
+      // barrier that ended iteration it-1
+      mbar_wait(bar_k0 + 8 * (b ^ 1), (uint32_t)((it + 1) >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < DH / 16; ++ks)
+        umma_bf16(tmem + 64 * (b ^ 1), C::desc_k(sQ, ks), C::desc_k(sK0 + (b ^ 1) * (TILE / 2), ks), idesc_s, ks > 0);
+      umma_commit(bar_s0 + 8 * (b ^ 1));
+    }
+    mbar_wait(bar_s0 + 8 * b, use_ph);
+    tc_fence_after();
+    if (tid == 0 && it + 2 < n_it) {                             // S(it) has retired: its K buffer is free
+      mbar_arrive_expect_tx(bar_k0 + 8 * b, TILE / 2);
+      tma_load_2d(sK0 + b * (TILE / 2), &map64, bar_k0 + 8 * b, 3 * D + h * DH, k0 + 128);
+    }
+    const int c0 = k0 + colhalf * 32;
+    uint32_t pk[16];
+    __syncwarp();                                                // warp 0: lane 0 rejoins before the aligned TMEM load
+    const bool skip = c0 > w_max_t || c0 + 31 < w_min_start;     // warp-uniform: whole chunk masked for these 32 rows
+    if (skip) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) pk[e] = 0u;
+    } else {
+      float v[32];
+      tmem_ld_32x32(t_lane + 64 * b + colhalf * 32, v);
+      const bool kv_all = __all_sync(0xffffffffu, s_kvalid[b][colhalf * 32 + lane] != 0);
+      if (w_all_rows && c0 + 31 <= w_min_t && c0 >= w_max_start && kv_all) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(silu_fast_f(v[2 * e]), silu_fast_f(v[2 * e + 1]));
+          pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float a[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int tj = c0 + 2 * e + u;
+            const bool keep = (tj <= ti) && (tj >= my_start) && s_kvalid[b][colhalf * 32 + 2 * e + u];
+            a[u] = keep ? silu_fast_f(v[2 * e + u]) : 0.f;
+          }
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(a[0], a[1]);
+          pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+      }
+    }
+    if (it > 0) {
+      mbar_wait(bar_o, (uint32_t)(it - 1) & 1u);                 // PV(it-1) retired: sP and its V buffer are free
+      if (tid == 0 && it + 1 < n_it) {
+        mbar_arrive_expect_tx(bar_v0 + 8 * (b ^ 1), TILE / 2);
+        tma_load_2d(sV0 + (b ^ 1) * (TILE / 2), &map64, bar_v0 + 8 * (b ^ 1), 1 * D + h * DH, k0 + 64);
+      }
+    }
+    {
+      // 32 keys of this row -> bf16 into the K-major SWIZZLE_128B P tile (128 rows x 64 keys = one 128-byte row each)
+      const uint32_t rbase = sP + (uint32_t)row * 128u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t addr = rbase + (uint32_t)(((colhalf * 4 + q) ^ (row & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                     "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                     : "memory");
+      }
+    }
+    if (tid < 64 && it + 1 < n_it) {
+      const int kk = k0 + 64 + tid;
+      s_kvalid[b ^ 1][tid] = kk < T ? key_valid[kk] : 0;
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      mbar_wait(bar_v0 + 8 * b, use_ph);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        umma_bf16(tmem + tO, desc_p(sP, ks), C::desc_mn(sV0 + b * (TILE / 2), ks), idesc_o, (it > 0 || ks > 0));
+      umma_commit(bar_o);
+    }
+  }
+  mbar_wait(bar_o, (uint32_t)(n_it - 1) & 1u);
+  tc_fence_after();
+  {
+    // warp (quarter, colhalf) stores columns [colhalf * DH/2, +DH/2) of its 32 rows
+    constexpr int HALF = DH / 2;
+#pragma unroll 1
+    for (int c = 0; c < HALF / 16; ++c) {
+      uint32_t r[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(t_lane + tO + colhalf * HALF + c * 16));
+      tmem_ld_wait();
+      if (ti < T) {
+        float* dst = out + (int64_t)ti * D + h * DH + colhalf * HALF + c * 16;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float o4[4] = {__uint_as_float(r[4 * e]) * inv_n, __uint_as_float(r[4 * e + 1]) * inv_n,
+                         __uint_as_float(r[4 * e + 2]) * inv_n, __uint_as_float(r[4 * e + 3]) * inv_n};
+          store4<float>(dst + 4 * e, o4);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
   }
 }
 
@@ -474,9 +676,21 @@ static int attn_tc_fwd_launch(const bf16* act_base, int64_t ld, const int32_t* s
   CUtensorMap m128, m64;
   if (b200_make_map_bf16(&m128, act_base, (uint64_t)ld, (uint64_t)T, (uint64_t)ld, DH, 128, DH * 2)) return 1;
   if (b200_make_map_bf16(&m64, act_base, (uint64_t)ld, (uint64_t)T, (uint64_t)ld, DH, 64, DH * 2)) return 1;
+  dim3 grid(ceil_div_i(T, 128), n_heads);
+  static int use_pipe = -1;
+  if (use_pipe < 0) {
+    const char* e = getenv("B200REC_ATTN_PIPE");
+    use_pipe = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  if (use_pipe) {
+    size_t smem_p = 3 * 128 * DH * 2 + 16384 + 256 + 1024;
+    { static bool once_p = false; if (!once_p) { B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_pipe_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p)); once_p = true; } }
+    attn_tc_fwd_pipe_kernel<DH><<<grid, 256, smem_p, st>>>(m128, m64, seq_off, B, key_valid, T, D, inv_n, out);
+    B200_LAUNCH_OK();
+    return 0;
+  }
   size_t smem = 2 * 128 * DH * 2 + 16384 + 256 + 1024;
   { static bool once_1 = false; if (!once_1) { B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); once_1 = true; } }
-  dim3 grid(ceil_div_i(T, 128), n_heads);
   attn_tc_fwd_kernel<DH><<<grid, 128, smem, st>>>(m128, m64, seq_off, B, key_valid, T, D, inv_n, out);
   B200_LAUNCH_OK();
   return 0;

@@ -33,7 +33,37 @@ struct TcParams {
   int64_t split_stride;           // elements between consecutive partial outputs
   int groups;                     // grouped launch: `groups` independent problems of identical shape
   int n_fastest;                  // tile order: consecutive tiles share the A (row) tile instead of the B tile
+  // tail split: the tiles of the last, partly filled wave (linear tile index >= tail_first) are cut into tail_split
+  // k-ranges of tail_kb k-blocks each, one per otherwise idle unit; their fp32 partial accumulators go to tail_ws
+  // ([tile][split][128 * CTAS rows][BN]) and tail_fixup_kernel sums them in split order and applies the epilogue
+  int tail_first, tail_split, tail_kb;
+  float* tail_ws;
 };
+
+// One unit of work of the persistent loop: an output tile and the k-blocks [kb_beg, kb_end) of it.
+struct TcWork {
+  int gtile, split, kb_beg, kb_end;
+  int tail_slot;   // >= 0: partial accumulators of a tail tile -> tail_ws slot
+};
+__device__ __forceinline__ TcWork tc_decode(const TcParams& p, int item, int num_tiles, int num_k) {
+  TcWork w;
+  if (p.tail_split > 0 && item >= p.tail_first) {
+    const int j = item - p.tail_first;
+    const int tt = j / p.tail_split;
+    w.split = j - tt * p.tail_split;
+    w.gtile = p.tail_first + tt;
+    w.kb_beg = w.split * p.tail_kb;
+    w.kb_end = min(num_k, w.kb_beg + p.tail_kb);
+    w.tail_slot = j;
+  } else {
+    w.gtile = item % num_tiles;
+    w.split = item / num_tiles;
+    w.kb_beg = w.split * p.kb_per_split;
+    w.kb_end = min(num_k, w.kb_beg + p.kb_per_split);
+    w.tail_slot = -1;
+  }
+  return w;
+}
 
 // Grouped launch (one persistent kernel over several same-shape problems, so that small problems share
 // waves instead of each paying its own tail): per-group operand maps and output pointers, by value.
@@ -172,7 +202,8 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
   const int num_tiles = tiles_pg * p.groups;
   const int num_k = (p.K + TC_BK - 1) / TC_BK;
   const int tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
-  const int num_items = num_tiles * p.split_k;
+  const int num_items = p.tail_split > 0 ? p.tail_first + (num_tiles - p.tail_first) * p.tail_split
+                                          : num_tiles * p.split_k;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -180,7 +211,8 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
       int s = 0;
       uint32_t ph = 0;
       for (int item = tile0; item < num_items; item += tile_step) {
-        const int gtile = item % num_tiles, split = item / num_tiles;
+        const TcWork wk = tc_decode(p, item, num_tiles, num_k);
+        const int gtile = wk.gtile;
         const int grp = gtile / tiles_pg, tile = gtile - grp * tiles_pg;
         const CUtensorMap* map_a = maps_a + grp;
         const CUtensorMap* map_b = maps_b + grp;
@@ -188,7 +220,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
         const int tn = p.n_fastest ? tile % p.num_n : tile / p.num_m;
         const int m0 = tm * (TC_BM * CTAS) + (int)rank * TC_BM;
         const int n0 = tn * p.BN + (int)rank * bn_cta;
-        const int kb_beg = split * p.kb_per_split, kb_end = min(num_k, kb_beg + p.kb_per_split);
+        const int kb_beg = wk.kb_beg, kb_end = wk.kb_end;
         for (int kb = kb_beg; kb < kb_end; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
@@ -225,8 +257,8 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
       int acc = 0;
       uint32_t acc_ph = 0;
       for (int item = tile0; item < num_items; item += tile_step) {
-        const int split = item / num_tiles;
-        const int kb_beg = split * p.kb_per_split, kb_end = min(num_k, kb_beg + p.kb_per_split);
+        const TcWork wk = tc_decode(p, item, num_tiles, num_k);
+        const int kb_beg = wk.kb_beg, kb_end = wk.kb_end;
         mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * (uint32_t)p.BN;
@@ -267,12 +299,16 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
     uint32_t acc_ph = 0;
     const EpiParams ep_base = ep;
     for (int item = tile0; item < num_items; item += tile_step) {
-      const int gtile = item % num_tiles, split = item / num_tiles;
+      const TcWork wk = tc_decode(p, item, num_tiles, num_k);
+      const int gtile = wk.gtile, split = wk.split;
       const int grp = gtile / tiles_pg, tile = gtile - grp * tiles_pg;
       const int tm = p.n_fastest ? tile / p.num_n : tile % p.num_m;
       const int tn = p.n_fastest ? tile % p.num_n : tile / p.num_m;
       const int m0 = tm * (TC_BM * CTAS) + (int)rank * TC_BM;
       const int n0 = tn * p.BN;
+      // tail item: raw fp32 partial accumulators of this CTA's 128 rows -> workspace slot (row pitch BN)
+      float* const tail_dst = wk.tail_slot < 0 ? nullptr
+          : p.tail_ws + ((int64_t)wk.tail_slot * (TC_BM * CTAS) + (int64_t)rank * TC_BM + quarter * 32) * p.BN;
       if (ga) {
         ep.C = ga->C[grp];
         ep.row_scale = ga->row_scale[grp];
@@ -383,6 +419,21 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
         __syncwarp();
         // phase 2: 8 lanes cover one 128-byte row segment, 4 rows per pass
         const int ncol = n0 + c * 32 + cg * 4;
+        if (tail_dst != nullptr) {
+#pragma unroll 2
+          for (int j = 0; j < 8; ++j) {
+            const int row = 4 * j + sub;
+            const uint32_t addr = stg + (uint32_t)row * 128u + (uint32_t)((cg ^ (row & 7)) << 4);
+            float x[4];
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3])
+                         : "r"(addr)
+                         : "memory");
+            store4<float>(tail_dst + (int64_t)row * p.BN + c * 32 + cg * 4, x);
+          }
+          __syncwarp();
+          continue;
+        }
         if (MODE == B200REC_EPI_FOLD_HEADS) {
           // rows of this warp = 32/hp users x hp heads.  Lane (cg, sub) folds rows [8*sub, 8*sub+8) of its
           // 4 columns; partial results of one user are combined across sub-lanes with shuffles.
@@ -469,6 +520,11 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap* maps_a, const CU
               }
             }
           }
+          __syncwarp();
+          continue;
+        }
+        if (epi_has_fast_chunk<MODE>() && ep.vec_ok && n0 + c * 32 + 32 <= ep.N) {
+          epi_chunk_fast<MODE>(ep, stg, m0 + quarter * 32, ncol, sub, cg);   // warp-uniform condition
           __syncwarp();
           continue;
         }
@@ -566,6 +622,35 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   }
 }
 
+// Tail split, second half: sums the k-range partials of every tail tile in ascending split order (deterministic) and
+// applies the real epilogue.  One thread per 4 consecutive columns of a row; grid = (tile chunks, tail tiles).
+template <int MODE>
+__global__ void __launch_bounds__(256) tail_fixup_kernel(const TcParams p, const EpiParams ep_in, int rows_per_tile) {
+  pdl_trigger();
+  EpiParams ep = ep_in;
+  if (ep.alpha_dev && (ep.mode == B200REC_EPI_STORE || ep.mode == B200REC_EPI_ACCUM)) ep.alpha *= *ep.alpha_dev;
+  const int tt = blockIdx.y;
+  const int tile = p.tail_first + tt;
+  const int tm = p.n_fastest ? tile / p.num_n : tile % p.num_m;
+  const int tn = p.n_fastest ? tile % p.num_n : tile / p.num_m;
+  const int bn4 = p.BN / 4;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = idx / bn4, c4 = idx - row * bn4;
+  if (row >= rows_per_tile) return;
+  const int m = tm * rows_per_tile + row, n = tn * p.BN + c4 * 4;
+  if (m >= ep.M || n >= ep.N) return;
+  const int64_t tile_elems = (int64_t)rows_per_tile * p.BN;
+  const float* src = p.tail_ws + (int64_t)tt * p.tail_split * tile_elems + (int64_t)row * p.BN + c4 * 4;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int sidx = 0; sidx < p.tail_split; ++sidx) {
+    float v[4];
+    load4<float>(src + (int64_t)sidx * tile_elems, v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] += v[k];
+  }
+  epi_apply_vec4<MODE>(ep, m, n, acc);
+}
+
 // ------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -613,10 +698,12 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, u
 static int g_num_sms = 0;
 static int g_force_bn = 0;    // test hook
 static int g_force_ctas = 0;  // test hook: 1 = never use CTA pairs
+static int g_tail_split = 1;  // tail split of the last partial wave (B200REC_TAIL_SPLIT=0 / b200rec_gemm_use_tail_split(0))
 static int g_use_pdl = 1;     // programmatic dependent launch of the GEMM kernels (B200REC_PDL=0 / b200rec_gemm_use_pdl(0))
 
 extern "C" void b200rec_gemm_use_pdl(int on) { g_use_pdl = on ? 1 : 0; }
 
+extern "C" void b200rec_gemm_use_tail_split(int on) { g_tail_split = on ? 1 : 0; }
 extern "C" void b200rec_gemm_force_bn(int bn) { g_force_bn = bn; }
 // partial-sum slots per row of the NCE_EXP epilogue: two epilogue warps per BN-wide column tile
 extern "C" int b200rec_gemm_nce_parts(int N) { return 2 * ceil_div_i(N, N > 128 ? 256 : 128); }
@@ -631,6 +718,8 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep_in, cudaStrea
     B200_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     const char* e = getenv("B200REC_PDL");
     if (e != nullptr && e[0] == '0') g_use_pdl = 0;
+    e = getenv("B200REC_TAIL_SPLIT");
+    if (e != nullptr && e[0] == '0') g_tail_split = 0;
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
@@ -706,7 +795,29 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep_in, cudaStrea
   } else {
     if (make_map(&mb, a->B, (uint64_t)a->N, (uint64_t)a->K, (uint64_t)a->ldb, 64, 64)) return 1;
   }
-  int tiles = p.num_m * p.num_n * p.split_k;
+  // Tail split: with a few tiles more than a whole number of waves (O-proj, d_oin, dn of config B: 84 tiles on 74 CTA
+  // pairs) the last wave keeps most SMs idle for a full tile time.  Its r tiles are cut into s = units / r k-ranges so
+  // that the wave lasts 1/s of a tile; partials meet in the workspace and tail_fixup_kernel applies the epilogue.
+  p.tail_first = 0; p.tail_split = 0; p.tail_kb = 0; p.tail_ws = nullptr;
+  {
+    const int tiles_total = p.num_m * p.num_n;
+    const int r = tiles_total % units;
+    if (g_tail_split && a->splitk_ws != nullptr && p.split_k == 1 && ep_in.mode <= B200REC_EPI_RESBLOCK &&
+        tiles_total > units && r > 0 && 2 * r <= units && num_k_host >= 32) {
+      // (measured: at K = 1024 the fix-up launch costs more than the saved 13 k-blocks; K = 4096: -9 us, K = 12288: -48 us)
+      int sp = std::min(units / r, num_k_host / 2);
+      if (sp >= 2) {
+        const int kb = ceil_div_i(num_k_host, sp);
+        sp = ceil_div_i(num_k_host, kb);
+        const size_t need = (size_t)r * sp * (TC_BM * ctas) * p.BN * sizeof(float);
+        if (sp >= 2 && need <= a->splitk_ws_bytes && ((uintptr_t)a->splitk_ws & 15) == 0) {
+          p.tail_first = tiles_total - r; p.tail_split = sp; p.tail_kb = kb; p.tail_ws = (float*)a->splitk_ws;
+        }
+      }
+    }
+  }
+  int tiles = p.tail_split > 0 ? p.tail_first + (p.num_m * p.num_n - p.tail_first) * p.tail_split
+                               : p.num_m * p.num_n * p.split_k;
   int grid = (tiles < units ? tiles : units) * ctas;
   EpiParams ep = ep_in;
   if (p.split_k > 1) {        // partial sums go to the workspace (alpha applied by the final reduction)
@@ -748,6 +859,17 @@ int gemm_tc_launch(const b200rec_gemm_args* a, const EpiParams& ep_in, cudaStrea
     default: b200rec_set_error("gemm: bad epilogue %d", ep.mode); return 1;
   }
 #undef TC_LAUNCH
+  if (p.tail_split > 0) {
+    const int rows = TC_BM * ctas;
+    dim3 fgrid(ceil_div_i(rows * (p.BN / 4), 256), p.num_m * p.num_n - p.tail_first);
+    switch (ep.mode) {
+      case B200REC_EPI_STORE: tail_fixup_kernel<0><<<fgrid, 256, 0, st>>>(p, ep, rows); break;
+      case B200REC_EPI_ACCUM: tail_fixup_kernel<1><<<fgrid, 256, 0, st>>>(p, ep, rows); break;
+      case B200REC_EPI_SILU_DUAL: tail_fixup_kernel<2><<<fgrid, 256, 0, st>>>(p, ep, rows); break;
+      case B200REC_EPI_BIAS_RESID: tail_fixup_kernel<3><<<fgrid, 256, 0, st>>>(p, ep, rows); break;
+      default: tail_fixup_kernel<4><<<fgrid, 256, 0, st>>>(p, ep, rows); break;
+    }
+  }
   if (p.split_k > 1) {
     const int64_t n4 = (int64_t)a->M * a->ldc / 4;
     splitk_reduce_kernel<<<(int)std::min<int64_t>((n4 + 255) / 256, 148 * 8), 256, 0, st>>>(
@@ -783,6 +905,7 @@ int gemm_tc_launch_grouped(const b200rec_gemm_args* a, int n, const EpiParams& e
   p.kb_per_split = ceil_div_i(a->K, TC_BK);
   p.split_stride = 0;
   p.groups = n;
+  p.tail_first = 0; p.tail_split = 0; p.tail_kb = 0; p.tail_ws = nullptr;
   p.n_fastest = 0;
   const uint32_t stage_bytes = TC_BM * 128u + (uint32_t)(p.BN / ctas) * 128u;
   p.stages = (TC_SMEM_LIMIT - 1024 - 256 - TC_STAGE_BYTES) / stage_bytes;

@@ -114,7 +114,7 @@ class GraphedTrainStep(object):
 
 def _read_gemm_events(events):
     """[(ms, flops)] of the GEMM launches of the last replay (call after a synchronize)."""
-    return [(e0.elapsed_time(e1), fl) for (e0, e1, fl) in events]
+    return [(ev[0].elapsed_time(ev[1]), ev[2]) + tuple(ev[3:]) for ev in events]
 
 
 class GraphedShardedStep(object):

@@ -592,6 +592,52 @@ def test_gemm_split_k_weight_gradient_shape():
     assert torch.equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("K", [2048, 4096, 2112])
+def test_gemm_tail_split_matches_unsplit(K):
+    """84 tiles of 256 x 256 on 74 CTA pairs (config B's O-proj / d_oin / dn): the 10 tiles of the last wave are cut into
+    k-ranges over the idle pairs and a fix-up kernel applies the epilogue.  Every epilogue that may take this path is
+    compared with the unsplit launch and with torch; the split run is bit-reproducible."""
+    M, N = 5248 - 40, 1024        # ragged last row tile
+    A, B = _mk_operands(M, N, K, 0, 1, torch.bfloat16, seed=130)
+    ref = _gemm_ref(A, B, 0, 1)
+    bias, resid = rnd(N, seed=131), rnd(M, N, seed=132)
+    r2 = rnd(M, 256, seed=133)
+    adev = torch.tensor(0.25, device=dev())
+    scale = max(1.0, ref.abs().max().item())
+
+    def run_all():
+        out = {}
+        kw = dict(lda=K, ldb=N, ldc=N, a_major=0, b_major=1)
+        out["store_bf16"] = torch.empty(M, N, dtype=torch.bfloat16, device=dev())
+        L.gemm(A, B, out["store_bf16"], M, N, K, alpha=0.5, **kw)
+        out["silu"], out["pre"] = (torch.empty(M, N, dtype=torch.bfloat16, device=dev()) for _ in range(2))
+        L.gemm(A, B, out["silu"], M, N, K, epilogue=L.EPI_SILU_DUAL, C2=out["pre"], ldc2=N, **kw)
+        out["bias_resid"] = torch.empty(M, N, device=dev())
+        L.gemm(A, B, out["bias_resid"], M, N, K, epilogue=L.EPI_BIAS_RESID, bias=bias, resid=resid, ldr=N, **kw)
+        out["resblock"] = torch.empty(M, N, device=dev())
+        out["z"] = torch.empty(M, N, dtype=torch.bfloat16, device=dev())
+        L.gemm(A, B, out["resblock"], M, N, K, epilogue=L.EPI_RESBLOCK, bias=bias, resid=r2, ldr=256, C2=out["z"],
+               ldc2=N, n_split=256, **kw)
+        out["accum"] = resid.clone()
+        L.gemm(A, B, out["accum"], M, N, K, epilogue=L.EPI_ACCUM, alpha=2.0, alpha_dev=adev, **kw)
+        return out
+
+    L.lib().b200rec_gemm_use_tail_split(0)
+    try:
+        plain = run_all()
+    finally:
+        L.lib().b200rec_gemm_use_tail_split(1)
+    split, again = run_all(), run_all()
+    want = {"store_bf16": 0.5 * ref, "silu": torch.nn.functional.silu(ref), "pre": ref, "bias_resid": ref + bias + resid,
+            "resblock": r2.repeat(1, 4) + torch.nn.functional.silu(ref + bias), "z": ref + bias,
+            "accum": resid + 0.5 * ref}
+    for k in want:
+        assert torch.equal(split[k], again[k]), k
+        tol = 2e-2 if split[k].dtype == torch.bfloat16 else 1e-5     # fp32 outputs differ only by summation order
+        assert (split[k].float() - plain[k].float()).abs().max().item() / scale < tol, k
+        assert (split[k].float() - want[k]).abs().max().item() / scale < 2e-2, k
+
+
 @pytest.mark.parametrize("am,bm,epi", [(0, 0, "store"), (1, 1, "store"), (0, 1, "accum")], ids=["kk", "mnmn", "kmn-accum"])
 def test_gemm_grouped_matches_single_launches(am, bm, epi):
     """b200rec_gemm_grouped: 5 same-shape problems in one persistent launch == 5 single launches (bit-exact:
