@@ -208,187 +208,224 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map128, const __grid_cons
 }
 
 
+// Sequence offsets staged in shared memory: the per-CTA prologue (and the dK/dV pass's per-tile metadata) does a binary
+// search per thread; against global memory that is ~6 dependent loads of L2 latency, a third of a short CTA's lifetime.
+#define AT_SEQ_SMEM 1025
+struct SeqTab {
+  const int32_t* p;     // shared-memory copy when it fits, else the global array
+  int B;
+};
+__device__ __forceinline__ SeqTab seq_tab_load(int32_t* s_seq, const int32_t* __restrict__ seq_off, int B) {
+  SeqTab t;
+  t.B = B;
+  if (B + 1 <= AT_SEQ_SMEM) {
+    for (int i = threadIdx.x; i <= B; i += blockDim.x) s_seq[i] = seq_off[i];
+    t.p = s_seq;
+  } else {
+    t.p = seq_off;
+  }
+  return t;     // visible after the caller's __syncthreads()
+}
+__device__ __forceinline__ int find_seq(const SeqTab& t, int tok) { return find_seq(t.p, t.B, tok); }
+
+// 32 packed bf16 pairs of this thread's chunk -> K-major SWIZZLE_128B tile [128 rows x 64 cols]
+__device__ __forceinline__ void put_pk32_sw128(uint32_t tile, int row, int colhalf, const uint32_t (&pk)[16]) {
+  const uint32_t rbase = tile + (uint32_t)row * 128u;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t addr = rbase + (uint32_t)(((colhalf * 4 + q) ^ (row & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                 "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  tmem_ld_wait();
+}
+
+
 // --------------------------------------------------------------------------------------- forward, pipelined
 // Same tiling (128 queries x 64-key tiles), but the per-key-tile chain  TMA -> S = Q K^T -> SiLU -> P -> O += P V  is
-// software-pipelined inside the CTA instead of relying on co-resident CTAs alone:
-//   * K / V double-buffered in shared memory: the TMA of tile it+2 (K) / it+1 (V) is issued as soon as the MMA that read
-//     the buffer has retired, a full iteration before it is needed;
-//   * TWO S accumulators in TMEM: S(it+1) is issued at the START of iteration it, so the tensor core computes it while
-//     the 256 threads run the SiLU of S(it); PV(it) is issued at the end of the iteration and retires under SiLU(it+1);
-//   * 256 threads, two per query row (each takes 32 of the 64 keys): half the dependent chain per thread;
-//   * chunks with no masked element (interior of a sequence, keys all valid) skip every compare / select;
+// software-pipelined inside the CTA and WARP-SPECIALISED (ncu of the first pipelined version, where thread 0 issued
+// between block barriers: 55 % of the stall samples sat in __syncthreads waiting for that one thread's serial
+// instruction stream):
+//   * warps 0..7 = 256 pointwise threads, two per query row (32 of the 64 keys each); warp 8 = issuer: one elected
+//     lane issues every TMA and every tcgen05.mma.  There is NO block barrier in the loop: the pointwise threads hand
+//     P over through an mbarrier (256 arrivals), the issuer hands S / O back through tcgen05.commit;
+//   * TWO S accumulators in TMEM: S(it+2) is issued right behind PV(it), so it retires one full iteration before the
+//     pointwise threads need it; K in a 3-deep, V in a 2-deep shared-memory ring, loaded >= 1 iteration ahead;
+//   * chunks with no masked element (interior of a sequence, keys all valid) skip every compare / select; key validity
+//     travels as one ballot word per 32-key chunk;
 //   * 1/n_pad is applied once to the output row instead of to every probability.
-// The critical path of an iteration is tcgen05.ld -> SiLU -> st.shared -> barrier; the pointwise SiLU (one MUFU per
-// score against 256 tensor flops, dh = 64) bounds the kernel at 1/2 of the tensor peak.
-// 64 KB of shared memory and 256 TMEM columns (S0 | S1 | O) per CTA: two CTAs per SM.
+// The pointwise SiLU (one MUFU per score against 256 tensor flops at dh = 64) bounds the kernel at 1/2 of the tensor
+// peak.  72 KB of shared memory and 256 TMEM columns (S0 | S1 | O) per CTA: two CTAs per SM.
+#define AT_THREADS 288
+__device__ __forceinline__ uint32_t kvalid_bits(const uint8_t* __restrict__ key_valid, int c0, int lane, int T) {
+  const int kk = c0 + lane;
+  return __ballot_sync(0xffffffffu, kk >= 0 && kk < T && key_valid[kk] != 0);
+}
+
 template <int DH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(AT_THREADS)
 attn_tc_fwd_pipe_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map64,
                         const int32_t* __restrict__ seq_off, int B, const uint8_t* __restrict__ key_valid, int T, int D,
                         float inv_n, float* __restrict__ out) {
   using C = AtCfg<DH>;
-  constexpr uint32_t TILE = 128 * C::SWZ;      // Q tile bytes; a 64-row K or V tile is TILE / 2
+  constexpr uint32_t TILE = 128 * C::SWZ, HT = TILE / 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = base, sK0 = sQ + TILE, sV0 = sK0 + TILE, sP = sV0 + TILE;   // sK0 / sV0: two TILE/2 buffers each
-  const uint32_t bars = sP + 16384;
-  const uint32_t bar_q = bars, bar_k0 = bars + 8, bar_v0 = bars + 24, bar_s0 = bars + 40, bar_o = bars + 56,
-                 tslot = bars + 64;
-  __shared__ uint8_t s_kvalid[2][64];
+  constexpr int NS = 3;                       // K / V ring depth (NS = 4 measured no faster: TMA latency is hidden)
+  const uint32_t sQ = base, sK0 = sQ + TILE, sV0 = sK0 + NS * HT, sP0 = sV0 + NS * HT;   // sP0: two 16 KB P tiles
+  const uint32_t bars = sP0 + 2 * 16384;
+  const uint32_t bar_q = bars, bar_k0 = bars + 8, bar_v0 = bar_k0 + 8 * NS, bar_s0 = bar_v0 + 8 * NS,
+                 bar_o0 = bar_s0 + 16, bar_p0 = bar_o0 + 16, tslot = bar_p0 + 16;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quarter = warp & 3, colhalf = warp >> 2;
   const int q0 = blockIdx.x * 128, h = blockIdx.y;
-  const int row = quarter * 32 + lane;
-  const int ti = q0 + row;
   if (tid == 0) {
-    tma_prefetch_desc(&map128);
-    tma_prefetch_desc(&map64);
     mbar_init(bar_q, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_k0 + 8 * i, 1); mbar_init(bar_v0 + 8 * i, 1); mbar_init(bar_s0 + 8 * i, 1); }
-    mbar_init(bar_o, 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(bar_k0 + 8 * i, 1); mbar_init(bar_v0 + 8 * i, 1); }
+    // two hand-over barriers, alternating by tile parity: with P double-buffered a fast warp may arrive for tile it+1
+    // before a slow one has arrived for tile it, and one barrier must never see two arrivals of a thread in one phase
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_s0 + 8 * i, 1); mbar_init(bar_o0 + 8 * i, 1); mbar_init(bar_p0 + 8 * i, 256); }
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc(tslot, 256);
-  const int kt_first = seq_off[find_seq(seq_off, B, q0)] >> 6;
-  const int kt_last = min(q0 + 127, T - 1) >> 6;
-  const int n_it = kt_last - kt_first + 1;
-  if (tid < 64) {
-    const int kk = kt_first * 64 + tid;
-    s_kvalid[0][tid] = kk < T ? key_valid[kk] : 0;
-  }
+  if (warp == 8) tmem_alloc(tslot, 256);
+  __shared__ int32_t s_seq[AT_SEQ_SMEM];
+  const SeqTab seqs = seq_tab_load(s_seq, seq_off, B);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  const int kt_first = seqs.p[find_seq(seqs, q0)] >> 6;
+  const int kt_last = min(q0 + 127, T - 1) >> 6;
+  const int n_it = kt_last - kt_first + 1;
   uint32_t tmem;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot));
-  const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16);
   const uint32_t tO = 128;  // TMEM columns: S0 = 0, S1 = 64, O = 128
 
-  const int my_start = ti < T ? seq_off[find_seq(seq_off, B, ti)] : INT_MAX;
-  const int w_min_start = warp_min_i(my_start);                       // earliest key any row of this warp may see
-  const int w_max_start = warp_max_i(ti < T ? my_start : INT_MIN);    // latest sequence start among the warp's rows
-  const int w_min_t = q0 + quarter * 32;                              // first row of the warp
-  const int w_max_t = min(q0 + quarter * 32 + 31, T - 1);             // latest key (causal) any row may see
-  const bool w_all_rows = q0 + quarter * 32 + 31 < T;
-  const uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
-  const uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_q, TILE);
-    tma_load_2d(sQ, &map128, bar_q, 2 * D + h * DH, q0);
-    for (int i = 0; i < 2 && i < n_it; ++i) {
-      mbar_arrive_expect_tx(bar_k0 + 8 * i, TILE / 2);
-      tma_load_2d(sK0 + i * (TILE / 2), &map64, bar_k0 + 8 * i, 3 * D + h * DH, (kt_first + i) * 64);
-      mbar_arrive_expect_tx(bar_v0 + 8 * i, TILE / 2);
-      tma_load_2d(sV0 + i * (TILE / 2), &map64, bar_v0 + 8 * i, 1 * D + h * DH, (kt_first + i) * 64);
-    }
-    mbar_wait(bar_q, 0);
-    mbar_wait(bar_k0, 0);
-    tc_fence_after();
+  if (warp == 8) {
+    // ===================== issuer =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&map128);
+      tma_prefetch_desc(&map64);
+      const uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);
+      auto load_k = [&](int it) {
+        const int j = it % NS;
+        mbar_arrive_expect_tx(bar_k0 + 8 * j, HT);
+        tma_load_2d(sK0 + j * HT, &map64, bar_k0 + 8 * j, 3 * D + h * DH, (kt_first + it) * 64);
+      };
+      auto load_v = [&](int it) {
+        const int j = it % NS;
+        mbar_arrive_expect_tx(bar_v0 + 8 * j, HT);
+        tma_load_2d(sV0 + j * HT, &map64, bar_v0 + 8 * j, 1 * D + h * DH, (kt_first + it) * 64);
+      };
+      auto issue_s = [&](int it) {
+        const int j = it % NS;
+        mbar_wait(bar_k0 + 8 * j, (uint32_t)(it / NS) & 1u);
+        tc_fence_after();
 #pragma unroll
-    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16(tmem + 0, C::desc_k(sQ, ks), C::desc_k(sK0, ks), idesc_s, ks > 0);
-    umma_commit(bar_s0);
-  }
-  for (int it = 0; it < n_it; ++it) {
-    const int b = it & 1;
-    const uint32_t use_ph = (uint32_t)(it >> 1) & 1u;          // parity of this use of the K / V / S buffers b
-    const int k0 = (kt_first + it) * 64;
-    if (tid == 0 && it + 1 < n_it) {
-      // S(it+1) into the other accumulator: it was last read by SiLU(it-1), which every thread finished before the
-      // barrier that ended iteration it-1
-      mbar_wait(bar_k0 + 8 * (b ^ 1), (uint32_t)((it + 1) >> 1) & 1u);
-      tc_fence_after();
-#pragma unroll
-      for (int ks = 0; ks < DH / 16; ++ks)
-        umma_bf16(tmem + 64 * (b ^ 1), C::desc_k(sQ, ks), C::desc_k(sK0 + (b ^ 1) * (TILE / 2), ks), idesc_s, ks > 0);
-      umma_commit(bar_s0 + 8 * (b ^ 1));
-    }
-    mbar_wait(bar_s0 + 8 * b, use_ph);
-    tc_fence_after();
-    if (tid == 0 && it + 2 < n_it) {                             // S(it) has retired: its K buffer is free
-      mbar_arrive_expect_tx(bar_k0 + 8 * b, TILE / 2);
-      tma_load_2d(sK0 + b * (TILE / 2), &map64, bar_k0 + 8 * b, 3 * D + h * DH, k0 + 128);
-    }
-    const int c0 = k0 + colhalf * 32;
-    uint32_t pk[16];
-    __syncwarp();                                                // warp 0: lane 0 rejoins before the aligned TMEM load
-    const bool skip = c0 > w_max_t || c0 + 31 < w_min_start;     // warp-uniform: whole chunk masked for these 32 rows
-    if (skip) {
-#pragma unroll
-      for (int e = 0; e < 16; ++e) pk[e] = 0u;
-    } else {
-      float v[32];
-      tmem_ld_32x32(t_lane + 64 * b + colhalf * 32, v);
-      const bool kv_all = __all_sync(0xffffffffu, s_kvalid[b][colhalf * 32 + lane] != 0);
-      if (w_all_rows && c0 + 31 <= w_min_t && c0 >= w_max_start && kv_all) {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(silu_fast_f(v[2 * e]), silu_fast_f(v[2 * e + 1]));
-          pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+        for (int ks = 0; ks < DH / 16; ++ks)
+          umma_bf16(tmem + 64 * (it & 1), C::desc_k(sQ, ks), C::desc_k(sK0 + j * HT, ks), idesc_s, ks > 0);
+        umma_commit(bar_s0 + 8 * (it & 1));
+      };
+      mbar_arrive_expect_tx(bar_q, TILE);
+      tma_load_2d(sQ, &map128, bar_q, 2 * D + h * DH, q0);
+      for (int i = 0; i < NS && i < n_it; ++i) { load_k(i); load_v(i); }
+      mbar_wait(bar_q, 0);
+      issue_s(0);
+      if (n_it > 1) issue_s(1);
+      for (int it = 0; it < n_it; ++it) {
+        const int b = it & 1;
+        mbar_wait(bar_p0 + 8 * b, (uint32_t)(it >> 1) & 1u);   // P(it) written; S(it) consumed (so S[b] and K(it)'s buffer are free)
+        tc_fence_after();
+        if (it + NS < n_it) load_k(it + NS);
+        if (it >= 2 && it - 2 + NS < n_it) {
+          // V(it-2)'s slot: the pointwise threads only arrive on bar_p(it) after seeing PV(it-2) retire
+          load_v(it - 2 + NS);
         }
+        mbar_wait(bar_v0 + 8 * (it % NS), (uint32_t)(it / NS) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16(tmem + tO, desc_p(sP0 + b * 16384, ks), C::desc_mn(sV0 + (it % NS) * HT, ks), idesc_o,
+                    (it > 0 || ks > 0));
+        umma_commit(bar_o0 + 8 * b);
+        if (it + 2 < n_it) issue_s(it + 2);
+      }
+    }
+  } else {
+    // ===================== pointwise warps =====================
+    const int quarter = warp & 3, colhalf = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const int ti = q0 + row;
+    const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16);
+    const int my_start = ti < T ? seqs.p[find_seq(seqs, ti)] : INT_MAX;
+    const int w_min_start = warp_min_i(my_start);                       // earliest key any row of this warp may see
+    const int w_max_start = warp_max_i(ti < T ? my_start : INT_MIN);    // latest sequence start among the warp's rows
+    const int w_min_t = q0 + quarter * 32;                              // first row of the warp
+    const int w_max_t = min(q0 + quarter * 32 + 31, T - 1);             // latest key (causal) any row may see
+    const bool w_all_rows = q0 + quarter * 32 + 31 < T;
+    // key validity of this thread's key column, fetched one iteration ahead of its use
+    auto kv_fetch = [&](int it) -> uint8_t {
+      const int kk = (kt_first + it) * 64 + colhalf * 32 + lane;
+      return (it < n_it && kk < T) ? key_valid[kk] : (uint8_t)0;
+    };
+    uint8_t kv_next = kv_fetch(0);
+    for (int it = 0; it < n_it; ++it) {
+      const int b = it & 1;
+      const int c0 = (kt_first + it) * 64 + colhalf * 32;
+      const bool skip = c0 > w_max_t || c0 + 31 < w_min_start;   // warp-uniform: whole chunk masked for these 32 rows
+      const uint32_t kvb = __ballot_sync(0xffffffffu, kv_next != 0);
+      kv_next = kv_fetch(it + 1);
+      mbar_wait(bar_s0 + 8 * b, (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      uint32_t pk[16];
+      if (skip) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pk[e] = 0u;
       } else {
+        float v[32];
+        tmem_ld_32x32(t_lane + 64 * b + colhalf * 32, v);
+        if (w_all_rows && c0 + 31 <= w_min_t && c0 >= w_max_start && kvb == 0xffffffffu) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float a[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int tj = c0 + 2 * e + u;
-            const bool keep = (tj <= ti) && (tj >= my_start) && s_kvalid[b][colhalf * 32 + 2 * e + u];
-            a[u] = keep ? silu_fast_f(v[2 * e + u]) : 0.f;
+          for (int e = 0; e < 16; ++e) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(silu_fast_f(v[2 * e]), silu_fast_f(v[2 * e + 1]));
+            pk[e] = *reinterpret_cast<uint32_t*>(&h2);
           }
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(a[0], a[1]);
-          pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float a[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int tj = c0 + 2 * e + u;
+              const bool keep = (tj <= ti) && (tj >= my_start) && ((kvb >> (2 * e + u)) & 1u);
+              a[u] = keep ? silu_fast_f(v[2 * e + u]) : 0.f;
+            }
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(a[0], a[1]);
+            pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+          }
         }
       }
+      if (it > 1) mbar_wait(bar_o0 + 8 * b, (uint32_t)((it >> 1) - 1) & 1u);   // PV(it-2) retired: this P tile is free
+      put_pk32_sw128(sP0 + b * 16384, row, colhalf, pk);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p0 + 8 * b);
     }
-    if (it > 0) {
-      mbar_wait(bar_o, (uint32_t)(it - 1) & 1u);                 // PV(it-1) retired: sP and its V buffer are free
-      if (tid == 0 && it + 1 < n_it) {
-        mbar_arrive_expect_tx(bar_v0 + 8 * (b ^ 1), TILE / 2);
-        tma_load_2d(sV0 + (b ^ 1) * (TILE / 2), &map64, bar_v0 + 8 * (b ^ 1), 1 * D + h * DH, k0 + 64);
-      }
-    }
-    {
-      // 32 keys of this row -> bf16 into the K-major SWIZZLE_128B P tile (128 rows x 64 keys = one 128-byte row each)
-      const uint32_t rbase = sP + (uint32_t)row * 128u;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t addr = rbase + (uint32_t)(((colhalf * 4 + q) ^ (row & 7)) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
-                     "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
-                     : "memory");
-      }
-    }
-    if (tid < 64 && it + 1 < n_it) {
-      const int kk = k0 + 64 + tid;
-      s_kvalid[b ^ 1][tid] = kk < T ? key_valid[kk] : 0;
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      mbar_wait(bar_v0 + 8 * b, use_ph);
-      tc_fence_after();
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma_bf16(tmem + tO, desc_p(sP, ks), C::desc_mn(sV0 + b * (TILE / 2), ks), idesc_o, (it > 0 || ks > 0));
-      umma_commit(bar_o);
-    }
-  }
-  mbar_wait(bar_o, (uint32_t)(n_it - 1) & 1u);
-  tc_fence_after();
-  {
-    // warp (quarter, colhalf) stores columns [colhalf * DH/2, +DH/2) of its 32 rows
-    constexpr int HALF = DH / 2;
+    if (n_it > 1) mbar_wait(bar_o0 + 8 * ((n_it - 2) & 1), (uint32_t)((n_it - 2) >> 1) & 1u);
+    mbar_wait(bar_o0 + 8 * ((n_it - 1) & 1), (uint32_t)((n_it - 1) >> 1) & 1u);
+    tc_fence_after();
+    constexpr int HALF = DH / 2;     // warp (quarter, colhalf) stores columns [colhalf * DH/2, +DH/2) of its 32 rows
 #pragma unroll 1
     for (int c = 0; c < HALF / 16; ++c) {
       uint32_t r[16];
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-          : "r"(t_lane + tO + colhalf * HALF + c * 16));
-      tmem_ld_wait();
+      tmem_ld_32x32b_x16(t_lane + tO + colhalf * HALF + c * 16, r);
       if (ti < T) {
         float* dst = out + (int64_t)ti * D + h * DH + colhalf * HALF + c * 16;
 #pragma unroll
@@ -402,7 +439,7 @@ attn_tc_fwd_pipe_kernel(const __grid_constant__ CUtensorMap map128, const __grid
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem, 256);
   }
@@ -670,34 +707,15 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map128, const __grid_
 
 
 // --------------------------------------------------------------------------------------- backward, pipelined
-// Both backward passes keep the two-CTAs-per-SM ping-pong (one CTA's pointwise phase runs under the other's MMAs) and
-// take the operand loads off the critical path: K / V (dQ pass) and Q / dO (dK,dV pass) tiles are prefetched into
-// rotating shared-memory buffers a full iteration ahead, the next tile's S / dA MMAs are issued back to back with this
-// tile's gradient MMA by the same elected thread (ONE commit covers all three, so one wait at the top of the next
-// iteration also proves that the dS / P buffers and the oldest operand buffer are free), 256 threads share the rows two
-// per row, unmasked chunks skip the compares and 1/n_pad is applied once per output row.
-// 32 packed bf16 pairs of this thread's chunk -> K-major SWIZZLE_128B tile [128 rows x 64 cols]
-__device__ __forceinline__ void put_pk32_sw128(uint32_t tile, int row, int colhalf, const uint32_t (&pk)[16]) {
-  const uint32_t rbase = tile + (uint32_t)row * 128u;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint32_t addr = rbase + (uint32_t)(((colhalf * 4 + q) ^ (row & 7)) << 4);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
-                 "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3])
-                 : "memory");
-  }
-}
-__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  tmem_ld_wait();
-}
-
+// Both backward passes use the same warp-specialised structure as the forward (warps 0..7 pointwise, warp 8 issuer, no
+// block barrier in the loop).  S and dA are single-buffered (TMEM: S | dA | gradient accumulators = 256 columns, two
+// CTAs per SM), so inside one CTA the pointwise phase and the S / dA MMAs of the next tile alternate; the second CTA
+// of the SM fills the gaps.  The next tile's S / dA MMAs are issued back to back with this tile's gradient MMAs, ONE
+// commit covers them all: a single wait at the top of the next iteration also proves that the dS / P buffers and the
+// oldest operand buffer are free.  Operand tiles (K, V for the dQ pass; Q, dO for the dK/dV pass) are prefetched into
+// shared-memory rings >= 1 iteration ahead; unmasked chunks skip the compares; 1/n_pad is applied once per output row.
 template <int DH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(AT_THREADS)
 attn_tc_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map64,
                            const __grid_constant__ CUtensorMap mapdo128, const int32_t* __restrict__ seq_off, int B,
                            const uint8_t* __restrict__ key_valid, int T, int D, float inv_n,
@@ -706,145 +724,140 @@ attn_tc_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap map128, const __g
   constexpr uint32_t TILE = 128 * C::SWZ, HT = TILE / 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = base, sdO = sQ + TILE, sK0 = sdO + TILE, sV0 = sK0 + 3 * HT, sdS = sV0 + 2 * HT;
+  const uint32_t sQ = base, sdO = sQ + TILE, sK0 = sdO + TILE, sV0 = sK0 + 3 * HT, sdS = sV0 + 3 * HT;
   const uint32_t bars = sdS + 16384;
-  const uint32_t bar_q = bars, bar_k0 = bars + 8, bar_v0 = bars + 32, bar_s = bars + 48, bar_fin = bars + 56,
-                 tslot = bars + 64;
-  __shared__ uint8_t s_kvalid[2][64];
+  const uint32_t bar_q = bars, bar_k0 = bars + 8, bar_v0 = bars + 32, bar_s = bars + 56, bar_g = bars + 64,
+                 bar_p = bars + 72, tslot = bars + 80;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quarter = warp & 3, colhalf = warp >> 2;
   const int q0 = blockIdx.x * 128, h = blockIdx.y;
-  const int row = quarter * 32 + lane;
-  const int ti = q0 + row;
   if (tid == 0) {
-    tma_prefetch_desc(&map128); tma_prefetch_desc(&map64); tma_prefetch_desc(&mapdo128);
     mbar_init(bar_q, 1);
     for (int i = 0; i < 3; ++i) mbar_init(bar_k0 + 8 * i, 1);
-    for (int i = 0; i < 2; ++i) mbar_init(bar_v0 + 8 * i, 1);
-    mbar_init(bar_s, 1); mbar_init(bar_fin, 1);
+    for (int i = 0; i < 3; ++i) mbar_init(bar_v0 + 8 * i, 1);
+    mbar_init(bar_s, 1); mbar_init(bar_g, 1);
+    mbar_init(bar_p, 256);
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc(tslot, 256);
-  const int kt_first = seq_off[find_seq(seq_off, B, q0)] >> 6;
-  const int kt_last = min(q0 + 127, T - 1) >> 6;
-  const int n_it = kt_last - kt_first + 1;
-  if (tid < 64) {
-    const int kk = kt_first * 64 + tid;
-    s_kvalid[0][tid] = kk < T ? key_valid[kk] : 0;
-  }
+  if (warp == 8) tmem_alloc(tslot, 256);
+  __shared__ int32_t s_seq[AT_SEQ_SMEM];
+  const SeqTab seqs = seq_tab_load(s_seq, seq_off, B);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  const int kt_first = seqs.p[find_seq(seqs, q0)] >> 6;
+  const int kt_last = min(q0 + 127, T - 1) >> 6;
+  const int n_it = kt_last - kt_first + 1;
   uint32_t tmem;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot));
-  const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16);
   const uint32_t tS = 0, tdA = 64, tdQ = 128;
 
-  const int my_start = ti < T ? seq_off[find_seq(seq_off, B, ti)] : INT_MAX;
-  const int w_min_start = warp_min_i(my_start);
-  const int w_max_start = warp_max_i(ti < T ? my_start : INT_MIN);
-  const int w_min_t = q0 + quarter * 32;
-  const int w_max_t = min(q0 + quarter * 32 + 31, T - 1);
-  const bool w_all_rows = q0 + quarter * 32 + 31 < T;
-  const uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
-  const uint32_t idesc_q = umma_idesc_bf16(128, DH, 0, 1);
-  auto issue_s_da = [&](int it) {   // S(it) = Q K^T, dA(it) = dO V^T  (elected thread)
-    const uint32_t k = sK0 + (uint32_t)(it % 3) * HT, v = sV0 + (uint32_t)(it & 1) * HT;
-#pragma unroll
-    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16(tmem + tS, C::desc_k(sQ, ks), C::desc_k(k, ks), idesc_s, ks > 0);
-#pragma unroll
-    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16(tmem + tdA, C::desc_k(sdO, ks), C::desc_k(v, ks), idesc_s, ks > 0);
-  };
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_q, 2 * TILE);
-    tma_load_2d(sQ, &map128, bar_q, 2 * D + h * DH, q0);
-    tma_load_2d(sdO, &mapdo128, bar_q, h * DH, q0);
-    for (int i = 0; i < 2 && i < n_it; ++i) {
-      mbar_arrive_expect_tx(bar_k0 + 8 * i, HT);
-      tma_load_2d(sK0 + i * HT, &map64, bar_k0 + 8 * i, 3 * D + h * DH, (kt_first + i) * 64);
-      mbar_arrive_expect_tx(bar_v0 + 8 * i, HT);
-      tma_load_2d(sV0 + i * HT, &map64, bar_v0 + 8 * i, 1 * D + h * DH, (kt_first + i) * 64);
-    }
-    mbar_wait(bar_q, 0);
-    mbar_wait(bar_k0, 0);
-    mbar_wait(bar_v0, 0);
-    tc_fence_after();
-    issue_s_da(0);
-    umma_commit(bar_s);
-  }
-  for (int it = 0; it < n_it; ++it) {
-    const int b2 = it & 1;
-    const int k0 = (kt_first + it) * 64;
-    mbar_wait(bar_s, (uint32_t)it & 1u);        // S(it), dA(it) and dQ(it-1) retired
-    tc_fence_after();
-    if (tid == 0 && it + 2 < n_it) {
-      const int j = (it + 2) % 3;                // held K(it-1): free
-      mbar_arrive_expect_tx(bar_k0 + 8 * j, HT);
-      tma_load_2d(sK0 + j * HT, &map64, bar_k0 + 8 * j, 3 * D + h * DH, k0 + 128);
-      mbar_arrive_expect_tx(bar_v0 + 8 * b2, HT);   // held V(it): dA(it) retired
-      tma_load_2d(sV0 + b2 * HT, &map64, bar_v0 + 8 * b2, 1 * D + h * DH, k0 + 128);
-    }
-    const int c0 = k0 + colhalf * 32;
-    uint32_t pk[16];
-    __syncwarp();
-    if (c0 > w_max_t || c0 + 31 < w_min_start) {   // warp-uniform: chunk fully masked
-#pragma unroll
-      for (int e = 0; e < 16; ++e) pk[e] = 0u;
-    } else {
-      float sv[32], da[32];
-      tmem_ld_32x32(t_lane + tS + colhalf * 32, sv);
-      tmem_ld_32x32(t_lane + tdA + colhalf * 32, da);
-      const bool kv_all = __all_sync(0xffffffffu, s_kvalid[b2][colhalf * 32 + lane] != 0);
-      if (w_all_rows && c0 + 31 <= w_min_t && c0 >= w_max_start && kv_all) {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(da[2 * e] * silu_grad_fast_f(sv[2 * e]),
-                                                    da[2 * e + 1] * silu_grad_fast_f(sv[2 * e + 1]));
-          pk[e] = *reinterpret_cast<uint32_t*>(&h2);
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float a[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int tj = c0 + 2 * e + u;
-            const bool keep = (tj <= ti) && (tj >= my_start) && s_kvalid[b2][colhalf * 32 + 2 * e + u];
-            a[u] = keep ? da[2 * e + u] * silu_grad_fast_f(sv[2 * e + u]) : 0.f;
-          }
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(a[0], a[1]);
-          pk[e] = *reinterpret_cast<uint32_t*>(&h2);
-        }
-      }
-    }
-    put_pk32_sw128(sdS, row, colhalf, pk);
-    if (tid < 64 && it + 1 < n_it) {
-      const int kk = k0 + 64 + tid;
-      s_kvalid[b2 ^ 1][tid] = kk < T ? key_valid[kk] : 0;
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t k = sK0 + (uint32_t)(it % 3) * HT;
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma_bf16(tmem + tdQ, desc_p(sdS, ks), C::desc_mn(k, ks), idesc_q, (it > 0 || ks > 0));      // dQ += dS K
-      if (it + 1 < n_it) {
-        mbar_wait(bar_k0 + 8 * ((it + 1) % 3), (uint32_t)((it + 1) / 3) & 1u);
-        mbar_wait(bar_v0 + 8 * (b2 ^ 1), (uint32_t)((it + 1) >> 1) & 1u);
+  if (warp == 8) {
+    if (lane == 0) {
+      tma_prefetch_desc(&map128); tma_prefetch_desc(&map64); tma_prefetch_desc(&mapdo128);
+      const uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+      const uint32_t idesc_q = umma_idesc_bf16(128, DH, 0, 1);
+      auto load_k = [&](int it) {
+        const int j = it % 3;
+        mbar_arrive_expect_tx(bar_k0 + 8 * j, HT);
+        tma_load_2d(sK0 + j * HT, &map64, bar_k0 + 8 * j, 3 * D + h * DH, (kt_first + it) * 64);
+      };
+      auto load_v = [&](int it) {
+        const int j = it % 3;
+        mbar_arrive_expect_tx(bar_v0 + 8 * j, HT);
+        tma_load_2d(sV0 + j * HT, &map64, bar_v0 + 8 * j, 1 * D + h * DH, (kt_first + it) * 64);
+      };
+      auto issue_s_da = [&](int it) {   // S(it) = Q K^T, dA(it) = dO V^T
+        mbar_wait(bar_k0 + 8 * (it % 3), (uint32_t)(it / 3) & 1u);
+        mbar_wait(bar_v0 + 8 * (it % 3), (uint32_t)(it / 3) & 1u);
         tc_fence_after();
-        issue_s_da(it + 1);
-        umma_commit(bar_s);
-      } else {
-        umma_commit(bar_fin);
+        const uint32_t k = sK0 + (uint32_t)(it % 3) * HT, v = sV0 + (uint32_t)(it % 3) * HT;
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks) umma_bf16(tmem + tS, C::desc_k(sQ, ks), C::desc_k(k, ks), idesc_s, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks) umma_bf16(tmem + tdA, C::desc_k(sdO, ks), C::desc_k(v, ks), idesc_s, ks > 0);
+      };
+      mbar_arrive_expect_tx(bar_q, 2 * TILE);
+      tma_load_2d(sQ, &map128, bar_q, 2 * D + h * DH, q0);
+      tma_load_2d(sdO, &mapdo128, bar_q, h * DH, q0);
+      for (int i = 0; i < 3 && i < n_it; ++i) { load_k(i); load_v(i); }
+      mbar_wait(bar_q, 0);
+      issue_s_da(0);
+      umma_commit(bar_s);
+      for (int it = 0; it < n_it; ++it) {
+        // dS(it) written; S / dA(it) consumed.  The pointwise threads waited for bar_g(it-1) (dQ(it-1) retired) before
+        // they wrote dS(it): K(it-1)'s ring slot is free; V(it)'s slot is free since dA(it) retired (bar_s(it))
+        mbar_wait(bar_p, (uint32_t)it & 1u);
+        tc_fence_after();
+        if (it >= 1 && it + 2 < n_it) load_k(it + 2);
+        if (it + 3 < n_it) load_v(it + 3);
+        // next tile's S / dA FIRST (the pointwise threads are waiting for them), this tile's dQ behind them: it retires
+        // under the next pointwise phase
+        if (it + 1 < n_it) {
+          issue_s_da(it + 1);
+          umma_commit(bar_s);
+        }
+        const uint32_t k = sK0 + (uint32_t)(it % 3) * HT;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16(tmem + tdQ, desc_p(sdS, ks), C::desc_mn(k, ks), idesc_q, (it > 0 || ks > 0));      // dQ += dS K
+        umma_commit(bar_g);
       }
     }
-  }
-  mbar_wait(bar_fin, 0);
-  tc_fence_after();
-  {
+  } else {
+    const int quarter = warp & 3, colhalf = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const int ti = q0 + row;
+    const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16);
+    const int my_start = ti < T ? seqs.p[find_seq(seqs, ti)] : INT_MAX;
+    const int w_min_start = warp_min_i(my_start);
+    const int w_max_start = warp_max_i(ti < T ? my_start : INT_MIN);
+    const int w_min_t = q0 + quarter * 32;
+    const int w_max_t = min(q0 + quarter * 32 + 31, T - 1);
+    const bool w_all_rows = q0 + quarter * 32 + 31 < T;
+    for (int it = 0; it < n_it; ++it) {
+      const int c0 = (kt_first + it) * 64 + colhalf * 32;
+      const bool skip = c0 > w_max_t || c0 + 31 < w_min_start;   // warp-uniform: chunk fully masked
+      const uint32_t kvb = skip ? 0u : kvalid_bits(key_valid, c0, lane, T);
+      mbar_wait(bar_s, (uint32_t)it & 1u);        // S(it), dA(it) retired
+      tc_fence_after();
+      uint32_t pk[16];
+      if (skip) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pk[e] = 0u;
+      } else {
+        float sv[32], da[32];
+        tmem_ld_32x32(t_lane + tS + colhalf * 32, sv);
+        tmem_ld_32x32(t_lane + tdA + colhalf * 32, da);
+        if (w_all_rows && c0 + 31 <= w_min_t && c0 >= w_max_start && kvb == 0xffffffffu) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(da[2 * e] * silu_grad_fast_f(sv[2 * e]),
+                                                      da[2 * e + 1] * silu_grad_fast_f(sv[2 * e + 1]));
+            pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float a[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int tj = c0 + 2 * e + u;
+              const bool keep = (tj <= ti) && (tj >= my_start) && ((kvb >> (2 * e + u)) & 1u);
+              a[u] = keep ? da[2 * e + u] * silu_grad_fast_f(sv[2 * e + u]) : 0.f;
+            }
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(a[0], a[1]);
+            pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+        }
+      }
+      if (it > 0) mbar_wait(bar_g, (uint32_t)(it - 1) & 1u);    // dQ(it-1) retired: sdS is free
+      put_pk32_sw128(sdS, row, colhalf, pk);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+    }
+    mbar_wait(bar_g, (uint32_t)(n_it - 1) & 1u);
+    tc_fence_after();
     constexpr int HALF = DH / 2;
 #pragma unroll 1
     for (int c = 0; c < HALF / 16; ++c) {
@@ -865,14 +878,14 @@ attn_tc_bwd_dq_pipe_kernel(const __grid_constant__ CUtensorMap map128, const __g
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem, 256);
   }
 }
 
 template <int DH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(AT_THREADS)
 attn_tc_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap map128, const __grid_constant__ CUtensorMap map64,
                             const __grid_constant__ CUtensorMap mapdo64, const int32_t* __restrict__ seq_off, int B,
                             const uint8_t* __restrict__ key_valid, int T, int D, float inv_n,
@@ -884,151 +897,173 @@ attn_tc_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap map128, const __
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sK = base, sV = sK + TILE, sQ0 = sV + TILE, sdO0 = sQ0 + 2 * HT, sPT = sdO0 + 2 * HT, sdST = sPT + 16384;
   const uint32_t bars = sdST + 16384;
-  const uint32_t bar_kv = bars, bar_q0 = bars + 8, bar_s = bars + 24, bar_fin = bars + 32, tslot = bars + 40;
-  __shared__ int s_qstart[2][64];
-  __shared__ int s_qsmax[2][2];      // per 32-query chunk: latest sequence start (INT_MAX when a query is beyond T)
+  const uint32_t bar_kv = bars, bar_q0 = bars + 8, bar_s = bars + 24, bar_g = bars + 32, bar_p = bars + 40,
+                 bar_m0 = bars + 48, tslot = bars + 64;
+  __shared__ int s_qstart[2][64];    // sequence start of every query of the tile (INT_MAX beyond T), by the issuer warp
+  __shared__ int s_qsmax[2][2];      // per 32-query chunk: the latest of them
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quarter = warp & 3, colhalf = warp >> 2;
   const int k0 = blockIdx.x * 128, h = blockIdx.y;
-  const int row = quarter * 32 + lane;
-  const int tj = k0 + row;
   if (tid == 0) {
-    tma_prefetch_desc(&map128); tma_prefetch_desc(&map64); tma_prefetch_desc(&mapdo64);
     mbar_init(bar_kv, 1);
-    for (int i = 0; i < 2; ++i) mbar_init(bar_q0 + 8 * i, 1);
-    mbar_init(bar_s, 1); mbar_init(bar_fin, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_q0 + 8 * i, 1); mbar_init(bar_m0 + 8 * i, 32); }
+    mbar_init(bar_s, 1); mbar_init(bar_g, 1);
+    mbar_init(bar_p, 256);
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc(tslot, 256);
-  const bool kv_ok = tj < T && key_valid[tj] != 0;
-  const int k_last = min(k0 + 127, T - 1);
-  const int q_hi = seq_off[find_seq(seq_off, B, k_last) + 1] - 1;   // last token of the last key's sequence
-  const int qt_first = k0 >> 6, qt_last = q_hi >> 6;
-  const int n_it = qt_last - qt_first + 1;
-  auto load_qstart = [&](int buf, int i0) {      // threads 0..63: sequence start of every query of the tile
-    const int qs = (i0 + tid < T) ? seq_off[find_seq(seq_off, B, i0 + tid)] : INT_MAX;
-    s_qstart[buf][tid] = qs;
-    const int mx = warp_max_i(qs);
-    if (lane == 0) s_qsmax[buf][warp] = mx;
-  };
-  if (tid < 64) load_qstart(0, qt_first * 64);
+  if (warp == 8) tmem_alloc(tslot, 256);
+  __shared__ int32_t s_seq[AT_SEQ_SMEM];
+  const SeqTab seqs = seq_tab_load(s_seq, seq_off, B);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  const int k_last = min(k0 + 127, T - 1);
+  const int q_hi = seqs.p[find_seq(seqs, k_last) + 1] - 1;   // last token of the last key's sequence
+  const int qt_first = k0 >> 6, qt_last = q_hi >> 6;
+  const int n_it = qt_last - qt_first + 1;
   uint32_t tmem;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot));
-  const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16);
   const uint32_t tS = 0, tdA = 64, tdK = 128, tdV = 192;
-  const bool w_kv_all = __all_sync(0xffffffffu, kv_ok);
-  const int w_key_lo = k0 + quarter * 32, w_key_hi = k0 + quarter * 32 + 31;
-  const uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
-  const uint32_t idesc_g = umma_idesc_bf16(128, DH, 0, 1);
-  auto issue_s_da = [&](int it) {   // S^T(it) = K Q^T, dA^T(it) = V dO^T
-    const uint32_t q = sQ0 + (uint32_t)(it & 1) * HT, g = sdO0 + (uint32_t)(it & 1) * HT;
+
+  if (warp == 8) {
+    // every lane: query metadata of a tile (two queries per lane) -> s_qstart / s_qsmax, published through bar_m
+    auto meta = [&](int it) {
+      const int buf = it & 1, i0 = (qt_first + it) * 64;
 #pragma unroll
-    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16(tmem + tS, C::desc_k(sK, ks), C::desc_k(q, ks), idesc_s, ks > 0);
-#pragma unroll
-    for (int ks = 0; ks < DH / 16; ++ks) umma_bf16(tmem + tdA, C::desc_k(sV, ks), C::desc_k(g, ks), idesc_s, ks > 0);
-  };
-  auto load_q_do = [&](int it) {
-    const int j = it & 1, i0 = (qt_first + it) * 64;
-    mbar_arrive_expect_tx(bar_q0 + 8 * j, TILE);
-    tma_load_2d(sQ0 + j * HT, &map64, bar_q0 + 8 * j, 2 * D + h * DH, i0);
-    tma_load_2d(sdO0 + j * HT, &mapdo64, bar_q0 + 8 * j, h * DH, i0);
-  };
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_kv, 2 * TILE);
-    tma_load_2d(sK, &map128, bar_kv, 3 * D + h * DH, k0);
-    tma_load_2d(sV, &map128, bar_kv, 1 * D + h * DH, k0);
-    load_q_do(0);
-    if (n_it > 1) load_q_do(1);
-    mbar_wait(bar_kv, 0);
-    mbar_wait(bar_q0, 0);
-    tc_fence_after();
-    issue_s_da(0);
-    umma_commit(bar_s);
-  }
-  for (int it = 0; it < n_it; ++it) {
-    const int b = it & 1;
-    const int i0 = (qt_first + it) * 64;
-    mbar_wait(bar_s, (uint32_t)it & 1u);        // S^T(it), dA^T(it), dV(it-1), dK(it-1) retired
-    tc_fence_after();
-    if (tid == 0 && it >= 1 && it + 1 < n_it) load_q_do(it + 1);   // buffer of tile it-1 is free
-    const int c0 = i0 + colhalf * 32;            // first query of this thread's chunk
-    uint32_t pp[16], pd[16];
-    __syncwarp();
-    if (c0 + 31 < w_key_lo) {                    // warp-uniform: every query of the chunk precedes every key
-#pragma unroll
-      for (int e = 0; e < 16; ++e) { pp[e] = 0u; pd[e] = 0u; }
-    } else {
-      float sv[32], da[32];
-      tmem_ld_32x32(t_lane + tS + colhalf * 32, sv);
-      tmem_ld_32x32(t_lane + tdA + colhalf * 32, da);
-      const bool fast = w_kv_all && c0 >= w_key_hi && s_qsmax[b][colhalf] <= w_key_lo;
-      if (fast) {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float p2[2], d2[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const float x = sv[2 * e + u];
-            const float sg = sigmoid_fast_f(x);                      // ONE MUFU for both P^T and dS^T
-            p2[u] = x * sg;
-            d2[u] = da[2 * e + u] * sg * fmaf(x, 1.f - sg, 1.f);
-          }
-          __nv_bfloat162 hp = __floats2bfloat162_rn(p2[0], p2[1]);
-          __nv_bfloat162 hd = __floats2bfloat162_rn(d2[0], d2[1]);
-          pp[e] = *reinterpret_cast<uint32_t*>(&hp);
-          pd[e] = *reinterpret_cast<uint32_t*>(&hd);
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float p2[2], d2[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int tq = c0 + 2 * e + u;
-            const bool keep = kv_ok && (tj <= tq) && (tj >= s_qstart[b][colhalf * 32 + 2 * e + u]);
-            const float x = sv[2 * e + u];
-            const float sg = sigmoid_fast_f(x);
-            p2[u] = keep ? x * sg : 0.f;
-            d2[u] = keep ? da[2 * e + u] * sg * fmaf(x, 1.f - sg, 1.f) : 0.f;
-          }
-          __nv_bfloat162 hp = __floats2bfloat162_rn(p2[0], p2[1]);
-          __nv_bfloat162 hd = __floats2bfloat162_rn(d2[0], d2[1]);
-          pp[e] = *reinterpret_cast<uint32_t*>(&hp);
-          pd[e] = *reinterpret_cast<uint32_t*>(&hd);
-        }
+      for (int half = 0; half < 2; ++half) {
+        const int q = i0 + half * 32 + lane;
+        const int qs = q < T ? seqs.p[find_seq(seqs, q)] : INT_MAX;
+        s_qstart[buf][half * 32 + lane] = qs;
+        const int mx = warp_max_i(qs);
+        if (lane == 0) s_qsmax[buf][half] = mx;
       }
-    }
-    put_pk32_sw128(sPT, row, colhalf, pp);
-    put_pk32_sw128(sdST, row, colhalf, pd);
-    if (tid < 64 && it + 1 < n_it) load_qstart(b ^ 1, i0 + 64);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
+      mbar_arrive(bar_m0 + 8 * buf);
+    };
+    const uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+    const uint32_t idesc_g = umma_idesc_bf16(128, DH, 0, 1);
+    auto issue_s_da = [&](int it) {   // S^T(it) = K Q^T, dA^T(it) = V dO^T   (lane 0)
+      mbar_wait(bar_q0 + 8 * (it & 1), (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
-      const uint32_t q = sQ0 + (uint32_t)b * HT, g = sdO0 + (uint32_t)b * HT;
+      const uint32_t q = sQ0 + (uint32_t)(it & 1) * HT, g = sdO0 + (uint32_t)(it & 1) * HT;
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma_bf16(tmem + tdV, desc_p(sPT, ks), C::desc_mn(g, ks), idesc_g, (it > 0 || ks > 0));   // dV += P^T dO
+      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16(tmem + tS, C::desc_k(sK, ks), C::desc_k(q, ks), idesc_s, ks > 0);
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma_bf16(tmem + tdK, desc_p(sdST, ks), C::desc_mn(q, ks), idesc_g, (it > 0 || ks > 0));  // dK += dS^T Q
-      if (it + 1 < n_it) {
-        mbar_wait(bar_q0 + 8 * (b ^ 1), (uint32_t)((it + 1) >> 1) & 1u);
-        tc_fence_after();
-        issue_s_da(it + 1);
-        umma_commit(bar_s);
-      } else {
-        umma_commit(bar_fin);
-      }
+      for (int ks = 0; ks < DH / 16; ++ks) umma_bf16(tmem + tdA, C::desc_k(sV, ks), C::desc_k(g, ks), idesc_s, ks > 0);
+    };
+    auto load_q_do = [&](int it) {
+      const int j = it & 1, i0 = (qt_first + it) * 64;
+      mbar_arrive_expect_tx(bar_q0 + 8 * j, TILE);
+      tma_load_2d(sQ0 + j * HT, &map64, bar_q0 + 8 * j, 2 * D + h * DH, i0);
+      tma_load_2d(sdO0 + j * HT, &mapdo64, bar_q0 + 8 * j, h * DH, i0);
+    };
+    if (lane == 0) {
+      tma_prefetch_desc(&map128); tma_prefetch_desc(&map64); tma_prefetch_desc(&mapdo64);
+      mbar_arrive_expect_tx(bar_kv, 2 * TILE);
+      tma_load_2d(sK, &map128, bar_kv, 3 * D + h * DH, k0);
+      tma_load_2d(sV, &map128, bar_kv, 1 * D + h * DH, k0);
+      load_q_do(0);
+      if (n_it > 1) load_q_do(1);
     }
-  }
-  mbar_wait(bar_fin, 0);
-  tc_fence_after();
-  {
+    __syncwarp();
+    meta(0);
+    if (n_it > 1) meta(1);
+    if (lane == 0) {
+      mbar_wait(bar_kv, 0);
+      issue_s_da(0);
+      umma_commit(bar_s);
+    }
+    __syncwarp();
+    for (int it = 0; it < n_it; ++it) {
+      // P^T / dS^T(it) written; S^T / dA^T(it) consumed.  The pointwise threads waited for bar_g(it-1) (dV / dK(it-1)
+      // retired) before writing: the Q / dO slot of tile it-1 is free; the metadata slot of tile it is free
+      mbar_wait(bar_p, (uint32_t)it & 1u);
+      __syncwarp();
+      if (lane == 0) {
+        tc_fence_after();
+        if (it >= 1 && it + 1 < n_it) load_q_do(it + 1);
+        if (it + 1 < n_it) {                       // next tile's S^T / dA^T first, this tile's dV / dK behind them
+          issue_s_da(it + 1);
+          umma_commit(bar_s);
+        }
+        const uint32_t q = sQ0 + (uint32_t)(it & 1) * HT, g = sdO0 + (uint32_t)(it & 1) * HT;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16(tmem + tdV, desc_p(sPT, ks), C::desc_mn(g, ks), idesc_g, (it > 0 || ks > 0));   // dV += P^T dO
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_bf16(tmem + tdK, desc_p(sdST, ks), C::desc_mn(q, ks), idesc_g, (it > 0 || ks > 0));  // dK += dS^T Q
+        umma_commit(bar_g);
+      }
+      __syncwarp();
+      if (it + 2 < n_it) meta(it + 2);              // slot of tile it: all its readers have arrived on bar_p(it)
+    }
+  } else {
+    const int quarter = warp & 3, colhalf = warp >> 2;
+    const int row = quarter * 32 + lane;
+    const int tj = k0 + row;
+    const uint32_t t_lane = tmem + ((uint32_t)(quarter * 32) << 16);
+    const bool kv_ok = tj < T && key_valid[tj] != 0;
+    const bool w_kv_all = __all_sync(0xffffffffu, kv_ok);
+    const int w_key_lo = k0 + quarter * 32, w_key_hi = k0 + quarter * 32 + 31;
+    for (int it = 0; it < n_it; ++it) {
+      const int b = it & 1;
+      const int c0 = (qt_first + it) * 64 + colhalf * 32;            // first query of this thread's chunk
+      mbar_wait(bar_m0 + 8 * b, (uint32_t)(it >> 1) & 1u);
+      mbar_wait(bar_s, (uint32_t)it & 1u);        // S^T(it), dA^T(it) retired
+      tc_fence_after();
+      uint32_t pp[16], pd[16];
+      if (c0 + 31 < w_key_lo) {                    // warp-uniform: every query of the chunk precedes every key
+#pragma unroll
+        for (int e = 0; e < 16; ++e) { pp[e] = 0u; pd[e] = 0u; }
+      } else {
+        float sv[32], da[32];
+        tmem_ld_32x32(t_lane + tS + colhalf * 32, sv);
+        tmem_ld_32x32(t_lane + tdA + colhalf * 32, da);
+        const bool fast = w_kv_all && c0 >= w_key_hi && s_qsmax[b][colhalf] <= w_key_lo;
+        if (fast) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float p2[2], d2[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const float x = sv[2 * e + u];
+              const float sg = sigmoid_fast_f(x);                      // ONE MUFU for both P^T and dS^T
+              p2[u] = x * sg;
+              d2[u] = da[2 * e + u] * sg * fmaf(x, 1.f - sg, 1.f);
+            }
+            __nv_bfloat162 hp = __floats2bfloat162_rn(p2[0], p2[1]);
+            __nv_bfloat162 hd = __floats2bfloat162_rn(d2[0], d2[1]);
+            pp[e] = *reinterpret_cast<uint32_t*>(&hp);
+            pd[e] = *reinterpret_cast<uint32_t*>(&hd);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float p2[2], d2[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int tq = c0 + 2 * e + u;
+              const bool keep = kv_ok && (tj <= tq) && (tj >= s_qstart[b][colhalf * 32 + 2 * e + u]);
+              const float x = sv[2 * e + u];
+              const float sg = sigmoid_fast_f(x);
+              p2[u] = keep ? x * sg : 0.f;
+              d2[u] = keep ? da[2 * e + u] * sg * fmaf(x, 1.f - sg, 1.f) : 0.f;
+            }
+            __nv_bfloat162 hp = __floats2bfloat162_rn(p2[0], p2[1]);
+            __nv_bfloat162 hd = __floats2bfloat162_rn(d2[0], d2[1]);
+            pp[e] = *reinterpret_cast<uint32_t*>(&hp);
+            pd[e] = *reinterpret_cast<uint32_t*>(&hd);
+          }
+        }
+      }
+      if (it > 0) mbar_wait(bar_g, (uint32_t)(it - 1) & 1u);    // dV / dK(it-1) retired: sPT / sdST are free
+      put_pk32_sw128(sPT, row, colhalf, pp);
+      put_pk32_sw128(sdST, row, colhalf, pd);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+    }
+    mbar_wait(bar_g, (uint32_t)(n_it - 1) & 1u);
+    tc_fence_after();
     constexpr int HALF = DH / 2;
 #pragma unroll 1
     for (int c = 0; c < HALF / 16; ++c) {
@@ -1054,7 +1089,7 @@ attn_tc_bwd_dkv_pipe_kernel(const __grid_constant__ CUtensorMap map128, const __
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem, 256);
   }
@@ -1075,9 +1110,9 @@ static int attn_tc_fwd_launch(const bf16* act_base, int64_t ld, const int32_t* s
     use_pipe = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
   if (use_pipe) {
-    size_t smem_p = 3 * 128 * DH * 2 + 16384 + 256 + 1024;
+    size_t smem_p = 128 * DH * 2 + 6 * 64 * DH * 2 + 2 * 16384 + 256 + 1024;
     { static bool once_p = false; if (!once_p) { B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_pipe_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p)); once_p = true; } }
-    attn_tc_fwd_pipe_kernel<DH><<<grid, 256, smem_p, st>>>(m128, m64, seq_off, B, key_valid, T, D, inv_n, out);
+    attn_tc_fwd_pipe_kernel<DH><<<grid, AT_THREADS, smem_p, st>>>(m128, m64, seq_off, B, key_valid, T, D, inv_n, out);
     B200_LAUNCH_OK();
     return 0;
   }
@@ -1111,15 +1146,15 @@ static int attn_tc_bwd_launch(const bf16* act_base, const bf16* pre_base, int64_
     use_pipe = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
   if (use_pipe) {
-    size_t smem_pq = 2 * 128 * DH * 2 + 5 * 64 * DH * 2 + 16384 + 256 + 1024;
+    size_t smem_pq = 2 * 128 * DH * 2 + 6 * 64 * DH * 2 + 16384 + 256 + 1024;
     size_t smem_pkv = 2 * 128 * DH * 2 + 4 * 64 * DH * 2 + 32768 + 256 + 1024;
     { static bool once_p = false; if (!once_p) {
         B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_bwd_dq_pipe_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pq));
         B200_CUDA_OK(cudaFuncSetAttribute(attn_tc_bwd_dkv_pipe_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pkv));
         once_p = true; } }
-    attn_tc_bwd_dq_pipe_kernel<DH><<<grid, 256, smem_pq, st>>>(m128, m64, do128, seq_off, B, key_valid, T, D, inv_n,
+    attn_tc_bwd_dq_pipe_kernel<DH><<<grid, AT_THREADS, smem_pq, st>>>(m128, m64, do128, seq_off, B, key_valid, T, D, inv_n,
                                                                pre_base + 2 * D, ld, d_pre_base + 2 * D);
-    attn_tc_bwd_dkv_pipe_kernel<DH><<<grid, 256, smem_pkv, st>>>(m128, m64, do64, seq_off, B, key_valid, T, D, inv_n,
+    attn_tc_bwd_dkv_pipe_kernel<DH><<<grid, AT_THREADS, smem_pkv, st>>>(m128, m64, do64, seq_off, B, key_valid, T, D, inv_n,
                                                                  pre_base + 3 * D, pre_base + 1 * D, ld,
                                                                  d_pre_base + 3 * D, d_pre_base + 1 * D);
     B200_LAUNCH_OK();
