@@ -509,6 +509,29 @@ int b200rec_adamw_rows(float* p, float* m, float* v, int64_t n_rows, int D, cons
                        float beta1, float beta2, float eps, float weight_decay, int step,
                        float grad_scale, const float* coef_dev, void* stream);
 
+/* ------------------------------------------------------------------ prior construction
+ * Co-occurrence graph of the reference's clustering scripts (code/item-clustering.py:152-162: all pairs of the distinct
+ * items of a user's training window; code/user-clustering.py:268-290: all pairs of the distinct users of an item,
+ * capped): `members` holds every group's members sorted ascending and de-duplicated, group g = members[group_off[g] ..
+ * group_off[g+1]) (at most `cap` of them are used when cap > 0, the reference's MAX_USERS_PER_ITEM slice).
+ * count: counts[g] = n (n - 1) / 2.  emit: keys[pair_off[g] + p] = (a << 32) | b over all pairs a < b of the group
+ * (pair_off = exclusive prefix sum of counts); a 64-bit sort + unique of the keys is the reference's edge set. */
+int b200rec_group_pairs_count(const int64_t* group_off, int64_t G, int cap, int64_t* counts, void* stream);
+int b200rec_group_pairs_emit(const int32_t* members, const int64_t* group_off, const int64_t* pair_off, int64_t G,
+                             int cap, uint64_t* keys, void* stream);
+/* Modularity local moving (the phase shared by Louvain and by igraph's Leiden, which the reference calls at
+ * code/item-clustering.py:240-245 with objective "modularity" and a resolution): node i's neighbouring communities are
+ * given as runs (run_comm ascending, run_w = summed integer edge weight; no self loops) in [node_off[i], node_off[i+1]).
+ * best_move: best[i] = argmax_C  w(i->C) - gamma * deg[i] * (tot[C] - [C == comm[i]] deg[i]) / two_m  if it beats
+ * staying strictly (ties: smaller id), only for nodes with (i & 1) == parity, never from a singleton to a singleton of
+ * larger id; IEEE double, no contraction.  apply: moves every node to best[i], updates tot / csize with integer atomics
+ * (exact in any order) and counts the moves in *moved. */
+int b200rec_louvain_best_move(const int64_t* node_off, const int32_t* run_comm, const int64_t* run_w,
+                              const int32_t* comm, const int64_t* deg, const int64_t* tot, const int32_t* csize,
+                              int64_t n, int64_t two_m, double gamma, int parity, int32_t* best, void* stream);
+int b200rec_louvain_apply(const int32_t* best, int32_t* comm, const int64_t* deg, int64_t* tot, int32_t* csize,
+                          int64_t n, uint64_t* moved, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

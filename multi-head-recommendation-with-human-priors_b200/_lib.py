@@ -137,6 +137,10 @@ _SIGS = {
     "b200rec_adamw": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P, _P]),
     "b200rec_adamw_tick": (C.c_int, [_P, _F, _F, _P]),
     "b200rec_adamw_multi": (C.c_int, [_P, _P, _I, _F, _F, _F, _F, _F, _I, _F, _P, _P]),
+    "b200rec_group_pairs_count": (C.c_int, [_P, _L, _I, _P, _P]),
+    "b200rec_group_pairs_emit": (C.c_int, [_P, _P, _P, _L, _I, _P, _P]),
+    "b200rec_louvain_best_move": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _L, _L, C.c_double, _I, _P, _P]),
+    "b200rec_louvain_apply": (C.c_int, [_P, _P, _P, _P, _P, _L, _P, _P]),
     "b200rec_adamw_rows": (C.c_int, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _F, _F, _F, _F, _F, _I, _F, _P, _P]),
 }
 EXPORTS = ["b200rec_last_error"] + sorted(_SIGS)
