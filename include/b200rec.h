@@ -532,6 +532,26 @@ int b200rec_louvain_best_move(const int64_t* node_off, const int32_t* run_comm, 
 int b200rec_louvain_apply(const int32_t* best, int32_t* comm, const int64_t* deg, int64_t* tot, int32_t* csize,
                           int64_t n, uint64_t* moved, void* stream);
 
+/* ------------------------------------------------------------------ ComiRec-SA readout on the HSTU body
+ * Replaces REC/model/IDNet/comirec.py:232-300 (+ autograd): self-attentive multi-interest pooling over the causal
+ * context and the hard readout against the future targets.  fp32, jagged tokens (valid positions only).
+ *   pool_fwd:   u[t, k, :] = sum_{t' <= t in t's sequence} softmax_{t'}(a[t', k]) y[t', :]  in one online-softmax pass per
+ *               (sequence, interest); M / S [T, K] = running maximum / denominator, kept for the backward.
+ *   select_fwd: for token t and offset p, best = first argmax_k <u[t, k], traw[tok_b * LP + tok_pos + 1 + p]>,
+ *               hd[t, p, :] = u[t, best, :], sel[t, p] = best.
+ *   select_bwd: du[t, k, :] = sum_p [sel[t, p] == k] d_hd[t, p, :].
+ *   pool_bwd:   dy[t, :] += ..., da[t, k] = ...  (closed form of the softmax-pooling gradient via suffix sums).
+ *   tanh / tanh_bwd: the attention net's activation (in place). */
+int b200rec_comi_tanh(float* z, int64_t n, void* stream);
+int b200rec_comi_tanh_bwd(const float* h, float* dh, int64_t n, void* stream);
+int b200rec_comi_pool_fwd(const float* a, const float* y, const int32_t* seq_off, int B, int K, int D, float* u, float* M,
+                          float* S, void* stream);
+int b200rec_comi_select_fwd(const float* u, const float* traw, const int32_t* tok_b, const int32_t* tok_pos, int T, int LP,
+                            int P, int K, int D, float* hd, int32_t* sel, void* stream);
+int b200rec_comi_select_bwd(const float* d_hd, const int32_t* sel, int T, int P, int K, int D, float* du, void* stream);
+int b200rec_comi_pool_bwd(const float* du, const float* u, const float* y, const float* a, const float* M, const float* S,
+                          const int32_t* seq_off, int B, int K, int D, float* dy, float* da, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -141,6 +141,12 @@ _SIGS = {
     "b200rec_group_pairs_emit": (C.c_int, [_P, _P, _P, _L, _I, _P, _P]),
     "b200rec_louvain_best_move": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _L, _L, C.c_double, _I, _P, _P]),
     "b200rec_louvain_apply": (C.c_int, [_P, _P, _P, _P, _P, _L, _P, _P]),
+    "b200rec_comi_tanh": (C.c_int, [_P, _L, _P]),
+    "b200rec_comi_tanh_bwd": (C.c_int, [_P, _P, _L, _P]),
+    "b200rec_comi_pool_fwd": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "b200rec_comi_select_fwd": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "b200rec_comi_select_bwd": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    "b200rec_comi_pool_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "b200rec_adamw_rows": (C.c_int, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _F, _F, _F, _F, _F, _I, _F, _P, _P]),
 }
 EXPORTS = ["b200rec_last_error"] + sorted(_SIGS)

@@ -233,6 +233,7 @@ class HSTU(nn.Module):
         self._verbose = False
         self._switch_logs = {}
         self._debug = None         # dict: when set, forward / backward stash clones of key intermediates (diagnostics)
+        self._readout = getattr(self, "_readout", None)   # comirec.ComiRec: multi-interest readout instead of decode heads
         self.reset_params()
         self._jobs = self._build_jobs()
 
@@ -837,7 +838,13 @@ class HSTU(nn.Module):
                tok_b.data_ptr(), tok_pos.data_ptr(), T, LP, D, x.data_ptr(), st)
         self._simt_len = T if static else 0      # dummy sequence of static-token mode: up to T tokens long
         y, saved = self._body_forward(x, w, seq_off, key_valid, B, T, Lc, Lc, need_grad)
-        hd, z, yb = self._heads_forward(y, w, T)
+        comi = None
+        if self._readout is not None:
+            # ComiRec (comirec.py): the queries are interests pooled over the causal context, one per offset
+            hd, comi = self._readout.train_forward(self, y, W, items, tok_b, tok_pos, seq_off, B, LP, T)
+            z = yb = None
+        else:
+            hd, z, yb = self._heads_forward(y, w, T)
         Hx = hd.shape[1]
         qhat = torch.empty((T * Hx, D), dtype=act, device=dev)
         qinv = torch.empty(T * Hx, dtype=torch.float32, device=dev)
@@ -893,7 +900,7 @@ class HSTU(nn.Module):
         scale = self.logit_scale.data.to(torch.float32)
         job_out = []
         qv = qhat.view(T, Hx * D)
-        hqs = [j.head if self.medusa_num_layers > 0 else 0 for j in self._jobs]
+        hqs = [j.head if (self.medusa_num_layers > 0 or self._readout is not None) else 0 for j in self._jobs]
         fused = act == torch.bfloat16 and self.use_fused_nce and D % 4 == 0 and D <= 2048
         if fused:
             # fused path: no fp32 [T, Nneg] logits in HBM.  positives + row reference -> ONE grouped
@@ -1016,7 +1023,7 @@ class HSTU(nn.Module):
                        items=items, mask=m, n_neg=n_neg, ld_neg=ld_neg, Hx=Hx, used_sets=used_sets,
                        gl_items=gl_items, gl_neg_ids=gl_neg_ids, uniq_rows_ids=uniq_rows_ids,
                        n_cache_rows=W.shape[0], push=prepared.get("push", True), cache_info=prepared.get("info"),
-                       grad_out=prepared.get("grad_out"), switch=sw, table=W)
+                       grad_out=prepared.get("grad_out"), switch=sw, table=W, comi=comi)
         return loss, logs, ctx
 
     def _train_backward(self, ctx, gscale):
@@ -1090,7 +1097,9 @@ class HSTU(nn.Module):
         L.call("b200rec_l2norm_bwd", ctx["qhat"].data_ptr(), a_dt, ctx["qinv"].data_ptr(), dqhat.data_ptr(), T * Hx, D,
                d_hd.data_ptr(), 0, st)
         dy = torch.empty((T, D), dtype=torch.float32, device=dev)
-        if self.medusa_num_layers > 0 and self.head_interaction == "hierarchical":
+        if self._readout is not None:
+            dy = self._readout.train_backward(self, d_hd, ctx, grads)
+        elif self.medusa_num_layers > 0 and self.head_interaction == "hierarchical":
             dy = self._hier_backward(d_hd, ctx["hier_tape"], ctx["y"], grads)
         elif self.medusa_num_layers > 0:
             dWc = torch.empty((Hx * D, D), dtype=torch.float32, device=dev)
@@ -1292,7 +1301,10 @@ class HSTU(nn.Module):
         y_last = torch.empty((B, D), dtype=torch.float32, device=dev)
         L.call("b200rec_gather_rows", y.data_ptr(), D, last.data_ptr(), B, y_last.data_ptr(), L.F32, st)
         self._last_user_y = y_last                 # body output of the last position (prior-switch heads read it)
-        hd, _, _ = self._heads_forward(y_last, w, B)
+        if self._readout is not None:
+            hd = self._readout.predict_heads(self, y, seq_off, B, T)       # [B, K interests, D] of the whole sequence
+        else:
+            hd, _, _ = self._heads_forward(y_last, w, B)
         H = self.medusa_num_heads
         if hd.shape[1] != H:                       # identity heads: every head is the body output
             hd = hd.expand(B, H, D).contiguous()

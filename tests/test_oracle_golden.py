@@ -79,3 +79,26 @@ def test_combine_equals_max_over_heads():
     v2, i2 = torch.topk(mx, 50, dim=-1)
     assert np.array_equal(idx, i2.numpy())
     assert np.array_equal(src, torch.gather(am, 1, i2).numpy())
+
+
+@pytest.mark.parametrize("name", ["comirec_p1", "comirec_p4"])
+def test_comirec_oracle_matches_live_reference_fixture(name):
+    """oracle/comirec_oracle.py against tests/golden/comirec_*.pt (live reference ComiRec, make_golden_comirec.py)."""
+    from oracle.comirec_oracle import OracleComiRec
+    fx = load_golden(name)
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in fx["state_dict"].items()}
+    model = OracleComiRec(fx["cfg"], sd)
+    out = model.forward(fx["train_batch"])
+    assert abs(float(out["loss"].detach()) - fx["loss"]) <= 2e-6 * max(1.0, abs(fx["loss"]))
+    out["loss"].backward()
+    for k, g in fx["grads"].items():
+        if g is None:
+            assert sd[k].grad is None, k
+            continue
+        err = (sd[k].grad - g).abs().max().item() / max(g.abs().max().item(), 1e-12)
+        assert err < 2e-3, (k, err)
+    for k, v in fx["logs"].items():
+        if k != "loss":
+            assert abs(float(out[k]) - v) <= 1e-5, k
+    scores = model.predict(fx["eval_batch"]["item_seq"], fx["item_feature"])
+    assert torch.allclose(scores, fx["scores"], rtol=1e-5, atol=1e-6)
