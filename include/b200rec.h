@@ -374,6 +374,34 @@ int b200rec_nce_combine(const float* stats, int n_parts, void* E, int64_t lde, i
                         const int32_t* tok_pos, int T, int LP, int P, const float* coef,
                         const float* logit_scale, float* loss, float* g0, float* dscale, int32_t* rank0,
                         int32_t* nvalid, float* row_scale, void* qs, int64_t ldqs, void* stream);
+/* Grouped forms: the loss of config B runs 12 (negative set, head) jobs over the same tokens; one launch per job left
+ * every one of these row kernels launch / tail bound.  grid.y = job, at most 16 jobs per launch (longer lists are cut into
+ * consecutive launches).  nce_combine_grouped: `ld_loss` is the row pitch of the loss outputs, so the jobs' [T, P] losses
+ * can be column blocks of ONE [T, n_jobs * P] tensor and a single b200rec_colsum reduces them all; g0 / dscale / rank0 /
+ * nvalid keep pitch P. */
+typedef struct {
+  const void* q_hat; uint32_t p_mask; int tok_ok_col; float* pos_cos; float* mref; float* thr;
+} b200rec_nce_pos_ref_job;
+int b200rec_nce_pos_ref_grouped(const b200rec_nce_pos_ref_job* jobs, int n_jobs, int64_t ldq, const void* t_hat, int D,
+                                const int32_t* tok_b, const int32_t* tok_pos, int T, int LP, int P,
+                                const uint8_t* tok_ok, int tok_ok_ld, const float* logit_scale, void* stream);
+typedef struct {
+  const float* stats; void* E; const uint32_t* same_bits; const uint8_t* row_any; const float* pos_cos;
+  const float* mref; const void* q_hat; const float* coef; float* loss; float* g0; float* dscale; int32_t* rank0;
+  int32_t* nvalid; float* row_scale; void* qs;
+} b200rec_nce_combine_job;
+int b200rec_nce_combine_grouped(const b200rec_nce_combine_job* jobs, int n_jobs, int n_parts, int64_t lde, int n_neg,
+                                int64_t ldq, int D, const int32_t* tok_b, const int32_t* tok_pos, int T, int LP, int P,
+                                int64_t ld_loss, const float* logit_scale, int64_t ldqs, void* stream);
+/* positive-logit backward over several jobs: bwd_q -- the jobs of ONE call must have distinct d_qhat slices (grid.y =
+ * job); bwd_t -- every job accumulates into the same d_that rows, in job order inside the kernel (deterministic). */
+typedef struct { const float* g0; const void* q_hat; float* d_qhat; } b200rec_nce_pos_bwd_job;
+int b200rec_nce_pos_bwd_q_grouped(const b200rec_nce_pos_bwd_job* jobs, int n_jobs, const void* t_hat, int act_dtype,
+                                  int D, const int32_t* tok_b, const int32_t* tok_pos, int T, int LP, int P,
+                                  const float* logit_scale, const float* gscale, int64_t ldd, void* stream);
+int b200rec_nce_pos_bwd_t_grouped(const b200rec_nce_pos_bwd_job* jobs, int n_jobs, int64_t ldq, int act_dtype, int D,
+                                  const int32_t* tok_index, int B, int LP, int P, const float* logit_scale,
+                                  const float* gscale, float* d_that, void* stream);
 /* cnt[p] = #valid tokens at offset p for this (head / category):  (hstu.py:705-707) */
 int b200rec_nce_count(const int32_t* tok_b, const int32_t* tok_pos, int T, int LP, int P,
                       const uint8_t* tok_ok, int tok_ok_ld, int tok_ok_col, int32_t* cnt,

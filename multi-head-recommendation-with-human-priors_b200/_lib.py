@@ -58,6 +58,20 @@ class GemmArgs(C.Structure):
     ]
 
 
+class NcePosRefJob(C.Structure):
+    _fields_ = [("q_hat", C.c_void_p), ("p_mask", C.c_uint32), ("tok_ok_col", C.c_int), ("pos_cos", C.c_void_p),
+                ("mref", C.c_void_p), ("thr", C.c_void_p)]
+
+
+class NceCombineJob(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("stats", "E", "same_bits", "row_any", "pos_cos", "mref", "q_hat", "coef", "loss",
+                                          "g0", "dscale", "rank0", "nvalid", "row_scale", "qs")]
+
+
+class NcePosBwdJob(C.Structure):
+    _fields_ = [("g0", C.c_void_p), ("q_hat", C.c_void_p), ("d_qhat", C.c_void_p)]
+
+
 _P, _I, _L, _F, _Z = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 _SIGS = {
     "b200rec_version": (C.c_int, []),
@@ -117,6 +131,10 @@ _SIGS = {
     "b200rec_nce_pos_ref": (C.c_int, [_P, _L, _P, _I, _P, _P, _I, _I, _I, C.c_uint32, _P, _I, _I, _P, _P, _P, _P, _P]),
     "b200rec_nce_combine": (C.c_int, [_P, _I, _P, _L, _I, _P, _P, _P, _P, _P, _L, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P,
                                       _P, _P, _P, _P, _P, _L, _P]),
+    "b200rec_nce_pos_ref_grouped": (C.c_int, [_P, _I, _L, _P, _I, _P, _P, _I, _I, _I, _P, _I, _P, _P]),
+    "b200rec_nce_combine_grouped": (C.c_int, [_P, _I, _I, _L, _I, _L, _I, _P, _P, _I, _I, _I, _L, _P, _L, _P]),
+    "b200rec_nce_pos_bwd_q_grouped": (C.c_int, [_P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _P, _P, _L, _P]),
+    "b200rec_nce_pos_bwd_t_grouped": (C.c_int, [_P, _I, _L, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P]),
     "b200rec_nce_count": (C.c_int, [_P, _P, _I, _I, _I, _P, _I, _I, _P, _P]),
     "b200rec_nce_coef": (C.c_int, [_P, _P, _F, _I, _P, _P]),
     "b200rec_nce_pos_bwd_q": (C.c_int, [_P, _P, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P, _L, _P]),
@@ -301,6 +319,22 @@ def gemm_grouped(problems, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epil
         gemm_timing.append((e0, e1, 2.0 * M * N * K * n, (M, N, K, n, epilogue, a_major, b_major)))
         return
     _check(lib().b200rec_gemm_grouped(arr, n, stream()), "b200rec_gemm_grouped")
+
+
+def job_array(cls, rows):
+    """ctypes array of job structs from dicts (tensors -> device pointers, None -> NULL)."""
+    arr = (cls * len(rows))()
+    for a, r in zip(arr, rows):
+        for k, v in r.items():
+            setattr(a, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
+    return arr
+
+
+def call_grouped(name, arr, *args):
+    """One C-ABI call over a job array; counts ceil(n / 16) launches (gpu_launches claim of bench.py)."""
+    global launches
+    launches += (len(arr) + 15) // 16
+    _check(getattr(lib(), name)(C.cast(arr, C.c_void_p), len(arr), *args), name)
 
 
 def colsum(x, rows, cols, ldx, out, accumulate=False):

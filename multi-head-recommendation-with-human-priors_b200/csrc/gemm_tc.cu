@@ -103,20 +103,38 @@ __device__ __forceinline__ void fold_items_warp(const EpiParams& ep, int cols, u
     for (int q = 0; q < NCH; ++q) tmem_ld_32x32_nowait(t_addr + (uint32_t)(b0 + q * 32), rr[q]);
     tmem_ld_wait();
     const int user0 = (nc0 + b0) / HP;
+    if (ep.fold_thr != nullptr) {
+      // streamed eval: only scores that can still enter the user's top-K leave the SM.  Two phases: (A) every user's
+      // masked max against its threshold with NO side effects, so the per-user threshold / head-mask loads of all UPB
+      // users are in flight together (one loop with the append inside serialised them behind its atomics: the H = 1
+      // sweep ran at 0.08 of the HBM rate); (B) the rare survivors append to the candidate lists.
+      unsigned long long pass = 0ull;
 #pragma unroll
-    for (int u = 0; u < UPB; ++u) {
-      const int user = user0 + u;
-      if (user >= n_users) break;                          // warp-uniform
-      const uint32_t bits = hmask & __ldg(ep.fold_on_bits + user);
-      float best = -INFINITY;
+      for (int u = 0; u < UPB; ++u) {
+        const int user = user0 + u;
+        const bool uok = user < n_users;
+        const uint32_t bits = uok ? (hmask & __ldg(ep.fold_on_bits + user)) : 0u;
+        const float thr = uok ? __ldg(ep.fold_thr + user) : INFINITY;
+        float best = -INFINITY;
 #pragma unroll
-      for (int h = 0; h < HP; ++h) {
-        const float x = __uint_as_float(rr[(u * HP + h) >> 5][(u * HP + h) & 31]);
-        best = fmaxf(best, ((bits >> h) & 1u) ? x : -INFINITY);
+        for (int h = 0; h < HP; ++h) {
+          const float x = __uint_as_float(rr[(u * HP + h) >> 5][(u * HP + h) & 31]);
+          best = fmaxf(best, ((bits >> h) & 1u) ? x : -INFINITY);
+        }
+        pass |= (unsigned long long)((best >= thr && best > -INFINITY) ? 1u : 0u) << u;
       }
-      if (ep.fold_thr != nullptr) {
-        // streamed eval: only scores that can still enter the user's top-K leave the SM
-        if (best >= __ldg(ep.fold_thr + user) && best > -INFINITY) {
+      if (pass != 0ull) {
+#pragma unroll
+        for (int u = 0; u < UPB; ++u) {
+          if (!((pass >> u) & 1ull)) continue;
+          const int user = user0 + u;
+          const uint32_t bits = hmask & __ldg(ep.fold_on_bits + user);
+          float best = -INFINITY;
+#pragma unroll
+          for (int h = 0; h < HP; ++h) {
+            const float x = __uint_as_float(rr[(u * HP + h) >> 5][(u * HP + h) & 31]);
+            best = fmaxf(best, ((bits >> h) & 1u) ? x : -INFINITY);
+          }
           int bh = 0;
 #pragma unroll
           for (int h = HP - 1; h >= 0; --h) {
@@ -131,7 +149,21 @@ __device__ __forceinline__ void fold_items_warp(const EpiParams& ep, int cols, u
                 ((unsigned long long)(~k) << 32) | (unsigned long long)(((uint32_t)m << 5) | (uint32_t)bh);
           }
         }
-      } else if (row_ok) {
+      }
+      continue;
+    }
+#pragma unroll
+    for (int u = 0; u < UPB; ++u) {
+      const int user = user0 + u;
+      if (user >= n_users) break;                          // warp-uniform
+      const uint32_t bits = hmask & __ldg(ep.fold_on_bits + user);
+      float best = -INFINITY;
+#pragma unroll
+      for (int h = 0; h < HP; ++h) {
+        const float x = __uint_as_float(rr[(u * HP + h) >> 5][(u * HP + h) & 31]);
+        best = fmaxf(best, ((bits >> h) & 1u) ? x : -INFINITY);
+      }
+      if (row_ok) {
         int bh = 0;
 #pragma unroll
         for (int h = HP - 1; h >= 0; --h) {

@@ -6,6 +6,7 @@
 
 #define NCE_THREADS 256
 #define NCE_MAXP 16
+#define NCE_MAX_JOBS 16   // jobs per grouped launch of the row kernels (job table by value in the kernel parameters)
 
 struct Stats {
   float m, s, w;  // max, sum exp(z-m), sum exp(z-m)*z
@@ -601,13 +602,19 @@ extern "C" int b200rec_nce_coef(const int32_t* cnt, const float* lam, float w, i
 }
 
 // ------------------------------------------------------------------------------ positive-logit backward
+struct NcePosBwdJob { const float* g0; const void* q_hat; float* d_qhat; };
+struct NcePosBwdJobs { NcePosBwdJob j[NCE_MAX_JOBS]; };
+
+// grid (T, jobs): the jobs of one launch write DISTINCT query-gradient slices (the caller groups them so)
 template <typename TA>
-__global__ void __launch_bounds__(256) nce_pos_bwd_q_kernel(const float* __restrict__ g0, const TA* __restrict__ t_hat,
-                                                            int D4, const int32_t* __restrict__ tok_b,
+__global__ void __launch_bounds__(256) nce_pos_bwd_q_kernel(const __grid_constant__ NcePosBwdJobs jobs,
+                                                            const TA* __restrict__ t_hat, int D4,
+                                                            const int32_t* __restrict__ tok_b,
                                                             const int32_t* __restrict__ tok_pos, int LP, int P,
                                                             const float* __restrict__ logit_scale,
-                                                            const float* __restrict__ gscale,
-                                                            float* __restrict__ d_qhat, int64_t ldd) {
+                                                            const float* __restrict__ gscale, int64_t ldd) {
+  const float* __restrict__ g0 = jobs.j[blockIdx.y].g0;
+  float* __restrict__ d_qhat = jobs.j[blockIdx.y].d_qhat;
   const int t = blockIdx.x;
   const float tau = __expf(fminf(fmaxf(*logit_scale, 0.f), 4.605170185988092f)) * (gscale ? *gscale : 1.f);
   const int64_t r0 = (int64_t)tok_b[t] * LP + tok_pos[t] + 1;
@@ -627,22 +634,46 @@ __global__ void __launch_bounds__(256) nce_pos_bwd_q_kernel(const float* __restr
   }
 }
 
-int b200rec_nce_pos_bwd_q(const float* g0, const void* t_hat, int act_dtype, int D, const int32_t* tok_b,
-                          const int32_t* tok_pos, int T, int LP, int P, const float* logit_scale,
-                          const float* gscale, float* d_qhat, int64_t ldd, void* stream) {
+static int nce_pos_bwd_q_launch(const NcePosBwdJobs& jobs, int n_jobs, const void* t_hat, int act_dtype, int D,
+                                const int32_t* tok_b, const int32_t* tok_pos, int T, int LP, int P,
+                                const float* logit_scale, const float* gscale, int64_t ldd, void* stream) {
   if (T == 0) return 0;
   B200_CHECK_ARG(D % 4 == 0 && ldd % 4 == 0, "nce_pos_bwd_q: bad D/ldd");
+  B200_CHECK_ARG(n_jobs >= 1 && n_jobs <= NCE_MAX_JOBS, "nce_pos_bwd_q: %d jobs (1..%d per launch)", n_jobs, NCE_MAX_JOBS);
   DISPATCH_ACT(act_dtype, TA, {
-    nce_pos_bwd_q_kernel<TA><<<T, 256, 0, (cudaStream_t)stream>>>(g0, (const TA*)t_hat, D / 4, tok_b, tok_pos, LP, P,
-                                                                  logit_scale, gscale, d_qhat, ldd);
+    nce_pos_bwd_q_kernel<TA><<<dim3(T, n_jobs), 256, 0, (cudaStream_t)stream>>>(jobs, (const TA*)t_hat, D / 4, tok_b,
+                                                                              tok_pos, LP, P, logit_scale, gscale, ldd);
   });
   B200_LAUNCH_OK();
   return 0;
 }
 
-// gather form: target row r = (b, pos_r) collects from queries at l = pos_r - 1 - p
+int b200rec_nce_pos_bwd_q(const float* g0, const void* t_hat, int act_dtype, int D, const int32_t* tok_b,
+                          const int32_t* tok_pos, int T, int LP, int P, const float* logit_scale,
+                          const float* gscale, float* d_qhat, int64_t ldd, void* stream) {
+  NcePosBwdJobs jobs;
+  jobs.j[0] = {g0, nullptr, d_qhat};
+  return nce_pos_bwd_q_launch(jobs, 1, t_hat, act_dtype, D, tok_b, tok_pos, T, LP, P, logit_scale, gscale, ldd, stream);
+}
+
+extern "C" int b200rec_nce_pos_bwd_q_grouped(const b200rec_nce_pos_bwd_job* jobs_in, int n_jobs, const void* t_hat,
+                                             int act_dtype, int D, const int32_t* tok_b, const int32_t* tok_pos, int T,
+                                             int LP, int P, const float* logit_scale, const float* gscale, int64_t ldd,
+                                             void* stream) {
+  for (int j0 = 0; j0 < n_jobs; j0 += NCE_MAX_JOBS) {
+    const int n = std::min(NCE_MAX_JOBS, n_jobs - j0);
+    NcePosBwdJobs jobs;
+    for (int j = 0; j < n; ++j) jobs.j[j] = {jobs_in[j0 + j].g0, jobs_in[j0 + j].q_hat, jobs_in[j0 + j].d_qhat};
+    if (nce_pos_bwd_q_launch(jobs, n, t_hat, act_dtype, D, tok_b, tok_pos, T, LP, P, logit_scale, gscale, ldd, stream))
+      return 1;
+  }
+  return 0;
+}
+
+// gather form: target row r = (b, pos_r) collects from queries at l = pos_r - 1 - p.  All jobs of the launch accumulate
+// into the SAME target-gradient row, one after the other in job order inside the thread: deterministic, one launch.
 template <typename TA>
-__global__ void __launch_bounds__(256) nce_pos_bwd_t_kernel(const float* __restrict__ g0, const TA* __restrict__ q_hat,
+__global__ void __launch_bounds__(256) nce_pos_bwd_t_kernel(const __grid_constant__ NcePosBwdJobs jobs, int n_jobs,
                                                             int64_t ldq, int D4, const int32_t* __restrict__ tok_index,
                                                             int LP, int P, const float* __restrict__ logit_scale,
                                                             const float* __restrict__ gscale,
@@ -650,46 +681,75 @@ __global__ void __launch_bounds__(256) nce_pos_bwd_t_kernel(const float* __restr
   const int64_t r = blockIdx.x;
   const int b = (int)(r / LP), pos_r = (int)(r - (int64_t)b * LP);
   const float tau = __expf(fminf(fmaxf(*logit_scale, 0.f), 4.605170185988092f)) * (gscale ? *gscale : 1.f);
-  __shared__ int s_t[NCE_MAXP];
-  __shared__ float s_g[NCE_MAXP];
-  if (threadIdx.x < P) {
-    int p = threadIdx.x;
-    int l = pos_r - 1 - p;
-    int t = l >= 0 ? tok_index[(int64_t)b * LP + l] : -1;
-    float g = t >= 0 ? g0[(int64_t)t * P + p] : 0.f;
-    s_t[p] = g != 0.f ? t : -1;
-    s_g[p] = g;
+  __shared__ int s_t[NCE_MAX_JOBS][NCE_MAXP];
+  __shared__ float s_g[NCE_MAX_JOBS][NCE_MAXP];
+  __shared__ int s_any;
+  if (threadIdx.x == 0) s_any = 0;
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < n_jobs * P; idx += blockDim.x) {
+    const int j = idx / P, p = idx - j * P;
+    const int l = pos_r - 1 - p;
+    const int t = l >= 0 ? tok_index[(int64_t)b * LP + l] : -1;
+    const float g = t >= 0 ? jobs.j[j].g0[(int64_t)t * P + p] : 0.f;
+    s_t[j][p] = g != 0.f ? t : -1;
+    s_g[j][p] = g;
+    if (g != 0.f) s_any = 1;
   }
   __syncthreads();
-  bool any = false;
-  for (int p = 0; p < P; ++p) any |= s_t[p] >= 0;
-  if (!any) return;
+  if (!s_any) return;
   for (int c = threadIdx.x; c < D4; c += blockDim.x) {
     float acc[4];
     load4<float>(d_that + (r * D4 + c) * 4, acc);
-    for (int p = 0; p < P; ++p) {
-      if (s_t[p] >= 0) {
-        float v[4];
-        load4<TA>(q_hat + (int64_t)s_t[p] * ldq + c * 4, v);
+    for (int j = 0; j < n_jobs; ++j) {
+      const TA* __restrict__ q_hat = (const TA*)jobs.j[j].q_hat;
+      for (int p = 0; p < P; ++p) {
+        if (s_t[j][p] >= 0) {
+          float v[4];
+          load4<TA>(q_hat + (int64_t)s_t[j][p] * ldq + c * 4, v);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) acc[k] += tau * s_g[p] * v[k];
+          for (int k = 0; k < 4; ++k) acc[k] += tau * s_g[j][p] * v[k];
+        }
       }
     }
     store4<float>(d_that + (r * D4 + c) * 4, acc);
   }
 }
 
-int b200rec_nce_pos_bwd_t(const float* g0, const void* q_hat, int64_t ldq, int act_dtype, int D,
-                          const int32_t* tok_index, int B, int LP, int P, const float* logit_scale,
-                          const float* gscale, float* d_that, void* stream) {
+static int nce_pos_bwd_t_launch(const NcePosBwdJobs& jobs, int n_jobs, int64_t ldq, int act_dtype, int D,
+                                const int32_t* tok_index, int B, int LP, int P, const float* logit_scale,
+                                const float* gscale, float* d_that, void* stream) {
   if (B == 0) return 0;
   B200_CHECK_ARG(D % 4 == 0 && ldq % 4 == 0, "nce_pos_bwd_t: bad D/ldq");
   B200_CHECK_ARG(P <= NCE_MAXP, "nce_pos_bwd_t: pred_len too large");
+  B200_CHECK_ARG(n_jobs >= 1 && n_jobs <= NCE_MAX_JOBS, "nce_pos_bwd_t: %d jobs (1..%d per launch)", n_jobs, NCE_MAX_JOBS);
   DISPATCH_ACT(act_dtype, TA, {
-    nce_pos_bwd_t_kernel<TA><<<B * LP, 256, 0, (cudaStream_t)stream>>>(g0, (const TA*)q_hat, ldq, D / 4, tok_index, LP,
-                                                                       P, logit_scale, gscale, d_that);
+    nce_pos_bwd_t_kernel<TA><<<B * LP, 256, 0, (cudaStream_t)stream>>>(jobs, n_jobs, ldq, D / 4, tok_index, LP, P,
+                                                                       logit_scale, gscale, d_that);
   });
   B200_LAUNCH_OK();
+  return 0;
+}
+
+int b200rec_nce_pos_bwd_t(const float* g0, const void* q_hat, int64_t ldq, int act_dtype, int D,
+                          const int32_t* tok_index, int B, int LP, int P, const float* logit_scale,
+                          const float* gscale, float* d_that, void* stream) {
+  NcePosBwdJobs jobs;
+  jobs.j[0] = {g0, q_hat, nullptr};
+  return nce_pos_bwd_t_launch(jobs, 1, ldq, act_dtype, D, tok_index, B, LP, P, logit_scale, gscale, d_that, stream);
+}
+
+extern "C" int b200rec_nce_pos_bwd_t_grouped(const b200rec_nce_pos_bwd_job* jobs_in, int n_jobs, int64_t ldq,
+                                             int act_dtype, int D, const int32_t* tok_index, int B, int LP, int P,
+                                             const float* logit_scale, const float* gscale, float* d_that,
+                                             void* stream) {
+  // chunks of NCE_MAX_JOBS run one after the other: the accumulation order stays the job order
+  for (int j0 = 0; j0 < n_jobs; j0 += NCE_MAX_JOBS) {
+    const int n = std::min(NCE_MAX_JOBS, n_jobs - j0);
+    NcePosBwdJobs jobs;
+    for (int j = 0; j < n; ++j) jobs.j[j] = {jobs_in[j0 + j].g0, jobs_in[j0 + j].q_hat, jobs_in[j0 + j].d_qhat};
+    if (nce_pos_bwd_t_launch(jobs, n, ldq, act_dtype, D, tok_index, B, LP, P, logit_scale, gscale, d_that, stream))
+      return 1;
+  }
   return 0;
 }
 
@@ -709,17 +769,28 @@ int b200rec_nce_pos_bwd_t(const float* g0, const void* q_hat, int64_t ldq, int a
 // E <= 2^100 (fp32 sums of 8192 terms cannot overflow) and the positive term never underflows against it; numerators
 // more than 2^-126 below the reference flush to zero, i.e. softmax weights below 1e-38 are dropped.
 // =============================================================================================================
+// Grouped launches of the per-job row kernels (one job = one (negative set, head) pair of the loss): the 12 jobs of config
+// B were 12 launches of ~5 us of work each, i.e. launch / tail bound; grid.y = job, the job table travels by value.
+struct NcePosRefJob {
+  const bf16* q_hat; uint32_t p_mask; int tok_ok_col; float* pos_cos; float* mref; float* thr;
+};
+struct NcePosRefJobs { NcePosRefJob j[NCE_MAX_JOBS]; };
+
 template <int MAXV>
-__global__ void __launch_bounds__(256) nce_pos_ref_kernel(const bf16* __restrict__ q_hat, int64_t ldq,
+__global__ void __launch_bounds__(256) nce_pos_ref_kernel(const __grid_constant__ NcePosRefJobs jobs, int64_t ldq,
                                                           const bf16* __restrict__ t_hat, int D4,
                                                           const int32_t* __restrict__ tok_b,
                                                           const int32_t* __restrict__ tok_pos, int T, int LP, int P,
-                                                          uint32_t p_mask, const uint8_t* __restrict__ tok_ok,
-                                                          int tok_ok_ld, int tok_ok_col,
-                                                          const float* __restrict__ logit_scale,
-                                                          float* __restrict__ pos_cos, float* __restrict__ mref,
-                                                          float* __restrict__ thr) {
+                                                          const uint8_t* __restrict__ tok_ok, int tok_ok_ld,
+                                                          const float* __restrict__ logit_scale) {
   pdl_trigger();
+  const NcePosRefJob& jb = jobs.j[blockIdx.y];
+  const bf16* __restrict__ q_hat = jb.q_hat;
+  const uint32_t p_mask = jb.p_mask;
+  const int tok_ok_col = jb.tok_ok_col;
+  float* __restrict__ pos_cos = jb.pos_cos;
+  float* __restrict__ mref = jb.mref;
+  float* __restrict__ thr = jb.thr;
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= T) return;
@@ -759,35 +830,80 @@ __global__ void __launch_bounds__(256) nce_pos_ref_kernel(const bf16* __restrict
   }
 }
 
-extern "C" int b200rec_nce_pos_ref(const void* q_hat, int64_t ldq, const void* t_hat, int D, const int32_t* tok_b,
-                                   const int32_t* tok_pos, int T, int LP, int P, uint32_t p_mask, const uint8_t* tok_ok,
-                                   int tok_ok_ld, int tok_ok_col, const float* logit_scale, float* pos_cos, float* mref,
-                                   float* thr, void* stream) {
+static int nce_pos_ref_launch(const NcePosRefJobs& jobs, int n_jobs, int64_t ldq, const void* t_hat, int D,
+                              const int32_t* tok_b, const int32_t* tok_pos, int T, int LP, int P, const uint8_t* tok_ok,
+                              int tok_ok_ld, const float* logit_scale, void* stream) {
   B200_CHECK_ARG(P >= 1 && P <= NCE_MAXP, "nce_pos_ref: pred_len %d not in [1,%d]", P, NCE_MAXP);
   B200_CHECK_ARG(D % 4 == 0 && ldq % 4 == 0 && D <= 2048, "nce_pos_ref: D=%d must be a multiple of 4, <= 2048", D);
+  B200_CHECK_ARG(n_jobs >= 1 && n_jobs <= NCE_MAX_JOBS, "nce_pos_ref: %d jobs (1..%d per launch)", n_jobs, NCE_MAX_JOBS);
   if (T == 0) return 0;
-  const int blocks = ceil_div_i(T, 8);
+  const dim3 grid(ceil_div_i(T, 8), n_jobs);
   if (D <= 512)
-    nce_pos_ref_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)q_hat, ldq, (const bf16*)t_hat, D / 4,
-                                                                    tok_b, tok_pos, T, LP, P, p_mask, tok_ok, tok_ok_ld,
-                                                                    tok_ok_col, logit_scale, pos_cos, mref, thr);
+    nce_pos_ref_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(jobs, ldq, (const bf16*)t_hat, D / 4, tok_b, tok_pos, T,
+                                                                  LP, P, tok_ok, tok_ok_ld, logit_scale);
   else
-    nce_pos_ref_kernel<16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)q_hat, ldq, (const bf16*)t_hat, D / 4,
-                                                                     tok_b, tok_pos, T, LP, P, p_mask, tok_ok, tok_ok_ld,
-                                                                     tok_ok_col, logit_scale, pos_cos, mref, thr);
+    nce_pos_ref_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(jobs, ldq, (const bf16*)t_hat, D / 4, tok_b, tok_pos, T,
+                                                                   LP, P, tok_ok, tok_ok_ld, logit_scale);
   B200_LAUNCH_OK();
   return 0;
 }
 
+extern "C" int b200rec_nce_pos_ref(const void* q_hat, int64_t ldq, const void* t_hat, int D, const int32_t* tok_b,
+                                   const int32_t* tok_pos, int T, int LP, int P, uint32_t p_mask, const uint8_t* tok_ok,
+                                   int tok_ok_ld, int tok_ok_col, const float* logit_scale, float* pos_cos, float* mref,
+                                   float* thr, void* stream) {
+  NcePosRefJobs jobs;
+  jobs.j[0] = {(const bf16*)q_hat, p_mask, tok_ok_col, pos_cos, mref, thr};
+  return nce_pos_ref_launch(jobs, 1, ldq, t_hat, D, tok_b, tok_pos, T, LP, P, tok_ok, tok_ok_ld, logit_scale, stream);
+}
+
+extern "C" int b200rec_nce_pos_ref_grouped(const b200rec_nce_pos_ref_job* jobs_in, int n_jobs, int64_t ldq,
+                                           const void* t_hat, int D, const int32_t* tok_b, const int32_t* tok_pos, int T,
+                                           int LP, int P, const uint8_t* tok_ok, int tok_ok_ld, const float* logit_scale,
+                                           void* stream) {
+  for (int j0 = 0; j0 < n_jobs; j0 += NCE_MAX_JOBS) {
+    const int n = std::min(NCE_MAX_JOBS, n_jobs - j0);
+    NcePosRefJobs jobs;
+    for (int j = 0; j < n; ++j) {
+      const b200rec_nce_pos_ref_job& x = jobs_in[j0 + j];
+      jobs.j[j] = {(const bf16*)x.q_hat, x.p_mask, x.tok_ok_col, x.pos_cos, x.mref, x.thr};
+    }
+    if (nce_pos_ref_launch(jobs, n, ldq, t_hat, D, tok_b, tok_pos, T, LP, P, tok_ok, tok_ok_ld, logit_scale, stream))
+      return 1;
+  }
+  return 0;
+}
+
+struct NceCombineJob {
+  const float* stats; bf16* E; const uint32_t* same_bits; const uint8_t* row_any; const float* pos_cos;
+  const float* mref; const bf16* q_hat; const float* coef; float* loss; float* g0; float* dscale; int32_t* rank0;
+  int32_t* nvalid; float* row_scale; bf16* qs;
+};
+struct NceCombineJobs { NceCombineJob j[NCE_MAX_JOBS]; };
+
+// ld_out: row pitch of the [T, P] loss output (P for a separate tensor; n_jobs * P when the jobs' losses are column blocks
+// of one [T, n_jobs * P] tensor, which lets ONE column-sum launch reduce every job's per-offset losses)
 __global__ void __launch_bounds__(256) nce_combine_kernel(
-    const float* __restrict__ stats, int n_parts, bf16* __restrict__ E, int64_t lde, int n_neg,
-    const uint32_t* __restrict__ same_bits, const uint8_t* __restrict__ row_any, const float* __restrict__ pos_cos,
-    const float* __restrict__ mref_a, const bf16* __restrict__ q_hat, int64_t ldq, int D4,
-    const int32_t* __restrict__ tok_b, const int32_t* __restrict__ tok_pos, int T, int LP, int P,
-    const float* __restrict__ coef, const float* __restrict__ logit_scale, float* __restrict__ loss,
-    float* __restrict__ g0, float* __restrict__ dscale, int32_t* __restrict__ rank0, int32_t* __restrict__ nvalid,
-    float* __restrict__ row_scale, bf16* __restrict__ qs, int64_t ldqs) {
+    const __grid_constant__ NceCombineJobs jobs, int n_parts, int64_t lde, int n_neg, int64_t ldq, int D4,
+    const int32_t* __restrict__ tok_b, const int32_t* __restrict__ tok_pos, int T, int LP, int P, int64_t ld_out,
+    const float* __restrict__ logit_scale, int64_t ldqs) {
   pdl_trigger();
+  const NceCombineJob& jb = jobs.j[blockIdx.y];
+  const float* __restrict__ stats = jb.stats;
+  bf16* __restrict__ E = jb.E;
+  const uint32_t* __restrict__ same_bits = jb.same_bits;
+  const uint8_t* __restrict__ row_any = jb.row_any;
+  const float* __restrict__ pos_cos = jb.pos_cos;
+  const float* __restrict__ mref_a = jb.mref;
+  const bf16* __restrict__ q_hat = jb.q_hat;
+  const float* __restrict__ coef = jb.coef;
+  float* __restrict__ loss = jb.loss;
+  float* __restrict__ g0 = jb.g0;
+  float* __restrict__ dscale = jb.dscale;
+  int32_t* __restrict__ rank0 = jb.rank0;
+  int32_t* __restrict__ nvalid = jb.nvalid;
+  float* __restrict__ row_scale = jb.row_scale;
+  bf16* __restrict__ qs = jb.qs;
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= T) return;
@@ -866,7 +982,7 @@ __global__ void __launch_bounds__(256) nce_combine_kernel(
       Csum += cp[p];
     }
     if (lane == 0) {
-      loss[(int64_t)t * P + p] = l_;
+      loss[(int64_t)t * ld_out + p] = l_;
       g0[(int64_t)t * P + p] = g_;
       dscale[(int64_t)t * P + p] = d_;
       rank0[(int64_t)t * P + p] = rk;
@@ -911,24 +1027,51 @@ __global__ void __launch_bounds__(256) nce_combine_kernel(
   }
 }
 
+static int nce_combine_launch(const NceCombineJobs& jobs, int n_jobs, int n_parts, int64_t lde, int n_neg, int64_t ldq,
+                              int D, const int32_t* tok_b, const int32_t* tok_pos, int T, int LP, int P, int64_t ld_out,
+                              const float* logit_scale, int64_t ldqs, void* stream) {
+  B200_CHECK_ARG(P >= 1 && P <= NCE_MAXP, "nce_combine: pred_len %d not in [1,%d]", P, NCE_MAXP);
+  B200_CHECK_ARG(D % 4 == 0 && ldq % 4 == 0 && ldqs % 4 == 0 && n_parts >= 1 && ld_out >= P,
+                 "nce_combine: bad D / ld / n_parts");
+  B200_CHECK_ARG(n_jobs >= 1 && n_jobs <= NCE_MAX_JOBS, "nce_combine: %d jobs (1..%d per launch)", n_jobs, NCE_MAX_JOBS);
+  if (T == 0) return 0;
+  nce_combine_kernel<<<dim3(ceil_div_i(T, 8), n_jobs), 256, 0, (cudaStream_t)stream>>>(
+      jobs, n_parts, lde, n_neg, ldq, D / 4, tok_b, tok_pos, T, LP, P, ld_out, logit_scale, ldqs);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
 extern "C" int b200rec_nce_combine(const float* stats, int n_parts, void* E, int64_t lde, int n_neg,
                                    const uint32_t* same_bits, const uint8_t* row_any, const float* pos_cos,
                                    const float* mref, const void* q_hat, int64_t ldq, int D, const int32_t* tok_b,
                                    const int32_t* tok_pos, int T, int LP, int P, const float* coef,
                                    const float* logit_scale, float* loss, float* g0, float* dscale, int32_t* rank0,
                                    int32_t* nvalid, float* row_scale, void* qs, int64_t ldqs, void* stream) {
-  B200_CHECK_ARG(P >= 1 && P <= NCE_MAXP, "nce_combine: pred_len %d not in [1,%d]", P, NCE_MAXP);
-  B200_CHECK_ARG(D % 4 == 0 && ldq % 4 == 0 && ldqs % 4 == 0 && n_parts >= 1, "nce_combine: bad D / ld / n_parts");
-  if (T == 0) return 0;
-  nce_combine_kernel<<<ceil_div_i(T, 8), 256, 0, (cudaStream_t)stream>>>(
-      stats, n_parts, (bf16*)E, lde, n_neg, same_bits, row_any, pos_cos, mref, (const bf16*)q_hat, ldq, D / 4, tok_b,
-      tok_pos, T, LP, P, coef, logit_scale, loss, g0, dscale, rank0, nvalid, row_scale, (bf16*)qs, ldqs);
-  B200_LAUNCH_OK();
+  NceCombineJobs jobs;
+  jobs.j[0] = {stats, (bf16*)E, same_bits, row_any, pos_cos, mref, (const bf16*)q_hat, coef, loss, g0, dscale, rank0,
+               nvalid, row_scale, (bf16*)qs};
+  return nce_combine_launch(jobs, 1, n_parts, lde, n_neg, ldq, D, tok_b, tok_pos, T, LP, P, P, logit_scale, ldqs, stream);
+}
+
+extern "C" int b200rec_nce_combine_grouped(const b200rec_nce_combine_job* jobs_in, int n_jobs, int n_parts, int64_t lde,
+                                           int n_neg, int64_t ldq, int D, const int32_t* tok_b, const int32_t* tok_pos,
+                                           int T, int LP, int P, int64_t ld_out, const float* logit_scale, int64_t ldqs,
+                                           void* stream) {
+  for (int j0 = 0; j0 < n_jobs; j0 += NCE_MAX_JOBS) {
+    const int n = std::min(NCE_MAX_JOBS, n_jobs - j0);
+    NceCombineJobs jobs;
+    for (int j = 0; j < n; ++j) {
+      const b200rec_nce_combine_job& x = jobs_in[j0 + j];
+      jobs.j[j] = {x.stats, (bf16*)x.E, x.same_bits, x.row_any, x.pos_cos, x.mref, (const bf16*)x.q_hat, x.coef, x.loss,
+                   x.g0, x.dscale, x.rank0, x.nvalid, x.row_scale, (bf16*)x.qs};
+    }
+    if (nce_combine_launch(jobs, n, n_parts, lde, n_neg, ldq, D, tok_b, tok_pos, T, LP, P, ld_out, logit_scale, ldqs,
+                           stream))
+      return 1;
+  }
   return 0;
 }
 
-
-// ---- pruned false-negative filter: tail norms + exact verification of the pairs the bound could not exclude ----
 __global__ void __launch_bounds__(256) tail_norm_kernel(const bf16* __restrict__ x, int64_t n, int D4, int k04,
                                                         float* __restrict__ out) {
   const int lane = threadIdx.x & 31;

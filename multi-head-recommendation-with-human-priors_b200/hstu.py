@@ -907,39 +907,44 @@ class HSTU(nn.Module):
             # GEMM whose epilogue writes bf16 softmax numerators E and per-row partial sums -> combine (loss, scalars,
             # row_scale with dL/dlogit = row_scale * E, scaled query copy for the dn GEMM)
             n_parts = L.lib().b200rec_gemm_nce_parts(n_neg)
-            pre = []
-            for j, hq in zip(self._jobs, hqs):
-                q_h = qv[:, hq * D:(hq + 1) * D]
-                pos_cos = torch.empty((T, P), dtype=torch.float32, device=dev)
-                mref = torch.empty(T, dtype=torch.float32, device=dev)
-                thr = torch.empty(T, dtype=torch.float32, device=dev)
-                L.call("b200rec_nce_pos_ref", q_h.data_ptr(), Hx * D, that.data_ptr(), D, tok_b.data_ptr(),
-                       tok_pos.data_ptr(), T, LP, P, j.p_mask, tok_ok.data_ptr(), n_col, j.col, scale.data_ptr(),
-                       pos_cos.data_ptr(), mref.data_ptr(), thr.data_ptr(), st)
-                E = torch.empty((T, ld_neg), dtype=act, device=dev)
-                stats = torch.empty((T, n_parts, 4), dtype=torch.float32, device=dev)
-                pre.append((q_h, pos_cos, mref, thr, E, stats))
-            L.gemm_grouped([(q_h, nhat[j.nset], E) for j, (q_h, _, _, _, E, _) in zip(self._jobs, pre)],
+            J = len(self._jobs)
+            # per-job row kernels run as ONE grouped launch each (grid.y = job): buffers are slices of job-major tensors
+            pos_cos_all = torch.empty((J, T, P), dtype=torch.float32, device=dev)
+            mref_all = torch.empty((J, T), dtype=torch.float32, device=dev)
+            thr_all = torch.empty((J, T), dtype=torch.float32, device=dev)
+            q_hs = [qv[:, hq * D:(hq + 1) * D] for hq in hqs]
+            L.call_grouped("b200rec_nce_pos_ref_grouped", L.job_array(L.NcePosRefJob, [
+                dict(q_hat=q_hs[i], p_mask=j.p_mask, tok_ok_col=j.col, pos_cos=pos_cos_all[i], mref=mref_all[i],
+                     thr=thr_all[i]) for i, j in enumerate(self._jobs)]),
+                Hx * D, that.data_ptr(), D, tok_b.data_ptr(), tok_pos.data_ptr(), T, LP, P, tok_ok.data_ptr(), n_col,
+                scale.data_ptr(), st)
+            Es = [torch.empty((T, ld_neg), dtype=act, device=dev) for _ in range(J)]
+            stats_all = torch.empty((J, T, n_parts, 4), dtype=torch.float32, device=dev)
+            L.gemm_grouped([(q_hs[i], nhat[j.nset], Es[i]) for i, j in enumerate(self._jobs)],
                            T, n_neg, D, lda=Hx * D, ldb=D, ldc=ld_neg, epilogue=L.EPI_NCE_EXP,
-                           nce=[(mref, thr, stats) for (_, _, mref, thr, _, stats) in pre], nce_logit_scale=scale)
-            for j, hq, (q_h, pos_cos, mref, thr, E, stats) in zip(self._jobs, hqs, pre):
-                lossv = torch.empty((T, P), dtype=torch.float32, device=dev)
-                g0 = torch.empty((T, P), dtype=torch.float32, device=dev)
-                dsc = torch.empty((T, P), dtype=torch.float32, device=dev)
-                rank0 = torch.empty((T, P), dtype=torch.int32, device=dev)
-                nval = torch.empty((T, P), dtype=torch.int32, device=dev)
-                rscale = torch.empty(T, dtype=torch.float32, device=dev)
-                qs = torch.empty((T, D), dtype=act, device=dev) if need_grad else None
-                L.call("b200rec_nce_combine", stats.data_ptr(), n_parts, E.data_ptr(), ld_neg, n_neg,
-                       bits[j.nset].data_ptr(), row_any[j.nset].data_ptr(), pos_cos.data_ptr(), mref.data_ptr(),
-                       q_h.data_ptr(), Hx * D, D, tok_b.data_ptr(), tok_pos.data_ptr(), T, LP, P,
-                       coefs[(j.col, j.w)].data_ptr(), scale.data_ptr(), lossv.data_ptr(), g0.data_ptr(), dsc.data_ptr(),
-                       rank0.data_ptr(), nval.data_ptr(), rscale.data_ptr(), L.ptr(qs), D, st)
-                per_p = torch.empty(P, dtype=torch.float32, device=dev)
-                L.colsum(lossv, T, P, P, per_p)
-                job_out.append(dict(job=j, per_p=per_p, g0=g0, dsc=dsc, rank0=rank0, nval=nval, hq=hq,
-                                    G=E if need_grad else None, rscale=rscale, qs=qs))
-            del pre
+                           nce=[(mref_all[i], thr_all[i], stats_all[i]) for i in range(J)], nce_logit_scale=scale)
+            lossv_all = torch.empty((T, J * P), dtype=torch.float32, device=dev)     # job i = columns [i*P, (i+1)*P)
+            g0_all = torch.empty((J, T, P), dtype=torch.float32, device=dev)
+            dsc_all = torch.empty((J, T, P), dtype=torch.float32, device=dev)
+            rank0_all = torch.empty((J, T, P), dtype=torch.int32, device=dev)
+            nval_all = torch.empty((J, T, P), dtype=torch.int32, device=dev)
+            rscale_all = torch.empty((J, T), dtype=torch.float32, device=dev)
+            qss = [torch.empty((T, D), dtype=act, device=dev) if need_grad else None for _ in range(J)]
+            L.call_grouped("b200rec_nce_combine_grouped", L.job_array(L.NceCombineJob, [
+                dict(stats=stats_all[i], E=Es[i], same_bits=bits[j.nset], row_any=row_any[j.nset], pos_cos=pos_cos_all[i],
+                     mref=mref_all[i], q_hat=q_hs[i], coef=coefs[(j.col, j.w)], loss=lossv_all[:, i * P:],
+                     g0=g0_all[i], dscale=dsc_all[i], rank0=rank0_all[i], nvalid=nval_all[i], row_scale=rscale_all[i],
+                     qs=qss[i]) for i, j in enumerate(self._jobs)]),
+                n_parts, ld_neg, n_neg, Hx * D, D, tok_b.data_ptr(), tok_pos.data_ptr(), T, LP, P, J * P,
+                scale.data_ptr(), D, st)
+            per_p_all = torch.empty(J * P, dtype=torch.float32, device=dev)
+            L.colsum(lossv_all, T, J * P, J * P, per_p_all)                       # every job's per-offset loss sums
+            for i, (j, hq) in enumerate(zip(self._jobs, hqs)):
+                job_out.append(dict(job=j, per_p=per_p_all[i * P:(i + 1) * P], g0=g0_all[i], dsc=dsc_all[i],
+                                    rank0=rank0_all[i], nval=nval_all[i], hq=hq, G=Es[i] if need_grad else None,
+                                    rscale=rscale_all[i], qs=qss[i]))
+            job_out[0]["dsc_all"] = dsc_all
+            job_sums = per_p_all.view(J, P).sum(dim=1)                             # one launch for all jobs
         else:
             pos_ws = torch.empty(T * P, dtype=torch.float32, device=dev)
             # all (head, negative set) logit GEMMs in one persistent launch (hstu.py:697: one matmul per head)
@@ -971,16 +976,19 @@ class HSTU(nn.Module):
         logs = {}
         S = self.num_segment_head
         seg_acc = {}
-        for o in job_out:
-            j, per_p = o["job"], o["per_p"]
-            total = total + per_p.sum()
+        if not fused:
+            job_sums = torch.stack([o["per_p"].sum() for o in job_out])
+        total = total + job_sums.sum()
+        job_sums = job_sums.detach()
+        for i, o in enumerate(job_out):
+            j = o["job"]
             if j.part == "nce":
-                logs[f"seg_{j.seg}_loss"] = per_p.sum().detach()
+                logs[f"seg_{j.seg}_loss"] = job_sums[i]
             else:
                 name = f"head_nce_{self.int_to_category[j.cat]}_loss"
-                logs[name] = logs.get(name, 0) + per_p.sum().detach()
+                logs[name] = logs.get(name, 0) + job_sums[i]
                 if self.head_interaction != "additive":
-                    seg_acc[j.seg] = seg_acc.get(j.seg, 0) + per_p.sum().detach()
+                    seg_acc[j.seg] = seg_acc.get(j.seg, 0) + job_sums[i]
         if self.loss == "prior" and self.head_interaction != "additive":
             for s in range(S):
                 logs[f"seg_{s}_loss"] = logs.get(f"seg_{s}_loss", 0) + seg_acc.get(s, 0)
@@ -1076,17 +1084,22 @@ class HSTU(nn.Module):
                 ldq_ = Hx * D
             L.gemm_grouped(probs, n_neg, D, T, lda=ld_neg, a_major=1, ldb=ldq_, b_major=1, ldc=D,
                            epilogue=L.EPI_STORE if r == 0 else L.EPI_ACCUM, alpha_dev=gscale)
+        # positive-logit backward: query side grouped over jobs with distinct head slices (rounds), target side in one launch
+        for idxs in rounds([o["hq"] for o in outs]):
+            L.call_grouped("b200rec_nce_pos_bwd_q_grouped", L.job_array(L.NcePosBwdJob, [
+                dict(g0=outs[i]["g0"], q_hat=None, d_qhat=dqhat[:, outs[i]["hq"] * D:]) for i in idxs]),
+                ctx["that"].data_ptr(), a_dt, D, ctx["tok_b"].data_ptr(), ctx["tok_pos"].data_ptr(), T, LP, P,
+                ctx["scale"].data_ptr(), gscale.data_ptr(), Hx * D, st)
+        L.call_grouped("b200rec_nce_pos_bwd_t_grouped", L.job_array(L.NcePosBwdJob, [
+            dict(g0=o["g0"], q_hat=qhat2[:, o["hq"] * D:], d_qhat=None) for o in outs]),
+            Hx * D, a_dt, D, ctx["tok_index"].data_ptr(), B, LP, P, ctx["scale"].data_ptr(), gscale.data_ptr(),
+            dthat.data_ptr(), st)
+        if outs[0].get("dsc_all") is not None:             # fused path: the jobs' [T, P] blocks are one contiguous tensor
+            dscale_sum = dscale_sum + outs[0]["dsc_all"].sum()                     # (torch's sum is a fixed-order tree)
+        else:
+            for o in outs:
+                L.call("b200rec_reduce_sum", o["dsc"].data_ptr(), T * P, 1.0, dscale_sum.data_ptr(), 1, st)
         for o in outs:
-            j, g0, hq = o["job"], o["g0"], o["hq"]
-            q_h = qhat2[:, hq * D:(hq + 1) * D]
-            dq_h = dqhat[:, hq * D:(hq + 1) * D]
-            L.call("b200rec_nce_pos_bwd_q", g0.data_ptr(), ctx["that"].data_ptr(), a_dt, D, ctx["tok_b"].data_ptr(),
-                   ctx["tok_pos"].data_ptr(), T, LP, P, ctx["scale"].data_ptr(), gscale.data_ptr(), dq_h.data_ptr(),
-                   Hx * D, st)
-            L.call("b200rec_nce_pos_bwd_t", g0.data_ptr(), q_h.data_ptr(), Hx * D, a_dt, D,
-                   ctx["tok_index"].data_ptr(), B, LP, P, ctx["scale"].data_ptr(), gscale.data_ptr(),
-                   dthat.data_ptr(), st)
-            L.call("b200rec_reduce_sum", o["dsc"].data_ptr(), T * P, 1.0, dscale_sum.data_ptr(), 1, st)
             o["G"] = o["qs"] = None
         if isinstance(self.logit_scale, nn.Parameter):
             grads[self.logit_scale] = (dscale_sum * gscale).reshape(self.logit_scale.shape)
