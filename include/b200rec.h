@@ -406,6 +406,16 @@ int b200rec_nce_pos_bwd_t_grouped(const b200rec_nce_pos_bwd_job* jobs, int n_job
 int b200rec_nce_count(const int32_t* tok_b, const int32_t* tok_pos, int T, int LP, int P,
                       const uint8_t* tok_ok, int tok_ok_ld, int tok_ok_col, int32_t* cnt,
                       void* stream);
+/* Every (validity column, loss weight) key of a step at once: cnt[c * P + p] (int32 workspace, n_col * P) = #valid tokens of
+ * tok_ok column c at offset p, coef[k * P + p] = lam[p] * key_w[k] / max(cnt[key_col[k], p], 1).  key_col / key_w are HOST
+ * arrays (n_keys <= 32); tok_ok is [rows, n_col] (n_col <= 32). */
+int b200rec_nce_coefs(const int32_t* tok_b, const int32_t* tok_pos, int T, int LP, int P, const uint8_t* tok_ok, int n_col,
+                      const int32_t* key_col, const float* key_w, int n_keys, const float* lam, int32_t* cnt,
+                      float* coef, void* stream);
+/* Top-k logging scalars of one job (hstu.py:621-629) from rank0 / nvalid [T, P]: over the rows whose offset 0 is served,
+ * out[0..6] = { #rows, mean #logits per row, acc@1, acc@5, acc@10, acc@50, acc@100 }; acc_ws: 64 bytes of workspace. */
+int b200rec_nce_topk_logs(const int32_t* rank0, const int32_t* nvalid, int T, int P, void* acc_ws, float* out,
+                          void* stream);
 /* positive-logit backward, deterministic:
  *   d_qhat[t,:]  += tau * sum_p g0[t,p] * t_hat[b, pos+1+p,:]            (query side)
  *   d_that[r,:]  += tau * sum_p g0[t(b, pos_r-1-p), p] * q_hat[t(...),:] (target side, gather form)

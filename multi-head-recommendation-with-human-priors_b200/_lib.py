@@ -135,6 +135,8 @@ _SIGS = {
     "b200rec_nce_combine_grouped": (C.c_int, [_P, _I, _I, _L, _I, _L, _I, _P, _P, _I, _I, _I, _L, _P, _L, _P]),
     "b200rec_nce_pos_bwd_q_grouped": (C.c_int, [_P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _P, _P, _L, _P]),
     "b200rec_nce_pos_bwd_t_grouped": (C.c_int, [_P, _I, _L, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "b200rec_nce_coefs": (C.c_int, [_P, _P, _I, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P]),
+    "b200rec_nce_topk_logs": (C.c_int, [_P, _P, _I, _I, _P, _P, _P]),
     "b200rec_nce_count": (C.c_int, [_P, _P, _I, _I, _I, _P, _I, _I, _P, _P]),
     "b200rec_nce_coef": (C.c_int, [_P, _P, _F, _I, _P, _P]),
     "b200rec_nce_pos_bwd_q": (C.c_int, [_P, _P, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P, _L, _P]),

@@ -601,6 +601,101 @@ extern "C" int b200rec_nce_coef(const int32_t* cnt, const float* lam, float w, i
   return 0;
 }
 
+// All (validity column, loss weight) keys of a step at once: cnt[c, p] = #valid tokens of column c at offset p (one
+// pass over the tokens for every column), coef[k, p] = lam[p] * w_k / max(cnt[col_k, p], 1).  3 launches instead of 3 per key.
+#define NCE_MAX_COLS 32
+struct NceCoefKeys { int col[NCE_MAX_JOBS * 2]; float w[NCE_MAX_JOBS * 2]; };
+
+__global__ void nce_count_all_kernel(const int32_t* __restrict__ tok_b, const int32_t* __restrict__ tok_pos, int T, int LP,
+                                     int P, const uint8_t* __restrict__ tok_ok, int n_col, int32_t* __restrict__ cnt) {
+  __shared__ int loc[NCE_MAX_COLS * NCE_MAXP];
+  for (int i = threadIdx.x; i < n_col * P; i += blockDim.x) loc[i] = 0;
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < T * P) {
+    int t = i / P, p = i - t * P;
+    int64_t r = (int64_t)tok_b[t] * LP + tok_pos[t] + 1 + p;
+    for (int c = 0; c < n_col; ++c)
+      if (tok_ok[r * n_col + c]) atomicAdd(&loc[c * P + p], 1);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < n_col * P; k += blockDim.x)
+    if (loc[k]) atomicAdd(&cnt[k], loc[k]);
+}
+
+__global__ void nce_coef_all_kernel(const int32_t* __restrict__ cnt, const float* __restrict__ lam,
+                                    const __grid_constant__ NceCoefKeys keys, int n_keys, int P, float* __restrict__ coef) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_keys * P) return;
+  const int k = i / P, p = i - k * P;
+  coef[i] = lam[p] * keys.w[k] / fmaxf((float)cnt[keys.col[k] * P + p], 1.f);
+}
+
+extern "C" int b200rec_nce_coefs(const int32_t* tok_b, const int32_t* tok_pos, int T, int LP, int P, const uint8_t* tok_ok,
+                                 int n_col, const int32_t* key_col, const float* key_w, int n_keys, const float* lam,
+                                 int32_t* cnt, float* coef, void* stream) {
+  B200_CHECK_ARG(P >= 1 && P <= NCE_MAXP && n_col >= 1 && n_col <= NCE_MAX_COLS, "nce_coefs: P=%d n_col=%d", P, n_col);
+  B200_CHECK_ARG(n_keys >= 1 && n_keys <= NCE_MAX_JOBS * 2, "nce_coefs: %d keys (1..%d)", n_keys, NCE_MAX_JOBS * 2);
+  NceCoefKeys keys;
+  for (int k = 0; k < n_keys; ++k) {
+    B200_CHECK_ARG(key_col[k] >= 0 && key_col[k] < n_col, "nce_coefs: key column %d out of range", key_col[k]);
+    keys.col[k] = key_col[k];
+    keys.w[k] = key_w[k];
+  }
+  B200_CUDA_OK(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * n_col * P, (cudaStream_t)stream));
+  if (T > 0)
+    nce_count_all_kernel<<<ceil_div_i((int64_t)T * P, 256), 256, 0, (cudaStream_t)stream>>>(tok_b, tok_pos, T, LP, P, tok_ok,
+                                                                                          n_col, cnt);
+  nce_coef_all_kernel<<<ceil_div_i(n_keys * P, 128), 128, 0, (cudaStream_t)stream>>>(cnt, lam, keys, n_keys, P, coef);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
+// Top-k logging scalars of one job from the rank of the positive (hstu.py:621-629): over the rows with a served offset 0
+// (nvalid[t, 0] > 0): out = { #rows, mean #logits, acc@1, @5, @10, @50, @100 }.  Integer sums -> exact in any order.
+__global__ void __launch_bounds__(256) nce_topk_logs_kernel(const int32_t* __restrict__ rank0,
+                                                            const int32_t* __restrict__ nvalid, int T, int P,
+                                                            unsigned long long* __restrict__ acc, float* __restrict__ out) {
+  __shared__ unsigned long long s[7];
+  if (threadIdx.x < 7) s[threadIdx.x] = 0ull;
+  __syncthreads();
+  unsigned long long loc[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+    const int nv = nvalid[(int64_t)t * P], r = rank0[(int64_t)t * P];
+    if (nv > 0) {
+      loc[0] += 1; loc[1] += (unsigned long long)nv;
+      loc[2] += r < 1; loc[3] += r < 5; loc[4] += r < 10; loc[5] += r < 50; loc[6] += r < 100;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 7; ++k)
+    if (loc[k]) atomicAdd(&s[k], loc[k]);
+  __syncthreads();
+  if (threadIdx.x < 7 && s[threadIdx.x]) atomicAdd(&acc[threadIdx.x], s[threadIdx.x]);
+  // the last block to finish turns the sums into the scalars
+  __shared__ unsigned int last;
+  __threadfence();
+  if (threadIdx.x == 0) last = (atomicAdd((unsigned int*)(acc + 7), 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (last && threadIdx.x < 7) {
+    __threadfence();
+    const volatile unsigned long long* a = acc;
+    const float den = fmaxf((float)a[0], 1.f);
+    out[threadIdx.x] = threadIdx.x == 0 ? (float)a[0] : (float)a[threadIdx.x] / den;
+  }
+}
+
+extern "C" int b200rec_nce_topk_logs(const int32_t* rank0, const int32_t* nvalid, int T, int P, void* acc_ws, float* out,
+                                     void* stream) {
+  B200_CUDA_OK(cudaMemsetAsync(acc_ws, 0, 8 * sizeof(unsigned long long), (cudaStream_t)stream));
+  B200_CUDA_OK(cudaMemsetAsync(out, 0, 7 * sizeof(float), (cudaStream_t)stream));
+  if (T == 0) return 0;
+  nce_topk_logs_kernel<<<std::min(ceil_div_i(T, 256), 64), 256, 0, (cudaStream_t)stream>>>(
+      rank0, nvalid, T, P, (unsigned long long*)acc_ws, out);
+  B200_LAUNCH_OK();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------ positive-logit backward
 struct NcePosBwdJob { const float* g0; const void* q_hat; float* d_qhat; };
 struct NcePosBwdJobs { NcePosBwdJob j[NCE_MAX_JOBS]; };

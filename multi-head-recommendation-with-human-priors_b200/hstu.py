@@ -19,6 +19,8 @@ from collections import defaultdict
 from logging import getLogger
 
 import numpy as np
+import ctypes
+
 import torch
 import torch.nn as nn
 
@@ -863,14 +865,15 @@ class HSTU(nn.Module):
         if prune_k0:
             t_aug = torch.empty((B * LP, prune_k0 + 16), dtype=act, device=dev)
             L.call("b200rec_prefix_aug", that.data_ptr(), B * LP, D, prune_k0, t_aug.data_ptr(), st)
-        for s in used_sets:
+        ra_all = torch.zeros((len(used_sets), B * LP + P + 1), dtype=torch.uint8, device=dev)   # one memset for all sets
+        for si, s in enumerate(used_sets):
             nh_ = torch.empty((n_neg, D), dtype=act, device=dev)
             ni_ = torch.empty(n_neg, dtype=torch.float32, device=dev)
             L.call("b200rec_gather_l2norm", W.data_ptr(), None, D, neg_ids[s].data_ptr(), n_neg, nh_.data_ptr(), a_dt,
                    ni_.data_ptr(), st)
             bt = torch.empty((B * LP, n_words), dtype=torch.int32, device=dev)
             # false-negative filter bits: that @ nhat^T > nce_thres   (hstu.py:613-614)
-            ra = torch.zeros(B * LP + P + 1, dtype=torch.uint8, device=dev)
+            ra = ra_all[si]
             if prune_k0:
                 # exact, ~16x fewer FLOPs: cos <= <prefix of k0 dims> + |tail_t| |tail_n| (Cauchy-Schwarz) marks the pairs
                 # that CAN pass; the full dot product is recomputed only for those (duplicates of a target)
@@ -886,16 +889,19 @@ class HSTU(nn.Module):
             nhat[s], ninv[s], bits[s], row_any[s] = nh_, ni_, bt, ra
         # ---- per-offset token counts -> loss coefficients (hstu.py:704-712, 846-852)
         lam = self.horizon_discount.to(torch.float32)
-        coefs, cnts = {}, {}
+        keys = []
         for j in self._jobs:
-            key = (j.col, j.w)
-            if key not in coefs:
-                cnt = torch.empty(P, dtype=torch.int32, device=dev)
-                L.call("b200rec_nce_count", tok_b.data_ptr(), tok_pos.data_ptr(), T, LP, P, tok_ok.data_ptr(), n_col,
-                       j.col, cnt.data_ptr(), st)
-                cf = torch.empty(P, dtype=torch.float32, device=dev)
-                L.call("b200rec_nce_coef", cnt.data_ptr(), lam.data_ptr(), float(j.w), P, cf.data_ptr(), st)
-                coefs[key], cnts[key] = cf, cnt
+            if (j.col, j.w) not in keys:
+                keys.append((j.col, j.w))
+        cnt_all = torch.empty(n_col * P, dtype=torch.int32, device=dev)
+        coef_all = torch.empty((len(keys), P), dtype=torch.float32, device=dev)
+        key_col = (ctypes.c_int32 * len(keys))(*[k[0] for k in keys])
+        key_w = (ctypes.c_float * len(keys))(*[float(k[1]) for k in keys])
+        L.call("b200rec_nce_coefs", tok_b.data_ptr(), tok_pos.data_ptr(), T, LP, P, tok_ok.data_ptr(), n_col,
+               ctypes.cast(key_col, ctypes.c_void_p), ctypes.cast(key_w, ctypes.c_void_p), len(keys), lam.data_ptr(),
+               cnt_all.data_ptr(),
+               coef_all.data_ptr(), st)
+        coefs = {k: coef_all[i] for i, k in enumerate(keys)}
         # ---- NCE jobs
         scale = self.logit_scale.data.to(torch.float32)
         job_out = []
@@ -999,19 +1005,13 @@ class HSTU(nn.Module):
             j = o["job"]
             if not (j.p_mask & 1) or (j.part == "prior" and j.cat != 0):
                 continue
-            r0, nv = o["rank0"][:, 0], o["nval"][:, 0]
-            sel = nv > 0
-            cntv = sel.sum()
-            den = cntv.clamp_min(1).float()
-            upd = {"nce_samples": (nv.float() * sel).sum() / den}
-            for k in (1, 5, 10, 50, 100):
-                if k > n_neg + 1:
-                    break
-                upd[f"nce_top{k}_acc"] = ((r0 < k) & sel).sum().float() / den
-            if cur is None:
-                cur = upd
-            else:
-                cur = {k: torch.where(cntv > 0, v, cur[k]) for k, v in upd.items()}
+            tk = torch.empty(7, dtype=torch.float32, device=dev)
+            L.call("b200rec_nce_topk_logs", o["rank0"].data_ptr(), o["nval"].data_ptr(), T, P,
+                   torch.empty(8, dtype=torch.int64, device=dev).data_ptr(), tk.data_ptr(), st)
+            names = ["nce_samples"] + [f"nce_top{k}_acc" for k in (1, 5, 10, 50, 100) if k <= n_neg + 1]
+            cur = tk if cur is None else torch.where(tk[0] > 0, tk, cur)
+        if cur is not None:
+            cur = {n: cur[1 + i] for i, n in enumerate(names)}
         if cur is not None:
             logs.update(cur)
         sw = None
