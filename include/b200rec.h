@@ -122,8 +122,10 @@ int b200rec_gate_ln_bwd(const void* d_oin, const void* u, const void* pre_u, int
                         const int64_t* rng_step_dev, void* stream);
 /* y = cast(x) elementwise, n elements (fp32 -> act dtype). */
 int b200rec_cast(const float* x, int64_t n, void* y, int y_dtype, void* stream);
-/* col_sum[j] = sum_i x[i, j]  (deterministic two-stage: 256-row slabs, then slabs in ascending
- * order), x act dtype or fp32, ld = ldx.  workspace: b200rec_colsum_workspace_bytes(rows, cols). */
+/* col_sum[j] = sum_i x[i, j]  (deterministic: 256-row slabs, then the slabs in ascending order by the block that finishes
+ * last for its 32-column tile; one launch), x act dtype or fp32, ld = ldx.  workspace: b200rec_colsum_workspace_bytes(rows,
+ * cols) bytes, 256-byte aligned; its first 4096 bytes (one uint32 counter per 32-column tile, cols <= 32768) must be ZERO on
+ * entry and are zero again when the kernel ends, so one zero-initialised buffer serves every call of a stream. */
 size_t b200rec_colsum_workspace_bytes(int rows, int cols);
 int b200rec_colsum(const void* x, int x_dtype, int ldx, int rows, int cols, float* out,
                    int accumulate, void* workspace, size_t workspace_bytes, void* stream);

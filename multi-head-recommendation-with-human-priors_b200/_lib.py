@@ -302,7 +302,7 @@ def gemm_grouped(problems, M, N, K, *, lda, ldb, ldc, a_major=0, b_major=0, epil
         a.in_dtype = dt(A)
         if dt(B) != a.in_dtype:
             raise B200RecError("gemm: A and B dtypes differ")
-        a.C, a.ldc, a.c_dtype = C_out.data_ptr(), ldc, dt(C_out)
+        a.C, a.ldc, a.c_dtype = C_out.data_ptr(), ldc, (F32 if epilogue == EPI_GT_BITS else dt(C_out))
         a.c2_dtype = F32
         a.epilogue, a.alpha, a.alpha_dev = epilogue, alpha, ptr(alpha_dev)
     if row_scales is not None:
@@ -339,9 +339,15 @@ def call_grouped(name, arr, *args):
     _check(getattr(lib(), name)(C.cast(arr, C.c_void_p), len(arr), *args), name)
 
 
+_COLSUM_WS = {}
+
+
 def colsum(x, rows, cols, ldx, out, accumulate=False):
-    """out[j] (+)= sum_i x[i, j]; deterministic."""
+    """out[j] (+)= sum_i x[i, j]; deterministic, one launch.  The workspace is persistent per device: its tile counters
+    start at zero and every call leaves them at zero (calls of one stream run in order)."""
     nbytes = lib().b200rec_colsum_workspace_bytes(rows, cols)
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    ws = _COLSUM_WS.get(x.device.index)
+    if ws is None or ws.numel() < nbytes:
+        ws = _COLSUM_WS[x.device.index] = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=x.device)
     call("b200rec_colsum", x.data_ptr(), dt(x), ldx, rows, cols, out.data_ptr(), 1 if accumulate else 0,
-         ws.data_ptr(), nbytes, stream())
+         ws.data_ptr(), ws.numel(), stream())

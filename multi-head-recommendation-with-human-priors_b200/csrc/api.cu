@@ -36,7 +36,10 @@ static bool nce_args_ok(const b200rec_gemm_args& x) {
 static bool gemm_groupable(const b200rec_gemm_args* a, int n) {
   const b200rec_gemm_args& f = a[0];
   if (f.in_dtype != B200REC_BF16 || (f.epilogue != B200REC_EPI_STORE && f.epilogue != B200REC_EPI_ACCUM &&
-                                      f.epilogue != B200REC_EPI_NCE_EXP)) return false;
+                                      f.epilogue != B200REC_EPI_NCE_EXP && f.epilogue != B200REC_EPI_GT_BITS)) return false;
+  if (f.epilogue == B200REC_EPI_GT_BITS)       // bit-pack groups: plain threshold only (no rank-1 addend, no row flag)
+    for (int g = 0; g < n; ++g)
+      if (a[g].gt_row != nullptr || a[g].gt_col != nullptr || a[g].row_scale != nullptr) return false;
   if (f.bias || f.resid || f.n_split != 0 || f.C2 != nullptr) return false;
   for (int g = 0; g < n; ++g) {
     const b200rec_gemm_args& x = a[g];

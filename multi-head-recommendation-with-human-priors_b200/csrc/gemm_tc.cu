@@ -922,6 +922,8 @@ int gemm_tc_launch_grouped(const b200rec_gemm_args* a, int n, const EpiParams& e
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_grouped_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_grouped_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_grouped_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_grouped_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_grouped_kernel<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_grouped_kernel<7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     B200_CUDA_OK(cudaFuncSetAttribute(gemm_tc_grouped_kernel<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     B200_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -988,11 +990,14 @@ int gemm_tc_launch_grouped(const b200rec_gemm_args* a, int n, const EpiParams& e
   } else if (ep.mode == B200REC_EPI_ACCUM) {
     if (ctas == 2) B200_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_grouped_kernel<1, 2>, ga, p, ep));
     else B200_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_grouped_kernel<1, 1>, ga, p, ep));
+  } else if (ep.mode == B200REC_EPI_GT_BITS) {
+    if (ctas == 2) B200_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_grouped_kernel<5, 2>, ga, p, ep));
+    else B200_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_grouped_kernel<5, 1>, ga, p, ep));
   } else if (ep.mode == B200REC_EPI_NCE_EXP) {
     if (ctas == 2) B200_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_grouped_kernel<7, 2>, ga, p, ep));
     else B200_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_grouped_kernel<7, 1>, ga, p, ep));
   } else {
-    b200rec_set_error("gemm_grouped: epilogue %d not supported (STORE / ACCUM / NCE_EXP)", ep.mode);
+    b200rec_set_error("gemm_grouped: epilogue %d not supported (STORE / ACCUM / GT_BITS / NCE_EXP)", ep.mode);
     return 1;
   }
   B200_LAUNCH_OK();

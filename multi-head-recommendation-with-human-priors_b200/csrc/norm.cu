@@ -318,13 +318,19 @@ int b200rec_cast(const float* x, int64_t n, void* y, int y_dtype, void* stream) 
   return 0;
 }
 
-// Column sums in two deterministic stages: (1) each block sums a 256-row slab of 32 columns into
-// ws[slab][col]; (2) one thread per column adds the slabs in ascending order.
+// Column sums, deterministic, ONE launch: (1) each block sums a 256-row slab of 32 columns into ws[slab][col]; (2) the
+// block that finishes LAST for its column tile (a counter per tile) adds the slabs in ascending order -- the order is fixed
+// whichever block that is.  Workspace = [counters: one uint32 per 32-column tile, zero on entry, restored to zero by the
+// kernel] ++ [partials].  (The separate final-stage kernel was 18 extra launches per training step.)
 #define CS_SLAB 256
+#define CS_MAX_COLS 32768
+#define CS_CNT_BYTES(cols) ((size_t)(CS_MAX_COLS / 32) * sizeof(uint32_t))   // FIXED size: calls with different widths share the buffer
 template <typename TX>
-__global__ void __launch_bounds__(256) colsum_partial_kernel(const TX* __restrict__ x, int64_t ldx, int rows, int cols,
-                                                             float* __restrict__ ws) {
+__global__ void __launch_bounds__(256) colsum_kernel(const TX* __restrict__ x, int64_t ldx, int rows, int cols,
+                                                     uint32_t* __restrict__ counters, float* __restrict__ ws,
+                                                     float* __restrict__ out, int accumulate) {
   __shared__ float part[8][33];
+  __shared__ uint32_t s_last;
   int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   int c = blockIdx.x * 32 + cx;
   int r0 = blockIdx.y * CS_SLAB, r1 = min(rows, r0 + CS_SLAB);
@@ -339,33 +345,39 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const TX* __restric
     for (int k = 0; k < 8; ++k) t += part[k][cx];
     ws[(int64_t)blockIdx.y * cols + c] = t;
   }
-}
-
-__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ ws, int slabs, int cols,
-                                                           float* __restrict__ out, int accumulate) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  float t = 0.f;
-  for (int s = 0; s < slabs; ++s) t += ws[(int64_t)s * cols + c];
-  out[c] = accumulate ? out[c] + t : t;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counters + blockIdx.x, 1u) == gridDim.y - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (ry == 0 && c < cols) {
+    const volatile float* w = ws;
+    float t = 0.f;
+    for (int sl = 0; sl < (int)gridDim.y; ++sl) t += w[(int64_t)sl * cols + c];
+    out[c] = accumulate ? out[c] + t : t;
+  }
+  if (threadIdx.x == 0) counters[blockIdx.x] = 0u;
 }
 
 size_t b200rec_colsum_workspace_bytes(int rows, int cols) {
-  return (size_t)std::max(1, ceil_div_i(rows, CS_SLAB)) * (size_t)std::max(cols, 1) * sizeof(float);
+  return CS_CNT_BYTES(std::max(cols, 1)) +
+         (size_t)std::max(1, ceil_div_i(rows, CS_SLAB)) * (size_t)std::max(cols, 1) * sizeof(float);
 }
 
 int b200rec_colsum(const void* x, int x_dtype, int ldx, int rows, int cols, float* out, int accumulate,
                    void* workspace, size_t workspace_bytes, void* stream) {
   if (cols == 0) return 0;
   B200_CHECK_ARG(workspace_bytes >= b200rec_colsum_workspace_bytes(rows, cols), "colsum: workspace too small");
+  B200_CHECK_ARG(cols <= CS_MAX_COLS, "colsum: at most %d columns per call (got %d)", CS_MAX_COLS, cols);
+  B200_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "colsum: workspace must be 256-byte aligned");
   int slabs = std::max(1, ceil_div_i(rows, CS_SLAB));
   dim3 grid(ceil_div_i(cols, 32), slabs);
+  uint32_t* counters = (uint32_t*)workspace;
+  float* ws = (float*)((char*)workspace + CS_CNT_BYTES(cols));
   DISPATCH_ACT(x_dtype, TX, {
-    colsum_partial_kernel<TX><<<grid, 256, 0, (cudaStream_t)stream>>>((const TX*)x, ldx, rows, cols,
-                                                                     (float*)workspace);
+    colsum_kernel<TX><<<grid, 256, 0, (cudaStream_t)stream>>>((const TX*)x, ldx, rows, cols, counters, ws, out, accumulate);
   });
-  colsum_final_kernel<<<ceil_div_i(cols, 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, slabs, cols,
-                                                                              out, accumulate);
   B200_LAUNCH_OK();
   return 0;
 }

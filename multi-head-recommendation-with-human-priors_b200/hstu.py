@@ -866,27 +866,45 @@ class HSTU(nn.Module):
             t_aug = torch.empty((B * LP, prune_k0 + 16), dtype=act, device=dev)
             L.call("b200rec_prefix_aug", that.data_ptr(), B * LP, D, prune_k0, t_aug.data_ptr(), st)
         ra_all = torch.zeros((len(used_sets), B * LP + P + 1), dtype=torch.uint8, device=dev)   # one memset for all sets
+        # every used negative set in ONE gather + normalise launch (and one prefix launch): the sets are row blocks
+        nU = len(used_sets)
+        if used_sets == list(range(n_sets)):
+            ids_used = neg_ids
+        else:
+            idx = getattr(self, "_used_sets_idx", None)      # device index, built once (never during a graph capture)
+            if idx is None or idx.device != dev or idx.numel() != nU:
+                idx = self._used_sets_idx = torch.tensor(used_sets, dtype=torch.int64, device=dev)
+            ids_used = neg_ids.index_select(0, idx)
+        nh_all = torch.empty((nU * n_neg, D), dtype=act, device=dev)
+        ni_all = torch.empty(nU * n_neg, dtype=torch.float32, device=dev)
+        L.call("b200rec_gather_l2norm", W.data_ptr(), None, D, ids_used.data_ptr(), nU * n_neg, nh_all.data_ptr(), a_dt,
+               ni_all.data_ptr(), st)
+        if prune_k0:
+            n_aug_all = torch.empty((nU * n_neg, prune_k0 + 16), dtype=act, device=dev)
+            L.call("b200rec_prefix_aug", nh_all.data_ptr(), nU * n_neg, D, prune_k0, n_aug_all.data_ptr(), st)
         for si, s in enumerate(used_sets):
-            nh_ = torch.empty((n_neg, D), dtype=act, device=dev)
-            ni_ = torch.empty(n_neg, dtype=torch.float32, device=dev)
-            L.call("b200rec_gather_l2norm", W.data_ptr(), None, D, neg_ids[s].data_ptr(), n_neg, nh_.data_ptr(), a_dt,
-                   ni_.data_ptr(), st)
+            nh_ = nh_all[si * n_neg:(si + 1) * n_neg]
+            ni_ = ni_all[si * n_neg:(si + 1) * n_neg]
             bt = torch.empty((B * LP, n_words), dtype=torch.int32, device=dev)
             # false-negative filter bits: that @ nhat^T > nce_thres   (hstu.py:613-614)
             ra = ra_all[si]
             if prune_k0:
                 # exact, ~16x fewer FLOPs: cos <= <prefix of k0 dims> + |tail_t| |tail_n| (Cauchy-Schwarz) marks the pairs
                 # that CAN pass; the full dot product is recomputed only for those (duplicates of a target)
-                n_aug = torch.empty((n_neg, prune_k0 + 16), dtype=act, device=dev)
-                L.call("b200rec_prefix_aug", nh_.data_ptr(), n_neg, D, prune_k0, n_aug.data_ptr(), st)
-                L.gemm(t_aug, n_aug, bt, B * LP, n_neg, prune_k0 + 16, lda=prune_k0 + 16, ldb=prune_k0 + 16, ldc=n_words,
-                       epilogue=L.EPI_GT_BITS, alpha=float(self.nce_thres) - 1e-5)
-                L.call("b200rec_gt_bits_verify", bt.data_ptr(), B * LP, n_words, n_neg, that.data_ptr(), nh_.data_ptr(), D,
-                       float(self.nce_thres), ra.data_ptr(), st)
+                pass                                   # candidate bits of every set: one grouped launch below
             else:
                 L.gemm(that, nh_, bt, B * LP, n_neg, D, lda=D, ldb=D, ldc=n_words, epilogue=L.EPI_GT_BITS,
                        alpha=float(self.nce_thres), C2=ra)
             nhat[s], ninv[s], bits[s], row_any[s] = nh_, ni_, bt, ra
+        ctx_neg_all = (nh_all, ni_all, ids_used)
+        if prune_k0:
+            ka = prune_k0 + 16
+            L.gemm_grouped([(t_aug, n_aug_all[si * n_neg:(si + 1) * n_neg], bits[s]) for si, s in enumerate(used_sets)],
+                           B * LP, n_neg, ka, lda=ka, ldb=ka, ldc=n_words, epilogue=L.EPI_GT_BITS,
+                           alpha=float(self.nce_thres) - 1e-5)
+            for s in used_sets:
+                L.call("b200rec_gt_bits_verify", bits[s].data_ptr(), B * LP, n_words, n_neg, that.data_ptr(),
+                       nhat[s].data_ptr(), D, float(self.nce_thres), row_any[s].data_ptr(), st)
         # ---- per-offset token counts -> loss coefficients (hstu.py:704-712, 846-852)
         lam = self.horizon_discount.to(torch.float32)
         keys = []
@@ -1031,7 +1049,7 @@ class HSTU(nn.Module):
                        items=items, mask=m, n_neg=n_neg, ld_neg=ld_neg, Hx=Hx, used_sets=used_sets,
                        gl_items=gl_items, gl_neg_ids=gl_neg_ids, uniq_rows_ids=uniq_rows_ids,
                        n_cache_rows=W.shape[0], push=prepared.get("push", True), cache_info=prepared.get("info"),
-                       grad_out=prepared.get("grad_out"), switch=sw, table=W, comi=comi)
+                       grad_out=prepared.get("grad_out"), switch=sw, table=W, comi=comi, neg_all=ctx_neg_all)
         return loss, logs, ctx
 
     def _train_backward(self, ctx, gscale):
@@ -1071,9 +1089,10 @@ class HSTU(nn.Module):
                            epilogue=L.EPI_STORE if r == 0 else L.EPI_ACCUM, alpha_dev=gscale,
                            row_scales=[outs[i]["rscale"] for i in idxs] if fused else None)
         # dn_hat += G^T @ q_hat   (both MN-major, K = T)
-        for o in outs:
-            if o["job"].nset not in dnhat:
-                dnhat[o["job"].nset] = torch.empty((n_neg, D), dtype=torch.float32, device=dev)
+        sets_used = ctx["used_sets"]
+        dnhat_all = torch.empty((len(sets_used) * n_neg, D), dtype=torch.float32, device=dev)
+        for si, s_ in enumerate(sets_used):
+            dnhat[s_] = dnhat_all[si * n_neg:(si + 1) * n_neg]
         for r, idxs in enumerate(rounds([o["job"].nset for o in outs])):
             if fused:
                 probs = [(outs[i]["G"], outs[i]["qs"], dnhat[outs[i]["job"].nset]) for i in idxs]
@@ -1190,11 +1209,11 @@ class HSTU(nn.Module):
         tgt_ids[:, 0] = 0                        # position 0 is never a target
         ids[T:T + B * LP] = tgt_ids.reshape(-1)
         off = T + B * LP
-        for s in sets:
-            L.call("b200rec_l2norm_bwd", ctx["nhat"][s].data_ptr(), a_dt, ctx["ninv"][s].data_ptr(),
-                   dnhat[s].data_ptr(), n_neg, D, rows[off:].data_ptr(), 0, st)
-            ids[off:off + n_neg] = ctx["neg_ids"][s] + shift
-            off += n_neg
+        nh_all, ni_all, ids_used = ctx["neg_all"]
+        L.call("b200rec_l2norm_bwd", nh_all.data_ptr(), a_dt, ni_all.data_ptr(), dnhat_all.data_ptr(), len(sets) * n_neg, D,
+               rows[off:].data_ptr(), 0, st)                       # every set in one launch (row blocks in set order)
+        ids[off:off + len(sets) * n_neg] = ids_used.reshape(-1) + shift
+        off += len(sets) * n_neg
         sw_gl = []
         if sw_pad is not None:
             # gradient rows of the aux loss at padded context positions -> the pad items' table rows (zero rows, and id 0

@@ -203,6 +203,26 @@ def test_cast_colsum_reduce():
     assert abs(float(s) - 0.5 * float(x.double().sum())) < 1e-2
 
 
+def test_colsum_shared_workspace_mixed_widths_is_deterministic():
+    """One persistent workspace serves calls of different widths (the tile counters live in a fixed-size region and are
+    left at zero); results are bit-reproducible and independent of the call order."""
+    outs = []
+    for order in ([3072, 40, 256, 3072, 1000], [40, 3072, 1000, 256, 3072]):
+        res = {}
+        for cols in order:
+            x = rnd(777, cols, seed=cols)
+            out = torch.full((cols,), float("nan"), device=dev())
+            L.colsum(x, 777, cols, cols, out)
+            assert torch.allclose(out, x.sum(0), rtol=1e-4, atol=1e-4), cols
+            acc = out.clone()
+            L.colsum(x, 777, cols, cols, acc, accumulate=True)
+            assert torch.allclose(acc, 2 * x.sum(0), rtol=1e-4, atol=1e-4), cols
+            res[cols] = out
+        outs.append(res)
+    for cols in outs[0]:
+        assert torch.equal(outs[0][cols], outs[1][cols])
+
+
 # ------------------------------------------------------------------------------------ GEMM
 def _gemm_ref(A, B, a_major, b_major):
     Am = A.float() if a_major == 0 else A.float().t()
