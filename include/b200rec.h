@@ -247,6 +247,11 @@ int b200rec_tail_norm(const void* x_hat, int64_t n, int D, int k0, float* out, v
 int b200rec_prefix_aug(const void* x_hat, int64_t n, int D, int k0, void* out, void* stream);
 int b200rec_gt_bits_verify(uint32_t* bits, int64_t M, int n_words, int N, const void* a_hat, const void* b_hat, int D,
                            float thres, uint8_t* row_any, void* stream);
+/* The same over n_sets negative sets in one launch (grid.y = set): the sets share a_hat; set s uses bits + s * bits_stride
+ * (uint32 elements), b_hat + s * b_stride (bf16 elements) and row_any + s * any_stride (bytes). */
+int b200rec_gt_bits_verify_sets(uint32_t* bits, int64_t M, int n_words, int N, const void* a_hat, const void* b_hat,
+                                int D, float thres, uint8_t* row_any, int n_sets, int64_t bits_stride,
+                                int64_t b_stride, int64_t any_stride, void* stream);
 /* n_groups independent problems args[0..n_groups).  Problems of identical shape / layout / dtypes with a
  * plain STORE or ACCUM epilogue (the per-head NCE GEMMs of hstu.py:697, the per-layer weight gradients)
  * run as ONE persistent tcgen05 launch (16 problems per launch), so that small problems share waves

@@ -128,6 +128,7 @@ _SIGS = {
     "b200rec_tail_norm": (C.c_int, [_P, _L, _I, _I, _P, _P]),
     "b200rec_prefix_aug": (C.c_int, [_P, _L, _I, _I, _P, _P]),
     "b200rec_gt_bits_verify": (C.c_int, [_P, _L, _I, _I, _P, _P, _I, _F, _P, _P]),
+    "b200rec_gt_bits_verify_sets": (C.c_int, [_P, _L, _I, _I, _P, _P, _I, _F, _P, _I, _L, _L, _L, _P]),
     "b200rec_nce_pos_ref": (C.c_int, [_P, _L, _P, _I, _P, _P, _I, _I, _I, C.c_uint32, _P, _I, _I, _P, _P, _P, _P, _P]),
     "b200rec_nce_combine": (C.c_int, [_P, _I, _P, _L, _I, _P, _P, _P, _P, _P, _L, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P,
                                       _P, _P, _P, _P, _P, _L, _P]),

@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(128) attn_seq_fwd_kernel(const bf16* __restric
                                                            const uint8_t* __restrict__ key_valid, int D, float inv_n,
                                                            float* __restrict__ out) {
   pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) Tile<DH> sq, sk, sv;
   __shared__ uint8_t kv[SEQ_MAX];
   const int h = blockIdx.x, b = blockIdx.y;
@@ -211,6 +212,7 @@ __global__ void __launch_bounds__(128) attn_seq_bwd_kernel(const bf16* __restric
                                                            const uint8_t* __restrict__ key_valid, int D, float inv_n,
                                                            const bf16* __restrict__ d_out, bf16* __restrict__ d_pre) {
   pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) Tile<DH> sq, sk, sv, sd;
   __shared__ uint8_t kv[SEQ_MAX];
   const int h = blockIdx.x, b = blockIdx.y;
@@ -293,11 +295,11 @@ extern "C" int b200rec_hstu_attn_seq_fwd(const void* act, int ld, const int32_t*
   B200_CHECK_ARG(((uintptr_t)act & 15) == 0 && ((uintptr_t)out & 7) == 0, "attn_seq: alignment");
   dim3 grid(n_heads, B);
   if (dh == 64)
-    attn_seq_fwd_kernel<64><<<grid, 128, 0, (cudaStream_t)stream>>>((const bf16*)act, ld, seq_off, key_valid,
-                                                                     n_heads * dh, inv_n, out);
+    B200_CUDA_OK(launch_pdl(attn_seq_fwd_kernel<64>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, (const bf16*)act, ld, seq_off, key_valid,
+                                                                     n_heads * dh, inv_n, out));
   else if (dh == 32)
-    attn_seq_fwd_kernel<32><<<grid, 128, 0, (cudaStream_t)stream>>>((const bf16*)act, ld, seq_off, key_valid,
-                                                                     n_heads * dh, inv_n, out);
+    B200_CUDA_OK(launch_pdl(attn_seq_fwd_kernel<32>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, (const bf16*)act, ld, seq_off, key_valid,
+                                                                     n_heads * dh, inv_n, out));
   else {
     b200rec_set_error("attn_seq: head dim %d not supported (32 or 64)", dh);
     return 1;
@@ -317,11 +319,11 @@ extern "C" int b200rec_hstu_attn_seq_bwd(const void* act, const void* pre, int l
                  "attn_seq: alignment");
   dim3 grid(n_heads, B);
   if (dh == 64)
-    attn_seq_bwd_kernel<64><<<grid, 128, 0, (cudaStream_t)stream>>>(
-        (const bf16*)act, (const bf16*)pre, ld, seq_off, key_valid, n_heads * dh, inv_n, (const bf16*)d_out, (bf16*)d_pre);
+    B200_CUDA_OK(launch_pdl(attn_seq_bwd_kernel<64>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, 
+        (const bf16*)act, (const bf16*)pre, ld, seq_off, key_valid, n_heads * dh, inv_n, (const bf16*)d_out, (bf16*)d_pre));
   else if (dh == 32)
-    attn_seq_bwd_kernel<32><<<grid, 128, 0, (cudaStream_t)stream>>>(
-        (const bf16*)act, (const bf16*)pre, ld, seq_off, key_valid, n_heads * dh, inv_n, (const bf16*)d_out, (bf16*)d_pre);
+    B200_CUDA_OK(launch_pdl(attn_seq_bwd_kernel<32>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, 
+        (const bf16*)act, (const bf16*)pre, ld, seq_off, key_valid, n_heads * dh, inv_n, (const bf16*)d_out, (bf16*)d_pre));
   else {
     b200rec_set_error("attn_seq: head dim %d not supported (32 or 64)", dh);
     return 1;

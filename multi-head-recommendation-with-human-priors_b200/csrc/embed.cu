@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(256) gather_l2norm_kernel(const float* __restr
                                                             const int64_t* __restrict__ ids, int64_t n,
                                                             TO* __restrict__ out, float* __restrict__ inv_norm) {
   pdl_trigger();
+  pdl_wait();
   int lane = threadIdx.x & 31;
   int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n) return;
@@ -122,14 +123,14 @@ int b200rec_gather_l2norm(const float* table, const float* rows_in, int D, const
   int blocks = ceil_div_i(n, 8);
   DISPATCH_ACT(out_dtype, TO, {
     if (D <= 512)
-      gather_l2norm_kernel<TO, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>(table, rows_in, D / 4, ids, n,
-                                                                            (TO*)out_hat, inv_norm);
+      B200_CUDA_OK(launch_pdl(gather_l2norm_kernel<TO, 4>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, table, rows_in, D / 4, ids, n,
+                                                                            (TO*)out_hat, inv_norm));
     else if (D <= 1024)
-      gather_l2norm_kernel<TO, 8><<<blocks, 256, 0, (cudaStream_t)stream>>>(table, rows_in, D / 4, ids, n,
-                                                                            (TO*)out_hat, inv_norm);
+      B200_CUDA_OK(launch_pdl(gather_l2norm_kernel<TO, 8>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, table, rows_in, D / 4, ids, n,
+                                                                            (TO*)out_hat, inv_norm));
     else
-      gather_l2norm_kernel<TO, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>(table, rows_in, D / 4, ids, n,
-                                                                            (TO*)out_hat, inv_norm);
+      B200_CUDA_OK(launch_pdl(gather_l2norm_kernel<TO, 16>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, table, rows_in, D / 4, ids, n,
+                                                                            (TO*)out_hat, inv_norm));
   });
   B200_LAUNCH_OK();
   return 0;
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const TA* __restrict__ 
                                                          const float* __restrict__ dxh, int64_t n, int D4,
                                                          float* __restrict__ dx, int accumulate) {
   pdl_trigger();
+  pdl_wait();
   int lane = threadIdx.x & 31;
   int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n) return;
@@ -180,14 +182,14 @@ int b200rec_l2norm_bwd(const void* x_hat, int act_dtype, const float* inv_norm, 
   int blocks = ceil_div_i(n, 8);
   DISPATCH_ACT(act_dtype, TA, {
     if (D <= 512)
-      l2norm_bwd_kernel<TA, 4><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TA*)x_hat, inv_norm, d_xhat, n,
-                                                                         D / 4, dx, accumulate);
+      B200_CUDA_OK(launch_pdl(l2norm_bwd_kernel<TA, 4>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const TA*)x_hat, inv_norm, d_xhat, n,
+                                                                         D / 4, dx, accumulate));
     else if (D <= 1024)
-      l2norm_bwd_kernel<TA, 8><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TA*)x_hat, inv_norm, d_xhat, n,
-                                                                         D / 4, dx, accumulate);
+      B200_CUDA_OK(launch_pdl(l2norm_bwd_kernel<TA, 8>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const TA*)x_hat, inv_norm, d_xhat, n,
+                                                                         D / 4, dx, accumulate));
     else
-      l2norm_bwd_kernel<TA, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TA*)x_hat, inv_norm, d_xhat, n,
-                                                                         D / 4, dx, accumulate);
+      B200_CUDA_OK(launch_pdl(l2norm_bwd_kernel<TA, 16>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const TA*)x_hat, inv_norm, d_xhat, n,
+                                                                         D / 4, dx, accumulate));
   });
   B200_LAUNCH_OK();
   return 0;

@@ -734,6 +734,14 @@ static int g_tail_split = 1;  // tail split of the last partial wave (B200REC_TA
 static int g_use_pdl = 1;     // programmatic dependent launch of the GEMM kernels (B200REC_PDL=0 / b200rec_gemm_use_pdl(0))
 
 extern "C" void b200rec_gemm_use_pdl(int on) { g_use_pdl = on ? 1 : 0; }
+int b200rec_pdl_enabled() {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("B200REC_PDL");
+    env = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return env && g_use_pdl;
+}
 
 extern "C" void b200rec_gemm_use_tail_split(int on) { g_tail_split = on ? 1 : 0; }
 extern "C" void b200rec_gemm_force_bn(int bn) { g_force_bn = bn; }

@@ -1235,8 +1235,13 @@ extern "C" int b200rec_tail_norm(const void* x_hat, int64_t n, int D, int k0, fl
 template <int MAXV>
 __global__ void __launch_bounds__(256) gt_bits_verify_kernel(uint32_t* __restrict__ bits, int64_t M, int n_words, int N,
                                                              const bf16* __restrict__ a, const bf16* __restrict__ b,
-                                                             int D4, float thres, uint8_t* __restrict__ row_any) {
+                                                             int D4, float thres, uint8_t* __restrict__ row_any,
+                                                             int64_t bits_stride, int64_t b_stride, int64_t any_stride) {
   pdl_trigger();
+  // grid.y = negative set: the sets share the row operand a, everything else is a strided block per set
+  bits += (int64_t)blockIdx.y * bits_stride;
+  b += (int64_t)blockIdx.y * b_stride;
+  row_any += (int64_t)blockIdx.y * any_stride;
   const int lane = threadIdx.x & 31;
   const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= M) return;
@@ -1288,17 +1293,32 @@ __global__ void __launch_bounds__(256) gt_bits_verify_kernel(uint32_t* __restric
   if (lane == 0 && keep_any) row_any[m] = 1;
 }
 
-extern "C" int b200rec_gt_bits_verify(uint32_t* bits, int64_t M, int n_words, int N, const void* a_hat,
-                                      const void* b_hat, int D, float thres, uint8_t* row_any, void* stream) {
+static int gt_bits_verify_launch(uint32_t* bits, int64_t M, int n_words, int N, const void* a_hat, const void* b_hat,
+                                 int D, float thres, uint8_t* row_any, int n_sets, int64_t bits_stride,
+                                 int64_t b_stride, int64_t any_stride, void* stream) {
   B200_CHECK_ARG(D % 4 == 0 && D <= 2048 && n_words * 32 >= N, "gt_bits_verify: bad D / n_words");
-  if (M == 0) return 0;
-  const int blocks = ceil_div_i(M, 8);
+  if (M == 0 || n_sets == 0) return 0;
+  const dim3 grid(ceil_div_i(M, 8), n_sets);
   if (D <= 512)
-    gt_bits_verify_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(bits, M, n_words, N, (const bf16*)a_hat,
-                                                                       (const bf16*)b_hat, D / 4, thres, row_any);
+    gt_bits_verify_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(bits, M, n_words, N, (const bf16*)a_hat,
+                                                                     (const bf16*)b_hat, D / 4, thres, row_any,
+                                                                     bits_stride, b_stride, any_stride);
   else
-    gt_bits_verify_kernel<16><<<blocks, 256, 0, (cudaStream_t)stream>>>(bits, M, n_words, N, (const bf16*)a_hat,
-                                                                        (const bf16*)b_hat, D / 4, thres, row_any);
+    gt_bits_verify_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(bits, M, n_words, N, (const bf16*)a_hat,
+                                                                      (const bf16*)b_hat, D / 4, thres, row_any,
+                                                                      bits_stride, b_stride, any_stride);
   B200_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int b200rec_gt_bits_verify(uint32_t* bits, int64_t M, int n_words, int N, const void* a_hat,
+                                      const void* b_hat, int D, float thres, uint8_t* row_any, void* stream) {
+  return gt_bits_verify_launch(bits, M, n_words, N, a_hat, b_hat, D, thres, row_any, 1, 0, 0, 0, stream);
+}
+
+extern "C" int b200rec_gt_bits_verify_sets(uint32_t* bits, int64_t M, int n_words, int N, const void* a_hat,
+                                           const void* b_hat, int D, float thres, uint8_t* row_any, int n_sets,
+                                           int64_t bits_stride, int64_t b_stride, int64_t any_stride, void* stream) {
+  return gt_bits_verify_launch(bits, M, n_words, N, a_hat, b_hat, D, thres, row_any, n_sets, bits_stride, b_stride,
+                               any_stride, stream);
 }

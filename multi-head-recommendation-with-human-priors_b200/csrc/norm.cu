@@ -11,6 +11,7 @@ __global__ void __launch_bounds__(ROW_THREADS) layernorm_fwd_kernel(const float*
                                                             TY* __restrict__ y, float* __restrict__ mean,
                                                             float* __restrict__ rstd) {
   pdl_trigger();
+  pdl_wait();
   int lane = threadIdx.x & 31;
   int r = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= T) return;
@@ -62,11 +63,11 @@ int b200rec_layernorm_fwd(const float* x, int T, int D, float eps, void* y, int 
   int blocks = ceil_div_i(T, ROWS_PER_BLOCK);
   DISPATCH_ACT(y_dtype, TY, {
     if (D <= 512)
-      layernorm_fwd_kernel<TY, 4><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>(x, T, D / 4, eps, (TY*)y, mean, rstd);
+      B200_CUDA_OK(launch_pdl(layernorm_fwd_kernel<TY, 4>, dim3(blocks), dim3(ROW_THREADS), 0, (cudaStream_t)stream, x, T, D / 4, eps, (TY*)y, mean, rstd));
     else if (D <= 1024)
-      layernorm_fwd_kernel<TY, 8><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>(x, T, D / 4, eps, (TY*)y, mean, rstd);
+      B200_CUDA_OK(launch_pdl(layernorm_fwd_kernel<TY, 8>, dim3(blocks), dim3(ROW_THREADS), 0, (cudaStream_t)stream, x, T, D / 4, eps, (TY*)y, mean, rstd));
     else
-      layernorm_fwd_kernel<TY, 16><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>(x, T, D / 4, eps, (TY*)y, mean, rstd);
+      B200_CUDA_OK(launch_pdl(layernorm_fwd_kernel<TY, 16>, dim3(blocks), dim3(ROW_THREADS), 0, (cudaStream_t)stream, x, T, D / 4, eps, (TY*)y, mean, rstd));
   });
   B200_LAUNCH_OK();
   return 0;
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(ROW_THREADS) layernorm_bwd_kernel(const TG* __
                                                             const float* __restrict__ resid, float* __restrict__ dx,
                                                             TG* __restrict__ dx_act) {
   pdl_trigger();
+  pdl_wait();
   int lane = threadIdx.x & 31;
   int r = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= T) return;
@@ -127,14 +129,14 @@ int b200rec_layernorm_bwd(const void* dy, int dy_dtype, int ldy, const float* x,
   int blocks = ceil_div_i(T, ROWS_PER_BLOCK);
   DISPATCH_ACT(dy_dtype, TG, {
     if (D <= 512)
-      layernorm_bwd_kernel<TG, 4><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>((const TG*)dy, ldy, x, mean, rstd, T,
-                                                                            D / 4, residual_grad, dx, (TG*)dx_act);
+      B200_CUDA_OK(launch_pdl(layernorm_bwd_kernel<TG, 4>, dim3(blocks), dim3(ROW_THREADS), 0, (cudaStream_t)stream, (const TG*)dy, ldy, x, mean, rstd, T,
+                                                                            D / 4, residual_grad, dx, (TG*)dx_act));
     else if (D <= 1024)
-      layernorm_bwd_kernel<TG, 8><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>((const TG*)dy, ldy, x, mean, rstd, T,
-                                                                            D / 4, residual_grad, dx, (TG*)dx_act);
+      B200_CUDA_OK(launch_pdl(layernorm_bwd_kernel<TG, 8>, dim3(blocks), dim3(ROW_THREADS), 0, (cudaStream_t)stream, (const TG*)dy, ldy, x, mean, rstd, T,
+                                                                            D / 4, residual_grad, dx, (TG*)dx_act));
     else
-      layernorm_bwd_kernel<TG, 16><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>((const TG*)dy, ldy, x, mean, rstd, T,
-                                                                            D / 4, residual_grad, dx, (TG*)dx_act);
+      B200_CUDA_OK(launch_pdl(layernorm_bwd_kernel<TG, 16>, dim3(blocks), dim3(ROW_THREADS), 0, (cudaStream_t)stream, (const TG*)dy, ldy, x, mean, rstd, T,
+                                                                            D / 4, residual_grad, dx, (TG*)dx_act));
   });
   B200_LAUNCH_OK();
   return 0;
@@ -147,6 +149,7 @@ __global__ void __launch_bounds__(ROW_THREADS) gate_ln_fwd_kernel(const TA* __re
                                                           TA* __restrict__ oin, float* __restrict__ mean,
                                                           float* __restrict__ rstd, DropCfg drop) {
   pdl_trigger();
+  pdl_wait();
   int lane = threadIdx.x & 31;
   int r = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= T) return;
@@ -203,14 +206,14 @@ int b200rec_gate_ln_fwd(const void* u, int ldu, const float* a, int T, int D, fl
   int blocks = ceil_div_i(T, ROWS_PER_BLOCK);
   DISPATCH_ACT(act_dtype, TA, {
     if (D <= 512)
-      gate_ln_fwd_kernel<TA, 4><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>((const TA*)u, ldu, a, T, D / 4, eps,
-                                                                          (TA*)oin, mean, rstd, drop);
+      B200_CUDA_OK(launch_pdl(gate_ln_fwd_kernel<TA, 4>, dim3(blocks), dim3(ROW_THREADS), 0, (cudaStream_t)stream, (const TA*)u, ldu, a, T, D / 4, eps,
+                                                                          (TA*)oin, mean, rstd, drop));
     else if (D <= 1024)
-      gate_ln_fwd_kernel<TA, 8><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>((const TA*)u, ldu, a, T, D / 4, eps,
-                                                                          (TA*)oin, mean, rstd, drop);
+      B200_CUDA_OK(launch_pdl(gate_ln_fwd_kernel<TA, 8>, dim3(blocks), dim3(ROW_THREADS), 0, (cudaStream_t)stream, (const TA*)u, ldu, a, T, D / 4, eps,
+                                                                          (TA*)oin, mean, rstd, drop));
     else
-      gate_ln_fwd_kernel<TA, 16><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>((const TA*)u, ldu, a, T, D / 4, eps,
-                                                                          (TA*)oin, mean, rstd, drop);
+      B200_CUDA_OK(launch_pdl(gate_ln_fwd_kernel<TA, 16>, dim3(blocks), dim3(ROW_THREADS), 0, (cudaStream_t)stream, (const TA*)u, ldu, a, T, D / 4, eps,
+                                                                          (TA*)oin, mean, rstd, drop));
   });
   B200_LAUNCH_OK();
   return 0;
@@ -224,6 +227,7 @@ __global__ void __launch_bounds__(ROW_THREADS) gate_ln_bwd_kernel(const TA* __re
                                                           TA* __restrict__ d_pre_u, TA* __restrict__ da,
                                                           DropCfg drop) {
   pdl_trigger();
+  pdl_wait();
   int lane = threadIdx.x & 31;
   int r = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (r >= T) return;
@@ -275,14 +279,14 @@ int b200rec_gate_ln_bwd(const void* d_oin, const void* u, const void* pre_u, int
   int blocks = ceil_div_i(T, ROWS_PER_BLOCK);
   DISPATCH_ACT(act_dtype, TA, {
     if (D <= 512)
-      gate_ln_bwd_kernel<TA, 4><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>(
-          (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, (TA*)da, drop);
+      B200_CUDA_OK(launch_pdl(gate_ln_bwd_kernel<TA, 4>, dim3(blocks), dim3(ROW_THREADS), 0, (cudaStream_t)stream, 
+          (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, (TA*)da, drop));
     else if (D <= 1024)
-      gate_ln_bwd_kernel<TA, 8><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>(
-          (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, (TA*)da, drop);
+      B200_CUDA_OK(launch_pdl(gate_ln_bwd_kernel<TA, 8>, dim3(blocks), dim3(ROW_THREADS), 0, (cudaStream_t)stream, 
+          (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, (TA*)da, drop));
     else
-      gate_ln_bwd_kernel<TA, 16><<<blocks, ROW_THREADS, 0, (cudaStream_t)stream>>>(
-          (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, (TA*)da, drop);
+      B200_CUDA_OK(launch_pdl(gate_ln_bwd_kernel<TA, 16>, dim3(blocks), dim3(ROW_THREADS), 0, (cudaStream_t)stream, 
+          (const TA*)d_oin, (const TA*)u, (const TA*)pre_u, ldu, a, mean, rstd, T, D / 4, (TA*)d_pre_u, (TA*)da, drop));
   });
   B200_LAUNCH_OK();
   return 0;
@@ -329,6 +333,8 @@ template <typename TX>
 __global__ void __launch_bounds__(256) colsum_kernel(const TX* __restrict__ x, int64_t ldx, int rows, int cols,
                                                      uint32_t* __restrict__ counters, float* __restrict__ ws,
                                                      float* __restrict__ out, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float part[8][33];
   __shared__ uint32_t s_last;
   int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
@@ -376,7 +382,7 @@ int b200rec_colsum(const void* x, int x_dtype, int ldx, int rows, int cols, floa
   uint32_t* counters = (uint32_t*)workspace;
   float* ws = (float*)((char*)workspace + CS_CNT_BYTES(cols));
   DISPATCH_ACT(x_dtype, TX, {
-    colsum_kernel<TX><<<grid, 256, 0, (cudaStream_t)stream>>>((const TX*)x, ldx, rows, cols, counters, ws, out, accumulate);
+    B200_CUDA_OK(launch_pdl(colsum_kernel<TX>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const TX*)x, ldx, rows, cols, counters, ws, out, accumulate));
   });
   B200_LAUNCH_OK();
   return 0;

@@ -882,10 +882,11 @@ class HSTU(nn.Module):
         if prune_k0:
             n_aug_all = torch.empty((nU * n_neg, prune_k0 + 16), dtype=act, device=dev)
             L.call("b200rec_prefix_aug", nh_all.data_ptr(), nU * n_neg, D, prune_k0, n_aug_all.data_ptr(), st)
+        bits_all = torch.empty((nU, B * LP, n_words), dtype=torch.int32, device=dev)
         for si, s in enumerate(used_sets):
             nh_ = nh_all[si * n_neg:(si + 1) * n_neg]
             ni_ = ni_all[si * n_neg:(si + 1) * n_neg]
-            bt = torch.empty((B * LP, n_words), dtype=torch.int32, device=dev)
+            bt = bits_all[si]
             # false-negative filter bits: that @ nhat^T > nce_thres   (hstu.py:613-614)
             ra = ra_all[si]
             if prune_k0:
@@ -902,9 +903,9 @@ class HSTU(nn.Module):
             L.gemm_grouped([(t_aug, n_aug_all[si * n_neg:(si + 1) * n_neg], bits[s]) for si, s in enumerate(used_sets)],
                            B * LP, n_neg, ka, lda=ka, ldb=ka, ldc=n_words, epilogue=L.EPI_GT_BITS,
                            alpha=float(self.nce_thres) - 1e-5)
-            for s in used_sets:
-                L.call("b200rec_gt_bits_verify", bits[s].data_ptr(), B * LP, n_words, n_neg, that.data_ptr(),
-                       nhat[s].data_ptr(), D, float(self.nce_thres), row_any[s].data_ptr(), st)
+            L.call("b200rec_gt_bits_verify_sets", bits_all.data_ptr(), B * LP, n_words, n_neg, that.data_ptr(),
+                   nh_all.data_ptr(), D, float(self.nce_thres), ra_all.data_ptr(), nU, B * LP * n_words, n_neg * D,
+                   ra_all.shape[1], st)
         # ---- per-offset token counts -> loss coefficients (hstu.py:704-712, 846-852)
         lam = self.horizon_discount.to(torch.float32)
         keys = []
