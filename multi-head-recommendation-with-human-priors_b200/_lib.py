@@ -341,14 +341,21 @@ def call_grouped(name, arr, *args):
 
 
 _COLSUM_WS = {}
+_COLSUM_WS_RETIRED = []          # outgrown workspaces: a captured graph may still hold their address, so never freed
+COLSUM_WS_BYTES = 32 << 20
 
 
 def colsum(x, rows, cols, ldx, out, accumulate=False):
     """out[j] (+)= sum_i x[i, j]; deterministic, one launch.  The workspace is persistent per device: its tile counters
-    start at zero and every call leaves them at zero (calls of one stream run in order)."""
+    start at zero and every call leaves them at zero (calls of one stream run in order).  Its address must stay valid for
+    every CUDA graph that captured a call, so it is allocated once at a size no training shape of this repo outgrows
+    (32 MiB = 256-row slabs x columns x 4 B); if a call still needs more, the old buffer is retired, not freed: a graph
+    captured earlier keeps replaying into it (it is self-contained: counters zero on entry and on exit)."""
     nbytes = lib().b200rec_colsum_workspace_bytes(rows, cols)
     ws = _COLSUM_WS.get(x.device.index)
     if ws is None or ws.numel() < nbytes:
-        ws = _COLSUM_WS[x.device.index] = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=x.device)
+        if ws is not None:
+            _COLSUM_WS_RETIRED.append(ws)
+        ws = _COLSUM_WS[x.device.index] = torch.zeros(max(2 * nbytes, COLSUM_WS_BYTES), dtype=torch.uint8, device=x.device)
     call("b200rec_colsum", x.data_ptr(), dt(x), ldx, rows, cols, out.data_ptr(), 1 if accumulate else 0,
          ws.data_ptr(), ws.numel(), stream())

@@ -223,6 +223,34 @@ def test_colsum_shared_workspace_mixed_widths_is_deterministic():
         assert torch.equal(outs[0][cols], outs[1][cols])
 
 
+def test_colsum_workspace_outlives_a_captured_graph():
+    """A CUDA graph that captured a colsum keeps the workspace address.  A later, larger call must not free that buffer
+    (the 2-GPU bench crashed on exactly this: a bigger token bucket on rank 1 re-allocated the workspace and the graphs
+    captured earlier then replayed into freed memory)."""
+    x = rnd(1000, 64, seed=5)
+    out = torch.zeros(64, device=dev())
+    L.colsum(x, 1000, 64, 64, out)                       # allocates the persistent workspace outside the capture
+    ws0 = L._COLSUM_WS[dev().index]
+    ptr0 = ws0.data_ptr()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        L.colsum(x, 1000, 64, 64, out)
+    # force the growth path without a multi-GiB operand: pretend the workspace is only 1 MiB
+    L._COLSUM_WS[dev().index] = ws0[:1 << 20]
+    y = rnd(70000, 4096, seed=6)                                             # 274 slabs x 4096 columns x 4 B = 4.5 MB
+    o2 = torch.zeros(4096, device=dev())
+    L.colsum(y, 70000, 4096, 4096, o2)
+    assert torch.allclose(o2, y.sum(0), rtol=1e-3, atol=1e-2)
+    assert L._COLSUM_WS[dev().index].data_ptr() != ptr0
+    assert any(t.data_ptr() == ptr0 for t in L._COLSUM_WS_RETIRED)          # retired, still allocated
+    out.fill_(float("nan"))
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.allclose(out, x.sum(0), rtol=1e-4, atol=1e-4)
+    assert int(ws0[:4096].view(torch.int32).abs().sum()) == 0               # counters left at zero
+
+
 # ------------------------------------------------------------------------------------ GEMM
 def _gemm_ref(A, B, a_major, b_major):
     Am = A.float() if a_major == 0 else A.float().t()
