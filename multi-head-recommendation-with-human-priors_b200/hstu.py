@@ -69,10 +69,14 @@ class _Body(nn.Module):
 
 
 class _ResBlock(nn.Module):
-    """Parameter holder for llm_heads.ResBlock (llm_heads.py:16-24): linear [D, D] + bias."""
+    """Parameter holder for llm_heads.ResBlock (llm_heads.py:16-27): [LayerNorm(D) when use_norm,] linear [D, D] + bias,
+    created in the reference's order."""
 
-    def __init__(self, D, zero_init=True):
+    def __init__(self, D, zero_init=True, use_norm=False):
         super().__init__()
+        self.use_norm = use_norm
+        if use_norm:
+            self.norm = nn.LayerNorm(D)
         self.linear = nn.Linear(D, D)
         if zero_init:
             nn.init.zeros_(self.linear.weight)
@@ -112,9 +116,6 @@ class HSTU(nn.Module):
             self.medusa_num_heads = self.num_segment_head + self.num_prior_head
         elif self.head_interaction == "hierarchical":
             self.medusa_num_heads = self.num_segment_head * self.num_prior_head
-            for k in ("head_norm", "cat_bottleneck", "share_seg_weights", "segment_embed"):
-                if config.get(k, False):
-                    raise NotImplementedError(f"hierarchical heads with {k}=True are not built")
         else:
             raise ValueError(f'Unknown head_interaction: {config["head_interaction"]}')
         self.medusa_num_layers = config["medusa_num_layers"]
@@ -164,12 +165,37 @@ class HSTU(nn.Module):
         else:
             if self.head_interaction == "hierarchical":
                 # hstu.py:443-483: per-category block, then per-(category, segment) block; distinct ResBlocks per layer
+                # options (hstu.py:444-451): LayerNorm inside every ResBlock, a LN-Linear-SiLU-Linear bottleneck in front of
+                # the category block, ONE segment block shared by every (category, segment), a learned segment offset
                 nl = self.medusa_num_layers
-                self.medusa_cat_head = nn.ModuleList(
-                    [nn.Sequential(*[_ResBlock(D, zero_init=False) for _ in range(nl)]) for _ in range(self.num_prior_head)])
-                self.medusa_seg_head = nn.ModuleList(
-                    [nn.ModuleList([nn.Sequential(*[_ResBlock(D, zero_init=False) for _ in range(nl)])
-                                    for _ in range(self.num_segment_head)]) for _ in range(self.num_prior_head)])
+                self.head_norm = bool(config.get("head_norm", False))
+                self.cat_bottleneck = bool(config.get("cat_bottleneck", False))
+                self.cat_bottleneck_dim = int(config.get("cat_bottleneck_dim", D // 2))
+                self.share_seg_weights = bool(config.get("share_seg_weights", False))
+                self.use_seg_embed = bool(config.get("segment_embed", False))
+                if self.use_seg_embed:
+                    self.segment_emb = nn.Embedding(self.num_segment_head, D)
+
+                def _blocks():
+                    return [_ResBlock(D, zero_init=False, use_norm=self.head_norm) for _ in range(nl)]
+
+                def _cat_block():
+                    layers = []
+                    if self.cat_bottleneck:
+                        layers += [nn.LayerNorm(D), nn.Linear(D, self.cat_bottleneck_dim), nn.SiLU(),
+                                   nn.Linear(self.cat_bottleneck_dim, D)]
+                    return nn.Sequential(*(layers + _blocks()))
+
+                self.medusa_cat_head = nn.ModuleList([_cat_block() for _ in range(self.num_prior_head)])
+                if self.share_seg_weights:
+                    shared_seg = nn.Sequential(*_blocks())
+                    self.medusa_seg_head = nn.ModuleList(
+                        [nn.ModuleList([shared_seg for _ in range(self.num_segment_head)])
+                         for _ in range(self.num_prior_head)])
+                else:
+                    self.medusa_seg_head = nn.ModuleList(
+                        [nn.ModuleList([nn.Sequential(*_blocks()) for _ in range(self.num_segment_head)])
+                         for _ in range(self.num_prior_head)])
             else:
                 self.medusa_head = nn.ModuleList(
                     [nn.Sequential(*([_ResBlock(D)] * self.medusa_num_layers)) for _ in range(self.medusa_num_heads)])
@@ -645,24 +671,64 @@ class HSTU(nn.Module):
             hd = hd2
         return hd, z, yb
 
-    # ---- hierarchical heads (hstu.py:652-663): head[s*C + c] = seg[c][s](cat[c](y)), every block a chain of
-    # ResBlocks.  A non-shipped variant of the HSTU scripts: one tcgen05 GEMM (ResBlock epilogue) per block
-    # application, recorded on a tape that the backward walks in reverse.
-    def _hier_apply(self, lin, x, out=None, ld_out=None, head=None):
+    # ---- hierarchical heads (hstu.py:652-663): head[s*C + c] = seg[c][s](cat[c](y) [+ segment_emb[s]]), every block a
+    # chain of ResBlocks [with a LayerNorm in front of each], the category block optionally behind a LN-Linear-SiLU-Linear
+    # bottleneck.  A non-shipped variant of the HSTU scripts: one GEMM (ResBlock / bias epilogue) per layer application,
+    # recorded on a tape that the backward walks in reverse; gradients of tensors / weights used more than once add up.
+    def _hier_operand(self, lin, x):
+        """(activation-dtype copy of x, weight operand) of one Linear on the tape."""
+        act = self._act()
+        if act == torch.float32:
+            return x, lin.weight.data
+        xa = torch.empty(x.shape, dtype=act, device=x.device)
+        L.call("b200rec_cast", x.data_ptr(), x.numel(), xa.data_ptr(), L.dt(act), L.stream())
+        return xa, self._shadow_get(lin.weight, f"hier{id(lin)}", tuple(lin.weight.shape))
+
+    def _hier_ln(self, norm, x):
+        """nn.LayerNorm with affine parameters: out = LN(x) * weight + bias (statistics by the LayerNorm kernel)."""
+        rows, D = x.shape
+        dev = x.device
+        xhat = torch.empty((rows, D), dtype=torch.float32, device=dev)
+        mean = torch.empty(rows, dtype=torch.float32, device=dev)
+        rstd = torch.empty(rows, dtype=torch.float32, device=dev)
+        L.call("b200rec_layernorm_fwd", x.data_ptr(), rows, D, float(norm.eps), xhat.data_ptr(), L.F32, mean.data_ptr(),
+               rstd.data_ptr(), L.stream())
+        out = torch.addcmul(norm.bias.data, xhat, norm.weight.data)
+        self._hier_tape.append(("ln", norm, x, xhat, mean, rstd, out))
+        return out
+
+    def _hier_linear(self, lin, x, silu):
+        """out = [silu](x @ W^T + b) without a residual (the bottleneck layers, hstu.py:456-460)."""
+        rows, Din = x.shape
+        Dout = lin.weight.shape[0]
+        act, dev = self._act(), x.device
+        xa, Wa = self._hier_operand(lin, x)
+        out = torch.empty((rows, Dout), dtype=torch.float32, device=dev)
+        z = None
+        if silu:
+            z = torch.empty((rows, Dout), dtype=act, device=dev)
+            zero = torch.zeros((rows, Dout), dtype=torch.float32, device=dev)       # RESBLOCK epilogue with a zero residual
+            L.gemm(xa, Wa, out, rows, Dout, Din, lda=Din, ldb=Din, ldc=Dout, epilogue=L.EPI_RESBLOCK, bias=lin.bias.data,
+                   resid=zero, ldr=Dout, C2=z, ldc2=Dout, n_split=Dout)
+        else:
+            L.gemm(xa, Wa, out, rows, Dout, Din, lda=Din, ldb=Din, ldc=Dout, epilogue=L.EPI_BIAS_RESID, bias=lin.bias.data)
+        self._hier_tape.append(("lin", lin, x, xa, Wa, z, out))
+        return out
+
+    def _hier_apply(self, blk, x, out=None, ld_out=None, head=None):
+        """One llm_heads.ResBlock: x = norm(x) when use_norm, then x + silu(linear(x)) (llm_heads.py:37-40)."""
+        if blk.use_norm:
+            x = self._hier_ln(blk.norm, x)
+        lin = blk.linear
         rows, D = x.shape
         act, dev = self._act(), x.device
-        if act == torch.float32:
-            xa, Wa = x, lin.weight.data
-        else:
-            xa = torch.empty((rows, D), dtype=act, device=dev)
-            L.call("b200rec_cast", x.data_ptr(), x.numel(), xa.data_ptr(), L.dt(act), L.stream())
-            Wa = self._shadow_get(lin.weight, f"hier{id(lin)}", (D, D))
+        xa, Wa = self._hier_operand(lin, x)
         if out is None:
             out, ld_out = torch.empty((rows, D), dtype=torch.float32, device=dev), D
         z = torch.empty((rows, D), dtype=act, device=dev)
         L.gemm(xa, Wa, out, rows, D, D, lda=D, ldb=D, ldc=ld_out, epilogue=L.EPI_RESBLOCK, bias=lin.bias.data, resid=x,
                ldr=D, C2=z, ldc2=D, n_split=D)
-        self._hier_tape.append((lin, x, xa, Wa, z, out, head))
+        self._hier_tape.append(("res", lin, x, xa, Wa, z, out, head))
         return out
 
     def _hier_forward(self, y, rows):
@@ -673,45 +739,108 @@ class HSTU(nn.Module):
         hd2 = hd.view(rows, H * D)
         for c in range(C):
             x = y
-            for blk in self.medusa_cat_head[c]:
-                x = self._hier_apply(blk.linear, x)
+            layers = list(self.medusa_cat_head[c])
+            if self.cat_bottleneck:
+                x = self._hier_ln(layers[0], x)
+                x = self._hier_linear(layers[1], x, silu=True)
+                x = self._hier_linear(layers[3], x, silu=False)
+                layers = layers[4:]
+            for blk in layers:
+                x = self._hier_apply(blk, x)
             for s_ in range(S):
                 xs = x
+                if self.use_seg_embed:                                    # hstu.py:657-661: seg_in = cat_emb + segment_emb[s]
+                    xs = x + self.segment_emb.weight.data[s_]
+                    self._hier_tape.append(("segadd", s_, x, xs))
                 blocks = list(self.medusa_seg_head[c][s_])
                 for blk in blocks[:-1]:
-                    xs = self._hier_apply(blk.linear, xs)
+                    xs = self._hier_apply(blk, xs)
                 h = s_ * C + c
-                self._hier_apply(blocks[-1].linear, xs, out=hd2[:, h * D:(h + 1) * D], ld_out=H * D, head=h)
+                self._hier_apply(blocks[-1], xs, out=hd2[:, h * D:(h + 1) * D], ld_out=H * D, head=h)
         return hd
 
     def _hier_backward(self, d_hd, tape, y, grads):
-        """d_hd fp32 [rows, H, D] -> dy fp32 [rows, D]; fills grads of every ResBlock on the tape."""
+        """d_hd fp32 [rows, H, D] -> dy fp32 [rows, D]; fills grads of every parameter on the tape."""
         rows, D = y.shape
         H = self.num_segment_head * self.num_prior_head
         act, a_dt, st, dev = self._act(), L.dt(self._act()), L.stream(), y.device
         d_hd2 = d_hd.view(rows, H * D)
         gmap = {}      # data_ptr of a tape tensor -> accumulated fp32 gradient
-        for lin, x, xa, Wa, z, out, head in reversed(tape):
-            if head is None:
-                d_out = gmap.pop(out.data_ptr())
-            else:      # the last block of head `head`: its slice of d_hd
-                d_out = d_hd2[:, head * D:(head + 1) * D].contiguous()
-            dz = torch.empty((rows, D), dtype=act, device=dev)
-            d_in = torch.empty((rows, D), dtype=torch.float32, device=dev)
-            L.call("b200rec_resblock_bwd", d_out.data_ptr(), z.data_ptr(), a_dt, rows, 1, D, dz.data_ptr(),
-                   d_in.data_ptr(), st)                                   # dz = d_out * silu'(z) ; d_in = d_out
-            # d_in += dz @ W   (W [Dout, Din] = [K, N] -> MN-major B)
-            L.gemm(dz, Wa, d_in, rows, D, D, lda=D, ldb=D, b_major=1, ldc=D, epilogue=L.EPI_ACCUM)
-            dW = torch.empty((D, D), dtype=torch.float32, device=dev)
-            L.gemm(dz, xa, dW, D, D, rows, lda=D, a_major=1, ldb=D, b_major=1, ldc=D)
-            db = torch.empty(D, dtype=torch.float32, device=dev)
-            L.colsum(dz, rows, D, D, db)
-            grads[lin.weight], grads[lin.bias] = dW, db
+
+        def g_in(x, g):                      # a tensor feeding several ops (y, a category output) collects every branch
             key = x.data_ptr()
             if key in gmap:
-                gmap[key].add_(d_in)
+                gmap[key].add_(g)
             else:
-                gmap[key] = d_in
+                gmap[key] = g
+
+        def g_par(p, g):                     # share_seg_weights: one block serves every (category, segment)
+            grads[p] = grads[p] + g if p in grads else g
+
+        def linear_bwd(lin, xa, Wa, dz, Din, Dout, acc=None):
+            """dz (act dtype) [rows, Dout] -> d_in fp32 [rows, Din] = [acc +] dz @ W; dW = dz^T @ x, db = column sums of dz."""
+            d_in = acc if acc is not None else torch.empty((rows, Din), dtype=torch.float32, device=dev)
+            L.gemm(dz, Wa, d_in, rows, Din, Dout, lda=Dout, ldb=Din, b_major=1, ldc=Din,    # W [Dout, Din] = [K, N]
+                   epilogue=L.EPI_ACCUM if acc is not None else L.EPI_STORE)
+            dW = torch.empty((Dout, Din), dtype=torch.float32, device=dev)
+            L.gemm(dz, xa, dW, Dout, Din, rows, lda=Dout, a_major=1, ldb=Din, b_major=1, ldc=Din)
+            db = torch.empty(Dout, dtype=torch.float32, device=dev)
+            L.colsum(dz, rows, Dout, Dout, db)
+            g_par(lin.weight, dW)
+            g_par(lin.bias, db)
+            return d_in
+
+        for op in reversed(tape):
+            kind = op[0]
+            if kind == "res":
+                _, lin, x, xa, Wa, z, out, head = op
+                if head is None:
+                    d_out = gmap.pop(out.data_ptr())
+                else:      # the last block of head `head`: its slice of d_hd
+                    d_out = d_hd2[:, head * D:(head + 1) * D].contiguous()
+                dz = torch.empty((rows, D), dtype=act, device=dev)
+                d_x = torch.empty((rows, D), dtype=torch.float32, device=dev)
+                L.call("b200rec_resblock_bwd", d_out.data_ptr(), z.data_ptr(), a_dt, rows, 1, D, dz.data_ptr(),
+                       d_x.data_ptr(), st)                                # dz = d_out * silu'(z) ; d_x = d_out (residual)
+                g_in(x, linear_bwd(lin, xa, Wa, dz, D, D, acc=d_x))          # d_x += dz @ W
+            elif kind == "lin":
+                _, lin, x, xa, Wa, z, out = op
+                d_out = gmap.pop(out.data_ptr())
+                Dout, Din = lin.weight.shape
+                if z is not None:                                          # through the SiLU
+                    dz = torch.empty((rows, Dout), dtype=act, device=dev)
+                    scratch = torch.empty((rows, Dout), dtype=torch.float32, device=dev)
+                    L.call("b200rec_resblock_bwd", d_out.data_ptr(), z.data_ptr(), a_dt, rows, 1, Dout, dz.data_ptr(),
+                           scratch.data_ptr(), st)
+                elif act == torch.float32:
+                    dz = d_out
+                else:
+                    dz = torch.empty((rows, Dout), dtype=act, device=dev)
+                    L.call("b200rec_cast", d_out.data_ptr(), d_out.numel(), dz.data_ptr(), a_dt, st)
+                g_in(x, linear_bwd(lin, xa, Wa, dz, Din, Dout))
+            elif kind == "ln":
+                _, norm, x, xhat, mean, rstd, out = op
+                d_out = gmap.pop(out.data_ptr())
+                Dn = x.shape[1]
+                dg = torch.empty(Dn, dtype=torch.float32, device=dev)
+                L.colsum(d_out * xhat, rows, Dn, Dn, dg)
+                db = torch.empty(Dn, dtype=torch.float32, device=dev)
+                L.colsum(d_out, rows, Dn, Dn, db)
+                g_par(norm.weight, dg)
+                g_par(norm.bias, db)
+                d_xhat = d_out * norm.weight.data
+                d_x = torch.empty((rows, Dn), dtype=torch.float32, device=dev)
+                L.call("b200rec_layernorm_bwd", d_xhat.data_ptr(), L.F32, Dn, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                       rows, Dn, None, d_x.data_ptr(), None, st)
+                g_in(x, d_x)
+            else:                                                          # "segadd": xs = x + segment_emb[s]
+                _, s_, x, xs = op
+                d_out = gmap.pop(xs.data_ptr())
+                w = self.segment_emb.weight
+                if w not in grads:
+                    grads[w] = torch.zeros_like(w.data)
+                L.colsum(d_out, rows, D, D, grads[w][s_], accumulate=True)
+                g_in(x, d_out)
         return gmap.pop(y.data_ptr())
 
     # ------------------------------------------------------------------ prior switch (hstu.py:512-544, 731-805)

@@ -144,10 +144,20 @@ class OracleHSTU:
         else:
             self.prior_w = [1.0 / self.C] * self.C
         self.int_to_category = cfg["int_to_category"]
-        if self.inter == "hierarchical":
-            for k in ("head_norm", "cat_bottleneck", "share_seg_weights", "segment_embed"):
-                if cfg_get(cfg, k, False):
-                    raise NotImplementedError(f"oracle covers hierarchical heads with {k}=False")
+        # hierarchical head options (hstu.py:444-483): LayerNorm inside every ResBlock, a bottleneck MLP in front of the
+        # category block, one segment block shared by every (category, segment), a learned per-segment input offset
+        self.head_norm = self.inter == "hierarchical" and bool(cfg_get(cfg, "head_norm", False))
+        self.cat_bottleneck = self.inter == "hierarchical" and bool(cfg_get(cfg, "cat_bottleneck", False))
+        self.seg_embed = self.inter == "hierarchical" and bool(cfg_get(cfg, "segment_embed", False))
+        if self.inter == "hierarchical" and bool(cfg_get(cfg, "share_seg_weights", False)) and self.mlayers > 0:
+            # hstu.py:473-478 registers ONE segment block under every medusa_seg_head.{c}.{s} name; a state dict saved to
+            # disk no longer aliases them, so tie the entries again (the gradient lands on the first name, like
+            # named_parameters() reports it)
+            for k in list(self.p):
+                if k.startswith("medusa_seg_head."):
+                    parts = k.split(".")
+                    parts[1], parts[2] = "0", "0"
+                    self.p[k] = self.p[".".join(parts)]
 
     # ---- pieces -----------------------------------------------------------------
     def embed(self, ids):
@@ -171,13 +181,32 @@ class OracleHSTU:
         """y [..., D] -> [H, ..., D]; head h = x + silu(W_h x + b_h), weight-tied when
         medusa_num_layers > 1 (hstu.py:486-493, llm_heads.py:26-40)."""
         if self.inter == "hierarchical":                                          # hstu.py:652-663, 915-925
-            def chain(x, prefix):
-                for l in range(self.mlayers):                                     # distinct ResBlocks per layer (:460,468)
+            D = y.shape[-1]
+
+            def chain(x, prefix, first=0):
+                for l in range(first, first + self.mlayers):                      # distinct ResBlocks per layer (:460,468)
+                    if self.head_norm:                                            # llm_heads.py:37-39: x = norm(x) FIRST,
+                        x = F.layer_norm(x, (D,), self.p[f"{prefix}.{l}.norm.weight"],   # the residual is the normed x
+                                         self.p[f"{prefix}.{l}.norm.bias"], 1e-5)
                     W, b = self.p[f"{prefix}.{l}.linear.weight"], self.p[f"{prefix}.{l}.linear.bias"]
                     x = x + F.silu(x @ W.t() + b)
                 return x
-            cat = [chain(y, f"medusa_cat_head.{c}") for c in range(self.C)]
-            outs = [chain(cat[c], f"medusa_seg_head.{c}.{s}") for s in range(self.S) for c in range(self.C)]
+
+            def cat_block(c):
+                x, pre, first = y, f"medusa_cat_head.{c}", 0
+                if self.cat_bottleneck:                                           # :455-461 LN, Linear, SiLU, Linear (no residual)
+                    x = F.layer_norm(x, (D,), self.p[f"{pre}.0.weight"], self.p[f"{pre}.0.bias"], 1e-5)
+                    x = F.silu(x @ self.p[f"{pre}.1.weight"].t() + self.p[f"{pre}.1.bias"])
+                    x = x @ self.p[f"{pre}.3.weight"].t() + self.p[f"{pre}.3.bias"]
+                    first = 4
+                return chain(x, pre, first)
+
+            cat = [cat_block(c) for c in range(self.C)]
+            outs = []
+            for s in range(self.S):                                               # :656-663 (share_seg_weights: the state
+                for c in range(self.C):                                           # dict aliases one block under every key)
+                    x = cat[c] + self.p["segment_emb.weight"][s] if self.seg_embed else cat[c]
+                    outs.append(chain(x, f"medusa_seg_head.{c}.{s}"))
             return torch.stack(outs, dim=0)                                       # h = s*C + c
         outs = []
         for h in range(self.H):
@@ -464,11 +493,19 @@ def recall_ndcg_sums(rec_topk, topk_list):
 
 
 def state_dict_from_module(module, dtype=torch.float32, requires_grad=False):
-    sd = {}
+    """Leaf copies of a module's state dict.  Entries that alias one tensor in the module (share_seg_weights registers one
+    block under several names, hstu.py:473-478) stay ONE leaf, so its gradient is the sum over all uses, like autograd's."""
+    sd, seen = {}, {}
     for k, v in module.state_dict().items():
+        key = (v.data_ptr(), tuple(v.shape), v.dtype) if v.numel() > 0 else None
+        if key is not None and key in seen:
+            sd[k] = seen[key]
+            continue
         t = v.detach().clone()
         if t.is_floating_point():
             t = t.to(dtype)
             t.requires_grad_(requires_grad)
         sd[k] = t
+        if key is not None:
+            seen[key] = t
     return sd

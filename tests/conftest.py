@@ -18,7 +18,7 @@ def golden_dir():
 
 
 GOLDEN_CASES = ["nce_single", "nce_2attn", "prior_additive", "prior_mult", "prior_event_given", "nce_pred4",
-                "tower_additive", "mult_2layers", "hier_2x7", "switch_bce", "switch_asl_master"]
+                "tower_additive", "mult_2layers", "hier_2x7", "hier_options", "switch_bce", "switch_asl_master"]
 
 
 def load_golden(name):

@@ -34,6 +34,11 @@ CASES = {
     # hierarchical heads seg[c][s](cat[c](x)) (hstu.py:443-483, 652-663), 2 segments x 7 categories, 2 layers each
     "hier_2x7": ("D", dict(TINY, head_interaction="hierarchical", num_segment_head=2, pred_len=4, eval_pred_len=4,
                            medusa_num_layers=2)),
+    # every hierarchical-head option at once (hstu.py:444-483): LayerNorm inside the ResBlocks, bottleneck MLP (32 -> 16 -> 32)
+    # in front of the category block, ONE segment block shared by all (category, segment), learned segment offsets
+    "hier_options": ("D", dict(TINY, head_interaction="hierarchical", num_segment_head=2, pred_len=4, eval_pred_len=4,
+                               medusa_num_layers=2, head_norm=True, cat_bottleneck=True, share_seg_weights=True,
+                               segment_embed=True)),
     # prior-switch aux heads (hstu.py:512-544, 731-805): weighted BCE over all positions / ASL on the last position with a
     # master switch, both used at test time to switch prior heads off
     "switch_bce": ("B", dict(TINY, prior_switch="in", prior_switch_loss_weight=0.7, use_prior_switch_test=True)),

@@ -22,7 +22,14 @@ SMALL = dict(n_layers=2, n_heads=2, item_embedding_size=32, hstu_embedding_size=
     ("D", dict(SMALL, medusa_num_layers=2)),                                        # weight-tied 2-layer heads
     ("D", dict(SMALL, head_interaction="hierarchical", num_segment_head=2, pred_len=4, eval_pred_len=4,
                medusa_num_layers=2)),                                              # seg[c][s](cat[c](x))
-], ids=["nce", "additive", "mult", "event", "mult-2seg", "tower", "tied-2layer", "hierarchical"])
+    ("D", dict(SMALL, head_interaction="hierarchical", num_segment_head=2, pred_len=4, eval_pred_len=4,
+               medusa_num_layers=2, head_norm=True, cat_bottleneck=True, share_seg_weights=True, segment_embed=True)),
+    ("D", dict(SMALL, head_interaction="hierarchical", num_segment_head=2, pred_len=4, eval_pred_len=4,
+               medusa_num_layers=1, head_norm=True, cat_bottleneck=True, cat_bottleneck_dim=8)),
+    ("D", dict(SMALL, head_interaction="hierarchical", num_segment_head=2, pred_len=4, eval_pred_len=4,
+               medusa_num_layers=1, share_seg_weights=True, segment_embed=True)),
+], ids=["nce", "additive", "mult", "event", "mult-2seg", "tower", "tied-2layer", "hierarchical", "hier-all-options",
+        "hier-norm-bottleneck", "hier-shared-segembed"])
 def test_train_step_matches_reference(preset, over):
     cfg = synth.make_config(preset, **over)
     dl = synth.make_dataload(cfg)
@@ -60,3 +67,24 @@ def test_relative_position_bias_matches_live_module():
                bucketization_fn=lambda x: (torch.log(torch.abs(x).clamp(min=1)) / 0.301).long())
         ref = m(torch.zeros(2, N, dtype=torch.long))[0, :L, :L]
         assert torch.equal(ref, orc.rel_pos_bias(m._pos_w.data, m._ts_w.data, L))
+
+
+@pytest.mark.parametrize("over", [
+    dict(),
+    dict(head_interaction="hierarchical", num_segment_head=2, pred_len=4, eval_pred_len=4, medusa_num_layers=2),
+    dict(head_interaction="hierarchical", num_segment_head=2, pred_len=4, eval_pred_len=4, medusa_num_layers=2,
+         head_norm=True, cat_bottleneck=True, share_seg_weights=True, segment_embed=True),
+], ids=["mult", "hierarchical", "hier-all-options"])
+def test_same_seed_init_is_bit_identical_to_the_reference(over):
+    """parameters are created in the reference's order with the reference's initialisers, so the same seed gives
+    the same weights (incl. the hierarchical-head options: segment_emb, bottleneck, per-block LayerNorm, shared block)."""
+    from b200rec.hstu import HSTU
+    cfg = synth.make_config("D", **dict(SMALL, **over))
+    dl = synth.make_dataload(cfg)
+    ref = rh.build_reference_model(dict(cfg), cfg["item_num"], dl.category_counts, dl.category_to_int, seed=2020)
+    torch.manual_seed(2020)
+    mine = HSTU(cfg, dl, compute_dtype=torch.float32)
+    rsd, msd = ref.state_dict(), mine.state_dict()
+    assert list(rsd) == list(msd)
+    for k in rsd:
+        assert torch.equal(rsd[k], msd[k]), k
