@@ -709,7 +709,7 @@ class HSTU(nn.Module):
             z = torch.empty((rows, Dout), dtype=act, device=dev)
             zero = torch.zeros((rows, Dout), dtype=torch.float32, device=dev)       # RESBLOCK epilogue with a zero residual
             L.gemm(xa, Wa, out, rows, Dout, Din, lda=Din, ldb=Din, ldc=Dout, epilogue=L.EPI_RESBLOCK, bias=lin.bias.data,
-                   resid=zero, ldr=Dout, C2=z, ldc2=Dout, n_split=Dout)
+                   resid=zero, ldr=Dout, C2=z, ldc2=Dout)      # n_split = 0: no column wrap (Dout need not be a multiple of 32)
         else:
             L.gemm(xa, Wa, out, rows, Dout, Din, lda=Din, ldb=Din, ldc=Dout, epilogue=L.EPI_BIAS_RESID, bias=lin.bias.data)
         self._hier_tape.append(("lin", lin, x, xa, Wa, z, out))
@@ -727,7 +727,7 @@ class HSTU(nn.Module):
             out, ld_out = torch.empty((rows, D), dtype=torch.float32, device=dev), D
         z = torch.empty((rows, D), dtype=act, device=dev)
         L.gemm(xa, Wa, out, rows, D, D, lda=D, ldb=D, ldc=ld_out, epilogue=L.EPI_RESBLOCK, bias=lin.bias.data, resid=x,
-               ldr=D, C2=z, ldc2=D, n_split=D)
+               ldr=D, C2=z, ldc2=D)
         self._hier_tape.append(("res", lin, x, xa, Wa, z, out, head))
         return out
 
