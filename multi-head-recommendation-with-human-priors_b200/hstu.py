@@ -171,6 +171,9 @@ class HSTU(nn.Module):
                 self.head_norm = bool(config.get("head_norm", False))
                 self.cat_bottleneck = bool(config.get("cat_bottleneck", False))
                 self.cat_bottleneck_dim = int(config.get("cat_bottleneck_dim", D // 2))
+                if self.cat_bottleneck and compute_dtype != torch.float32 and self.cat_bottleneck_dim % 8 != 0:
+                    raise NotImplementedError("cat_bottleneck_dim must be a multiple of 8 in bf16 mode (16-byte TMA row pitch "
+                                              f"of the tcgen05 GEMM operands), got {self.cat_bottleneck_dim}")
                 self.share_seg_weights = bool(config.get("share_seg_weights", False))
                 self.use_seg_embed = bool(config.get("segment_embed", False))
                 if self.use_seg_embed:

@@ -67,7 +67,8 @@ def test_product_package_does_not_import_oracle():
 def test_unsupported_configs_raise():
     from b200rec import synth
     from b200rec.hstu import HSTU
-    for over in (dict(prior_switch="in_out", prior_switch_loss_weight=1.0), dict(pos_sample_mix_ratio=0.1)):
+    for over in (dict(prior_switch="in_out", prior_switch_loss_weight=1.0), dict(pos_sample_mix_ratio=0.1),
+                 dict(head_interaction="hierarchical", cat_bottleneck=True, cat_bottleneck_dim=12)):   # bf16: 16-byte TMA pitch
         cfg = synth.make_config("D", item_num=200, **over)
         with pytest.raises(NotImplementedError):
             HSTU(cfg, synth.make_dataload(cfg))
