@@ -21,13 +21,19 @@ TINY = dict(n_layers=2, n_heads=2, item_embedding_size=32, hstu_embedding_size=3
 CASES = {
     "comirec_p1": dict(TINY, interest_num=4),
     "comirec_p4": dict(TINY, pred_len=4, eval_pred_len=4, interest_num=3, interest_hidden=20),
+    # REMI (remi.py): routing regularisation + interest-aware hard negatives; the shipped remi.yaml values first
+    "remi_p1": dict(TINY, model="REMI", interest_num=4, lambda_rr=100.0, beta_ihn=1.0, attention_net_bias=False,
+                    interest_hidden_ratio=0.5),
+    "remi_p3_beta4": dict(TINY, model="REMI", pred_len=3, eval_pred_len=3, interest_num=3, lambda_rr=10.0, beta_ihn=4.0,
+                          attention_net_bias=True, interest_hidden=20),
+    "remi_p2_beta0": dict(TINY, model="REMI", pred_len=2, eval_pred_len=2, interest_num=4, lambda_rr=100.0, beta_ihn=0.0),
 }
 
 
 def _assert_margin(ref, batch, cfg):
     """Top-2 gap of the readout similarities on the valid (token, offset) pairs: the selection must not hinge on rounding."""
     from oracle.comirec_oracle import OracleComiRec
-    o = OracleComiRec(cfg, {k: v.detach().clone() for k, v in ref.state_dict().items()})
+    o = OracleComiRec(dict(cfg), {k: v.detach().clone() for k, v in ref.state_dict().items()})
     items, _, mask, _ = batch
     L, P = o.L, o.P
     m = mask.bool()
@@ -48,7 +54,10 @@ def _assert_margin(ref, batch, cfg):
 def run_case(name, over):
     cfg = synth.make_config("A2", **over)
     rh.load()
-    from REC.model.IDNet.comirec import ComiRec
+    if over.get("model") == "REMI":
+        from REC.model.IDNet.remi import REMI as ComiRec
+    else:
+        from REC.model.IDNet.comirec import ComiRec
     torch.manual_seed(2020)
     with contextlib.redirect_stdout(io.StringIO()):
         ref = ComiRec(rh.RefConfig(dict(cfg)), rh.RefDataload(cfg["item_num"]))
@@ -81,5 +90,7 @@ def run_case(name, over):
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
     for name, over in CASES.items():
-        run_case(name, over)
+        if not only or any(name.startswith(o) for o in only):
+            run_case(name, over)

@@ -81,13 +81,14 @@ def test_combine_equals_max_over_heads():
     assert np.array_equal(src, torch.gather(am, 1, i2).numpy())
 
 
-@pytest.mark.parametrize("name", ["comirec_p1", "comirec_p4"])
+@pytest.mark.parametrize("name", ["comirec_p1", "comirec_p4", "remi_p1", "remi_p3_beta4", "remi_p2_beta0"])
 def test_comirec_oracle_matches_live_reference_fixture(name):
-    """oracle/comirec_oracle.py against tests/golden/comirec_*.pt (live reference ComiRec, make_golden_comirec.py)."""
-    from oracle.comirec_oracle import OracleComiRec
+    """oracle/comirec_oracle.py against tests/golden/comirec_*.pt / remi_*.pt (live reference ComiRec / REMI classes,
+    make_golden_comirec.py)."""
+    from oracle.comirec_oracle import OracleComiRec, OracleREMI
     fx = load_golden(name)
     sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in fx["state_dict"].items()}
-    model = OracleComiRec(fx["cfg"], sd)
+    model = (OracleREMI if name.startswith("remi") else OracleComiRec)(fx["cfg"], sd)
     out = model.forward(fx["train_batch"])
     assert abs(float(out["loss"].detach()) - fx["loss"]) <= 2e-6 * max(1.0, abs(fx["loss"]))
     out["loss"].backward()
