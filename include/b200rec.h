@@ -320,6 +320,18 @@ int b200rec_nce_loss_fwd(const float* logits, int64_t ld_logits, int n_neg,
                          const uint8_t* tok_ok, int tok_ok_ld, int tok_ok_col, const float* coef,
                          const float* logit_scale, float* loss, float* g0, float* dscale,
                          int32_t* rank0, int32_t* nvalid, void* G, int64_t ldg, void* stream);
+/* REMI's interest-aware hard negatives (REC/model/IDNet/remi.py:198-277 with beta_ihn > 0, + autograd) on the same
+ * inputs and with the same outputs as b200rec_nce_loss_fwd (generic shared-memory kernel only):
+ *   loss = coef * (logaddexp(z_pos, LSE_j((beta+1) z_j) - LSE_j(beta z_j) + log n_neg) - z_pos),  z = tau * cos,
+ * the sums over the negatives the false-negative filter keeps, n_neg = all negatives of the row (remi.py:244).
+ * g0 = d loss / d z_pos, dscale = d loss / d log tau, G[t, j] = d loss / d cos-logit (act dtype), rank0 / nvalid as above
+ * (rank0 is filled for every served offset).  A row without any kept negative has loss 0 and zero gradients. */
+int b200rec_nce_ihn_loss_fwd(const float* logits, int64_t ld_logits, int n_neg, const uint32_t* same_bits,
+                             const void* q_hat, int64_t ldq, const void* t_hat, int act_dtype, int D,
+                             const int32_t* tok_b, const int32_t* tok_pos, int T, int LP, int P, uint32_t p_mask,
+                             const uint8_t* tok_ok, int tok_ok_ld, int tok_ok_col, const float* coef,
+                             const float* logit_scale, float beta, float* loss, float* g0, float* dscale,
+                             int32_t* rank0, int32_t* nvalid, void* G, int64_t ldg, void* stream);
 /* gscale (nullable device scalar) multiplies the upstream gradient in the two pos_bwd calls. */
 /* coef[p] = lam[p] * w / max(cnt[p], 1)   (hstu.py:708-712, 850-852) */
 int b200rec_nce_coef(const int32_t* cnt, const float* lam, float w, int P, float* coef, void* stream);
@@ -596,6 +608,14 @@ int b200rec_comi_select_fwd(const float* u, const float* traw, const int32_t* to
 int b200rec_comi_select_bwd(const float* d_hd, const int32_t* sel, int T, int P, int K, int D, float* du, void* stream);
 int b200rec_comi_pool_bwd(const float* du, const float* u, const float* y, const float* a, const float* M, const float* S,
                           const int32_t* seq_off, int B, int K, int D, float* dy, float* da, void* stream);
+/* REMI's routing regulariser on the same routing logits (REC/model/IDNet/remi.py:156-196, 356-372, + autograd):
+ *   var2[t, k] = (variance over the n valid window positions of the routing weights of interest k at token t / D)^2,
+ *   rr = sum(var2) / seq_off[B_real]  (mean over the valid positions; the caller sums), da[t, k] = d rr / d a[t, k]
+ * (nullable: forward only; otherwise scratch = [T, K, 3] floats).  One scan per (sequence, interest) instead of the
+ * reference's [B*L, K, L] routing tensor.  Sequences >= B_real (the dummy sequence of static-token mode) are skipped:
+ * the caller zero-fills var2 / da. */
+int b200rec_comi_rr(const float* a, const int32_t* seq_off, int B_real, int K, int D, float* var2, float* scratch,
+                    float* da, void* stream);
 
 #ifdef __cplusplus
 }

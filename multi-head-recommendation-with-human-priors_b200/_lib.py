@@ -119,6 +119,8 @@ _SIGS = {
     "b200rec_hstu_attn_seq_bwd": (C.c_int, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P, _P]),
     "b200rec_nce_loss_fwd": (C.c_int, [_P, _L, _I, _P, _P, _P, _P, _L, _P, _I, _I, _P, _P, _I, _I, _I, C.c_uint32,
                                        _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
+    "b200rec_nce_ihn_loss_fwd": (C.c_int, [_P, _L, _I, _P, _P, _L, _P, _I, _I, _P, _P, _I, _I, _I, C.c_uint32,
+                                           _P, _I, _I, _P, _P, _F, _P, _P, _P, _P, _P, _P, _L, _P]),
     "b200rec_switch_rows": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "b200rec_switch_loss": (C.c_int, [_P, _L, _I, _I, _I, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _F, _P,
                                       _P, _P, _P, _P]),
@@ -168,6 +170,7 @@ _SIGS = {
     "b200rec_comi_select_fwd": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "b200rec_comi_select_bwd": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "b200rec_comi_pool_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "b200rec_comi_rr": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "b200rec_adamw_rows": (C.c_int, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _F, _F, _F, _F, _F, _I, _F, _P, _P]),
 }
 EXPORTS = ["b200rec_last_error"] + sorted(_SIGS)

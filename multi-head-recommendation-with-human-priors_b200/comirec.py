@@ -12,8 +12,10 @@ and the P per-offset query sets run through the HSTU NCE machinery as P "heads" 
 comes back through the select / pooling / attention-net backward kernels into the body.  predict() scores the K
 interests of the whole sequence against the catalogue ([B, K, N], comirec.py:351-414).
 
-Not built: REMI's routing regulariser and interest-aware negatives (remi.py), `skip_hstu`, dropout inside
-attention_net during training (p > 0 raises), item_embedding_size != hstu_embedding_size.  Module registration order
+REMI (remi.py) is the same model with two training-time additions, both built here: the routing regulariser on the
+attention-net logits (b200rec_comi_rr) and the interest-aware hard-negative loss (b200rec_nce_ihn_loss_fwd).
+Not built: `skip_hstu`, dropout inside attention_net during training (p > 0 raises), item_embedding_size !=
+hstu_embedding_size.  Module registration order
 differs from the reference (attention_net is created after the body's parameters), so a same-seed init is not
 bit-identical; loading a reference state dict is.
 """
@@ -35,7 +37,10 @@ class _Readout(object):
         D, Hd, K = y.shape[1], self.hidden, self.K
         lin1, lin2 = model.attention_net[0], model.attention_net[3]
         h = torch.empty((T, Hd), dtype=torch.float32, device=y.device)
-        L.gemm(y, lin1.weight.data, h, T, Hd, D, lda=D, ldb=D, ldc=Hd, epilogue=L.EPI_BIAS_RESID, bias=lin1.bias.data)
+        if lin1.bias is not None:
+            L.gemm(y, lin1.weight.data, h, T, Hd, D, lda=D, ldb=D, ldc=Hd, epilogue=L.EPI_BIAS_RESID, bias=lin1.bias.data)
+        else:                                               # REMI: attention_net_bias = False (remi.py:91)
+            L.gemm(y, lin1.weight.data, h, T, Hd, D, lda=D, ldb=D, ldc=Hd)
         L.call("b200rec_comi_tanh", h.data_ptr(), h.numel(), L.stream())
         a = torch.empty((T, K), dtype=torch.float32, device=y.device)
         L.gemm(h, lin2.weight.data, a, T, K, Hd, lda=Hd, ldb=Hd, ldc=K)
@@ -50,11 +55,25 @@ class _Readout(object):
                S.data_ptr(), L.stream())
         return u, M, S
 
-    def train_forward(self, model, y, W, items, tok_b, tok_pos, seq_off, B, LP, T):
+    def _routing_reg(self, model, a, seq_off, B_real, T, need_grad):
+        """REMI's routing regulariser (remi.py:156-196, 356-372) from the routing logits a [T, K]: (rr, d rr / d a)."""
+        K, dev = self.K, a.device
+        var2 = torch.zeros((T, K), dtype=torch.float32, device=dev)            # dummy tokens (static mode) stay 0
+        da = torch.zeros((T, K), dtype=torch.float32, device=dev) if need_grad else None
+        scratch = torch.empty((T, K, 3), dtype=torch.float32, device=dev) if need_grad else None
+        L.call("b200rec_comi_rr", a.data_ptr(), seq_off.data_ptr(), B_real, K, model._hstu_embedding_dim, var2.data_ptr(),
+               L.ptr(scratch), L.ptr(da), L.stream())
+        n_valid = seq_off[B_real].to(torch.float32).clamp(min=1.0)             # device scalar: no host sync
+        return var2.sum() / n_valid, da
+
+    def train_forward(self, model, y, W, items, tok_b, tok_pos, seq_off, B, LP, T, B_real=None, need_grad=True):
         D, P, K = y.shape[1], model.pred_len, self.K
         if model.training and model.attention_net[2].p > 0:
             raise NotImplementedError("ComiRec: dropout inside attention_net (hidden_dropout_prob > 0 in training) is not built")
         h, a = self._logits(model, y, T)
+        rr = da_rr = None
+        if float(getattr(model, "lambda_rr", 0.0)) > 0:
+            rr, da_rr = self._routing_reg(model, a, seq_off, B if B_real is None else B_real, T, need_grad)
         u, M, S = self._pool(y, a, seq_off, B, T)
         traw = torch.empty((B * LP, D), dtype=torch.float32, device=y.device)
         L.call("b200rec_gather_rows", W.data_ptr(), D, items.reshape(-1).data_ptr(), B * LP, traw.data_ptr(), L.F32, L.stream())
@@ -62,7 +81,7 @@ class _Readout(object):
         sel = torch.empty((T, P), dtype=torch.int32, device=y.device)
         L.call("b200rec_comi_select_fwd", u.data_ptr(), traw.data_ptr(), tok_b.data_ptr(), tok_pos.data_ptr(), T, LP, P, K, D,
                hd.data_ptr(), sel.data_ptr(), L.stream())
-        return hd, dict(y=y, h=h, a=a, u=u, M=M, S=S, sel=sel)
+        return hd, dict(y=y, h=h, a=a, u=u, M=M, S=S, sel=sel, rr=rr, da_rr=da_rr)
 
     def train_backward(self, model, d_hd, ctx, grads):
         c = ctx["comi"]
@@ -78,6 +97,8 @@ class _Readout(object):
         da = torch.zeros((T, K), dtype=torch.float32, device=dev)
         L.call("b200rec_comi_pool_bwd", du.data_ptr(), u.data_ptr(), y.data_ptr(), a.data_ptr(), c["M"].data_ptr(),
                c["S"].data_ptr(), ctx["seq_off"].data_ptr(), B, K, D, dy.data_ptr(), da.data_ptr(), st)
+        if c.get("da_rr") is not None:                      # + lambda_rr * d rr / d a, scaled like every other gradient
+            da.add_(c["da_rr"] * (ctx["gscale"].reshape(()) * float(model.lambda_rr)))
         # attention net: a = h W2^T, h = tanh(y W1^T + b1)
         dW2 = torch.empty((K, Hd), dtype=torch.float32, device=dev)
         L.gemm(da, h, dW2, K, Hd, T, lda=K, a_major=1, ldb=Hd, b_major=1, ldc=Hd)
@@ -86,10 +107,12 @@ class _Readout(object):
         L.call("b200rec_comi_tanh_bwd", h.data_ptr(), dh.data_ptr(), dh.numel(), st)          # dh -> dz1
         dW1 = torch.empty((Hd, D), dtype=torch.float32, device=dev)
         L.gemm(dh, y, dW1, Hd, D, T, lda=Hd, a_major=1, ldb=D, b_major=1, ldc=D)
-        db1 = torch.empty(Hd, dtype=torch.float32, device=dev)
-        L.colsum(dh, T, Hd, Hd, db1)
+        if lin1.bias is not None:
+            db1 = torch.empty(Hd, dtype=torch.float32, device=dev)
+            L.colsum(dh, T, Hd, Hd, db1)
+            grads[lin1.bias] = db1
         L.gemm(dh, lin1.weight.data, dy, T, D, Hd, lda=Hd, ldb=D, b_major=1, ldc=D, epilogue=L.EPI_ACCUM)
-        grads[lin1.weight], grads[lin1.bias], grads[lin2.weight] = dW1, db1, dW2
+        grads[lin1.weight], grads[lin2.weight] = dW1, dW2
         return dy
 
     def predict_heads(self, model, y, seq_off, B, T):
@@ -114,16 +137,21 @@ class ComiRec(HSTU):
             raise NotImplementedError("ComiRec: skip_hstu is not built")
         D = cfg["hstu_embedding_size"]
         self._comi_K = int(config.get("interest_num", None) or 4)                       # comirec.py:89
-        self._comi_hidden = int(config.get("interest_hidden", None) or D // 2)          # comirec.py:88
+        self._comi_hidden, net_bias = self._attention_net_shape(config, D)
         self._readout = _Readout(self._comi_K, self._comi_hidden)
         super().__init__(cfg, dataload, compute_dtype)
         self.num_interest = self._comi_K
         self.medusa_num_heads = self._comi_K            # eval: one score row per interest (comirec.py:409-411)
         self.attention_net = nn.Sequential(             # comirec.py:91-96
-            nn.Linear(D, self._comi_hidden, bias=True), nn.Tanh(), nn.Dropout(self._linear_dropout_rate),
+            nn.Linear(D, self._comi_hidden, bias=net_bias), nn.Tanh(), nn.Dropout(self._linear_dropout_rate),
             nn.Linear(self._comi_hidden, self._comi_K, bias=False))
         for p in self.attention_net.parameters():       # comirec.py:135-146 (reset_params)
             truncated_normal_(p.data, mean=0.0, std=0.02)
+
+    @staticmethod
+    def _attention_net_shape(config, D):
+        """(hidden width, first Linear has a bias) of the attention net (comirec.py:88, 92)."""
+        return int(config.get("interest_hidden", None) or D // 2), True
 
     def _build_jobs(self):
         """One NCE job per prediction offset: offset p has its own queries (the interest chosen against ITS target),
@@ -134,6 +162,28 @@ class ComiRec(HSTU):
         out = super().forward(interaction, n_tokens=n_tokens, prepared=prepared)
         out.pop("seg_0_loss", None)                     # the HSTU path's per-segment log has no ComiRec counterpart
         return out
+
+
+class REMI(ComiRec):
+    """REC/model/IDNet/remi.py:14 `REMI(config, dataload)`: ComiRec-SA on the HSTU body trained with routing
+    regularisation (lambda_rr, remi.py:156-196, 356-372: b200rec_comi_rr) and interest-aware hard negatives (beta_ihn,
+    remi.py:198-277: b200rec_nce_ihn_loss_fwd on the un-fused logits; beta_ihn <= 0 is the plain sampled softmax of
+    ComiRec on the fused path).  predict() is ComiRec's (remi.py:439-496).  Same state-dict names; the attention net's
+    first Linear has no bias when `attention_net_bias` is False, its width defaults to D * interest_hidden_ratio."""
+
+    def __init__(self, config, dataload, compute_dtype=torch.bfloat16):
+        lam, beta = config.get("lambda_rr", None), config.get("beta_ihn", None)
+        self.lambda_rr = 100.0 if lam is None else float(lam)                           # remi.py:38
+        self.beta_ihn = 1.0 if beta is None else float(beta)                            # remi.py:40
+        self._ihn_beta = max(self.beta_ihn, 0.0)
+        super().__init__(config, dataload, compute_dtype)
+
+    @staticmethod
+    def _attention_net_shape(config, D):
+        ratio = config.get("interest_hidden_ratio", None)
+        hidden = config.get("interest_hidden", None) or int(D * (0.5 if ratio is None else float(ratio)))   # remi.py:87
+        bias = config.get("attention_net_bias", None)
+        return int(hidden), True if bias is None else bool(bias)                                        # remi.py:91
 
 
 def _hstu_config(config):

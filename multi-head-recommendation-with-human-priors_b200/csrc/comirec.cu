@@ -204,3 +204,30 @@ extern "C" int b200rec_comi_pool_bwd(const float* du, const float* u, const floa
   B200_LAUNCH_OK();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------- REMI routing regulariser
+// remi.py:156-196, 356-372 (and its autograd): one thread per (sequence, interest) runs the scans of remi_core.cuh
+// over the sequence's tokens (the work is O(T K) scalars: latency-bound by design, a few microseconds).  Sequences
+// b >= B_real (the dummy sequence of static-token mode) are not visited: their var2 / da entries stay as the caller
+// initialised them (zero).  The mean is over the seq_off[B_real] valid positions of the batch, read on the device.
+#include "remi_core.cuh"
+
+__global__ void __launch_bounds__(128) comi_rr_kernel(const float* __restrict__ a, const int32_t* __restrict__ seq_off,
+                                                      int B_real, int K, int D, float* __restrict__ var2,
+                                                      float* __restrict__ scratch, float* __restrict__ da) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B_real * K) return;
+  const int b = idx / K, k = idx % K;
+  const float inv_n = 1.f / fmaxf((float)seq_off[B_real], 1.f);
+  remi_rr_scan(a, K, k, seq_off[b], seq_off[b + 1], 1.f / (float)D, inv_n, var2, scratch, da);
+}
+
+extern "C" int b200rec_comi_rr(const float* a, const int32_t* seq_off, int B_real, int K, int D, float* var2,
+                               float* scratch, float* da, void* stream) {
+  B200_CHECK_ARG(K >= 1 && D >= 1 && B_real >= 0, "comi_rr: bad B=%d K=%d D=%d", B_real, K, D);
+  B200_CHECK_ARG(da == nullptr || scratch != nullptr, "comi_rr: the backward needs the [T, K, 3] scratch");
+  if (B_real == 0) return 0;
+  comi_rr_kernel<<<(B_real * K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a, seq_off, B_real, K, D, var2, scratch, da);
+  B200_LAUNCH_OK();
+  return 0;
+}

@@ -560,6 +560,184 @@ int b200rec_nce_loss_fwd(const float* logits, int64_t ld_logits, int n_neg, cons
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// REMI's interest-aware hard negatives (REC/model/IDNet/remi.py:198-277 with beta > 0, + autograd): per (token, offset)
+//     loss = logaddexp(z_pos, LSE_j((beta + 1) z_j) - LSE_j(beta z_j) + log N) - z_pos,     z = tau * cos,
+// the sums over the negatives the false-negative filter keeps, N = ALL negatives of the row (remi.py:244).  With
+// sigma = e^(log_neg - lse) (the mass of the negative term), p1 / p2 = softmax of (beta + 1) z / beta z over the kept
+// negatives:  d loss / d z_pos = -sigma,  d loss / d z_j = sigma ((beta + 1) p1_j - beta p2_j),
+//             d loss / d log tau = sigma ((beta + 1) <p1, z> - beta <p2, z> - z_pos).
+// Same block-per-query-row layout, inputs and outputs as nce_loss_fwd_kernel (rank0 / nvalid feed the same top-k
+// logging); every offset takes the filtered pass (the two temperatures leave nothing to share between offsets).
+template <typename TA>
+__global__ void __launch_bounds__(NCE_THREADS)
+nce_ihn_loss_fwd_kernel(const float* __restrict__ logits, int64_t ld_logits, int n_neg,
+                        const uint32_t* __restrict__ same_bits, const TA* __restrict__ q_hat, int64_t ldq,
+                        const TA* __restrict__ t_hat, int D, const int32_t* __restrict__ tok_b,
+                        const int32_t* __restrict__ tok_pos, int LP, int P, uint32_t p_mask,
+                        const uint8_t* __restrict__ tok_ok, int tok_ok_ld, int tok_ok_col,
+                        const float* __restrict__ coef, const float* __restrict__ logit_scale, float beta,
+                        float* __restrict__ loss, float* __restrict__ g0, float* __restrict__ dscale,
+                        int32_t* __restrict__ rank0, int32_t* __restrict__ nvalid, TA* __restrict__ G, int64_t ldg) {
+  extern __shared__ __align__(16) float sm[];
+  float* z = sm;               // [n_neg]  scaled logits tau * cos
+  float* qrow = sm + n_neg;    // [D]
+  __shared__ Stats red_stats[NCE_THREADS / 32];
+  __shared__ float red[40];
+  __shared__ float s_pos[NCE_MAXP], s_coef[NCE_MAXP], s_c1[NCE_MAXP], s_c2[NCE_MAXP], s_ln1[NCE_MAXP], s_ln2[NCE_MAXP];
+  __shared__ int s_valid[NCE_MAXP], s_live[NCE_MAXP];
+  __shared__ int s_any;
+
+  const int t = blockIdx.x;
+  const int b = tok_b[t], pos = tok_pos[t];
+  const float tau = __expf(fminf(fmaxf(*logit_scale, 0.f), 4.605170185988092f));  // clamp(0, ln 100)
+  const int n_words = (n_neg + 31) >> 5;
+
+  if (threadIdx.x < NCE_MAXP) {
+    int p = threadIdx.x;
+    int ok = 0;
+    if (p < P && ((p_mask >> p) & 1u)) {
+      int64_t r = (int64_t)b * LP + pos + 1 + p;
+      ok = tok_ok[r * tok_ok_ld + tok_ok_col] != 0;
+    }
+    s_valid[p] = ok;
+    s_live[p] = 0;
+    s_coef[p] = (p < P) ? coef[p] : 0.f;
+  }
+  if (threadIdx.x == 0) s_any = 0;
+  __syncthreads();
+  if (threadIdx.x < P && s_valid[threadIdx.x]) s_any = 1;
+  __syncthreads();
+  if (!s_any) {  // no prediction offset uses this row
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+      loss[(int64_t)t * P + p] = 0.f;
+      g0[(int64_t)t * P + p] = 0.f;
+      dscale[(int64_t)t * P + p] = 0.f;
+      rank0[(int64_t)t * P + p] = -1;
+      nvalid[(int64_t)t * P + p] = 0;
+    }
+    if (G)
+      for (int j = threadIdx.x; j < n_neg; j += blockDim.x) G[(int64_t)t * ldg + j] = from_f32<TA>(0.f);
+    return;
+  }
+
+  for (int d = threadIdx.x; d < D; d += blockDim.x) qrow[d] = to_f32(q_hat[(int64_t)t * ldq + d]);
+  for (int j = threadIdx.x; j < n_neg; j += blockDim.x) z[j] = tau * logits[(int64_t)t * ld_logits + j];
+  __syncthreads();
+
+  for (int p = 0; p < P; ++p) {  // positive logits
+    if (!s_valid[p]) continue;
+    int64_t r = (int64_t)b * LP + pos + 1 + p;
+    float acc = 0.f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) acc += qrow[d] * to_f32(t_hat[r * D + d]);
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) s_pos[p] = tau * acc;
+    __syncthreads();
+  }
+
+  const float b1 = beta + 1.f;
+  for (int p = 0; p < P; ++p) {
+    if (!s_valid[p]) {
+      if (threadIdx.x == 0) {
+        loss[(int64_t)t * P + p] = 0.f;
+        g0[(int64_t)t * P + p] = 0.f;
+        dscale[(int64_t)t * P + p] = 0.f;
+        rank0[(int64_t)t * P + p] = -1;
+        nvalid[(int64_t)t * P + p] = 0;
+      }
+      continue;
+    }
+    const uint32_t* bits = same_bits + ((int64_t)b * LP + pos + 1 + p) * n_words;
+    const float zp = s_pos[p];
+    float m = -INFINITY;
+    for (int j = threadIdx.x; j < n_neg; j += blockDim.x)
+      if (!((bits[j >> 5] >> (j & 31)) & 1u)) m = fmaxf(m, z[j]);
+    Stats l1, l2;                      // temperature (beta + 1) and beta; w accumulates e * z
+    l1.m = b1 * m; l1.s = 0.f; l1.w = 0.f; l1.gt = 0; l1.cnt = 0;      // -inf stays -inf (beta > 0)
+    l2.m = beta * m; l2.s = 0.f; l2.w = 0.f; l2.gt = 0; l2.cnt = 0;
+    for (int j = threadIdx.x; j < n_neg; j += blockDim.x)
+      if (!((bits[j >> 5] >> (j & 31)) & 1u)) {
+        const float d = z[j] - m;
+        const float e1 = expf(b1 * d), e2 = expf(beta * d);
+        l1.s += e1;
+        l1.w += e1 * z[j];
+        l1.gt += z[j] > zp;
+        l1.cnt += 1;
+        l2.s += e2;
+        l2.w += e2 * z[j];
+      }
+    const Stats st1 = block_stats(l1, red_stats);
+    const Stats st2 = block_stats(l2, red_stats);
+    const float c = s_coef[p];
+    float lossv = 0.f, g0v = 0.f, dsv = 0.f, c1 = 0.f, c2 = 0.f, ln1 = 0.f, ln2 = 0.f;
+    int live = 0;
+    if (st1.cnt > 0) {                 // no kept negative: log_neg = -inf, the loss and every gradient are 0
+      ln1 = st1.m + logf(st1.s);
+      ln2 = st2.m + logf(st2.s);
+      const float log_neg = ln1 - ln2 + logf((float)n_neg);
+      const float M = fmaxf(zp, log_neg);
+      const float lse = M + logf(expf(zp - M) + expf(log_neg - M));
+      const float sig = expf(log_neg - lse);
+      lossv = c * (lse - zp);
+      g0v = -c * sig;
+      dsv = c * sig * (b1 * st1.w / st1.s - beta * st2.w / st2.s - zp);
+      c1 = c * sig * b1;
+      c2 = c * sig * beta;
+      live = 1;
+    }
+    if (threadIdx.x == 0) {
+      loss[(int64_t)t * P + p] = lossv;
+      g0[(int64_t)t * P + p] = g0v;
+      dscale[(int64_t)t * P + p] = dsv;
+      rank0[(int64_t)t * P + p] = st1.gt;
+      nvalid[(int64_t)t * P + p] = st1.cnt + 1;
+      s_c1[p] = c1; s_c2[p] = c2; s_ln1[p] = ln1; s_ln2[p] = ln2;
+      s_live[p] = live;
+    }
+  }
+  if (G == nullptr) return;
+  __syncthreads();
+  // gradient w.r.t. the cosine logits:  G[j] = tau * sum_p coef_p sigma_p ((beta + 1) p1_p[j] - beta p2_p[j])
+  for (int j = threadIdx.x; j < n_neg; j += blockDim.x) {
+    float g = 0.f;
+    for (int p = 0; p < P; ++p) {
+      if (s_live[p]) {
+        const uint32_t* bits = same_bits + ((int64_t)b * LP + pos + 1 + p) * n_words;
+        if (!((bits[j >> 5] >> (j & 31)) & 1u))
+          g += s_c1[p] * expf(b1 * z[j] - s_ln1[p]) - s_c2[p] * expf(beta * z[j] - s_ln2[p]);
+      }
+    }
+    G[(int64_t)t * ldg + j] = from_f32<TA>(tau * g);
+  }
+}
+
+extern "C" int b200rec_nce_ihn_loss_fwd(const float* logits, int64_t ld_logits, int n_neg, const uint32_t* same_bits,
+                             const void* q_hat, int64_t ldq, const void* t_hat, int act_dtype, int D,
+                             const int32_t* tok_b, const int32_t* tok_pos, int T, int LP, int P, uint32_t p_mask,
+                             const uint8_t* tok_ok, int tok_ok_ld, int tok_ok_col, const float* coef,
+                             const float* logit_scale, float beta, float* loss, float* g0, float* dscale,
+                             int32_t* rank0, int32_t* nvalid, void* G, int64_t ldg, void* stream) {
+  B200_CHECK_ARG(P >= 1 && P <= NCE_MAXP, "nce_ihn_loss_fwd: pred_len %d not in [1,%d]", P, NCE_MAXP);
+  B200_CHECK_ARG(beta > 0.f && n_neg >= 1, "nce_ihn_loss_fwd: beta %f must be > 0 (beta <= 0 is b200rec_nce_loss_fwd)", beta);
+  if (T == 0) return 0;
+  size_t smem = (size_t)(n_neg + D) * sizeof(float);
+  B200_CHECK_ARG(smem <= 200 * 1024, "nce_ihn_loss_fwd: n_neg=%d too large for the shared-memory row cache", n_neg);
+  DISPATCH_ACT(act_dtype, TA, {
+    {
+      static size_t smem_set = 0;      // raised outside any capture by the eager warm-up of a graphed step
+      if (smem > smem_set) {
+        B200_CUDA_OK(cudaFuncSetAttribute(nce_ihn_loss_fwd_kernel<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+      }
+    }
+    nce_ihn_loss_fwd_kernel<TA><<<T, NCE_THREADS, smem, (cudaStream_t)stream>>>(
+        logits, ld_logits, n_neg, same_bits, (const TA*)q_hat, ldq, (const TA*)t_hat, D, tok_b, tok_pos, LP, P,
+        p_mask, tok_ok, tok_ok_ld, tok_ok_col, coef, logit_scale, beta, loss, g0, dscale, rank0, nvalid, (TA*)G, ldg);
+  });
+  B200_LAUNCH_OK();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------ counts / coefs
 __global__ void nce_count_kernel(const int32_t* __restrict__ tok_b, const int32_t* __restrict__ tok_pos, int T,
                                  int LP, int P, const uint8_t* __restrict__ tok_ok, int tok_ok_ld, int tok_ok_col,

@@ -975,7 +975,8 @@ class HSTU(nn.Module):
         comi = None
         if self._readout is not None:
             # ComiRec (comirec.py): the queries are interests pooled over the causal context, one per offset
-            hd, comi = self._readout.train_forward(self, y, W, items, tok_b, tok_pos, seq_off, B, LP, T)
+            hd, comi = self._readout.train_forward(self, y, W, items, tok_b, tok_pos, seq_off, B, LP, T,
+                                                   B_real=B - (1 if static else 0), need_grad=need_grad)
             z = yb = None
         else:
             hd, z, yb = self._heads_forward(y, w, T)
@@ -1058,7 +1059,8 @@ class HSTU(nn.Module):
         job_out = []
         qv = qhat.view(T, Hx * D)
         hqs = [j.head if (self.medusa_num_layers > 0 or self._readout is not None) else 0 for j in self._jobs]
-        fused = act == torch.bfloat16 and self.use_fused_nce and D % 4 == 0 and D <= 2048
+        ihn_beta = float(getattr(self, "_ihn_beta", 0.0))      # comirec.REMI: interest-aware hard negatives (remi.py:198-277)
+        fused = act == torch.bfloat16 and self.use_fused_nce and D % 4 == 0 and D <= 2048 and ihn_beta <= 0
         if fused:
             # fused path: no fp32 [T, Nneg] logits in HBM.  positives + row reference -> ONE grouped
             # GEMM whose epilogue writes bf16 softmax numerators E and per-row partial sums -> combine (loss, scalars,
@@ -1116,12 +1118,19 @@ class HSTU(nn.Module):
                 rank0 = torch.empty((T, P), dtype=torch.int32, device=dev)
                 nval = torch.empty((T, P), dtype=torch.int32, device=dev)
                 G = torch.empty((T, ld_neg), dtype=act, device=dev) if need_grad else None
-                L.call("b200rec_nce_loss_fwd", logits.data_ptr(), ld_neg, n_neg, bits[j.nset].data_ptr(),
-                       row_any[j.nset].data_ptr(), pos_ws.data_ptr(), q_h.data_ptr(),
-                       Hx * D, that.data_ptr(), a_dt, D, tok_b.data_ptr(), tok_pos.data_ptr(), T, LP, P, j.p_mask,
-                       tok_ok.data_ptr(), n_col, j.col, coefs[(j.col, j.w)].data_ptr(), scale.data_ptr(),
-                       lossv.data_ptr(), g0.data_ptr(), dsc.data_ptr(), rank0.data_ptr(), nval.data_ptr(), L.ptr(G),
-                       ld_neg, st)
+                if ihn_beta > 0:
+                    L.call("b200rec_nce_ihn_loss_fwd", logits.data_ptr(), ld_neg, n_neg, bits[j.nset].data_ptr(),
+                           q_h.data_ptr(), Hx * D, that.data_ptr(), a_dt, D, tok_b.data_ptr(), tok_pos.data_ptr(), T, LP, P,
+                           j.p_mask, tok_ok.data_ptr(), n_col, j.col, coefs[(j.col, j.w)].data_ptr(), scale.data_ptr(),
+                           ihn_beta, lossv.data_ptr(), g0.data_ptr(), dsc.data_ptr(), rank0.data_ptr(), nval.data_ptr(),
+                           L.ptr(G), ld_neg, st)
+                else:
+                    L.call("b200rec_nce_loss_fwd", logits.data_ptr(), ld_neg, n_neg, bits[j.nset].data_ptr(),
+                           row_any[j.nset].data_ptr(), pos_ws.data_ptr(), q_h.data_ptr(),
+                           Hx * D, that.data_ptr(), a_dt, D, tok_b.data_ptr(), tok_pos.data_ptr(), T, LP, P, j.p_mask,
+                           tok_ok.data_ptr(), n_col, j.col, coefs[(j.col, j.w)].data_ptr(), scale.data_ptr(),
+                           lossv.data_ptr(), g0.data_ptr(), dsc.data_ptr(), rank0.data_ptr(), nval.data_ptr(), L.ptr(G),
+                           ld_neg, st)
                 per_p = torch.empty(P, dtype=torch.float32, device=dev)
                 L.colsum(lossv, T, P, P, per_p)
                 job_out.append(dict(job=j, per_p=per_p, g0=g0, dsc=dsc, rank0=rank0, nval=nval, G=G, hq=hq,
@@ -1170,6 +1179,9 @@ class HSTU(nn.Module):
             sw = self._switch_forward(y, tok_index, items, W, tags, B - (1 if static else 0), LP, need_grad)
             total = total + sw["loss"]
             logs.update(sw["logs"])
+        if comi is not None and comi.get("rr") is not None:          # REMI routing regulariser (remi.py:356-372)
+            total = total + comi["rr"] * float(self.lambda_rr)
+            logs["rr_loss"] = comi["rr"].detach()
         loss = total * half
         if self._debug is not None:
             self._debug.update(x0=x.clone(), y=y.clone(), hd=hd.clone(), qhat=qhat.clone(), that=that.clone(),
@@ -1263,6 +1275,7 @@ class HSTU(nn.Module):
                d_hd.data_ptr(), 0, st)
         dy = torch.empty((T, D), dtype=torch.float32, device=dev)
         if self._readout is not None:
+            ctx["gscale"] = gscale
             dy = self._readout.train_backward(self, d_hd, ctx, grads)
         elif self.medusa_num_layers > 0 and self.head_interaction == "hierarchical":
             dy = self._hier_backward(d_hd, ctx["hier_tape"], ctx["y"], grads)

@@ -109,7 +109,7 @@ def ihn_token_loss(q, t, negs, tau, thres, beta):
     logits = torch.cat([pos, neg], dim=-1)
     n_all = neg.shape[1]
     log_num = torch.logsumexp((beta + 1.0) * neg, dim=1, keepdim=True)                              # :251-252
-    log_z = torch.logsumexp(beta * neg, dim=1, keepdim=True) - torch.log(torch.tensor(float(n_all)))  # :255-257
+    log_z = torch.logsumexp(beta * neg, dim=1, keepdim=True) - torch.log(torch.tensor(float(n_all), dtype=neg.dtype))  # :247-257
     log_neg = torch.where(torch.isfinite(log_z), log_num - log_z, torch.full_like(log_num, float("-inf")))   # :261-264
     loss = (torch.logaddexp(pos, log_neg) - pos).squeeze(-1)                                        # :268-271
     return loss, logits
