@@ -81,7 +81,7 @@ def test_train_step_bf16_within_tolerance():
         g, r = p.grad.cpu().flatten().double(), g_ref.flatten().double()
         worst[k] = float((g @ r) / (g.norm() * r.norm() + 1e-30))
     print("REMI bf16 gradient cosines (min 5):", sorted(worst.items(), key=lambda kv: kv[1])[:5])
-    bad = {k: c for k, c in worst.items() if c <= 0.95}
+    bad = {k: c for k, c in worst.items() if c <= 0.99}                 # measured on B200: >= 0.99995
     assert not bad, bad
 
 
