@@ -43,6 +43,17 @@ def cosine_schedule_with_warmup(step, warmup_steps, total_steps, num_cycles=0.5)
 SCHEDULES = {"cosine": cosine_schedule_with_warmup, "linear": linear_schedule_with_warmup}
 
 
+def get_model(model_name):
+    """REC/utils/utils.py:38-57: module `<model_name.lower()>` of the package, attribute `<model_name>` (HSTU, ComiRec,
+    REMI); the same ValueError for a name without a module."""
+    import importlib
+    import importlib.util
+    module_path = f"{__package__}.{model_name.lower()}"
+    if importlib.util.find_spec(module_path) is None:
+        raise ValueError("`model_name` [{}] is not the name of an existing model.".format(model_name))
+    return getattr(importlib.import_module(module_path), model_name)
+
+
 def early_stopping(value, best, cur_step, max_step, bigger=True):
     """utils/utils.py:60-101 -> (best, cur_step, stop_flag, update_flag)."""
     stop_flag = update_flag = False

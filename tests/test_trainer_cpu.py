@@ -89,3 +89,14 @@ def test_interaction_data_host_layout():
     assert list(zip(d3.h_sample_uid.tolist(), d3.h_sample_end.tolist())) == [w for w in want if w[1] > 0]
     d2 = InteractionData(user_seq, train_len, 14, L, device="cpu", sample_last_only=True, pred_len=2)
     assert list(zip(d2.h_sample_uid.tolist(), d2.h_sample_end.tolist())) == [(1, 1), (2, 3), (3, 9), (4, 11)]
+
+
+def test_get_model_resolves_like_the_reference():
+    """REC/utils/utils.py:38-57: module <name.lower()>, attribute <name>; unknown names raise ValueError."""
+    import pytest
+    from b200rec.trainer import get_model
+    from b200rec.hstu import HSTU
+    from b200rec.comirec import ComiRec, REMI
+    assert get_model("HSTU") is HSTU and get_model("ComiRec") is ComiRec and get_model("REMI") is REMI
+    with pytest.raises(ValueError):
+        get_model("SASRec")
